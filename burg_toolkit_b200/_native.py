@@ -1,0 +1,125 @@
+"""ctypes binding of libburgb200.so (include/burg_b200.h).
+
+The shared library is the product: if it is missing, or a call fails, this module raises -- there is
+no CPU fallback anywhere in the package.  Device memory and streams come from torch (plumbing); only raw
+pointers cross the C ABI.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libburgb200.so')
+
+BT_HIT_ORIGIN, BT_HIT_WIDTH, BT_HIT_SIGN, BT_HIT_CONE, BT_HIT_BELOW_Z = 1, 2, 4, 8, 16
+
+# numpy view of struct bt_hit (72 bytes)
+HIT_DTYPE = np.dtype([('loc', '<f8', (3,)), ('nrm', '<f8', (3,)), ('t', '<f8'), ('angle', '<f8'),
+                      ('tri', '<i4'), ('flags', '<u4')])
+assert HIT_DTYPE.itemsize == 72
+
+
+class AgsParams(C.Structure):
+    _fields_ = [('angle_max', C.c_double), ('opening_width', C.c_double), ('width_tolerance', C.c_double),
+                ('min_grasp_width', C.c_double), ('no_contact_below_z', C.c_double),
+                ('use_below_z', C.c_int32), ('max_hits_per_ray', C.c_int32)]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [('n_vertices', C.c_int64), ('n_triangles', C.c_int64), ('n_nodes', C.c_int64),
+                ('device_bytes', C.c_int64), ('surface_area', C.c_double), ('build_ms', C.c_double),
+                ('bounds_min', C.c_float * 3), ('bounds_max', C.c_float * 3), ('device', C.c_int32),
+                ('max_depth', C.c_int32)]
+
+
+class GripperPart(C.Structure):
+    _fields_ = [('box_min', C.c_double * 3), ('box_max', C.c_double * 3), ('tri_begin', C.c_int32),
+                ('tri_end', C.c_int32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    'bt_version': (C.c_int, []),
+    'bt_last_error': (C.c_char_p, []),
+    'bt_device_info': (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    'bt_malloc': (C.c_int, [C.c_int, C.c_int64, C.POINTER(_P)]),
+    'bt_free': (C.c_int, [_P]),
+    'bt_memcpy_h2d': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'bt_memcpy_d2h': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'bt_stream_sync': (C.c_int, [_P]),
+    'bt_mesh_create': (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int, C.POINTER(_P)]),
+    'bt_mesh_destroy': (C.c_int, [_P]),
+    'bt_mesh_get_info': (C.c_int, [_P, C.POINTER(MeshInfo)]),
+    'bt_mesh_copy_bvh': (C.c_int, [_P, _P, _P]),
+    'bt_sample_surface': (C.c_int, [_P, C.c_int64, C.c_uint64, _P, _P, _P, _P]),
+    'bt_cone_rays': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_uint64, _P, _P]),
+    'bt_random_unit_vectors': (C.c_int, [C.c_int64, C.c_uint64, _P, _P]),
+    'bt_ags_cast': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(AgsParams), _P, _P, _P, _P]),
+    'bt_ags_select': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P, _P, _P, _P,
+                                C.c_int64, _P]),
+    'bt_expand_orientations': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P,
+                                         _P, _P, _P]),
+    'bt_gripper_create': (C.c_int, [_P, C.c_int32, C.POINTER(GripperPart), C.c_int32, C.c_int, C.POINTER(_P)]),
+    'bt_gripper_destroy': (C.c_int, [_P]),
+    'bt_collide': (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P, _P]),
+    'bt_compact': (C.c_int, [_P, C.c_uint8, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    'bt_coverage': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    'bt_pairwise_distances': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """dlopen the library (once).  Raises NativeError with a build hint if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(f'{LIB_PATH} not found -- build it with `python burg_toolkit_b200/csrc/build.py` '
+                          f'(nvcc, sm_100a). burg_toolkit_b200 has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().bt_last_error()
+        raise NativeError(f'libburgb200 error {rc}: {msg.decode() if msg else "?"}')
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError('no CUDA device visible: burg_toolkit_b200 runs on B200 (sm_100a) only, '
+                          'there is no CPU fallback')
+    return torch
+
+
+def ptr(t):
+    """raw device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

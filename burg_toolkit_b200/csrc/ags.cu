@@ -1,0 +1,579 @@
+// ags.cu -- antipodal grasp sampling kernels: surface samples (S1), cone rays (S2), the friction-cone
+// ray caster with the antipodal filters (R1-R6), target selection (R7) and orientation expansion (O1/O2).
+//
+// Reference being replaced: burg_toolkit/sampling.py:185-352 (AntipodalGraspSampler.sample hot loop) and the
+// leaves it calls (trimesh ray_triangle_id, mesh_processing.compute_interpolated_vertex_normals :110-153,
+// util.angle :46-82, construct_grasp_set :132-183, construct_halfspace_grasp_set :72-130).
+//
+// Precision contract: the broad phase (LBVH, float32 slabs over padded boxes) only proposes candidates; every
+// accept/reject decision is taken in float64 with the reference's formulas, operation order and tolerances.
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace bt {
+
+constexpr int STACK_SIZE = 64;
+constexpr float T_BEHIND = -1e-5f;        // boxes wholly behind the origin by more than this cannot hold a
+                                          // hit that passes the reference's forward test (> -1e-6)
+
+struct MeshView {
+    const float4* __restrict__ nodes;
+    const double* __restrict__ tri_rec;
+    const int32_t* __restrict__ leaf_tri;
+    const int32_t* __restrict__ faces;
+    const double* __restrict__ verts;
+    const double* __restrict__ vnormals;
+};
+
+__device__ __forceinline__ bool slab_hit(float bx0, float by0, float bz0, float bx1, float by1, float bz1,
+                                         float idx, float idy, float idz, float oox, float ooy, float ooz) {
+    float tx0 = fmaf(bx0, idx, -oox), tx1 = fmaf(bx1, idx, -oox);
+    float ty0 = fmaf(by0, idy, -ooy), ty1 = fmaf(by1, idy, -ooy);
+    float tz0 = fmaf(bz0, idz, -ooz), tz1 = fmaf(bz1, idz, -ooz);
+    float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
+    float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    return (tnear <= tfar) & (tfar >= T_BEHIND);
+}
+
+__device__ __forceinline__ float safe_rcp(float d) {
+    return 1.0f / (fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d);
+}
+
+// trimesh ray_triangle_id narrow phase for one (ray, triangle record); returns true and t if it is a hit
+__device__ __forceinline__ bool exact_ray_triangle(const double* __restrict__ rec, d3 o, d3 d, double& t_out) {
+    const double2* r2 = reinterpret_cast<const double2*>(rec);
+    double2 a = __ldg(r2 + 0), b = __ldg(r2 + 1), c = __ldg(r2 + 2);
+    d3 v0 = mk3(a.x, a.y, b.x), n = mk3(b.y, c.x, c.y);
+    // intersections.planes_lines
+    double proj_ori = dot3(sub3(v0, o), n);
+    double proj_dir = dot3(d, n);
+    if (!(fabs(proj_dir) > 1e-5)) return false;
+    double t = proj_ori / proj_dir;
+    d3 p = add3(scl3(d, t), o);
+    // forward test: dot(location - origin, direction) > -1e-6
+    if (!(dot3(sub3(p, o), d) > -1e-6)) return false;
+    // triangles.points_to_barycentric(method='cramer')
+    double2 e = __ldg(r2 + 3), f = __ldg(r2 + 4), g = __ldg(r2 + 5), h = __ldg(r2 + 6), k = __ldg(r2 + 7);
+    d3 e0 = mk3(e.x, e.y, f.x), e1 = mk3(f.y, g.x, g.y);
+    double d00 = h.x, d01 = h.y, d11 = k.x, inv = k.y;
+    d3 w = sub3(p, v0);
+    double d02 = dot3(e0, w), d12 = dot3(e1, w);
+    double b2 = (d00 * d12 - d01 * d02) * inv;
+    double b1 = (d11 * d02 - d01 * d12) * inv;
+    double b0 = 1.0 - b1 - b2;
+    const double lo = -1e-13, hi = 1.0 + 1e-13;
+    bool hit = (b0 > lo) & (b1 > lo) & (b2 > lo) & (b0 < hi) & (b1 < hi) & (b2 < hi);
+    t_out = t;
+    return hit;
+}
+
+// mesh_processing.compute_interpolated_vertex_normals for one point on triangle `tri`
+__device__ __forceinline__ d3 interpolated_normal(const MeshView& mv, int32_t tri, d3 p) {
+    const int32_t* fc = mv.faces + 3 * (int64_t)tri;
+    double w[3];
+    d3 vn[3];
+    int onehot = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int64_t v = fc[k];
+        d3 vert = ld3(mv.verts + 3 * v);
+        vn[k] = ld3(mv.vnormals + 3 * v);
+        double dist = norm3(sub3(vert, p));
+        w[k] = 1.0 / sqrt(dist);
+        if (dist == 0.0) onehot = k;             // later vertices win, like the reference's loop
+    }
+    if (onehot >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = (k == onehot) ? 1.0 : 0.0;
+    }
+    d3 s = mk3(((w[0] * vn[0].x + w[1] * vn[1].x) + w[2] * vn[2].x) / 3.0,
+               ((w[0] * vn[0].y + w[1] * vn[1].y) + w[2] * vn[2].y) / 3.0,
+               ((w[0] * vn[0].z + w[1] * vn[1].z) + w[2] * vn[2].z) / 3.0);
+    return div3(s, norm3(s));
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(128)
+cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
+            int n_rays, bt_ags_params P, int cap, int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits,
+            int32_t* __restrict__ overflow) {
+    int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (ray >= n_total) return;
+    const int64_t ref = ray / n_rays;
+    const d3 o = ld3(ref_pts + 3 * ref);
+    const d3 d = ld3(dirs + 3 * ray);
+    const float idx = safe_rcp((float)d.x), idy = safe_rcp((float)d.y), idz = safe_rcp((float)d.z);
+    const float oox = (float)o.x * idx, ooy = (float)o.y * idy, ooz = (float)o.z * idz;
+
+    double hit_t[CAP];
+    int32_t hit_tri[CAP];
+    int n_hit = 0;
+    bool over = false;
+
+    int stack[STACK_SIZE];
+    int sp = 0;
+    int cur = 0;
+    while (true) {
+        if (cur < 0) {
+            const int leaf = ~cur;
+            double t;
+            if (exact_ray_triangle(mv.tri_rec + 16 * (int64_t)leaf, o, d, t)) {
+                if (n_hit < cap) { hit_t[n_hit] = t; hit_tri[n_hit] = __ldg(mv.leaf_tri + leaf); ++n_hit; }
+                else over = true;
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        const float4 q0 = __ldg(mv.nodes + 4 * (int64_t)cur + 0);
+        const float4 q1 = __ldg(mv.nodes + 4 * (int64_t)cur + 1);
+        const float4 q2 = __ldg(mv.nodes + 4 * (int64_t)cur + 2);
+        const float4 q3 = __ldg(mv.nodes + 4 * (int64_t)cur + 3);
+        const bool hl = slab_hit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, idx, idy, idz, oox, ooy, ooz);
+        const bool hr = slab_hit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, idx, idy, idz, oox, ooy, ooz);
+        const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
+        if (hl && hr) { stack[sp++] = r; cur = l; }
+        else if (hl) cur = l;
+        else if (hr) cur = r;
+        else { if (sp == 0) break; cur = stack[--sp]; }
+    }
+
+    // canonical order: (t, triangle id) ascending
+    for (int i = 1; i < n_hit; ++i) {
+        double t = hit_t[i];
+        int32_t tr = hit_tri[i];
+        int j = i - 1;
+        while (j >= 0 && (hit_t[j] > t || (hit_t[j] == t && hit_tri[j] > tr))) {
+            hit_t[j + 1] = hit_t[j]; hit_tri[j + 1] = hit_tri[j]; --j;
+        }
+        hit_t[j + 1] = t; hit_tri[j + 1] = tr;
+    }
+
+    bt_hit* out = hits + ray * (int64_t)cap;
+    int n_out = 0;
+    for (int i = 0; i < n_hit; ++i) {
+        const double t = hit_t[i];
+        const d3 p = add3(scl3(d, t), o);
+        // trimesh intersects_id(return_locations=True): unique rows of (location, ray) at 1e-8
+        const double kx = rint(p.x * 1e8 - 1e-6), ky = rint(p.y * 1e8 - 1e-6), kz = rint(p.z * 1e8 - 1e-6);
+        bool dup = false;
+        for (int j = 0; j < n_out; ++j) {
+            const double* q = out[j].loc;
+            if (rint(q[0] * 1e8 - 1e-6) == kx && rint(q[1] * 1e8 - 1e-6) == ky && rint(q[2] * 1e8 - 1e-6) == kz) { dup = true; break; }
+        }
+        if (dup) continue;
+        const int32_t tri = hit_tri[i];
+        uint32_t flags = 0;
+        // sampling.py:239  ~np.isclose(loc, p_r, atol=1e-11).all(-1)   (rtol = 1e-5 relative to p_r)
+        const bool close = (fabs(p.x - o.x) <= 1e-11 + 1e-5 * fabs(o.x)) & (fabs(p.y - o.y) <= 1e-11 + 1e-5 * fabs(o.y)) &
+                           (fabs(p.z - o.z) <= 1e-11 + 1e-5 * fabs(o.z));
+        if (close) flags |= BT_HIT_ORIGIN;
+        // sampling.py:248-251
+        const d3 dv = sub3(p, o);
+        const double dist = norm3(dv);
+        if (!((dist <= P.opening_width - P.width_tolerance) | (dist >= P.min_grasp_width))) flags |= BT_HIT_WIDTH;
+        // sampling.py:259, :289-308
+        const d3 nrm = interpolated_normal(mv, tri, p);
+        const double dotp = dot3(dv, nrm);
+        const double ang = atan(norm3(cross3(dv, nrm)) / dotp);
+        if (!(dotp > 0.0)) flags |= BT_HIT_SIGN;
+        if (!(ang <= P.angle_max)) flags |= BT_HIT_CONE;
+        if (P.use_below_z && !(p.z > P.no_contact_below_z)) flags |= BT_HIT_BELOW_Z;
+        bt_hit h;
+        h.loc[0] = p.x; h.loc[1] = p.y; h.loc[2] = p.z;
+        h.nrm[0] = nrm.x; h.nrm[1] = nrm.y; h.nrm[2] = nrm.z;
+        h.t = t; h.angle = ang; h.tri = tri; h.flags = flags;
+        out[n_out++] = h;
+    }
+    hit_count[ray] = n_out;
+    if (over && overflow) atomicAdd(overflow, 1);
+}
+
+// ---- S1 ------------------------------------------------------------------------------------------------
+__global__ void sample_surface_kernel(const double* __restrict__ cdf, const int32_t* __restrict__ faces,
+                                      const double* __restrict__ verts, int64_t nF, int64_t n, uint64_t seed,
+                                      double* __restrict__ pts, double* __restrict__ nrm, int32_t* __restrict__ tri_out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // open3d SamplePointsUniformlyImpl: triangle f owns sample slots [round(cdf[f-1]*n), round(cdf[f]*n))
+    int64_t lo = 0, hi = nF - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)llrint(cdf[mid] * (double)n) > i) hi = mid; else lo = mid + 1;
+    }
+    const int32_t f = (int32_t)lo;
+    uint32_t r[4];
+    philox4x32(seed, (uint64_t)i, 0x53414d50ull, r);
+    const double r1 = u01(r[0], r[1]), r2 = u01(r[2], r[3]);
+    const double s = sqrt(r1);
+    const double a = 1.0 - s, b = s * (1.0 - r2), c = s * r2;
+    const int32_t* fc = faces + 3 * (int64_t)f;
+    d3 v0 = ld3(verts + 3 * (int64_t)fc[0]), v1 = ld3(verts + 3 * (int64_t)fc[1]), v2 = ld3(verts + 3 * (int64_t)fc[2]);
+    d3 p = add3(add3(scl3(v0, a), scl3(v1, b)), scl3(v2, c));
+    d3 cr = cross3(sub3(v1, v0), sub3(v2, v0));
+    double nn = norm3(cr);
+    d3 nv = nn > 0 ? div3(cr, nn) : mk3(0, 0, 1);
+    st3(pts + 3 * i, p);
+    st3(nrm + 3 * i, nv);
+    if (tri_out) tri_out[i] = f;
+}
+
+// ---- S2 ------------------------------------------------------------------------------------------------
+__global__ void cone_rays_kernel(const double* __restrict__ normals, int64_t n_ref, int n_rays, double angle,
+                                 uint64_t seed, double* __restrict__ dirs) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_ref * n_rays) return;
+    const int64_t ref = i / n_rays;
+    uint32_t r[4];
+    philox4x32(seed, (uint64_t)i, 0x434f4e45ull, r);
+    const double az = u01(r[0], r[1]) * (2.0 * 3.14159265358979323846);      // U(0, 2 pi)   sampling.py:32
+    const double inc = u01(r[2], r[3]) * angle;                               // U(0, angle)  sampling.py:36
+    double si, ci, sa, ca;
+    sincos(inc, &si, &ci);
+    sincos(az, &sa, &ca);
+    const d3 c = mk3(si * ca, si * sa, ci);
+    // util.rotation_to_align_vectors([0,0,1], axis): R = 2 k k^T / (k^T k) - I,  k = z + axis/|axis|
+    d3 axis = ld3(normals + 3 * ref);
+    axis = mk3(-axis.x, -axis.y, -axis.z);
+    const double an = norm3(axis);
+    d3 k = mk3(axis.x / an, axis.y / an, 1.0 + axis.z / an);
+    if (norm3(k) == 0.0) {                      // axis == -z exactly: half turn about any vector orthogonal to z
+        uint32_t q[4];
+        philox4x32(seed, (uint64_t)ref, 0x4f525448ull, q);
+        const double phi = u01(q[0], q[1]) * (2.0 * 3.14159265358979323846);
+        k = mk3(cos(phi), sin(phi), 0.0);
+    }
+    const double kk = dot3(k, k);
+    const double kc = dot3(k, c);
+    const double f = 2.0 * kc / kk;
+    st3(dirs + 3 * i, mk3(f * k.x - c.x, f * k.y - c.y, f * k.z - c.z));
+}
+
+__global__ void unit_vectors_kernel(int64_t n, uint64_t seed, double* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 v = mk3(0, 0, 1);
+    for (uint64_t attempt = 0; attempt < 8; ++attempt) {
+        uint32_t a[4], b[4];
+        philox4x32(seed, (uint64_t)i, 0x554e4954ull + (attempt << 32), a);
+        philox4x32(seed, (uint64_t)i, 0x554e4955ull + (attempt << 32), b);
+        // Box-Muller: three standard normals
+        const double u1 = 1.0 - u01(a[0], a[1]), u2 = u01(a[2], a[3]), u3 = 1.0 - u01(b[0], b[1]), u4 = u01(b[2], b[3]);
+        const double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
+        const double tp = 2.0 * 3.14159265358979323846;
+        d3 g = mk3(r1 * cos(tp * u2), r1 * sin(tp * u2), r2 * cos(tp * u4));
+        const double mag = norm3(g);
+        if (mag > 1e-5) { v = div3(g, mag); break; }
+    }
+    st3(out + 3 * i, v);
+}
+
+// ---- R7 ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t choice_key(uint64_t seed, int64_t ref, int ordinal) {
+    uint32_t r[4];
+    philox4x32(seed, (uint64_t)ref, 0x43484f49ull + ((uint64_t)ordinal << 32), r);
+    return (((uint64_t)r[0] << 32) | r[1]) >> 1;      // 63 bits, so that ~0 can be the 'none' sentinel
+}
+
+// one warp per reference point: number of valid hits, capped at max_targets
+__global__ void select_count_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits,
+                                    int64_t n_ref, int n_rays, int cap, int max_targets,
+                                    int32_t* __restrict__ pair_count) {
+    const int64_t ref = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ref >= n_ref) return;
+    int cnt = 0;
+    for (int r = lane; r < n_rays; r += 32) {
+        const int64_t ray = ref * n_rays + r;
+        const int c = hit_count[ray];
+        for (int h = 0; h < c; ++h) cnt += (hits[ray * cap + h].flags == 0u);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    if (lane == 0) pair_count[ref] = min(cnt, max_targets);
+}
+
+__global__ void zero_first_kernel(int64_t* p) { *p = 0; }
+
+__global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits,
+                                   int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
+                                   const int64_t* __restrict__ pair_offset, int64_t cap_pairs,
+                                   int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
+    const int64_t ref = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ref >= n_ref) return;
+    const int64_t base = pair_offset[ref];
+    const int n_take = (int)(pair_offset[ref + 1] - base);
+    if (n_take == 0) return;
+    // total number of valid hits (to know whether a random subset has to be drawn)
+    int total = 0;
+    for (int r = lane; r < n_rays; r += 32) {
+        const int64_t ray = ref * n_rays + r;
+        const int c = hit_count[ray];
+        for (int h = 0; h < c; ++h) total += (hits[ray * cap + h].flags == 0u);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
+    const bool random_subset = (seed != 0) && (total > max_targets);
+
+    if (!random_subset) {
+        // canonical order: ray ascending, then t ascending; ordinals via a warp scan per chunk of 32 rays
+        int run = 0;
+        for (int r0 = 0; r0 < n_rays; r0 += 32) {
+            const int r = r0 + lane;
+            int c = 0, nv = 0;
+            int64_t ray = ref * n_rays + r;
+            if (r < n_rays) {
+                c = hit_count[ray];
+                for (int h = 0; h < c; ++h) nv += (hits[ray * cap + h].flags == 0u);
+            }
+            int incl = nv;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, s);
+                if (lane >= s) incl += v;
+            }
+            int ord = run + incl - nv;
+            for (int h = 0; h < c; ++h) {
+                const bt_hit* hp = hits + ray * cap + h;
+                if (hp->flags == 0u) {
+                    if (ord < n_take && base + ord < cap_pairs) {
+                        pair_ref[base + ord] = (int32_t)ref;
+                        pair_q[3 * (base + ord) + 0] = hp->loc[0];
+                        pair_q[3 * (base + ord) + 1] = hp->loc[1];
+                        pair_q[3 * (base + ord) + 2] = hp->loc[2];
+                    }
+                    ++ord;
+                }
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        return;
+    }
+    // random subset without replacement: the n_take hits with the smallest Philox keys, in key order
+    uint64_t prev_key = 0;
+    int prev_ord = -1;
+    for (int pick = 0; pick < n_take; ++pick) {
+        uint64_t best_key = ~0ull;
+        int best_ord = 0x7fffffff, best_slot = -1;
+        int run = 0;
+        for (int r0 = 0; r0 < n_rays; r0 += 32) {
+            const int r = r0 + lane;
+            int c = 0, nv = 0;
+            int64_t ray = ref * n_rays + r;
+            if (r < n_rays) {
+                c = hit_count[ray];
+                for (int h = 0; h < c; ++h) nv += (hits[ray * cap + h].flags == 0u);
+            }
+            int incl = nv;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, s);
+                if (lane >= s) incl += v;
+            }
+            int ord = run + incl - nv;
+            for (int h = 0; h < c; ++h) {
+                if (hits[ray * cap + h].flags == 0u) {
+                    const uint64_t key = choice_key(seed, ref, ord);
+                    const bool after_prev = (prev_ord < 0) || key > prev_key || (key == prev_key && ord > prev_ord);
+                    const bool better = key < best_key || (key == best_key && ord < best_ord);
+                    if (after_prev && better) { best_key = key; best_ord = ord; best_slot = r * cap + h; }
+                    ++ord;
+                }
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const uint64_t ok = __shfl_xor_sync(0xffffffffu, best_key, s);
+            const int oo = __shfl_xor_sync(0xffffffffu, best_ord, s);
+            const int os = __shfl_xor_sync(0xffffffffu, best_slot, s);
+            if (ok < best_key || (ok == best_key && oo < best_ord)) { best_key = ok; best_ord = oo; best_slot = os; }
+        }
+        if (lane == 0 && best_slot >= 0 && base + pick < cap_pairs) {
+            const bt_hit* hp = hits + ref * n_rays * (int64_t)cap + best_slot;
+            pair_ref[base + pick] = (int32_t)ref;
+            pair_q[3 * (base + pick) + 0] = hp->loc[0];
+            pair_q[3 * (base + pick) + 1] = hp->loc[1];
+            pair_q[3 * (base + pick) + 2] = hp->loc[2];
+        }
+        prev_key = best_key;
+        prev_ord = best_ord;
+    }
+}
+
+// ---- O1 / O2 -------------------------------------------------------------------------------------------
+struct OrientTable { double c[64]; double s[64]; };
+
+__global__ void expand_kernel(const double* __restrict__ ref_pts, const int64_t* __restrict__ pair_offset,
+                              const int32_t* __restrict__ pair_ref, const double* __restrict__ pair_q,
+                              const double* __restrict__ frame_vecs, int64_t n_ref, int n_o, int halfspace,
+                              OrientTable tab, float* __restrict__ gs, double* __restrict__ contacts) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n_pairs = pair_offset[n_ref];
+    if (row >= n_pairs * n_o) return;
+    const int64_t slot = row / n_o;                   // target-major slot: owns width + contacts of this row
+    const int64_t ref = pair_ref[slot];
+    const int64_t base = pair_offset[ref];
+    const int64_t k = pair_offset[ref + 1] - base;
+    const int64_t r = row - base * n_o;               // row index inside the reference point's group
+    const d3 p_r = ld3(ref_pts + 3 * ref);
+    // width and contacts follow the target-major slot (sampling.py:181 / :128 and :341-344)
+    const d3 q_slot = ld3(pair_q + 3 * slot);
+    const double width = norm3(sub3(q_slot, p_r));
+    int64_t ti;           // which target's pose
+    int oi;               // which orientation
+    if (halfspace) { ti = r / n_o; oi = (int)(r % n_o); }      // sampling.py:117  index = i * n_o + j
+    else { oi = (int)(r / k); ti = r % k; }                    // sampling.py:177  orientation-major
+    const d3 q = ld3(pair_q + 3 * (base + ti));
+    const d3 dv = sub3(q, p_r);
+    const d3 centre = add3(p_r, scl3(dv, 0.5));
+    const double dist = norm3(dv);
+    d3 x = div3(dv, dist);
+    d3 y, z;
+    if (!halfspace) {
+        const d3 u = ld3(frame_vecs + 3 * ref);
+        d3 y0 = cross3(x, u);
+        y0 = div3(y0, norm3(y0));
+        d3 z0 = cross3(x, y0);
+        z0 = div3(z0, norm3(z0));
+        // tf_basis @ tf_rot (4x4 float64 matmul = ascending-k FMA chain; zero terms drop out exactly):
+        //   y = fma(z0, sin, y0*cos)     z = fma(z0, cos, y0*(-sin))
+        const double c = tab.c[oi], s = tab.s[oi];
+        y = mk3(fma(z0.x, s, y0.x * c), fma(z0.y, s, y0.y * c), fma(z0.z, s, y0.z * c));
+        z = mk3(fma(z0.x, c, y0.x * (-s)), fma(z0.y, c, y0.y * (-s)), fma(z0.z, c, y0.z * (-s)));
+    } else {
+        if (x.z < 0) x = mk3(-x.x, -x.y, -x.z);
+        // y_tangent = -cross(x, [0,0,1]) normalised
+        d3 yt = mk3(-(x.y * 1.0 - x.z * 0.0), -(x.z * 0.0 - x.x * 1.0), -(x.x * 0.0 - x.y * 0.0));
+        yt = div3(yt, norm3(yt));
+        // Rodrigues rotation of y_tangent about x by theta
+        const double c = tab.c[oi], s = tab.s[oi];
+        const d3 xc = cross3(x, yt);
+        const double xd = dot3(x, yt) * (1.0 - c);
+        z = mk3(yt.x * c + xc.x * s + x.x * xd, yt.y * c + xc.y * s + x.y * xd, yt.z * c + xc.z * s + x.z * xd);
+        y = cross3(z, x);
+        y = div3(y, norm3(y));
+    }
+    float* g = gs + 14 * row;
+    g[0] = (float)centre.x; g[1] = (float)centre.y; g[2] = (float)centre.z;
+    g[3] = (float)x.x; g[4] = (float)y.x; g[5] = (float)z.x;
+    g[6] = (float)x.y; g[7] = (float)y.y; g[8] = (float)z.y;
+    g[9] = (float)x.z; g[10] = (float)y.z; g[11] = (float)z.z;
+    g[12] = 0.0f;
+    g[13] = (float)width;
+    if (contacts) {
+        double* c = contacts + 6 * row;
+        st3(c, p_r);
+        st3(c + 3, q_slot);
+    }
+}
+
+static MeshView view_of(const MeshDev& m) {
+    MeshView v;
+    v.nodes = m.nodes; v.tri_rec = m.tri_rec; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
+    v.vnormals = m.vnormals;
+    return v;
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+extern "C" int bt_sample_surface(const bt_mesh* mesh, int64_t n, uint64_t seed, double* d_pts, double* d_nrm,
+                                 int32_t* d_tri, void* stream) {
+    BT_REQUIRE(mesh && d_pts && d_nrm, "null pointer");
+    BT_REQUIRE(n >= 0, "negative count");
+    if (n == 0) return BT_OK;
+    BT_CUDA(cudaSetDevice(mesh->m.device));
+    sample_surface_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        mesh->m.area_cdf, mesh->m.faces, mesh->m.verts, mesh->m.nF, n, seed, d_pts, d_nrm, d_tri);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_cone_rays(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed,
+                            double* d_dirs, void* stream) {
+    BT_REQUIRE(d_normals && d_dirs, "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
+    if (n_ref == 0) return BT_OK;
+    cone_rays_kernel<<<(unsigned)ceil_div(n_ref * n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_normals, n_ref, n_rays, angle, seed, d_dirs);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, void* stream) {
+    BT_REQUIRE(d_out && n >= 0, "bad arguments");
+    if (n == 0) return BT_OK;
+    unit_vectors_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(n, seed, d_out);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
+                           int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
+                           int32_t* d_overflow, void* stream) {
+    BT_REQUIRE(mesh && d_ref_pts && d_dirs && params && d_hit_count && d_hits, "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
+    const int cap = params->max_hits_per_ray;
+    BT_REQUIRE(cap >= 1 && cap <= 32, "max_hits_per_ray must be in [1, 32]");
+    BT_CUDA(cudaSetDevice(mesh->m.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_overflow) BT_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
+    if (n_ref == 0) return BT_OK;
+    const int64_t total = n_ref * n_rays;
+    const unsigned grid = (unsigned)ceil_div(total, 128);
+    MeshView mv = view_of(mesh->m);
+    if (cap <= 8)
+        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, d_hit_count, d_hits, d_overflow);
+    else if (cap <= 16)
+        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, d_hit_count, d_hits, d_overflow);
+    else
+        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, d_hit_count, d_hits, d_overflow);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, int64_t n_ref, int32_t n_rays,
+                             int32_t cap, int32_t max_targets, uint64_t seed, int32_t* d_pair_count,
+                             int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs,
+                             void* stream) {
+    BT_REQUIRE(d_hit_count && d_hits && d_pair_count && d_pair_offset && d_pair_ref && d_pair_q, "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_rays > 0 && cap >= 1 && max_targets >= 1, "bad counts");
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_first_kernel<<<1, 1, 0, st>>>(d_pair_offset);
+    BT_LAUNCH_CHECK();
+    if (n_ref == 0) return BT_OK;
+    const unsigned grid = (unsigned)ceil_div(n_ref * 32, 128);
+    select_count_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, n_ref, n_rays, cap, max_targets, d_pair_count);
+    BT_LAUNCH_CHECK();
+    size_t tmp_bytes = 0;
+    BT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
+    Scratch tmp;
+    BT_CUDA(tmp.alloc(tmp_bytes, st));
+    BT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
+    select_fill_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, n_ref, n_rays, cap, max_targets, seed,
+                                             d_pair_offset, cap_pairs, d_pair_ref, d_pair_q);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_expand_orientations(const double* d_ref_pts, const int64_t* d_pair_offset,
+                                      const int32_t* d_pair_ref, const double* d_pair_q, const double* d_frame_vecs,
+                                      int64_t n_ref, int64_t cap_pairs, int32_t n_o, int32_t halfspace,
+                                      const double* h_cos, const double* h_sin, float* d_gs, double* d_contacts,
+                                      void* stream) {
+    BT_REQUIRE(d_ref_pts && d_pair_offset && d_pair_ref && d_pair_q && d_gs && h_cos && h_sin, "null pointer");
+    BT_REQUIRE(halfspace || d_frame_vecs, "frame vectors required unless halfspace");
+    BT_REQUIRE(n_o >= 1 && n_o <= 64, "n_orientations must be in [1, 64]");
+    if (cap_pairs <= 0 || n_ref <= 0) return BT_OK;
+    OrientTable tab;
+    for (int i = 0; i < 64; ++i) { tab.c[i] = i < n_o ? h_cos[i] : 0.0; tab.s[i] = i < n_o ? h_sin[i] : 0.0; }
+    expand_kernel<<<(unsigned)ceil_div(cap_pairs * n_o, 128), 128, 0, (cudaStream_t)stream>>>(
+        d_ref_pts, d_pair_offset, d_pair_ref, d_pair_q, d_frame_vecs, n_ref, n_o, halfspace, tab, d_gs, d_contacts);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}

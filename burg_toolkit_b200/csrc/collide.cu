@@ -1,0 +1,337 @@
+// collide.cu -- gripper-vs-scene collision (K1) and stream compaction of the surviving grasps.
+//
+// Reference being replaced: AntipodalGraspSampler.check_collisions (burg_toolkit/sampling.py:354-397), i.e. one
+// trimesh CollisionManager.in_collision_single -> FCL mesh/mesh query per grasp in a Python loop.  FCL's answer
+// is "does any triangle of the posed gripper mesh intersect any scene triangle" (surface test: containment is not
+// a collision) decided by the 17-axis separating-axis test of Intersect::intersect_Triangle / project6.
+//
+// Here: one thread per (grasp, gripper part).  A part is a group of gripper triangles with its TCP-frame AABB; under
+// pose * diag(s,1,1) it is an exact oriented box in the world, which is walked down the scene LBVH with a
+// conservative float32 box test; at the leaves the float64 17-axis test runs on the world-space vertices.
+#include <cub/cub.cuh>
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bt {
+
+constexpr int CSTACK = 64;
+constexpr int MAX_PARTS = 64;
+
+struct PartDev {
+    float cx, cy, cz;      // box centre, TCP frame
+    float hx, hy, hz;      // half extents
+    int32_t tri_begin, tri_end;
+};
+
+// FCL Intersect::project6: true if `ax` does NOT separate {p1,p2,p3} from {q1,q2,q3}
+__device__ __forceinline__ bool project6(d3 ax, d3 p1, d3 p2, d3 p3, d3 q1, d3 q2, d3 q3) {
+    const double P1 = dot3(ax, p1), P2 = dot3(ax, p2), P3 = dot3(ax, p3);
+    const double Q1 = dot3(ax, q1), Q2 = dot3(ax, q2), Q3 = dot3(ax, q3);
+    const double mn1 = fmin(P1, fmin(P2, P3));
+    const double mx2 = fmax(Q1, fmax(Q2, Q3));
+    if (mn1 > mx2) return false;
+    const double mx1 = fmax(P1, fmax(P2, P3));
+    const double mn2 = fmin(Q1, fmin(Q2, Q3));
+    if (mn2 > mx1) return false;
+    return true;
+}
+
+// FCL Intersect::intersect_Triangle(P1,P2,P3, Q1,Q2,Q3): P = scene triangle, Q = posed gripper triangle
+__device__ bool tri_tri_intersect(d3 P1, d3 P2, d3 P3, d3 Q1, d3 Q2, d3 Q3) {
+    const d3 p1 = sub3(P1, P1), p2 = sub3(P2, P1), p3 = sub3(P3, P1);
+    const d3 q1 = sub3(Q1, P1), q2 = sub3(Q2, P1), q3 = sub3(Q3, P1);
+    const d3 e1 = sub3(p2, p1), e2 = sub3(p3, p2);
+    const d3 n1 = cross3(e1, e2);
+    if (!project6(n1, p1, p2, p3, q1, q2, q3)) return false;
+    const d3 f1 = sub3(q2, q1), f2 = sub3(q3, q2);
+    const d3 m1 = cross3(f1, f2);
+    if (!project6(m1, p1, p2, p3, q1, q2, q3)) return false;
+    const d3 e3 = sub3(p1, p3), f3 = sub3(q1, q3);
+    if (!project6(cross3(e1, f1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e1, f2), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e1, f3), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e2, f1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e2, f2), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e2, f3), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e3, f1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e3, f2), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e3, f3), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e1, n1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e2, n1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(e3, n1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(f1, m1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(f2, m1), p1, p2, p3, q1, q2, q3)) return false;
+    if (!project6(cross3(f3, m1), p1, p2, p3, q1, q2, q3)) return false;
+    return true;
+}
+
+struct Obb {
+    float cx, cy, cz;
+    float ux[3], uy[3], uz[3];     // world-space axes (columns of R)
+    float h[3];                    // half extents along the axes (inflated)
+    float ax, ay, az;              // half extents of the OBB's world AABB
+};
+
+// conservative overlap: 3 world axes + 3 box axes (the 9 cross axes are skipped -> false positives only)
+__device__ __forceinline__ bool obb_overlaps_aabb(const Obb& b, float x0, float y0, float z0, float x1, float y1, float z1) {
+    const float ex = 0.5f * (x1 - x0), ey = 0.5f * (y1 - y0), ez = 0.5f * (z1 - z0);
+    const float dx = 0.5f * (x1 + x0) - b.cx, dy = 0.5f * (y1 + y0) - b.cy, dz = 0.5f * (z1 + z0) - b.cz;
+    if (fabsf(dx) > ex + b.ax || fabsf(dy) > ey + b.ay || fabsf(dz) > ez + b.az) return false;
+    float pr;
+    pr = fabsf(fmaf(dx, b.ux[0], fmaf(dy, b.ux[1], dz * b.ux[2])));
+    if (pr > b.h[0] + fmaf(ex, fabsf(b.ux[0]), fmaf(ey, fabsf(b.ux[1]), ez * fabsf(b.ux[2])))) return false;
+    pr = fabsf(fmaf(dx, b.uy[0], fmaf(dy, b.uy[1], dz * b.uy[2])));
+    if (pr > b.h[1] + fmaf(ex, fabsf(b.uy[0]), fmaf(ey, fabsf(b.uy[1]), ez * fabsf(b.uy[2])))) return false;
+    pr = fabsf(fmaf(dx, b.uz[0], fmaf(dy, b.uz[1], dz * b.uz[2])));
+    if (pr > b.h[2] + fmaf(ex, fabsf(b.uz[0]), fmaf(ey, fabsf(b.uz[1]), ez * fabsf(b.uz[2])))) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
+               int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
+               const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
+               unsigned int* __restrict__ out_words) {
+    extern __shared__ double s_gtris[];            // gripper triangles, TCP frame
+    __shared__ PartDev s_parts[MAX_PARTS];
+    const int n_gt = parts[n_parts - 1].tri_end;
+    for (int i = threadIdx.x; i < 9 * n_gt; i += blockDim.x) s_gtris[i] = gtris[i];
+    for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_parts[i] = parts[i];
+    __syncthreads();
+
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t row = idx / n_parts;
+    const int part = (int)(idx - row * n_parts);
+    const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
+    if (row >= n) return;
+    volatile unsigned int* word = out_words + (row >> 2);
+    const unsigned int bit = 1u << (8 * (row & 3));
+    if (*word & bit) return;                       // another part of this grasp already collides
+
+    const float* g = gs + 14 * row;
+    float gf[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) gf[k] = __ldg(g + k);
+    // sampling.py:392-394 in float32 (numpy >= 2 scalar promotion): s = (width + tol) / opening_width
+    const float sf = use_width ? (gf[13] + tol) / ow : 1.0f;
+    const double s = (double)sf;
+    // M = pose[:3,:3] @ diag(s,1,1); T = pose[:3,3]
+    const double m00 = (double)gf[3] * s, m01 = gf[4], m02 = gf[5];
+    const double m10 = (double)gf[6] * s, m11 = gf[7], m12 = gf[8];
+    const double m20 = (double)gf[9] * s, m21 = gf[10], m22 = gf[11];
+    const double tx = gf[0], ty = gf[1], tz = gf[2];
+
+    const PartDev pd = s_parts[part];
+    Obb b;
+    b.ux[0] = gf[3]; b.ux[1] = gf[6]; b.ux[2] = gf[9];
+    b.uy[0] = gf[4]; b.uy[1] = gf[7]; b.uy[2] = gf[10];
+    b.uz[0] = gf[5]; b.uz[1] = gf[8]; b.uz[2] = gf[11];
+    b.cx = (float)((m00 * pd.cx + m01 * pd.cy) + m02 * pd.cz + tx);
+    b.cy = (float)((m10 * pd.cx + m11 * pd.cy) + m12 * pd.cz + ty);
+    b.cz = (float)((m20 * pd.cx + m21 * pd.cy) + m22 * pd.cz + tz);
+    // the rotation block of a float32 grasp row is orthonormal only to ~1e-7; scale the half extents by the
+    // actual column norms (+ margin) so the box test stays conservative
+    const float nx = sqrtf(b.ux[0] * b.ux[0] + b.ux[1] * b.ux[1] + b.ux[2] * b.ux[2]);
+    const float ny = sqrtf(b.uy[0] * b.uy[0] + b.uy[1] * b.uy[1] + b.uy[2] * b.uy[2]);
+    const float nz = sqrtf(b.uz[0] * b.uz[0] + b.uz[1] * b.uz[1] + b.uz[2] * b.uz[2]);
+    b.h[0] = pd.hx * fabsf(sf) * nx * nx * 1.0001f + inflate;      // projections use the un-normalised axes
+    b.h[1] = pd.hy * ny * ny * 1.0001f + inflate;
+    b.h[2] = pd.hz * nz * nz * 1.0001f + inflate;
+    {
+        const float e0 = pd.hx * fabsf(sf) * 1.0001f, e1 = pd.hy * 1.0001f, e2 = pd.hz * 1.0001f;
+        b.ax = fabsf(b.ux[0]) * e0 + fabsf(b.uy[0]) * e1 + fabsf(b.uz[0]) * e2 + inflate;
+        b.ay = fabsf(b.ux[1]) * e0 + fabsf(b.uy[1]) * e1 + fabsf(b.uz[1]) * e2 + inflate;
+        b.az = fabsf(b.ux[2]) * e0 + fabsf(b.uy[2]) * e1 + fabsf(b.uz[2]) * e2 + inflate;
+    }
+
+    int stack[CSTACK];
+    int sp = 0;
+    int cur = 0;
+    while (true) {
+        if (cur < 0) {
+            const double* tv = tri_verts + 9 * (int64_t)(~cur);
+            const d3 P1 = ld3(tv), P2 = ld3(tv + 3), P3 = ld3(tv + 6);
+            for (int t = pd.tri_begin; t < pd.tri_end; ++t) {
+                const double* gt = s_gtris + 9 * t;
+                d3 Q[3];
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    const double px = gt[3 * v], py = gt[3 * v + 1], pz = gt[3 * v + 2];
+                    Q[v] = mk3(((m00 * px + m01 * py) + m02 * pz) + tx, ((m10 * px + m11 * py) + m12 * pz) + ty,
+                               ((m20 * px + m21 * py) + m22 * pz) + tz);
+                }
+                if (tri_tri_intersect(P1, P2, P3, Q[0], Q[1], Q[2])) {
+                    atomicOr(out_words + (row >> 2), bit);
+                    return;
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        const float4 q0 = __ldg(nodes + 4 * (int64_t)cur + 0);
+        const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
+        const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
+        const float4 q3 = __ldg(nodes + 4 * (int64_t)cur + 3);
+        const bool hl = obb_overlaps_aabb(b, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+        const bool hr = obb_overlaps_aabb(b, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+        const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
+        if (hl && hr) { stack[sp++] = r; cur = l; }
+        else if (hl) cur = l;
+        else if (hr) cur = r;
+        else { if (sp == 0) break; cur = stack[--sp]; }
+    }
+}
+
+// ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------
+constexpr int CB = 256;
+
+__global__ void compact_count_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
+                                     const int64_t* __restrict__ d_n, int32_t* __restrict__ block_count) {
+    __shared__ int warp_tot[CB / 32];
+    const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
+    const int64_t i = blockIdx.x * (int64_t)CB + threadIdx.x;
+    const bool k = (i < n) && (mask[i] == keep);
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < CB / 32; ++w) t += warp_tot[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void compact_scatter_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
+                                       const int64_t* __restrict__ d_n, const int64_t* __restrict__ block_offset,
+                                       int64_t n_blocks, const float* __restrict__ gs, const double* __restrict__ contacts,
+                                       float* __restrict__ out_gs, double* __restrict__ out_contacts, int64_t* __restrict__ n_out) {
+    __shared__ int warp_off[CB / 32];
+    const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
+    const int64_t i = blockIdx.x * (int64_t)CB + threadIdx.x;
+    const bool k = (i < n) && (mask[i] == keep);
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_off[w] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) { int c = warp_off[q]; warp_off[q] = run; run += c; }
+        if (blockIdx.x == n_blocks - 1 && n_out) *n_out = block_offset[blockIdx.x] + run;
+    }
+    __syncthreads();
+    if (!k) return;
+    const int64_t dst = block_offset[blockIdx.x] + warp_off[w] + __popc(bal & ((1u << lane) - 1u));
+#pragma unroll
+    for (int c = 0; c < 14; ++c) out_gs[14 * dst + c] = gs[14 * i + c];
+    if (contacts && out_contacts) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) out_contacts[6 * dst + c] = contacts[6 * i + c];
+    }
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+struct bt_gripper {
+    int device = 0;
+    int n_tris = 0, n_parts = 0;
+    double* tris = nullptr;        // [n_tris, 9] TCP frame
+    bt::PartDev* parts = nullptr;  // [n_parts]
+};
+
+extern "C" int bt_gripper_create(const double* h_tris, int32_t n_gt, const bt_gripper_part* h_parts, int32_t n_parts,
+                                 int device, bt_gripper** out) {
+    BT_REQUIRE(h_tris && h_parts && out, "null pointer");
+    BT_REQUIRE(n_gt > 0 && n_parts > 0 && n_parts <= MAX_PARTS, "bad counts (1 <= n_parts <= 64)");
+    BT_REQUIRE(9 * (size_t)n_gt * sizeof(double) <= 160 * 1024, "gripper mesh too large for shared memory staging");
+    std::vector<PartDev> parts(n_parts);
+    int expect = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        const bt_gripper_part& hp = h_parts[p];
+        BT_REQUIRE(hp.tri_begin == expect && hp.tri_end > hp.tri_begin && hp.tri_end <= n_gt, "parts must tile [0, n_tris)");
+        expect = hp.tri_end;
+        parts[p].cx = (float)(0.5 * (hp.box_min[0] + hp.box_max[0]));
+        parts[p].cy = (float)(0.5 * (hp.box_min[1] + hp.box_max[1]));
+        parts[p].cz = (float)(0.5 * (hp.box_min[2] + hp.box_max[2]));
+        // half extents rounded up a little: the box must contain every triangle of the part
+        parts[p].hx = (float)(0.5 * (hp.box_max[0] - hp.box_min[0])) * 1.00001f + 1e-9f;
+        parts[p].hy = (float)(0.5 * (hp.box_max[1] - hp.box_min[1])) * 1.00001f + 1e-9f;
+        parts[p].hz = (float)(0.5 * (hp.box_max[2] - hp.box_min[2])) * 1.00001f + 1e-9f;
+        parts[p].tri_begin = hp.tri_begin;
+        parts[p].tri_end = hp.tri_end;
+    }
+    BT_REQUIRE(expect == n_gt, "parts must cover every gripper triangle");
+    BT_CUDA(cudaSetDevice(device));
+    bt_gripper* g = new bt_gripper();
+    g->device = device; g->n_tris = n_gt; g->n_parts = n_parts;
+    cudaError_t e = cudaMalloc(&g->tris, sizeof(double) * 9 * (size_t)n_gt);
+    if (e == cudaSuccess) e = cudaMalloc(&g->parts, sizeof(PartDev) * n_parts);
+    if (e == cudaSuccess) e = cudaMemcpy(g->tris, h_tris, sizeof(double) * 9 * (size_t)n_gt, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->parts, parts.data(), sizeof(PartDev) * n_parts, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(g->tris); cudaFree(g->parts); delete g; return cuda_fail(e, "bt_gripper_create", __FILE__, __LINE__); }
+    *out = g;
+    return BT_OK;
+}
+
+extern "C" int bt_gripper_destroy(bt_gripper* g) {
+    if (!g) return BT_OK;
+    cudaSetDevice(g->device);
+    cudaFree(g->tris); cudaFree(g->parts);
+    delete g;
+    return BT_OK;
+}
+
+extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const float* d_gs, int64_t n,
+                          const int64_t* d_n, double opening_width, double width_tolerance, int32_t use_width,
+                          uint8_t* d_colliding, void* stream) {
+    BT_REQUIRE(scene && gripper && d_gs && d_colliding, "null pointer");
+    BT_REQUIRE(n >= 0, "negative count");
+    BT_REQUIRE(scene->m.device == gripper->device, "scene and gripper live on different devices");
+    BT_REQUIRE((reinterpret_cast<uintptr_t>(d_colliding) & 3) == 0, "d_colliding must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    BT_CUDA(cudaSetDevice(scene->m.device));
+    BT_CUDA(cudaMemsetAsync(d_colliding, 0, (size_t)ceil_div(n, 4) * 4, st));
+    if (n == 0) return BT_OK;
+    float max_abs = 0.1f;
+    for (int k = 0; k < 3; ++k)
+        max_abs = fmaxf(max_abs, fmaxf(fabsf(scene->m.info.bounds_min[k]), fabsf(scene->m.info.bounds_max[k])));
+    const float inflate = 2e-5f * max_abs + 1e-6f;
+    const size_t tri_bytes = sizeof(double) * 9 * (size_t)gripper->n_tris;
+    if (tri_bytes > 48 * 1024)
+        BT_CUDA(cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+    const int64_t threads = n * gripper->n_parts;
+    collide_kernel<<<(unsigned)ceil_div(threads, 128), 128, tri_bytes, st>>>(
+        scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
+        (float)opening_width, (float)width_tolerance, use_width, inflate, reinterpret_cast<unsigned int*>(d_colliding));
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
+                          int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
+                          void* stream) {
+    BT_REQUIRE(d_mask && d_gs && d_out_gs && d_n_out, "null pointer");
+    BT_REQUIRE(n >= 0, "negative count");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { BT_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), st)); return BT_OK; }
+    const int64_t n_blocks = ceil_div(n, CB);
+    Scratch counts, offsets, tmp;
+    BT_CUDA(counts.alloc(sizeof(int32_t) * n_blocks, st));
+    BT_CUDA(offsets.alloc(sizeof(int64_t) * n_blocks, st));
+    compact_count_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, counts.as<int32_t>());
+    BT_LAUNCH_CHECK();
+    size_t tmp_bytes = 0;
+    BT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
+    BT_CUDA(tmp.alloc(tmp_bytes, st));
+    BT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
+    compact_scatter_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, offsets.as<int64_t>(), n_blocks,
+                                                              d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}

@@ -1,0 +1,127 @@
+// common.cuh -- shared host/device helpers for libburgb200 (sm_100a only).
+//
+// The whole library is compiled with -fmad=false: float64 paths reproduce numpy's separate multiply /
+// add roundings, and every fused multiply-add that IS wanted (float32 traversal math, the sgemm-style
+// FMA chains of metrics.py) is written explicitly with fmaf()/fma().
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/burg_b200.h"
+
+namespace bt {
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define BT_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return bt::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define BT_REQUIRE(cond, msg)                                                  \
+    do {                                                                       \
+        if (!(cond)) { bt::set_error("%s: %s", __func__, msg); return BT_E_INVALID; } \
+    } while (0)
+
+#define BT_LAUNCH_CHECK() BT_CUDA(cudaGetLastError())
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// stream-ordered scratch buffer (cudaMallocAsync / cudaFreeAsync)
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    }
+    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- device mesh -------------------------------------------------------------------------------------
+// LBVH node: 64 bytes = 4 x float4, holds BOTH children's boxes so one fetch decides both descents.
+//   q0 = (l.min.x, l.min.y, l.min.z, l.max.x)
+//   q1 = (l.max.y, l.max.z, r.min.x, r.min.y)
+//   q2 = (r.min.z, r.max.x, r.max.y, r.max.z)
+//   q3 = (left, right, -, -) as int bits; child >= 0: internal node index, child < 0: leaf ~child
+// Triangle record for the exact ray test: 128 bytes = 16 doubles (one cache line):
+//   v0[3] n[3] e0[3] e1[3] d00 d01 d11 inv_den     (e0 = v1-v0, e1 = v2-v0, trimesh 'cramer' constants)
+// Triangle vertices for the exact triangle/triangle test: 9 doubles (v0 v1 v2).
+struct MeshDev {
+    int device = 0;
+    int64_t nV = 0, nF = 0;
+    // caller order
+    double*  verts = nullptr;      // [nV,3]
+    double*  vnormals = nullptr;   // [nV,3]
+    int32_t* faces = nullptr;      // [nF,3]
+    double*  area_cdf = nullptr;   // [nF] inclusive normalised cumulative area (caller order)
+    // LBVH (leaf order = Morton order)
+    float4*  nodes = nullptr;      // [max(nF-1,1)*4]
+    double*  tri_rec = nullptr;    // [nF,16]  leaf order
+    double*  tri_verts = nullptr;  // [nF,9]   leaf order
+    int32_t* leaf_tri = nullptr;   // [nF]     leaf -> caller's triangle id
+    int32_t  root = 0;             // root child code (internal 0, or ~0 if single triangle)
+    bt_mesh_info info{};
+};
+
+}  // namespace bt
+
+struct bt_mesh {
+    bt::MeshDev m;
+};
+
+// ---- small device math (float64, numpy operation order; no contraction thanks to -fmad=false) --------
+namespace bt {
+
+struct d3 { double x, y, z; };
+
+__host__ __device__ inline d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ inline d3 ld3(const double* p) { return mk3(p[0], p[1], p[2]); }
+__host__ __device__ inline void st3(double* p, d3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__host__ __device__ inline d3 sub3(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ inline d3 add3(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ inline d3 scl3(d3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ inline d3 div3(d3 a, double s) { return mk3(a.x / s, a.y / s, a.z / s); }
+// np.sum(a*b, -1) / np.dot(a*b, ones) : (x + y) + z with separately rounded products
+__host__ __device__ inline double dot3(d3 a, d3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// np.cross : c0 = a1*b2 - a2*b1, ...
+__host__ __device__ inline d3 cross3(d3 a, d3 b) {
+    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// np.linalg.norm(v, axis=-1) : sqrt((x*x + y*y) + z*z)
+__host__ __device__ inline double norm3(d3 a) { return sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
+
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011) -- device-side candidate generation
+__host__ __device__ inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                             uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__host__ __device__ inline void philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// 53-bit uniform in [0,1) from two 32-bit words
+__host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace bt

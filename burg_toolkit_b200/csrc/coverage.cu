@@ -1,0 +1,388 @@
+// coverage.cu -- grasp-set coverage / precision and the pairwise SE(3) distances behind it (M1-M5).
+//
+// Reference being replaced: burg_toolkit/metrics.py -- euclidean_distances :9-27, angular_distances :30-60,
+// combined_distances :63-77, coverage_brute_force :141-158, coverage :161-229 (cKDTree.query_ball_tree + a Python
+// loop).  The predicate is  covered_i = any_j ( 1000*|t_i - t_j| + deg(R_i, R_j) <= eps )  in float32 with the
+// reference's exact operation order:
+//     d    = sqrt((dx*dx + dy*dy) + dz*dz)                      separate multiplies / adds
+//     g_r  = fma(a_r2, b_r2, fma(a_r1, b_r1, a_r0 * b_r0))      sgemm-style chain, r = 0..2 (rows of R1, R2)
+//     c    = ((g0 + g1) + g2 - 1) / 2 ;  k = rint(c * 1e4) ;  deg = LUT[k + 10000]   (np.around(.,4) -> arccos -> rad2deg)
+//     comb = 1000*d + deg
+// Every pair first goes through a cheap conservative float32 translation reject (3 FFMA + compare); only its rare
+// survivors run the exact recipe.  algo 0 tiles all pairs through shared memory; algo 1 bins both sets in a uniform
+// grid of cell size ~eps/1000 and only visits the 27 neighbouring cells (result identical: the predicate is an OR).
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace bt {
+
+constexpr int COV_THREADS = 256;
+constexpr int COV_RPT = 4;                       // reference rows per thread
+constexpr int COV_TILE = 1024;                   // queries staged per shared-memory tile (16 KB)
+
+struct CovParams {
+    float eps;              // epsilon (float32 compare, metrics.py:157/:219)
+    float weight;           // 1000.0f
+    float r2_reject;        // conservative squared-distance bound for the fast reject
+    double r2_kd;           // (eps/1000)^2 in float64 (mode 1)
+    int mode;
+    float cx, cy, cz;       // centring offset for the expanded-form reject
+};
+
+// exact reference recipe for one pair; rows are the raw float32[14] grasp rows
+__device__ __noinline__ bool pair_covered(const float* __restrict__ a, const float* __restrict__ b,
+                                             const float* __restrict__ lut, const CovParams& P) {
+    const float dx = __fsub_rn(a[0], b[0]), dy = __fsub_rn(a[1], b[1]), dz = __fsub_rn(a[2], b[2]);
+    const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float wd = __fmul_rn(P.weight, d);
+    if (!(wd <= P.eps)) return false;                       // deg >= 0, so the sum cannot come back under eps
+    if (P.mode == 1) {                                      // cKDTree.query_ball_tree candidate test, float64
+        const double ex = (double)a[0] - (double)b[0], ey = (double)a[1] - (double)b[1], ez = (double)a[2] - (double)b[2];
+        if (!(((ex * ex + ey * ey) + ez * ez) <= P.r2_kd)) return false;
+    }
+    float g[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        g[r] = __fmaf_rn(a[3 + 3 * r + 2], b[3 + 3 * r + 2], __fmaf_rn(a[3 + 3 * r + 1], b[3 + 3 * r + 1], __fmul_rn(a[3 + 3 * r], b[3 + 3 * r])));
+    const float tr = __fadd_rn(__fadd_rn(g[0], g[1]), g[2]);
+    const float c = __fdiv_rn(__fsub_rn(tr, 1.0f), 2.0f);
+    const float kf = rintf(__fmul_rn(c, 10000.0f));
+    if (!(fabsf(kf) <= 10000.0f)) return false;             // arccos(>1) = NaN in the reference -> never <= eps
+    const float deg = __ldg(lut + ((int)kf + 10000));
+    return __fadd_rn(wd, deg) <= P.eps;
+}
+
+// ---- algo 0: all pairs, query tiles in shared memory ---------------------------------------------------------
+__global__ void __launch_bounds__(COV_THREADS)
+coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ qry, int64_t n_qry,
+                      int64_t q_per_split, const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
+    __shared__ float4 tile[COV_TILE];
+    const int64_t row0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT) + threadIdx.x;
+    // per-row constants of the expanded form  |a-q|^2 = |q|^2 - 2 a.q + |a|^2  (centred coordinates)
+    float ax[COV_RPT], ay[COV_RPT], az[COV_RPT], thr[COV_RPT];
+    bool cov[COV_RPT];
+#pragma unroll
+    for (int r = 0; r < COV_RPT; ++r) {
+        const int64_t i = row0 + (int64_t)r * COV_THREADS;
+        cov[r] = false;
+        if (i < n_ref) {
+            const float x = ref[14 * i] - P.cx, y = ref[14 * i + 1] - P.cy, z = ref[14 * i + 2] - P.cz;
+            ax[r] = -2.0f * x; ay[r] = -2.0f * y; az[r] = -2.0f * z;
+            thr[r] = P.r2_reject - fmaf(x, x, fmaf(y, y, z * z));
+        } else { ax[r] = ay[r] = az[r] = 0.f; thr[r] = -1e30f; }
+    }
+    const int64_t q_begin = (int64_t)blockIdx.y * q_per_split;
+    const int64_t q_end = min(n_qry, q_begin + q_per_split);
+    for (int64_t q0 = q_begin; q0 < q_end; q0 += COV_TILE) {
+        const int cnt = (int)min((int64_t)COV_TILE, q_end - q0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += COV_THREADS) {
+            const float* q = qry + 14 * (q0 + j);
+            const float x = q[0] - P.cx, y = q[1] - P.cy, z = q[2] - P.cz;
+            tile[j] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const float4 q = tile[j];
+#pragma unroll
+            for (int r = 0; r < COV_RPT; ++r) {
+                const float s = fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w)));
+                if (s <= thr[r]) {                                   // rare: run the exact recipe
+                    const int64_t i = row0 + (int64_t)r * COV_THREADS;
+                    if (!cov[r] && pair_covered(ref + 14 * i, qry + 14 * (q0 + j), lut, P)) cov[r] = true;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < COV_RPT; ++r) {
+        const int64_t i = row0 + (int64_t)r * COV_THREADS;
+        if (i < n_ref && cov[r]) covered[i] = 1;                     // all writers store the same value
+    }
+}
+
+// ---- algo 1: uniform grid -----------------------------------------------------------------------------------
+struct Grid {
+    float ox, oy, oz;       // origin
+    float inv_h;
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int n) {
+    int c = (int)floorf((x - o) * inv_h);
+    return max(0, min(n - 1, c));
+}
+
+__device__ __forceinline__ uint32_t float_flip(float f) {           // order-preserving float -> uint
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float float_unflip(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+}
+
+__global__ void bounds_kernel(const float* __restrict__ rows, int64_t n, uint32_t* __restrict__ mm /*[6]: min xyz, max xyz*/) {
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float v = rows[14 * i + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], s));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], s));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(mm + k, float_flip(lo[k])); atomicMax(mm + 3 + k, float_flip(hi[k])); }
+    }
+}
+
+__global__ void cell_key_kernel(const float* __restrict__ rows, int64_t n, Grid g, uint32_t* __restrict__ keys,
+                                int32_t* __restrict__ ids) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = cell_coord(rows[14 * i], g.ox, g.inv_h, g.nx);
+    const int cy = cell_coord(rows[14 * i + 1], g.oy, g.inv_h, g.ny);
+    const int cz = cell_coord(rows[14 * i + 2], g.oz, g.inv_h, g.nz);
+    keys[i] = (uint32_t)((cx * g.ny + cy) * g.nz + cz);
+    ids[i] = (int32_t)i;
+}
+
+// sorted query translations as float4 (x, y, z, original index) + dense cell range table
+__global__ void gather_sorted_kernel(const float* __restrict__ rows, const int32_t* __restrict__ sorted_ids,
+                                     const uint32_t* __restrict__ sorted_keys, int64_t n, float4* __restrict__ out,
+                                     int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_end) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t id = sorted_ids[i];
+    out[i] = make_float4(rows[14 * (int64_t)id], rows[14 * (int64_t)id + 1], rows[14 * (int64_t)id + 2], __int_as_float(id));
+    if (cell_start) {
+        const uint32_t k = sorted_keys[i];
+        if (i == 0 || sorted_keys[i - 1] != k) cell_start[k] = (int32_t)i;
+        if (i == n - 1 || sorted_keys[i + 1] != k) cell_end[k] = (int32_t)i + 1;
+    }
+}
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128)
+coverage_grid_kernel(const float* __restrict__ ref, const int32_t* __restrict__ ref_sorted_ids, int64_t n_ref,
+                     const float* __restrict__ qry, const float4* __restrict__ q_sorted,
+                     const uint32_t* __restrict__ q_keys, int n_qry, const int32_t* __restrict__ cell_start,
+                     const int32_t* __restrict__ cell_end, Grid g, const float* __restrict__ lut, CovParams P,
+                     uint8_t* __restrict__ covered) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_ref) return;
+    const int64_t i = ref_sorted_ids[s];                 // refs are walked in cell order -> a warp shares cells
+    const float* a = ref + 14 * i;
+    const float x = a[0], y = a[1], z = a[2];
+    const int cx = cell_coord(x, g.ox, g.inv_h, g.nx), cy = cell_coord(y, g.oy, g.inv_h, g.ny), cz = cell_coord(z, g.oz, g.inv_h, g.nz);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+    bool cov = false;
+    for (int ix = max(cx - 1, 0); ix <= min(cx + 1, g.nx - 1) && !cov; ++ix)
+        for (int iy = max(cy - 1, 0); iy <= min(cy + 1, g.ny - 1) && !cov; ++iy) {
+            const uint32_t k0 = (uint32_t)((ix * g.ny + iy) * g.nz + z0), k1 = (uint32_t)((ix * g.ny + iy) * g.nz + z1);
+            int b, e;
+            if (cell_start) {
+                // consecutive z cells are consecutive keys; empty cells have start == end == 0
+                b = -1; e = 0;
+                for (uint32_t k = k0; k <= k1; ++k) {
+                    const int cs = cell_start[k], ce = cell_end[k];
+                    if (ce > cs) { if (b < 0) b = cs; e = ce; }
+                }
+                if (b < 0) continue;
+            } else {
+                b = lower_bound_u32(q_keys, n_qry, k0);
+                e = lower_bound_u32(q_keys, n_qry, k1 + 1);
+            }
+            for (int j = b; j < e; ++j) {
+                const float4 q = __ldg(q_sorted + j);
+                const float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (d2 <= P.r2_reject) {
+                    if (pair_covered(a, qry + 14 * (int64_t)__float_as_int(q.w), lut, P)) { cov = true; break; }
+                }
+            }
+        }
+    if (cov) covered[i] = 1;
+}
+
+__global__ void count_covered_kernel(const uint8_t* __restrict__ covered, int64_t n, unsigned long long* __restrict__ count) {
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += covered[i] ? 1 : 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+__global__ void pairwise_kernel(const float* __restrict__ g1, int64_t n1, const float* __restrict__ g2, int64_t n2,
+                                int which, float weight, const float* __restrict__ lut, float* __restrict__ out) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n1 * n2) return;
+    const float* a = g1 + 14 * (idx / n2);
+    const float* b = g2 + 14 * (idx % n2);
+    float d = 0.f, ang = 0.f;
+    if (which != 1) {
+        const float dx = __fsub_rn(a[0], b[0]), dy = __fsub_rn(a[1], b[1]), dz = __fsub_rn(a[2], b[2]);
+        d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    }
+    if (which != 0) {
+        float g[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            g[r] = __fmaf_rn(a[3 + 3 * r + 2], b[3 + 3 * r + 2], __fmaf_rn(a[3 + 3 * r + 1], b[3 + 3 * r + 1], __fmul_rn(a[3 + 3 * r], b[3 + 3 * r])));
+        const float c = __fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(g[0], g[1]), g[2]), 1.0f), 2.0f);
+        const float kf = rintf(__fmul_rn(c, 10000.0f));
+        ang = (fabsf(kf) <= 10000.0f) ? lut[(int)kf + 10000] : __int_as_float(0x7fc00000);
+    }
+    out[idx] = which == 0 ? d : (which == 1 ? ang : __fadd_rn(__fmul_rn(weight, d), ang));
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+// bounding box of both translation sets (one tiny read-back; the metric API is synchronous anyway)
+static int data_bounds(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, float lo[3], float hi[3],
+                       cudaStream_t st) {
+    Scratch mm;
+    BT_CUDA(mm.alloc(6 * sizeof(uint32_t), st));
+    uint32_t h_mm[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    BT_CUDA(cudaMemcpyAsync(mm.p, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, st));
+    bounds_kernel<<<148 * 4, 256, 0, st>>>(d_ref, n_ref, mm.as<uint32_t>());
+    bounds_kernel<<<148 * 4, 256, 0, st>>>(d_qry, n_qry, mm.as<uint32_t>());
+    BT_LAUNCH_CHECK();
+    BT_CUDA(cudaMemcpyAsync(h_mm, mm.p, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) { lo[k] = float_unflip(h_mm[k]); hi[k] = float_unflip(h_mm[3 + k]); }
+    return BT_OK;
+}
+
+static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, const float* lut,
+                    CovParams P, float r_bound, uint8_t* d_covered, cudaStream_t st) {
+    // bounds of both sets -> grid
+    float lo[3], hi[3];
+    {
+        int rc = data_bounds(d_ref, n_ref, d_qry, n_qry, lo, hi, st);   // host sync: the grid shape is decided here
+        if (rc != BT_OK) return rc;
+    }
+    float extent = 0.f;
+    for (int k = 0; k < 3; ++k) extent = fmaxf(extent, hi[k] - lo[k]);
+    if (!(extent >= 0.f) || !isfinite(extent)) { set_error("bt_coverage: non-finite translations"); return BT_E_INVALID; }
+    // cell size: >= the largest distance that can pass the exact test, with head-room for the float32 rounding of
+    // the cell index, and at most 1023 cells per axis
+    float h = fmaxf(r_bound * 1.01f, extent / 1023.0f);
+    if (!(h > 0.f)) h = 1.0f;
+    Grid g;
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+    g.inv_h = 1.0f / h;
+    g.nx = (int)fminf(1024.f, floorf((hi[0] - lo[0]) / h) + 1.f);
+    g.ny = (int)fminf(1024.f, floorf((hi[1] - lo[1]) / h) + 1.f);
+    g.nz = (int)fminf(1024.f, floorf((hi[2] - lo[2]) / h) + 1.f);
+    const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
+    const bool dense = n_cells <= (1ll << 24);
+    int key_bits = 1;
+    while ((1ll << key_bits) < n_cells) ++key_bits;
+
+    Scratch keys, keys_s, ids, ids_s, rkeys, rkeys_s, rids, rids_s, qs, cs, ce, tmp;
+    BT_CUDA(keys.alloc(sizeof(uint32_t) * n_qry, st)); BT_CUDA(keys_s.alloc(sizeof(uint32_t) * n_qry, st));
+    BT_CUDA(ids.alloc(sizeof(int32_t) * n_qry, st));   BT_CUDA(ids_s.alloc(sizeof(int32_t) * n_qry, st));
+    BT_CUDA(rkeys.alloc(sizeof(uint32_t) * n_ref, st)); BT_CUDA(rkeys_s.alloc(sizeof(uint32_t) * n_ref, st));
+    BT_CUDA(rids.alloc(sizeof(int32_t) * n_ref, st));   BT_CUDA(rids_s.alloc(sizeof(int32_t) * n_ref, st));
+    BT_CUDA(qs.alloc(sizeof(float4) * n_qry, st));
+    if (dense) {
+        BT_CUDA(cs.alloc(sizeof(int32_t) * n_cells, st));
+        BT_CUDA(ce.alloc(sizeof(int32_t) * n_cells, st));
+        BT_CUDA(cudaMemsetAsync(cs.p, 0, sizeof(int32_t) * n_cells, st));
+        BT_CUDA(cudaMemsetAsync(ce.p, 0, sizeof(int32_t) * n_cells, st));
+    }
+    size_t b1 = 0, b2 = 0;
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, keys.as<uint32_t>(), keys_s.as<uint32_t>(), ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, key_bits, st));
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, key_bits, st));
+    BT_CUDA(tmp.alloc(b1 > b2 ? b1 : b2, st));
+    cell_key_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, n_qry, g, keys.as<uint32_t>(), ids.as<int32_t>());
+    cell_key_kernel<<<(unsigned)ceil_div(n_ref, 256), 256, 0, st>>>(d_ref, n_ref, g, rkeys.as<uint32_t>(), rids.as<int32_t>());
+    BT_LAUNCH_CHECK();
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b1, keys.as<uint32_t>(), keys_s.as<uint32_t>(), ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, key_bits, st));
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, key_bits, st));
+    gather_sorted_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, ids_s.as<int32_t>(), keys_s.as<uint32_t>(), n_qry, qs.as<float4>(),
+                                                                          dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr);
+    BT_LAUNCH_CHECK();
+    coverage_grid_kernel<<<(unsigned)ceil_div(n_ref, 128), 128, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
+                                                                          (int)n_qry, dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr,
+                                                                          g, lut, P, d_covered);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, double epsilon,
+                           const float* d_lut, int32_t mode, int32_t algo, uint8_t* d_covered, int64_t* d_count,
+                           void* stream) {
+    BT_REQUIRE(d_ref && d_qry && d_lut && d_covered && d_count, "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_qry >= 0 && n_ref < (1ll << 31) && n_qry < (1ll << 31), "bad counts");
+    BT_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (brute force semantics) or 1 (kd-tree semantics)");
+    BT_REQUIRE(algo == 0 || algo == 1, "algo must be 0 (tiles) or 1 (grid)");
+    cudaStream_t st = (cudaStream_t)stream;
+    BT_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    if (n_ref == 0) return BT_OK;
+    BT_CUDA(cudaMemsetAsync(d_covered, 0, (size_t)n_ref, st));
+    if (n_qry == 0 || !(epsilon >= 0.0)) return BT_OK;
+    CovParams P;
+    P.eps = (float)epsilon; P.weight = 1000.0f; P.mode = mode;      // the float32 compare of metrics.py:157/:219
+    const double r = epsilon / 1000.0;                              // the float64 radius of metrics.py:209
+    P.r2_kd = r * r;
+    // largest d with fl(1000*d) <= eps is eps/1000 * (1 + 2^-23); add margin
+    const float r_bound = (float)(r * (1.0 + 1e-6)) + 1e-12f;
+    P.cx = P.cy = P.cz = 0.f;
+    if (algo == 1) {
+        P.r2_reject = r_bound * r_bound * 1.0001f;          // direct-difference form: a few ulps of rounding only
+        int rc = run_grid(d_ref, n_ref, d_qry, n_qry, d_lut, P, r_bound, d_covered, st);
+        if (rc != BT_OK) return rc;
+    } else {
+        // centre on the first query row and bound the rounding of the expanded form by the data's spread; both are
+        // read back once (tiny, but a host sync -- the metric API is synchronous anyway)
+        float lo[3], hi[3], smax = 0.f;
+        {
+            int rc = data_bounds(d_ref, n_ref, d_qry, n_qry, lo, hi, st);
+            if (rc != BT_OK) return rc;
+        }
+        P.cx = 0.5f * (lo[0] + hi[0]); P.cy = 0.5f * (lo[1] + hi[1]); P.cz = 0.5f * (lo[2] + hi[2]);
+        for (int k = 0; k < 3; ++k) { const float e = 0.5f * (hi[k] - lo[k]) * 1.001f; smax += e * e; }
+        if (!isfinite(smax)) { set_error("bt_coverage: non-finite translations"); return BT_E_INVALID; }
+        // |computed - exact| <= ~24 eps32 * max|x|^2 for the 4-term FMA chain plus the two precomputed norms
+        P.r2_reject = r_bound * r_bound * 1.0001f + 64.0f * 5.97e-8f * smax;
+        const int64_t row_blocks = ceil_div(n_ref, COV_THREADS * COV_RPT);
+        int64_t splits = ceil_div(148 * 8, row_blocks);
+        splits = splits < 1 ? 1 : splits;
+        int64_t q_per_split = ceil_div(ceil_div(n_qry, splits), COV_TILE) * COV_TILE;
+        splits = ceil_div(n_qry, q_per_split);
+        dim3 grid((unsigned)row_blocks, (unsigned)splits);
+        coverage_tiles_kernel<<<grid, COV_THREADS, 0, st>>>(d_ref, n_ref, d_qry, n_qry, q_per_split, d_lut, P, d_covered);
+        BT_LAUNCH_CHECK();
+    }
+    count_covered_kernel<<<148, 256, 0, st>>>(d_covered, n_ref, reinterpret_cast<unsigned long long*>(d_count));
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_pairwise_distances(const float* d_gs1, int64_t n1, const float* d_gs2, int64_t n2, int32_t which,
+                                     float weight, const float* d_lut, float* d_out, void* stream) {
+    BT_REQUIRE(d_gs1 && d_gs2 && d_out, "null pointer");
+    BT_REQUIRE(which >= 0 && which <= 2, "which must be 0, 1 or 2");
+    BT_REQUIRE(which == 0 || d_lut, "lookup table required for angular / combined distances");
+    if (n1 <= 0 || n2 <= 0) return BT_OK;
+    pairwise_kernel<<<(unsigned)ceil_div(n1 * n2, 256), 256, 0, (cudaStream_t)stream>>>(d_gs1, n1, d_gs2, n2, which, weight, d_lut, d_out);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}

@@ -1,0 +1,416 @@
+// mesh.cu -- library plumbing, device mesh upload and the GPU-built LBVH.
+//
+// Replaces the set-up half of the reference's sampler (sampling.py:191-192: as_trimesh +
+// RayMeshIntersector construction; :372-380: CollisionManager population).  The LBVH is the Karras 2012
+// construction: 30-bit Morton codes of the triangle-box centres -> radix sort (CUB) -> one thread per
+// internal node finds its key range and split -> bottom-up refit with arrival counters -> final 64-byte
+// nodes that carry BOTH children's boxes (one float4x4 fetch per traversal step).
+#include <cub/cub.cuh>
+#include <stdarg.h>
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bt {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return BT_E_CUDA;
+}
+
+// ---- kernels -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void morton_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces, int64_t nF,
+                              double3 bmin, double3 inv_ext, uint32_t* __restrict__ keys, int32_t* __restrict__ ids) {
+    int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    const int32_t* fc = faces + 3 * f;
+    d3 a = ld3(verts + 3 * (int64_t)fc[0]), b = ld3(verts + 3 * (int64_t)fc[1]), c = ld3(verts + 3 * (int64_t)fc[2]);
+    double cx = 0.5 * (fmin(a.x, fmin(b.x, c.x)) + fmax(a.x, fmax(b.x, c.x)));
+    double cy = 0.5 * (fmin(a.y, fmin(b.y, c.y)) + fmax(a.y, fmax(b.y, c.y)));
+    double cz = 0.5 * (fmin(a.z, fmin(b.z, c.z)) + fmax(a.z, fmax(b.z, c.z)));
+    uint32_t ix = (uint32_t)fmin(fmax((cx - bmin.x) * inv_ext.x * 1024.0, 0.0), 1023.0);
+    uint32_t iy = (uint32_t)fmin(fmax((cy - bmin.y) * inv_ext.y * 1024.0, 0.0), 1023.0);
+    uint32_t iz = (uint32_t)fmin(fmax((cz - bmin.z) * inv_ext.z * 1024.0, 0.0), 1023.0);
+    keys[f] = (expand_bits10(ix) << 2) | (expand_bits10(iy) << 1) | expand_bits10(iz);
+    ids[f] = (int32_t)f;
+}
+
+// per leaf (Morton order): exact-test records, f32 leaf boxes (rounded outward + pad), areas in caller order
+__global__ void leaf_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces,
+                            const int32_t* __restrict__ sorted_ids, int64_t nF, float pad,
+                            double* __restrict__ tri_rec, double* __restrict__ tri_verts, int32_t* __restrict__ leaf_tri,
+                            float* __restrict__ box_min, float* __restrict__ box_max, double* __restrict__ area) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nF) return;
+    int32_t f = sorted_ids[i];
+    const int32_t* fc = faces + 3 * (int64_t)f;
+    d3 v0 = ld3(verts + 3 * (int64_t)fc[0]), v1 = ld3(verts + 3 * (int64_t)fc[1]), v2 = ld3(verts + 3 * (int64_t)fc[2]);
+    d3 e0 = sub3(v1, v0), e1 = sub3(v2, v0);
+    d3 cr = cross3(e0, e1);
+    double nn = norm3(cr);                       // trimesh util.unitize: v * (1 / sqrt(dot(v*v, ones)))
+    d3 n = mk3(0.0, 0.0, 0.0);
+    if (nn > 1e-13) { double inv = 1.0 / nn; n = scl3(cr, inv); }
+    double d00 = dot3(e0, e0), d01 = dot3(e0, e1), d11 = dot3(e1, e1);
+    double inv_den = 1.0 / (d00 * d11 - d01 * d01);
+    double* r = tri_rec + 16 * i;
+    st3(r + 0, v0); st3(r + 3, n); st3(r + 6, e0); st3(r + 9, e1);
+    r[12] = d00; r[13] = d01; r[14] = d11; r[15] = inv_den;
+    double* tv = tri_verts + 9 * i;
+    st3(tv + 0, v0); st3(tv + 3, v1); st3(tv + 6, v2);
+    leaf_tri[i] = f;
+    area[f] = 0.5 * nn;
+    int64_t slot = (nF - 1) + i;                 // leaves follow the nF-1 internal boxes
+    box_min[3 * slot + 0] = __double2float_rd(fmin(v0.x, fmin(v1.x, v2.x))) - pad;
+    box_min[3 * slot + 1] = __double2float_rd(fmin(v0.y, fmin(v1.y, v2.y))) - pad;
+    box_min[3 * slot + 2] = __double2float_rd(fmin(v0.z, fmin(v1.z, v2.z))) - pad;
+    box_max[3 * slot + 0] = __double2float_ru(fmax(v0.x, fmax(v1.x, v2.x))) + pad;
+    box_max[3 * slot + 1] = __double2float_ru(fmax(v0.y, fmax(v1.y, v2.y))) + pad;
+    box_max[3 * slot + 2] = __double2float_ru(fmax(v0.z, fmax(v1.z, v2.z))) + pad;
+}
+
+__device__ __forceinline__ int delta_fn(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a != b) return __clz(a ^ b);
+    return 32 + __clz((uint32_t)i ^ (uint32_t)j);     // duplicate codes: fall back to the sorted position
+}
+
+// Karras 2012, one thread per internal node.  child code: >= 0 internal node, < 0 leaf ~code.
+__global__ void hierarchy_kernel(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ left,
+                                 int32_t* __restrict__ right, int32_t* __restrict__ parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_fn(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta_fn(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_fn(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_fn(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_fn(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int32_t lc = (lo == gamma) ? ~gamma : gamma;
+    int32_t rc = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+    left[i] = lc;
+    right[i] = rc;
+    parent[lc < 0 ? (n - 1) + (~lc) : lc] = i;
+    parent[rc < 0 ? (n - 1) + (~rc) : rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__device__ __forceinline__ int box_slot(int32_t code, int n) { return code < 0 ? (n - 1) + (~code) : code; }
+
+__global__ void refit_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                             const int32_t* __restrict__ parent, float* box_min, float* box_max,
+                             int* __restrict__ arrivals, int* __restrict__ max_depth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int depth = 0;
+    for (int p = parent[(n - 1) + i]; p >= 0; p = parent[p]) ++depth;
+    atomicMax(max_depth, depth);
+    int cur = parent[(n - 1) + i];
+    while (cur >= 0) {
+        __threadfence();
+        if (atomicAdd(&arrivals[cur], 1) == 0) return;       // first arrival: sibling subtree not done yet
+        __threadfence();
+        int a = box_slot(left[cur], n), b = box_slot(right[cur], n);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float lo = fminf(__ldcg(box_min + 3 * a + k), __ldcg(box_min + 3 * b + k));
+            float hi = fmaxf(__ldcg(box_max + 3 * a + k), __ldcg(box_max + 3 * b + k));
+            __stcg(box_min + 3 * cur + k, lo);
+            __stcg(box_max + 3 * cur + k, hi);
+        }
+        cur = parent[cur];
+    }
+}
+
+__global__ void emit_nodes_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                  const float* __restrict__ box_min, const float* __restrict__ box_max,
+                                  float4* __restrict__ nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int a = box_slot(left[i], n), b = box_slot(right[i], n);
+    float4 q0 = make_float4(box_min[3 * a], box_min[3 * a + 1], box_min[3 * a + 2], box_max[3 * a]);
+    float4 q1 = make_float4(box_max[3 * a + 1], box_max[3 * a + 2], box_min[3 * b], box_min[3 * b + 1]);
+    float4 q2 = make_float4(box_min[3 * b + 2], box_max[3 * b], box_max[3 * b + 1], box_max[3 * b + 2]);
+    float4 q3 = make_float4(__int_as_float(left[i]), __int_as_float(right[i]), 0.f, 0.f);
+    nodes[4 * i + 0] = q0; nodes[4 * i + 1] = q1; nodes[4 * i + 2] = q2; nodes[4 * i + 3] = q3;
+}
+
+__global__ void single_leaf_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
+                                        float4* __restrict__ nodes) {
+    // nF == 1: node 0 = (leaf 0 | empty box)
+    nodes[0] = make_float4(box_min[0], box_min[1], box_min[2], box_max[0]);
+    nodes[1] = make_float4(box_max[1], box_max[2], 1e30f, 1e30f);
+    nodes[2] = make_float4(1e30f, -1e30f, -1e30f, -1e30f);
+    nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
+}
+
+__global__ void normalise_cdf_kernel(double* cdf, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double total = cdf[n - 1];
+    if (i < n - 1) cdf[i] = cdf[i] / total;     // last element fixed up afterwards (it is read by everyone)
+}
+__global__ void finish_cdf_kernel(double* cdf, int64_t n, double* total_out) {
+    *total_out = cdf[n - 1];
+    cdf[n - 1] = 1.0;
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+// ---- library ---------------------------------------------------------------------------------------
+extern "C" int bt_version(void) { return 100; }
+
+extern "C" const char* bt_last_error(void) { return bt::g_err; }
+
+extern "C" int bt_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
+    cudaDeviceProp p;
+    BT_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+    return BT_OK;
+}
+
+extern "C" int bt_malloc(int device, int64_t bytes, void** d_ptr) {
+    BT_REQUIRE(d_ptr && bytes >= 0, "bad arguments");
+    BT_CUDA(cudaSetDevice(device));
+    BT_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return BT_OK;
+}
+extern "C" int bt_free(void* d_ptr) {
+    BT_CUDA(cudaFree(d_ptr));
+    return BT_OK;
+}
+extern "C" int bt_memcpy_h2d(void* d_dst, const void* h_src, int64_t bytes, void* stream) {
+    BT_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return BT_OK;
+}
+extern "C" int bt_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes, void* stream) {
+    BT_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return BT_OK;
+}
+extern "C" int bt_stream_sync(void* stream) {
+    BT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return BT_OK;
+}
+
+// ---- mesh ------------------------------------------------------------------------------------------
+static int mesh_free(MeshDev& m) {
+    cudaFree(m.verts); cudaFree(m.vnormals); cudaFree(m.faces); cudaFree(m.area_cdf);
+    cudaFree(m.nodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.leaf_tri);
+    m = MeshDev();
+    return BT_OK;
+}
+
+extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F, int64_t nF,
+                              const double* h_VN, int device, bt_mesh** out) {
+    BT_REQUIRE(h_V && h_F && out, "null pointer");
+    BT_REQUIRE(nV > 0 && nF > 0, "empty mesh");
+    BT_REQUIRE(nF < (1ll << 30), "too many triangles");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("bt_mesh_create: no CUDA device available (this library has no CPU fallback)");
+        return BT_E_NODEVICE;
+    }
+    BT_CUDA(cudaSetDevice(device));
+    for (int64_t i = 0; i < 3 * nF; ++i)
+        if (h_F[i] < 0 || h_F[i] >= nV) { set_error("bt_mesh_create: face index out of range"); return BT_E_INVALID; }
+
+    // host-side set-up: bounds, optional area-weighted vertex normals (io.load_mesh convention, io.py:96)
+    double lo[3] = {h_V[0], h_V[1], h_V[2]}, hi[3] = {h_V[0], h_V[1], h_V[2]};
+    for (int64_t v = 0; v < nV; ++v)
+        for (int k = 0; k < 3; ++k) {
+            double x = h_V[3 * v + k];
+            if (!(x == x) || fabs(x) > 1e30) { set_error("bt_mesh_create: non-finite vertex"); return BT_E_INVALID; }
+            lo[k] = x < lo[k] ? x : lo[k];
+            hi[k] = x > hi[k] ? x : hi[k];
+        }
+    std::vector<double> vn_host;
+    if (!h_VN) {
+        vn_host.assign(3 * nV, 0.0);
+        std::vector<double> cr(3 * nF);
+        for (int64_t f = 0; f < nF; ++f) {
+            d3 a = ld3(h_V + 3 * (int64_t)h_F[3 * f]), b = ld3(h_V + 3 * (int64_t)h_F[3 * f + 1]), c = ld3(h_V + 3 * (int64_t)h_F[3 * f + 2]);
+            st3(&cr[3 * f], cross3(sub3(b, a), sub3(c, a)));
+        }
+        for (int k = 0; k < 3; ++k)                     // same accumulation order as np.add.at(vn, F[:, k], cross)
+            for (int64_t f = 0; f < nF; ++f)
+                for (int c = 0; c < 3; ++c) vn_host[3 * (int64_t)h_F[3 * f + k] + c] += cr[3 * f + c];
+        for (int64_t v = 0; v < nV; ++v) {
+            double nn = norm3(ld3(&vn_host[3 * v]));
+            if (nn > 0) { for (int c = 0; c < 3; ++c) vn_host[3 * v + c] /= nn; }
+            else { vn_host[3 * v] = 0; vn_host[3 * v + 1] = 0; vn_host[3 * v + 2] = 1; }
+        }
+        h_VN = vn_host.data();
+    }
+
+    bt_mesh* h = new bt_mesh();
+    MeshDev& m = h->m;
+    m.device = device; m.nV = nV; m.nF = nF;
+    const int64_t nNodes = nF > 1 ? nF - 1 : 1;
+    cudaStream_t st = nullptr;
+#define MESH_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = cuda_fail(_e, #call, __FILE__, __LINE__); mesh_free(m); delete h; return rc; } } while (0)
+    MESH_TRY(cudaMalloc(&m.verts, sizeof(double) * 3 * nV));
+    MESH_TRY(cudaMalloc(&m.vnormals, sizeof(double) * 3 * nV));
+    MESH_TRY(cudaMalloc(&m.faces, sizeof(int32_t) * 3 * nF));
+    MESH_TRY(cudaMalloc(&m.area_cdf, sizeof(double) * nF));
+    MESH_TRY(cudaMalloc(&m.nodes, sizeof(float4) * 4 * nNodes));
+    MESH_TRY(cudaMalloc(&m.tri_rec, sizeof(double) * 16 * nF));
+    MESH_TRY(cudaMalloc(&m.tri_verts, sizeof(double) * 9 * nF));
+    MESH_TRY(cudaMalloc(&m.leaf_tri, sizeof(int32_t) * nF));
+    MESH_TRY(cudaMemcpy(m.verts, h_V, sizeof(double) * 3 * nV, cudaMemcpyHostToDevice));
+    MESH_TRY(cudaMemcpy(m.vnormals, h_VN, sizeof(double) * 3 * nV, cudaMemcpyHostToDevice));
+    MESH_TRY(cudaMemcpy(m.faces, h_F, sizeof(int32_t) * 3 * nF, cudaMemcpyHostToDevice));
+
+    cudaEvent_t ev0, ev1;
+    MESH_TRY(cudaEventCreate(&ev0));
+    MESH_TRY(cudaEventCreate(&ev1));
+    MESH_TRY(cudaEventRecord(ev0, st));
+
+    // scratch
+    uint32_t *keys = nullptr, *keys_sorted = nullptr;
+    int32_t *ids = nullptr, *ids_sorted = nullptr, *left = nullptr, *right = nullptr, *parent = nullptr;
+    float *box_min = nullptr, *box_max = nullptr;
+    int *arrivals = nullptr, *max_depth = nullptr;
+    double *area = nullptr, *total_area = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0, cub_bytes2 = 0;
+    const int n = (int)nF;
+    MESH_TRY(cudaMalloc(&keys, sizeof(uint32_t) * nF));
+    MESH_TRY(cudaMalloc(&keys_sorted, sizeof(uint32_t) * nF));
+    MESH_TRY(cudaMalloc(&ids, sizeof(int32_t) * nF));
+    MESH_TRY(cudaMalloc(&ids_sorted, sizeof(int32_t) * nF));
+    MESH_TRY(cudaMalloc(&left, sizeof(int32_t) * nNodes));
+    MESH_TRY(cudaMalloc(&right, sizeof(int32_t) * nNodes));
+    MESH_TRY(cudaMalloc(&parent, sizeof(int32_t) * (2 * nF)));
+    MESH_TRY(cudaMalloc(&box_min, sizeof(float) * 3 * 2 * nF));
+    MESH_TRY(cudaMalloc(&box_max, sizeof(float) * 3 * 2 * nF));
+    MESH_TRY(cudaMalloc(&arrivals, sizeof(int) * nNodes));
+    MESH_TRY(cudaMalloc(&max_depth, sizeof(int)));
+    MESH_TRY(cudaMalloc(&area, sizeof(double) * nF));
+    MESH_TRY(cudaMalloc(&total_area, sizeof(double)));
+    MESH_TRY(cudaMemsetAsync(arrivals, 0, sizeof(int) * nNodes, st));
+    MESH_TRY(cudaMemsetAsync(max_depth, 0, sizeof(int), st));
+    MESH_TRY(cudaMemsetAsync(parent, 0xFF, sizeof(int32_t) * (2 * nF), st));
+    MESH_TRY(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_sorted, ids, ids_sorted, n, 0, 30, st));
+    MESH_TRY(cub::DeviceScan::InclusiveSum(nullptr, cub_bytes2, area, m.area_cdf, n, st));
+    if (cub_bytes2 > cub_bytes) cub_bytes = cub_bytes2;
+    MESH_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1));
+
+    double ext[3], inv_ext[3], max_abs = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        ext[k] = hi[k] - lo[k];
+        inv_ext[k] = ext[k] > 0 ? 1.0 / ext[k] : 0.0;
+        max_abs = fmax(max_abs, fmax(fabs(lo[k]), fabs(hi[k])));
+    }
+    // conservative padding of every box: covers float32 rounding of the slab arithmetic and the 1e-13 /
+    // 1e-6 tolerances of the exact tests (DESIGN.md "broad phase is result-neutral")
+    const float pad = (float)(2e-5 * max_abs + 1e-9);
+    const int T = 256;
+    const int G = (int)ceil_div(nF, T);
+    morton_kernel<<<G, T, 0, st>>>(m.verts, m.faces, nF, make_double3(lo[0], lo[1], lo[2]),
+                                   make_double3(inv_ext[0], inv_ext[1], inv_ext[2]), keys, ids);
+    MESH_TRY(cudaGetLastError());
+    MESH_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, ids, ids_sorted, n, 0, 30, st));
+    leaf_kernel<<<G, T, 0, st>>>(m.verts, m.faces, ids_sorted, nF, pad, m.tri_rec, m.tri_verts, m.leaf_tri,
+                                 box_min, box_max, area);
+    MESH_TRY(cudaGetLastError());
+    if (nF > 1) {
+        hierarchy_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(keys_sorted, n, left, right, parent);
+        MESH_TRY(cudaGetLastError());
+        refit_kernel<<<G, T, 0, st>>>(n, left, right, parent, box_min, box_max, arrivals, max_depth);
+        MESH_TRY(cudaGetLastError());
+        emit_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, box_min, box_max, m.nodes);
+        MESH_TRY(cudaGetLastError());
+    } else {
+        single_leaf_node_kernel<<<1, 1, 0, st>>>(box_min, box_max, m.nodes);
+        MESH_TRY(cudaGetLastError());
+    }
+    MESH_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, cub_bytes, area, m.area_cdf, n, st));
+    normalise_cdf_kernel<<<G, T, 0, st>>>(m.area_cdf, nF);
+    MESH_TRY(cudaGetLastError());
+    finish_cdf_kernel<<<1, 1, 0, st>>>(m.area_cdf, nF, total_area);
+    MESH_TRY(cudaGetLastError());
+    MESH_TRY(cudaEventRecord(ev1, st));
+    MESH_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    MESH_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+    int depth = 0;
+    double total = 0.0;
+    MESH_TRY(cudaMemcpy(&depth, max_depth, sizeof(int), cudaMemcpyDeviceToHost));
+    MESH_TRY(cudaMemcpy(&total, total_area, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    cudaFree(keys); cudaFree(keys_sorted); cudaFree(ids); cudaFree(ids_sorted); cudaFree(left); cudaFree(right);
+    cudaFree(parent); cudaFree(box_min); cudaFree(box_max); cudaFree(arrivals); cudaFree(max_depth);
+    cudaFree(area); cudaFree(total_area); cudaFree(cub_tmp);
+#undef MESH_TRY
+    if (depth > 60) {
+        set_error("bt_mesh_create: LBVH depth %d exceeds the traversal stack (64)", depth);
+        mesh_free(m); delete h;
+        return BT_E_CAPACITY;
+    }
+    m.root = 0;
+    m.info.n_vertices = nV; m.info.n_triangles = nF; m.info.n_nodes = nNodes;
+    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 26 * nF) + sizeof(int32_t) * 4 * nF + 64 * nNodes);
+    m.info.surface_area = total;
+    m.info.build_ms = ms;
+    for (int k = 0; k < 3; ++k) { m.info.bounds_min[k] = (float)lo[k]; m.info.bounds_max[k] = (float)hi[k]; }
+    m.info.device = device;
+    m.info.max_depth = depth;
+    *out = h;
+    return BT_OK;
+}
+
+extern "C" int bt_mesh_destroy(bt_mesh* mesh) {
+    if (!mesh) return BT_OK;
+    cudaSetDevice(mesh->m.device);
+    mesh_free(mesh->m);
+    delete mesh;
+    return BT_OK;
+}
+
+extern "C" int bt_mesh_get_info(const bt_mesh* mesh, bt_mesh_info* info) {
+    BT_REQUIRE(mesh && info, "null pointer");
+    *info = mesh->m.info;
+    return BT_OK;
+}
+
+extern "C" int bt_mesh_copy_bvh(const bt_mesh* mesh, float* h_nodes, int32_t* h_leaf_tri) {
+    BT_REQUIRE(mesh, "null pointer");
+    BT_CUDA(cudaSetDevice(mesh->m.device));
+    if (h_nodes) BT_CUDA(cudaMemcpy(h_nodes, mesh->m.nodes, sizeof(float) * 16 * mesh->m.info.n_nodes, cudaMemcpyDeviceToHost));
+    if (h_leaf_tri) BT_CUDA(cudaMemcpy(h_leaf_tri, mesh->m.leaf_tri, sizeof(int32_t) * mesh->m.nF, cudaMemcpyDeviceToHost));
+    return BT_OK;
+}

@@ -1,0 +1,177 @@
+"""Device-side handles: meshes (with their LBVH), grippers, lookup tables.
+
+Thin RAII wrappers over the opaque C handles of libburgb200 plus a tiny cache so that repeated calls
+with the same mesh object do not rebuild the LBVH.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _native as nat
+from .mesh import as_mesh
+
+
+def device_index(device=None):
+    torch = nat.require_cuda()
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    return torch.device(device).index or 0
+
+
+class DeviceMesh:
+    """A triangle mesh resident on one GPU: float64 vertices / normals, per-triangle exact-test
+    records, and the LBVH (``bt_mesh_create``).  Also used for merged collision scenes."""
+
+    def __init__(self, vertices, triangles, vertex_normals=None, device=None):
+        nat.require_cuda()
+        self.device = device_index(device)
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        f = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+        vn = None if vertex_normals is None else np.ascontiguousarray(vertex_normals, dtype=np.float64).reshape(-1, 3)
+        if vn is not None and vn.shape != v.shape:
+            raise ValueError('vertex_normals must match vertices')
+        self.n_vertices, self.n_triangles = len(v), len(f)
+        handle = C.c_void_p()
+        nat.call('bt_mesh_create', v.ctypes.data, len(v), f.ctypes.data, len(f),
+                 None if vn is None else vn.ctypes.data, self.device, C.byref(handle))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, _destroy, 'bt_mesh_destroy', handle)
+
+    @classmethod
+    def from_mesh(cls, mesh, device=None):
+        m = as_mesh(mesh)
+        return cls(m.vertices, m.triangles, m.vertex_normals, device)
+
+    @classmethod
+    def from_meshes(cls, meshes, device=None):
+        """merge several meshes into one collision scene (vertex normals are irrelevant there)"""
+        verts, tris, off = [], [], 0
+        for m in meshes:
+            m = as_mesh(m, need_vertex_normals=False)
+            verts.append(np.asarray(m.vertices, dtype=np.float64))
+            tris.append(np.asarray(m.triangles, dtype=np.int64) + off)
+            off += len(m.vertices)
+        v, f = np.concatenate(verts), np.concatenate(tris).astype(np.int32)
+        return cls(v, f, np.zeros_like(v), device)
+
+    @property
+    def info(self):
+        out = nat.MeshInfo()
+        nat.call('bt_mesh_get_info', self.handle, C.byref(out))
+        return out
+
+    def bvh(self):
+        """(nodes float32 [n_nodes, 16], leaf_tri int32 [n_triangles]) -- validation only"""
+        inf = self.info
+        nodes = np.empty((inf.n_nodes, 16), dtype=np.float32)
+        leaf = np.empty(inf.n_triangles, dtype=np.int32)
+        nat.call('bt_mesh_copy_bvh', self.handle, nodes.ctypes.data, leaf.ctypes.data)
+        return nodes, leaf
+
+
+def _destroy(fn, handle):
+    try:
+        getattr(nat.load(), fn)(handle)
+    except Exception:
+        pass
+
+
+_mesh_cache = {}
+
+
+def cached_device_mesh(mesh, device=None):
+    """DeviceMesh for ``mesh`` keyed by object identity + vertex/triangle counts (rebuilds if the
+    mesh object was replaced)."""
+    dev = device_index(device)
+    m = as_mesh(mesh)
+    key = (id(mesh), dev)
+    tag = (len(m.vertices), len(m.triangles), float(np.asarray(m.vertices).sum()))
+    hit = _mesh_cache.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    dm = DeviceMesh(m.vertices, m.triangles, m.vertex_normals, dev)
+    _mesh_cache[key] = (tag, dm)
+    if len(_mesh_cache) > 16:
+        _mesh_cache.pop(next(iter(_mesh_cache)))
+    return dm
+
+
+class DeviceGripper:
+    """Gripper triangles in the TCP frame, grouped into parts (``bt_gripper_create``)."""
+
+    def __init__(self, tcp_triangles, part_slices=None, device=None):
+        nat.require_cuda()
+        self.device = device_index(device)
+        tris = np.ascontiguousarray(tcp_triangles, dtype=np.float64).reshape(-1, 3, 3)
+        if part_slices is None:
+            tris, part_slices = split_into_parts(tris)
+        parts = (nat.GripperPart * len(part_slices))()
+        for p, (b, e) in zip(parts, part_slices):
+            lo, hi = tris[b:e].min(axis=(0, 1)), tris[b:e].max(axis=(0, 1))
+            p.box_min[:] = lo.tolist()
+            p.box_max[:] = hi.tolist()
+            p.tri_begin, p.tri_end = b, e
+        self.n_triangles, self.n_parts = len(tris), len(part_slices)
+        handle = C.c_void_p()
+        nat.call('bt_gripper_create', tris.ctypes.data, len(tris), parts, len(part_slices), self.device,
+                 C.byref(handle))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, _destroy, 'bt_gripper_destroy', handle)
+
+    @classmethod
+    def from_gripper(cls, gripper, device=None):
+        if hasattr(gripper, 'tcp_triangles'):
+            tris = gripper.tcp_triangles()
+        else:
+            m = gripper.mesh
+            tf = np.asarray(gripper.tf_base_to_TCP, dtype=np.float64)
+            v = np.asarray(m.vertices, dtype=np.float64) @ tf[:3, :3].T + tf[:3, 3]
+            tris = v[np.asarray(m.triangles)]
+        # the simplified 3-box mesh is laid out box by box, 12 triangles each
+        slices = None
+        if getattr(gripper, '_mesh', 1) is None and len(tris) == 36:
+            slices = [(0, 12), (12, 24), (24, 36)]
+        return cls(tris, slices, device)
+
+
+def split_into_parts(tris, max_tris=16, max_parts=64):
+    """Spatial median split of a triangle soup into <= max_parts groups of consecutive triangles
+    (each part's tight TCP-frame box is what the device walks down the scene LBVH)."""
+    tris = np.asarray(tris, dtype=np.float64).reshape(-1, 3, 3)
+    per = max(max_tris, int(np.ceil(len(tris) / max_parts)))
+    order, slices = [], []
+
+    def rec(idx):
+        if len(idx) <= per:
+            slices.append((len(order), len(order) + len(idx)))
+            order.extend(idx.tolist())
+            return
+        c = tris[idx].mean(axis=1)
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        srt = idx[np.argsort(c[:, axis], kind='stable')]
+        rec(srt[:len(srt) // 2])
+        rec(srt[len(srt) // 2:])
+
+    rec(np.arange(len(tris)))
+    return tris[np.array(order)], slices
+
+
+_lut_cache = {}
+
+
+def acos_luts(device=None):
+    """(degrees, radians) float32[20001] tables of arccos(k / 1e4), k = -10000..10000, evaluated with
+    numpy exactly as ``np.rad2deg(np.arccos(np.around(x, 4)))`` does (reference metrics.py:49-56,
+    :75), so the transcendental is bit-identical to the reference by construction."""
+    torch = nat.require_cuda()
+    dev = device_index(device)
+    if dev not in _lut_cache:
+        k = np.arange(-10000, 10001, dtype=np.float32)
+        arg = np.around(k / np.float32(10000.0), 4).astype(np.float32)
+        rad = np.arccos(arg).astype(np.float32)
+        deg = np.rad2deg(rad).astype(np.float32)
+        _lut_cache[dev] = (torch.from_numpy(deg).to(f'cuda:{dev}'), torch.from_numpy(rad).to(f'cuda:{dev}'))
+    return _lut_cache[dev]

@@ -1,0 +1,155 @@
+"""Grasp-set metrics on the B200: pairwise SE(3) distances, coverage and precision.
+
+Host-side mirror of the reference module ``burg_toolkit/metrics.py`` -- same function names, arguments
+and return types -- with the arithmetic done by ``csrc/coverage.cu`` through the C ABI:
+
+  ========================  =======================  ==========================================
+  reference                 file:line                here
+  ========================  =======================  ==========================================
+  euclidean_distances       metrics.py:9-27          bt_pairwise_distances(which=0)
+  angular_distances         metrics.py:30-60         bt_pairwise_distances(which=1)
+  combined_distances        metrics.py:63-77         bt_pairwise_distances(which=2)
+  coverage_brute_force      metrics.py:141-158       bt_coverage(mode=0)
+  coverage                  metrics.py:161-229       bt_coverage(mode=1)   (kd-tree semantics)
+  (precision -- absent)     Eppner et al. 2019       coverage(query, reference)
+  ========================  =======================  ==========================================
+
+Results are float32 bit-identical to the reference's numpy evaluation (tests/test_gpu_metrics.py).
+Inputs may be ``Grasp`` / ``GraspSet`` objects, float32 ``[N, 14]`` numpy arrays, or CUDA float32
+tensors of that shape (already resident: no host->device copy is made).
+"""
+from timeit import default_timer as timer
+
+import numpy as np
+
+from . import _native as nat
+from . import device as dev
+from .grasp import Grasp, GraspSet
+
+
+def _rows(obj):
+    """-> float32 C-contiguous [N,14] numpy array, or a CUDA tensor passed through."""
+    if isinstance(obj, Grasp):
+        return np.ascontiguousarray(obj._grasp_array.reshape(1, 14), dtype=np.float32)
+    if isinstance(obj, GraspSet):
+        return np.ascontiguousarray(obj._gs_array, dtype=np.float32)
+    if hasattr(obj, '_grasp_array'):                       # reference Grasp object (duck typed)
+        return np.ascontiguousarray(np.asarray(obj._grasp_array).reshape(1, 14), dtype=np.float32)
+    if hasattr(obj, '_gs_array'):                          # reference GraspSet object
+        return np.ascontiguousarray(obj._gs_array, dtype=np.float32)
+    if isinstance(obj, np.ndarray):
+        if obj.ndim != 2 or obj.shape[1] != 14:
+            raise ValueError(f'expected [N, 14] rows, got {obj.shape}')
+        return np.ascontiguousarray(obj, dtype=np.float32)
+    torch = nat.require_cuda()
+    if isinstance(obj, torch.Tensor):
+        if not obj.is_cuda or obj.dtype != torch.float32 or obj.dim() != 2 or obj.shape[1] != 14:
+            raise ValueError('tensor inputs must be CUDA float32 [N, 14]')
+        return obj.contiguous()
+    raise TypeError(f'cannot interpret {type(obj)} as a grasp set')
+
+
+def _to_device(rows, device):
+    torch = nat.require_cuda()
+    if isinstance(rows, np.ndarray):
+        return torch.from_numpy(rows).to(f'cuda:{device}', non_blocking=False)
+    return rows
+
+
+def _device_of(*objs):
+    torch = nat.require_cuda()
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            return o.device.index
+    return torch.cuda.current_device()
+
+
+def _pairwise(graspset1, graspset2, which, weight=1000.0):
+    torch = nat.require_cuda()
+    a, b = _rows(graspset1), _rows(graspset2)
+    device = _device_of(a, b)
+    with torch.cuda.device(device):
+        da, db = _to_device(a, device), _to_device(b, device)
+        deg, rad = dev.acos_luts(device)
+        out = torch.empty((da.shape[0], db.shape[0]), dtype=torch.float32, device=da.device)
+        lut = None if which == 0 else (rad if which == 1 else deg)
+        nat.call('bt_pairwise_distances', nat.ptr(da), da.shape[0], nat.ptr(db), db.shape[0], which,
+                 float(weight), nat.ptr(lut), nat.ptr(out), nat.current_stream())
+        return out.cpu().numpy()
+
+
+def euclidean_distances(graspset1, graspset2):
+    """(N, M) float32 translation distances [m] (reference metrics.py:9-27)."""
+    return _pairwise(graspset1, graspset2, 0)
+
+
+def angular_distances(graspset1, graspset2):
+    """(N, M) float32 rotation distances [rad], ``arccos(around((tr(R1 R2^T) - 1) / 2, 4))``
+    (reference metrics.py:30-60); NaN where the rounded cosine leaves [-1, 1], as in the reference."""
+    out = _pairwise(graspset1, graspset2, 1)
+    if np.any(np.isnan(out)):
+        print(f'WARNING: {np.count_nonzero(np.isnan(out))} nan values in angular distances'
+              f'(despite rounding before arccos computation to avoid numerical issues)')
+    return out
+
+
+def combined_distances(graspset1, graspset2, weight=1000.0):
+    """(N, M) float32 ``weight * euclidean [m] + angular [deg]`` (reference metrics.py:63-77)."""
+    return _pairwise(graspset1, graspset2, 2, weight)
+
+
+def covered_mask(reference_grasp_set, query_grasp_set, epsilon=15.0, kd_semantics=True, algo='auto',
+                 return_device=False):
+    """bool[N]: which reference grasps have a query grasp within ``epsilon`` (B200 extension; the
+    reference only returns the fraction).
+
+    kd_semantics=True  follows ``metrics.coverage`` (candidates restricted by the float64 radius test of
+                       cKDTree.query_ball_tree, metrics.py:203-220),
+    kd_semantics=False follows ``metrics.coverage_brute_force`` (metrics.py:157).
+    algo: 'tiles' (all pairs), 'grid' (uniform-grid culled) or 'auto'."""
+    torch = nat.require_cuda()
+    a, b = _rows(reference_grasp_set), _rows(query_grasp_set)
+    device = _device_of(a, b)
+    with torch.cuda.device(device):
+        da, db = _to_device(a, device), _to_device(b, device)
+        n, m = da.shape[0], db.shape[0]
+        if algo == 'auto':
+            algo = 'grid' if n * m >= (1 << 22) else 'tiles'
+        if algo not in ('tiles', 'grid'):
+            raise ValueError("algo must be 'auto', 'tiles' or 'grid'")
+        deg, _ = dev.acos_luts(device)
+        covered = torch.empty(((n + 3) // 4) * 4, dtype=torch.uint8, device=da.device)
+        count = torch.empty(1, dtype=torch.int64, device=da.device)
+        nat.call('bt_coverage', nat.ptr(da), n, nat.ptr(db), m, float(epsilon), nat.ptr(deg),
+                 1 if kd_semantics else 0, 1 if algo == 'grid' else 0, nat.ptr(covered), nat.ptr(count),
+                 nat.current_stream())
+        if return_device:
+            return covered[:n], count
+        return covered[:n].cpu().numpy().astype(bool)
+
+
+def coverage_brute_force(reference_grasp_set, query_grasp_set, epsilon=15.0):
+    """Fraction of reference grasps covered by the query set, full-matrix semantics
+    (reference metrics.py:141-158)."""
+    n = len(_rows(reference_grasp_set))
+    _, count = covered_mask(reference_grasp_set, query_grasp_set, epsilon, kd_semantics=False, return_device=True)
+    return int(count.item()) / n
+
+
+def coverage(reference_grasp_set, query_grasp_set, epsilon=15.0, print_timings=False):
+    """Fraction of reference grasps covered by the query set, kd-tree semantics
+    (reference metrics.py:161-229)."""
+    t1 = timer()
+    n = len(_rows(reference_grasp_set))
+    _, count = covered_mask(reference_grasp_set, query_grasp_set, epsilon, kd_semantics=True, return_device=True)
+    covered = int(count.item())
+    if print_timings:
+        print('it took:')
+        print(timer() - t1, 'seconds on the GPU (upload, pairwise tiles, count)')
+    return covered / n
+
+
+def precision(reference_grasp_set, query_grasp_set, epsilon=15.0):
+    """Fraction of QUERY grasps that lie within ``epsilon`` of some reference grasp, i.e.
+    ``coverage`` with the roles swapped (Eppner et al. 2019; the reference has no such function)."""
+    return coverage(query_grasp_set, reference_grasp_set, epsilon)

@@ -1,0 +1,439 @@
+"""Antipodal grasp sampling on the B200.
+
+Host-side mirror of the reference's ``burg_toolkit/sampling.py`` for the hot path: the same class
+(``AntipodalGraspSampler`` with the same public attributes and defaults, sampling.py:57-70), the same
+methods (``sample`` :185-352, ``check_collisions`` :354-397, ``construct_grasp_set`` :132-183,
+``construct_halfspace_grasp_set`` :72-130) and ``rays_within_cone`` (:17-48).  All arithmetic runs in the
+CUDA kernels of ``csrc/`` through the C ABI (``include/burg_b200.h``); there is no CPU fallback.
+
+Reference quirks that are kept on purpose (SURVEY.md TL;DR 3):
+  * the width filter is an OR and therefore a no-op for sane parameters (sampling.py:249-251);
+  * ``sample(n)`` returns >= n grasps: whole reference points are consumed (sampling.py:220);
+  * every surface crossing of a ray is a candidate; the origin triangle is removed by
+    ``np.isclose(loc, p_r, atol=1e-11)`` whose rtol (1e-5) is relative to p_r (sampling.py:239);
+  * with ``max_targets_per_ref_point > 1`` poses are orientation-major while widths / contacts are
+    target-major (sampling.py:177 vs :181, :344).
+
+Two execution modes:
+  * batch (default): reference points are processed thousands at a time; random numbers come from the
+    device (Philox) and are keyed by a seed drawn from ``np.random`` (so ``np.random.seed`` makes runs
+    reproducible), results are cut at the first reference point where >= n grasps exist -- the same
+    stopping rule as the reference's loop.
+  * ``reference_rng = True``: one reference point per launch, consuming the legacy global numpy RNG in
+    exactly the reference's order (ray angles, target shuffle, frame vector).  With identical surface
+    samples (``surface_samples``) this reproduces the reference's output; used by the parity tests.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+from . import device as dev
+from . import util
+from .grasp import GraspSet
+from .mesh import as_mesh
+
+
+def rays_within_cone(axis, angle, n=10, uniform_on_plane=False):
+    """``n`` unit ray directions inside the cone around ``axis`` with half-angle ``angle`` [rad]
+    (reference sampling.py:17-48).  Host version: consumes ``np.random`` like the reference (azimuth
+    draws first, then inclinations); the batch path uses the device kernel ``bt_cone_rays`` instead."""
+    azimuth = np.random.uniform(0, 2 * np.pi, n)
+    if uniform_on_plane:
+        inclination = np.arctan(np.random.uniform(0, np.tan(angle), n))
+    else:
+        inclination = np.random.uniform(0, angle, n)
+    cartesian = np.empty((n, 3, 1))
+    cartesian[:, 0, 0] = np.sin(inclination) * np.cos(azimuth)
+    cartesian[:, 1, 0] = np.sin(inclination) * np.sin(azimuth)
+    cartesian[:, 2, 0] = np.cos(inclination)
+    rot_mat = util.rotation_to_align_vectors([0, 0, 1], axis)
+    return np.matmul(rot_mat, cartesian)[:, :, 0]
+
+
+def _orientation_tables(n_orientations, halfspace):
+    """cos / sin of the orientation angles, evaluated with numpy exactly as the reference does
+    (sampling.py:169-174: arange(0, 2pi, 2pi/n); :106: linspace(0, pi, n))."""
+    if halfspace:
+        theta = np.linspace(0, np.pi, num=n_orientations)
+    else:
+        theta = np.arange(0, 2 * np.pi, 2 * np.pi / n_orientations)[:n_orientations]
+    return np.ascontiguousarray(np.cos(theta)), np.ascontiguousarray(np.sin(theta))
+
+
+class CastResult:
+    """Per-ray hit lists of one ``bt_ags_cast`` launch, resident on the device."""
+
+    def __init__(self, hit_count, hits, overflow, n_ref, n_rays, cap):
+        self.hit_count, self.hits, self.overflow = hit_count, hits, overflow
+        self.n_ref, self.n_rays, self.cap = n_ref, n_rays, cap
+
+    def to_host(self):
+        """-> (hit_count int32 [n_ref, n_rays], hits structured [n_ref, n_rays, cap] (nat.HIT_DTYPE))"""
+        cnt = self.hit_count.cpu().numpy().reshape(self.n_ref, self.n_rays)
+        raw = self.hits.cpu().numpy().view(nat.HIT_DTYPE).reshape(self.n_ref, self.n_rays, self.cap)
+        return cnt, raw
+
+    def flat_hits(self):
+        """canonical flat list: (ref, ray, hit records) ordered by (ref, ray, t)"""
+        cnt, raw = self.to_host()
+        sel = np.arange(self.cap)[None, None, :] < cnt[:, :, None]
+        ref_idx, ray_idx, _ = np.nonzero(sel)
+        return ref_idx, ray_idx, raw[sel]
+
+
+class AntipodalGraspSampler:
+    """A sampler for antipodal grasps: looks for two contact points that satisfy the antipodal
+    constraint for a friction coefficient ``mu`` (reference sampling.py:51-397)."""
+
+    def __init__(self):
+        # -- the reference's configuration surface (sampling.py:57-70) --
+        self.gripper = None
+        self.mu = 0.25
+        self.n_orientations = 12
+        self.n_rays = 100
+        self.min_grasp_width = 0.002
+        self.width_tolerance = 0.005
+        self.max_targets_per_ref_point = 1
+        self.only_grasp_from_above = False
+        self.no_contact_below_z = None
+        self.verbose = True
+        self.verbose_debug = False
+        self.mesh = None
+        # -- B200 extensions --
+        self.device = None                  # CUDA device index (default: current)
+        self.reference_rng = False          # True: sequential mode that consumes np.random like the reference
+        self.surface_samples = None         # optional (n_sample, 6) [point | normal] override of stage S1
+        self.max_hits_per_ray = 8           # per-ray hit list capacity (doubled automatically on overflow)
+        self.max_passes = 10                # cap on wrap-arounds of the reference-point list (the reference spins forever)
+        self.last_stats = {}
+
+    # -----------------------------------------------------------------------------------------------
+    # device plumbing
+    # -----------------------------------------------------------------------------------------------
+    def _device(self):
+        return dev.device_index(self.device)
+
+    def _device_mesh(self):
+        if self.mesh is None:
+            raise ValueError('AntipodalGraspSampler.mesh is not set')
+        return dev.cached_device_mesh(self.mesh, self._device())
+
+    def _params(self, cap=None):
+        p = nat.AgsParams()
+        p.angle_max = float(np.arctan(self.mu))
+        p.opening_width = float(self.gripper.opening_width) if self.gripper is not None else 0.08
+        p.width_tolerance = float(self.width_tolerance)
+        p.min_grasp_width = float(self.min_grasp_width)
+        p.use_below_z = 0 if self.no_contact_below_z is None else 1
+        p.no_contact_below_z = 0.0 if self.no_contact_below_z is None else float(self.no_contact_below_z)
+        p.max_hits_per_ray = int(cap or self.max_hits_per_ray)
+        return p
+
+    def _tensor(self, array, dtype):
+        torch = nat.require_cuda()
+        if isinstance(array, torch.Tensor):
+            return array.to(device=f'cuda:{self._device()}', dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(array)).to(device=f'cuda:{self._device()}', dtype=dtype)
+
+    # -----------------------------------------------------------------------------------------------
+    # stages (each is one C-ABI call; inputs may be numpy arrays or CUDA tensors)
+    # -----------------------------------------------------------------------------------------------
+    def sample_surface(self, n, seed):
+        """S1: ``n`` area-weighted surface points + triangle normals -> (pts, nrm, tri) CUDA tensors."""
+        torch = nat.require_cuda()
+        dm = self._device_mesh()
+        with torch.cuda.device(dm.device):
+            pts = torch.empty((n, 3), dtype=torch.float64, device='cuda')
+            nrm = torch.empty((n, 3), dtype=torch.float64, device='cuda')
+            tri = torch.empty((n,), dtype=torch.int32, device='cuda')
+            nat.call('bt_sample_surface', dm.handle, n, int(seed), nat.ptr(pts), nat.ptr(nrm), nat.ptr(tri),
+                     nat.current_stream())
+        return pts, nrm, tri
+
+    def cone_rays(self, ref_normals, seed):
+        """S2: [n_ref, n_rays, 3] directions in the friction cone about ``-normal`` (device RNG)."""
+        torch = nat.require_cuda()
+        nrm = self._tensor(ref_normals, torch.float64)
+        with torch.cuda.device(nrm.device):
+            dirs = torch.empty((nrm.shape[0], self.n_rays, 3), dtype=torch.float64, device=nrm.device)
+            nat.call('bt_cone_rays', nat.ptr(nrm), nrm.shape[0], int(self.n_rays), float(np.arctan(self.mu)),
+                     int(seed), nat.ptr(dirs), nat.current_stream())
+        return dirs
+
+    def cast(self, ref_points, directions, cap=None):
+        """R1-R6: all crossings of every ray with ``self.mesh`` + the per-hit antipodal filters."""
+        torch = nat.require_cuda()
+        dm = self._device_mesh()
+        pts = self._tensor(ref_points, torch.float64).reshape(-1, 3)
+        dirs = self._tensor(directions, torch.float64)
+        n_ref = pts.shape[0]
+        n_rays = dirs.numel() // (3 * n_ref) if n_ref else self.n_rays
+        cap = int(cap or self.max_hits_per_ray)
+        with torch.cuda.device(dm.device):
+            while True:
+                params = self._params(cap)
+                hit_count = torch.empty((n_ref * n_rays,), dtype=torch.int32, device='cuda')
+                hits = torch.empty((n_ref * n_rays * cap, 72), dtype=torch.uint8, device='cuda')
+                overflow = torch.zeros((1,), dtype=torch.int32, device='cuda')
+                nat.call('bt_ags_cast', dm.handle, nat.ptr(pts), nat.ptr(dirs), n_ref, n_rays, C.byref(params),
+                         nat.ptr(hit_count), nat.ptr(hits), nat.ptr(overflow), nat.current_stream())
+                if cap >= 32 or int(overflow.item()) == 0:
+                    break
+                cap = min(32, cap * 2)                   # a ray crossed more surfaces than the list holds
+        return CastResult(hit_count, hits, overflow, n_ref, n_rays, cap)
+
+    def select(self, cast, seed):
+        """R7: per reference point up to ``max_targets_per_ref_point`` valid hits -> contact pairs."""
+        torch = nat.require_cuda()
+        k = int(self.max_targets_per_ref_point)
+        cap_pairs = max(1, cast.n_ref * k)
+        with torch.cuda.device(cast.hits.device):
+            pair_count = torch.empty((max(cast.n_ref, 1),), dtype=torch.int32, device='cuda')
+            pair_offset = torch.zeros((cast.n_ref + 1,), dtype=torch.int64, device='cuda')
+            pair_ref = torch.empty((cap_pairs,), dtype=torch.int32, device='cuda')
+            pair_q = torch.empty((cap_pairs, 3), dtype=torch.float64, device='cuda')
+            nat.call('bt_ags_select', nat.ptr(cast.hit_count), nat.ptr(cast.hits), cast.n_ref, cast.n_rays, cast.cap,
+                     k, int(seed), nat.ptr(pair_count), nat.ptr(pair_offset), nat.ptr(pair_ref), nat.ptr(pair_q),
+                     cap_pairs, nat.current_stream())
+        return pair_count, pair_offset, pair_ref, pair_q, cap_pairs
+
+    def expand(self, ref_points, pair_offset, pair_ref, pair_q, frame_vecs, cap_pairs):
+        """O1/O2: contact pairs -> n_orientations grasps each (float32 [*,14] rows + float64 contacts)."""
+        torch = nat.require_cuda()
+        pts = self._tensor(ref_points, torch.float64).reshape(-1, 3)
+        n_o = int(self.n_orientations)
+        half = 1 if self.only_grasp_from_above else 0
+        cos_t, sin_t = _orientation_tables(n_o, half)
+        fv = None if frame_vecs is None else self._tensor(frame_vecs, torch.float64)
+        with torch.cuda.device(pts.device):
+            gs = torch.zeros((cap_pairs * n_o, 14), dtype=torch.float32, device='cuda')
+            contacts = torch.zeros((cap_pairs * n_o, 2, 3), dtype=torch.float64, device='cuda')
+            nat.call('bt_expand_orientations', nat.ptr(pts), nat.ptr(pair_offset), nat.ptr(pair_ref), nat.ptr(pair_q),
+                     nat.ptr(fv), pts.shape[0], cap_pairs, n_o, half, cos_t.ctypes.data, sin_t.ctypes.data,
+                     nat.ptr(gs), nat.ptr(contacts), nat.current_stream())
+        return gs, contacts
+
+    def frame_vectors(self, n, seed):
+        torch = nat.require_cuda()
+        with torch.cuda.device(self._device()):
+            out = torch.empty((n, 3), dtype=torch.float64, device='cuda')
+            nat.call('bt_random_unit_vectors', n, int(seed), nat.ptr(out), nat.current_stream())
+        return out
+
+    def evaluate_candidates(self, ref_points, ref_normals=None, directions=None, seed=1, frame_vecs=None,
+                            choice_seed=0):
+        """Whole device pipeline for a batch of reference points: rays -> cast + filters -> target choice ->
+        orientation expansion.  ``directions`` / ``frame_vecs`` may be host-seeded (parity runs) or None
+        (generated on the device).  -> dict of CUDA tensors; nothing is copied to the host."""
+        torch = nat.require_cuda()
+        pts = self._tensor(ref_points, torch.float64).reshape(-1, 3)
+        n_ref = pts.shape[0]
+        if directions is None:
+            if ref_normals is None:
+                raise ValueError('either directions or ref_normals is required')
+            directions = self.cone_rays(ref_normals, seed)
+        cast = self.cast(pts, directions)
+        pair_count, pair_offset, pair_ref, pair_q, cap_pairs = self.select(cast, choice_seed)
+        if frame_vecs is None and not self.only_grasp_from_above:
+            frame_vecs = self.frame_vectors(n_ref, seed + 0x9E3779B9)
+        gs, contacts = self.expand(pts, pair_offset, pair_ref, pair_q, frame_vecs, cap_pairs)
+        return dict(cast=cast, pair_count=pair_count, pair_offset=pair_offset, pair_ref=pair_ref, pair_q=pair_q,
+                    gs=gs, contacts=contacts, n_ref=n_ref, cap_pairs=cap_pairs, directions=directions)
+
+    # -----------------------------------------------------------------------------------------------
+    # reference API
+    # -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def construct_grasp_set(reference_point, target_points, n_orientations, frame_vec=None, device=None):
+        """Grasps at the centre between ``reference_point`` and each target, x-axis towards the target,
+        ``n_orientations`` rotations about it (reference sampling.py:132-183).  The random unit vector of
+        sampling.py:157 is drawn from ``np.random`` unless ``frame_vec`` is given."""
+        return _construct(reference_point, target_points, n_orientations, False, frame_vec, device)
+
+    @staticmethod
+    def construct_halfspace_grasp_set(reference_point, target_points, n_orientations, device=None):
+        """Same, approaching only from the upper half space (reference sampling.py:72-130)."""
+        return _construct(reference_point, target_points, n_orientations, True, None, device)
+
+    def _ref_points(self, n):
+        """stage S1 + shuffle + z filter (sampling.py:199-205) -> (n_sample, 6) float64 CUDA tensor"""
+        torch = nat.require_cuda()
+        m = as_mesh(self.mesh)
+        n_sample = int(np.max([n, 1000, len(m.triangles)]))
+        if self.surface_samples is not None:
+            ref = np.array(self.surface_samples, dtype=np.float64)
+            np.random.shuffle(ref)                                  # sampling.py:201 (legacy global RNG)
+            ref = torch.from_numpy(ref).to(f'cuda:{self._device()}')
+        else:
+            seed = int(np.random.randint(1, 2 ** 62))
+            pts, nrm, _ = self.sample_surface(n_sample, seed)
+            ref = torch.cat([pts, nrm], dim=1)
+            gen = torch.Generator(device=ref.device)
+            gen.manual_seed(seed)
+            ref = ref[torch.randperm(n_sample, device=ref.device, generator=gen)]
+        if self.no_contact_below_z is not None:
+            ref = ref[ref[:, 2] > self.no_contact_below_z]
+        return ref.contiguous()
+
+    def sample(self, n=10):
+        """-> (GraspSet with >= n grasps, contacts float64 (N, 2, 3))  (reference sampling.py:185-352)."""
+        if self.verbose:
+            print('preparing to sample grasps...')
+        torch = nat.require_cuda()
+        ref = self._ref_points(n)
+        if self.verbose:
+            print(f'sampled {len(ref)} first contact point candidates, beginning to find grasps.')
+        if len(ref) == 0:
+            raise ValueError('no reference points left after the z filter')
+        if self.reference_rng:
+            return self._sample_sequential(n, ref.cpu().numpy())
+        n_o, k = int(self.n_orientations), int(self.max_targets_per_ref_point)
+        seed = int(np.random.randint(1, 2 ** 62))
+        rows, contacts, total = [], [], 0
+        cursor, consumed, n_refs_used = 0, 0, 0
+        batch = max(64, int(np.ceil(n / (n_o * 0.8))) + 16)
+        while total < n and consumed < self.max_passes * len(ref):
+            idx = (cursor + torch.arange(batch, device=ref.device)) % len(ref)
+            pts, nrm = ref[idx, 0:3].contiguous(), ref[idx, 3:6].contiguous()
+            out = self.evaluate_candidates(pts, nrm, seed=seed + consumed, choice_seed=seed + 7 * consumed + 1)
+            per_ref = out['pair_count'][:batch].to(torch.int64) * n_o
+            cum = torch.cumsum(per_ref, 0)
+            need = n - total
+            reached = torch.nonzero(cum >= need)
+            take_refs = int(reached[0].item()) + 1 if len(reached) else batch
+            take_rows = int(cum[take_refs - 1].item())
+            rows.append(out['gs'][:take_rows].cpu().numpy())
+            contacts.append(out['contacts'][:take_rows].cpu().numpy())
+            total += take_rows
+            n_refs_used += take_refs
+            cursor = (cursor + take_refs) % len(ref)
+            consumed += take_refs
+            batch = min(1 << 16, max(64, int((n - total) / max(total / max(n_refs_used, 1), 1e-3)) + 16))
+        self.last_stats = dict(ref_points_used=n_refs_used, candidates=n_refs_used * self.n_rays, grasps=total,
+                               exhausted=total < n)
+        if total < n and self.verbose:
+            print(f'warning: only {total} grasps found after {self.max_passes} passes over the reference points')
+        gs = GraspSet.from_array(np.concatenate(rows) if rows else np.zeros((0, 14), dtype=np.float32))
+        return gs, (np.concatenate(contacts) if contacts else np.empty((0, 2, 3)))
+
+    def _sample_sequential(self, n, ref_points):
+        """the reference's loop verbatim in structure (sampling.py:215-352), one launch per reference point,
+        with the host consuming np.random in the reference's order."""
+        angle = np.arctan(self.mu)
+        gs = GraspSet()
+        gs_contacts = np.empty((0, 2, 3))
+        i_ref, iterations = 0, 0
+        while len(gs) < n and iterations < self.max_passes * len(ref_points):
+            iterations += 1
+            p_r, n_r = ref_points[i_ref, 0:3], ref_points[i_ref, 3:6]
+            i_ref = (i_ref + 1) % len(ref_points)
+            ray_directions = rays_within_cone(-n_r, angle, self.n_rays)
+            _, _, hits = self.cast(p_r.reshape(1, 3), ray_directions.reshape(1, -1, 3)).flat_hits()
+            locations = hits['loc'][hits['flags'] == 0]
+            if len(locations) == 0:
+                continue
+            if len(locations) > self.max_targets_per_ref_point:
+                indices = np.arange(len(locations))
+                np.random.shuffle(indices)
+                locations = locations[indices[:self.max_targets_per_ref_point]]
+            if self.only_grasp_from_above:
+                grasps = self.construct_halfspace_grasp_set(p_r, locations, self.n_orientations, device=self._device())
+            else:
+                grasps = self.construct_grasp_set(p_r, locations, self.n_orientations, device=self._device())
+            contacts = np.empty((len(locations), 2, 3))
+            contacts[:, 0] = p_r
+            contacts[:, 1] = locations
+            gs_contacts = np.concatenate([gs_contacts, np.repeat(contacts, self.n_orientations, axis=0)], axis=0)
+            gs.add(grasps)
+        self.last_stats = dict(ref_points_used=iterations, candidates=iterations * self.n_rays, grasps=len(gs),
+                               exhausted=len(gs) < n)
+        return gs, gs_contacts
+
+    def check_collisions(self, graspset, use_width=True, width_tolerance=0.01, additional_objects=None,
+                         exclude_shape=False):
+        """bool[N]: does the gripper mesh, posed at each grasp (and squeezed in x to the grasp width plus
+        ``width_tolerance`` if ``use_width``), intersect the object and/or ``additional_objects``
+        (reference sampling.py:354-397)."""
+        if not additional_objects and exclude_shape:
+            raise ValueError('no collision objects specified.')
+        torch = nat.require_cuda()
+        device = self._device()
+        meshes = ([] if exclude_shape else [self.mesh]) + list(additional_objects or [])
+        scene = self._scene(meshes, device)
+        gripper = self._device_gripper(device)
+        rows = graspset if isinstance(graspset, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(graspset._gs_array, dtype=np.float32)).to(f'cuda:{device}')
+        if self.verbose:
+            print('checking collisions...')
+        colliding = collide_rows(scene, gripper, rows, float(self.gripper.opening_width), float(width_tolerance),
+                                 bool(use_width))
+        return colliding.cpu().numpy().astype(bool)
+
+    def _scene(self, meshes, device):
+        key = tuple(id(m) for m in meshes)
+        cache = getattr(self, '_scene_cache', None)
+        if cache is not None and cache[0] == key and cache[1].device == device:
+            return cache[1]
+        scene = dev.cached_device_mesh(meshes[0], device) if len(meshes) == 1 else dev.DeviceMesh.from_meshes(meshes, device)
+        self._scene_cache = (key, scene, meshes)
+        return scene
+
+    def _device_gripper(self, device):
+        cache = getattr(self, '_gripper_cache', None)
+        if cache is not None and cache[0] is self.gripper and cache[1].device == device:
+            return cache[1]
+        g = dev.DeviceGripper.from_gripper(self.gripper, device)
+        self._gripper_cache = (self.gripper, g)
+        return g
+
+
+def collide_rows(scene, gripper, rows, opening_width, width_tolerance, use_width, n_valid=None):
+    """K1 on device-resident float32 [N,14] rows -> uint8 CUDA tensor [N] (1 = colliding)."""
+    torch = nat.require_cuda()
+    n = rows.shape[0]
+    with torch.cuda.device(rows.device):
+        out = torch.empty((((n + 3) // 4) * 4,), dtype=torch.uint8, device=rows.device)
+        nat.call('bt_collide', scene.handle, gripper.handle, nat.ptr(rows), n, nat.ptr(n_valid), opening_width,
+                 width_tolerance, 1 if use_width else 0, nat.ptr(out), nat.current_stream())
+    return out[:n]
+
+
+def compact_rows(mask, keep_value, rows, contacts=None, n_valid=None):
+    """ordered stream compaction of grasp rows (and contacts) -> (rows, contacts, count tensor)"""
+    torch = nat.require_cuda()
+    n = rows.shape[0]
+    with torch.cuda.device(rows.device):
+        out_rows = torch.empty_like(rows)
+        out_contacts = None if contacts is None else torch.empty_like(contacts)
+        count = torch.zeros((1,), dtype=torch.int64, device=rows.device)
+        nat.call('bt_compact', nat.ptr(mask), int(keep_value), nat.ptr(rows), nat.ptr(contacts), n, nat.ptr(n_valid),
+                 nat.ptr(out_rows), nat.ptr(out_contacts), nat.ptr(count), nat.current_stream())
+    return out_rows, out_contacts, count
+
+
+def _construct(reference_point, target_points, n_orientations, halfspace, frame_vec, device):
+    torch = nat.require_cuda()
+    d = dev.device_index(device)
+    p_r = np.reshape(np.asarray(reference_point, dtype=np.float64), (1, 3))
+    targets = np.reshape(np.asarray(target_points, dtype=np.float64), (-1, 3))
+    k = len(targets)
+    if not halfspace and frame_vec is None:
+        x_axis = (targets - p_r) / np.linalg.norm(targets - p_r, axis=-1)[:, np.newaxis]
+        y_axis = np.zeros(x_axis.shape)
+        while (np.linalg.norm(y_axis, axis=-1) == 0).any():          # sampling.py:156-158
+            frame_vec = util.generate_random_unit_vector()
+            y_axis = np.cross(x_axis, frame_vec)
+    cos_t, sin_t = _orientation_tables(n_orientations, halfspace)
+    with torch.cuda.device(d):
+        pts = torch.from_numpy(p_r).cuda()
+        q = torch.from_numpy(np.ascontiguousarray(targets)).cuda()
+        off = torch.tensor([0, k], dtype=torch.int64, device='cuda')
+        ref = torch.zeros((max(k, 1),), dtype=torch.int32, device='cuda')
+        fv = None if halfspace else torch.from_numpy(np.asarray(frame_vec, dtype=np.float64).reshape(1, 3)).cuda()
+        gs = torch.zeros((k * n_orientations, 14), dtype=torch.float32, device='cuda')
+        if k:
+            nat.call('bt_expand_orientations', nat.ptr(pts), nat.ptr(off), nat.ptr(ref), nat.ptr(q), nat.ptr(fv), 1, k,
+                     int(n_orientations), 1 if halfspace else 0, cos_t.ctypes.data, sin_t.ctypes.data, nat.ptr(gs),
+                     None, nat.current_stream())
+        return GraspSet.from_array(gs.cpu().numpy())

@@ -1,0 +1,202 @@
+/*
+ * burg_b200.h -- C ABI of libburgb200.so: the B200 (sm_100a) implementation of burg_toolkit's
+ * antipodal-grasp-sampling and grasp-set-metric hot path.
+ *
+ * The reference (mrudorfer/burg-toolkit) is pure Python and has no FFI of its own; its boundary for
+ * this path is the Python API (burg_toolkit/sampling.py:51-397, burg_toolkit/metrics.py:9-229).  Each
+ * entry point below names the reference interface whose arithmetic it replaces; the Python mirror
+ * (burg_toolkit_b200/sampling.py, metrics.py) binds them with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on failure (BT_E_*); bt_last_error() gives the message
+ *     (thread-local).  No function ever falls back to the CPU.
+ *   - pointers named h_* are HOST memory, d_* are DEVICE memory on the mesh's / current device; plain
+ *     C types only.  Arrays are row-major and densely packed.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ *     asynchronous w.r.t. the host unless stated ("synchronises").
+ *   - scratch memory comes from the stream-ordered allocator (cudaMallocAsync) on `stream`.
+ */
+#ifndef BURG_B200_H
+#define BURG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BT_API __attribute__((visibility("default")))
+#else
+#define BT_API
+#endif
+
+#define BT_OK            0
+#define BT_E_INVALID    -1   /* bad argument                                   */
+#define BT_E_CUDA       -2   /* CUDA runtime error (message has the details)   */
+#define BT_E_CAPACITY   -3   /* an output capacity was exceeded                */
+#define BT_E_NODEVICE   -4   /* no CUDA device / wrong architecture            */
+
+/* hit flags written by bt_ags_cast (a hit is a valid antipodal target iff flags == 0) */
+#define BT_HIT_ORIGIN    1u  /* sampling.py:239   hit coincides with the reference point          */
+#define BT_HIT_WIDTH     2u  /* sampling.py:249   fails (d <= ow - tol) | (d >= min_width)  (an OR) */
+#define BT_HIT_SIGN      4u  /* sampling.py:295   sign(d . n) <= 0                                 */
+#define BT_HIT_CONE      8u  /* sampling.py:305   angle > atan(mu)                                 */
+#define BT_HIT_BELOW_Z  16u  /* sampling.py:316   z <= no_contact_below_z                          */
+
+typedef struct bt_mesh bt_mesh;     /* device-resident triangle soup + LBVH (one object, or a merged scene) */
+
+/* One ray/triangle crossing as the reference sees it after trimesh's intersects_location
+ * (sampling.py:231-232) plus the per-hit quantities of sampling.py:239-319.  72 bytes. */
+typedef struct bt_hit {
+    double   loc[3];    /* intersection location                                  */
+    double   nrm[3];    /* interpolated vertex normal (mesh_processing.py:110-153) */
+    double   t;         /* ray parameter  proj_ori / proj_dir                      */
+    double   angle;     /* atan(|d x n| / d . n)   (util.py:46-82), radians        */
+    int32_t  tri;       /* triangle index in the caller's face array               */
+    uint32_t flags;     /* BT_HIT_* bits                                           */
+} bt_hit;
+
+typedef struct bt_ags_params {      /* AntipodalGraspSampler attributes, sampling.py:57-70 */
+    double  angle_max;              /* np.arctan(mu), computed by the caller (sampling.py:211)   */
+    double  opening_width;          /* gripper.opening_width                                      */
+    double  width_tolerance;        /* default 0.005                                              */
+    double  min_grasp_width;        /* default 0.002                                              */
+    double  no_contact_below_z;     /* used iff use_below_z                                       */
+    int32_t use_below_z;
+    int32_t max_hits_per_ray;       /* capacity of the per-ray hit list (>=1, <= 32)              */
+} bt_ags_params;
+
+typedef struct bt_mesh_info {
+    int64_t n_vertices, n_triangles, n_nodes;
+    int64_t device_bytes;
+    double  surface_area;
+    double  build_ms;               /* LBVH build time (CUDA events)                              */
+    float   bounds_min[3], bounds_max[3];
+    int32_t device;
+    int32_t max_depth;              /* deepest leaf of the LBVH                                   */
+} bt_mesh_info;
+
+typedef struct bt_gripper_part {    /* a group of gripper triangles and their TCP-frame AABB */
+    double  box_min[3], box_max[3];
+    int32_t tri_begin, tri_end;     /* [begin, end) into the gripper triangle array */
+} bt_gripper_part;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+BT_API int         bt_version(void);
+BT_API const char* bt_last_error(void);
+BT_API int         bt_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem);
+BT_API int         bt_malloc(int device, int64_t bytes, void** d_ptr);   /* plain cudaMalloc for non-torch callers */
+BT_API int         bt_free(void* d_ptr);
+BT_API int         bt_memcpy_h2d(void* d_dst, const void* h_src, int64_t bytes, void* stream);
+BT_API int         bt_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes, void* stream);
+BT_API int         bt_stream_sync(void* stream);
+
+/* ---- mesh / scene ---------------------------------------------------------------------------------
+ * replaces mesh_processing.as_trimesh + trimesh.Trimesh construction + RayMeshIntersector / collision
+ * manager set-up (sampling.py:191-192, 372-380).  h_VN may be NULL (area-weighted vertex normals are
+ * then computed, the io.load_mesh convention io.py:96).  Face normals are always recomputed as
+ * normalise(cross(v1-v0, v2-v0)) (trimesh).  Builds the LBVH; synchronises. */
+BT_API int bt_mesh_create(const double* h_V, int64_t n_vertices, const int32_t* h_F, int64_t n_triangles,
+                   const double* h_VN, int device, bt_mesh** out);
+BT_API int bt_mesh_destroy(bt_mesh* mesh);
+BT_API int bt_mesh_get_info(const bt_mesh* mesh, bt_mesh_info* info);
+/* debug/validation: copy the LBVH out (nodes: 16 floats each; leaf_tri: sorted leaf -> caller's triangle id) */
+BT_API int bt_mesh_copy_bvh(const bt_mesh* mesh, float* h_nodes, int32_t* h_leaf_tri);
+
+/* ---- S1: area-weighted surface samples (replaces mesh_processing.poisson_disk_sampling's uniform
+ * stage, mesh_processing.py:52-83 -> open3d SamplePointsUniformlyImpl).  d_pts/d_nrm: [n,3] f64,
+ * d_tri: [n] i32 (may be NULL). */
+BT_API int bt_sample_surface(const bt_mesh* mesh, int64_t n, uint64_t seed, double* d_pts, double* d_nrm,
+                      int32_t* d_tri, void* stream);
+
+/* ---- S2: friction-cone ray directions (replaces sampling.rays_within_cone, sampling.py:17-48, for
+ * axis = -normal).  d_normals: [n_ref,3] f64, d_dirs: [n_ref,n_rays,3] f64. */
+BT_API int bt_cone_rays(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed,
+                 double* d_dirs, void* stream);
+
+/* random unit vectors (util.generate_random_unit_vector, util.py:32-43): normalised N(0,1)^3; [n,3] f64 */
+BT_API int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, void* stream);
+
+/* ---- R1..R6: cast every ray of every reference point against the mesh, ALL crossings, and evaluate the
+ * antipodal filters per hit (replaces intersector.intersects_location + sampling.py:239-319).
+ *   d_ref_pts [n_ref,3] f64, d_dirs [n_ref,n_rays,3] f64
+ *   d_hit_count [n_ref*n_rays] i32      number of hits of each ray (after trimesh's 1e-8 de-duplication)
+ *   d_hits      [n_ref*n_rays*cap] bt_hit   a ray's hits sorted by (t, tri); cap = max_hits_per_ray
+ *   d_overflow  [1] i32                 set to the number of rays whose hit list overflowed (may be NULL) */
+BT_API int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
+                int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
+                int32_t* d_overflow, void* stream);
+
+/* ---- R7: per reference point pick up to max_targets of its valid hits (replaces sampling.py:328-331).
+ *   seed == 0 : deterministic, the first max_targets valid hits in canonical order (ray, t)
+ *   seed != 0 : uniformly random subset keyed by (seed, reference point)
+ *   d_pair_count [n_ref] i32 out; d_pair_offset [n_ref+1] i64 out (exclusive scan);
+ *   d_pair_ref [cap_pairs] i32, d_pair_q [cap_pairs,3] f64 out; cap_pairs >= n_ref*max_targets is always enough */
+BT_API int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, int64_t n_ref, int32_t n_rays,
+                  int32_t max_hits_per_ray, int32_t max_targets, uint64_t seed, int32_t* d_pair_count,
+                  int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs,
+                  void* stream);
+
+/* ---- O1/O2: expand contact pairs into n_orientations gripper poses (replaces construct_grasp_set,
+ * sampling.py:132-183, and construct_halfspace_grasp_set, :72-130, incl. the reference's row order:
+ * within a reference point's group of k pairs, row r has the pose of (orientation r / k, target r % k)
+ * but width / contacts of target r / n_orientations).
+ *   d_ref_pts [n_ref,3]; d_pair_offset [n_ref+1]; d_pair_q [n_pairs,3];
+ *   d_frame_vecs [n_ref,3] f64 (the random unit vector of sampling.py:157; ignored for halfspace)
+ *   h_cos/h_sin [n_orientations] f64 host tables of the orientation angles (computed with numpy by the
+ *   caller so they are bit-identical to the reference's np.cos/np.sin)
+ *   d_gs [n_pairs*n_orientations,14] f32 out, d_contacts [n_pairs*n_orientations,2,3] f64 out (may be NULL)
+ *   the total pair count is read on the device from d_pair_offset[n_ref] (no host sync); the launch is
+ *   sized for cap_pairs; n_orientations <= 64 */
+BT_API int bt_expand_orientations(const double* d_ref_pts, const int64_t* d_pair_offset, const int32_t* d_pair_ref,
+                           const double* d_pair_q, const double* d_frame_vecs, int64_t n_ref, int64_t cap_pairs,
+                           int32_t n_orientations, int32_t halfspace, const double* h_cos,
+                           const double* h_sin, float* d_gs, double* d_contacts, void* stream);
+
+/* ---- K1: gripper-vs-scene collision (replaces AntipodalGraspSampler.check_collisions,
+ * sampling.py:354-397 -> trimesh CollisionManager -> FCL).  colliding[i] = any triangle of the gripper
+ * mesh, mapped by pose_i * diag(s_i,1,1,1) with s_i = (width_i + tol)/opening_width (float32
+ * arithmetic as numpy>=2 evaluates sampling.py:394) intersects any scene triangle (FCL's 17-axis
+ * separating-axis test; touching counts; containment does not).
+ *   bt_gripper_create: h_tris [n_tris,3,3] f64 in the TCP frame (gripper.mesh after tf_base_to_TCP,
+ *   sampling.py:382-385); h_parts [n_parts] groups of consecutive triangles with their TCP-frame AABB
+ *   bt_collide: d_gs [n,14] f32; d_n (may be NULL) device pointer to the actual row count (<= n);
+ *   d_colliding [n] u8 out (4-byte aligned, capacity padded to a multiple of 4 bytes) */
+typedef struct bt_gripper bt_gripper;
+BT_API int bt_gripper_create(const double* h_tris, int32_t n_tris, const bt_gripper_part* h_parts, int32_t n_parts,
+                      int device, bt_gripper** out);
+BT_API int bt_gripper_destroy(bt_gripper* gripper);
+BT_API int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const float* d_gs, int64_t n,
+               const int64_t* d_n, double opening_width, double width_tolerance, int32_t use_width,
+               uint8_t* d_colliding, void* stream);
+
+/* ---- stream compaction of the surviving grasps: keeps rows with mask[i] == keep_value.
+ *   d_out_gs [n,14], d_out_contacts [n,2,3] (may be NULL with d_contacts), d_n_out [1] i64 */
+BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
+               int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
+               void* stream);
+
+/* ---- M1..M5: coverage (replaces metrics.coverage / coverage_brute_force, metrics.py:141-229, and the
+ * distance functions they call, :9-77).  covered[i] = any_j ( 1000*|t_i - t_j| + deg(R_i, R_j) <= eps ),
+ * all float32 in the reference's operation order; deg() goes through the caller-supplied 20001-entry
+ * table of np.rad2deg(np.arccos(k/1e4)) so the transcendental is bit-identical to numpy.
+ *   mode 0: brute-force semantics (coverage_brute_force)
+ *   mode 1: kd-tree semantics (coverage): additionally requires the float64 squared translation distance
+ *           to be <= (eps/1000)^2, the cKDTree.query_ball_tree candidate test
+ *   algo 0: all-pairs tiles; algo 1: uniform-grid culled (queries binned in cells of eps/1000)
+ *   d_covered [n_ref] u8 out, d_count [1] i64 out */
+BT_API int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, double epsilon,
+                const float* d_acos_deg_lut, int32_t mode, int32_t algo, uint8_t* d_covered,
+                int64_t* d_count, void* stream);
+
+/* pairwise distance matrices (metrics.py:9-77), [n1,n2] f32 out; which: 0 euclidean, 1 angular [rad lut
+ * supplied by caller as d_lut], 2 combined (lut = degrees) */
+BT_API int bt_pairwise_distances(const float* d_gs1, int64_t n1, const float* d_gs2, int64_t n2, int32_t which,
+                          float weight, const float* d_lut, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BURG_B200_H */

@@ -252,7 +252,7 @@ def meshes_collide(query_tris, scene_tris, chunk=4_000_000):
         st = scene_tris[idx]
         ov = ((a_min[:, None, :] <= smax[idx][None]) & (a_max[:, None, :] >= smin[idx][None])).all(axis=-1)
         ia, ib = np.nonzero(ov)
-        if len(ia) and tri_tri_intersect(query_tris[ia], st[ib]).any():
+        if len(ia) and tri_tri_intersect(st[ib], query_tris[ia]).any():     # FCL: P = scene (model 1), Q = query
             return True
     return False
 

@@ -1,0 +1,148 @@
+"""GPU parity tests (through the C ABI) for the metric path: bit-exact against the golden fixtures that
+the reference's own metrics.py produced, and against the oracle port on seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def metrics():
+    from burg_toolkit_b200 import metrics as m
+    return m
+
+
+def _gs(rows):
+    from burg_toolkit_b200.grasp import GraspSet
+    return GraspSet.from_array(np.ascontiguousarray(rows, dtype=np.float32))
+
+
+def random_rows(n, seed, cube=0.2):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    rows = np.zeros((n, 14), dtype=np.float32)
+    rows[:, 0:3] = rng.random((n, 3)) * cube
+    rows[:, 3:12] = Rotation.random(n, random_state=seed).as_matrix().reshape(n, 9)
+    return rows
+
+
+def perturbed_rows(rows, seed, frac=0.5, sigma_t=0.005, sigma_deg=5.0):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(len(rows), int(len(rows) * frac), replace=False)
+    out = rows[idx].copy()
+    out[:, 0:3] += rng.normal(0, sigma_t, (len(idx), 3)).astype(np.float32)
+    rv = rng.normal(0, np.deg2rad(sigma_deg), (len(idx), 3))
+    out[:, 3:12] = (Rotation.from_rotvec(rv).as_matrix() @ rows[idx, 3:12].reshape(-1, 3, 3).astype(np.float64)).reshape(-1, 9)
+    return out
+
+
+def test_known_answer_3mm_15deg(metrics):
+    k = load_golden('known_answers')
+    gs = _gs(k['gs'])
+    comb = metrics.combined_distances(gs[0], gs[1])
+    assert comb.dtype == np.float32 and comb.shape == (1, 1)
+    assert comb[0, 0] == np.float32(18.005714416503906)
+    assert np.array_equal(metrics.euclidean_distances(gs[0], gs[1]), k['euclid_3mm'])
+    assert np.array_equal(np.rad2deg(metrics.angular_distances(gs[0], gs[1])), k['angular_15deg'])
+    assert metrics.coverage_brute_force(gs, gs[0:20]) == 0.4 == metrics.coverage(gs, gs[0:20])
+
+
+def test_pairwise_distances_bit_exact(metrics):
+    g = load_golden('metrics_small')
+    ref, qry = _gs(g['ref']), _gs(g['qry'])
+    assert np.array_equal(metrics.euclidean_distances(ref, qry), g['euclidean'])
+    assert np.array_equal(metrics.angular_distances(ref, qry), g['angular'])
+    assert np.array_equal(metrics.combined_distances(ref, qry), g['combined'])
+
+
+@pytest.mark.parametrize('algo', ['tiles', 'grid'])
+def test_coverage_golden(metrics, algo):
+    g = load_golden('metrics_small')
+    ref, qry = g['ref'], g['qry']
+    for kd in (True, False):
+        want = port.covered_kd(ref, qry) if kd else port.covered_brute_force(ref, qry)
+        got = metrics.covered_mask(_gs(ref), _gs(qry), kd_semantics=kd, algo=algo)
+        assert np.array_equal(got, want)
+    assert metrics.coverage(_gs(ref), _gs(qry)) == float(g['coverage_kd'])
+    assert metrics.coverage_brute_force(_gs(ref), _gs(qry)) == float(g['coverage_brute'])
+    assert metrics.precision(_gs(ref), _gs(qry)) == float(g['precision_kd'])
+    assert metrics.coverage(_gs(ref), _gs(qry), epsilon=5.0) == float(g['coverage_eps5'])
+    assert metrics.coverage_brute_force(_gs(ref), _gs(qry), epsilon=30.0) == float(g['coverage_eps30'])
+
+
+@pytest.mark.parametrize('algo', ['tiles', 'grid'])
+def test_coverage_mid_golden(metrics, algo):
+    g = load_golden('metrics_mid')
+    for q, key in [('qry_uniform', 'coverage_uniform'), ('qry_perturbed', 'coverage_perturbed')]:
+        got = metrics.covered_mask(_gs(g['ref']), _gs(g[q]), algo=algo)
+        assert got.mean() == float(g[key])
+        assert np.array_equal(got, port.covered_kd(g['ref'], g[q]))
+    assert metrics.precision(_gs(g['ref']), _gs(g['qry_perturbed'])) == float(g['precision_perturbed'])
+
+
+def test_edge_cases(metrics):
+    rows = random_rows(37, 4, cube=0.01)
+    gs = _gs(rows)
+    assert metrics.coverage(gs, gs) == 1.0                                  # identical sets
+    assert metrics.coverage(gs, gs, epsilon=0.0) == 1.0                     # 0 <= 0
+    empty = _gs(np.zeros((0, 14), dtype=np.float32))
+    assert metrics.coverage(gs, empty) == 0.0
+    far = rows.copy()
+    far[:, 0] += 10.0
+    assert metrics.coverage(gs, _gs(far)) == 0.0
+    one = _gs(rows[:1])
+    assert metrics.coverage(one, gs) == 1.0 and metrics.combined_distances(one, one)[0, 0] == 0.0
+    for algo in ('tiles', 'grid'):
+        m = metrics.covered_mask(gs, _gs(rows[5:6]), algo=algo)
+        assert m[5] and np.array_equal(m, port.covered_kd(rows, rows[5:6]))
+
+
+@pytest.mark.parametrize('n,m,cube', [(1025, 2049, 0.05), (5000, 3000, 0.08), (3000, 5000, 1.0)])
+def test_coverage_ragged_sizes_vs_oracle(metrics, n, m, cube):
+    ref = random_rows(n, 21, cube)
+    qry = np.concatenate([random_rows(m - m // 3, 22, cube), perturbed_rows(ref, 23, frac=(m // 3) / n)])[:m]
+    want_kd, want_bf = port.covered_kd(ref, qry), port.covered_brute_force(ref, qry)
+    for algo in ('tiles', 'grid'):
+        assert np.array_equal(metrics.covered_mask(_gs(ref), _gs(qry), algo=algo), want_kd)
+        assert np.array_equal(metrics.covered_mask(_gs(ref), _gs(qry), kd_semantics=False, algo=algo), want_bf)
+    assert 0 < want_kd.sum() < n
+
+
+def test_threshold_band(metrics):
+    """pairs placed exactly on / one float32 ulp around the translation threshold (angular part 0)."""
+    base = np.zeros((1, 14), dtype=np.float32)
+    base[0, 3], base[0, 7], base[0, 11] = 1, 1, 1
+    qs = []
+    d = np.float32(0.015)
+    for delta in [np.nextafter(d, np.float32(0)), d, np.nextafter(d, np.float32(1)), np.float32(0.0150001)]:
+        q = base.copy()
+        q[0, 0] = delta
+        qs.append(q)
+    for q in qs:
+        for kd in (True, False):
+            want = port.covered_kd(base, q) if kd else port.covered_brute_force(base, q)
+            for algo in ('tiles', 'grid'):
+                got = metrics.covered_mask(_gs(base), _gs(q), kd_semantics=kd, algo=algo)
+                assert np.array_equal(got, want), (float(q[0, 0]), kd, algo)
+
+
+def test_full_size_properties(metrics):
+    """BASELINE config 2 (100k x 100k): size-independent properties instead of an oracle run."""
+    import torch
+    n = 100_000
+    ref = random_rows(n, 1)
+    qry = np.concatenate([random_rows(n // 2, 2), perturbed_rows(ref, 3)])
+    dref, dqry = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
+    grid = metrics.covered_mask(dref, dqry, algo='grid')
+    tiles = metrics.covered_mask(dref, dqry, algo='tiles')
+    assert np.array_equal(grid, tiles)                                        # two algorithms, one answer
+    assert metrics.coverage(dref, dref) == 1.0                                # idempotence
+    sub = metrics.covered_mask(dref, dqry[: n // 4], algo='grid')
+    assert not (sub & ~grid).any()                                            # monotone in the query set
+    idx = np.random.default_rng(0).choice(n, 300, replace=False)
+    assert np.array_equal(grid[idx], port.covered_kd(ref[idx], qry))           # spot check against the oracle
+    assert 0.2 < grid.mean() < 0.8
