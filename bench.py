@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the AGS + coverage hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ags_c3|coverage_c2]
+
+Prints ONE JSON line (rank 0).  Workloads (BASELINE.json `configs`):
+  ags_c3       config 3: AGS on the 99 904-triangle 'YCB-like' mesh, 10 000 reference points x 100 rays = 1 M
+               candidates per step per GPU, max_targets_per_ref_point = 1, 12 orientations, gripper-vs-object
+               collision + compaction.  metric: candidates/s.  (default; the config the metric's target is quoted on)
+  coverage_c2  config 2: coverage of two 100k grasp sets (perturbed pair).  metric: pairs/s.
+
+A "step" is one pass of the device pipeline over one batch of synthetic candidates.  The timed region holds
+exactly K steps, each bracketed by CUDA events on the launching stream; L2 is flushed between steps (outside the
+event pairs); the reported time is the max over ranks of the summed step times.
+
+--impl reference times the reference's CPU algorithm on the host cores instead: the reference is pure Python on
+un-installable third-party leaves, so this arm runs the oracle port (oracle/coracle.c: same arithmetic, BVH broad
+phase, OpenMP over all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_REF = 10_000
+N_RAYS = 100
+N_ORIENT = 12
+COV_N = 100_000
+AGS_KERNELS = ['sample_surface_kernel', 'cone_rays_kernel', 'cast_kernel', 'zero_first_kernel', 'select_count_kernel',
+               'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'collide_kernel', 'compact_count_kernel',
+               'compact_scatter_kernel']
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.stop_flag, self.thread = gpu_index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-i',
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': int(statistics.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------------------------------------------
+def c3_mesh():
+    from burg_toolkit_b200 import mesh as bmesh
+    return bmesh.create_bumpy_sphere(224, 224, radius=0.035, amplitude=0.15, seed=1)
+
+
+def random_rows(n, seed, cube=0.2):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    rows = np.zeros((n, 14), dtype=np.float32)
+    rows[:, 0:3] = rng.random((n, 3)) * cube
+    rows[:, 3:12] = Rotation.random(n, random_state=seed).as_matrix().reshape(n, 9)
+    return rows
+
+
+def perturbed_rows(rows, seed, frac=0.5, sigma_t=0.005, sigma_deg=5.0):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(len(rows), int(len(rows) * frac), replace=False)
+    out = rows[idx].copy()
+    out[:, 0:3] += rng.normal(0, sigma_t, (len(idx), 3)).astype(np.float32)
+    rv = rng.normal(0, np.deg2rad(sigma_deg), (len(idx), 3))
+    out[:, 3:12] = (Rotation.from_rotvec(rv).as_matrix() @ rows[idx, 3:12].reshape(-1, 3, 3).astype(np.float64)).reshape(-1, 9)
+    return out
+
+
+def coverage_sets(n):
+    ref = random_rows(n, 1)
+    qry = np.concatenate([random_rows(n - n // 2, 2), perturbed_rows(ref, 3)])
+    return ref, qry
+
+
+def host_candidates(mesh, n_ref, seed):
+    """host-side reference points, normals, cone rays and frame vectors (CPU baseline / parity inputs)"""
+    from oracle import leaves, port
+    rng = np.random.default_rng(seed)
+    m = port.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
+    tn = leaves.unitize(np.cross(m.triangles[:, 1] - m.triangles[:, 0], m.triangles[:, 2] - m.triangles[:, 0]))
+    pts, nrm, _ = leaves.sample_points_uniformly(m.vertices, m.faces, tn, n_ref, rng)
+    sel = rng.permutation(len(pts))
+    pts, nrm = pts[sel], nrm[sel]
+    angle = np.arctan(0.25)
+    dirs = np.stack([port.cone_rays(-nrm[i], rng.uniform(0, 2 * np.pi, N_RAYS), rng.uniform(0, angle, N_RAYS)) for i in range(len(pts))])
+    fv = rng.normal(size=(len(pts), 3))
+    fv /= np.linalg.norm(fv, axis=1, keepdims=True)
+    return pts, nrm, dirs, fv
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port, all host threads)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_ags(mesh, n_ref, seed=100):
+    """one bounded CPU sample of the AGS workload -> (candidates, seconds, threads)"""
+    from oracle import cport
+    from burg_toolkit_b200.gripper import ParallelJawGripper
+    cm = cport.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
+    pts, nrm, dirs, fv = host_candidates(mesh, n_ref, seed)
+    gt = ParallelJawGripper().tcp_triangles()
+    t0 = time.perf_counter()
+    out = cport.pipeline(cm, cm, pts, dirs, fv, gt, n_orientations=N_ORIENT, coll_tol=0.01, max_hits_per_ray=16)
+    dt = time.perf_counter() - t0
+    return len(pts) * N_RAYS, dt, cport.num_threads(), out
+
+
+def cpu_coverage(n, seed=0):
+    """the reference's kd-tree coverage (scipy cKDTree + Python loop, metrics.py:161-229) restated in oracle/port.py"""
+    from oracle import port
+    ref, qry = coverage_sets(n)
+    t0 = time.perf_counter()
+    cov = port.covered_kd(ref, qry)
+    dt = time.perf_counter() - t0
+    return n * len(qry), dt, 1, float(cov.mean())
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    if args.workload == 'ags_c3':
+        mesh = c3_mesh()
+        n_ref = args.cpu_ref_points
+        for _ in range(max(args.warmup, 0)):
+            cpu_ags(mesh, max(8, n_ref // 8))
+        times, cands, threads = [], 0, 1
+        for s in range(args.steps):
+            c, dt, threads, _ = cpu_ags(mesh, n_ref, seed=100 + s)
+            times.append(dt)
+            cands += c
+        total = sum(times)
+        value, unit, metric = cands / total, 'candidates/s', 'AGS candidates/sec (ray+cone+collision)'
+        sample = f'{n_ref} reference points x {N_RAYS} rays per step ({n_ref * N_RAYS} candidates) of the ags_c3 workload'
+        config = {'workload': 'ags_c3', 'mesh_triangles': len(mesh.triangles), 'ref_points_per_step': n_ref,
+                  'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1, 'collision': 'gripper-vs-object'}
+    else:
+        n = args.cpu_coverage_n
+        times, pairs, threads = [], 0, 1
+        for s in range(args.steps):
+            p, dt, threads, _ = cpu_coverage(n)
+            times.append(dt)
+            pairs += p
+        total = sum(times)
+        value, unit, metric = pairs / total, 'pairs/s', 'coverage pairs/sec'
+        sample = f'{n} x {n} grasps per step (kd-tree coverage, single-threaded like the reference)'
+        config = {'workload': 'coverage_c2', 'n_ref': n, 'n_query': n}
+    line = {'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(args.steps, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.workload == 'ags_c3' else 'f32',
+            'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': value, 'unit': unit, 'cores': threads, 'kind': 'port', 'sample': sample,
+                             'host_cpus': cores},
+            'e2e': {'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def event_ms(pairs):
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+    from burg_toolkit_b200 import metrics, sampling
+    from burg_toolkit_b200.gripper import ParallelJawGripper
+
+    peak_gbs, peak_src = measured_peaks()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')       # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    clocks = ClockSampler(local_rank)
+    line = {}
+    if args.workload == 'ags_c3':
+        mesh = c3_mesh()
+        ags = sampling.AntipodalGraspSampler()
+        ags.mesh, ags.gripper, ags.verbose, ags.device = mesh, ParallelJawGripper(), False, local_rank
+        ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
+        dm = ags._device_mesh()
+        info = dm.info
+        gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if (world > 1 and rank == 0) else None
+
+        def step(seed, timers=None):
+            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timers=timers)
+            if world > 1:       # the path's only exchange: compacted grasp lists + counts to rank 0 over NVLink
+                dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
+                dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
+            return out
+
+        for w in range(args.warmup):
+            step(1000 * rank + w + 1)
+        barrier()
+        clocks.start()
+        timers, step_events, stats = {}, [], []
+        for s in range(args.steps):
+            flush.fill_(s & 0xff)                                                    # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step(7919 * (rank + 1) + s, timers)
+            e1.record()
+            step_events.append((e0, e1))
+            stats.append((out['n_grasps'], out['n_free'], out['overflow']))
+        barrier()
+        clk = clocks.stop()
+        step_ms = event_ms(step_events)
+        total_ms = max_over_ranks(sum(step_ms))
+        candidates = sum_over_ranks(N_REF * N_RAYS * args.steps)
+        value = candidates / (total_ms * 1e-3)
+        stage_ms = {k: statistics.mean(event_ms(v)) for k, v in timers.items()}
+        n_grasps = int(torch.stack([a.reshape(()) for a, _, _ in stats]).double().mean().item())
+        n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // max(world, 1)
+        overflow = int(torch.stack([c.reshape(()) for _, _, c in stats]).sum().item())
+
+        # roofline of the dominant kernel (cast): algorithmic bytes per launch / its event-timed duration
+        cast_ms = stage_ms['cast']
+        alg_bytes = N_REF * N_RAYS * 64 + 80 * info.n_triangles
+        achieved = alg_bytes / (cast_ms * 1e-3) / 1e9
+        prof = {}
+        ppath = os.path.join(ROOT, 'profiles', 'roofline_inputs.json')
+        if os.path.exists(ppath):
+            with open(ppath) as fh:
+                prof = json.load(fh)
+        roofline = {'bound': 'hbm', 'kernel': 'cast_kernel', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+                    'frac': achieved / peak_gbs, 'traffic': prof.get('cast_kernel', {}).get('dram_bytes_per_launch'),
+                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': cast_ms,
+                    'rays_per_s': N_REF * N_RAYS / (cast_ms * 1e-3),
+                    'note': 'mesh+LBVH (26 MB) is L2-resident by design, so HBM is not the binding roof; see DESIGN.md'}
+
+        # end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+        pts, nrm, _ = [t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank)]
+        pinned = {}
+        for w in range(max(args.warmup, 1)):
+            ags.evaluate_host(pts, nrm, seed=w + 1, pinned=pinned)
+        barrier()
+        e2e_events, h2d, d2h = [], 0, 0
+        for s in range(args.steps):
+            flush.fill_(s & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = ags.evaluate_host(pts, nrm, seed=s + 11, pinned=pinned)
+            e1.record()
+            e2e_events.append((e0, e1))
+            h2d, d2h = res['h2d_bytes'], res['d2h_bytes']
+        barrier()
+        e2e_ms = max_over_ranks(sum(event_ms(e2e_events)))
+        e2e_value = candidates / (e2e_ms * 1e-3)
+
+        line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
+                'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
+                'config': {'workload': 'ags_c3', 'mesh': 'bumpy sphere 224x224 (YCB-like, seed 1)',
+                           'mesh_triangles': int(info.n_triangles), 'ref_points_per_step_per_gpu': N_REF, 'n_rays': N_RAYS,
+                           'candidates_per_step_per_gpu': N_REF * N_RAYS, 'n_orientations': N_ORIENT,
+                           'max_targets_per_ref_point': 1, 'collision': 'gripper-vs-object, use_width, tol 0.01',
+                           'mode': 'reference mode (one pair per reference point)', 'l2': 'flushed between steps (256 MB write)',
+                           'bvh_build_ms': info.build_ms, 'bvh_max_depth': int(info.max_depth),
+                           'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow},
+                'roofline': roofline, 'stage_ms': stage_ms,
+                'e2e': {'value': e2e_value, 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': e2e_ms / args.steps},
+                'gpu_launches': len(AGS_KERNELS) * args.steps, 'kernels': AGS_KERNELS}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            c, dt, threads, _ = cpu_ags(mesh, args.cpu_ref_points)
+            line['cpu_baseline'] = {'value': c / dt, 'unit': 'candidates/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'{args.cpu_ref_points} reference points x {N_RAYS} rays ({c} candidates) of the same '
+                                              f'workload, oracle/coracle.c with OpenMP, {dt:.1f} s', 'host_cpus': os.cpu_count()}
+            # secondary metric of BASELINE.json: coverage pairs/s (config 2), same JSON line
+            line['secondary'] = coverage_numbers(args, torch, metrics, flush, barrier, short=True)
+    else:
+        line = coverage_numbers(args, torch, metrics, flush, barrier, short=False, clocks=clocks)
+        clk = line.pop('clocks')
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            p, dt, threads, cov = cpu_coverage(args.cpu_coverage_n)
+            line['cpu_baseline'] = {'value': p / dt, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'{args.cpu_coverage_n} x {args.cpu_coverage_n} grasps, kd-tree coverage '
+                                              f'(scipy cKDTree + Python loop as metrics.py:161-229), {dt:.1f} s'}
+    line.update({'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak',
+                 'vs_baseline': None, 'data': 'synthetic', 'clocks': clk})
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
+    """coverage 100k x 100k (perturbed pair, eps 15): device-resident pairs/s and e2e (host rows in, fraction out)"""
+    ref, qry = coverage_sets(COV_N)
+    dref, dqry = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
+    pairs = float(len(ref)) * float(len(qry))
+    res = {}
+    steps = max(3, args.steps // 2) if short else args.steps
+    for algo in ('grid', 'tiles'):
+        for _ in range(max(args.warmup, 3)):
+            metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
+        barrier()
+        if clocks is not None and algo == 'grid':
+            clocks.start()
+        ev = []
+        for s in range(steps):
+            flush.fill_(s & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, count = metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
+            e1.record()
+            ev.append((e0, e1))
+        barrier()
+        ms = statistics.mean(event_ms(ev))
+        res[algo] = {'ms': ms, 'pairs_per_s': pairs / (ms * 1e-3), 'coverage': int(count.item()) / len(ref)}
+    clk = clocks.stop() if clocks is not None else None
+    ev = []
+    for s in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frac = metrics.coverage(ref, qry)                       # host rows in (pageable), python float out
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    e2e_ms = statistics.mean(event_ms(ev))
+    # FP32-issue roofline of the tiles kernel: 4 lane-ops per rejected pair (3 FFMA + 1 compare), SURVEY.md 8d
+    lane_ops = 148 * 128 * 1.965e9
+    out = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
+           'ms_per_step': res['grid']['ms'],
+           'config': {'workload': 'coverage_c2', 'n_ref': len(ref), 'n_query': len(qry), 'epsilon': 15.0,
+                      'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
+                      'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
+                      'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
+           'tiles_all_pairs': res['tiles'],
+           'roofline': {'bound': 'fp32-issue', 'kernel': 'coverage_tiles_kernel', 'achieved': res['tiles']['pairs_per_s'] * 4 / 1e12,
+                        'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': res['tiles']['pairs_per_s'] * 4 / lane_ops,
+                        'traffic': None, 'note': '4 FP32 lane-ops per pair (3 FFMA + 1 compare); HBM bytes are negligible (10 MB)'},
+           'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes),
+                   'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac},
+           'gpu_launches': 8 * steps, 'clocks': clk}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'coverage_c2'])
+    ap.add_argument('--cpu-ref-points', type=int, default=4000, help='reference points per CPU sample (x100 rays)')
+    ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

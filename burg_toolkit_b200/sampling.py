@@ -161,8 +161,11 @@ class AntipodalGraspSampler:
                      int(seed), nat.ptr(dirs), nat.current_stream())
         return dirs
 
-    def cast(self, ref_points, directions, cap=None):
-        """R1-R6: all crossings of every ray with ``self.mesh`` + the per-hit antipodal filters."""
+    def cast(self, ref_points, directions, cap=None, retry_on_overflow=True):
+        """R1-R6: all crossings of every ray with ``self.mesh`` + the per-hit antipodal filters.
+        ``retry_on_overflow`` reads the overflow counter back (one host sync) and re-runs with a larger hit
+        list if some ray crossed more surfaces than fit; the asynchronous pipeline passes False and reports
+        the counter instead."""
         torch = nat.require_cuda()
         dm = self._device_mesh()
         pts = self._tensor(ref_points, torch.float64).reshape(-1, 3)
@@ -178,7 +181,7 @@ class AntipodalGraspSampler:
                 overflow = torch.zeros((1,), dtype=torch.int32, device='cuda')
                 nat.call('bt_ags_cast', dm.handle, nat.ptr(pts), nat.ptr(dirs), n_ref, n_rays, C.byref(params),
                          nat.ptr(hit_count), nat.ptr(hits), nat.ptr(overflow), nat.current_stream())
-                if cap >= 32 or int(overflow.item()) == 0:
+                if not retry_on_overflow or cap >= 32 or int(overflow.item()) == 0:
                     break
                 cap = min(32, cap * 2)                   # a ray crossed more surfaces than the list holds
         return CastResult(hit_count, hits, overflow, n_ref, n_rays, cap)
@@ -240,6 +243,92 @@ class AntipodalGraspSampler:
         gs, contacts = self.expand(pts, pair_offset, pair_ref, pair_q, frame_vecs, cap_pairs)
         return dict(cast=cast, pair_count=pair_count, pair_offset=pair_offset, pair_ref=pair_ref, pair_q=pair_q,
                     gs=gs, contacts=contacts, n_ref=n_ref, cap_pairs=cap_pairs, directions=directions)
+
+    def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, check_collisions=True,
+                     collision_width_tolerance=0.01, use_width=True, additional_objects=None, exclude_shape=False,
+                     compact=True, timers=None):
+        """The whole device pipeline for one batch of candidates, nothing leaves the GPU:
+
+            [S1 surface samples] -> S2 cone rays -> R1-R6 cast + filters -> R7 target choice -> O1/O2 orientation
+            expansion -> [K1 gripper-vs-scene collision -> ballot/scan compaction of the collision-free grasps]
+
+        ``ref_points`` / ``ref_normals``: [n_ref, 3] numpy arrays or CUDA tensors; if None, ``n_ref`` points are
+        drawn on the device (S1).  Candidates evaluated = n_ref * n_rays.
+        ``timers``: optional dict name -> list; CUDA event pairs around each stage are appended (bench.py).
+        -> dict of CUDA tensors (``gs``, ``contacts``, ``colliding``, ``n_grasps`` ...)."""
+        torch = nat.require_cuda()
+        device = self._device()
+
+        def stage(name, fn, *a, **k):
+            if timers is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            timers.setdefault(name, []).append((e0, e1))
+            return r
+
+        with torch.cuda.device(device):
+            if ref_points is None:
+                pts, nrm, _ = stage('sample_surface', self.sample_surface, int(n_ref), seed)
+            else:
+                pts = self._tensor(ref_points, torch.float64).reshape(-1, 3)
+                nrm = self._tensor(ref_normals, torch.float64).reshape(-1, 3)
+            n_ref = pts.shape[0]
+            dirs = stage('cone_rays', self.cone_rays, nrm, seed)
+            cast = stage('cast', self.cast, pts, dirs, None, False)
+            pair_count, pair_offset, pair_ref, pair_q, cap_pairs = stage('select', self.select, cast, seed + 1)
+            fv = None if self.only_grasp_from_above else stage('frame_vectors', self.frame_vectors, n_ref, seed + 2)
+            gs, contacts = stage('expand', self.expand, pts, pair_offset, pair_ref, pair_q, fv, cap_pairs)
+            n_rows = pair_offset[n_ref:n_ref + 1] * int(self.n_orientations)        # device scalar, no sync
+            out = dict(n_ref=n_ref, n_candidates=n_ref * int(self.n_rays), cast=cast, pair_count=pair_count,
+                       pair_offset=pair_offset, gs=gs, contacts=contacts, n_grasps=n_rows, overflow=cast.overflow)
+            if check_collisions:
+                meshes = ([] if exclude_shape else [self.mesh]) + list(additional_objects or [])
+                scene = self._scene(meshes, device)
+                gripper = self._device_gripper(device)
+                colliding = stage('collide', collide_rows, scene, gripper, gs, float(self.gripper.opening_width),
+                                  float(collision_width_tolerance), bool(use_width), n_rows)
+                out['colliding'] = colliding
+                if compact:
+                    free_gs, free_contacts, n_free = stage('compact', compact_rows, colliding, 0, gs, contacts, n_rows)
+                    out.update(free_gs=free_gs, free_contacts=free_contacts, n_free=n_free)
+        return out
+
+    def evaluate_host(self, ref_points, ref_normals, seed=1, pinned=None, **kwargs):
+        """End-to-end call with HOST buffers: uploads the reference points / normals, runs ``run_pipeline`` and
+        returns host results (GraspSet of collision-free grasps, contacts, counts).  ``pinned``: optional dict of
+        reusable pinned staging tensors (created on first use)."""
+        torch = nat.require_cuda()
+        device = self._device()
+        pinned = {} if pinned is None else pinned
+        n = len(ref_points)
+        with torch.cuda.device(device):
+            for key, arr in (('pts', ref_points), ('nrm', ref_normals)):
+                if key not in pinned or pinned[key].shape[0] != n:
+                    pinned[key] = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+                pinned[key].numpy()[...] = arr
+            pts = pinned['pts'].to(f'cuda:{device}', non_blocking=True)
+            nrm = pinned['nrm'].to(f'cuda:{device}', non_blocking=True)
+            out = self.run_pipeline(pts, nrm, seed=seed, **kwargs)
+            key_gs, key_c, key_n = ('free_gs', 'free_contacts', 'n_free') if 'free_gs' in out else ('gs', 'contacts', 'n_grasps')
+            cap = out[key_gs].shape[0]
+            if 'out_gs' not in pinned or pinned['out_gs'].shape[0] != cap:
+                pinned['out_gs'] = torch.empty((cap, 14), dtype=torch.float32).pin_memory()
+                pinned['out_c'] = torch.empty((cap, 2, 3), dtype=torch.float64).pin_memory()
+                pinned['out_n'] = torch.empty((2,), dtype=torch.int64).pin_memory()
+            pinned['out_n'][0:1].copy_(out[key_n], non_blocking=True)
+            pinned['out_n'][1:2].copy_(out['n_grasps'], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            k = int(pinned['out_n'][0])                    # read the count, then copy exactly that many rows
+            pinned['out_gs'][:k].copy_(out[key_gs][:k], non_blocking=True)
+            pinned['out_c'][:k].copy_(out[key_c][:k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d = 2 * n * 24
+        d2h = k * (56 + 48) + 16
+        return dict(gs=GraspSet.from_array(pinned['out_gs'][:k].numpy()), contacts=pinned['out_c'][:k].numpy(),
+                    n_grasps=int(pinned['out_n'][1]), n_free=k, h2d_bytes=h2d, d2h_bytes=d2h, n_candidates=out['n_candidates'])
 
     # -----------------------------------------------------------------------------------------------
     # reference API

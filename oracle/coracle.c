@@ -336,46 +336,79 @@ static int tri_tri(const double *P, const double *Q) {
     return 1;
 }
 
-static int tri_hits_scene(const CoMesh *s, const double *Q) {
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) { if (Q[3 * v + k] < lo[k]) lo[k] = Q[3 * v + k]; if (Q[3 * v + k] > hi[k]) hi[k] = Q[3 * v + k]; }
+/* conservative oriented-box vs node-box overlap: 3 world axes + the 3 box axes (false positives only) */
+typedef struct { double c[3], ax[3][3] /* half-axis vectors */, ext[3] /* world half extents */; } OBox;
+
+static int obox_hits_node(const OBox *b, const Node *n) {
+    double e[3], d[3];
+    for (int k = 0; k < 3; ++k) { e[k] = 0.5 * (n->hi[k] - n->lo[k]); d[k] = 0.5 * (n->hi[k] + n->lo[k]) - b->c[k]; }
+    for (int k = 0; k < 3; ++k) if (fabs(d[k]) > e[k] + b->ext[k]) return 0;
+    for (int j = 0; j < 3; ++j) {
+        const double *a = b->ax[j];
+        double len2 = dot3(a, a);
+        double proj = fabs(dot3(d, a));
+        double r_box = len2;                                       /* |a_j . a_j|; other axes are orthogonal up to 1e-7 */
+        double r_node = e[0] * fabs(a[0]) + e[1] * fabs(a[1]) + e[2] * fabs(a[2]);
+        if (proj > (r_box * 1.000001 + 1e-12) + r_node) return 0;
+    }
+    return 1;
+}
+
+/* does any of the part's posed triangles Q[0..nq) intersect a scene triangle? (part box walks the tree) */
+static int part_hits_scene(const CoMesh *s, const OBox *b, const double *Q, int nq) {
     int stack[128], sp = 0;
     stack[sp++] = 0;
     while (sp) {
         const Node *n = s->nodes + stack[--sp];
-        if (n->lo[0] > hi[0] || n->hi[0] < lo[0] || n->lo[1] > hi[1] || n->hi[1] < lo[1] || n->lo[2] > hi[2] || n->hi[2] < lo[2]) continue;
+        if (!obox_hits_node(b, n)) continue;
         if (n->count > 0) {
             for (int i = n->start; i < n->start + n->count; ++i) {
                 int f = s->order[i];
                 double P[9];
                 for (int v = 0; v < 3; ++v) memcpy(P + 3 * v, s->V + 3 * s->F[3 * f + v], 24);
-                if (tri_tri(P, Q)) return 1;
+                for (int t = 0; t < nq; ++t) if (tri_tri(P, Q + 9 * t)) return 1;
             }
         } else { stack[sp++] = n->left; stack[sp++] = n->right; }
     }
     return 0;
 }
 
-static int grasp_collides(const CoMesh *scene, const float *g, const double *gtris, int n_gt, float ow, float tol, int use_width) {
+/* parts: n_parts+1 triangle boundaries; each part's TCP-frame AABB becomes an oriented box under pose*diag(s,1,1) */
+static int grasp_collides(const CoMesh *scene, const float *g, const double *gtris, const int *parts, int n_parts,
+                          float ow, float tol, int use_width) {
     float sf = use_width ? (g[13] + tol) / ow : 1.0f;       /* float32, numpy >= 2 promotion of sampling.py:394 */
     double s = (double)sf, M[3][3], T[3] = {g[0], g[1], g[2]};
     for (int i = 0; i < 3; ++i) { M[i][0] = (double)g[3 + 3 * i] * s; M[i][1] = g[4 + 3 * i]; M[i][2] = g[5 + 3 * i]; }
-    for (int t = 0; t < n_gt; ++t) {
-        double Q[9];
-        for (int v = 0; v < 3; ++v) {
-            const double *p = gtris + 9 * t + 3 * v;
-            for (int i = 0; i < 3; ++i) Q[3 * v + i] = ((M[i][0] * p[0] + M[i][1] * p[1]) + M[i][2] * p[2]) + T[i];
+    for (int p = 0; p < n_parts; ++p) {
+        int t0 = parts[p], t1 = parts[p + 1], nq = t1 - t0;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        double *Q = (double *)malloc(sizeof(double) * 9 * nq);
+        for (int t = t0; t < t1; ++t)
+            for (int v = 0; v < 3; ++v) {
+                const double *pt = gtris + 9 * t + 3 * v;
+                for (int k = 0; k < 3; ++k) { if (pt[k] < lo[k]) lo[k] = pt[k]; if (pt[k] > hi[k]) hi[k] = pt[k]; }
+                for (int i = 0; i < 3; ++i) Q[9 * (t - t0) + 3 * v + i] = ((M[i][0] * pt[0] + M[i][1] * pt[1]) + M[i][2] * pt[2]) + T[i];
+            }
+        OBox b;
+        double cl[3], hl[3];
+        for (int k = 0; k < 3; ++k) { cl[k] = 0.5 * (lo[k] + hi[k]); hl[k] = 0.5 * (hi[k] - lo[k]) * 1.000001 + 1e-9; }
+        for (int i = 0; i < 3; ++i) {
+            b.c[i] = ((M[i][0] * cl[0] + M[i][1] * cl[1]) + M[i][2] * cl[2]) + T[i];
+            for (int j = 0; j < 3; ++j) b.ax[j][i] = M[i][j] * hl[j];
         }
-        if (tri_hits_scene(scene, Q)) return 1;
+        for (int i = 0; i < 3; ++i) b.ext[i] = (fabs(b.ax[0][i]) + fabs(b.ax[1][i]) + fabs(b.ax[2][i])) * 1.000001 + 1e-9;
+        int hit = part_hits_scene(scene, &b, Q, nq);
+        free(Q);
+        if (hit) return 1;
     }
     return 0;
 }
 
-void co_collide(const CoMesh *scene, const float *gs, int64_t n, const double *gtris, int n_gt, double ow, double tol,
-                int use_width, uint8_t *colliding) {
+void co_collide(const CoMesh *scene, const float *gs, int64_t n, const double *gtris, const int *parts, int n_parts,
+                double ow, double tol, int use_width, uint8_t *colliding) {
 #pragma omp parallel for schedule(dynamic, 8)
     for (int64_t i = 0; i < n; ++i)
-        colliding[i] = (uint8_t)grasp_collides(scene, gs + 14 * i, gtris, n_gt, (float)ow, (float)tol, use_width);
+        colliding[i] = (uint8_t)grasp_collides(scene, gs + 14 * i, gtris, parts, n_parts, (float)ow, (float)tol, use_width);
 }
 
 /* ---- the whole per-reference-point pipeline (what bench.py --impl reference times) --------------------------
@@ -385,7 +418,7 @@ void co_collide(const CoMesh *scene, const float *gs, int64_t n, const double *g
  * without a valid target are left zero.  returns the number of contact pairs found. */
 int64_t co_pipeline(const CoMesh *m, const CoMesh *scene, const double *ref_pts, const double *dirs, const double *frame_vecs,
                     int64_t n_ref, int n_rays, const CoParams *P, int n_o, const double *cs, const double *sn,
-                    const double *gtris, int n_gt, double coll_tol, int use_width,
+                    const double *gtris, const int *parts, int n_parts, double coll_tol, int use_width,
                     float *rows, double *contacts, uint8_t *colliding, int32_t *pair_count) {
     int64_t total = 0;
     const int cap = P->max_hits_per_ray;
@@ -406,7 +439,7 @@ int64_t co_pipeline(const CoMesh *m, const CoMesh *scene, const double *ref_pts,
             expand_one(p_r, q, frame_vecs + 3 * r, n_o, cs, sn, rows + 14 * n_o * r, contacts ? contacts + 6 * n_o * r : NULL);
             if (scene)
                 for (int o = 0; o < n_o; ++o)
-                    colliding[n_o * r + o] = (uint8_t)grasp_collides(scene, rows + 14 * (n_o * r + o), gtris, n_gt,
+                    colliding[n_o * r + o] = (uint8_t)grasp_collides(scene, rows + 14 * (n_o * r + o), gtris, parts, n_parts,
                                                                      (float)P->opening_width, (float)coll_tol, use_width);
             total += 1;
         }

@@ -38,11 +38,11 @@ def lib():
         l.co_num_threads.restype = C.c_int
         l.co_ags_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(Params),
                                   C.c_void_p, C.c_void_p]
-        l.co_collide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_double, C.c_double,
-                                 C.c_int, C.c_void_p]
+        l.co_collide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                 C.c_double, C.c_int, C.c_void_p]
         l.co_pipeline.restype = C.c_int64
         l.co_pipeline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
-                                  C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
@@ -91,12 +91,19 @@ def cast(mesh, ref_pts, dirs, **params):
     return cnt, hits
 
 
+def _parts(n_tris, group=12):
+    """triangle boundaries of the gripper's parts (the simplified mesh is 3 boxes x 12 triangles; any other mesh is
+    cut into consecutive groups -- only the broad phase depends on this, not the result)"""
+    return np.ascontiguousarray(np.unique(np.concatenate([np.arange(0, n_tris, group), [n_tris]])), dtype=np.int32)
+
+
 def collide(scene, rows, gripper_tris, opening_width, width_tolerance=0.01, use_width=True):
     rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 14)
     gt = np.ascontiguousarray(gripper_tris, dtype=np.float64).reshape(-1, 9)
+    parts = _parts(len(gt))
     out = np.zeros(len(rows), dtype=np.uint8)
-    lib().co_collide(scene.handle, rows.ctypes.data, len(rows), gt.ctypes.data, len(gt), opening_width,
-                     width_tolerance, 1 if use_width else 0, out.ctypes.data)
+    lib().co_collide(scene.handle, rows.ctypes.data, len(rows), gt.ctypes.data, parts.ctypes.data, len(parts) - 1,
+                     opening_width, width_tolerance, 1 if use_width else 0, out.ctypes.data)
     return out.astype(bool)
 
 
@@ -108,6 +115,7 @@ def pipeline(mesh, scene, ref_pts, dirs, frame_vecs, gripper_tris, n_orientation
     fv = np.ascontiguousarray(frame_vecs, dtype=np.float64).reshape(-1, 3)
     gt = np.ascontiguousarray(gripper_tris, dtype=np.float64).reshape(-1, 9)
     n_ref, n_rays = dirs.shape[:2]
+    parts = _parts(len(gt))
     p = make_params(**params)
     theta = np.arange(0, 2 * np.pi, 2 * np.pi / n_orientations)[:n_orientations]
     cs, sn = np.ascontiguousarray(np.cos(theta)), np.ascontiguousarray(np.sin(theta))
@@ -117,7 +125,7 @@ def pipeline(mesh, scene, ref_pts, dirs, frame_vecs, gripper_tris, n_orientation
     pair_count = np.zeros(n_ref, dtype=np.int32)
     n_pairs = lib().co_pipeline(mesh.handle, None if scene is None else scene.handle, ref_pts.ctypes.data,
                                 dirs.ctypes.data, fv.ctypes.data, n_ref, n_rays, C.byref(p), n_orientations,
-                                cs.ctypes.data, sn.ctypes.data, gt.ctypes.data, len(gt), coll_tol,
+                                cs.ctypes.data, sn.ctypes.data, gt.ctypes.data, parts.ctypes.data, len(parts) - 1, coll_tol,
                                 1 if use_width else 0, rows.ctypes.data, contacts.ctypes.data, colliding.ctypes.data,
                                 pair_count.ctypes.data)
     return dict(n_pairs=int(n_pairs), rows=rows, contacts=contacts, colliding=colliding.astype(bool), pair_count=pair_count)
