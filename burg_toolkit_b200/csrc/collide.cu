@@ -23,6 +23,7 @@ struct PartDev {
     float cx, cy, cz;      // box centre, TCP frame
     float hx, hy, hz;      // half extents
     int32_t tri_begin, tri_end;
+    int32_t is_box;        // the part's triangles are exactly the 12 faces of its box (closed surface)
 };
 
 // FCL Intersect::project6: true if `ax` does NOT separate {p1,p2,p3} from {q1,q2,q3}
@@ -89,6 +90,55 @@ __device__ __forceinline__ bool obb_overlaps_aabb(const Obb& b, float x0, float 
     return true;
 }
 
+// Conservative float32 classification of a scene triangle against the part's (solid) oriented box, in box-local
+// coordinates q (metres along the three box axes):
+//   0 = certainly disjoint from the box (some separating axis found, extents inflated by `m`)
+//   1 = certainly strictly inside the box (all vertices inside the box shrunk by `m`)  -- only meaningful for is_box parts:
+//       a triangle inside a closed box cannot touch the box's surface triangles
+//   2 = undecided -> run the exact float64 test
+__device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, float e1, float e2, float m) {
+    const float E[3] = {e0 + m, e1 + m, e2 + m};
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float lo = fminf(q[0][k], fminf(q[1][k], q[2][k])), hi = fmaxf(q[0][k], fmaxf(q[1][k], q[2][k]));
+        if (lo > E[k] || hi < -E[k]) return 0;
+        inside = inside && (lo > -(E[k] - 2.f * m)) && (hi < (E[k] - 2.f * m));
+    }
+    if (inside) return 1;
+    // triangle plane
+    const float f0[3] = {q[1][0] - q[0][0], q[1][1] - q[0][1], q[1][2] - q[0][2]};
+    const float f1[3] = {q[2][0] - q[1][0], q[2][1] - q[1][1], q[2][2] - q[1][2]};
+    const float f2[3] = {q[0][0] - q[2][0], q[0][1] - q[2][1], q[0][2] - q[2][2]};
+    const float n[3] = {f0[1] * f1[2] - f0[2] * f1[1], f0[2] * f1[0] - f0[0] * f1[2], f0[0] * f1[1] - f0[1] * f1[0]};
+    const float nn = fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]);
+    const float dist = n[0] * q[0][0] + n[1] * q[0][1] + n[2] * q[0][2];
+    const float rad = E[0] * fabsf(n[0]) + E[1] * fabsf(n[1]) + E[2] * fabsf(n[2]);
+    if (fabsf(dist) > rad + 1e-6f * nn) return 0;
+    // 9 edge-cross axes  a = e_i x f_j  (e_i = unit box axes)
+    const float* F[3] = {f0, f1, f2};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float fx = F[j][0], fy = F[j][1], fz = F[j][2];
+        {   // e_0 x f = (0, -fz, fy)
+            const float p0 = -fz * q[0][1] + fy * q[0][2], p1 = -fz * q[1][1] + fy * q[1][2], p2 = -fz * q[2][1] + fy * q[2][2];
+            const float r = E[1] * fabsf(fz) + E[2] * fabsf(fy) + 1e-6f * (fabsf(fy) + fabsf(fz));
+            if (fminf(p0, fminf(p1, p2)) > r || fmaxf(p0, fmaxf(p1, p2)) < -r) return 0;
+        }
+        {   // e_1 x f = (fz, 0, -fx)
+            const float p0 = fz * q[0][0] - fx * q[0][2], p1 = fz * q[1][0] - fx * q[1][2], p2 = fz * q[2][0] - fx * q[2][2];
+            const float r = E[0] * fabsf(fz) + E[2] * fabsf(fx) + 1e-6f * (fabsf(fx) + fabsf(fz));
+            if (fminf(p0, fminf(p1, p2)) > r || fmaxf(p0, fmaxf(p1, p2)) < -r) return 0;
+        }
+        {   // e_2 x f = (-fy, fx, 0)
+            const float p0 = -fy * q[0][0] + fx * q[0][1], p1 = -fy * q[1][0] + fx * q[1][1], p2 = -fy * q[2][0] + fx * q[2][1];
+            const float r = E[0] * fabsf(fy) + E[1] * fabsf(fx) + 1e-6f * (fabsf(fx) + fabsf(fy));
+            if (fminf(p0, fminf(p1, p2)) > r || fmaxf(p0, fmaxf(p1, p2)) < -r) return 0;
+        }
+    }
+    return 2;
+}
+
 __global__ void __launch_bounds__(128)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
                int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
@@ -101,11 +151,13 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_parts[i] = parts[i];
     __syncthreads();
 
+    // part-major: consecutive threads pose the SAME part for consecutive grasps (the orientations of one contact
+    // pair), so a warp walks the same region of the LBVH
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t row = idx / n_parts;
-    const int part = (int)(idx - row * n_parts);
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    if (row >= n) return;
+    const int part = (int)(idx / n_cap);
+    const int64_t row = idx - (int64_t)part * n_cap;
+    if (part >= n_parts || row >= n) return;
     volatile unsigned int* word = out_words + (row >> 2);
     const unsigned int bit = 1u << (8 * (row & 3));
     if (*word & bit) return;                       // another part of this grasp already collides
@@ -128,9 +180,10 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     b.ux[0] = gf[3]; b.ux[1] = gf[6]; b.ux[2] = gf[9];
     b.uy[0] = gf[4]; b.uy[1] = gf[7]; b.uy[2] = gf[10];
     b.uz[0] = gf[5]; b.uz[1] = gf[8]; b.uz[2] = gf[11];
-    b.cx = (float)((m00 * pd.cx + m01 * pd.cy) + m02 * pd.cz + tx);
-    b.cy = (float)((m10 * pd.cx + m11 * pd.cy) + m12 * pd.cz + ty);
-    b.cz = (float)((m20 * pd.cx + m21 * pd.cy) + m22 * pd.cz + tz);
+    const double cxd = (m00 * pd.cx + m01 * pd.cy) + m02 * pd.cz + tx;
+    const double cyd = (m10 * pd.cx + m11 * pd.cy) + m12 * pd.cz + ty;
+    const double czd = (m20 * pd.cx + m21 * pd.cy) + m22 * pd.cz + tz;
+    b.cx = (float)cxd; b.cy = (float)cyd; b.cz = (float)czd;
     // the rotation block of a float32 grasp row is orthonormal only to ~1e-7; scale the half extents by the
     // actual column norms (+ margin) so the box test stays conservative
     const float nx = sqrtf(b.ux[0] * b.ux[0] + b.ux[1] * b.ux[1] + b.ux[2] * b.ux[2]);
@@ -146,6 +199,11 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
         b.az = fabsf(b.ux[2]) * e0 + fabsf(b.uy[2]) * e1 + fabsf(b.uz[2]) * e2 + inflate;
     }
 
+    // box-local frame for the leaf classifier: unit axes and half extents in metres
+    const float inx = 1.0f / nx, iny = 1.0f / ny, inz = 1.0f / nz;
+    const float le0 = pd.hx * fabsf(sf) * nx, le1 = pd.hy * ny, le2 = pd.hz * nz;
+    const float cls_margin = inflate + 1e-4f * fmaxf(le0, fmaxf(le1, le2));
+
     int stack[CSTACK];
     int sp = 0;
     int cur = 0;
@@ -153,6 +211,23 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
         if (cur < 0) {
             const double* tv = tri_verts + 9 * (int64_t)(~cur);
             const d3 P1 = ld3(tv), P2 = ld3(tv + 3), P3 = ld3(tv + 6);
+            {
+                float q[3][3];
+                const d3 PV[3] = {P1, P2, P3};
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    const float dx = (float)(PV[v].x - cxd), dy = (float)(PV[v].y - cyd), dz = (float)(PV[v].z - czd);
+                    q[v][0] = fmaf(dx, b.ux[0], fmaf(dy, b.ux[1], dz * b.ux[2])) * inx;
+                    q[v][1] = fmaf(dx, b.uy[0], fmaf(dy, b.uy[1], dz * b.uy[2])) * iny;
+                    q[v][2] = fmaf(dx, b.uz[0], fmaf(dy, b.uz[1], dz * b.uz[2])) * inz;
+                }
+                const int cls = classify_triangle(q, le0, le1, le2, cls_margin);
+                if (cls == 0 || (cls == 1 && pd.is_box)) {
+                    if (sp == 0) break;
+                    cur = stack[--sp];
+                    continue;
+                }
+            }
             for (int t = pd.tri_begin; t < pd.tri_end; ++t) {
                 const double* gt = s_gtris + 9 * t;
                 d3 Q[3];
@@ -238,6 +313,43 @@ __global__ void compact_scatter_kernel(const uint8_t* __restrict__ mask, uint8_t
 
 using namespace bt;
 
+// true iff the part's triangles are exactly the 12 faces of its axis-aligned (TCP frame) box: every face of the box
+// carries two triangles whose vertices are corners of that face and which share exactly one diagonal
+static bool part_is_closed_box(const double* tris, const bt_gripper_part& hp) {
+    if (hp.tri_end - hp.tri_begin != 12) return false;
+    int per_face[6] = {0, 0, 0, 0, 0, 0};
+    int corner_mask[6][2];
+    for (int t = hp.tri_begin; t < hp.tri_end; ++t) {
+        const double* v = tris + 9 * t;
+        int corner[3];
+        for (int k = 0; k < 3; ++k) {
+            int c = 0;
+            for (int a = 0; a < 3; ++a) {
+                const double x = v[3 * k + a];
+                if (x == hp.box_max[a]) c |= 1 << a;
+                else if (x != hp.box_min[a]) return false;          // not a box corner
+            }
+            corner[k] = c;
+        }
+        if (corner[0] == corner[1] || corner[1] == corner[2] || corner[0] == corner[2]) return false;
+        int face = -1;
+        for (int a = 0; a < 3 && face < 0; ++a)
+            for (int side = 0; side < 2 && face < 0; ++side) {
+                bool all = true;
+                for (int k = 0; k < 3; ++k) all = all && (((corner[k] >> a) & 1) == side);
+                if (all) face = 2 * a + side;
+            }
+        if (face < 0 || per_face[face] >= 2) return false;
+        corner_mask[face][per_face[face]++] = (1 << corner[0]) | (1 << corner[1]) | (1 << corner[2]);
+    }
+    for (int f = 0; f < 6; ++f) {
+        if (per_face[f] != 2) return false;
+        const int shared = corner_mask[f][0] & corner_mask[f][1];
+        if (__builtin_popcount(shared) != 2 || __builtin_popcount(corner_mask[f][0] | corner_mask[f][1]) != 4) return false;
+    }
+    return true;
+}
+
 struct bt_gripper {
     int device = 0;
     int n_tris = 0, n_parts = 0;
@@ -265,6 +377,7 @@ extern "C" int bt_gripper_create(const double* h_tris, int32_t n_gt, const bt_gr
         parts[p].hz = (float)(0.5 * (hp.box_max[2] - hp.box_min[2])) * 1.00001f + 1e-9f;
         parts[p].tri_begin = hp.tri_begin;
         parts[p].tri_end = hp.tri_end;
+        parts[p].is_box = part_is_closed_box(h_tris, hp) ? 1 : 0;
     }
     BT_REQUIRE(expect == n_gt, "parts must cover every gripper triangle");
     BT_CUDA(cudaSetDevice(device));
@@ -305,7 +418,7 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
     const size_t tri_bytes = sizeof(double) * 9 * (size_t)gripper->n_tris;
     if (tri_bytes > 48 * 1024)
         BT_CUDA(cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
-    const int64_t threads = n * gripper->n_parts;
+    const int64_t threads = n * gripper->n_parts;          // part-major: thread = part * n + row
     collide_kernel<<<(unsigned)ceil_div(threads, 128), 128, tri_bytes, st>>>(
         scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
         (float)opening_width, (float)width_tolerance, use_width, inflate, reinterpret_cast<unsigned int*>(d_colliding));

@@ -329,8 +329,10 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
 extern "C" int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, double epsilon,
                            const float* d_lut, int32_t mode, int32_t algo, uint8_t* d_covered, int64_t* d_count,
                            void* stream) {
-    BT_REQUIRE(d_ref && d_qry && d_lut && d_covered && d_count, "null pointer");
+    BT_REQUIRE(d_lut && d_count, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_qry >= 0 && n_ref < (1ll << 31) && n_qry < (1ll << 31), "bad counts");
+    BT_REQUIRE((d_ref && d_covered) || n_ref == 0, "null reference set");
+    BT_REQUIRE(d_qry || n_qry == 0, "null query set");
     BT_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (brute force semantics) or 1 (kd-tree semantics)");
     BT_REQUIRE(algo == 0 || algo == 1, "algo must be 0 (tiles) or 1 (grid)");
     cudaStream_t st = (cudaStream_t)stream;
