@@ -21,6 +21,7 @@ constexpr float T_BEHIND = -1e-5f;        // boxes wholly behind the origin by m
 struct MeshView {
     const float4* __restrict__ nodes;
     const double* __restrict__ tri_rec;
+    const float4* __restrict__ tri_f32;
     const int32_t* __restrict__ leaf_tri;
     const int32_t* __restrict__ faces;
     const double* __restrict__ verts;
@@ -94,51 +95,101 @@ __device__ __forceinline__ d3 interpolated_normal(const MeshView& mv, int32_t tr
     return div3(s, norm3(s));
 }
 
+// Conservative float32 ray/triangle pre-test (division-free Moeller-Trumbore).  It may only say "no" when the exact
+// float64 test of the reference certainly says "no": every comparison carries an absolute slack E that bounds the
+// float32 rounding of the inputs and of the dot/cross products, plus a relative slack on the determinant.
+__device__ __forceinline__ bool maybe_hit_f32(const float4* __restrict__ tr, float ox, float oy, float oz,
+                                              float dx, float dy, float dz) {
+    const float4 v0 = __ldg(tr + 0), e0 = __ldg(tr + 1), e1 = __ldg(tr + 2);
+    // pvec = d x e1
+    const float px = dy * e1.z - dz * e1.y, py = dz * e1.x - dx * e1.z, pz = dx * e1.y - dy * e1.x;
+    float det = fmaf(e0.x, px, fmaf(e0.y, py, e0.z * pz));
+    const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
+    float U = fmaf(tx, px, fmaf(ty, py, tz * pz));
+    // qvec = tvec x e0
+    const float qx = ty * e0.z - tz * e0.y, qy = tz * e0.x - tx * e0.z, qz = tx * e0.y - ty * e0.x;
+    float V = fmaf(dx, qx, fmaf(dy, qy, dz * qz));
+    float T = fmaf(e1.x, qx, fmaf(e1.y, qy, e1.z * qz));
+    if (det < 0.f) { det = -det; U = -U; V = -V; T = -T; }
+    const float l0 = fabsf(e0.x) + fabsf(e0.y) + fabsf(e0.z), l1 = fabsf(e1.x) + fabsf(e1.y) + fabsf(e1.z);
+    const float lt = fabsf(tx) + fabsf(ty) + fabsf(tz) + fabsf(ox) + fabsf(oy) + fabsf(oz) + fabsf(v0.x) + fabsf(v0.y) + fabsf(v0.z);
+    // |error| of U, V, T, det <= ~16 eps32 * (|tvec|+|o|+|v0|) * |e0| * |e1|-ish products; 256 eps32 is generous
+    const float E = 1.6e-5f * (lt * fmaxf(l0, l1) + l0 * l1) + 1e-3f * det;
+    return (U >= -E) & (V >= -E) & (U + V <= det + E) & (T >= -(E + 1e-4f * det) - 1e-4f * l0 * l1);
+}
+
+constexpr int NPEND = 32;
+
+// One thread per ray.  Phase 1 walks the LBVH in float32 (both child boxes per 64-byte node) and parks the leaves that
+// survive the float32 pre-test; phase 2 runs the reference's float64 narrow phase on the parked leaves (threads of a
+// warp are converged again by then); phase 3 orders, de-duplicates and filters the hits and writes the records.
 template <int CAP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
             int n_rays, bt_ags_params P, int cap, int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits,
             int32_t* __restrict__ overflow) {
     int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (ray >= n_total) return;
     const int64_t ref = ray / n_rays;
-    const d3 o = ld3(ref_pts + 3 * ref);
-    const d3 d = ld3(dirs + 3 * ray);
-    const float idx = safe_rcp((float)d.x), idy = safe_rcp((float)d.y), idz = safe_rcp((float)d.z);
-    const float oox = (float)o.x * idx, ooy = (float)o.y * idy, ooz = (float)o.z * idz;
-
+    int pend[NPEND];
+    int n_pend = 0;
+    bool over = false;
     double hit_t[CAP];
     int32_t hit_tri[CAP];
     int n_hit = 0;
-    bool over = false;
 
-    int stack[STACK_SIZE];
-    int sp = 0;
-    int cur = 0;
-    while (true) {
-        if (cur < 0) {
-            const int leaf = ~cur;
+    // phase 2 (also used as an emergency flush when the parking list fills up): exact float64 tests
+    auto run_exact = [&]() {
+        const d3 o = ld3(ref_pts + 3 * ref);
+        const d3 d = ld3(dirs + 3 * ray);
+        for (int i = 0; i < n_pend; ++i) {
+            const int leaf = pend[i];
             double t;
             if (exact_ray_triangle(mv.tri_rec + 16 * (int64_t)leaf, o, d, t)) {
                 if (n_hit < cap) { hit_t[n_hit] = t; hit_tri[n_hit] = __ldg(mv.leaf_tri + leaf); ++n_hit; }
                 else over = true;
             }
+        }
+        n_pend = 0;
+    };
+
+    {
+        const float ox = (float)ref_pts[3 * ref], oy = (float)ref_pts[3 * ref + 1], oz = (float)ref_pts[3 * ref + 2];
+        const float dx = (float)dirs[3 * ray], dy = (float)dirs[3 * ray + 1], dz = (float)dirs[3 * ray + 2];
+        const float idx = safe_rcp(dx), idy = safe_rcp(dy), idz = safe_rcp(dz);
+        const float oox = ox * idx, ooy = oy * idy, ooz = oz * idz;
+        int stack[STACK_SIZE];
+        int sp = 0;
+        int cur = 0;
+        while (true) {
+            // descend through internal nodes
+            while (cur >= 0) {
+                const float4 q0 = __ldg(mv.nodes + 4 * (int64_t)cur + 0);
+                const float4 q1 = __ldg(mv.nodes + 4 * (int64_t)cur + 1);
+                const float4 q2 = __ldg(mv.nodes + 4 * (int64_t)cur + 2);
+                const float4 q3 = __ldg(mv.nodes + 4 * (int64_t)cur + 3);
+                const bool hl = slab_hit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, idx, idy, idz, oox, ooy, ooz);
+                const bool hr = slab_hit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, idx, idy, idz, oox, ooy, ooz);
+                const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
+                if (hl && hr) { stack[sp++] = r; cur = l; }
+                else if (hl) cur = l;
+                else if (hr) cur = r;
+                else { if (sp == 0) { cur = 0x7fffffff; break; } cur = stack[--sp]; }
+            }
+            if (cur == 0x7fffffff) break;
+            // a leaf
+            const int leaf = ~cur;
+            if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
+                if (n_pend == NPEND) run_exact();
+                pend[n_pend++] = leaf;
+            }
             if (sp == 0) break;
             cur = stack[--sp];
-            continue;
         }
-        const float4 q0 = __ldg(mv.nodes + 4 * (int64_t)cur + 0);
-        const float4 q1 = __ldg(mv.nodes + 4 * (int64_t)cur + 1);
-        const float4 q2 = __ldg(mv.nodes + 4 * (int64_t)cur + 2);
-        const float4 q3 = __ldg(mv.nodes + 4 * (int64_t)cur + 3);
-        const bool hl = slab_hit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, idx, idy, idz, oox, ooy, ooz);
-        const bool hr = slab_hit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, idx, idy, idz, oox, ooy, ooz);
-        const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
-        if (hl && hr) { stack[sp++] = r; cur = l; }
-        else if (hl) cur = l;
-        else if (hr) cur = r;
-        else { if (sp == 0) break; cur = stack[--sp]; }
     }
+    run_exact();
+    const d3 o = ld3(ref_pts + 3 * ref);
+    const d3 d = ld3(dirs + 3 * ray);
 
     // canonical order: (t, triangle id) ascending
     for (int i = 1; i < n_hit; ++i) {
@@ -473,7 +524,7 @@ __global__ void expand_kernel(const double* __restrict__ ref_pts, const int64_t*
 
 static MeshView view_of(const MeshDev& m) {
     MeshView v;
-    v.nodes = m.nodes; v.tri_rec = m.tri_rec; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
+    v.nodes = m.nodes; v.tri_rec = m.tri_rec; v.tri_f32 = m.tri_f32; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
     v.vnormals = m.vnormals;
     return v;
 }

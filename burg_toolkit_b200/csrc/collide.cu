@@ -139,7 +139,14 @@ __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, 
     return 2;
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int PEND = 8;                    // undecided leaves a thread may hold before the warp flushes them
+
+// One thread per (gripper part, grasp) walks the scene LBVH with the part's oriented box (float32, conservative) and
+// classifies every reached scene triangle (disjoint / inside a closed box / undecided).  Undecided leaves are parked in a
+// small per-thread list; whenever a list is full or the warp's traversals are done, the WARP runs the exact float64
+// test cooperatively: lane l tests gripper triangle l of the owner's part against the parked scene triangle, so the
+// expensive 17-axis tests run 12..32 wide instead of on one lane.
+__global__ void __launch_bounds__(128, 4)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
                int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
                const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
@@ -153,19 +160,21 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
 
     // part-major: consecutive threads pose the SAME part for consecutive grasps (the orientations of one contact
     // pair), so a warp walks the same region of the LBVH
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    const int part = (int)(idx / n_cap);
-    const int64_t row = idx - (int64_t)part * n_cap;
-    if (part >= n_parts || row >= n) return;
-    volatile unsigned int* word = out_words + (row >> 2);
+    int part = (int)(idx / n_cap);
+    int64_t row = idx - (int64_t)part * n_cap;
+    bool traversing = (part < n_parts) && (row < n);
+    if (!traversing) { part = 0; row = 0; }
     const unsigned int bit = 1u << (8 * (row & 3));
-    if (*word & bit) return;                       // another part of this grasp already collides
+    if (traversing && (*((volatile unsigned int*)out_words + (row >> 2)) & bit)) traversing = false;   // another part already collides
 
     const float* g = gs + 14 * row;
     float gf[14];
 #pragma unroll
-    for (int k = 0; k < 14; ++k) gf[k] = __ldg(g + k);
+    for (int k = 0; k < 14; ++k) gf[k] = traversing ? __ldg(g + k) : 0.f;
     // sampling.py:392-394 in float32 (numpy >= 2 scalar promotion): s = (width + tol) / opening_width
     const float sf = use_width ? (gf[13] + tol) / ow : 1.0f;
     const double s = (double)sf;
@@ -198,66 +207,89 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
         b.ay = fabsf(b.ux[1]) * e0 + fabsf(b.uy[1]) * e1 + fabsf(b.uz[1]) * e2 + inflate;
         b.az = fabsf(b.ux[2]) * e0 + fabsf(b.uy[2]) * e1 + fabsf(b.uz[2]) * e2 + inflate;
     }
-
     // box-local frame for the leaf classifier: unit axes and half extents in metres
-    const float inx = 1.0f / nx, iny = 1.0f / ny, inz = 1.0f / nz;
+    const float inx = nx > 0.f ? 1.0f / nx : 0.f, iny = ny > 0.f ? 1.0f / ny : 0.f, inz = nz > 0.f ? 1.0f / nz : 0.f;
     const float le0 = pd.hx * fabsf(sf) * nx, le1 = pd.hy * ny, le2 = pd.hz * nz;
     const float cls_margin = inflate + 1e-4f * fmaxf(le0, fmaxf(le1, le2));
 
     int stack[CSTACK];
-    int sp = 0;
+    int pend[PEND];
+    int sp = 0, np = 0;
     int cur = 0;
+    bool collided = false;
     while (true) {
-        if (cur < 0) {
-            const double* tv = tri_verts + 9 * (int64_t)(~cur);
-            const d3 P1 = ld3(tv), P2 = ld3(tv + 3), P3 = ld3(tv + 6);
-            {
+        // ---- phase A: traverse until this thread's walk ends or its pending list is full -------------------------
+        while (traversing && np < PEND) {
+            if (cur < 0) {
+                const double* tv = tri_verts + 9 * (int64_t)(~cur);
                 float q[3][3];
-                const d3 PV[3] = {P1, P2, P3};
 #pragma unroll
                 for (int v = 0; v < 3; ++v) {
-                    const float dx = (float)(PV[v].x - cxd), dy = (float)(PV[v].y - cyd), dz = (float)(PV[v].z - czd);
+                    const float dx = (float)(tv[3 * v] - cxd), dy = (float)(tv[3 * v + 1] - cyd), dz = (float)(tv[3 * v + 2] - czd);
                     q[v][0] = fmaf(dx, b.ux[0], fmaf(dy, b.ux[1], dz * b.ux[2])) * inx;
                     q[v][1] = fmaf(dx, b.uy[0], fmaf(dy, b.uy[1], dz * b.uy[2])) * iny;
                     q[v][2] = fmaf(dx, b.uz[0], fmaf(dy, b.uz[1], dz * b.uz[2])) * inz;
                 }
                 const int cls = classify_triangle(q, le0, le1, le2, cls_margin);
-                if (cls == 0 || (cls == 1 && pd.is_box)) {
-                    if (sp == 0) break;
-                    cur = stack[--sp];
-                    continue;
-                }
+                if (!(cls == 0 || (cls == 1 && pd.is_box))) pend[np++] = ~cur;
+                if (sp == 0) { traversing = false; break; }
+                cur = stack[--sp];
+                continue;
             }
-            for (int t = pd.tri_begin; t < pd.tri_end; ++t) {
-                const double* gt = s_gtris + 9 * t;
-                d3 Q[3];
-#pragma unroll
-                for (int v = 0; v < 3; ++v) {
-                    const double px = gt[3 * v], py = gt[3 * v + 1], pz = gt[3 * v + 2];
-                    Q[v] = mk3(((m00 * px + m01 * py) + m02 * pz) + tx, ((m10 * px + m11 * py) + m12 * pz) + ty,
-                               ((m20 * px + m21 * py) + m22 * pz) + tz);
-                }
-                if (tri_tri_intersect(P1, P2, P3, Q[0], Q[1], Q[2])) {
-                    atomicOr(out_words + (row >> 2), bit);
-                    return;
-                }
-            }
-            if (sp == 0) break;
-            cur = stack[--sp];
-            continue;
+            const float4 q0 = __ldg(nodes + 4 * (int64_t)cur + 0);
+            const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
+            const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
+            const float4 q3 = __ldg(nodes + 4 * (int64_t)cur + 3);
+            const bool hl = obb_overlaps_aabb(b, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+            const bool hr = obb_overlaps_aabb(b, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+            const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
+            if (hl && hr) { stack[sp++] = r; cur = l; }
+            else if (hl) cur = l;
+            else if (hr) cur = r;
+            else { if (sp == 0) { traversing = false; break; } cur = stack[--sp]; }
         }
-        const float4 q0 = __ldg(nodes + 4 * (int64_t)cur + 0);
-        const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
-        const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
-        const float4 q3 = __ldg(nodes + 4 * (int64_t)cur + 3);
-        const bool hl = obb_overlaps_aabb(b, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-        const bool hr = obb_overlaps_aabb(b, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
-        const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
-        if (hl && hr) { stack[sp++] = r; cur = l; }
-        else if (hl) cur = l;
-        else if (hr) cur = r;
-        else { if (sp == 0) break; cur = stack[--sp]; }
+        __syncwarp();
+        // ---- phase B: the warp drains every lane's pending list with the exact test ---------------------------------
+        unsigned has = __ballot_sync(FULL, np > 0);
+        while (has) {
+            const int src = __ffs(has) - 1;
+            const int cnt = __shfl_sync(FULL, np, src);
+            const int tb = __shfl_sync(FULL, pd.tri_begin, src), te = __shfl_sync(FULL, pd.tri_end, src);
+            const double b00 = __shfl_sync(FULL, m00, src), b01 = __shfl_sync(FULL, m01, src), b02 = __shfl_sync(FULL, m02, src);
+            const double b10 = __shfl_sync(FULL, m10, src), b11 = __shfl_sync(FULL, m11, src), b12 = __shfl_sync(FULL, m12, src);
+            const double b20 = __shfl_sync(FULL, m20, src), b21 = __shfl_sync(FULL, m21, src), b22 = __shfl_sync(FULL, m22, src);
+            const double ux = __shfl_sync(FULL, tx, src), uy = __shfl_sync(FULL, ty, src), uz = __shfl_sync(FULL, tz, src);
+            bool found = false;
+            for (int k = 0; k < cnt && !found; ++k) {
+                const int leaf = __shfl_sync(FULL, pend[k < PEND ? k : 0], src);
+                const double* tv = tri_verts + 9 * (int64_t)leaf;
+                const d3 P1 = ld3(tv), P2 = ld3(tv + 3), P3 = ld3(tv + 6);
+                for (int t0 = tb; t0 < te && !found; t0 += 32) {
+                    const int t = t0 + lane;
+                    bool hit = false;
+                    if (t < te) {
+                        const double* gt = s_gtris + 9 * t;
+                        d3 Q[3];
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+                            const double px = gt[3 * v], py = gt[3 * v + 1], pz = gt[3 * v + 2];
+                            Q[v] = mk3(((b00 * px + b01 * py) + b02 * pz) + ux, ((b10 * px + b11 * py) + b12 * pz) + uy,
+                                       ((b20 * px + b21 * py) + b22 * pz) + uz);
+                        }
+                        hit = tri_tri_intersect(P1, P2, P3, Q[0], Q[1], Q[2]);
+                    }
+                    found = __any_sync(FULL, hit);
+                }
+            }
+            if (lane == src) {
+                np = 0;
+                if (found) { collided = true; traversing = false; }
+            }
+            has = __ballot_sync(FULL, np > 0);
+        }
+        if (!__any_sync(FULL, traversing)) break;
     }
+    if (collided) atomicOr(out_words + (row >> 2), bit);
 }
 
 // ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------

@@ -54,6 +54,7 @@ struct Scratch {
 // Triangle record for the exact ray test: 128 bytes = 16 doubles (one cache line):
 //   v0[3] n[3] e0[3] e1[3] d00 d01 d11 inv_den     (e0 = v1-v0, e1 = v2-v0, trimesh 'cramer' constants)
 // Triangle vertices for the exact triangle/triangle test: 9 doubles (v0 v1 v2).
+// Float32 triangle for the conservative ray pre-test: 3 x float4 (v0, e0, e1), 48 bytes.
 struct MeshDev {
     int device = 0;
     int64_t nV = 0, nF = 0;
@@ -66,6 +67,7 @@ struct MeshDev {
     float4*  nodes = nullptr;      // [max(nF-1,1)*4]
     double*  tri_rec = nullptr;    // [nF,16]  leaf order
     double*  tri_verts = nullptr;  // [nF,9]   leaf order
+    float4*  tri_f32 = nullptr;    // [nF,3]   leaf order: (v0 | 0) (e0 | 0) (e1 | 0) for the float32 pre-test
     int32_t* leaf_tri = nullptr;   // [nF]     leaf -> caller's triangle id
     int32_t  root = 0;             // root child code (internal 0, or ~0 if single triangle)
     bt_mesh_info info{};

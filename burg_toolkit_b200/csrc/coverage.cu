@@ -19,7 +19,7 @@
 namespace bt {
 
 constexpr int COV_THREADS = 256;
-constexpr int COV_RPT = 4;                       // reference rows per thread
+constexpr int COV_RPT = 8;                       // reference rows per thread
 constexpr int COV_TILE = 1024;                   // queries staged per shared-memory tile (16 KB)
 
 struct CovParams {
@@ -55,24 +55,33 @@ __device__ __noinline__ bool pair_covered(const float* __restrict__ a, const flo
 }
 
 // ---- algo 0: all pairs, query tiles in shared memory ---------------------------------------------------------
+// Fast path per pair: 3 FFMA + 1 compare on the expanded form |q|^2 - 2 a.q <= r^2 - |a|^2 (centred coordinates).
+// Survivors (a few per thousand) are NOT evaluated in place -- that would leave one lane of a warp running the exact
+// recipe while 31 wait -- but appended to a shared-memory queue and drained by the whole block after each tile.
+constexpr int COV_QCAP = 4096;
+
 __global__ void __launch_bounds__(COV_THREADS)
 coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ qry, int64_t n_qry,
                       int64_t q_per_split, const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
     __shared__ float4 tile[COV_TILE];
-    const int64_t row0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT) + threadIdx.x;
-    // per-row constants of the expanded form  |a-q|^2 = |q|^2 - 2 a.q + |a|^2  (centred coordinates)
+    __shared__ unsigned int queue[COV_QCAP];
+    __shared__ unsigned char s_cov[COV_THREADS * COV_RPT];
+    __shared__ int q_count;
+    const int64_t block_row0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT);
+    // per-row constants of the expanded form (centred coordinates)
     float ax[COV_RPT], ay[COV_RPT], az[COV_RPT], thr[COV_RPT];
-    bool cov[COV_RPT];
 #pragma unroll
     for (int r = 0; r < COV_RPT; ++r) {
-        const int64_t i = row0 + (int64_t)r * COV_THREADS;
-        cov[r] = false;
+        const int lr = threadIdx.x + r * COV_THREADS;
+        const int64_t i = block_row0 + lr;
+        s_cov[lr] = 0;
         if (i < n_ref) {
             const float x = ref[14 * i] - P.cx, y = ref[14 * i + 1] - P.cy, z = ref[14 * i + 2] - P.cz;
             ax[r] = -2.0f * x; ay[r] = -2.0f * y; az[r] = -2.0f * z;
             thr[r] = P.r2_reject - fmaf(x, x, fmaf(y, y, z * z));
         } else { ax[r] = ay[r] = az[r] = 0.f; thr[r] = -1e30f; }
     }
+    if (threadIdx.x == 0) q_count = 0;
     const int64_t q_begin = (int64_t)blockIdx.y * q_per_split;
     const int64_t q_end = min(n_qry, q_begin + q_per_split);
     for (int64_t q0 = q_begin; q0 < q_end; q0 += COV_TILE) {
@@ -84,23 +93,45 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
             tile[j] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
         }
         __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
             const float4 q = tile[j];
+            bool any = false;
+            bool pass[COV_RPT];
 #pragma unroll
             for (int r = 0; r < COV_RPT; ++r) {
                 const float s = fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w)));
-                if (s <= thr[r]) {                                   // rare: run the exact recipe
-                    const int64_t i = row0 + (int64_t)r * COV_THREADS;
-                    if (!cov[r] && pair_covered(ref + 14 * i, qry + 14 * (q0 + j), lut, P)) cov[r] = true;
+                pass[r] = s <= thr[r];
+                any |= pass[r];
+            }
+            if (any) {
+#pragma unroll
+                for (int r = 0; r < COV_RPT; ++r) {
+                    if (pass[r]) {
+                        const int lr = threadIdx.x + r * COV_THREADS;
+                        const int pos = atomicAdd(&q_count, 1);
+                        if (pos < COV_QCAP) queue[pos] = ((unsigned)lr << 10) | (unsigned)j;
+                        else if (!s_cov[lr] && pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
+                    }
                 }
             }
         }
+        __syncthreads();
+        const int n_q = min(q_count, COV_QCAP);
+        for (int e = threadIdx.x; e < n_q; e += COV_THREADS) {
+            const unsigned code = queue[e];
+            const int lr = (int)(code >> 10), j = (int)(code & 1023u);
+            if (!s_cov[lr] && pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) q_count = 0;
     }
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < COV_RPT; ++r) {
-        const int64_t i = row0 + (int64_t)r * COV_THREADS;
-        if (i < n_ref && cov[r]) covered[i] = 1;                     // all writers store the same value
+        const int lr = threadIdx.x + r * COV_THREADS;
+        const int64_t i = block_row0 + lr;
+        if (i < n_ref && s_cov[lr]) covered[i] = 1;                  // all writers store the same value
     }
 }
 
@@ -176,17 +207,21 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, i
     return lo;
 }
 
-__global__ void __launch_bounds__(128)
+// one WARP per reference grasp (walked in cell order): the lanes stride over the sorted queries of the 27 neighbouring
+// cells (3 consecutive z cells are one contiguous range -> 9 coalesced ranges), survivors of the translation reject run
+// the exact recipe, the warp stops at the first covering query.
+__global__ void __launch_bounds__(256)
 coverage_grid_kernel(const float* __restrict__ ref, const int32_t* __restrict__ ref_sorted_ids, int64_t n_ref,
                      const float* __restrict__ qry, const float4* __restrict__ q_sorted,
                      const uint32_t* __restrict__ q_keys, int n_qry, const int32_t* __restrict__ cell_start,
                      const int32_t* __restrict__ cell_end, Grid g, const float* __restrict__ lut, CovParams P,
                      uint8_t* __restrict__ covered) {
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (s >= n_ref) return;
-    const int64_t i = ref_sorted_ids[s];                 // refs are walked in cell order -> a warp shares cells
+    const int64_t i = ref_sorted_ids[s];
     const float* a = ref + 14 * i;
-    const float x = a[0], y = a[1], z = a[2];
+    const float x = __ldg(a), y = __ldg(a + 1), z = __ldg(a + 2);
     const int cx = cell_coord(x, g.ox, g.inv_h, g.nx), cy = cell_coord(y, g.oy, g.inv_h, g.ny), cz = cell_coord(z, g.oz, g.inv_h, g.nz);
     const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
     bool cov = false;
@@ -198,7 +233,7 @@ coverage_grid_kernel(const float* __restrict__ ref, const int32_t* __restrict__ 
                 // consecutive z cells are consecutive keys; empty cells have start == end == 0
                 b = -1; e = 0;
                 for (uint32_t k = k0; k <= k1; ++k) {
-                    const int cs = cell_start[k], ce = cell_end[k];
+                    const int cs = __ldg(cell_start + k), ce = __ldg(cell_end + k);
                     if (ce > cs) { if (b < 0) b = cs; e = ce; }
                 }
                 if (b < 0) continue;
@@ -206,16 +241,19 @@ coverage_grid_kernel(const float* __restrict__ ref, const int32_t* __restrict__ 
                 b = lower_bound_u32(q_keys, n_qry, k0);
                 e = lower_bound_u32(q_keys, n_qry, k1 + 1);
             }
-            for (int j = b; j < e; ++j) {
-                const float4 q = __ldg(q_sorted + j);
-                const float dx = x - q.x, dy = y - q.y, dz = z - q.z;
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (d2 <= P.r2_reject) {
-                    if (pair_covered(a, qry + 14 * (int64_t)__float_as_int(q.w), lut, P)) { cov = true; break; }
+            for (int j0 = b; j0 < e && !cov; j0 += 32) {
+                const int j = j0 + lane;
+                bool mine = false;
+                if (j < e) {
+                    const float4 q = __ldg(q_sorted + j);
+                    const float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d2 <= P.r2_reject) mine = pair_covered(a, qry + 14 * (int64_t)__float_as_int(q.w), lut, P);
                 }
+                cov = __any_sync(0xffffffffu, mine);
             }
         }
-    if (cov) covered[i] = 1;
+    if (cov && lane == 0) covered[i] = 1;
 }
 
 __global__ void count_covered_kernel(const uint8_t* __restrict__ covered, int64_t n, unsigned long long* __restrict__ count) {
@@ -319,7 +357,7 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
     gather_sorted_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, ids_s.as<int32_t>(), keys_s.as<uint32_t>(), n_qry, qs.as<float4>(),
                                                                           dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr);
     BT_LAUNCH_CHECK();
-    coverage_grid_kernel<<<(unsigned)ceil_div(n_ref, 128), 128, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
+    coverage_grid_kernel<<<(unsigned)ceil_div(n_ref * 32, 256), 256, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
                                                                           (int)n_qry, dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr,
                                                                           g, lut, P, d_covered);
     BT_LAUNCH_CHECK();

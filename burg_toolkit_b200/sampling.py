@@ -181,8 +181,14 @@ class AntipodalGraspSampler:
                 overflow = torch.zeros((1,), dtype=torch.int32, device='cuda')
                 nat.call('bt_ags_cast', dm.handle, nat.ptr(pts), nat.ptr(dirs), n_ref, n_rays, C.byref(params),
                          nat.ptr(hit_count), nat.ptr(hits), nat.ptr(overflow), nat.current_stream())
-                if not retry_on_overflow or cap >= 32 or int(overflow.item()) == 0:
+                if not retry_on_overflow:
                     break
+                n_over = int(overflow.item())
+                if n_over == 0:
+                    break
+                if cap >= 32:
+                    raise RuntimeError(f'{n_over} rays cross more than 32 surfaces of the mesh; the hit list cannot '
+                                       f'hold them (bt_ags_cast max_hits_per_ray <= 32)')
                 cap = min(32, cap * 2)                   # a ray crossed more surfaces than the list holds
         return CastResult(hit_count, hits, overflow, n_ref, n_rays, cap)
 
