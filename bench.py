@@ -36,7 +36,7 @@ N_RAYS = 100
 N_ORIENT = 12
 COV_N = 100_000
 AGS_KERNELS = ['sample_surface_kernel', 'cone_rays_kernel', 'cast_kernel', 'zero_first_kernel', 'select_count_kernel',
-               'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'collide_kernel', 'compact_count_kernel',
+               'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'scale_count_kernel', 'collide_kernel', 'compact_count_kernel',
                'compact_scatter_kernel']
 
 
@@ -247,8 +247,11 @@ def run_b200(args, rank, world, local_rank):
         info = dm.info
         gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if (world > 1 and rank == 0) else None
 
-        def step(seed, timers=None):
-            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timers=timers)
+        from burg_toolkit_b200.device import StageTimer
+        stage_timer = StageTimer(local_rank)
+
+        def step(seed, timer=None):
+            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer)
             if world > 1:       # the path's only exchange: compacted grasp lists + counts to rank 0 over NVLink
                 dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
                 dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
@@ -258,22 +261,24 @@ def run_b200(args, rank, world, local_rank):
             step(1000 * rank + w + 1)
         barrier()
         clocks.start()
-        timers, step_events, stats = {}, [], []
+        stage_acc, step_events, stats = {}, [], []
         for s in range(args.steps):
             flush.fill_(s & 0xff)                                                    # L2 flush, outside the event pair
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = step(7919 * (rank + 1) + s, timers)
+            out = step(7919 * (rank + 1) + s, stage_timer)
             e1.record()
             step_events.append((e0, e1))
-            stats.append((out['n_grasps'], out['n_free'], out['overflow']))
+            stats.append((out['n_grasps'].clone(), out['n_free'].clone(), out['overflow'].clone()))
+            for name, ms in stage_timer.read().items():          # waits for this step's last stage (outside the event pair)
+                stage_acc.setdefault(name, []).append(ms)
         barrier()
         clk = clocks.stop()
         step_ms = event_ms(step_events)
         total_ms = max_over_ranks(sum(step_ms))
         candidates = sum_over_ranks(N_REF * N_RAYS * args.steps)
         value = candidates / (total_ms * 1e-3)
-        stage_ms = {k: statistics.mean(event_ms(v)) for k, v in timers.items()}
+        stage_ms = {k: statistics.mean(v) for k, v in stage_acc.items()}
         n_grasps = int(torch.stack([a.reshape(()) for a, _, _ in stats]).double().mean().item())
         n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // max(world, 1)
         overflow = int(torch.stack([c.reshape(()) for _, _, c in stats]).sum().item())

@@ -38,6 +38,27 @@ class GripperPart(C.Structure):
                 ('tri_end', C.c_int32)]
 
 
+N_STAGES = 8
+STAGE_NAMES = ('sample_surface', 'cone_rays', 'cast', 'select', 'frame_vectors', 'expand', 'collide', 'compact')
+
+
+class PipelineConfig(C.Structure):
+    _fields_ = [('ags', AgsParams), ('n_rays', C.c_int32), ('n_orientations', C.c_int32), ('max_targets', C.c_int32),
+                ('halfspace', C.c_int32), ('check_collisions', C.c_int32), ('use_width', C.c_int32),
+                ('compact', C.c_int32), ('reserved', C.c_int32), ('collision_width_tolerance', C.c_double),
+                ('orient_cos', C.c_double * 64), ('orient_sin', C.c_double * 64)]
+
+
+class PipelineBuffers(C.Structure):
+    _fields_ = [('ref_pts', C.c_void_p), ('ref_nrm', C.c_void_p), ('dirs', C.c_void_p), ('frame_vecs', C.c_void_p),
+                ('sample_surface', C.c_int32), ('generate_dirs', C.c_int32), ('generate_frame_vecs', C.c_int32),
+                ('reserved', C.c_int32),
+                ('hit_count', C.c_void_p), ('hits', C.c_void_p), ('overflow', C.c_void_p), ('pair_count', C.c_void_p),
+                ('pair_offset', C.c_void_p), ('pair_ref', C.c_void_p), ('pair_q', C.c_void_p), ('cap_pairs', C.c_int64),
+                ('gs', C.c_void_p), ('contacts', C.c_void_p), ('n_grasps', C.c_void_p), ('colliding', C.c_void_p),
+                ('free_gs', C.c_void_p), ('free_contacts', C.c_void_p), ('n_free', C.c_void_p)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -68,6 +89,11 @@ _SIGNATURES = {
     'bt_gripper_destroy': (C.c_int, [_P]),
     'bt_collide': (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P, _P]),
     'bt_compact': (C.c_int, [_P, C.c_uint8, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    'bt_timer_create': (C.c_int, [C.c_int, C.POINTER(_P)]),
+    'bt_timer_destroy': (C.c_int, [_P]),
+    'bt_timer_read': (C.c_int, [_P, C.POINTER(C.c_float)]),
+    'bt_ags_pipeline': (C.c_int, [_P, _P, _P, C.POINTER(PipelineConfig), C.POINTER(PipelineBuffers), C.c_int64,
+                                  C.c_uint64, _P, _P]),
     'bt_coverage': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     'bt_pairwise_distances': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P]),
 }

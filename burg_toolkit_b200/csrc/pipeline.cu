@@ -1,0 +1,121 @@
+// pipeline.cu -- the whole AGS batch pipeline behind one C-ABI call, plus per-stage CUDA-event timers.
+//
+// Replaces the body of the reference's hot loop (burg_toolkit/sampling.py:220-350) followed by check_collisions
+// (:354-397) for a batch of reference points: the host enqueues ~15 launches on one stream and returns; nothing is
+// copied to or from the host and no stage waits for the CPU.
+#include "common.cuh"
+
+struct bt_timer {
+    int device = 0;
+    cudaEvent_t ev[BT_N_STAGES + 1][2];
+    bool ran[BT_N_STAGES];
+};
+
+namespace bt {
+__global__ void scale_count_kernel(const int64_t* __restrict__ n_pairs, int n_o, int64_t* __restrict__ n_rows) {
+    *n_rows = *n_pairs * n_o;
+}
+}  // namespace bt
+
+using namespace bt;
+
+extern "C" int bt_timer_create(int device, bt_timer** out) {
+    BT_REQUIRE(out, "null pointer");
+    BT_CUDA(cudaSetDevice(device));
+    bt_timer* t = new bt_timer();
+    t->device = device;
+    for (int i = 0; i < BT_N_STAGES; ++i) {
+        t->ran[i] = false;
+        for (int k = 0; k < 2; ++k) {
+            cudaError_t e = cudaEventCreate(&t->ev[i][k]);
+            if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+        }
+    }
+    *out = t;
+    return BT_OK;
+}
+
+extern "C" int bt_timer_destroy(bt_timer* t) {
+    if (!t) return BT_OK;
+    cudaSetDevice(t->device);
+    for (int i = 0; i < BT_N_STAGES; ++i) for (int k = 0; k < 2; ++k) cudaEventDestroy(t->ev[i][k]);
+    delete t;
+    return BT_OK;
+}
+
+extern "C" int bt_timer_read(bt_timer* t, float* h_stage_ms) {
+    BT_REQUIRE(t && h_stage_ms, "null pointer");
+    BT_CUDA(cudaSetDevice(t->device));
+    for (int i = 0; i < BT_N_STAGES; ++i) {
+        h_stage_ms[i] = -1.0f;
+        if (!t->ran[i]) continue;
+        BT_CUDA(cudaEventSynchronize(t->ev[i][1]));
+        BT_CUDA(cudaEventElapsedTime(&h_stage_ms[i], t->ev[i][0], t->ev[i][1]));
+    }
+    return BT_OK;
+}
+
+#define STAGE_BEGIN(i) do { if (timer) { timer->ran[i] = true; BT_CUDA(cudaEventRecord(timer->ev[i][0], st)); } } while (0)
+#define STAGE_END(i)   do { if (timer) BT_CUDA(cudaEventRecord(timer->ev[i][1], st)); } while (0)
+#define STAGE_CALL(expr) do { int _rc = (expr); if (_rc != BT_OK) return _rc; } while (0)
+
+extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, const bt_gripper* gripper,
+                               const bt_pipeline_config* cfg, const bt_pipeline_buffers* b, int64_t n_ref,
+                               uint64_t seed, bt_timer* timer, void* stream) {
+    BT_REQUIRE(target && cfg && b, "null pointer");
+    BT_REQUIRE(n_ref >= 0, "negative count");
+    BT_REQUIRE(b->ref_pts && b->dirs && b->hit_count && b->hits && b->overflow && b->pair_count && b->pair_offset &&
+               b->pair_ref && b->pair_q && b->gs && b->n_grasps, "missing buffer");
+    BT_REQUIRE(b->ref_nrm || (!b->sample_surface && !b->generate_dirs), "reference normals required to generate rays");
+    BT_REQUIRE(cfg->halfspace || b->frame_vecs, "frame vector buffer required unless halfspace");
+    BT_REQUIRE(b->cap_pairs >= n_ref * (int64_t)cfg->max_targets, "cap_pairs too small");
+    BT_REQUIRE(!cfg->check_collisions || (scene && gripper && b->colliding), "collision stage needs scene, gripper and mask buffer");
+    BT_REQUIRE(!cfg->compact || (cfg->check_collisions && b->free_gs && b->n_free), "compaction needs the collision stage and its buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    BT_CUDA(cudaSetDevice(target->m.device));
+    if (timer) for (int i = 0; i < BT_N_STAGES; ++i) timer->ran[i] = false;
+    const int n_o = cfg->n_orientations;
+
+    if (b->sample_surface) {
+        STAGE_BEGIN(0);
+        STAGE_CALL(bt_sample_surface(target, n_ref, seed, b->ref_pts, b->ref_nrm, nullptr, stream));
+        STAGE_END(0);
+    }
+    if (b->generate_dirs) {
+        STAGE_BEGIN(1);
+        STAGE_CALL(bt_cone_rays(b->ref_nrm, n_ref, cfg->n_rays, cfg->ags.angle_max, seed + 0x1000, b->dirs, stream));
+        STAGE_END(1);
+    }
+    STAGE_BEGIN(2);
+    STAGE_CALL(bt_ags_cast(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->overflow, stream));
+    STAGE_END(2);
+    STAGE_BEGIN(3);
+    STAGE_CALL(bt_ags_select(b->hit_count, b->hits, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray, cfg->max_targets,
+                             seed + 0x2000, b->pair_count, b->pair_offset, b->pair_ref, b->pair_q, b->cap_pairs, stream));
+    STAGE_END(3);
+    if (b->generate_frame_vecs && !cfg->halfspace) {
+        STAGE_BEGIN(4);
+        STAGE_CALL(bt_random_unit_vectors(n_ref, seed + 0x3000, b->frame_vecs, stream));
+        STAGE_END(4);
+    }
+    STAGE_BEGIN(5);
+    STAGE_CALL(bt_expand_orientations(b->ref_pts, b->pair_offset, b->pair_ref, b->pair_q, b->frame_vecs, n_ref, b->cap_pairs,
+                                      n_o, cfg->halfspace, cfg->orient_cos, cfg->orient_sin, b->gs, b->contacts, stream));
+    scale_count_kernel<<<1, 1, 0, st>>>(b->pair_offset + n_ref, n_o, b->n_grasps);
+    BT_LAUNCH_CHECK();
+    STAGE_END(5);
+    if (cfg->check_collisions) {
+        const int64_t cap_rows = b->cap_pairs * n_o;
+        STAGE_BEGIN(6);
+        STAGE_CALL(bt_collide(scene, gripper, b->gs, cap_rows, b->n_grasps, cfg->ags.opening_width,
+                              cfg->collision_width_tolerance, cfg->use_width, b->colliding, stream));
+        STAGE_END(6);
+        if (cfg->compact) {
+            STAGE_BEGIN(7);
+            STAGE_CALL(bt_compact(b->colliding, 0, b->gs, b->contacts, cap_rows, b->n_grasps, b->free_gs,
+                                  b->contacts ? b->free_contacts : nullptr, b->n_free, stream));
+            STAGE_END(7);
+        }
+    }
+    return BT_OK;
+}

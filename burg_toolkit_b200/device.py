@@ -175,3 +175,63 @@ def acos_luts(device=None):
         deg = np.rad2deg(rad).astype(np.float32)
         _lut_cache[dev] = (torch.from_numpy(deg).to(f'cuda:{dev}'), torch.from_numpy(rad).to(f'cuda:{dev}'))
     return _lut_cache[dev]
+
+
+class StageTimer:
+    """per-stage CUDA-event timer of ``bt_ags_pipeline`` (``bt_timer``)."""
+
+    def __init__(self, device=None):
+        nat.require_cuda()
+        self.device = device_index(device)
+        handle = C.c_void_p()
+        nat.call('bt_timer_create', self.device, C.byref(handle))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, _destroy, 'bt_timer_destroy', handle)
+
+    def read(self):
+        """-> dict stage name -> milliseconds of the LAST pipeline call (synchronises)"""
+        ms = (C.c_float * nat.N_STAGES)()
+        nat.call('bt_timer_read', self.handle, ms)
+        return {name: float(ms[i]) for i, name in enumerate(nat.STAGE_NAMES) if ms[i] >= 0}
+
+
+class PipelineWorkspace:
+    """All device buffers of one ``bt_ags_pipeline`` call, allocated once per shape (torch owns the memory)."""
+
+    def __init__(self, n_ref, n_rays, cap, n_orientations, max_targets, device, collisions, compact):
+        torch = nat.require_cuda()
+        self.key = (n_ref, n_rays, cap, n_orientations, max_targets, device, collisions, compact)
+        d = f'cuda:{device}'
+        self.n_ref, self.cap_pairs = n_ref, max(1, n_ref * max_targets)
+        rows = self.cap_pairs * n_orientations
+        f64, i32, i64, f32, u8 = torch.float64, torch.int32, torch.int64, torch.float32, torch.uint8
+        self.ref_pts = torch.empty((max(n_ref, 1), 3), dtype=f64, device=d)
+        self.ref_nrm = torch.empty((max(n_ref, 1), 3), dtype=f64, device=d)
+        self.dirs = torch.empty((max(n_ref, 1), n_rays, 3), dtype=f64, device=d)
+        self.frame_vecs = torch.empty((max(n_ref, 1), 3), dtype=f64, device=d)
+        self.hit_count = torch.empty((max(n_ref, 1) * n_rays,), dtype=i32, device=d)
+        self.hits = torch.empty((max(n_ref, 1) * n_rays * cap, 72), dtype=u8, device=d)
+        self.overflow = torch.zeros((1,), dtype=i32, device=d)
+        self.pair_count = torch.empty((max(n_ref, 1),), dtype=i32, device=d)
+        self.pair_offset = torch.zeros((n_ref + 1,), dtype=i64, device=d)
+        self.pair_ref = torch.empty((self.cap_pairs,), dtype=i32, device=d)
+        self.pair_q = torch.empty((self.cap_pairs, 3), dtype=f64, device=d)
+        self.gs = torch.zeros((rows, 14), dtype=f32, device=d)
+        self.contacts = torch.zeros((rows, 2, 3), dtype=f64, device=d)
+        self.n_grasps = torch.zeros((1,), dtype=i64, device=d)
+        self.colliding = torch.zeros((((rows + 3) // 4) * 4,), dtype=u8, device=d) if collisions else None
+        self.free_gs = torch.zeros((rows, 14), dtype=f32, device=d) if compact else None
+        self.free_contacts = torch.zeros((rows, 2, 3), dtype=f64, device=d) if compact else None
+        self.n_free = torch.zeros((1,), dtype=i64, device=d) if compact else None
+        self.rows = rows
+
+    def buffers(self, sample_surface, generate_dirs, generate_frame_vecs):
+        b = nat.PipelineBuffers()
+        for name in ('ref_pts', 'ref_nrm', 'dirs', 'frame_vecs', 'hit_count', 'hits', 'overflow', 'pair_count',
+                     'pair_offset', 'pair_ref', 'pair_q', 'gs', 'contacts', 'n_grasps', 'colliding', 'free_gs',
+                     'free_contacts', 'n_free'):
+            t = getattr(self, name)
+            setattr(b, name, None if t is None else t.data_ptr())
+        b.sample_surface, b.generate_dirs, b.generate_frame_vecs = int(sample_surface), int(generate_dirs), int(generate_frame_vecs)
+        b.cap_pairs = self.cap_pairs
+        return b

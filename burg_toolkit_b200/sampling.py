@@ -250,56 +250,68 @@ class AntipodalGraspSampler:
         return dict(cast=cast, pair_count=pair_count, pair_offset=pair_offset, pair_ref=pair_ref, pair_q=pair_q,
                     gs=gs, contacts=contacts, n_ref=n_ref, cap_pairs=cap_pairs, directions=directions)
 
-    def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, check_collisions=True,
-                     collision_width_tolerance=0.01, use_width=True, additional_objects=None, exclude_shape=False,
-                     compact=True, timers=None):
-        """The whole device pipeline for one batch of candidates, nothing leaves the GPU:
+    def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, directions=None, frame_vecs=None,
+                     check_collisions=True, collision_width_tolerance=0.01, use_width=True, additional_objects=None,
+                     exclude_shape=False, compact=True, timer=None):
+        """The whole device pipeline for one batch of candidates in ONE C-ABI call (``bt_ags_pipeline``); nothing
+        leaves the GPU and the host never waits:
 
-            [S1 surface samples] -> S2 cone rays -> R1-R6 cast + filters -> R7 target choice -> O1/O2 orientation
+            [S1 surface samples] -> [S2 cone rays] -> R1-R6 cast + filters -> R7 target choice -> O1/O2 orientation
             expansion -> [K1 gripper-vs-scene collision -> ballot/scan compaction of the collision-free grasps]
 
         ``ref_points`` / ``ref_normals``: [n_ref, 3] numpy arrays or CUDA tensors; if None, ``n_ref`` points are
-        drawn on the device (S1).  Candidates evaluated = n_ref * n_rays.
-        ``timers``: optional dict name -> list; CUDA event pairs around each stage are appended (bench.py).
-        -> dict of CUDA tensors (``gs``, ``contacts``, ``colliding``, ``n_grasps`` ...)."""
+        drawn on the device (S1).  ``directions`` / ``frame_vecs``: host-seeded inputs for parity runs, else device
+        RNG keyed by ``seed``.  Candidates evaluated = n_ref * n_rays.  ``timer``: optional ``device.StageTimer``.
+        -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
         torch = nat.require_cuda()
         device = self._device()
-
-        def stage(name, fn, *a, **k):
-            if timers is None:
-                return fn(*a, **k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            timers.setdefault(name, []).append((e0, e1))
-            return r
-
+        dm = self._device_mesh()
+        if ref_points is not None:
+            n_ref = len(ref_points)
+        n_ref = int(n_ref)
+        n_o, k, cap = int(self.n_orientations), int(self.max_targets_per_ref_point), int(self.max_hits_per_ray)
+        if not 1 <= n_o <= 64:
+            raise ValueError('n_orientations must be in [1, 64]')
+        key = (n_ref, int(self.n_rays), cap, n_o, k, device, bool(check_collisions), bool(check_collisions and compact))
+        ws = getattr(self, '_workspace', None)
+        if ws is None or ws.key != key:
+            ws = self._workspace = dev.PipelineWorkspace(*key)
         with torch.cuda.device(device):
-            if ref_points is None:
-                pts, nrm, _ = stage('sample_surface', self.sample_surface, int(n_ref), seed)
-            else:
-                pts = self._tensor(ref_points, torch.float64).reshape(-1, 3)
-                nrm = self._tensor(ref_normals, torch.float64).reshape(-1, 3)
-            n_ref = pts.shape[0]
-            dirs = stage('cone_rays', self.cone_rays, nrm, seed)
-            cast = stage('cast', self.cast, pts, dirs, None, False)
-            pair_count, pair_offset, pair_ref, pair_q, cap_pairs = stage('select', self.select, cast, seed + 1)
-            fv = None if self.only_grasp_from_above else stage('frame_vectors', self.frame_vectors, n_ref, seed + 2)
-            gs, contacts = stage('expand', self.expand, pts, pair_offset, pair_ref, pair_q, fv, cap_pairs)
-            n_rows = pair_offset[n_ref:n_ref + 1] * int(self.n_orientations)        # device scalar, no sync
-            out = dict(n_ref=n_ref, n_candidates=n_ref * int(self.n_rays), cast=cast, pair_count=pair_count,
-                       pair_offset=pair_offset, gs=gs, contacts=contacts, n_grasps=n_rows, overflow=cast.overflow)
+            if ref_points is not None:
+                ws.ref_pts.copy_(self._tensor(ref_points, torch.float64).reshape(-1, 3), non_blocking=True)
+                if ref_normals is not None:
+                    ws.ref_nrm.copy_(self._tensor(ref_normals, torch.float64).reshape(-1, 3), non_blocking=True)
+            if directions is not None:
+                ws.dirs.copy_(self._tensor(directions, torch.float64).reshape(n_ref, -1, 3), non_blocking=True)
+            if frame_vecs is not None:
+                ws.frame_vecs.copy_(self._tensor(frame_vecs, torch.float64).reshape(-1, 3), non_blocking=True)
+            cfg = nat.PipelineConfig()
+            cfg.ags = self._params(cap)
+            cfg.n_rays, cfg.n_orientations, cfg.max_targets = int(self.n_rays), n_o, k
+            cfg.halfspace = 1 if self.only_grasp_from_above else 0
+            cfg.check_collisions, cfg.use_width = int(bool(check_collisions)), int(bool(use_width))
+            cfg.compact = int(bool(check_collisions and compact))
+            cfg.collision_width_tolerance = float(collision_width_tolerance)
+            cos_t, sin_t = _orientation_tables(n_o, cfg.halfspace)
+            cfg.orient_cos[:n_o] = cos_t.tolist()
+            cfg.orient_sin[:n_o] = sin_t.tolist()
+            scene = gripper = None
             if check_collisions:
                 meshes = ([] if exclude_shape else [self.mesh]) + list(additional_objects or [])
                 scene = self._scene(meshes, device)
                 gripper = self._device_gripper(device)
-                colliding = stage('collide', collide_rows, scene, gripper, gs, float(self.gripper.opening_width),
-                                  float(collision_width_tolerance), bool(use_width), n_rows)
-                out['colliding'] = colliding
-                if compact:
-                    free_gs, free_contacts, n_free = stage('compact', compact_rows, colliding, 0, gs, contacts, n_rows)
-                    out.update(free_gs=free_gs, free_contacts=free_contacts, n_free=n_free)
+            bufs = ws.buffers(ref_points is None, directions is None, frame_vecs is None)
+            nat.call('bt_ags_pipeline', dm.handle, None if scene is None else scene.handle,
+                     None if gripper is None else gripper.handle, C.byref(cfg), C.byref(bufs), n_ref, int(seed),
+                     None if timer is None else timer.handle, nat.current_stream())
+        out = dict(n_ref=n_ref, n_candidates=n_ref * int(self.n_rays), pair_count=ws.pair_count, pair_offset=ws.pair_offset,
+                   pair_ref=ws.pair_ref, pair_q=ws.pair_q, gs=ws.gs, contacts=ws.contacts, n_grasps=ws.n_grasps,
+                   overflow=ws.overflow, ref_pts=ws.ref_pts, ref_nrm=ws.ref_nrm, directions=ws.dirs,
+                   cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap), cap_pairs=ws.cap_pairs)
+        if check_collisions:
+            out['colliding'] = ws.colliding[:ws.rows]
+            if compact:
+                out.update(free_gs=ws.free_gs, free_contacts=ws.free_contacts, n_free=ws.n_free)
         return out
 
     def evaluate_host(self, ref_points, ref_normals, seed=1, pinned=None, **kwargs):

@@ -178,6 +178,52 @@ BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_
                int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
                void* stream);
 
+/* ---- the whole AGS pipeline in ONE call (what AntipodalGraspSampler.sample's loop body + check_collisions do
+ * per batch, sampling.py:220-350 and :354-397): [S1] -> [S2] -> R1..R6 -> R7 -> [frame vectors] -> O1/O2 ->
+ * [K1 -> compaction].  All buffers are caller-allocated device memory (torch tensors in the Python mirror); the call
+ * only enqueues kernels on `stream` and never synchronises.  bt_timer (optional) records one CUDA event per stage
+ * boundary so a benchmark can read per-stage device times afterwards. */
+typedef struct bt_timer bt_timer;
+#define BT_N_STAGES 8        /* sample_surface, cone_rays, cast, select, frame_vectors, expand, collide, compact */
+BT_API int bt_timer_create(int device, bt_timer** out);
+BT_API int bt_timer_destroy(bt_timer* timer);
+BT_API int bt_timer_read(bt_timer* timer, float* h_stage_ms /* [BT_N_STAGES], -1 for stages that did not run */);  /* synchronises */
+
+typedef struct bt_pipeline_config {
+    bt_ags_params ags;
+    int32_t n_rays, n_orientations, max_targets, halfspace;
+    int32_t check_collisions, use_width, compact, reserved;
+    double  collision_width_tolerance;
+    double  orient_cos[64], orient_sin[64];   /* numpy-evaluated cos/sin of the orientation angles */
+} bt_pipeline_config;
+
+typedef struct bt_pipeline_buffers {
+    double*  ref_pts;        /* [n_ref,3]   in, or out of S1 when sample_surface != 0       */
+    double*  ref_nrm;        /* [n_ref,3]                                                    */
+    double*  dirs;           /* [n_ref,n_rays,3] in, or out of S2 when generate_dirs != 0    */
+    double*  frame_vecs;     /* [n_ref,3]   in, or generated when generate_frame_vecs != 0   */
+    int32_t  sample_surface, generate_dirs, generate_frame_vecs, reserved;
+    int32_t* hit_count;      /* [n_ref*n_rays]                                               */
+    bt_hit*  hits;           /* [n_ref*n_rays*max_hits_per_ray]                              */
+    int32_t* overflow;       /* [1]                                                          */
+    int32_t* pair_count;     /* [n_ref]                                                      */
+    int64_t* pair_offset;    /* [n_ref+1]                                                    */
+    int32_t* pair_ref;       /* [cap_pairs]                                                  */
+    double*  pair_q;         /* [cap_pairs,3]                                                */
+    int64_t  cap_pairs;      /* >= n_ref * max_targets                                       */
+    float*   gs;             /* [cap_pairs*n_orientations,14]                                */
+    double*  contacts;       /* [cap_pairs*n_orientations,2,3]                               */
+    int64_t* n_grasps;       /* [1] number of posed grasps = pairs * n_orientations          */
+    uint8_t* colliding;      /* [cap rows, padded to 4]   (check_collisions)                 */
+    float*   free_gs;        /* [cap rows,14]             (compact)                          */
+    double*  free_contacts;  /* [cap rows,2,3]            (compact)                          */
+    int64_t* n_free;         /* [1]                       (compact)                          */
+} bt_pipeline_buffers;
+
+BT_API int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, const bt_gripper* gripper,
+                    const bt_pipeline_config* config, const bt_pipeline_buffers* buffers, int64_t n_ref,
+                    uint64_t seed, bt_timer* timer, void* stream);
+
 /* ---- M1..M5: coverage (replaces metrics.coverage / coverage_brute_force, metrics.py:141-229, and the
  * distance functions they call, :9-77).  covered[i] = any_j ( 1000*|t_i - t_j| + deg(R_i, R_j) <= eps ),
  * all float32 in the reference's operation order; deg() goes through the caller-supplied 20001-entry
