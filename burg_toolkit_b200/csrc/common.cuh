@@ -33,12 +33,27 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// keep freed scratch memory in the device's default pool across synchronisation points (the default release
+// threshold of 0 hands it back to the driver at every sync, which turns the next cudaMallocAsync into a ~ms call)
+inline void retain_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 // stream-ordered scratch buffer (cudaMallocAsync / cudaFreeAsync)
 struct Scratch {
     void* p = nullptr;
     cudaStream_t s = nullptr;
     cudaError_t alloc(size_t bytes, cudaStream_t stream) {
         s = stream;
+        retain_pool_memory();
         return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
     }
     ~Scratch() { if (p) cudaFreeAsync(p, s); }
