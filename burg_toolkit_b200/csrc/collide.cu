@@ -10,6 +10,7 @@
 // conservative float32 box test; at the leaves the float64 17-axis test runs on the world-space vertices.
 #include <cub/cub.cuh>
 #include <math.h>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -139,18 +140,60 @@ __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, 
     return 2;
 }
 
-constexpr int PEND = 8;                    // undecided leaves a thread may hold before the warp flushes them
+// ---- persistent collision kernel --------------------------------------------------------------------------------
+// Work item = (gripper part, grasp).  Traversal lengths differ by orders of magnitude between items (a stem far from the
+// object ends at the root, a finger grazing the surface visits hundreds of nodes), so items are NOT bound to threads:
+// warps are persistent and every lane fetches a new item from a global counter as soon as enough lanes of its warp have
+// run dry (refill at >= 8 idle lanes keeps both the set-up code and the traversal loop well filled).
+//   phase A (per lane): the part's oriented box walks the scene LBVH (float32, conservative 6-axis test); each reached
+//                       triangle is classified disjoint / inside-a-closed-box / undecided; undecided leaves are parked.
+//   phase B (per warp): parked leaves are drained with FCL's exact float64 17-axis test, lane l <-> gripper triangle l.
+constexpr int PEND = 6;                    // undecided leaves a lane may park before the warp drains
+constexpr int REFILL_AT = 8;               // idle lanes that trigger a refill
 
-// One thread per (gripper part, grasp) walks the scene LBVH with the part's oriented box (float32, conservative) and
-// classifies every reached scene triangle (disjoint / inside a closed box / undecided).  Undecided leaves are parked in a
-// small per-thread list; whenever a list is full or the warp's traversals are done, the WARP runs the exact float64
-// test cooperatively: lane l tests gripper triangle l of the owner's part against the parked scene triangle, so the
-// expensive 17-axis tests run 12..32 wide instead of on one lane.
+struct LaneBox {
+    float u[3][3];                         // world axes (columns of R), un-normalised
+    float h[3], a[3];                      // half extents: along the axes (projection units) / of the world AABB, inflated
+    float inv_n[3], le[3];                 // 1/|axis|, half extents in metres
+    float cf[3];                           // centre (float32)
+    double c[3];                           // centre (float64, for the leaf classifier)
+    float margin;
+    int tri_begin, tri_end, is_box;
+};
+
+__device__ __forceinline__ bool lanebox_overlaps(const LaneBox& b, float x0, float y0, float z0, float x1, float y1, float z1) {
+    const float ex = 0.5f * (x1 - x0), ey = 0.5f * (y1 - y0), ez = 0.5f * (z1 - z0);
+    const float dx = 0.5f * (x1 + x0) - b.cf[0], dy = 0.5f * (y1 + y0) - b.cf[1], dz = 0.5f * (z1 + z0) - b.cf[2];
+    if (fabsf(dx) > ex + b.a[0] || fabsf(dy) > ey + b.a[1] || fabsf(dz) > ez + b.a[2]) return false;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float pr = fabsf(fmaf(dx, b.u[j][0], fmaf(dy, b.u[j][1], dz * b.u[j][2])));
+        if (pr > b.h[j] + fmaf(ex, fabsf(b.u[j][0]), fmaf(ey, fabsf(b.u[j][1]), ez * fabsf(b.u[j][2])))) return false;
+    }
+    return true;
+}
+
+// pose * diag(s,1,1): M (row-major 3x3) and T of grasp `row`  (sampling.py:392-395; s in float32 as numpy >= 2 does)
+__device__ __forceinline__ void grasp_affine(const float* __restrict__ gs, int64_t row, float ow, float tol, int use_width,
+                                             double M[9], double T[3], float& sf_out) {
+    const float* g = gs + 14 * row;
+    const float sf = use_width ? (__ldg(g + 13) + tol) / ow : 1.0f;
+    const double s = (double)sf;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        M[3 * i + 0] = (double)__ldg(g + 3 + 3 * i) * s;
+        M[3 * i + 1] = (double)__ldg(g + 4 + 3 * i);
+        M[3 * i + 2] = (double)__ldg(g + 5 + 3 * i);
+        T[i] = (double)__ldg(g + i);
+    }
+    sf_out = sf;
+}
+
 __global__ void __launch_bounds__(128, 4)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
                int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
                const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
-               unsigned int* __restrict__ out_words) {
+               unsigned long long* __restrict__ work_counter, uint8_t* __restrict__ out) {
     extern __shared__ double s_gtris[];            // gripper triangles, TCP frame
     __shared__ PartDev s_parts[MAX_PARTS];
     const int n_gt = parts[n_parts - 1].tri_end;
@@ -158,81 +201,81 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_parts[i] = parts[i];
     __syncthreads();
 
-    // part-major: consecutive threads pose the SAME part for consecutive grasps (the orientations of one contact
-    // pair), so a warp walks the same region of the LBVH
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    int part = (int)(idx / n_cap);
-    int64_t row = idx - (int64_t)part * n_cap;
-    bool traversing = (part < n_parts) && (row < n);
-    if (!traversing) { part = 0; row = 0; }
-    const unsigned int bit = 1u << (8 * (row & 3));
-    if (traversing && (*((volatile unsigned int*)out_words + (row >> 2)) & bit)) traversing = false;   // another part already collides
+    const int64_t total = n * n_parts;             // item = part * n + row  (part-major: neighbouring items share a region)
 
-    const float* g = gs + 14 * row;
-    float gf[14];
-#pragma unroll
-    for (int k = 0; k < 14; ++k) gf[k] = traversing ? __ldg(g + k) : 0.f;
-    // sampling.py:392-394 in float32 (numpy >= 2 scalar promotion): s = (width + tol) / opening_width
-    const float sf = use_width ? (gf[13] + tol) / ow : 1.0f;
-    const double s = (double)sf;
-    // M = pose[:3,:3] @ diag(s,1,1); T = pose[:3,3]
-    const double m00 = (double)gf[3] * s, m01 = gf[4], m02 = gf[5];
-    const double m10 = (double)gf[6] * s, m11 = gf[7], m12 = gf[8];
-    const double m20 = (double)gf[9] * s, m21 = gf[10], m22 = gf[11];
-    const double tx = gf[0], ty = gf[1], tz = gf[2];
-
-    const PartDev pd = s_parts[part];
-    Obb b;
-    b.ux[0] = gf[3]; b.ux[1] = gf[6]; b.ux[2] = gf[9];
-    b.uy[0] = gf[4]; b.uy[1] = gf[7]; b.uy[2] = gf[10];
-    b.uz[0] = gf[5]; b.uz[1] = gf[8]; b.uz[2] = gf[11];
-    const double cxd = (m00 * pd.cx + m01 * pd.cy) + m02 * pd.cz + tx;
-    const double cyd = (m10 * pd.cx + m11 * pd.cy) + m12 * pd.cz + ty;
-    const double czd = (m20 * pd.cx + m21 * pd.cy) + m22 * pd.cz + tz;
-    b.cx = (float)cxd; b.cy = (float)cyd; b.cz = (float)czd;
-    // the rotation block of a float32 grasp row is orthonormal only to ~1e-7; scale the half extents by the
-    // actual column norms (+ margin) so the box test stays conservative
-    const float nx = sqrtf(b.ux[0] * b.ux[0] + b.ux[1] * b.ux[1] + b.ux[2] * b.ux[2]);
-    const float ny = sqrtf(b.uy[0] * b.uy[0] + b.uy[1] * b.uy[1] + b.uy[2] * b.uy[2]);
-    const float nz = sqrtf(b.uz[0] * b.uz[0] + b.uz[1] * b.uz[1] + b.uz[2] * b.uz[2]);
-    b.h[0] = pd.hx * fabsf(sf) * nx * nx * 1.0001f + inflate;      // projections use the un-normalised axes
-    b.h[1] = pd.hy * ny * ny * 1.0001f + inflate;
-    b.h[2] = pd.hz * nz * nz * 1.0001f + inflate;
-    {
-        const float e0 = pd.hx * fabsf(sf) * 1.0001f, e1 = pd.hy * 1.0001f, e2 = pd.hz * 1.0001f;
-        b.ax = fabsf(b.ux[0]) * e0 + fabsf(b.uy[0]) * e1 + fabsf(b.uz[0]) * e2 + inflate;
-        b.ay = fabsf(b.ux[1]) * e0 + fabsf(b.uy[1]) * e1 + fabsf(b.uz[1]) * e2 + inflate;
-        b.az = fabsf(b.ux[2]) * e0 + fabsf(b.uy[2]) * e1 + fabsf(b.uz[2]) * e2 + inflate;
-    }
-    // box-local frame for the leaf classifier: unit axes and half extents in metres
-    const float inx = nx > 0.f ? 1.0f / nx : 0.f, iny = ny > 0.f ? 1.0f / ny : 0.f, inz = nz > 0.f ? 1.0f / nz : 0.f;
-    const float le0 = pd.hx * fabsf(sf) * nx, le1 = pd.hy * ny, le2 = pd.hz * nz;
-    const float cls_margin = inflate + 1e-4f * fmaxf(le0, fmaxf(le1, le2));
-
+    LaneBox b;
+    int64_t row = 0;
     int stack[CSTACK];
     int pend[PEND];
-    int sp = 0, np = 0;
-    int cur = 0;
-    bool collided = false;
+    int sp = 0, np = 0, cur = 0;
+    bool busy = false, exhausted = false;
+
     while (true) {
-        // ---- phase A: traverse until this thread's walk ends or its pending list is full -------------------------
-        while (traversing && np < PEND) {
+        // ---- refill --------------------------------------------------------------------------------------------------
+        const unsigned idle = __ballot_sync(FULL, !busy);
+        if (!exhausted && (__popc(idle) >= REFILL_AT)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (!busy) {
+                const int64_t item = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (item < total) {
+                    const int part = (int)(item / n);
+                    row = item - (int64_t)part * n;
+                    if (!out[row]) {                                       // another part of this grasp may already collide
+                        double M[9], T[3];
+                        float sf;
+                        grasp_affine(gs, row, ow, tol, use_width, M, T, sf);
+                        const PartDev pd = s_parts[part];
+                        const float* g = gs + 14 * row;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) { b.u[j][0] = __ldg(g + 3 + j); b.u[j][1] = __ldg(g + 6 + j); b.u[j][2] = __ldg(g + 9 + j); }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            b.c[i] = (M[3 * i] * pd.cx + M[3 * i + 1] * pd.cy) + M[3 * i + 2] * pd.cz + T[i];
+                            b.cf[i] = (float)b.c[i];
+                        }
+                        const float ext[3] = {pd.hx * fabsf(sf), pd.hy, pd.hz};
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            // a float32 rotation block is orthonormal only to ~1e-7: use the actual column norms
+                            const float nn = sqrtf(b.u[j][0] * b.u[j][0] + b.u[j][1] * b.u[j][1] + b.u[j][2] * b.u[j][2]);
+                            b.h[j] = ext[j] * nn * nn * 1.0001f + inflate;
+                            b.inv_n[j] = nn > 0.f ? 1.0f / nn : 0.f;
+                            b.le[j] = ext[j] * nn;
+                        }
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            b.a[a] = (fabsf(b.u[0][a]) * ext[0] + fabsf(b.u[1][a]) * ext[1] + fabsf(b.u[2][a]) * ext[2]) * 1.0001f + inflate;
+                        b.margin = inflate + 1e-4f * fmaxf(b.le[0], fmaxf(b.le[1], b.le[2]));
+                        b.tri_begin = pd.tri_begin; b.tri_end = pd.tri_end; b.is_box = pd.is_box;
+                        busy = true; sp = 0; np = 0; cur = 0;
+                    }
+                }
+            }
+            if (base + (unsigned long long)__popc(idle) >= (unsigned long long)total) exhausted = true;
+        }
+        if (!__any_sync(FULL, busy)) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- phase A: a bounded burst of traversal steps ---------------------------------------------------------------
+        for (int step = 0; step < 16 && busy && np < PEND; ++step) {
             if (cur < 0) {
                 const double* tv = tri_verts + 9 * (int64_t)(~cur);
                 float q[3][3];
 #pragma unroll
                 for (int v = 0; v < 3; ++v) {
-                    const float dx = (float)(tv[3 * v] - cxd), dy = (float)(tv[3 * v + 1] - cyd), dz = (float)(tv[3 * v + 2] - czd);
-                    q[v][0] = fmaf(dx, b.ux[0], fmaf(dy, b.ux[1], dz * b.ux[2])) * inx;
-                    q[v][1] = fmaf(dx, b.uy[0], fmaf(dy, b.uy[1], dz * b.uy[2])) * iny;
-                    q[v][2] = fmaf(dx, b.uz[0], fmaf(dy, b.uz[1], dz * b.uz[2])) * inz;
+                    const float dx = (float)(tv[3 * v] - b.c[0]), dy = (float)(tv[3 * v + 1] - b.c[1]), dz = (float)(tv[3 * v + 2] - b.c[2]);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) q[v][j] = fmaf(dx, b.u[j][0], fmaf(dy, b.u[j][1], dz * b.u[j][2])) * b.inv_n[j];
                 }
-                const int cls = classify_triangle(q, le0, le1, le2, cls_margin);
-                if (!(cls == 0 || (cls == 1 && pd.is_box))) pend[np++] = ~cur;
-                if (sp == 0) { traversing = false; break; }
+                const int cls = classify_triangle(q, b.le[0], b.le[1], b.le[2], b.margin);
+                if (!(cls == 0 || (cls == 1 && b.is_box))) pend[np++] = ~cur;
+                if (sp == 0) { busy = false; break; }
                 cur = stack[--sp];
                 continue;
             }
@@ -240,25 +283,25 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
             const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
             const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
             const float4 q3 = __ldg(nodes + 4 * (int64_t)cur + 3);
-            const bool hl = obb_overlaps_aabb(b, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-            const bool hr = obb_overlaps_aabb(b, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+            const bool hl = lanebox_overlaps(b, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+            const bool hr = lanebox_overlaps(b, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
             const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
             if (hl && hr) { stack[sp++] = r; cur = l; }
             else if (hl) cur = l;
             else if (hr) cur = r;
-            else { if (sp == 0) { traversing = false; break; } cur = stack[--sp]; }
+            else { if (sp == 0) { busy = false; break; } cur = stack[--sp]; }
         }
         __syncwarp();
-        // ---- phase B: the warp drains every lane's pending list with the exact test ---------------------------------
-        unsigned has = __ballot_sync(FULL, np > 0);
+        // ---- phase B: drain parked leaves of lanes that are full or finished ------------------------------------------
+        unsigned has = __ballot_sync(FULL, np > 0 && (np >= PEND || !busy));
         while (has) {
             const int src = __ffs(has) - 1;
             const int cnt = __shfl_sync(FULL, np, src);
-            const int tb = __shfl_sync(FULL, pd.tri_begin, src), te = __shfl_sync(FULL, pd.tri_end, src);
-            const double b00 = __shfl_sync(FULL, m00, src), b01 = __shfl_sync(FULL, m01, src), b02 = __shfl_sync(FULL, m02, src);
-            const double b10 = __shfl_sync(FULL, m10, src), b11 = __shfl_sync(FULL, m11, src), b12 = __shfl_sync(FULL, m12, src);
-            const double b20 = __shfl_sync(FULL, m20, src), b21 = __shfl_sync(FULL, m21, src), b22 = __shfl_sync(FULL, m22, src);
-            const double ux = __shfl_sync(FULL, tx, src), uy = __shfl_sync(FULL, ty, src), uz = __shfl_sync(FULL, tz, src);
+            const int tb = __shfl_sync(FULL, b.tri_begin, src), te = __shfl_sync(FULL, b.tri_end, src);
+            const int64_t srow = __shfl_sync(FULL, row, src);
+            double M[9], T[3];
+            float sf;
+            grasp_affine(gs, srow, ow, tol, use_width, M, T, sf);        // same address in every lane: broadcast loads
             bool found = false;
             for (int k = 0; k < cnt && !found; ++k) {
                 const int leaf = __shfl_sync(FULL, pend[k < PEND ? k : 0], src);
@@ -273,8 +316,8 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
 #pragma unroll
                         for (int v = 0; v < 3; ++v) {
                             const double px = gt[3 * v], py = gt[3 * v + 1], pz = gt[3 * v + 2];
-                            Q[v] = mk3(((b00 * px + b01 * py) + b02 * pz) + ux, ((b10 * px + b11 * py) + b12 * pz) + uy,
-                                       ((b20 * px + b21 * py) + b22 * pz) + uz);
+                            Q[v] = mk3(((M[0] * px + M[1] * py) + M[2] * pz) + T[0], ((M[3] * px + M[4] * py) + M[5] * pz) + T[1],
+                                       ((M[6] * px + M[7] * py) + M[8] * pz) + T[2]);
                         }
                         hit = tri_tri_intersect(P1, P2, P3, Q[0], Q[1], Q[2]);
                     }
@@ -283,13 +326,11 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
             }
             if (lane == src) {
                 np = 0;
-                if (found) { collided = true; traversing = false; }
+                if (found) { out[row] = 1; busy = false; }
             }
-            has = __ballot_sync(FULL, np > 0);
+            has = __ballot_sync(FULL, np > 0 && (np >= PEND || !busy));
         }
-        if (!__any_sync(FULL, traversing)) break;
     }
-    if (collided) atomicOr(out_words + (row >> 2), bit);
 }
 
 // ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------
@@ -448,12 +489,18 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
         max_abs = fmaxf(max_abs, fmaxf(fabsf(scene->m.info.bounds_min[k]), fabsf(scene->m.info.bounds_max[k])));
     const float inflate = 2e-5f * max_abs + 1e-6f;
     const size_t tri_bytes = sizeof(double) * 9 * (size_t)gripper->n_tris;
-    if (tri_bytes > 48 * 1024)
+    if (tri_bytes > 8 * 1024)
         BT_CUDA(cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
-    const int64_t threads = n * gripper->n_parts;          // part-major: thread = part * n + row
-    collide_kernel<<<(unsigned)ceil_div(threads, 128), 128, tri_bytes, st>>>(
+    Scratch counter;
+    BT_CUDA(counter.alloc(sizeof(unsigned long long), st));
+    BT_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->m.device);
+    const int64_t items = n * gripper->n_parts;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * 4);   // persistent: 4 CTAs / SM
+    collide_kernel<<<grid, 128, tri_bytes, st>>>(
         scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
-        (float)opening_width, (float)width_tolerance, use_width, inflate, reinterpret_cast<unsigned int*>(d_colliding));
+        (float)opening_width, (float)width_tolerance, use_width, inflate, counter.as<unsigned long long>(), d_colliding);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
