@@ -10,6 +10,7 @@
 // conservative float32 box test; at the leaves the float64 17-axis test runs on the world-space vertices.
 #include <cub/cub.cuh>
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -20,11 +21,17 @@ namespace bt {
 constexpr int CSTACK = 64;
 constexpr int MAX_PARTS = 64;
 
+// One traversal item of the gripper: a (sub-)box of a part in the TCP frame plus the part it belongs to.  Long thin parts
+// (fingers, the stem) are cut into segments along their longest axis: a short box overlaps far fewer LBVH nodes than a
+// long one grazing the surface, which removes the heavy tail of the per-item work distribution.  The exact test always
+// uses ALL triangles of the part; the segment only drives the conservative broad phase.
 struct PartDev {
-    float cx, cy, cz;      // box centre, TCP frame
-    float hx, hy, hz;      // half extents
+    float cx, cy, cz;      // segment centre, TCP frame
+    float hx, hy, hz;      // segment half extents
+    float ox, oy, oz;      // segment centre minus full-part centre, TCP frame
+    float fhx, fhy, fhz;   // full part half extents
     int32_t tri_begin, tri_end;
-    int32_t is_box;        // the part's triangles are exactly the 12 faces of its box (closed surface)
+    int32_t is_box;        // the part's triangles are exactly the 12 faces of its (full) box: a closed surface
 };
 
 // FCL Intersect::project6: true if `ax` does NOT separate {p1,p2,p3} from {q1,q2,q3}
@@ -97,14 +104,16 @@ __device__ __forceinline__ bool obb_overlaps_aabb(const Obb& b, float x0, float 
 //   1 = certainly strictly inside the box (all vertices inside the box shrunk by `m`)  -- only meaningful for is_box parts:
 //       a triangle inside a closed box cannot touch the box's surface triangles
 //   2 = undecided -> run the exact float64 test
-__device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, float e1, float e2, float m) {
+__device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, float e1, float e2, float m,
+                                                 const float off[3], const float fe[3]) {
     const float E[3] = {e0 + m, e1 + m, e2 + m};
     bool inside = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float lo = fminf(q[0][k], fminf(q[1][k], q[2][k])), hi = fmaxf(q[0][k], fmaxf(q[1][k], q[2][k]));
         if (lo > E[k] || hi < -E[k]) return 0;
-        inside = inside && (lo > -(E[k] - 2.f * m)) && (hi < (E[k] - 2.f * m));
+        // 'inside' is judged against the FULL part box (coordinates shifted by the segment offset), shrunk by m
+        inside = inside && (lo + off[k] > -(fe[k] - m)) && (hi + off[k] < (fe[k] - m));
     }
     if (inside) return 1;
     // triangle plane
@@ -155,6 +164,7 @@ struct LaneBox {
     float u[3][3];                         // world axes (columns of R), un-normalised
     float h[3], a[3];                      // half extents: along the axes (projection units) / of the world AABB, inflated
     float inv_n[3], le[3];                 // 1/|axis|, half extents in metres
+    float off[3], fe[3];                   // segment offset inside the full part box / full half extents, metres
     float cf[3];                           // centre (float32)
     double c[3];                           // centre (float64, for the leaf classifier)
     float margin;
@@ -246,6 +256,9 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
                             b.h[j] = ext[j] * nn * nn * 1.0001f + inflate;
                             b.inv_n[j] = nn > 0.f ? 1.0f / nn : 0.f;
                             b.le[j] = ext[j] * nn;
+                            const float sc = (j == 0) ? fabsf(sf) : 1.0f;
+                            b.off[j] = (j == 0 ? pd.ox : (j == 1 ? pd.oy : pd.oz)) * (j == 0 ? sf : 1.0f) * nn;
+                            b.fe[j] = (j == 0 ? pd.fhx : (j == 1 ? pd.fhy : pd.fhz)) * sc * nn;
                         }
 #pragma unroll
                         for (int a = 0; a < 3; ++a)
@@ -273,7 +286,7 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
 #pragma unroll
                     for (int j = 0; j < 3; ++j) q[v][j] = fmaf(dx, b.u[j][0], fmaf(dy, b.u[j][1], dz * b.u[j][2])) * b.inv_n[j];
                 }
-                const int cls = classify_triangle(q, b.le[0], b.le[1], b.le[2], b.margin);
+                const int cls = classify_triangle(q, b.le[0], b.le[1], b.le[2], b.margin, b.off, b.fe);
                 if (!(cls == 0 || (cls == 1 && b.is_box))) pend[np++] = ~cur;
                 if (sp == 0) { busy = false; break; }
                 cur = stack[--sp];
@@ -435,24 +448,39 @@ extern "C" int bt_gripper_create(const double* h_tris, int32_t n_gt, const bt_gr
     BT_REQUIRE(h_tris && h_parts && out, "null pointer");
     BT_REQUIRE(n_gt > 0 && n_parts > 0 && n_parts <= MAX_PARTS, "bad counts (1 <= n_parts <= 64)");
     BT_REQUIRE(9 * (size_t)n_gt * sizeof(double) <= 160 * 1024, "gripper mesh too large for shared memory staging");
-    std::vector<PartDev> parts(n_parts);
+    std::vector<PartDev> parts;
     int expect = 0;
+    double seg_len = 0.048;                                    // metres; BT_COLLIDE_SEG overrides (tuning knob)
+    if (const char* e = getenv("BT_COLLIDE_SEG")) { const double v = atof(e); if (v > 0) seg_len = v; }
     for (int p = 0; p < n_parts; ++p) {
         const bt_gripper_part& hp = h_parts[p];
         BT_REQUIRE(hp.tri_begin == expect && hp.tri_end > hp.tri_begin && hp.tri_end <= n_gt, "parts must tile [0, n_tris)");
         expect = hp.tri_end;
-        parts[p].cx = (float)(0.5 * (hp.box_min[0] + hp.box_max[0]));
-        parts[p].cy = (float)(0.5 * (hp.box_min[1] + hp.box_max[1]));
-        parts[p].cz = (float)(0.5 * (hp.box_min[2] + hp.box_max[2]));
-        // half extents rounded up a little: the box must contain every triangle of the part
-        parts[p].hx = (float)(0.5 * (hp.box_max[0] - hp.box_min[0])) * 1.00001f + 1e-9f;
-        parts[p].hy = (float)(0.5 * (hp.box_max[1] - hp.box_min[1])) * 1.00001f + 1e-9f;
-        parts[p].hz = (float)(0.5 * (hp.box_max[2] - hp.box_min[2])) * 1.00001f + 1e-9f;
-        parts[p].tri_begin = hp.tri_begin;
-        parts[p].tri_end = hp.tri_end;
-        parts[p].is_box = part_is_closed_box(h_tris, hp) ? 1 : 0;
+        double c[3], h[3];
+        for (int k = 0; k < 3; ++k) { c[k] = 0.5 * (hp.box_min[k] + hp.box_max[k]); h[k] = 0.5 * (hp.box_max[k] - hp.box_min[k]); }
+        int axis = 0;
+        if (h[1] > h[axis]) axis = 1;
+        if (h[2] > h[axis]) axis = 2;
+        int nseg = (int)ceil(2.0 * h[axis] / seg_len);
+        if (nseg < 1) nseg = 1;
+        if ((int)parts.size() + nseg + (n_parts - p - 1) > MAX_PARTS) nseg = 1;      // stay within the shared-memory table
+        const int is_box = part_is_closed_box(h_tris, hp) ? 1 : 0;
+        for (int sgm = 0; sgm < nseg; ++sgm) {
+            PartDev d;
+            double sc[3] = {c[0], c[1], c[2]}, sh[3] = {h[0], h[1], h[2]};
+            sh[axis] = h[axis] / nseg;
+            sc[axis] = c[axis] - h[axis] + (2 * sgm + 1) * sh[axis];
+            d.cx = (float)sc[0]; d.cy = (float)sc[1]; d.cz = (float)sc[2];
+            // half extents rounded up a little: the segments must cover the part's box (and so all its triangles)
+            d.hx = (float)sh[0] * 1.00001f + 1e-9f; d.hy = (float)sh[1] * 1.00001f + 1e-9f; d.hz = (float)sh[2] * 1.00001f + 1e-9f;
+            d.ox = (float)(sc[0] - c[0]); d.oy = (float)(sc[1] - c[1]); d.oz = (float)(sc[2] - c[2]);
+            d.fhx = (float)h[0]; d.fhy = (float)h[1]; d.fhz = (float)h[2];
+            d.tri_begin = hp.tri_begin; d.tri_end = hp.tri_end; d.is_box = is_box;
+            parts.push_back(d);
+        }
     }
     BT_REQUIRE(expect == n_gt, "parts must cover every gripper triangle");
+    n_parts = (int)parts.size();
     BT_CUDA(cudaSetDevice(device));
     bt_gripper* g = new bt_gripper();
     g->device = device; g->n_tris = n_gt; g->n_parts = n_parts;
