@@ -86,35 +86,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # synthetic inputs
 # ---------------------------------------------------------------------------------------------------------------
-def c3_mesh():
-    from burg_toolkit_b200 import mesh as bmesh
-    return bmesh.create_bumpy_sphere(224, 224, radius=0.035, amplitude=0.15, seed=1)
-
-
-def random_rows(n, seed, cube=0.2):
-    from scipy.spatial.transform import Rotation
-    rng = np.random.default_rng(seed)
-    rows = np.zeros((n, 14), dtype=np.float32)
-    rows[:, 0:3] = rng.random((n, 3)) * cube
-    rows[:, 3:12] = Rotation.random(n, random_state=seed).as_matrix().reshape(n, 9)
-    return rows
-
-
-def perturbed_rows(rows, seed, frac=0.5, sigma_t=0.005, sigma_deg=5.0):
-    from scipy.spatial.transform import Rotation
-    rng = np.random.default_rng(seed)
-    idx = rng.choice(len(rows), int(len(rows) * frac), replace=False)
-    out = rows[idx].copy()
-    out[:, 0:3] += rng.normal(0, sigma_t, (len(idx), 3)).astype(np.float32)
-    rv = rng.normal(0, np.deg2rad(sigma_deg), (len(idx), 3))
-    out[:, 3:12] = (Rotation.from_rotvec(rv).as_matrix() @ rows[idx, 3:12].reshape(-1, 3, 3).astype(np.float64)).reshape(-1, 9)
-    return out
-
-
-def coverage_sets(n):
-    ref = random_rows(n, 1)
-    qry = np.concatenate([random_rows(n - n // 2, 2), perturbed_rows(ref, 3)])
-    return ref, qry
+from burg_toolkit_b200.synthetic import c3_mesh, coverage_sets, perturbed_rows, random_rows  # noqa: E402,F401
 
 
 def host_candidates(mesh, n_ref, seed):

@@ -182,7 +182,8 @@ BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_
  * per batch, sampling.py:220-350 and :354-397): [S1] -> [S2] -> R1..R6 -> R7 -> [frame vectors] -> O1/O2 ->
  * [K1 -> compaction].  All buffers are caller-allocated device memory (torch tensors in the Python mirror); the call
  * only enqueues kernels on `stream` and never synchronises.  bt_timer (optional) records one CUDA event per stage
- * boundary so a benchmark can read per-stage device times afterwards. */
+ * boundary so a benchmark can read per-stage device times afterwards.  seed == 0 makes the target choice deterministic
+ * (first valid hit in canonical order), any other seed keys the device RNG streams. */
 typedef struct bt_timer bt_timer;
 #define BT_N_STAGES 8        /* sample_surface, cone_rays, cast, select, frame_vectors, expand, collide, compact */
 BT_API int bt_timer_create(int device, bt_timer** out);
