@@ -9,6 +9,7 @@
 // accept/reject decision is taken in float64 with the reference's formulas, operation order and tolerances.
 #include <cub/cub.cuh>
 #include <math.h>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -20,6 +21,8 @@ constexpr float T_BEHIND = -1e-5f;        // boxes wholly behind the origin by m
 
 struct MeshView {
     const float4* __restrict__ nodes;
+    const uint4* __restrict__ qnodes;
+    double gmin[3], gscale[3];
     const double* __restrict__ tri_rec;
     const float4* __restrict__ tri_f32;
     const int32_t* __restrict__ leaf_tri;
@@ -37,6 +40,14 @@ __device__ __forceinline__ bool slab_hit(float bx0, float by0, float bz0, float 
     float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
     return (tnear <= tfar) & (tfar >= T_BEHIND);
 }
+
+// exact uint16 -> float32 without the conversion pipe: OR the 16 bits into the mantissa of 2^23 and subtract 2^23
+__device__ __forceinline__ float u16lo(unsigned w) { return __uint_as_float((w & 0xffffu) | 0x4B000000u) - 8388608.0f; }
+__device__ __forceinline__ float u16hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
+
+// 2^23 + q as a float: one logic instruction per coordinate, the 2^23 is absorbed by the caller's FMA constant
+__device__ __forceinline__ float m16lo(unsigned w) { return __uint_as_float((w & 0xffffu) | 0x4B000000u); }
+__device__ __forceinline__ float m16hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
 __device__ __forceinline__ float safe_rcp(float d) {
     return 1.0f / (fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d);
@@ -120,14 +131,101 @@ __device__ __forceinline__ bool maybe_hit_f32(const float4* __restrict__ tr, flo
 
 constexpr int NPEND = 32;
 
+// ---- stage 1 of the ray caster: float32 traversal with ray re-fetch ---------------------------------------------------
+// Every warp owns a contiguous slice of rays (rays of one reference point are neighbours, so the slice is coherent) and
+// keeps its 32 lanes busy: a lane whose ray has left the tree immediately takes the next ray of the slice (warp-uniform
+// counter, no atomics).  Per ray the kernel emits the leaves that survive the conservative float32 pre-test (at most
+// CCAP; a ray with more is flagged and re-walked by the resolve kernel).  Only float32 state is live, so occupancy is
+// high; the float64 work happens in the second kernel with all lanes converged.
+constexpr int CCAP = 16;
+
+__global__ void __launch_bounds__(128, 8)
+traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
+                int n_rays, int rays_per_warp, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t slice_begin = warp * rays_per_warp;
+    if (slice_begin >= n_total) return;
+    const int slice_len = (int)min((int64_t)rays_per_warp, n_total - slice_begin);
+    const unsigned ref0 = (unsigned)(slice_begin / n_rays), rem0 = (unsigned)(slice_begin - (int64_t)ref0 * n_rays);
+    int next = 0;                                     // warp-uniform: first ray of the slice nobody has taken yet
+
+    const int DONE = (int)0x80000000;                 // never a leaf code: leaf codes are ~index with index < 2^30
+    int64_t ray = -1;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
+    int stack[STACK_SIZE];
+    int sp = 0, cur = DONE, n_cand = 0;
+    bool active = false;
+
+    while (true) {
+        // ---- re-fetch: when enough lanes have run dry they take the next rays of the slice ---------------------------
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (next < slice_len && (__popc(idle) >= 8 || idle == FULL)) {
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            if (!active && next + rank < slice_len) {
+                const unsigned k = rem0 + (unsigned)(next + rank);           // 32-bit arithmetic: no 64-bit division here
+                const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays;
+                ray = slice_begin + next + rank;
+                ox = (float)ref_pts[3 * ref]; oy = (float)ref_pts[3 * ref + 1]; oz = (float)ref_pts[3 * ref + 2];
+                dx = (float)dirs[3 * ray]; dy = (float)dirs[3 * ray + 1]; dz = (float)dirs[3 * ray + 2];
+                // the ray in grid coordinates (same parameter t): origin (o - gmin) * scale, direction d * scale.
+                // Box coordinates arrive as 2^23 + q (uint16 OR-ed into the mantissa of 2^23); instead of subtracting 2^23
+                // per coordinate the offset is folded into the FMA constant: t = fma(2^23 + q, 1/dg, -(2^23/dg + og/dg)).
+                // The rounding of that constant displaces the plane by < 0.52 grid cells -- the boxes were rounded
+                // outward by one extra cell for exactly this reason (quantize_nodes_kernel).
+                const float gdx = dx * (float)mv.gscale[0], gdy = dy * (float)mv.gscale[1], gdz = dz * (float)mv.gscale[2];
+                idx = __frcp_rn(fabsf(gdx) < 1e-20f ? copysignf(1e-20f, gdx) : gdx);
+                idy = __frcp_rn(fabsf(gdy) < 1e-20f ? copysignf(1e-20f, gdy) : gdy);
+                idz = __frcp_rn(fabsf(gdz) < 1e-20f ? copysignf(1e-20f, gdz) : gdz);
+                oox = fmaf(8388608.0f, idx, (float)((ref_pts[3 * ref] - mv.gmin[0]) * mv.gscale[0]) * idx);
+                ooy = fmaf(8388608.0f, idy, (float)((ref_pts[3 * ref + 1] - mv.gmin[1]) * mv.gscale[1]) * idy);
+                ooz = fmaf(8388608.0f, idz, (float)((ref_pts[3 * ref + 2] - mv.gmin[2]) * mv.gscale[2]) * idz);
+                sp = 0; cur = 0; n_cand = 0; active = true;
+            }
+            next = min(slice_len, next + __popc(idle));
+        }
+        if (!__any_sync(FULL, active)) {
+            if (next >= slice_len) break;
+            continue;
+        }
+        // ---- a short burst of node steps for the lanes that stand on an internal node ---------------------------------
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            if (cur >= 0) {
+                const uint4 A = __ldg(mv.qnodes + 2 * (int64_t)cur);            // 32-byte node: 2 x LDG.128
+                const uint4 B = __ldg(mv.qnodes + 2 * (int64_t)cur + 1);
+                const bool hl = slab_hit(m16lo(A.x), m16hi(A.x), m16lo(A.y), m16hi(A.y), m16lo(A.z), m16hi(A.z), idx, idy, idz, oox, ooy, ooz);
+                const bool hr = slab_hit(m16lo(A.w), m16hi(A.w), m16lo(B.x), m16hi(B.x), m16lo(B.y), m16hi(B.y), idx, idy, idz, oox, ooy, ooz);
+                const int l = (int)B.z, r = (int)B.w;
+                if (hl && hr) { stack[sp++] = r; cur = l; }
+                else if (hl) cur = l;
+                else if (hr) cur = r;
+                else if (sp > 0) cur = stack[--sp];
+                else cur = DONE;                                    // walk finished
+            }
+        }
+        // ---- one leaf step for the lanes that stand on a leaf ------------------------------------------------------------
+        if (cur < 0 && cur != DONE) {
+            const int leaf = ~cur;
+            if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
+                if (n_cand < CCAP) cand[ray * CCAP + n_cand] = leaf;
+                ++n_cand;
+            }
+            cur = sp > 0 ? stack[--sp] : DONE;
+        }
+        if (active && cur == DONE) { cand_count[ray] = n_cand; active = false; }
+    }
+}
+
 // One thread per ray.  Phase 1 walks the LBVH in float32 (both child boxes per 64-byte node) and parks the leaves that
 // survive the float32 pre-test; phase 2 runs the reference's float64 narrow phase on the parked leaves (threads of a
 // warp are converged again by then); phase 3 orders, de-duplicates and filters the hits and writes the records.
 template <int CAP>
 __global__ void __launch_bounds__(128, 6)
 cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
-            int n_rays, bt_ags_params P, int cap, int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits,
-            int32_t* __restrict__ overflow) {
+            int n_rays, bt_ags_params P, int cap, const int32_t* __restrict__ cand_count, const int32_t* __restrict__ cand,
+            int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, int32_t* __restrict__ overflow) {
     int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (ray >= n_total) return;
     const int64_t ref = ray / n_rays;
@@ -153,24 +251,34 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         n_pend = 0;
     };
 
-    {
-        const float ox = (float)ref_pts[3 * ref], oy = (float)ref_pts[3 * ref + 1], oz = (float)ref_pts[3 * ref + 2];
-        const float dx = (float)dirs[3 * ray], dy = (float)dirs[3 * ray + 1], dz = (float)dirs[3 * ray + 2];
-        const float idx = safe_rcp(dx), idy = safe_rcp(dy), idz = safe_rcp(dz);
-        const float oox = ox * idx, ooy = oy * idy, ooz = oz * idz;
+    const int n_cand = cand_count ? cand_count[ray] : CCAP + 1;
+    if (n_cand <= CCAP) {
+        // the usual case: stage 1 (traverse_kernel) already found this ray's candidate leaves
+        for (int i = 0; i < n_cand; ++i) {
+            if (n_pend == NPEND) run_exact();
+            pend[n_pend++] = cand[ray * CCAP + i];
+        }
+    } else {
+        // no candidate list (or it overflowed): walk the tree here
+        const double odx = ref_pts[3 * ref], ody = ref_pts[3 * ref + 1], odz = ref_pts[3 * ref + 2];
+        const double ddx = dirs[3 * ray], ddy = dirs[3 * ray + 1], ddz = dirs[3 * ray + 2];
+        const float ox = (float)odx, oy = (float)ody, oz = (float)odz;
+        const float dx = (float)ddx, dy = (float)ddy, dz = (float)ddz;
+        // the ray in grid coordinates (same parameter t): origin (o - gmin) * scale, direction d * scale
+        const float idx = safe_rcp((float)(ddx * mv.gscale[0])), idy = safe_rcp((float)(ddy * mv.gscale[1])), idz = safe_rcp((float)(ddz * mv.gscale[2]));
+        const float oox = (float)((odx - mv.gmin[0]) * mv.gscale[0]) * idx, ooy = (float)((ody - mv.gmin[1]) * mv.gscale[1]) * idy,
+                    ooz = (float)((odz - mv.gmin[2]) * mv.gscale[2]) * idz;
         int stack[STACK_SIZE];
         int sp = 0;
         int cur = 0;
         while (true) {
-            // descend through internal nodes
+            // descend through internal nodes: one 32-byte fetch (2 x LDG.128) decides both children
             while (cur >= 0) {
-                const float4 q0 = __ldg(mv.nodes + 4 * (int64_t)cur + 0);
-                const float4 q1 = __ldg(mv.nodes + 4 * (int64_t)cur + 1);
-                const float4 q2 = __ldg(mv.nodes + 4 * (int64_t)cur + 2);
-                const float4 q3 = __ldg(mv.nodes + 4 * (int64_t)cur + 3);
-                const bool hl = slab_hit(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, idx, idy, idz, oox, ooy, ooz);
-                const bool hr = slab_hit(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, idx, idy, idz, oox, ooy, ooz);
-                const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
+                const uint4 A = __ldg(mv.qnodes + 2 * (int64_t)cur);
+                const uint4 B = __ldg(mv.qnodes + 2 * (int64_t)cur + 1);
+                const bool hl = slab_hit(u16lo(A.x), u16hi(A.x), u16lo(A.y), u16hi(A.y), u16lo(A.z), u16hi(A.z), idx, idy, idz, oox, ooy, ooz);
+                const bool hr = slab_hit(u16lo(A.w), u16hi(A.w), u16lo(B.x), u16hi(B.x), u16lo(B.y), u16hi(B.y), idx, idy, idz, oox, ooy, ooz);
+                const int l = (int)B.z, r = (int)B.w;
                 if (hl && hr) { stack[sp++] = r; cur = l; }
                 else if (hl) cur = l;
                 else if (hr) cur = r;
@@ -216,22 +324,28 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         }
         if (dup) continue;
         const int32_t tri = hit_tri[i];
+        // The reference applies its masks in sequence and computes normals / angles only for the hits that are still
+        // alive (sampling.py:239-319).  flags = the FIRST filter that rejects the hit; later quantities of a rejected
+        // hit are never computed by the reference and are left at zero / NaN here.
         uint32_t flags = 0;
+        d3 nrm = mk3(0.0, 0.0, 0.0);
+        double ang = __longlong_as_double(0x7ff8000000000000ll);
         // sampling.py:239  ~np.isclose(loc, p_r, atol=1e-11).all(-1)   (rtol = 1e-5 relative to p_r)
         const bool close = (fabs(p.x - o.x) <= 1e-11 + 1e-5 * fabs(o.x)) & (fabs(p.y - o.y) <= 1e-11 + 1e-5 * fabs(o.y)) &
                            (fabs(p.z - o.z) <= 1e-11 + 1e-5 * fabs(o.z));
-        if (close) flags |= BT_HIT_ORIGIN;
-        // sampling.py:248-251
         const d3 dv = sub3(p, o);
-        const double dist = norm3(dv);
-        if (!((dist <= P.opening_width - P.width_tolerance) | (dist >= P.min_grasp_width))) flags |= BT_HIT_WIDTH;
-        // sampling.py:259, :289-308
-        const d3 nrm = interpolated_normal(mv, tri, p);
-        const double dotp = dot3(dv, nrm);
-        const double ang = atan(norm3(cross3(dv, nrm)) / dotp);
-        if (!(dotp > 0.0)) flags |= BT_HIT_SIGN;
-        if (!(ang <= P.angle_max)) flags |= BT_HIT_CONE;
-        if (P.use_below_z && !(p.z > P.no_contact_below_z)) flags |= BT_HIT_BELOW_Z;
+        if (close) flags = BT_HIT_ORIGIN;
+        else if (const double dist = norm3(dv);                      // sampling.py:248-251
+                 !((dist <= P.opening_width - P.width_tolerance) | (dist >= P.min_grasp_width))) flags = BT_HIT_WIDTH;
+        else {
+            // sampling.py:259, :289-308
+            nrm = interpolated_normal(mv, tri, p);
+            const double dotp = dot3(dv, nrm);
+            ang = atan(norm3(cross3(dv, nrm)) / dotp);
+            if (!(dotp > 0.0)) flags = BT_HIT_SIGN;
+            else if (!(ang <= P.angle_max)) flags = BT_HIT_CONE;
+            else if (P.use_below_z && !(p.z > P.no_contact_below_z)) flags = BT_HIT_BELOW_Z;
+        }
         bt_hit h;
         h.loc[0] = p.x; h.loc[1] = p.y; h.loc[2] = p.z;
         h.nrm[0] = nrm.x; h.nrm[1] = nrm.y; h.nrm[2] = nrm.z;
@@ -524,7 +638,10 @@ __global__ void expand_kernel(const double* __restrict__ ref_pts, const int64_t*
 
 static MeshView view_of(const MeshDev& m) {
     MeshView v;
-    v.nodes = m.nodes; v.tri_rec = m.tri_rec; v.tri_f32 = m.tri_f32; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
+    v.nodes = m.nodes;
+    v.qnodes = m.qnodes;
+    for (int k = 0; k < 3; ++k) { v.gmin[k] = m.grid_min[k]; v.gscale[k] = m.grid_scale[k]; }
+    v.tri_rec = m.tri_rec; v.tri_f32 = m.tri_f32; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
     v.vnormals = m.vnormals;
     return v;
 }
@@ -578,12 +695,26 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
     const int64_t total = n_ref * n_rays;
     const unsigned grid = (unsigned)ceil_div(total, 128);
     MeshView mv = view_of(mesh->m);
+    // stage 1: float32 traversal with ray re-fetch -> candidate leaves per ray
+    Scratch cc, cl;
+    BT_CUDA(cc.alloc(sizeof(int32_t) * total, st));
+    BT_CUDA(cl.alloc(sizeof(int32_t) * total * CCAP, st));
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mesh->m.device);
+    // slice length: a few rays per lane for balance, but enough warps to fill the machine (32 warps / SM)
+    int64_t rpw = ceil_div(total, (int64_t)sm_count * 32 * 2);
+    rpw = std::max<int64_t>(32, std::min<int64_t>(256, ceil_div(rpw, 32) * 32));
+    const int64_t n_warps = ceil_div(total, rpw);
+    traverse_kernel<<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,
+                                                                           cc.as<int32_t>(), cl.as<int32_t>());
+    BT_LAUNCH_CHECK();
+    // stage 2: exact float64 narrow phase, ordering, de-duplication, filters, hit records
     if (cap <= 8)
-        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, d_hit_count, d_hits, d_overflow);
+        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_overflow);
     else if (cap <= 16)
-        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, d_hit_count, d_hits, d_overflow);
+        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_overflow);
     else
-        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, d_hit_count, d_hits, d_overflow);
+        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_overflow);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

@@ -66,6 +66,11 @@ struct Scratch {
 //   q1 = (l.max.y, l.max.z, r.min.x, r.min.y)
 //   q2 = (r.min.z, r.max.x, r.max.y, r.max.z)
 //   q3 = (left, right, -, -) as int bits; child >= 0: internal node index, child < 0: leaf ~child
+// Quantised LBVH node for the ray caster: 32 bytes = 2 x uint4.  Box coordinates are uint16 on a global grid over the
+// padded scene bounds, rounded outward by one extra cell (resolution = extent / 65534, ~1 um for a 7 cm object), which
+// halves the bytes -- and the L1 wavefronts -- per traversal step:
+//   A = (l.lo.x | l.lo.y << 16,  l.lo.z | l.hi.x << 16,  l.hi.y | l.hi.z << 16,  r.lo.x | r.lo.y << 16)
+//   B = (r.lo.z | r.hi.x << 16,  r.hi.y | r.hi.z << 16,  left,  right)
 // Triangle record for the exact ray test: 128 bytes = 16 doubles (one cache line):
 //   v0[3] n[3] e0[3] e1[3] d00 d01 d11 inv_den     (e0 = v1-v0, e1 = v2-v0, trimesh 'cramer' constants)
 // Triangle vertices for the exact triangle/triangle test: 9 doubles (v0 v1 v2).
@@ -79,7 +84,9 @@ struct MeshDev {
     int32_t* faces = nullptr;      // [nF,3]
     double*  area_cdf = nullptr;   // [nF] inclusive normalised cumulative area (caller order)
     // LBVH (leaf order = Morton order)
-    float4*  nodes = nullptr;      // [max(nF-1,1)*4]
+    float4*  nodes = nullptr;      // [max(nF-1,1)*4]   float32 boxes (collision kernel)
+    uint4*   qnodes = nullptr;     // [max(nF-1,1)*2]   the same nodes, boxes as uint16 on a global grid (ray caster): 32 B
+    double   grid_min[3] = {0, 0, 0}, grid_scale[3] = {1, 1, 1};   // grid coordinate = (x - grid_min) * grid_scale
     double*  tri_rec = nullptr;    // [nF,16]  leaf order
     double*  tri_verts = nullptr;  // [nF,9]   leaf order
     float4*  tri_f32 = nullptr;    // [nF,3]   leaf order: (v0 | 0) (e0 | 0) (e1 | 0) for the float32 pre-test

@@ -168,6 +168,35 @@ __global__ void emit_nodes_kernel(int n, const int32_t* __restrict__ left, const
     nodes[4 * i + 0] = q0; nodes[4 * i + 1] = q1; nodes[4 * i + 2] = q2; nodes[4 * i + 3] = q3;
 }
 
+__device__ __forceinline__ unsigned quant_lo(float x, double gmin, double gscale) {
+    const double g = floor(((double)x - gmin) * gscale) - 1.0;
+    return (unsigned)fmin(fmax(g, 0.0), 65535.0);
+}
+__device__ __forceinline__ unsigned quant_hi(float x, double gmin, double gscale) {
+    const double g = ceil(((double)x - gmin) * gscale) + 1.0;
+    return (unsigned)fmin(fmax(g, 0.0), 65535.0);
+}
+
+// float32 nodes -> 32-byte nodes with uint16 boxes on the global grid, rounded outward (+1 cell)
+__global__ void quantize_nodes_kernel(int n_nodes, const float4* __restrict__ nodes, double3 gmin, double3 gscale,
+                                      uint4* __restrict__ qnodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4 q0 = nodes[4 * i], q1 = nodes[4 * i + 1], q2 = nodes[4 * i + 2], q3 = nodes[4 * i + 3];
+    uint4 A, B;
+    A.x = quant_lo(q0.x, gmin.x, gscale.x) | (quant_lo(q0.y, gmin.y, gscale.y) << 16);
+    A.y = quant_lo(q0.z, gmin.z, gscale.z) | (quant_hi(q0.w, gmin.x, gscale.x) << 16);
+    A.z = quant_hi(q1.x, gmin.y, gscale.y) | (quant_hi(q1.y, gmin.z, gscale.z) << 16);
+    A.w = quant_lo(q1.z, gmin.x, gscale.x) | (quant_lo(q1.w, gmin.y, gscale.y) << 16);
+    B.x = quant_lo(q2.x, gmin.z, gscale.z) | (quant_hi(q2.y, gmin.x, gscale.x) << 16);
+    B.y = quant_hi(q2.z, gmin.y, gscale.y) | (quant_hi(q2.w, gmin.z, gscale.z) << 16);
+    B.z = __float_as_uint(q3.x);
+    B.w = __float_as_uint(q3.y);
+    if (q1.z > q2.y) { A.w = 0xffffffffu; B.x = 0x0000ffffu; B.y = 0u; }      // empty right box (single-triangle mesh) stays empty
+    qnodes[2 * i] = A;
+    qnodes[2 * i + 1] = B;
+}
+
 __global__ void single_leaf_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
                                         float4* __restrict__ nodes) {
     // nF == 1: node 0 = (leaf 0 | empty box)
@@ -233,7 +262,7 @@ extern "C" int bt_stream_sync(void* stream) {
 // ---- mesh ------------------------------------------------------------------------------------------
 static int mesh_free(MeshDev& m) {
     cudaFree(m.verts); cudaFree(m.vnormals); cudaFree(m.faces); cudaFree(m.area_cdf);
-    cudaFree(m.nodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
+    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
     m = MeshDev();
     return BT_OK;
 }
@@ -291,6 +320,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cudaMalloc(&m.faces, sizeof(int32_t) * 3 * nF));
     MESH_TRY(cudaMalloc(&m.area_cdf, sizeof(double) * nF));
     MESH_TRY(cudaMalloc(&m.nodes, sizeof(float4) * 4 * nNodes));
+    MESH_TRY(cudaMalloc(&m.qnodes, sizeof(uint4) * 2 * nNodes));
     MESH_TRY(cudaMalloc(&m.tri_rec, sizeof(double) * 16 * nF));
     MESH_TRY(cudaMalloc(&m.tri_verts, sizeof(double) * 9 * nF));
     MESH_TRY(cudaMalloc(&m.tri_f32, sizeof(float4) * 3 * nF));
@@ -363,6 +393,17 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
         single_leaf_node_kernel<<<1, 1, 0, st>>>(box_min, box_max, m.nodes);
         MESH_TRY(cudaGetLastError());
     }
+    {
+        const double margin = 2.0 * (double)pad + 1e-7;
+        for (int k = 0; k < 3; ++k) {
+            m.grid_min[k] = lo[k] - margin;
+            m.grid_scale[k] = 65534.0 / ((hi[k] + margin) - m.grid_min[k]);
+        }
+        quantize_nodes_kernel<<<(int)ceil_div(nNodes, T), T, 0, st>>>(
+            (int)nNodes, m.nodes, make_double3(m.grid_min[0], m.grid_min[1], m.grid_min[2]),
+            make_double3(m.grid_scale[0], m.grid_scale[1], m.grid_scale[2]), m.qnodes);
+        MESH_TRY(cudaGetLastError());
+    }
     MESH_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, cub_bytes, area, m.area_cdf, n, st));
     normalise_cdf_kernel<<<G, T, 0, st>>>(m.area_cdf, nF);
     MESH_TRY(cudaGetLastError());
@@ -388,7 +429,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     }
     m.root = 0;
     m.info.n_vertices = nV; m.info.n_triangles = nF; m.info.n_nodes = nNodes;
-    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 26 * nF) + sizeof(int32_t) * 4 * nF + 48 * nF + 64 * nNodes);
+    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 26 * nF) + sizeof(int32_t) * 4 * nF + 48 * nF + 96 * nNodes);
     m.info.surface_area = total;
     m.info.build_ms = ms;
     for (int k = 0; k < 3; ++k) { m.info.bounds_min[k] = (float)lo[k]; m.info.bounds_max[k] = (float)hi[k]; }

@@ -403,7 +403,7 @@ class AntipodalGraspSampler:
         while total < n and consumed < self.max_passes * len(ref):
             idx = (cursor + torch.arange(batch, device=ref.device)) % len(ref)
             pts, nrm = ref[idx, 0:3].contiguous(), ref[idx, 3:6].contiguous()
-            out = self.evaluate_candidates(pts, nrm, seed=seed + consumed, choice_seed=seed + 7 * consumed + 1)
+            out = self.run_pipeline(pts, nrm, seed=seed + consumed, check_collisions=False)
             per_ref = out['pair_count'][:batch].to(torch.int64) * n_o
             cum = torch.cumsum(per_ref, 0)
             need = n - total

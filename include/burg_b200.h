@@ -38,7 +38,9 @@ extern "C" {
 #define BT_E_CAPACITY   -3   /* an output capacity was exceeded                */
 #define BT_E_NODEVICE   -4   /* no CUDA device / wrong architecture            */
 
-/* hit flags written by bt_ags_cast (a hit is a valid antipodal target iff flags == 0) */
+/* hit flags written by bt_ags_cast: the FIRST mask of the reference's sequence (sampling.py:239-319) that rejects the hit;
+ * a hit is a valid antipodal target iff flags == 0.  nrm / angle of hits rejected by the origin or width mask are 0 / NaN
+ * (the reference never computes them). */
 #define BT_HIT_ORIGIN    1u  /* sampling.py:239   hit coincides with the reference point          */
 #define BT_HIT_WIDTH     2u  /* sampling.py:249   fails (d <= ow - tol) | (d >= min_width)  (an OR) */
 #define BT_HIT_SIGN      4u  /* sampling.py:295   sign(d . n) <= 0                                 */

@@ -251,24 +251,28 @@ static int cast_one(const CoMesh *m, const double *o, const double *d, const CoP
         }
         if (dup) continue;
         CoHit *h = out + n_out++;
+        /* masks in the reference's order; flags = the first one that rejects the hit, later quantities stay 0 / NaN */
         uint32_t flags = 0;
         int close = 1;
-        double dv[3];
+        double dv[3], ang = NAN;
         for (int k = 0; k < 3; ++k) {
             if (!(fabs(p[k] - o[k]) <= 1e-11 + 1e-5 * fabs(o[k]))) close = 0;
             dv[k] = p[k] - o[k];
             h->loc[k] = p[k];
+            h->nrm[k] = 0.0;
         }
-        if (close) flags |= HIT_ORIGIN;
         double dist = norm3(dv);
-        if (!((dist <= P->opening_width - P->width_tolerance) || (dist >= P->min_grasp_width))) flags |= HIT_WIDTH;
-        interp_normal(m, th[i].tri, p, h->nrm);
-        double dotp = dot3(dv, h->nrm), cr[3];
-        cross3(dv, h->nrm, cr);
-        double ang = atan(norm3(cr) / dotp);
-        if (!(dotp > 0.0)) flags |= HIT_SIGN;
-        if (!(ang <= P->angle_max)) flags |= HIT_CONE;
-        if (P->use_below_z && !(p[2] > P->no_contact_below_z)) flags |= HIT_BELOW_Z;
+        if (close) flags = HIT_ORIGIN;
+        else if (!((dist <= P->opening_width - P->width_tolerance) || (dist >= P->min_grasp_width))) flags = HIT_WIDTH;
+        else {
+            interp_normal(m, th[i].tri, p, h->nrm);
+            double dotp = dot3(dv, h->nrm), cr[3];
+            cross3(dv, h->nrm, cr);
+            ang = atan(norm3(cr) / dotp);
+            if (!(dotp > 0.0)) flags = HIT_SIGN;
+            else if (!(ang <= P->angle_max)) flags = HIT_CONE;
+            else if (P->use_below_z && !(p[2] > P->no_contact_below_z)) flags = HIT_BELOW_Z;
+        }
         h->t = th[i].t; h->angle = ang; h->tri = th[i].tri; h->flags = flags;
     }
     return n_out;

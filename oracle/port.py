@@ -180,29 +180,43 @@ def interpolated_normals(mesh, points, index_tri):
 
 def hit_flags(mesh, p_r, loc, index_tri, mu=0.25, opening_width=0.08, width_tolerance=0.005,
               min_grasp_width=0.002, no_contact_below_z=None):
-    """sampling.py:239-319 evaluated independently per hit -> (flags uint32, normals, angles, dist).
+    """sampling.py:239-319 -> (flags uint32, normals, angles, dist).
 
-    The reference applies the masks in sequence; a hit survives iff its flags are 0.  (Normals and
-    angles of hits the reference would already have dropped are computed anyway; they do not
-    influence surviving hits.)"""
+    The reference applies its masks in sequence (origin, width, sign, cone, z) and computes normals / angles only
+    for the hits that survived the origin and width masks.  ``flags`` holds the FIRST mask that rejects a hit (0 = the
+    hit survives all of them); normals of hits rejected by the origin / width masks are zero and their angles NaN,
+    because the reference never computes them."""
     p_r = np.asarray(p_r, dtype=np.float64)
     flags = np.zeros(len(loc), dtype=np.uint32)
     if len(loc) == 0:
         return flags, np.zeros((0, 3)), np.zeros(0), np.zeros(0)
-    is_origin = np.isclose(loc, p_r, atol=1e-11).all(axis=-1)
-    flags[is_origin] |= HIT_ORIGIN
+    alive = np.ones(len(loc), dtype=bool)
+
+    def reject(mask, bit):
+        hit = alive & mask
+        flags[hit] = bit
+        alive[hit] = False
+
+    reject(np.isclose(loc, p_r, atol=1e-11).all(axis=-1), HIT_ORIGIN)
     dist = np.linalg.norm(loc - p_r, axis=-1)
-    within = (dist <= opening_width - width_tolerance) | (dist >= min_grasp_width)
-    flags[~within] |= HIT_WIDTH
-    normals = interpolated_normals(mesh, loc, index_tri)
-    d = (loc - p_r).reshape(-1, 3)
-    dotp = np.sum(d * normals, axis=-1)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        angles = np.arctan(np.linalg.norm(np.cross(d, normals), axis=-1) / dotp)
-    flags[~(np.sign(dotp) > 0)] |= HIT_SIGN
-    flags[~(angles <= np.arctan(mu))] |= HIT_CONE
-    if no_contact_below_z is not None:
-        flags[~(loc[:, 2] > no_contact_below_z)] |= HIT_BELOW_Z
+    reject(~((dist <= opening_width - width_tolerance) | (dist >= min_grasp_width)), HIT_WIDTH)
+    normals = np.zeros((len(loc), 3))
+    angles = np.full(len(loc), np.nan)
+    idx = np.nonzero(alive)[0]
+    if len(idx):
+        normals[idx] = interpolated_normals(mesh, loc[idx], index_tri[idx])
+        d = (loc[idx] - p_r).reshape(-1, 3)
+        dotp = np.sum(d * normals[idx], axis=-1)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            angles[idx] = np.arctan(np.linalg.norm(np.cross(d, normals[idx]), axis=-1) / dotp)
+        sign_bad = np.zeros(len(loc), dtype=bool)
+        sign_bad[idx] = ~(np.sign(dotp) > 0)
+        reject(sign_bad, HIT_SIGN)
+        cone_bad = np.zeros(len(loc), dtype=bool)
+        cone_bad[idx] = ~(angles[idx] <= np.arctan(mu))
+        reject(cone_bad, HIT_CONE)
+        if no_contact_below_z is not None:
+            reject(~(loc[:, 2] > no_contact_below_z), HIT_BELOW_Z)
     return flags, normals, angles, dist
 
 
