@@ -35,7 +35,7 @@ N_REF = 10_000
 N_RAYS = 100
 N_ORIENT = 12
 COV_N = 100_000
-AGS_KERNELS = ['sample_surface_kernel', 'cone_rays_kernel', 'cast_kernel', 'zero_first_kernel', 'select_count_kernel',
+AGS_KERNELS = ['sample_surface_kernel', 'cone_rays_kernel', 'traverse_kernel', 'cast_kernel', 'zero_first_kernel', 'select_count_kernel',
                'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'scale_count_kernel', 'collide_kernel', 'compact_count_kernel',
                'compact_scatter_kernel']
 
@@ -160,7 +160,7 @@ def run_reference(args, rank, world):
         total = sum(times)
         value, unit, metric = pairs / total, 'pairs/s', 'coverage pairs/sec'
         sample = f'{n} x {n} grasps per step (kd-tree coverage, single-threaded like the reference)'
-        config = {'workload': 'coverage_c2', 'n_ref': n, 'n_query': n}
+        config = {'workload': args.workload, 'n_ref': n, 'n_query': n}
     line = {'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(args.steps, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.workload == 'ags_c3' else 'f32',
@@ -255,20 +255,40 @@ def run_b200(args, rank, world, local_rank):
         n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // max(world, 1)
         overflow = int(torch.stack([c.reshape(()) for _, _, c in stats]).sum().item())
 
-        # roofline of the dominant kernel (cast): algorithmic bytes per launch / its event-timed duration
+        # work counters (instrumented kernel instantiations, one extra untimed step) for the L2 traffic model
+        from burg_toolkit_b200 import _native as nat
+        counters = torch.zeros(8, dtype=torch.int64, device='cuda')
+        nat.call('bt_debug_set_counters', counters.data_ptr())
+        step(424242 + rank)
+        torch.cuda.synchronize()
+        nat.call('bt_debug_set_counters', None)
+        cnt = [int(x) for x in counters.cpu().tolist()]
+        n_cand = N_REF * N_RAYS
+        per_ray = {'nodes': cnt[0] / n_cand, 'leaf_pretests': cnt[1] / n_cand, 'exact_tests': cnt[2] / n_cand}
+        per_grasp = {'nodes': cnt[3] / max(n_grasps, 1), 'leaves_classified': cnt[4] / max(n_grasps, 1),
+                     'leaves_exact': cnt[5] / max(n_grasps, 1)}
+
+        # roofline of the dominant stage (the ray caster = traverse_kernel + cast_kernel): algorithmic HBM bytes per launch
+        # (64 B per candidate + 80 B per triangle) over its event-timed duration, against the measured HBM peak;
+        # plus the traversal-traffic model against L2 (the mesh + LBVH are L2-resident by design, HBM is not the binding roof)
         cast_ms = stage_ms['cast']
         alg_bytes = N_REF * N_RAYS * 64 + 80 * info.n_triangles
         achieved = alg_bytes / (cast_ms * 1e-3) / 1e9
+        l2_bytes = cnt[0] * 32 + cnt[1] * 48 + cnt[2] * 128 + n_cand * (24 + 2 * 72)
         prof = {}
         ppath = os.path.join(ROOT, 'profiles', 'roofline_inputs.json')
         if os.path.exists(ppath):
             with open(ppath) as fh:
                 prof = json.load(fh)
-        roofline = {'bound': 'hbm', 'kernel': 'cast_kernel', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
-                    'frac': achieved / peak_gbs, 'traffic': prof.get('cast_kernel', {}).get('dram_bytes_per_launch'),
+        roofline = {'bound': 'hbm', 'kernel': 'traverse_kernel + cast_kernel (ray caster stage)', 'achieved': achieved, 'peak': peak_gbs,
+                    'unit': 'GB/s', 'frac': achieved / peak_gbs, 'traffic': prof.get('cast_stage', {}).get('dram_bytes_per_launch'),
                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': cast_ms,
                     'rays_per_s': N_REF * N_RAYS / (cast_ms * 1e-3),
-                    'note': 'mesh+LBVH (26 MB) is L2-resident by design, so HBM is not the binding roof; see DESIGN.md'}
+                    'l2_model': {'bytes_per_launch': l2_bytes, 'achieved_gbs': l2_bytes / (cast_ms * 1e-3) / 1e9,
+                                 'definition': 'nodes*32 + leaf_pretests*48 + exact_tests*128 + rays*(24 in + 2*72 out)',
+                                 'per_ray': per_ray},
+                    'collide_per_grasp': per_grasp,
+                    'note': 'mesh+LBVH (34 MB) is L2-resident by design, so HBM is not the binding roof; see DESIGN.md section 4'}
 
         # end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
         pts, nrm, _ = [t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank)]
@@ -327,12 +347,13 @@ def run_b200(args, rank, world, local_rank):
 
 def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
     """coverage 100k x 100k (perturbed pair, eps 15): device-resident pairs/s and e2e (host rows in, fraction out)"""
-    ref, qry = coverage_sets(COV_N)
+    n_cov = 1_000_000 if args.workload == 'coverage_c5' else COV_N
+    ref, qry = coverage_sets(n_cov)
     dref, dqry = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
     pairs = float(len(ref)) * float(len(qry))
     res = {}
     steps = max(3, args.steps // 2) if short else args.steps
-    for algo in ('grid', 'tiles'):
+    for algo in (('grid',) if n_cov > 200_000 else ('grid', 'tiles')):
         for _ in range(max(args.warmup, 3)):
             metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
         barrier()
@@ -363,13 +384,13 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
     lane_ops = 148 * 128 * 1.965e9
     out = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
            'ms_per_step': res['grid']['ms'],
-           'config': {'workload': 'coverage_c2', 'n_ref': len(ref), 'n_query': len(qry), 'epsilon': 15.0,
+           'config': {'workload': args.workload if args.workload != 'ags_c3' else 'coverage_c2', 'n_ref': len(ref), 'n_query': len(qry), 'epsilon': 15.0,
                       'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
                       'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
                       'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
-           'tiles_all_pairs': res['tiles'],
-           'roofline': {'bound': 'fp32-issue', 'kernel': 'coverage_tiles_kernel', 'achieved': res['tiles']['pairs_per_s'] * 4 / 1e12,
-                        'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': res['tiles']['pairs_per_s'] * 4 / lane_ops,
+           'tiles_all_pairs': res.get('tiles'),
+           'roofline': {'bound': 'fp32-issue', 'kernel': 'coverage_tiles_kernel', 'achieved': res.get('tiles', res['grid'])['pairs_per_s'] * 4 / 1e12,
+                        'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': res.get('tiles', res['grid'])['pairs_per_s'] * 4 / lane_ops,
                         'traffic': None, 'note': '4 FP32 lane-ops per pair (3 FFMA + 1 compare); HBM bytes are negligible (10 MB)'},
            'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes),
                    'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac},
@@ -383,7 +404,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'coverage_c2'])
+    ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'coverage_c2', 'coverage_c5'])
     ap.add_argument('--cpu-ref-points', type=int, default=4000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')

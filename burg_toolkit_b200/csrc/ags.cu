@@ -139,9 +139,12 @@ constexpr int NPEND = 32;
 // high; the float64 work happens in the second kernel with all lanes converged.
 constexpr int CCAP = 16;
 
+template <bool STATS>
 __global__ void __launch_bounds__(128, 8)
 traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
-                int n_rays, int rays_per_warp, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand) {
+                int n_rays, int rays_per_warp, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
+                unsigned long long* __restrict__ counters) {
+    unsigned long long st_nodes = 0, st_leaves = 0, st_cand = 0;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -193,6 +196,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             if (cur >= 0) {
+                if (STATS) ++st_nodes;
                 const uint4 A = __ldg(mv.qnodes + 2 * (int64_t)cur);            // 32-byte node: 2 x LDG.128
                 const uint4 B = __ldg(mv.qnodes + 2 * (int64_t)cur + 1);
                 const bool hl = slab_hit(m16lo(A.x), m16hi(A.x), m16lo(A.y), m16hi(A.y), m16lo(A.z), m16hi(A.z), idx, idy, idz, oox, ooy, ooz);
@@ -208,14 +212,17 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
         // ---- one leaf step for the lanes that stand on a leaf ------------------------------------------------------------
         if (cur < 0 && cur != DONE) {
             const int leaf = ~cur;
+            if (STATS) ++st_leaves;
             if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
                 if (n_cand < CCAP) cand[ray * CCAP + n_cand] = leaf;
                 ++n_cand;
+                if (STATS) ++st_cand;
             }
             cur = sp > 0 ? stack[--sp] : DONE;
         }
         if (active && cur == DONE) { cand_count[ray] = n_cand; active = false; }
     }
+    if (STATS) { atomicAdd(counters + 0, st_nodes); atomicAdd(counters + 1, st_leaves); atomicAdd(counters + 2, st_cand); }
 }
 
 // One thread per ray.  Phase 1 walks the LBVH in float32 (both child boxes per 64-byte node) and parks the leaves that
@@ -705,8 +712,12 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
     int64_t rpw = ceil_div(total, (int64_t)sm_count * 32 * 2);
     rpw = std::max<int64_t>(32, std::min<int64_t>(256, ceil_div(rpw, 32) * 32));
     const int64_t n_warps = ceil_div(total, rpw);
-    traverse_kernel<<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,
-                                                                           cc.as<int32_t>(), cl.as<int32_t>());
+    if (g_counters_host_copy)
+        traverse_kernel<true><<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,
+                                                                                     cc.as<int32_t>(), cl.as<int32_t>(), g_counters_host_copy);
+    else
+        traverse_kernel<false><<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,
+                                                                                      cc.as<int32_t>(), cl.as<int32_t>(), nullptr);
     BT_LAUNCH_CHECK();
     // stage 2: exact float64 narrow phase, ordering, de-duplication, filters, hit records
     if (cap <= 8)

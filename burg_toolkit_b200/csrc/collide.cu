@@ -199,11 +199,14 @@ __device__ __forceinline__ void grasp_affine(const float* __restrict__ gs, int64
     sf_out = sf;
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(128, 4)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
                int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
                const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
-               unsigned long long* __restrict__ work_counter, uint8_t* __restrict__ out) {
+               unsigned long long* __restrict__ work_counter, uint8_t* __restrict__ out,
+               unsigned long long* __restrict__ counters) {
+    unsigned long long st_nodes = 0, st_leaves = 0, st_exact = 0;
     extern __shared__ double s_gtris[];            // gripper triangles, TCP frame
     __shared__ PartDev s_parts[MAX_PARTS];
     const int n_gt = parts[n_parts - 1].tri_end;
@@ -287,11 +290,13 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
                     for (int j = 0; j < 3; ++j) q[v][j] = fmaf(dx, b.u[j][0], fmaf(dy, b.u[j][1], dz * b.u[j][2])) * b.inv_n[j];
                 }
                 const int cls = classify_triangle(q, b.le[0], b.le[1], b.le[2], b.margin, b.off, b.fe);
-                if (!(cls == 0 || (cls == 1 && b.is_box))) pend[np++] = ~cur;
+                if (STATS) ++st_leaves;
+                if (!(cls == 0 || (cls == 1 && b.is_box))) { pend[np++] = ~cur; if (STATS) ++st_exact; }
                 if (sp == 0) { busy = false; break; }
                 cur = stack[--sp];
                 continue;
             }
+            if (STATS) ++st_nodes;
             const float4 q0 = __ldg(nodes + 4 * (int64_t)cur + 0);
             const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
             const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
@@ -344,6 +349,7 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
             has = __ballot_sync(FULL, np > 0 && (np >= PEND || !busy));
         }
     }
+    if (STATS) { atomicAdd(counters + 3, st_nodes); atomicAdd(counters + 4, st_leaves); atomicAdd(counters + 5, st_exact); }
 }
 
 // ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------
@@ -518,7 +524,10 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
     const float inflate = 2e-5f * max_abs + 1e-6f;
     const size_t tri_bytes = sizeof(double) * 9 * (size_t)gripper->n_tris;
     if (tri_bytes > 8 * 1024)
-        BT_CUDA(cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+    {
+        BT_CUDA(cudaFuncSetAttribute(collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+        BT_CUDA(cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+    }
     Scratch counter;
     BT_CUDA(counter.alloc(sizeof(unsigned long long), st));
     BT_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
@@ -526,9 +535,16 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->m.device);
     const int64_t items = n * gripper->n_parts;
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * 4);   // persistent: 4 CTAs / SM
-    collide_kernel<<<grid, 128, tri_bytes, st>>>(
-        scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
-        (float)opening_width, (float)width_tolerance, use_width, inflate, counter.as<unsigned long long>(), d_colliding);
+    if (g_counters_host_copy)
+        collide_kernel<true><<<grid, 128, tri_bytes, st>>>(
+            scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
+            (float)opening_width, (float)width_tolerance, use_width, inflate, counter.as<unsigned long long>(), d_colliding,
+            g_counters_host_copy);
+    else
+        collide_kernel<false><<<grid, 128, tri_bytes, st>>>(
+            scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
+            (float)opening_width, (float)width_tolerance, use_width, inflate, counter.as<unsigned long long>(), d_colliding,
+            nullptr);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

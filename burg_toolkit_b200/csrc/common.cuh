@@ -60,6 +60,12 @@ struct Scratch {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// ---- instrumentation (bt_debug_set_counters): when a counter array is installed the traversal kernels are launched in
+// their STATS instantiation and accumulate work counts there; slots:
+//   0 cast: LBVH nodes visited      1 cast: float32 leaf pre-tests     2 cast: exact float64 ray/triangle tests
+//   3 collide: LBVH nodes visited   4 collide: leaves classified       5 collide: leaves sent to the exact test
+extern unsigned long long* g_counters_host_copy;      // device pointer as seen by the host (NULL = off)
+
 // ---- device mesh -------------------------------------------------------------------------------------
 // LBVH node: 64 bytes = 4 x float4, holds BOTH children's boxes so one fetch decides both descents.
 //   q0 = (l.min.x, l.min.y, l.min.z, l.max.x)

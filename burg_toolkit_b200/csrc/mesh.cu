@@ -221,6 +221,13 @@ __global__ void finish_cdf_kernel(double* cdf, int64_t n, double* total_out) {
 
 using namespace bt;
 
+unsigned long long* bt::g_counters_host_copy = nullptr;
+
+extern "C" int bt_debug_set_counters(uint64_t* d_counters) {
+    bt::g_counters_host_copy = reinterpret_cast<unsigned long long*>(d_counters);
+    return BT_OK;
+}
+
 // ---- library ---------------------------------------------------------------------------------------
 extern "C" int bt_version(void) { return 100; }
 

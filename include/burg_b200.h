@@ -95,6 +95,13 @@ BT_API int         bt_memcpy_h2d(void* d_dst, const void* h_src, int64_t bytes, 
 BT_API int         bt_memcpy_d2h(void* h_dst, const void* d_src, int64_t bytes, void* stream);
 BT_API int         bt_stream_sync(void* stream);
 
+/* instrumentation: install (or remove, with NULL) a device array of 8 uint64 counters; while installed, bt_ags_cast and
+ * bt_collide run instrumented instantiations of their kernels that add to it:
+ *   [0] cast LBVH nodes visited  [1] cast float32 leaf pre-tests  [2] cast exact float64 tests
+ *   [3] collide LBVH nodes visited  [4] collide leaves classified  [5] collide leaves sent to the exact test
+ * (used by bench.py, outside the timed region, for the L2 traffic model of the roofline) */
+BT_API int bt_debug_set_counters(uint64_t* d_counters);
+
 /* ---- mesh / scene ---------------------------------------------------------------------------------
  * replaces mesh_processing.as_trimesh + trimesh.Trimesh construction + RayMeshIntersector / collision
  * manager set-up (sampling.py:191-192, 372-380).  h_VN may be NULL (area-weighted vertex normals are
