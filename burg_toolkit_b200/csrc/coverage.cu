@@ -29,6 +29,7 @@ struct CovParams {
     double r2_kd;           // (eps/1000)^2 in float64 (mode 1)
     int mode;
     float cx, cy, cz;       // centring offset for the expanded-form reject
+    float qdot_min;         // conservative lower bound on |q1 . q2| = cos(angle / 2) for the angular part to fit under eps
 };
 
 // exact reference recipe for one pair; rows are the raw float32[14] grasp rows
@@ -135,6 +136,20 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
     }
 }
 
+// unit quaternion (x, y, z, w) of a float32 rotation block (row-major 9 floats); approximate (used only for a conservative
+// bound): |q1 . q2| = cos(angle(R1 R2^T) / 2)
+__device__ __forceinline__ float4 quat_of(const float* __restrict__ R) {
+    const float m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8];
+    const float tr = m00 + m11 + m22;
+    float x, y, z, w;
+    if (tr > 0.f) { w = tr + 1.f; x = m21 - m12; y = m02 - m20; z = m10 - m01; }
+    else if (m00 > m11 && m00 > m22) { x = 1.f + m00 - m11 - m22; w = m21 - m12; y = m01 + m10; z = m02 + m20; }
+    else if (m11 > m22) { y = 1.f + m11 - m00 - m22; w = m02 - m20; x = m01 + m10; z = m12 + m21; }
+    else { z = 1.f + m22 - m00 - m11; w = m10 - m01; x = m02 + m20; y = m12 + m21; }
+    const float inv = rsqrtf(fmaxf(x * x + y * y + z * z + w * w, 1e-30f));
+    return make_float4(x * inv, y * inv, z * inv, w * inv);
+}
+
 // ---- algo 1: uniform grid -----------------------------------------------------------------------------------
 struct Grid {
     float ox, oy, oz;       // origin
@@ -189,11 +204,13 @@ __global__ void cell_key_kernel(const float* __restrict__ rows, int64_t n, Grid 
 // sorted query translations as float4 (x, y, z, original index) + dense cell range table
 __global__ void gather_sorted_kernel(const float* __restrict__ rows, const int32_t* __restrict__ sorted_ids,
                                      const uint32_t* __restrict__ sorted_keys, int64_t n, float4* __restrict__ out,
+                                     float4* __restrict__ out_quat,
                                      int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_end) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t id = sorted_ids[i];
     out[i] = make_float4(rows[14 * (int64_t)id], rows[14 * (int64_t)id + 1], rows[14 * (int64_t)id + 2], __int_as_float(id));
+    if (out_quat) out_quat[i] = quat_of(rows + 14 * (int64_t)id + 3);
     if (cell_start) {
         const uint32_t k = sorted_keys[i];
         if (i == 0 || sorted_keys[i - 1] != k) cell_start[k] = (int32_t)i;
@@ -254,6 +271,158 @@ coverage_grid_kernel(const float* __restrict__ ref, const int32_t* __restrict__ 
             }
         }
     if (cov && lane == 0) covered[i] = 1;
+}
+
+// Cell-tile kernel (dense grid): one block per chunk of CELL_REFS consecutive references IN CELL ORDER.  The chunk's
+// references live in a few neighbouring cells; the block walks the bounding cell box of the chunk, grown by one cell,
+// stages the sorted queries of every (x, y) column -- a contiguous range because z is the fastest key digit -- in shared
+// memory tiles and runs the 3-FFMA + compare reject of the all-pairs kernel on them, with coordinates centred on the
+// chunk so that the expanded form stays exact to a few ulps.  Survivors go through the shared queue to the exact recipe.
+constexpr int CELL_THREADS = 128;
+constexpr int CELL_RPT = 2;
+constexpr int CELL_REFS = CELL_THREADS * CELL_RPT;
+constexpr int CELL_TILE = 1024;
+constexpr int CELL_QCAP = 2048;
+
+__global__ void __launch_bounds__(CELL_THREADS)
+coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__ ref_sorted_ids, int64_t n_ref,
+                      const float* __restrict__ qry, const float4* __restrict__ q_sorted, const float4* __restrict__ q_quat_sorted,
+                      const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_end, Grid g,
+                      const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
+    __shared__ float4 tile[CELL_TILE];
+    __shared__ float4 tile_quat[CELL_TILE + 4];            // query orientations as unit quaternions (+ zero padding for the 4-wide loop)
+    __shared__ int tile_id[CELL_TILE];
+    __shared__ unsigned int queue[CELL_QCAP];
+    __shared__ unsigned char s_cov[CELL_REFS];
+    __shared__ int s_box[6];                               // min x y z, max x y z (cell coordinates of the chunk)
+    __shared__ int q_count;
+    const int64_t s0 = (int64_t)blockIdx.x * CELL_REFS;
+    if (threadIdx.x < 3) { s_box[threadIdx.x] = 0x7fffffff; s_box[3 + threadIdx.x] = -1; }
+    if (threadIdx.x == 0) q_count = 0;
+    __syncthreads();
+    int64_t row[CELL_RPT];
+    float px[CELL_RPT], py[CELL_RPT], pz[CELL_RPT];
+    float4 quat[CELL_RPT];
+#pragma unroll
+    for (int r = 0; r < CELL_RPT; ++r) {
+        const int lr = threadIdx.x + r * CELL_THREADS;
+        s_cov[lr] = 0;
+        row[r] = -1;
+        quat[r] = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (s0 + lr < n_ref) {
+            row[r] = ref_sorted_ids[s0 + lr];
+            px[r] = ref[14 * row[r]]; py[r] = ref[14 * row[r] + 1]; pz[r] = ref[14 * row[r] + 2];
+            quat[r] = quat_of(ref + 14 * row[r] + 3);
+            const int cx = cell_coord(px[r], g.ox, g.inv_h, g.nx), cy = cell_coord(py[r], g.oy, g.inv_h, g.ny), cz = cell_coord(pz[r], g.oz, g.inv_h, g.nz);
+            atomicMin(&s_box[0], cx); atomicMin(&s_box[1], cy); atomicMin(&s_box[2], cz);
+            atomicMax(&s_box[3], cx); atomicMax(&s_box[4], cy); atomicMax(&s_box[5], cz);
+        } else { px[r] = py[r] = pz[r] = 0.f; }
+    }
+    __syncthreads();
+    const int x0 = max(s_box[0] - 1, 0), x1 = min(s_box[3] + 1, g.nx - 1);
+    const int y0 = max(s_box[1] - 1, 0), y1 = min(s_box[4] + 1, g.ny - 1);
+    const int z0 = max(s_box[2] - 1, 0), z1 = min(s_box[5] + 1, g.nz - 1);
+    // centre of the chunk's cell box in world coordinates: all staged points lie within a few cells of it
+    const float h = 1.0f / g.inv_h;
+    const float ccx = g.ox + 0.5f * (x0 + x1 + 1) * h, ccy = g.oy + 0.5f * (y0 + y1 + 1) * h, ccz = g.oz + 0.5f * (z0 + z1 + 1) * h;
+    const float ext = 0.5f * h * (float)(max(x1 - x0, max(y1 - y0, z1 - z0)) + 1);
+    // rounding of the 4-term FMA chain and the two squared norms, for centred coordinates bounded by ext*sqrt(3)
+    const float r2 = P.r2_reject + 64.0f * 5.97e-8f * (3.0f * ext * ext);
+    float ax[CELL_RPT], ay[CELL_RPT], az[CELL_RPT], thr[CELL_RPT], qmin[CELL_RPT];
+#pragma unroll
+    for (int r = 0; r < CELL_RPT; ++r) {
+        const float x = px[r] - ccx, y = py[r] - ccy, z = pz[r] - ccz;
+        ax[r] = -2.0f * x; ay[r] = -2.0f * y; az[r] = -2.0f * z;
+        thr[r] = r2 - fmaf(x, x, fmaf(y, y, z * z));
+        qmin[r] = row[r] >= 0 ? P.qdot_min : 2.0f;
+    }
+    for (int ix = x0; ix <= x1; ++ix)
+        for (int iy = y0; iy <= y1; ++iy) {
+            // contiguous range of the column's cells z0..z1 (empty cells have start == end == 0)
+            int b = -1, e = 0;
+            for (int iz = z0; iz <= z1; ++iz) {
+                const int k = (ix * g.ny + iy) * g.nz + iz;
+                const int cs = __ldg(cell_start + k), ce = __ldg(cell_end + k);
+                if (ce > cs) { if (b < 0) b = cs; e = ce; }
+            }
+            if (b < 0) continue;
+            for (int t0 = b; t0 < e; t0 += CELL_TILE) {
+                const int cnt = min(CELL_TILE, e - t0);
+                __syncthreads();
+                for (int j = threadIdx.x; j < cnt; j += CELL_THREADS) {
+                    const float4 q = __ldg(q_sorted + t0 + j);
+                    const float x = q.x - ccx, y = q.y - ccy, z = q.z - ccz;
+                    tile[j] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
+                    const int qi = __float_as_int(q.w);
+                    tile_id[j] = qi;
+                    tile_quat[j] = __ldg(q_quat_sorted + t0 + j);
+                }
+                if (threadIdx.x < 4) tile_quat[cnt + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < CELL_RPT; ++r)
+                    if (s_cov[threadIdx.x + r * CELL_THREADS]) qmin[r] = 2.0f;        // already covered: stop testing this row
+                __syncthreads();
+                // In a grid walk ~15 % of the candidates pass the translation test but only ~0.1 % the rotation test, so the
+                // orientation bound goes FIRST here: |q1 . q2| = cos(angle / 2), 4 FMAs on the staged quaternions.  Four
+                // queries x CELL_RPT rows are evaluated branch-free (8 independent FMA chains); the rare passes are handled
+                // afterwards so that the hot loop has no control dependencies.
+                for (int j0 = 0; j0 < cnt; j0 += 4) {
+                    float4 qq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) qq[u] = tile_quat[j0 + u];
+                    // slack[u] = max over the rows of (|q_row . q_u| - qmin_row): >= 0 iff some row passes the orientation bound
+                    float slack[4] = {-4.f, -4.f, -4.f, -4.f};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int r = 0; r < CELL_RPT; ++r) {
+                            const float qd = fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)));
+                            slack[u] = fmaxf(slack[u], fabsf(qd) - qmin[r]);
+                        }
+                    const float any_slack = fmaxf(fmaxf(slack[0], slack[1]), fmaxf(slack[2], slack[3]));
+                    unsigned pass = 0;
+                    if (any_slack >= 0.f) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int r = 0; r < CELL_RPT; ++r) {
+                                const float qd = fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)));
+                                pass |= (fabsf(qd) >= qmin[r] ? 1u : 0u) << (u * CELL_RPT + r);
+                            }
+                    }
+                    if (pass) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int r = 0; r < CELL_RPT; ++r) {
+                                const int j = j0 + u;
+                                if (!((pass >> (u * CELL_RPT + r)) & 1u) || j >= cnt) continue;
+                                const float4 q = tile[j];
+                                const float sv = fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w)));
+                                if (sv > thr[r]) continue;
+                                const int lr = threadIdx.x + r * CELL_THREADS;
+                                const int pos = atomicAdd(&q_count, 1);
+                                if (pos < CELL_QCAP) queue[pos] = ((unsigned)lr << 10) | (unsigned)j;
+                                else if (!s_cov[lr] && pair_covered(ref + 14 * row[r], qry + 14 * (int64_t)tile_id[j], lut, P)) s_cov[lr] = 1;
+                            }
+                    }
+                }
+                __syncthreads();
+                const int n_q = min(q_count, CELL_QCAP);
+                for (int i = threadIdx.x; i < n_q; i += CELL_THREADS) {
+                    const unsigned code = queue[i];
+                    const int lr = (int)(code >> 10), j = (int)(code & 1023u);
+                    const int64_t rr = ref_sorted_ids[s0 + lr];
+                    if (!s_cov[lr] && pair_covered(ref + 14 * rr, qry + 14 * (int64_t)tile_id[j], lut, P)) s_cov[lr] = 1;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) q_count = 0;
+            }
+        }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < CELL_RPT; ++r)
+        if (row[r] >= 0 && s_cov[threadIdx.x + r * CELL_THREADS]) covered[row[r]] = 1;
 }
 
 __global__ void count_covered_kernel(const uint8_t* __restrict__ covered, int64_t n, unsigned long long* __restrict__ count) {
@@ -330,6 +499,8 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
     g.nz = (int)fminf(1024.f, floorf((hi[2] - lo[2]) / h) + 1.f);
     const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
     const bool dense = n_cells <= (1ll << 24);
+    // dense data (hundreds of queries per cell): block-per-chunk tiles; sparse data: warp-per-reference walk
+    const bool use_cells = dense && (double)n_qry / (double)n_cells >= 128.0;
     int key_bits = 1;
     while ((1ll << key_bits) < n_cells) ++key_bits;
 
@@ -354,12 +525,19 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
     BT_LAUNCH_CHECK();
     BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b1, keys.as<uint32_t>(), keys_s.as<uint32_t>(), ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, key_bits, st));
     BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, key_bits, st));
+    Scratch qq;
+    if (use_cells) BT_CUDA(qq.alloc(sizeof(float4) * n_qry, st));
     gather_sorted_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, ids_s.as<int32_t>(), keys_s.as<uint32_t>(), n_qry, qs.as<float4>(),
+                                                                          use_cells ? qq.as<float4>() : nullptr,
                                                                           dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr);
     BT_LAUNCH_CHECK();
-    coverage_grid_kernel<<<(unsigned)ceil_div(n_ref * 32, 256), 256, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
-                                                                          (int)n_qry, dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr,
-                                                                          g, lut, P, d_covered);
+    if (use_cells)
+        coverage_cells_kernel<<<(unsigned)ceil_div(n_ref, CELL_REFS), CELL_THREADS, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(),
+                                                                                             qq.as<float4>(), cs.as<int32_t>(), ce.as<int32_t>(), g, lut, P, d_covered);
+    else
+        coverage_grid_kernel<<<(unsigned)ceil_div(n_ref * 32, 256), 256, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
+                                                                                  (int)n_qry, dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr,
+                                                                                  g, lut, P, d_covered);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
@@ -385,6 +563,8 @@ extern "C" int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry
     // largest d with fl(1000*d) <= eps is eps/1000 * (1 + 2^-23); add margin
     const float r_bound = (float)(r * (1.0 + 1e-6)) + 1e-12f;
     P.cx = P.cy = P.cz = 0.f;
+    // deg <= eps needs angle <= eps (+ the 4-decimal rounding of the cosine, < 0.03 deg at eps >= 1): |q1.q2| >= cos((eps + 0.1 deg)/2)
+    P.qdot_min = epsilon >= 179.0 ? -1.0f : (float)(cos((epsilon + 0.1) * 0.5 * 3.14159265358979323846 / 180.0) - 2e-5);
     if (algo == 1) {
         P.r2_reject = r_bound * r_bound * 1.0001f;          // direct-difference form: a few ulps of rounding only
         int rc = run_grid(d_ref, n_ref, d_qry, n_qry, d_lut, P, r_bound, d_covered, st);
