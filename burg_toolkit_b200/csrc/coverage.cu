@@ -456,9 +456,66 @@ __global__ void pairwise_kernel(const float* __restrict__ g1, int64_t n1, const 
     out[idx] = which == 0 ? d : (which == 1 ? ang : __fadd_rn(__fmul_rn(weight, d), ang));
 }
 
+// ---- avg_gripper_point_distances (metrics.py:94-138) ------------------------------------------------------------------
+struct KeyPoints { double p[32][3]; int k; };
+
+// key points of every grasp: float32 pose entries x float64 points, products accumulated as numpy's einsum kernel does,
+// in two lanes: (R0 p0 + R2 p2) + (R1 p1 + t * 1)
+__global__ void keypoints_kernel(const float* __restrict__ gs, int64_t n, KeyPoints kp, double* __restrict__ out) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * kp.k) return;
+    const int64_t i = idx / kp.k;
+    const int l = (int)(idx - i * kp.k);
+    const float* g = gs + 14 * i;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double r0 = g[3 + 3 * j], r1 = g[4 + 3 * j], r2 = g[5 + 3 * j], t = g[j];
+        out[3 * idx + j] = (r0 * kp.p[l][0] + r2 * kp.p[l][2]) + (r1 * kp.p[l][1] + t * 1.0);
+    }
+}
+
+__global__ void avg_point_distance_kernel(const double* __restrict__ kp1, int64_t n1, const double* __restrict__ kp2, int64_t n2,
+                                          int k, int symmetric, double* __restrict__ out) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n1 * n2) return;
+    const double* a = kp1 + 3 * k * (idx / n2);
+    const double* b = kp2 + 3 * k * (idx % n2);
+    const int flip[5] = {1, 0, 3, 2, 4};                        // metrics.py:131
+    double sum = 0.0;
+    for (int l = 0; l < k; ++l) {
+        d3 dv = sub3(ld3(a + 3 * l), ld3(b + 3 * l));
+        double d = norm3(dv);
+        if (symmetric) d = fmin(d, norm3(sub3(ld3(a + 3 * l), ld3(b + 3 * flip[l]))));
+        sum = (l == 0) ? d : sum + d;
+    }
+    out[idx] = sum / (double)k;
+}
+
 }  // namespace bt
 
 using namespace bt;
+
+extern "C" int bt_avg_gripper_point_distances(const float* d_gs1, int64_t n1, const float* d_gs2, int64_t n2,
+                                              const double* h_points, int32_t n_points, int32_t consider_symmetry,
+                                              double* d_out, void* stream) {
+    BT_REQUIRE(d_gs1 && d_gs2 && h_points && d_out, "null pointer");
+    BT_REQUIRE(n_points >= 1 && n_points <= 32, "1 <= n_points <= 32");
+    BT_REQUIRE(!consider_symmetry || n_points == 5, "consider_symmetry needs the 5 default key points (reference metrics.py:128-131)");
+    if (n1 <= 0 || n2 <= 0) return BT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KeyPoints kp;
+    kp.k = n_points;
+    for (int l = 0; l < 32; ++l) for (int c = 0; c < 3; ++c) kp.p[l][c] = l < n_points ? h_points[3 * l + c] : 0.0;
+    Scratch k1, k2;
+    BT_CUDA(k1.alloc(sizeof(double) * 3 * n_points * n1, st));
+    BT_CUDA(k2.alloc(sizeof(double) * 3 * n_points * n2, st));
+    keypoints_kernel<<<(unsigned)ceil_div(n1 * n_points, 256), 256, 0, st>>>(d_gs1, n1, kp, k1.as<double>());
+    keypoints_kernel<<<(unsigned)ceil_div(n2 * n_points, 256), 256, 0, st>>>(d_gs2, n2, kp, k2.as<double>());
+    avg_point_distance_kernel<<<(unsigned)ceil_div(n1 * n2, 256), 256, 0, st>>>(k1.as<double>(), n1, k2.as<double>(), n2, n_points,
+                                                                               consider_symmetry, d_out);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
 
 // bounding box of both translation sets (one tiny read-back; the metric API is synchronous anyway)
 static int data_bounds(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, float lo[3], float hi[3],

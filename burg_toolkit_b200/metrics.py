@@ -98,6 +98,34 @@ def combined_distances(graspset1, graspset2, weight=1000.0):
     return _pairwise(graspset1, graspset2, 2, weight)
 
 
+def _get_default_gripper_keypoints():
+    """five key points of a model gripper (reference metrics.py:80-91): two per finger, one at the stem"""
+    w, h, tip = 0.08, 0.08, 0.03
+    return np.array([[-w / 2, 0, 0], [w / 2, 0, 0], [-w / 2, 0, tip], [w / 2, 0, tip], [0, 0, h]])
+
+
+def avg_gripper_point_distances(graspset1, graspset2, gripper_points=None, consider_symmetry=False):
+    """(N, M) float64: average distance between corresponding key points of a model gripper posed at the grasps of
+    both sets (reference metrics.py:94-138).  ``gripper_points``: (K, 3) array or an object with ``.points``;
+    ``consider_symmetry`` also tries the flipped gripper (default key points only, as in the reference)."""
+    torch = nat.require_cuda()
+    if gripper_points is None:
+        gripper_points = _get_default_gripper_keypoints()
+    elif hasattr(gripper_points, 'points'):                      # open3d point cloud
+        gripper_points = np.asarray(gripper_points.points)
+    pts = np.ascontiguousarray(np.asarray(gripper_points, dtype=np.float64)[:, 0:3])
+    if consider_symmetry and len(pts) != 5:
+        raise IndexError('consider_symmetry only works for the 5 default gripper points (reference metrics.py:128-131)')
+    a, b = _rows(graspset1), _rows(graspset2)
+    device = _device_of(a, b)
+    with torch.cuda.device(device):
+        da, db = _to_device(a, device), _to_device(b, device)
+        out = torch.empty((da.shape[0], db.shape[0]), dtype=torch.float64, device=da.device)
+        nat.call('bt_avg_gripper_point_distances', nat.ptr(da), da.shape[0], nat.ptr(db), db.shape[0], pts.ctypes.data,
+                 len(pts), 1 if consider_symmetry else 0, nat.ptr(out), nat.current_stream())
+        return out.cpu().numpy()
+
+
 def covered_mask(reference_grasp_set, query_grasp_set, epsilon=15.0, kd_semantics=True, algo='auto',
                  return_device=False):
     """bool[N]: which reference grasps have a query grasp within ``epsilon`` (B200 extension; the

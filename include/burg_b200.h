@@ -252,6 +252,13 @@ BT_API int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry, in
 BT_API int bt_pairwise_distances(const float* d_gs1, int64_t n1, const float* d_gs2, int64_t n2, int32_t which,
                           float weight, const float* d_lut, float* d_out, void* stream);
 
+/* average key-point distance between every pair of grasps (replaces metrics.avg_gripper_point_distances,
+ * metrics.py:94-138; h_points [n_points,3] f64 key points in the gripper frame, default = metrics.py:80-91);
+ * [n1,n2] f64 out.  consider_symmetry also tries the second gripper flipped (points [1,0,3,2,4], needs n_points == 5). */
+BT_API int bt_avg_gripper_point_distances(const float* d_gs1, int64_t n1, const float* d_gs2, int64_t n2,
+                                          const double* h_points, int32_t n_points, int32_t consider_symmetry,
+                                          double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,35 @@ def coverage(ref_rows, qry_rows, epsilon=15.0, brute_force=False):
     return np.count_nonzero(cov) / len(cov)
 
 
+DEFAULT_GRIPPER_KEYPOINTS = np.array([[-0.04, 0, 0], [0.04, 0, 0], [-0.04, 0, 0.03], [0.04, 0, 0.03], [0, 0, 0.08]])
+
+
+def avg_gripper_point_distances(rows1, rows2, gripper_points=None, consider_symmetry=False):
+    """metrics.py:94-138 -> (N, M) float64: key points of a model gripper (metrics.py:80-91) are mapped by both poses
+    (float32 pose entries times float64 points; numpy's einsum kernel accumulates the four products in two SIMD lanes:
+    (R0 p0 + R2 p2) + (R1 p1 + t), verified bit-exact against np.einsum on this image), the
+    point-wise distances are averaged; with ``consider_symmetry`` the second gripper is also tried flipped
+    (points [1, 0, 3, 2, 4], metrics.py:129-135)."""
+    pts = DEFAULT_GRIPPER_KEYPOINTS if gripper_points is None else np.asarray(gripper_points, dtype=np.float64)
+    rows1 = np.asarray(rows1, dtype=F32).reshape(-1, 14)
+    rows2 = np.asarray(rows2, dtype=F32).reshape(-1, 14)
+
+    def tf_points(rows):
+        rot = rows[:, 3:12].reshape(-1, 3, 3).astype(np.float64)
+        t = rows[:, 0:3].astype(np.float64)
+        out = np.empty((len(rows), len(pts), 3))
+        for j in range(3):
+            out[:, :, j] = (rot[:, j, 0:1] * pts[None, :, 0] + rot[:, j, 2:3] * pts[None, :, 2]) + \
+                           (rot[:, j, 1:2] * pts[None, :, 1] + t[:, j:j + 1] * 1.0)
+        return out
+
+    a, b = tf_points(rows1), tf_points(rows2)
+    dist = np.linalg.norm(a[:, None] - b[None], axis=-1)
+    if consider_symmetry:
+        dist = np.minimum(dist, np.linalg.norm(a[:, None] - b[None][:, :, [1, 0, 3, 2, 4], :], axis=-1))
+    return np.average(dist, axis=-1)
+
+
 # =============================================================================================
 # antipodal grasp sampling  (reference burg_toolkit/sampling.py, util.py, mesh_processing.py)
 # =============================================================================================

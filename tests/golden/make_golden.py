@@ -10,6 +10,7 @@ functions the reference itself calls (the wrappers only record, they do not alte
 Outputs (tests/golden/):
   metrics_small.npz   pairwise distances + brute/KD coverage of metrics.py on 300 x 200 grasps
   metrics_mid.npz     KD coverage on 4000 x 4000 grasps (uniform pair and perturbed pair)
+  metrics_keypoints.npz  avg_gripper_point_distances (default / symmetric / custom key points) on 120 x 90 grasps
   known_answers.npz   the reference tests' known answers (tests/grasp_testing.py:13-51,87-117)
   ags_icosphere.npz   sampler run on an icosphere (1280 tris, r = 0.03), every loop iteration recorded
   ags_screwdriver.npz sampler run on data/samples/flathead-screwdriver (4000 tris), n_orientations=18,
@@ -70,6 +71,13 @@ def make_metrics():
                         precision_kd=ns.metrics.coverage(qry, ref),
                         coverage_eps5=ns.metrics.coverage(ref, qry, epsilon=5.0),
                         coverage_eps30=ns.metrics.coverage_brute_force(ref, qry, epsilon=30.0))
+    custom = np.random.default_rng(5).normal(size=(7, 3)) * 0.03
+    np.savez_compressed(os.path.join(HERE, 'metrics_keypoints.npz'),
+                        ref=ref._gs_array[:120], qry=qry._gs_array[:90],
+                        avg=ns.metrics.avg_gripper_point_distances(ref[0:120], qry[0:90]),
+                        avg_symmetric=ns.metrics.avg_gripper_point_distances(ref[0:120], qry[0:90], consider_symmetry=True),
+                        custom_points=custom,
+                        avg_custom=ns.metrics.avg_gripper_point_distances(ref[0:120], qry[0:90], gripper_points=custom))
     print('metrics_small: coverage', ns.metrics.coverage(ref, qry), 'brute', ns.metrics.coverage_brute_force(ref, qry))
 
     ref = random_graspset(4000, 11, cube=0.1)

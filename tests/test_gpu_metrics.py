@@ -84,6 +84,18 @@ def test_coverage_mid_golden(metrics, algo):
     assert metrics.precision(_gs(g['ref']), _gs(g['qry_perturbed'])) == float(g['precision_perturbed'])
 
 
+def test_avg_gripper_point_distances_bit_exact(metrics):
+    g = load_golden('metrics_keypoints')
+    ref, qry = _gs(g['ref']), _gs(g['qry'])
+    out = metrics.avg_gripper_point_distances(ref, qry)
+    assert out.dtype == np.float64 and np.array_equal(out, g['avg'])
+    assert np.array_equal(metrics.avg_gripper_point_distances(ref, qry, consider_symmetry=True), g['avg_symmetric'])
+    assert np.array_equal(metrics.avg_gripper_point_distances(ref, qry, gripper_points=g['custom_points']), g['avg_custom'])
+    assert np.array_equal(metrics.avg_gripper_point_distances(ref[0], qry), g['avg'][0:1])
+    with pytest.raises(IndexError):
+        metrics.avg_gripper_point_distances(ref, qry, gripper_points=g['custom_points'], consider_symmetry=True)
+
+
 def test_edge_cases(metrics):
     rows = random_rows(37, 4, cube=0.01)
     gs = _gs(rows)

@@ -37,6 +37,13 @@ def test_metrics_small_bit_exact():
     assert port.coverage(ref, qry, epsilon=30.0, brute_force=True) == float(g['coverage_eps30'])
 
 
+def test_avg_gripper_point_distances_matches_reference():
+    g = load_golden('metrics_keypoints')
+    assert np.array_equal(port.avg_gripper_point_distances(g['ref'], g['qry']), g['avg'])
+    assert np.array_equal(port.avg_gripper_point_distances(g['ref'], g['qry'], consider_symmetry=True), g['avg_symmetric'])
+    assert np.array_equal(port.avg_gripper_point_distances(g['ref'], g['qry'], g['custom_points']), g['avg_custom'])
+
+
 def test_metrics_mid():
     g = load_golden('metrics_mid')
     assert port.coverage(g['ref'], g['qry_uniform']) == float(g['coverage_uniform'])
