@@ -544,3 +544,70 @@ def _construct(reference_point, target_points, n_orientations, halfspace, frame_
                      int(n_orientations), 1 if halfspace else 0, cos_t.ctypes.data, sin_t.ctypes.data, nat.ptr(gs),
                      None, nat.current_stream())
         return GraspSet.from_array(gs.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generators around the sampler (reference sampling.py:400-495), device-side
+# ---------------------------------------------------------------------------------------------------------------------
+def grasp_perturbations(grasps, radii=None, include_original_grasp=True, device=None):
+    """Perturbed grasp poses on 6-d 'spheres' (1 mm translation = 1 deg rotation): per radius and grasp 6 translations
+    (+-radius mm along each pose axis) and 6 rotations (+-radius deg about each pose axis), optionally preceded by the
+    original grasp; all perturbations of the first grasp come first, and so on (reference sampling.py:400-454)."""
+    from .grasp import Grasp
+    torch = nat.require_cuda()
+    if radii is None:
+        radii = [5, 10, 15]
+    elif not isinstance(radii, list):
+        raise ValueError('radii must be a list (or None)')
+    if not isinstance(grasps, GraspSet):
+        if isinstance(grasps, Grasp):
+            grasps = grasps.as_grasp_set()
+        else:
+            raise ValueError('g must be a grasp.Grasp or a grasp.GraspSet')
+    if len(radii) > 16:
+        raise ValueError('at most 16 radii are supported')
+    per = len(radii) * 12 + int(include_original_grasp)
+    d = dev.device_index(device)
+    r = np.ascontiguousarray(radii, dtype=np.float64)
+    with torch.cuda.device(d):
+        rows = torch.from_numpy(grasps.as_contiguous()).cuda()
+        out = torch.zeros((len(grasps) * per, 14), dtype=torch.float32, device='cuda')
+        nat.call('bt_grasp_perturbations', nat.ptr(rows), len(grasps), r.ctypes.data, len(radii),
+                 int(include_original_grasp), nat.ptr(out), nat.current_stream())
+        return GraspSet.from_array(out.cpu().numpy())
+
+
+def random_poses(n, seed=None, device=None):
+    """(n, 4, 4) float64 random poses: uniform random orientations, positions in [0, 1) (reference sampling.py:457-469).
+    The random numbers come from the device generator keyed by ``seed`` (default: drawn from ``np.random``)."""
+    torch = nat.require_cuda()
+    if seed is None:
+        seed = int(np.random.randint(1, 2 ** 62))
+    with torch.cuda.device(dev.device_index(device)):
+        out = torch.empty((int(n), 4, 4), dtype=torch.float64, device='cuda')
+        nat.call('bt_random_poses', int(n), int(seed), nat.ptr(out), nat.current_stream())
+        return out.cpu().numpy()
+
+
+def farthest_point_sampling(point_cloud, k, device=None):
+    """(k,) indices of an approximate farthest point sampling of ``point_cloud`` ((n, c >= 3), xyz first): index 0, then
+    repeatedly the point with the largest distance to all points chosen so far (reference sampling.py:472-495)."""
+    torch = nat.require_cuda()
+    if len(point_cloud) < k:
+        raise ValueError(f'given point cloud has only {len(point_cloud)} elements, cannot sample {k} points')
+    with torch.cuda.device(dev.device_index(device)):
+        if isinstance(point_cloud, torch.Tensor):
+            pts = point_cloud.cuda()
+        else:
+            arr = np.asarray(point_cloud)
+            if arr.dtype not in (np.float32, np.float64):
+                arr = arr.astype(np.float64)
+            pts = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        if pts.dtype not in (torch.float32, torch.float64):
+            pts = pts.to(torch.float64)
+        pts = pts.contiguous()
+        out = torch.zeros((int(k),), dtype=torch.int64, device='cuda')
+        if k > 0:
+            nat.call('bt_farthest_point_sampling', nat.ptr(pts), 1 if pts.dtype == torch.float64 else 0, pts.shape[1],
+                     pts.shape[0], int(k), nat.ptr(out), nat.current_stream())
+        return out.cpu().numpy()

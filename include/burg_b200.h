@@ -259,6 +259,20 @@ BT_API int bt_avg_gripper_point_distances(const float* d_gs1, int64_t n1, const 
                                           const double* h_points, int32_t n_points, int32_t consider_symmetry,
                                           double* d_out, void* stream);
 
+/* ---- generators feeding the path -------------------------------------------------------------
+ * bt_random_poses: [n,4,4] f64 homogeneous transforms, uniform random rotation + translation U[0,1)^3 (replaces
+ *   sampling.random_poses, sampling.py:457-469; device RNG, distributional parity only)
+ * bt_grasp_perturbations: for every grasp [original +] per radius 6 translations (+-radius mm along each pose axis) and
+ *   6 rotations (+-radius deg about each pose axis); rows float32 [n * (12 * n_radii + include_original), 14] in the
+ *   reference's order (replaces sampling.grasp_perturbations, sampling.py:400-454)
+ * bt_farthest_point_sampling: k indices, the first one is 0, then repeatedly the point farthest from all chosen ones
+ *   (replaces sampling.farthest_point_sampling, sampling.py:472-495); points [n, stride >= 3] f32 or f64 (xyz first) */
+BT_API int bt_random_poses(int64_t n, uint64_t seed, double* d_out, void* stream);
+BT_API int bt_grasp_perturbations(const float* d_gs, int64_t n, const double* h_radii, int32_t n_radii,
+                                  int32_t include_original, float* d_out, void* stream);
+BT_API int bt_farthest_point_sampling(const void* d_points, int32_t is_float64, int32_t stride, int64_t n, int64_t k,
+                                      int64_t* d_indices, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -425,3 +425,52 @@ def sample_loop(mesh, surface_samples, n, seed, gripper_opening_width=0.08, mu=0
         contacts = np.concatenate([contacts, np.repeat(c, n_orientations, axis=0)], axis=0)
         rows = np.concatenate([rows, new_rows])
     return rows, contacts, records
+
+
+# =============================================================================================
+# generators around the sampler  (reference burg_toolkit/sampling.py:400-495)
+# =============================================================================================
+def grasp_perturbations(rows, radii=(5, 10, 15), include_original=True):
+    """sampling.py:400-454 on raw float32 rows -> float32 [n * (12 * len(radii) + include_original), 14]."""
+    from scipy.spatial.transform import Rotation
+    rows = np.asarray(rows, dtype=F32).reshape(-1, 14)
+    out = []
+    for row in rows:
+        pose = np.eye(4)
+        pose[:3, :3] = row[3:12].reshape(3, 3)
+        pose[:3, 3] = row[0:3]
+        if include_original:
+            out.append(row.copy())
+        for radius in radii:
+            shift = radius / 1000
+            for axis in range(3):
+                for sign in (1, -1):
+                    p = pose.copy()
+                    p[0:3, 3] = p[0:3, 3] + sign * shift * p[0:3, axis]
+                    out.append(_pose_row(p))
+            rot_rad = np.deg2rad(radius)
+            for axis in range(3):
+                for sign in (1, -1):
+                    p = pose.copy()
+                    p[:3, :3] = Rotation.from_rotvec(sign * rot_rad * p[0:3, axis]).as_matrix() @ p[:3, :3]
+                    out.append(_pose_row(p))
+    return np.array(out, dtype=F32).reshape(-1, 14)
+
+
+def _pose_row(pose):
+    r = np.zeros(14, dtype=F32)
+    r[0:3] = pose[0:3, 3].astype(F32)
+    r[3:12] = pose[0:3, 0:3].reshape(9).astype(F32)
+    return r
+
+
+def farthest_point_sampling(point_cloud, k):
+    """sampling.py:472-495 (arithmetic in the input's dtype)."""
+    pc = np.asarray(point_cloud)[:, :3]
+    idx = np.zeros(k, dtype=int)
+    dist = np.full(len(pc), fill_value=np.inf)
+    for i in range(1, k):
+        cur = ((pc[idx[i - 1]] - pc) ** 2).sum(axis=1)
+        dist = np.minimum(dist, cur)
+        idx[i] = np.argmax(dist)
+    return idx

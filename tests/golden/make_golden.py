@@ -17,6 +17,7 @@ Outputs (tests/golden/):
                       sample(100) -> 108 grasps (tests/grasp_testing.py:68-82)
   ags_bumpy.npz       sampler run on the non-convex 'YCB-like' shape at low resolution with
                       max_targets_per_ref_point=3 and only_grasp_from_above in a second pass
+  generators.npz      grasp_perturbations (default radii / one custom radius) and farthest_point_sampling (f64 / f32)
   collisions.npz      check_collisions of the icosphere / screwdriver grasps (shape only, + plane)
 """
 import os
@@ -267,7 +268,24 @@ def _plane_vf(mesh):
     return plane.vertices, plane.triangles
 
 
+def make_generators():
+    import contextlib, io
+    gs = random_graspset(20, 31, cube=0.1)
+    gs.widths = np.linspace(0.01, 0.07, 20)
+    gs.scores = np.linspace(0, 1, 20)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p_default = ns.sampling.grasp_perturbations(gs)
+        p_custom = ns.sampling.grasp_perturbations(gs[3], radii=[2], include_original_grasp=False)
+    pc = np.random.default_rng(8).normal(size=(5000, 6))
+    np.savez_compressed(os.path.join(HERE, 'generators.npz'), gs=gs._gs_array, perturbed_default=p_default._gs_array,
+                        perturbed_custom=p_custom._gs_array, cloud=pc,
+                        fps_f64=ns.sampling.farthest_point_sampling(pc, 200),
+                        fps_f32=ns.sampling.farthest_point_sampling(pc.astype(np.float32), 150))
+    print('generators:', p_default._gs_array.shape, p_custom._gs_array.shape)
+
+
 if __name__ == '__main__':
+    make_generators()
     make_known_answers()
     make_metrics()
     make_ags()

@@ -151,3 +151,11 @@ def test_port_against_live_reference_metrics():
     assert np.array_equal(ns.metrics.combined_distances(a, b), port.combined_distances(a._gs_array, b._gs_array))
     assert ns.metrics.coverage(a, b) == port.coverage(a._gs_array, b._gs_array)
     assert ns.metrics.coverage_brute_force(a, b) == port.coverage(a._gs_array, b._gs_array, brute_force=True)
+
+
+def test_generators_match_reference():
+    g = load_golden('generators')
+    assert np.array_equal(port.grasp_perturbations(g['gs']), g['perturbed_default'])
+    assert np.array_equal(port.grasp_perturbations(g['gs'][3:4], radii=[2], include_original=False), g['perturbed_custom'])
+    assert np.array_equal(port.farthest_point_sampling(g['cloud'], 200), g['fps_f64'])
+    assert np.array_equal(port.farthest_point_sampling(g['cloud'].astype(np.float32), 150), g['fps_f32'])
