@@ -53,7 +53,7 @@ class PipelineBuffers(C.Structure):
     _fields_ = [('ref_pts', C.c_void_p), ('ref_nrm', C.c_void_p), ('dirs', C.c_void_p), ('frame_vecs', C.c_void_p),
                 ('sample_surface', C.c_int32), ('generate_dirs', C.c_int32), ('generate_frame_vecs', C.c_int32),
                 ('reserved', C.c_int32),
-                ('hit_count', C.c_void_p), ('hits', C.c_void_p), ('overflow', C.c_void_p), ('pair_count', C.c_void_p),
+                ('hit_count', C.c_void_p), ('valid_mask', C.c_void_p), ('hits', C.c_void_p), ('overflow', C.c_void_p), ('pair_count', C.c_void_p),
                 ('pair_offset', C.c_void_p), ('pair_ref', C.c_void_p), ('pair_q', C.c_void_p), ('cap_pairs', C.c_int64),
                 ('gs', C.c_void_p), ('contacts', C.c_void_p), ('n_grasps', C.c_void_p), ('colliding', C.c_void_p),
                 ('free_gs', C.c_void_p), ('free_contacts', C.c_void_p), ('n_free', C.c_void_p)]
@@ -81,8 +81,8 @@ _SIGNATURES = {
     'bt_sample_surface': (C.c_int, [_P, C.c_int64, C.c_uint64, _P, _P, _P, _P]),
     'bt_cone_rays': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_uint64, _P, _P]),
     'bt_random_unit_vectors': (C.c_int, [C.c_int64, C.c_uint64, _P, _P]),
-    'bt_ags_cast': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(AgsParams), _P, _P, _P, _P]),
-    'bt_ags_select': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P, _P, _P, _P,
+    'bt_ags_cast': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(AgsParams), _P, _P, _P, _P, _P]),
+    'bt_ags_select': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P, _P, _P, _P,
                                 C.c_int64, _P]),
     'bt_expand_orientations': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P,
                                          _P, _P, _P]),

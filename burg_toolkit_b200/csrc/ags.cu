@@ -232,7 +232,8 @@ template <int CAP>
 __global__ void __launch_bounds__(128, 6)
 cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
             int n_rays, bt_ags_params P, int cap, const int32_t* __restrict__ cand_count, const int32_t* __restrict__ cand,
-            int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, int32_t* __restrict__ overflow) {
+            int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, uint32_t* __restrict__ valid_mask,
+            int32_t* __restrict__ overflow) {
     int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (ray >= n_total) return;
     const int64_t ref = ray / n_rays;
@@ -319,6 +320,7 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
 
     bt_hit* out = hits + ray * (int64_t)cap;
     int n_out = 0;
+    uint32_t vmask = 0;
     for (int i = 0; i < n_hit; ++i) {
         const double t = hit_t[i];
         const d3 p = add3(scl3(d, t), o);
@@ -357,9 +359,11 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         h.loc[0] = p.x; h.loc[1] = p.y; h.loc[2] = p.z;
         h.nrm[0] = nrm.x; h.nrm[1] = nrm.y; h.nrm[2] = nrm.z;
         h.t = t; h.angle = ang; h.tri = tri; h.flags = flags;
+        if (flags == 0u) vmask |= 1u << n_out;
         out[n_out++] = h;
     }
     hit_count[ray] = n_out;
+    if (valid_mask) valid_mask[ray] = vmask;
     if (over && overflow) atomicAdd(overflow, 1);
 }
 
@@ -450,17 +454,25 @@ __device__ __forceinline__ uint64_t choice_key(uint64_t seed, int64_t ref, int o
 }
 
 // one warp per reference point: number of valid hits, capped at max_targets
+// number of valid hits of one ray: from the caster's bit mask if there is one, else by scanning the hit records
+__device__ __forceinline__ uint32_t ray_valid_mask(const uint32_t* __restrict__ valid_mask, const int32_t* __restrict__ hit_count,
+                                                   const bt_hit* __restrict__ hits, int64_t ray, int cap) {
+    if (valid_mask) return valid_mask[ray];
+    uint32_t m = 0;
+    const int c = hit_count[ray];
+    for (int h = 0; h < c; ++h) m |= (hits[ray * cap + h].flags == 0u ? 1u : 0u) << h;
+    return m;
+}
+
 __global__ void select_count_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits,
-                                    int64_t n_ref, int n_rays, int cap, int max_targets,
+                                    const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets,
                                     int32_t* __restrict__ pair_count) {
     const int64_t ref = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (ref >= n_ref) return;
     int cnt = 0;
     for (int r = lane; r < n_rays; r += 32) {
-        const int64_t ray = ref * n_rays + r;
-        const int c = hit_count[ray];
-        for (int h = 0; h < c; ++h) cnt += (hits[ray * cap + h].flags == 0u);
+        cnt += __popc(ray_valid_mask(valid_mask, hit_count, hits, ref * n_rays + r, cap));
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
@@ -470,7 +482,7 @@ __global__ void select_count_kernel(const int32_t* __restrict__ hit_count, const
 __global__ void zero_first_kernel(int64_t* p) { *p = 0; }
 
 __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits,
-                                   int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
+                                   const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
                                    const int64_t* __restrict__ pair_offset, int64_t cap_pairs,
                                    int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
     const int64_t ref = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -481,11 +493,7 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
     if (n_take == 0) return;
     // total number of valid hits (to know whether a random subset has to be drawn)
     int total = 0;
-    for (int r = lane; r < n_rays; r += 32) {
-        const int64_t ray = ref * n_rays + r;
-        const int c = hit_count[ray];
-        for (int h = 0; h < c; ++h) total += (hits[ray * cap + h].flags == 0u);
-    }
+    for (int r = lane; r < n_rays; r += 32) total += __popc(ray_valid_mask(valid_mask, hit_count, hits, ref * n_rays + r, cap));
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
     const bool random_subset = (seed != 0) && (total > max_targets);
@@ -495,12 +503,10 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
         int run = 0;
         for (int r0 = 0; r0 < n_rays; r0 += 32) {
             const int r = r0 + lane;
-            int c = 0, nv = 0;
+            uint32_t vm = 0;
             int64_t ray = ref * n_rays + r;
-            if (r < n_rays) {
-                c = hit_count[ray];
-                for (int h = 0; h < c; ++h) nv += (hits[ray * cap + h].flags == 0u);
-            }
+            if (r < n_rays) vm = ray_valid_mask(valid_mask, hit_count, hits, ray, cap);
+            const int nv = __popc(vm);
             int incl = nv;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
@@ -508,9 +514,10 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
                 if (lane >= s) incl += v;
             }
             int ord = run + incl - nv;
-            for (int h = 0; h < c; ++h) {
+            for (; vm; vm &= vm - 1) {
+                const int h = __ffs(vm) - 1;
                 const bt_hit* hp = hits + ray * cap + h;
-                if (hp->flags == 0u) {
+                {
                     if (ord < n_take && base + ord < cap_pairs) {
                         pair_ref[base + ord] = (int32_t)ref;
                         pair_q[3 * (base + ord) + 0] = hp->loc[0];
@@ -533,12 +540,10 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
         int run = 0;
         for (int r0 = 0; r0 < n_rays; r0 += 32) {
             const int r = r0 + lane;
-            int c = 0, nv = 0;
+            uint32_t vm = 0;
             int64_t ray = ref * n_rays + r;
-            if (r < n_rays) {
-                c = hit_count[ray];
-                for (int h = 0; h < c; ++h) nv += (hits[ray * cap + h].flags == 0u);
-            }
+            if (r < n_rays) vm = ray_valid_mask(valid_mask, hit_count, hits, ray, cap);
+            const int nv = __popc(vm);
             int incl = nv;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
@@ -546,8 +551,9 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
                 if (lane >= s) incl += v;
             }
             int ord = run + incl - nv;
-            for (int h = 0; h < c; ++h) {
-                if (hits[ray * cap + h].flags == 0u) {
+            for (; vm; vm &= vm - 1) {
+                const int h = __ffs(vm) - 1;
+                {
                     const uint64_t key = choice_key(seed, ref, ord);
                     const bool after_prev = (prev_ord < 0) || key > prev_key || (key == prev_key && ord > prev_ord);
                     const bool better = key < best_key || (key == best_key && ord < best_ord);
@@ -690,7 +696,7 @@ extern "C" int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, v
 
 extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
                            int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
-                           int32_t* d_overflow, void* stream) {
+                           uint32_t* d_valid_mask, int32_t* d_overflow, void* stream) {
     BT_REQUIRE(mesh && d_ref_pts && d_dirs && params && d_hit_count && d_hits, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
     const int cap = params->max_hits_per_ray;
@@ -721,16 +727,16 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
     BT_LAUNCH_CHECK();
     // stage 2: exact float64 narrow phase, ordering, de-duplication, filters, hit records
     if (cap <= 8)
-        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_overflow);
+        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_valid_mask, d_overflow);
     else if (cap <= 16)
-        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_overflow);
+        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_valid_mask, d_overflow);
     else
-        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_overflow);
+        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_valid_mask, d_overflow);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
 
-extern "C" int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, int64_t n_ref, int32_t n_rays,
+extern "C" int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays,
                              int32_t cap, int32_t max_targets, uint64_t seed, int32_t* d_pair_count,
                              int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs,
                              void* stream) {
@@ -741,14 +747,14 @@ extern "C" int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, i
     BT_LAUNCH_CHECK();
     if (n_ref == 0) return BT_OK;
     const unsigned grid = (unsigned)ceil_div(n_ref * 32, 128);
-    select_count_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, n_ref, n_rays, cap, max_targets, d_pair_count);
+    select_count_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, d_valid_mask, n_ref, n_rays, cap, max_targets, d_pair_count);
     BT_LAUNCH_CHECK();
     size_t tmp_bytes = 0;
     BT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
     Scratch tmp;
     BT_CUDA(tmp.alloc(tmp_bytes, st));
     BT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
-    select_fill_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, n_ref, n_rays, cap, max_targets, seed,
+    select_fill_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, d_valid_mask, n_ref, n_rays, cap, max_targets, seed,
                                              d_pair_offset, cap_pairs, d_pair_ref, d_pair_q);
     BT_LAUNCH_CHECK();
     return BT_OK;

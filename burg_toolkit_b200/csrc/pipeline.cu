@@ -87,10 +87,10 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
         STAGE_END(1);
     }
     STAGE_BEGIN(2);
-    STAGE_CALL(bt_ags_cast(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->overflow, stream));
+    STAGE_CALL(bt_ags_cast(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->valid_mask, b->overflow, stream));
     STAGE_END(2);
     STAGE_BEGIN(3);
-    STAGE_CALL(bt_ags_select(b->hit_count, b->hits, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray, cfg->max_targets,
+    STAGE_CALL(bt_ags_select(b->hit_count, b->hits, b->valid_mask, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray, cfg->max_targets,
                              seed ? seed + 0x2000 : 0 /* seed 0: first valid hit in canonical order */, b->pair_count, b->pair_offset, b->pair_ref, b->pair_q, b->cap_pairs, stream));
     STAGE_END(3);
     if (b->generate_frame_vecs && !cfg->halfspace) {

@@ -210,6 +210,7 @@ class PipelineWorkspace:
         self.dirs = torch.empty((max(n_ref, 1), n_rays, 3), dtype=f64, device=d)
         self.frame_vecs = torch.empty((max(n_ref, 1), 3), dtype=f64, device=d)
         self.hit_count = torch.empty((max(n_ref, 1) * n_rays,), dtype=i32, device=d)
+        self.valid_mask = torch.empty((max(n_ref, 1) * n_rays,), dtype=i32, device=d)
         self.hits = torch.empty((max(n_ref, 1) * n_rays * cap, 72), dtype=u8, device=d)
         self.overflow = torch.zeros((1,), dtype=i32, device=d)
         self.pair_count = torch.empty((max(n_ref, 1),), dtype=i32, device=d)
@@ -227,7 +228,7 @@ class PipelineWorkspace:
 
     def buffers(self, sample_surface, generate_dirs, generate_frame_vecs):
         b = nat.PipelineBuffers()
-        for name in ('ref_pts', 'ref_nrm', 'dirs', 'frame_vecs', 'hit_count', 'hits', 'overflow', 'pair_count',
+        for name in ('ref_pts', 'ref_nrm', 'dirs', 'frame_vecs', 'hit_count', 'valid_mask', 'hits', 'overflow', 'pair_count',
                      'pair_offset', 'pair_ref', 'pair_q', 'gs', 'contacts', 'n_grasps', 'colliding', 'free_gs',
                      'free_contacts', 'n_free'):
             t = getattr(self, name)

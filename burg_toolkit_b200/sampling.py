@@ -64,8 +64,8 @@ def _orientation_tables(n_orientations, halfspace):
 class CastResult:
     """Per-ray hit lists of one ``bt_ags_cast`` launch, resident on the device."""
 
-    def __init__(self, hit_count, hits, overflow, n_ref, n_rays, cap):
-        self.hit_count, self.hits, self.overflow = hit_count, hits, overflow
+    def __init__(self, hit_count, hits, overflow, n_ref, n_rays, cap, valid_mask=None):
+        self.hit_count, self.hits, self.overflow, self.valid_mask = hit_count, hits, overflow, valid_mask
         self.n_ref, self.n_rays, self.cap = n_ref, n_rays, cap
 
     def to_host(self):
@@ -179,8 +179,9 @@ class AntipodalGraspSampler:
                 hit_count = torch.empty((n_ref * n_rays,), dtype=torch.int32, device='cuda')
                 hits = torch.empty((n_ref * n_rays * cap, 72), dtype=torch.uint8, device='cuda')
                 overflow = torch.zeros((1,), dtype=torch.int32, device='cuda')
+                valid_mask = torch.empty((n_ref * n_rays,), dtype=torch.int32, device='cuda')
                 nat.call('bt_ags_cast', dm.handle, nat.ptr(pts), nat.ptr(dirs), n_ref, n_rays, C.byref(params),
-                         nat.ptr(hit_count), nat.ptr(hits), nat.ptr(overflow), nat.current_stream())
+                         nat.ptr(hit_count), nat.ptr(hits), nat.ptr(valid_mask), nat.ptr(overflow), nat.current_stream())
                 if not retry_on_overflow:
                     break
                 n_over = int(overflow.item())
@@ -190,7 +191,7 @@ class AntipodalGraspSampler:
                     raise RuntimeError(f'{n_over} rays cross more than 32 surfaces of the mesh; the hit list cannot '
                                        f'hold them (bt_ags_cast max_hits_per_ray <= 32)')
                 cap = min(32, cap * 2)                   # a ray crossed more surfaces than the list holds
-        return CastResult(hit_count, hits, overflow, n_ref, n_rays, cap)
+        return CastResult(hit_count, hits, overflow, n_ref, n_rays, cap, valid_mask)
 
     def select(self, cast, seed):
         """R7: per reference point up to ``max_targets_per_ref_point`` valid hits -> contact pairs."""
@@ -202,7 +203,7 @@ class AntipodalGraspSampler:
             pair_offset = torch.zeros((cast.n_ref + 1,), dtype=torch.int64, device='cuda')
             pair_ref = torch.empty((cap_pairs,), dtype=torch.int32, device='cuda')
             pair_q = torch.empty((cap_pairs, 3), dtype=torch.float64, device='cuda')
-            nat.call('bt_ags_select', nat.ptr(cast.hit_count), nat.ptr(cast.hits), cast.n_ref, cast.n_rays, cast.cap,
+            nat.call('bt_ags_select', nat.ptr(cast.hit_count), nat.ptr(cast.hits), nat.ptr(cast.valid_mask), cast.n_ref, cast.n_rays, cast.cap,
                      k, int(seed), nat.ptr(pair_count), nat.ptr(pair_offset), nat.ptr(pair_ref), nat.ptr(pair_q),
                      cap_pairs, nat.current_stream())
         return pair_count, pair_offset, pair_ref, pair_q, cap_pairs
@@ -307,7 +308,7 @@ class AntipodalGraspSampler:
         out = dict(n_ref=n_ref, n_candidates=n_ref * int(self.n_rays), pair_count=ws.pair_count, pair_offset=ws.pair_offset,
                    pair_ref=ws.pair_ref, pair_q=ws.pair_q, gs=ws.gs, contacts=ws.contacts, n_grasps=ws.n_grasps,
                    overflow=ws.overflow, ref_pts=ws.ref_pts, ref_nrm=ws.ref_nrm, directions=ws.dirs,
-                   cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap), cap_pairs=ws.cap_pairs)
+                   cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap, ws.valid_mask), cap_pairs=ws.cap_pairs)
         if check_collisions:
             out['colliding'] = ws.colliding[:ws.rows]
             if compact:

@@ -133,17 +133,20 @@ BT_API int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, void*
  *   d_ref_pts [n_ref,3] f64, d_dirs [n_ref,n_rays,3] f64
  *   d_hit_count [n_ref*n_rays] i32      number of hits of each ray (after trimesh's 1e-8 de-duplication)
  *   d_hits      [n_ref*n_rays*cap] bt_hit   a ray's hits sorted by (t, tri); cap = max_hits_per_ray
+ *   d_valid_mask [n_ref*n_rays] u32     bit h set iff hit h of the ray has flags == 0 (may be NULL; lets bt_ags_select
+ *                                       work without re-reading the hit records)
  *   d_overflow  [1] i32                 set to the number of rays whose hit list overflowed (may be NULL) */
 BT_API int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
                 int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
-                int32_t* d_overflow, void* stream);
+                uint32_t* d_valid_mask, int32_t* d_overflow, void* stream);
 
 /* ---- R7: per reference point pick up to max_targets of its valid hits (replaces sampling.py:328-331).
  *   seed == 0 : deterministic, the first max_targets valid hits in canonical order (ray, t)
  *   seed != 0 : uniformly random subset keyed by (seed, reference point)
  *   d_pair_count [n_ref] i32 out; d_pair_offset [n_ref+1] i64 out (exclusive scan);
  *   d_pair_ref [cap_pairs] i32, d_pair_q [cap_pairs,3] f64 out; cap_pairs >= n_ref*max_targets is always enough */
-BT_API int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, int64_t n_ref, int32_t n_rays,
+BT_API int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, const uint32_t* d_valid_mask /* may be NULL */,
+                  int64_t n_ref, int32_t n_rays,
                   int32_t max_hits_per_ray, int32_t max_targets, uint64_t seed, int32_t* d_pair_count,
                   int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs,
                   void* stream);
@@ -214,6 +217,7 @@ typedef struct bt_pipeline_buffers {
     double*  frame_vecs;     /* [n_ref,3]   in, or generated when generate_frame_vecs != 0   */
     int32_t  sample_surface, generate_dirs, generate_frame_vecs, reserved;
     int32_t* hit_count;      /* [n_ref*n_rays]                                               */
+    uint32_t* valid_mask;    /* [n_ref*n_rays]                                               */
     bt_hit*  hits;           /* [n_ref*n_rays*max_hits_per_ray]                              */
     int32_t* overflow;       /* [1]                                                          */
     int32_t* pair_count;     /* [n_ref]                                                      */
