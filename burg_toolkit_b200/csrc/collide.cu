@@ -153,12 +153,18 @@ __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, 
 // Work item = (gripper part, grasp).  Traversal lengths differ by orders of magnitude between items (a stem far from the
 // object ends at the root, a finger grazing the surface visits hundreds of nodes), so items are NOT bound to threads:
 // warps are persistent and every lane fetches a new item from a global counter as soon as enough lanes of its warp have
-// run dry (refill at >= 8 idle lanes keeps both the set-up code and the traversal loop well filled).
-//   phase A (per lane): the part's oriented box walks the scene LBVH (float32, conservative 6-axis test); each reached
-//                       triangle is classified disjoint / inside-a-closed-box / undecided; undecided leaves are parked.
-//   phase B (per warp): parked leaves are drained with FCL's exact float64 17-axis test, lane l <-> gripper triangle l.
-constexpr int PEND = 6;                    // undecided leaves a lane may park before the warp drains
-constexpr int REFILL_AT = 8;               // idle lanes that trigger a refill
+// run dry.  The three kinds of work have very different instruction streams, so they never share a divergent branch:
+//   walk     (per lane)      the part's oriented box walks the scene LBVH (float32, conservative 6-axis test) in short
+//                            bursts; a reached leaf is only APPENDED to the warp's classification queue (shared memory).
+//   classify (warp, 32 wide) once 32 leaves are queued every lane takes one (item, leaf) entry -- of ANY lane's item: the
+//                            box is rebuilt from the grasp row -- and classifies the triangle in box-local float32
+//                            coordinates: disjoint / inside-a-closed-box / undecided.  Undecided entries go to the exact queue.
+//   exact    (half warps)    two queued entries per pass: lane l of a half tests gripper triangle l of the part with FCL's
+//                            float64 17-axis test.  A hit sets out[row] and tells the lane still walking that item to stop.
+constexpr int TQ_CAP = 1024;               // task stack entries per warp
+constexpr int CWARPS = 4;                  // warps per block
+constexpr int CQ_CAP = 96;                 // classification queue: < 32 left over + at most 64 new entries per pass
+constexpr int XQ_CAP = 64;                 // exact queue: <= 1 left over + 32 new entries
 
 struct LaneBox {
     float u[3][3];                         // world axes (columns of R), un-normalised
@@ -168,20 +174,7 @@ struct LaneBox {
     float cf[3];                           // centre (float32)
     double c[3];                           // centre (float64, for the leaf classifier)
     float margin;
-    int tri_begin, tri_end, is_box;
 };
-
-__device__ __forceinline__ bool lanebox_overlaps(const LaneBox& b, float x0, float y0, float z0, float x1, float y1, float z1) {
-    const float ex = 0.5f * (x1 - x0), ey = 0.5f * (y1 - y0), ez = 0.5f * (z1 - z0);
-    const float dx = 0.5f * (x1 + x0) - b.cf[0], dy = 0.5f * (y1 + y0) - b.cf[1], dz = 0.5f * (z1 + z0) - b.cf[2];
-    if (fabsf(dx) > ex + b.a[0] || fabsf(dy) > ey + b.a[1] || fabsf(dz) > ez + b.a[2]) return false;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const float pr = fabsf(fmaf(dx, b.u[j][0], fmaf(dy, b.u[j][1], dz * b.u[j][2])));
-        if (pr > b.h[j] + fmaf(ex, fabsf(b.u[j][0]), fmaf(ey, fabsf(b.u[j][1]), ez * fabsf(b.u[j][2])))) return false;
-    }
-    return true;
-}
 
 // pose * diag(s,1,1): M (row-major 3x3) and T of grasp `row`  (sampling.py:392-395; s in float32 as numpy >= 2 does)
 __device__ __forceinline__ void grasp_affine(const float* __restrict__ gs, int64_t row, float ow, float tol, int use_width,
@@ -199,157 +192,327 @@ __device__ __forceinline__ void grasp_affine(const float* __restrict__ gs, int64
     sf_out = sf;
 }
 
+// the oriented box of traversal item (grasp row, part segment); callers use a subset of the fields (the rest is dead code)
+__device__ __forceinline__ void build_lanebox(LaneBox& b, const float* __restrict__ gs, int64_t row, const PartDev& pd,
+                                              float ow, float tol, int use_width, float inflate) {
+    double M[9], T[3];
+    float sf;
+    grasp_affine(gs, row, ow, tol, use_width, M, T, sf);
+    const float* g = gs + 14 * row;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { b.u[j][0] = __ldg(g + 3 + j); b.u[j][1] = __ldg(g + 6 + j); b.u[j][2] = __ldg(g + 9 + j); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        b.c[i] = (M[3 * i] * pd.cx + M[3 * i + 1] * pd.cy) + M[3 * i + 2] * pd.cz + T[i];
+        b.cf[i] = (float)b.c[i];
+    }
+    const float ext[3] = {pd.hx * fabsf(sf), pd.hy, pd.hz};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        // a float32 rotation block is orthonormal only to ~1e-7: use the actual column norms
+        const float nn = sqrtf(b.u[j][0] * b.u[j][0] + b.u[j][1] * b.u[j][1] + b.u[j][2] * b.u[j][2]);
+        b.h[j] = ext[j] * nn * nn * 1.0001f + inflate;
+        b.inv_n[j] = nn > 0.f ? 1.0f / nn : 0.f;
+        b.le[j] = ext[j] * nn;
+        const float sc = (j == 0) ? fabsf(sf) : 1.0f;
+        b.off[j] = (j == 0 ? pd.ox : (j == 1 ? pd.oy : pd.oz)) * (j == 0 ? sf : 1.0f) * nn;
+        b.fe[j] = (j == 0 ? pd.fhx : (j == 1 ? pd.fhy : pd.fhz)) * sc * nn;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        b.a[a] = (fabsf(b.u[0][a]) * ext[0] + fabsf(b.u[1][a]) * ext[1] + fabsf(b.u[2][a]) * ext[2]) * 1.0001f + inflate;
+    b.margin = inflate + 1e-4f * fmaxf(b.le[0], fmaxf(b.le[1], b.le[2]));
+}
+
+// The traversal box of an item in plain float32 and without divisions / square roots (no slow-path subroutine calls in
+// the refill code): the walk is a conservative broad phase, so the squeeze factor and the centre may carry float32
+// rounding (~1e-8 m), which the inflation (>= 1e-6 m) covers.  Layout: u[9] (axes, [j][k]), h[3], a[3], cf[3].
+struct WalkBox { float u[3][3], h[3], a[3], cf[3]; };
+
+__device__ __forceinline__ void build_walkbox(WalkBox& b, const float* __restrict__ gs, int64_t row, const PartDev& pd,
+                                              float inv_ow, float tol, int use_width, float inflate) {
+    const float* g = gs + 14 * row;
+    const float sf = use_width ? (__ldg(g + 13) + tol) * inv_ow : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { b.u[j][0] = __ldg(g + 3 + j); b.u[j][1] = __ldg(g + 6 + j); b.u[j][2] = __ldg(g + 9 + j); }
+    const float px = pd.cx * sf;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b.cf[i] = fmaf(b.u[0][i], px, fmaf(b.u[1][i], pd.cy, fmaf(b.u[2][i], pd.cz, __ldg(g + i))));
+    const float ext[3] = {pd.hx * fabsf(sf) * 1.000001f, pd.hy, pd.hz};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float nn2 = b.u[j][0] * b.u[j][0] + b.u[j][1] * b.u[j][1] + b.u[j][2] * b.u[j][2];
+        b.h[j] = ext[j] * nn2 * 1.0001f + inflate;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        b.a[a] = (fabsf(b.u[0][a]) * ext[0] + fabsf(b.u[1][a]) * ext[1] + fabsf(b.u[2][a]) * ext[2]) * 1.0001f + inflate;
+}
+
+__device__ __forceinline__ uint8_t load_flag(const uint8_t* p) { return *reinterpret_cast<const volatile uint8_t*>(p); }
+
+struct CollideParams { float ow, tol, inflate; int use_width; };
+
+// classify scene triangle `tv` against the box of item (row, part): true = undecided, run the exact test
+__device__ __forceinline__ bool leaf_undecided(const float* __restrict__ gs, int row, const PartDev* pd_ptr, const double* __restrict__ tv,
+                                            CollideParams cp) {
+    const PartDev pd = *pd_ptr;
+    LaneBox cb;
+    build_lanebox(cb, gs, row, pd, cp.ow, cp.tol, cp.use_width, cp.inflate);
+    float q[3][3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const float dx = (float)(tv[3 * v] - cb.c[0]), dy = (float)(tv[3 * v + 1] - cb.c[1]), dz = (float)(tv[3 * v + 2] - cb.c[2]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) q[v][j] = fmaf(dx, cb.u[j][0], fmaf(dy, cb.u[j][1], dz * cb.u[j][2])) * cb.inv_n[j];
+    }
+    const int cls = classify_triangle(q, cb.le[0], cb.le[1], cb.le[2], cb.margin, cb.off, cb.fe);
+    return !(cls == 0 || (cls == 1 && pd.is_box));
+}
+
+// FCL's exact test of scene triangle `tv` against gripper triangle `gt` (TCP frame) under the affine map of grasp `row`
+__device__ __forceinline__ bool exact_pair_hit(const float* __restrict__ gs, int row, const double* __restrict__ tv, const double* gt,
+                                            CollideParams cp) {
+    double M[9], T[3];
+    float sf;
+    grasp_affine(gs, row, cp.ow, cp.tol, cp.use_width, M, T, sf);
+    d3 Q[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const double px = gt[3 * v], py = gt[3 * v + 1], pz = gt[3 * v + 2];
+        Q[v] = mk3(((M[0] * px + M[1] * py) + M[2] * pz) + T[0], ((M[3] * px + M[4] * py) + M[5] * pz) + T[1],
+                   ((M[6] * px + M[7] * py) + M[8] * pz) + T[2]);
+    }
+    return tri_tri_intersect(ld3(tv), ld3(tv + 3), ld3(tv + 6), Q[0], Q[1], Q[2]);
+}
+
+// The queue-draining passes live in their own (not inlined) function: their register needs (float64 triangle pairs)
+// would otherwise push the traversal state of the walking lanes into local memory for the whole kernel.  The walk boxes
+// are parked in shared memory around the call, so nothing but a few scalars is live across it.
+struct DrainArgs {
+    const float* gs; const double* tri_verts; const double* gtris; const PartDev* parts; uint8_t* out;
+    int *cq_row, *cq_leaf, *cq_meta, *xq_row, *xq_leaf, *xq_meta, *slot_row, *slot_dead;
+    CollideParams cp;
+};
+
+// exact passes first (keeps the exact queue below 2 + 32 entries), then classification; returns (nx, ncq)
 template <bool STATS>
-__global__ void __launch_bounds__(128, 4)
+__device__ __noinline__ int2 drain_queues(const DrainArgs& a, int nx, int ncq, bool final, int lane, unsigned long long* st) {
+    const unsigned FULL = 0xffffffffu;
+while (true) {
+        if (nx >= 2 || (final && ncq == 0 && nx > 0)) {
+            // exact: two queued entries per pass, one per half warp
+            const int half = lane >> 4, sub = lane & 15;
+            const int e = nx - 1 - half;
+            int x_row = 0, x_leaf = 0, x_meta = 0, tb = 0, cnt = 0;
+            if (e >= 0) {
+                x_row = a.xq_row[e]; x_leaf = a.xq_leaf[e]; x_meta = a.xq_meta[e];
+                if (!load_flag(a.out + x_row)) { tb = a.parts[x_meta & 0xff].tri_begin; cnt = a.parts[x_meta & 0xff].tri_end - tb; }
+            }
+            const int max_cnt = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
+            bool found = false;
+            for (int t0 = 0; t0 < max_cnt; t0 += 16) {
+                bool hit = false;
+                if (!found && t0 + sub < cnt)
+                    hit = exact_pair_hit(a.gs, x_row, a.tri_verts + 9 * (int64_t)x_leaf, a.gtris + 9 * (tb + t0 + sub), a.cp);
+                const unsigned hb = __ballot_sync(FULL, hit);
+                found = found || (((hb >> (16 * half)) & 0xffffu) != 0u);
+            }
+            if (found && sub == 0) { a.out[x_row] = 1; if (a.slot_row[x_meta >> 8] == x_row) a.slot_dead[x_meta >> 8] = 1; }
+            nx = max(nx - 2, 0);
+            __syncwarp();
+        } else if (ncq >= 32 || (final && ncq > 0)) {
+            // classify: 32 queued (item, leaf) entries at a time
+            const int take = min(32, ncq), qbase = ncq - take;
+            bool undecided = false;
+            int e_row = 0, e_leaf = 0, e_meta = 0;
+            if (lane < take) {
+                e_row = a.cq_row[qbase + lane]; e_leaf = a.cq_leaf[qbase + lane]; e_meta = a.cq_meta[qbase + lane];
+                if (!load_flag(a.out + e_row)) {
+                    undecided = leaf_undecided(a.gs, e_row, &a.parts[e_meta & 0xff], a.tri_verts + 9 * (int64_t)e_leaf, a.cp);
+                    if (STATS) { ++st[0]; if (undecided) ++st[1]; }
+                }
+            }
+            const unsigned ub = __ballot_sync(FULL, undecided);
+            if (undecided) {
+                const int slot = nx + __popc(ub & ((1u << lane) - 1u));
+                a.xq_row[slot] = e_row; a.xq_leaf[slot] = e_leaf; a.xq_meta[slot] = e_meta;
+            }
+            nx += __popc(ub);
+            ncq = qbase;
+            __syncwarp();
+        } else {
+            break;
+        }
+    }
+    return make_int2(nx, ncq);
+}
+
+// branch-free version of the conservative 6-axis box test (all 32 lanes of a pass run the same instructions)
+__device__ __forceinline__ bool box_overlaps(const float* bx, float x0, float y0, float z0, float x1, float y1, float z1) {
+    // bx: u[9] ([j][k]), h[3], a[3], cf[3]
+    const float ex = 0.5f * (x1 - x0), ey = 0.5f * (y1 - y0), ez = 0.5f * (z1 - z0);
+    const float dx = 0.5f * (x1 + x0) - bx[15], dy = 0.5f * (y1 + y0) - bx[16], dz = 0.5f * (z1 + z0) - bx[17];
+    bool ov = (fabsf(dx) <= ex + bx[12]) & (fabsf(dy) <= ey + bx[13]) & (fabsf(dz) <= ez + bx[14]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float pr = fabsf(fmaf(dx, bx[3 * j], fmaf(dy, bx[3 * j + 1], dz * bx[3 * j + 2])));
+        ov = ov & (pr <= bx[9 + j] + fmaf(ex, fabsf(bx[3 * j]), fmaf(ey, fabsf(bx[3 * j + 1]), ez * fabsf(bx[3 * j + 2]))));
+    }
+    return ov;
+}
+
+// Work item = (gripper part segment, grasp).  Traversal lengths differ by orders of magnitude between items (a stem far
+// from the object ends at the root, a finger grazing the surface visits hundreds of nodes), so neither items nor their
+// walks are bound to threads.  Every warp keeps up to 32 items in flight in shared-memory SLOTS (oriented box, row, part)
+// and one LIFO stack of TASKS (slot, LBVH node) for all of them:
+//   walk     each pass the 32 lanes pop 32 tasks -- of whatever items -- test both children of the node against the
+//            slot's box (float32, conservative 6 axes, branch-free), push internal children as new tasks and leaf children
+//            as (row, part, leaf) entries of the classification queue.  Lane utilisation no longer depends on how long the
+//            individual walks are.  A slot is free again when its pending-task count drops to zero; free slots are
+//            refilled from a global work counter.
+//   classify once 32 leaves are queued every lane takes one entry and classifies the triangle in box-local float32
+//            coordinates: disjoint / inside-a-closed-box / undecided.  Undecided entries go to the exact queue.
+//   exact    two queued entries per pass, one per half warp: lane l tests gripper triangle l of the part with FCL's
+//            float64 17-axis test.  A hit sets out[row] and marks the slot dead (its remaining tasks are discarded).
+// Stack bound: a multi-pop pass grows the stack by at most 32, a single-pop pass (taken near the capacity) by at most
+// one per tree level, so TQ_CAP - (max_depth + 2) is a safe threshold for switching to single pops.
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(32 * CWARPS, MINB)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
                int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
                const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
-               unsigned long long* __restrict__ work_counter, uint8_t* __restrict__ out,
+               int max_depth, int refill_at, unsigned long long* __restrict__ work_counter, uint8_t* out,
                unsigned long long* __restrict__ counters) {
-    unsigned long long st_nodes = 0, st_leaves = 0, st_exact = 0;
+    unsigned long long st_nodes = 0;
     extern __shared__ double s_gtris[];            // gripper triangles, TCP frame
     __shared__ PartDev s_parts[MAX_PARTS];
+    __shared__ int s_cq_row[CWARPS][CQ_CAP], s_cq_leaf[CWARPS][CQ_CAP], s_cq_meta[CWARPS][CQ_CAP];
+    __shared__ int s_xq_row[CWARPS][XQ_CAP], s_xq_leaf[CWARPS][XQ_CAP], s_xq_meta[CWARPS][XQ_CAP];
+    __shared__ float s_box[CWARPS][18][32];
+    __shared__ int s_row[CWARPS][32], s_part[CWARPS][32], s_pending[CWARPS][32], s_dead[CWARPS][32];
+    __shared__ int s_tq[CWARPS][TQ_CAP];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
     const int n_gt = parts[n_parts - 1].tri_end;
     for (int i = threadIdx.x; i < 9 * n_gt; i += blockDim.x) s_gtris[i] = gtris[i];
     for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_parts[i] = parts[i];
+    s_row[w][lane] = -1; s_pending[w][lane] = 0; s_dead[w][lane] = 0;
     __syncthreads();
+    int* tq = s_tq[w];
+    int* cq_row = s_cq_row[w]; int* cq_leaf = s_cq_leaf[w]; int* cq_meta = s_cq_meta[w];
 
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
     const int64_t total = n * n_parts;             // item = part * n + row  (part-major: neighbouring items share a region)
+    const float inv_ow = 1.0f / ow;
+    const int multi_limit = TQ_CAP - (max_depth + 2) - 32;      // multi-pop passes only while nt <= multi_limit
 
-    LaneBox b;
-    int64_t row = 0;
-    int stack[CSTACK];
-    int pend[PEND];
-    int sp = 0, np = 0, cur = 0;
-    bool busy = false, exhausted = false;
+    DrainArgs da;
+    da.gs = gs; da.tri_verts = tri_verts; da.gtris = s_gtris; da.parts = s_parts; da.out = out;
+    da.cq_row = cq_row; da.cq_leaf = cq_leaf; da.cq_meta = cq_meta;
+    da.xq_row = s_xq_row[w]; da.xq_leaf = s_xq_leaf[w]; da.xq_meta = s_xq_meta[w];
+    da.slot_row = s_row[w]; da.slot_dead = s_dead[w];
+    da.cp.ow = ow; da.cp.tol = tol; da.cp.inflate = inflate; da.cp.use_width = use_width;
+    unsigned long long st_drain[2] = {0, 0};
+
+    unsigned free_mask = FULL;                     // warp-uniform: slots without pending tasks
+    int nt = 0, nx = 0, ncq = 0;                   // warp-uniform: entries on the task stack / exact queue / classification queue
+    bool exhausted = false;
 
     while (true) {
-        // ---- refill --------------------------------------------------------------------------------------------------
-        const unsigned idle = __ballot_sync(FULL, !busy);
-        if (!exhausted && (__popc(idle) >= REFILL_AT)) {
+        // ---- refill free slots with new items ---------------------------------------------------------------------------
+        const int n_free = __popc(free_mask);
+        if (!exhausted && n_free >= refill_at && nt <= multi_limit) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)__popc(idle));
+            if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)n_free);
             base = __shfl_sync(FULL, base, 0);
-            if (!busy) {
-                const int64_t item = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+            bool take = false;
+            int slot = 0;
+            if (lane < n_free) {
+                const int64_t item = (int64_t)base + lane;
                 if (item < total) {
                     const int part = (int)(item / n);
-                    row = item - (int64_t)part * n;
-                    if (!out[row]) {                                       // another part of this grasp may already collide
-                        double M[9], T[3];
-                        float sf;
-                        grasp_affine(gs, row, ow, tol, use_width, M, T, sf);
-                        const PartDev pd = s_parts[part];
-                        const float* g = gs + 14 * row;
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) { b.u[j][0] = __ldg(g + 3 + j); b.u[j][1] = __ldg(g + 6 + j); b.u[j][2] = __ldg(g + 9 + j); }
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            b.c[i] = (M[3 * i] * pd.cx + M[3 * i + 1] * pd.cy) + M[3 * i + 2] * pd.cz + T[i];
-                            b.cf[i] = (float)b.c[i];
-                        }
-                        const float ext[3] = {pd.hx * fabsf(sf), pd.hy, pd.hz};
+                    const int64_t row = item - (int64_t)part * n;
+                    if (!load_flag(out + row)) {                               // another part of this grasp may already collide
+                        slot = __fns(free_mask, 0, lane + 1);
+                        WalkBox b;
+                        build_walkbox(b, gs, row, s_parts[part], inv_ow, tol, use_width, inflate);
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
-                            // a float32 rotation block is orthonormal only to ~1e-7: use the actual column norms
-                            const float nn = sqrtf(b.u[j][0] * b.u[j][0] + b.u[j][1] * b.u[j][1] + b.u[j][2] * b.u[j][2]);
-                            b.h[j] = ext[j] * nn * nn * 1.0001f + inflate;
-                            b.inv_n[j] = nn > 0.f ? 1.0f / nn : 0.f;
-                            b.le[j] = ext[j] * nn;
-                            const float sc = (j == 0) ? fabsf(sf) : 1.0f;
-                            b.off[j] = (j == 0 ? pd.ox : (j == 1 ? pd.oy : pd.oz)) * (j == 0 ? sf : 1.0f) * nn;
-                            b.fe[j] = (j == 0 ? pd.fhx : (j == 1 ? pd.fhy : pd.fhz)) * sc * nn;
-                        }
 #pragma unroll
-                        for (int a = 0; a < 3; ++a)
-                            b.a[a] = (fabsf(b.u[0][a]) * ext[0] + fabsf(b.u[1][a]) * ext[1] + fabsf(b.u[2][a]) * ext[2]) * 1.0001f + inflate;
-                        b.margin = inflate + 1e-4f * fmaxf(b.le[0], fmaxf(b.le[1], b.le[2]));
-                        b.tri_begin = pd.tri_begin; b.tri_end = pd.tri_end; b.is_box = pd.is_box;
-                        busy = true; sp = 0; np = 0; cur = 0;
+                            for (int k = 0; k < 3; ++k) s_box[w][3 * j + k][slot] = b.u[j][k];
+                            s_box[w][9 + j][slot] = b.h[j]; s_box[w][12 + j][slot] = b.a[j]; s_box[w][15 + j][slot] = b.cf[j];
+                        }
+                        s_row[w][slot] = (int)row; s_part[w][slot] = part; s_pending[w][slot] = 1; s_dead[w][slot] = 0;
+                        take = true;
                     }
                 }
             }
-            if (base + (unsigned long long)__popc(idle) >= (unsigned long long)total) exhausted = true;
+            const unsigned tb = __ballot_sync(FULL, take);
+            if (take) tq[nt + __popc(tb & lt)] = slot << 26;                    // (slot, root node 0)
+            free_mask &= ~__reduce_or_sync(FULL, take ? (1u << slot) : 0u);
+            nt += __popc(tb);
+            if (base + (unsigned long long)n_free >= (unsigned long long)total) exhausted = true;
+            __syncwarp();
         }
-        if (!__any_sync(FULL, busy)) {
-            if (exhausted) break;
-            continue;
+        if (nt == 0) {
+            if (!exhausted) continue;              // every slot is free here, so the next refill takes 32 items
+            break;
         }
-        // ---- phase A: a bounded burst of traversal steps ---------------------------------------------------------------
-        for (int step = 0; step < 16 && busy && np < PEND; ++step) {
-            if (cur < 0) {
-                const double* tv = tri_verts + 9 * (int64_t)(~cur);
-                float q[3][3];
+        // ---- walk: pop up to 32 tasks, test both children, push ---------------------------------------------------------
+        const int take_n = nt <= multi_limit ? min(32, nt) : 1;
+        const bool has = lane < take_n;
+        nt -= take_n;
+        int slot = 0, l = 0, r = 0;
+        bool hl = false, hr = false;
+        if (has) {
+            const int task = tq[nt + lane];
+            slot = task >> 26;
+            if (!s_dead[w][slot]) {
+                const int node = task & 0x3ffffff;
+                if (STATS) ++st_nodes;
+                const float4 q0 = __ldg(nodes + 4 * (int64_t)node + 0);
+                const float4 q1 = __ldg(nodes + 4 * (int64_t)node + 1);
+                const float4 q2 = __ldg(nodes + 4 * (int64_t)node + 2);
+                const float4 q3 = __ldg(nodes + 4 * (int64_t)node + 3);
+                float bx[18];
 #pragma unroll
-                for (int v = 0; v < 3; ++v) {
-                    const float dx = (float)(tv[3 * v] - b.c[0]), dy = (float)(tv[3 * v + 1] - b.c[1]), dz = (float)(tv[3 * v + 2] - b.c[2]);
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) q[v][j] = fmaf(dx, b.u[j][0], fmaf(dy, b.u[j][1], dz * b.u[j][2])) * b.inv_n[j];
-                }
-                const int cls = classify_triangle(q, b.le[0], b.le[1], b.le[2], b.margin, b.off, b.fe);
-                if (STATS) ++st_leaves;
-                if (!(cls == 0 || (cls == 1 && b.is_box))) { pend[np++] = ~cur; if (STATS) ++st_exact; }
-                if (sp == 0) { busy = false; break; }
-                cur = stack[--sp];
-                continue;
+                for (int k = 0; k < 18; ++k) bx[k] = s_box[w][k][slot];
+                hl = box_overlaps(bx, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+                hr = box_overlaps(bx, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+                l = __float_as_int(q3.x); r = __float_as_int(q3.y);
             }
-            if (STATS) ++st_nodes;
-            const float4 q0 = __ldg(nodes + 4 * (int64_t)cur + 0);
-            const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
-            const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
-            const float4 q3 = __ldg(nodes + 4 * (int64_t)cur + 3);
-            const bool hl = lanebox_overlaps(b, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-            const bool hr = lanebox_overlaps(b, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
-            const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
-            if (hl && hr) { stack[sp++] = r; cur = l; }
-            else if (hl) cur = l;
-            else if (hr) cur = r;
-            else { if (sp == 0) { busy = false; break; } cur = stack[--sp]; }
         }
+        __syncwarp();                               // all pops are done before anything is pushed over them
+        const bool pl = hl && l >= 0, pr = hr && r >= 0, ll = hl && l < 0, lr = hr && r < 0;
+        const unsigned bl = __ballot_sync(FULL, pl), br = __ballot_sync(FULL, pr);
+        if (pl) tq[nt + __popc(bl & lt)] = l | (slot << 26);
+        nt += __popc(bl);
+        if (pr) tq[nt + __popc(br & lt)] = r | (slot << 26);
+        nt += __popc(br);
+        const unsigned cl = __ballot_sync(FULL, ll), cr = __ballot_sync(FULL, lr);
+        if (cl | cr) {
+            if (ll) { const int q = ncq + __popc(cl & lt); cq_row[q] = s_row[w][slot]; cq_leaf[q] = ~l; cq_meta[q] = s_part[w][slot] | (slot << 8); }
+            ncq += __popc(cl);
+            if (lr) { const int q = ncq + __popc(cr & lt); cq_row[q] = s_row[w][slot]; cq_leaf[q] = ~r; cq_meta[q] = s_part[w][slot] | (slot << 8); }
+            ncq += __popc(cr);
+        }
+        bool freed = false;
+        if (has) {
+            const int delta = (int)pl + (int)pr - 1;
+            freed = (atomicAdd(&s_pending[w][slot], delta) + delta) == 0;
+        }
+        free_mask |= __reduce_or_sync(FULL, freed ? (1u << slot) : 0u);
         __syncwarp();
-        // ---- phase B: drain parked leaves of lanes that are full or finished ------------------------------------------
-        unsigned has = __ballot_sync(FULL, np > 0 && (np >= PEND || !busy));
-        while (has) {
-            const int src = __ffs(has) - 1;
-            const int cnt = __shfl_sync(FULL, np, src);
-            const int tb = __shfl_sync(FULL, b.tri_begin, src), te = __shfl_sync(FULL, b.tri_end, src);
-            const int64_t srow = __shfl_sync(FULL, row, src);
-            double M[9], T[3];
-            float sf;
-            grasp_affine(gs, srow, ow, tol, use_width, M, T, sf);        // same address in every lane: broadcast loads
-            bool found = false;
-            for (int k = 0; k < cnt && !found; ++k) {
-                const int leaf = __shfl_sync(FULL, pend[k < PEND ? k : 0], src);
-                const double* tv = tri_verts + 9 * (int64_t)leaf;
-                const d3 P1 = ld3(tv), P2 = ld3(tv + 3), P3 = ld3(tv + 6);
-                for (int t0 = tb; t0 < te && !found; t0 += 32) {
-                    const int t = t0 + lane;
-                    bool hit = false;
-                    if (t < te) {
-                        const double* gt = s_gtris + 9 * t;
-                        d3 Q[3];
-#pragma unroll
-                        for (int v = 0; v < 3; ++v) {
-                            const double px = gt[3 * v], py = gt[3 * v + 1], pz = gt[3 * v + 2];
-                            Q[v] = mk3(((M[0] * px + M[1] * py) + M[2] * pz) + T[0], ((M[3] * px + M[4] * py) + M[5] * pz) + T[1],
-                                       ((M[6] * px + M[7] * py) + M[8] * pz) + T[2]);
-                        }
-                        hit = tri_tri_intersect(P1, P2, P3, Q[0], Q[1], Q[2]);
-                    }
-                    found = __any_sync(FULL, hit);
-                }
-            }
-            if (lane == src) {
-                np = 0;
-                if (found) { out[row] = 1; busy = false; }
-            }
-            has = __ballot_sync(FULL, np > 0 && (np >= PEND || !busy));
+        // ---- drain the queues ---------------------------------------------------------------------------------------------
+        if (nx >= 2 || ncq >= 32) {
+            const int2 res = drain_queues<STATS>(da, nx, ncq, false, lane, st_drain);
+            nx = res.x; ncq = res.y;
         }
     }
-    if (STATS) { atomicAdd(counters + 3, st_nodes); atomicAdd(counters + 4, st_leaves); atomicAdd(counters + 5, st_exact); }
+    if (nx > 0 || ncq > 0) drain_queues<STATS>(da, nx, ncq, true, lane, st_drain);
+    if (STATS) { atomicAdd(counters + 3, st_nodes); atomicAdd(counters + 4, st_drain[0]); atomicAdd(counters + 5, st_drain[1]); }
 }
 
 // ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------
@@ -511,7 +674,7 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
                           const int64_t* d_n, double opening_width, double width_tolerance, int32_t use_width,
                           uint8_t* d_colliding, void* stream) {
     BT_REQUIRE(scene && gripper && d_gs && d_colliding, "null pointer");
-    BT_REQUIRE(n >= 0, "negative count");
+    BT_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "row count must be in [0, 2^31)");
     BT_REQUIRE(scene->m.device == gripper->device, "scene and gripper live on different devices");
     BT_REQUIRE((reinterpret_cast<uintptr_t>(d_colliding) & 3) == 0, "d_colliding must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -523,28 +686,36 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
         max_abs = fmaxf(max_abs, fmaxf(fabsf(scene->m.info.bounds_min[k]), fabsf(scene->m.info.bounds_max[k])));
     const float inflate = 2e-5f * max_abs + 1e-6f;
     const size_t tri_bytes = sizeof(double) * 9 * (size_t)gripper->n_tris;
-    if (tri_bytes > 8 * 1024)
-    {
-        BT_CUDA(cudaFuncSetAttribute(collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
-        BT_CUDA(cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+    // tuning knobs (environment, read once): traversal burst length, refill threshold, occupancy variant
+    static int refill_at = 0, minb = 0;
+    if (!refill_at) {
+        const char* e;
+        refill_at = (e = getenv("BT_COLLIDE_REFILL")) ? std::max(1, std::min(32, atoi(e))) : 24;
+        minb = (e = getenv("BT_COLLIDE_MINB")) ? atoi(e) : 4;
     }
+    BT_REQUIRE(scene->m.info.n_nodes < (1 << 26), "scene LBVH has more than 2^26 nodes");
+    BT_REQUIRE(scene->m.info.max_depth + 2 + 64 <= TQ_CAP, "scene LBVH too deep for the task stack");
     Scratch counter;
     BT_CUDA(counter.alloc(sizeof(unsigned long long), st));
     BT_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->m.device);
     const int64_t items = n * gripper->n_parts;
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * 4);   // persistent: 4 CTAs / SM
-    if (g_counters_host_copy)
-        collide_kernel<true><<<grid, 128, tri_bytes, st>>>(
-            scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
-            (float)opening_width, (float)width_tolerance, use_width, inflate, counter.as<unsigned long long>(), d_colliding,
-            g_counters_host_copy);
-    else
-        collide_kernel<false><<<grid, 128, tri_bytes, st>>>(
-            scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,
-            (float)opening_width, (float)width_tolerance, use_width, inflate, counter.as<unsigned long long>(), d_colliding,
-            nullptr);
+    const int per_sm = minb == 3 ? 3 : 4;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * per_sm);   // persistent CTAs
+#define BT_COLLIDE_LAUNCH(STATS, MINB, CNT)                                                                                   \
+    do {                                                                                                                      \
+        if (tri_bytes > 8 * 1024)                                                                                             \
+            BT_CUDA(cudaFuncSetAttribute(collide_kernel<STATS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes)); \
+        collide_kernel<STATS, MINB><<<grid, 32 * CWARPS, tri_bytes, st>>>(                                                    \
+            scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,               \
+            (float)opening_width, (float)width_tolerance, use_width, inflate, (int)scene->m.info.max_depth, refill_at,                              \
+            counter.as<unsigned long long>(), d_colliding, CNT);                                                              \
+    } while (0)
+    if (g_counters_host_copy) BT_COLLIDE_LAUNCH(true, 4, g_counters_host_copy);
+    else if (minb == 3) BT_COLLIDE_LAUNCH(false, 3, nullptr);
+    else BT_COLLIDE_LAUNCH(false, 4, nullptr);
+#undef BT_COLLIDE_LAUNCH
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
