@@ -49,23 +49,63 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML every ~2 ms when the
+    bindings are importable (nvidia-smi takes ~100 ms per query, longer than a whole timed region here), else nvidia-smi."""
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.stop_flag, self.thread = gpu_index, [], False, None
+        self.gpu, self.sm, self.mx, self.reasons = gpu_index, [], [], set()
+        self.stop_flag, self.thread, self.source = False, None, 'nvidia-smi'
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML indexes physical devices
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    idx = int(ids[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml, self.source = pynvml, 'nvml'
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for name, bit in (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-i',
+                              str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(',')] if out else []
+        if r and r[0].isdigit():
+            self.sm.append(int(r[0]))
+        if len(r) > 1 and r[1].isdigit():
+            self.mx.append(int(r[1]))
+        for i in range(4):
+            if len(r) >= 6 and r[2 + i].lower().startswith('active'):
+                self.reasons.add(self.NAMES[i])
 
     def _run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-i',
-                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002 if self.nvml is not None else 0.1)
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -75,12 +115,8 @@ class ClockSampler:
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=6)
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
-        return {'sm_mhz': int(statistics.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+        return {'sm_mhz': int(statistics.median(self.sm)) if self.sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -105,6 +141,28 @@ def host_candidates(mesh, n_ref, seed):
     return pts, nrm, dirs, fv
 
 
+def host_candidates_fast(mesh, n_ref, seed):
+    """the same distribution as host_candidates, vectorised over reference points (CPU timing samples only; the parity
+    tests use host_candidates / the oracle's own generator)"""
+    from oracle import leaves, port
+    rng = np.random.default_rng(seed)
+    m = port.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
+    tn = leaves.unitize(np.cross(m.triangles[:, 1] - m.triangles[:, 0], m.triangles[:, 2] - m.triangles[:, 0]))
+    pts, nrm, _ = leaves.sample_points_uniformly(m.vertices, m.faces, tn, n_ref, rng)
+    sel = rng.permutation(len(pts))
+    pts, nrm = pts[sel], nrm[sel]
+    n = len(pts)
+    az, inc = rng.uniform(0, 2 * np.pi, (n, N_RAYS)), rng.uniform(0, np.arctan(0.25), (n, N_RAYS))
+    cart = np.stack([np.sin(inc) * np.cos(az), np.sin(inc) * np.sin(az), np.cos(inc)], axis=-1)       # (n, rays, 3)
+    k = -nrm / np.linalg.norm(nrm, axis=1, keepdims=True) + np.array([0.0, 0.0, 1.0])                 # util.py:7-29
+    k[np.linalg.norm(k, axis=1) == 0] = [1.0, 0.0, 0.0]
+    kc = np.einsum('nk,nrk->nr', k, cart)
+    dirs = 2.0 * kc[..., None] * k[:, None, :] / np.einsum('nk,nk->n', k, k)[:, None, None] - cart
+    fv = rng.normal(size=(n, 3))
+    fv /= np.linalg.norm(fv, axis=1, keepdims=True)
+    return pts, nrm, np.ascontiguousarray(dirs), fv
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port, all host threads)
 # ---------------------------------------------------------------------------------------------------------------
@@ -113,7 +171,7 @@ def cpu_ags(mesh, n_ref, seed=100):
     from oracle import cport
     from burg_toolkit_b200.gripper import ParallelJawGripper
     cm = cport.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
-    pts, nrm, dirs, fv = host_candidates(mesh, n_ref, seed)
+    pts, nrm, dirs, fv = host_candidates_fast(mesh, n_ref, seed)
     gt = ParallelJawGripper().tcp_triangles()
     t0 = time.perf_counter()
     out = cport.pipeline(cm, cm, pts, dirs, fv, gt, n_orientations=N_ORIENT, coll_tol=0.01, max_hits_per_ray=16)
@@ -281,7 +339,7 @@ def run_b200(args, rank, world, local_rank):
             with open(ppath) as fh:
                 prof = json.load(fh)
         roofline = {'bound': 'hbm', 'kernel': 'traverse_kernel + cast_kernel (ray caster stage)', 'achieved': achieved, 'peak': peak_gbs,
-                    'unit': 'GB/s', 'frac': achieved / peak_gbs, 'traffic': prof.get('cast_stage', {}).get('dram_bytes_per_launch'),
+                    'unit': 'GB/s', 'frac': achieved / peak_gbs, 'traffic': prof.get('cast_stage', {}).get('dram_bytes_per_launch'), 'traffic_source': prof.get('cast_stage', {}).get('source'),
                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': cast_ms,
                     'rays_per_s': N_REF * N_RAYS / (cast_ms * 1e-3),
                     'l2_model': {'bytes_per_launch': l2_bytes, 'achieved_gbs': l2_bytes / (cast_ms * 1e-3) / 1e9,
@@ -405,7 +463,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'coverage_c2', 'coverage_c5'])
-    ap.add_argument('--cpu-ref-points', type=int, default=4000, help='reference points per CPU sample (x100 rays)')
+    ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -161,9 +161,10 @@ __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, 
 //                            coordinates: disjoint / inside-a-closed-box / undecided.  Undecided entries go to the exact queue.
 //   exact    (half warps)    two queued entries per pass: lane l of a half tests gripper triangle l of the part with FCL's
 //                            float64 17-axis test.  A hit sets out[row] and tells the lane still walking that item to stop.
-constexpr int TQ_CAP = 1024;               // task stack entries per warp
+constexpr int WU = 1;                      // tasks per lane and pass
+constexpr int TQ_CAP = 768;               // task stack entries per warp
 constexpr int CWARPS = 4;                  // warps per block
-constexpr int CQ_CAP = 96;                 // classification queue: < 32 left over + at most 64 new entries per pass
+constexpr int CQ_CAP = 32 + 64 * WU;        // classification queue: < 32 left over + at most 64 * WU new entries per pass
 constexpr int XQ_CAP = 64;                 // exact queue: <= 1 left over + 32 new entries
 
 struct LaneBox {
@@ -406,7 +407,7 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
     const int64_t total = n * n_parts;             // item = part * n + row  (part-major: neighbouring items share a region)
     const float inv_ow = 1.0f / ow;
-    const int multi_limit = TQ_CAP - (max_depth + 2) - 32;      // multi-pop passes only while nt <= multi_limit
+    const int multi_limit = TQ_CAP - (max_depth + 2) - 32 * WU; // multi-pop passes only while nt <= multi_limit
 
     DrainArgs da;
     da.gs = gs; da.tri_verts = tri_verts; da.gtris = s_gtris; da.parts = s_parts; da.out = out;
@@ -460,50 +461,67 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
             if (!exhausted) continue;              // every slot is free here, so the next refill takes 32 items
             break;
         }
-        // ---- walk: pop up to 32 tasks, test both children, push ---------------------------------------------------------
-        const int take_n = nt <= multi_limit ? min(32, nt) : 1;
-        const bool has = lane < take_n;
+        // ---- walk: pop up to 32 * WU tasks (WU per lane: independent node fetches in flight), test both children, push ---
+        const int take_n = nt <= multi_limit ? min(32 * WU, nt) : 1;
         nt -= take_n;
-        int slot = 0, l = 0, r = 0;
-        bool hl = false, hr = false;
-        if (has) {
-            const int task = tq[nt + lane];
-            slot = task >> 26;
-            if (!s_dead[w][slot]) {
-                const int node = task & 0x3ffffff;
-                if (STATS) ++st_nodes;
-                const float4 q0 = __ldg(nodes + 4 * (int64_t)node + 0);
-                const float4 q1 = __ldg(nodes + 4 * (int64_t)node + 1);
-                const float4 q2 = __ldg(nodes + 4 * (int64_t)node + 2);
+        int slot[WU], l[WU], r[WU], task[WU];
+        bool has[WU], hl[WU], hr[WU];
+        float4 q0[WU], q1[WU], q2[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            has[u] = lane + 32 * u < take_n;
+            task[u] = has[u] ? tq[nt + lane + 32 * u] : 0;
+            slot[u] = task[u] >> 26;
+            has[u] = has[u];
+            hl[u] = hr[u] = false; l[u] = r[u] = 0;
+        }
+        bool live[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            live[u] = has[u] && !s_dead[w][slot[u]];
+            if (live[u]) {
+                const int node = task[u] & 0x3ffffff;
+                q0[u] = __ldg(nodes + 4 * (int64_t)node + 0);
+                q1[u] = __ldg(nodes + 4 * (int64_t)node + 1);
+                q2[u] = __ldg(nodes + 4 * (int64_t)node + 2);
                 const float4 q3 = __ldg(nodes + 4 * (int64_t)node + 3);
+                l[u] = __float_as_int(q3.x); r[u] = __float_as_int(q3.y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            if (live[u]) {
+                if (STATS) ++st_nodes;
                 float bx[18];
 #pragma unroll
-                for (int k = 0; k < 18; ++k) bx[k] = s_box[w][k][slot];
-                hl = box_overlaps(bx, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-                hr = box_overlaps(bx, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
-                l = __float_as_int(q3.x); r = __float_as_int(q3.y);
+                for (int k = 0; k < 18; ++k) bx[k] = s_box[w][k][slot[u]];
+                hl[u] = box_overlaps(bx, q0[u].x, q0[u].y, q0[u].z, q0[u].w, q1[u].x, q1[u].y);
+                hr[u] = box_overlaps(bx, q1[u].z, q1[u].w, q2[u].x, q2[u].y, q2[u].z, q2[u].w);
             }
         }
         __syncwarp();                               // all pops are done before anything is pushed over them
-        const bool pl = hl && l >= 0, pr = hr && r >= 0, ll = hl && l < 0, lr = hr && r < 0;
-        const unsigned bl = __ballot_sync(FULL, pl), br = __ballot_sync(FULL, pr);
-        if (pl) tq[nt + __popc(bl & lt)] = l | (slot << 26);
-        nt += __popc(bl);
-        if (pr) tq[nt + __popc(br & lt)] = r | (slot << 26);
-        nt += __popc(br);
-        const unsigned cl = __ballot_sync(FULL, ll), cr = __ballot_sync(FULL, lr);
-        if (cl | cr) {
-            if (ll) { const int q = ncq + __popc(cl & lt); cq_row[q] = s_row[w][slot]; cq_leaf[q] = ~l; cq_meta[q] = s_part[w][slot] | (slot << 8); }
-            ncq += __popc(cl);
-            if (lr) { const int q = ncq + __popc(cr & lt); cq_row[q] = s_row[w][slot]; cq_leaf[q] = ~r; cq_meta[q] = s_part[w][slot] | (slot << 8); }
-            ncq += __popc(cr);
+        unsigned freed_bits = 0;
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            const bool pl = hl[u] && l[u] >= 0, pr = hr[u] && r[u] >= 0, ll = hl[u] && l[u] < 0, lr = hr[u] && r[u] < 0;
+            const unsigned bl = __ballot_sync(FULL, pl), br = __ballot_sync(FULL, pr);
+            if (pl) tq[nt + __popc(bl & lt)] = l[u] | (slot[u] << 26);
+            nt += __popc(bl);
+            if (pr) tq[nt + __popc(br & lt)] = r[u] | (slot[u] << 26);
+            nt += __popc(br);
+            const unsigned cl = __ballot_sync(FULL, ll), cr = __ballot_sync(FULL, lr);
+            if (cl | cr) {
+                if (ll) { const int q = ncq + __popc(cl & lt); cq_row[q] = s_row[w][slot[u]]; cq_leaf[q] = ~l[u]; cq_meta[q] = s_part[w][slot[u]] | (slot[u] << 8); }
+                ncq += __popc(cl);
+                if (lr) { const int q = ncq + __popc(cr & lt); cq_row[q] = s_row[w][slot[u]]; cq_leaf[q] = ~r[u]; cq_meta[q] = s_part[w][slot[u]] | (slot[u] << 8); }
+                ncq += __popc(cr);
+            }
+            if (has[u]) {
+                const int delta = (int)pl + (int)pr - 1;
+                if (atomicAdd(&s_pending[w][slot[u]], delta) + delta == 0) freed_bits |= 1u << slot[u];
+            }
         }
-        bool freed = false;
-        if (has) {
-            const int delta = (int)pl + (int)pr - 1;
-            freed = (atomicAdd(&s_pending[w][slot], delta) + delta) == 0;
-        }
-        free_mask |= __reduce_or_sync(FULL, freed ? (1u << slot) : 0u);
+        free_mask |= __reduce_or_sync(FULL, freed_bits);
         __syncwarp();
         // ---- drain the queues ---------------------------------------------------------------------------------------------
         if (nx >= 2 || ncq >= 32) {
@@ -694,14 +712,14 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
         minb = (e = getenv("BT_COLLIDE_MINB")) ? atoi(e) : 4;
     }
     BT_REQUIRE(scene->m.info.n_nodes < (1 << 26), "scene LBVH has more than 2^26 nodes");
-    BT_REQUIRE(scene->m.info.max_depth + 2 + 64 <= TQ_CAP, "scene LBVH too deep for the task stack");
+    BT_REQUIRE(scene->m.info.max_depth + 2 + 64 * WU <= TQ_CAP, "scene LBVH too deep for the task stack");
     Scratch counter;
     BT_CUDA(counter.alloc(sizeof(unsigned long long), st));
     BT_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->m.device);
     const int64_t items = n * gripper->n_parts;
-    const int per_sm = minb == 3 ? 3 : 4;
+    const int per_sm = (minb == 5 || minb == 6) ? minb : 4;
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * per_sm);   // persistent CTAs
 #define BT_COLLIDE_LAUNCH(STATS, MINB, CNT)                                                                                   \
     do {                                                                                                                      \
@@ -713,7 +731,8 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
             counter.as<unsigned long long>(), d_colliding, CNT);                                                              \
     } while (0)
     if (g_counters_host_copy) BT_COLLIDE_LAUNCH(true, 4, g_counters_host_copy);
-    else if (minb == 3) BT_COLLIDE_LAUNCH(false, 3, nullptr);
+    else if (minb == 6) BT_COLLIDE_LAUNCH(false, 6, nullptr);
+    else if (minb == 5) BT_COLLIDE_LAUNCH(false, 5, nullptr);
     else BT_COLLIDE_LAUNCH(false, 4, nullptr);
 #undef BT_COLLIDE_LAUNCH
     BT_LAUNCH_CHECK();
