@@ -122,7 +122,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # synthetic inputs
 # ---------------------------------------------------------------------------------------------------------------
-from burg_toolkit_b200.synthetic import c3_mesh, coverage_sets, perturbed_rows, random_rows  # noqa: E402,F401
+from burg_toolkit_b200.synthetic import c3_mesh, c4_scene, coverage_sets, perturbed_rows, random_rows  # noqa: E402,F401
 
 
 def host_candidates(mesh, n_ref, seed):
@@ -166,15 +166,31 @@ def host_candidates_fast(mesh, n_ref, seed):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port, all host threads)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_ags(mesh, n_ref, seed=100):
-    """one bounded CPU sample of the AGS workload -> (candidates, seconds, threads)"""
+_CPU_MESHES = {}
+
+
+def merged_scene(meshes):
+    """vertices / faces of a list of meshes concatenated into one (the CPU port's scene for config 4)"""
+    v = np.concatenate([m.vertices for m in meshes])
+    off = np.cumsum([0] + [len(m.vertices) for m in meshes[:-1]])
+    f = np.concatenate([m.triangles + o for m, o in zip(meshes, off)])
+    return v, f
+
+
+def cpu_ags(mesh, n_ref, seed=100, scene_meshes=None):
+    """one bounded CPU sample of the AGS workload -> (candidates, seconds, threads); the BVH builds are not timed"""
     from oracle import cport
     from burg_toolkit_b200.gripper import ParallelJawGripper
-    cm = cport.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
+    key = (id(mesh), id(scene_meshes))
+    if key not in _CPU_MESHES:
+        cm = cport.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
+        cs = cm if scene_meshes is None else cport.Mesh(*merged_scene(scene_meshes))
+        _CPU_MESHES[key] = (cm, cs)
+    cm, cs = _CPU_MESHES[key]
     pts, nrm, dirs, fv = host_candidates_fast(mesh, n_ref, seed)
     gt = ParallelJawGripper().tcp_triangles()
     t0 = time.perf_counter()
-    out = cport.pipeline(cm, cm, pts, dirs, fv, gt, n_orientations=N_ORIENT, coll_tol=0.01, max_hits_per_ray=16)
+    out = cport.pipeline(cm, cs, pts, dirs, fv, gt, n_orientations=N_ORIENT, coll_tol=0.01, max_hits_per_ray=16)
     dt = time.perf_counter() - t0
     return len(pts) * N_RAYS, dt, cport.num_threads(), out
 
@@ -193,21 +209,28 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count()
-    if args.workload == 'ags_c3':
-        mesh = c3_mesh()
+    if args.workload in ('ags_c3', 'ags_c4'):
+        scene_meshes = None
+        if args.workload == 'ags_c3':
+            mesh = c3_mesh()
+        else:
+            scene_meshes = c4_scene().get_mesh_list()
+            mesh = scene_meshes[1]
         n_ref = args.cpu_ref_points
         for _ in range(max(args.warmup, 0)):
-            cpu_ags(mesh, max(8, n_ref // 8))
+            cpu_ags(mesh, max(8, n_ref // 8), scene_meshes=scene_meshes)
         times, cands, threads = [], 0, 1
         for s in range(args.steps):
-            c, dt, threads, _ = cpu_ags(mesh, n_ref, seed=100 + s)
+            c, dt, threads, _ = cpu_ags(mesh, n_ref, seed=100 + s, scene_meshes=scene_meshes)
             times.append(dt)
             cands += c
         total = sum(times)
         value, unit, metric = cands / total, 'candidates/s', 'AGS candidates/sec (ray+cone+collision)'
-        sample = f'{n_ref} reference points x {N_RAYS} rays per step ({n_ref * N_RAYS} candidates) of the ags_c3 workload'
-        config = {'workload': 'ags_c3', 'mesh_triangles': len(mesh.triangles), 'ref_points_per_step': n_ref,
-                  'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1, 'collision': 'gripper-vs-object'}
+        sample = f'{n_ref} reference points x {N_RAYS} rays per step ({n_ref * N_RAYS} candidates) of the {args.workload} workload'
+        config = {'workload': args.workload, 'mesh_triangles': len(mesh.triangles), 'ref_points_per_step': n_ref,
+                  'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1,
+                  'collision': 'gripper-vs-object' if scene_meshes is None else
+                  f'gripper-vs-scene ({sum(len(m.triangles) for m in scene_meshes)} triangles)'}
     else:
         n = args.cpu_coverage_n
         times, pairs, threads = [], 0, 1
@@ -221,7 +244,7 @@ def run_reference(args, rank, world):
         config = {'workload': args.workload, 'n_ref': n, 'n_query': n}
     line = {'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(args.steps, 1), 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.workload == 'ags_c3' else 'f32',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.workload.startswith('ags') else 'f32',
             'data': 'synthetic', 'config': config,
             'cpu_baseline': {'value': value, 'unit': unit, 'cores': threads, 'kind': 'port', 'sample': sample,
                              'host_cpus': cores},
@@ -268,11 +291,27 @@ def run_b200(args, rank, world, local_rank):
 
     clocks = ClockSampler(local_rank)
     line = {}
-    if args.workload == 'ags_c3':
-        mesh = c3_mesh()
+    if args.workload in ('ags_c3', 'ags_c4'):
         ags = sampling.AntipodalGraspSampler()
-        ags.mesh, ags.gripper, ags.verbose, ags.device = mesh, ParallelJawGripper(), False, local_rank
+        ags.gripper, ags.verbose, ags.device = ParallelJawGripper(), False, local_rank
         ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
+        if args.workload == 'ags_c3':
+            mesh = c3_mesh()
+            targets, scene_meshes, pipe_kw = [mesh], None, {}
+        else:       # config 4: 20 objects + ground slab; every step samples on one object, gripper vs the WHOLE scene
+            scene_meshes = c4_scene().get_mesh_list()
+            targets = scene_meshes[1:]
+            mesh = targets[0]
+            pipe_kw = {'additional_objects': scene_meshes, 'exclude_shape': True}
+        scene_tris = sum(len(m.triangles) for m in scene_meshes) if scene_meshes else len(mesh.triangles)
+        from burg_toolkit_b200 import mesh as bmesh
+        ags.mesh = bmesh.create_icosphere(1, 0.03)               # first build in the process also loads the CUDA module
+        ags._device_mesh()
+        build_ms = []
+        for t in targets:                                       # build every target's LBVH before the timed region
+            ags.mesh = t
+            build_ms.append(ags._device_mesh().info.build_ms)
+        ags.mesh = mesh
         dm = ags._device_mesh()
         info = dm.info
         gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if (world > 1 and rank == 0) else None
@@ -281,16 +320,17 @@ def run_b200(args, rank, world, local_rank):
         stage_timer = StageTimer(local_rank)
 
         def step(seed, timer=None):
-            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer)
+            ags.mesh = targets[seed % len(targets)]
+            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer, **pipe_kw)
             if world > 1:       # the path's only exchange: compacted grasp lists + counts to rank 0 over NVLink
                 dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
                 dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
             return out
 
+        clocks.start()                                          # samples cover warm-up + timed region (all under load)
         for w in range(args.warmup):
             step(1000 * rank + w + 1)
         barrier()
-        clocks.start()
         stage_acc, step_events, stats = {}, [], []
         for s in range(args.steps):
             flush.fill_(s & 0xff)                                                    # L2 flush, outside the event pair
@@ -349,17 +389,18 @@ def run_b200(args, rank, world, local_rank):
                     'note': 'mesh+LBVH (34 MB) is L2-resident by design, so HBM is not the binding roof; see DESIGN.md section 4'}
 
         # end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+        ags.mesh = mesh
         pts, nrm, _ = [t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank)]
         pinned = {}
         for w in range(max(args.warmup, 1)):
-            ags.evaluate_host(pts, nrm, seed=w + 1, pinned=pinned)
+            ags.evaluate_host(pts, nrm, seed=w + 1, pinned=pinned, **pipe_kw)
         barrier()
         e2e_events, h2d, d2h = [], 0, 0
         for s in range(args.steps):
             flush.fill_(s & 0xff)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            res = ags.evaluate_host(pts, nrm, seed=s + 11, pinned=pinned)
+            res = ags.evaluate_host(pts, nrm, seed=s + 11, pinned=pinned, **pipe_kw)
             e1.record()
             e2e_events.append((e0, e1))
             h2d, d2h = res['h2d_bytes'], res['d2h_bytes']
@@ -369,24 +410,29 @@ def run_b200(args, rank, world, local_rank):
 
         line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
                 'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
-                'config': {'workload': 'ags_c3', 'mesh': 'bumpy sphere 224x224 (YCB-like, seed 1)',
-                           'mesh_triangles': int(info.n_triangles), 'ref_points_per_step_per_gpu': N_REF, 'n_rays': N_RAYS,
+                'config': {'workload': args.workload,
+                           'mesh': 'bumpy sphere 224x224 (YCB-like, seed 1)' if scene_meshes is None else
+                                   '20 bumpy objects (158x158 grids, seeds 10-29) on a 1.0 x 0.5 m ground slab; target object changes every step',
+                           'mesh_triangles': int(info.n_triangles), 'scene_triangles': int(scene_tris),
+                           'ref_points_per_step_per_gpu': N_REF, 'n_rays': N_RAYS,
                            'candidates_per_step_per_gpu': N_REF * N_RAYS, 'n_orientations': N_ORIENT,
-                           'max_targets_per_ref_point': 1, 'collision': 'gripper-vs-object, use_width, tol 0.01',
+                           'max_targets_per_ref_point': 1,
+                           'collision': ('gripper-vs-object' if scene_meshes is None else 'gripper-vs-scene') + ', use_width, tol 0.01',
                            'mode': 'reference mode (one pair per reference point)', 'l2': 'flushed between steps (256 MB write)',
-                           'bvh_build_ms': info.build_ms, 'bvh_max_depth': int(info.max_depth),
+                           'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
                            'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow},
                 'roofline': roofline, 'stage_ms': stage_ms,
                 'e2e': {'value': e2e_value, 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_ms / args.steps},
                 'gpu_launches': len(AGS_KERNELS) * args.steps, 'kernels': AGS_KERNELS}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            c, dt, threads, _ = cpu_ags(mesh, args.cpu_ref_points)
+            c, dt, threads, _ = cpu_ags(mesh, args.cpu_ref_points, scene_meshes=scene_meshes)
             line['cpu_baseline'] = {'value': c / dt, 'unit': 'candidates/s', 'cores': threads, 'kind': 'port',
                                     'sample': f'{args.cpu_ref_points} reference points x {N_RAYS} rays ({c} candidates) of the same '
                                               f'workload, oracle/coracle.c with OpenMP, {dt:.1f} s', 'host_cpus': os.cpu_count()}
             # secondary metric of BASELINE.json: coverage pairs/s (config 2), same JSON line
-            line['secondary'] = coverage_numbers(args, torch, metrics, flush, barrier, short=True)
+            if args.workload == 'ags_c3':
+                line['secondary'] = coverage_numbers(args, torch, metrics, flush, barrier, short=True)
     else:
         line = coverage_numbers(args, torch, metrics, flush, barrier, short=False, clocks=clocks)
         clk = line.pop('clocks')
@@ -438,18 +484,34 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
         ev.append((e0, e1))
     barrier()
     e2e_ms = statistics.mean(event_ms(ev))
-    # FP32-issue roofline of the tiles kernel: 4 lane-ops per rejected pair (3 FFMA + 1 compare), SURVEY.md 8d
+    # FP32-issue roofline: 4 lane-ops per tested pair (3 FFMA + 1 compare).  The all-pairs kernel tests
+    # every pair; the grid kernels test only the pairs of the 27 neighbouring cells, counted here on the host.
     lane_ops = 148 * 128 * 1.965e9
+    if 'tiles' in res:
+        roof_kernel, tested, roof_ms = 'coverage_tiles_kernel', pairs, res['tiles']['ms']
+    else:
+        cell = 1.01 * 15.0 / 1000.0
+        lo = np.minimum(ref[:, :3].min(0), qry[:, :3].min(0))
+        cr, cq = np.floor((ref[:, :3] - lo) / cell).astype(np.int64), np.floor((qry[:, :3] - lo) / cell).astype(np.int64)
+        dims = np.maximum(cr.max(0), cq.max(0)) + 3
+        occ = np.zeros(tuple(dims), dtype=np.int64)
+        np.add.at(occ, tuple((cq + 1).T), 1)
+        nb = sum(np.roll(occ, (dx, dy, dz), axis=(0, 1, 2)) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1))
+        tested = float(nb[tuple((cr + 1).T)].sum())
+        roof_kernel, roof_ms = 'coverage_cells_kernel / coverage_grid_kernel (27-cell neighbourhood)', res['grid']['ms']
+    achieved_ops = tested * 4 / (roof_ms * 1e-3)
     out = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
            'ms_per_step': res['grid']['ms'],
-           'config': {'workload': args.workload if args.workload != 'ags_c3' else 'coverage_c2', 'n_ref': len(ref), 'n_query': len(qry), 'epsilon': 15.0,
+           'config': {'workload': args.workload if not args.workload.startswith('ags') else 'coverage_c2', 'n_ref': len(ref), 'n_query': len(qry), 'epsilon': 15.0,
                       'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
                       'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
                       'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
            'tiles_all_pairs': res.get('tiles'),
-           'roofline': {'bound': 'fp32-issue', 'kernel': 'coverage_tiles_kernel', 'achieved': res.get('tiles', res['grid'])['pairs_per_s'] * 4 / 1e12,
-                        'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': res.get('tiles', res['grid'])['pairs_per_s'] * 4 / lane_ops,
-                        'traffic': None, 'note': '4 FP32 lane-ops per pair (3 FFMA + 1 compare); HBM bytes are negligible (10 MB)'},
+           'roofline': {'bound': 'fp32-issue', 'kernel': roof_kernel, 'achieved': achieved_ops / 1e12,
+                        'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': achieved_ops / lane_ops,
+                        'pairs_tested_per_launch': tested, 'traffic': None,
+                        'note': '4 FP32 lane-ops per tested pair (3 FFMA + 1 compare); value counts nominal N*M pairs, the roofline '
+                                'counts the pairs the kernel actually tests; HBM bytes are negligible'},
            'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes),
                    'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac},
            'gpu_launches': 8 * steps, 'clocks': clk}
@@ -462,7 +524,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'coverage_c2', 'coverage_c5'])
+    ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'ags_c4', 'coverage_c2', 'coverage_c5'])
     ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')

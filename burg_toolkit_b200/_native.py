@@ -97,6 +97,7 @@ _SIGNATURES = {
                                   C.c_uint64, _P, _P]),
     'bt_coverage': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     'bt_avg_gripper_point_distances': (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P]),
+    'bt_mesh_pair_collide': (C.c_int, [_P, _P, _P, _P]),
     'bt_random_poses': (C.c_int, [C.c_int64, C.c_uint64, _P, _P]),
     'bt_grasp_perturbations': (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P]),
     'bt_farthest_point_sampling': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),

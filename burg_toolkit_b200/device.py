@@ -80,6 +80,7 @@ def _destroy(fn, handle):
 
 
 _mesh_cache = {}
+MESH_CACHE_SIZE = 256
 
 
 def cached_device_mesh(mesh, device=None):
@@ -89,12 +90,13 @@ def cached_device_mesh(mesh, device=None):
     m = as_mesh(mesh)
     key = (id(mesh), dev)
     tag = (len(m.vertices), len(m.triangles), float(np.asarray(m.vertices).sum()))
-    hit = _mesh_cache.get(key)
+    hit = _mesh_cache.pop(key, None)
     if hit is not None and hit[0] == tag:
+        _mesh_cache[key] = hit                       # most recently used last
         return hit[1]
     dm = DeviceMesh(m.vertices, m.triangles, m.vertex_normals, dev)
     _mesh_cache[key] = (tag, dm)
-    if len(_mesh_cache) > 16:
+    if len(_mesh_cache) > MESH_CACHE_SIZE:           # least recently used first (a cluttered scene has tens of objects)
         _mesh_cache.pop(next(iter(_mesh_cache)))
     return dm
 

@@ -612,3 +612,48 @@ def farthest_point_sampling(point_cloud, k, device=None):
             nat.call('bt_farthest_point_sampling', nat.ptr(pts), 1 if pts.dtype == torch.float64 else 0, pts.shape[1],
                      pts.shape[0], int(k), nat.ptr(out), nat.current_stream())
         return out.cpu().numpy()
+
+
+def sample_scene(object_library, ground_area, instances_per_scene, instances_per_object=1, max_tries=20, rng=None,
+                 device=None):
+    """Samples a physically plausible scene from the objects of ``object_library`` (reference sampling.py:498-569):
+    every object gets a random rotation about z, one of its stable poses and a random xy offset that keeps its bounding
+    box on the ground area; a placement is kept if the new object's mesh does not collide with the meshes already
+    placed (``bt_mesh_pair_collide`` instead of a trimesh CollisionManager), otherwise it is retried up to ``max_tries``
+    times.  ``rng``: optional ``np.random.Generator`` for reproducible scenes (the reference is unseeded)."""
+    import logging
+    from scipy.spatial.transform import Rotation as R
+    from . import core, mesh_processing
+    scene = core.Scene(ground_area=ground_area)
+    rng = np.random.default_rng() if rng is None else rng
+    population = [obj_type for obj_type in object_library.values() for _ in range(instances_per_object)]
+    obj_types = rng.choice(np.array(population, dtype=object), instances_per_scene, replace=False)
+    placed = []                                     # posed meshes already in the scene (mutually collision-free)
+    for object_type in obj_types:
+        success = False
+        for _ in range(max_tries):
+            angle = rng.random() * np.pi * 2
+            tf_rot = np.eye(4)
+            tf_rot[:3, :3] = R.from_rotvec(angle * np.array([0, 0, 1])).as_matrix()
+            pose = tf_rot @ object_type.stable_poses.sample_pose(uniformly=True, rng=rng)
+            instance = core.ObjectInstance(object_type, pose)
+            m = instance.get_mesh()
+            min_x, min_y, _ = m.get_min_bound()
+            max_x, max_y, _ = m.get_max_bound()
+            range_x, range_y = ground_area[0] - (max_x - min_x), ground_area[1] - (max_y - min_y)
+            if range_x < 0 or range_y < 0:
+                continue                            # the ground area is too small for this object
+            x, y = rng.random() * range_x - min_x, rng.random() * range_y - min_y
+            instance.pose[0, 3] = x + pose[0, 3]
+            instance.pose[1, 3] = y + pose[1, 3]
+            candidate = instance.get_mesh()
+            # the meshes already placed do not collide with each other, so only pairs with the new mesh can
+            if not any(len(placed) in pair for pair in mesh_processing.collisions(placed + [candidate], device=device)):
+                scene.objects.append(instance)
+                placed.append(candidate)
+                success = True
+                break
+        if not success:
+            logging.warning(f'Could not add object to scene, exceeded number of max_tries ({max_tries}). Returning '
+                            f'scene with fewer object instances than requested.')
+    return scene

@@ -37,7 +37,7 @@ def c4_scene(n_objects=20, grid=158, ground=(1.0, 0.5), seed=7):
         pose = np.eye(4)
         pose[:2, :2] = [[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]
         pose[:3, 3] = [xy[0], xy[1], -float(m.vertices[:, 2].min())]
-        instances.append(ObjectInstance(ObjectType(f'bumpy_{k}', m), pose))
+        instances.append(ObjectInstance(ObjectType(f'bumpy_{k}', mesh=m), pose))
     return Scene(ground_area=ground, objects=instances)
 
 

@@ -65,3 +65,54 @@ def tf_from_xyz_pos(x_axis, y_axis, z_axis, position=None):
     tf[:, :3, 2] = z_axis
     tf[:, :3, 3] = position
     return tf.reshape(4, 4) if n == 1 else tf
+
+
+# trimesh.ray.ray_util.contains_points: the fixed first ray direction
+_CONTAINS_DIRECTION = np.array([0.4395064455, 0.617598629942, 0.652231566745])
+
+
+def mesh_contains_points(mesh, points, device=None, rng=None):
+    """The rows of ``points`` ((n, k >= 3), xyz first) that lie inside ``mesh`` (reference util.py:268-292, which
+    calls trimesh's ``RayMeshIntersector.contains_points``): a ray is cast forwards and backwards from every point inside
+    the mesh's bounding box; a point is inside if both directions cross the surface an odd number of times, outside if
+    both counts are even -- or if they disagree and one of them is zero; the remaining ('broken') points are decided by
+    one more pair of rays in a random direction.  The rays are cast on the device (``bt_ags_cast``, two rays per point).
+    Like the reference: undefined for points that lie on a triangle."""
+    from . import _native as nat
+    from .mesh import as_mesh
+    from .sampling import AntipodalGraspSampler
+    nat.require_cuda()
+    m = as_mesh(mesh)
+    points = np.asarray(points)
+    xyz = np.ascontiguousarray(points[:, 0:3], dtype=np.float64)
+    ags = AntipodalGraspSampler()
+    ags.mesh, ags.device, ags.verbose = m, device, False
+
+    def parity(p, direction):
+        dirs = np.broadcast_to(np.stack([direction, -direction]), (len(p), 2, 3))
+        hit_count = ags.cast(p, np.ascontiguousarray(dirs)).hit_count.cpu().numpy().reshape(len(p), 2)
+        return hit_count
+
+    def contains(p, direction, recurse):
+        out = np.zeros(len(p), dtype=bool)
+        lo, hi = np.asarray(m.vertices).min(axis=0), np.asarray(m.vertices).max(axis=0)
+        inside_aabb = ((p > lo) & (p < hi)).all(axis=1)                 # trimesh.bounds.contains: strict
+        if not inside_aabb.any():
+            return out
+        q = p[inside_aabb]
+        hits = parity(q, direction)
+        odd = (hits % 2) == 1
+        agree = odd[:, 0] == odd[:, 1]
+        res = np.zeros(len(q), dtype=bool)
+        res[agree] = odd[agree, 0]
+        one_freespace = (hits == 0).any(axis=1)
+        broken = ~agree & ~one_freespace
+        if broken.any() and recurse:
+            g = np.random if rng is None else rng
+            new_direction = g.random(3) - 0.5
+            new_direction = new_direction / np.linalg.norm(new_direction)
+            res[broken] = contains(q[broken], new_direction, False)
+        out[inside_aabb] = res
+        return out
+
+    return points[contains(xyz, _CONTAINS_DIRECTION, True)]

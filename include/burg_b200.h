@@ -184,6 +184,13 @@ BT_API int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const flo
                const int64_t* d_n, double opening_width, double width_tolerance, int32_t use_width,
                uint8_t* d_colliding, void* stream);
 
+/* ---- mesh-vs-mesh collision (replaces mesh_processing.collisions, mesh_processing.py:266-281, the
+ * pair test behind Scene.colliding_instances core.py:666-687 and sampling.sample_scene sampling.py:498-569 ->
+ * trimesh CollisionManager.in_collision_internal -> FCL).  Both meshes are in world coordinates.  d_flag[0] (i32, device)
+ * becomes 1 iff some triangle of `a` intersects some triangle of `b` (FCL's 17-axis test with a's triangle in the P role;
+ * touching counts, containment does not), else 0.  Only enqueues work on `stream`. */
+BT_API int bt_mesh_pair_collide(const bt_mesh* a, const bt_mesh* b, int32_t* d_flag, void* stream);
+
 /* ---- stream compaction of the surviving grasps: keeps rows with mask[i] == keep_value.
  *   d_out_gs [n,14], d_out_contacts [n,2,3] (may be NULL with d_contacts), d_n_out [1] i64 */
 BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,

@@ -180,6 +180,48 @@ class RayMeshIntersector:
         tri, ray, loc, t = canonical_unique(tri, ray, loc, t)
         return loc, ray, tri
 
+    def contains_points(self, points):
+        """Restated ``trimesh.ray.ray_util.contains_points`` (called by util.py:290)."""
+        return contains_points(self, points)
+
+
+CONTAINS_DIRECTION = np.array([0.4395064455, 0.617598629942, 0.652231566745])     # trimesh's fixed first direction
+
+
+def contains_points(intersector, points, check_direction=None):
+    """trimesh ``ray_util.contains_points``: points outside the (strict) bounding box are outside; for the others a ray
+    is cast forwards and backwards; odd/odd -> inside, even/even -> outside, disagreement with one side at zero hits ->
+    outside ('a very solid indicator we are in free space'); the rest is re-tested ONCE with a random direction
+    (``unitize(np.random.random(3) - .5)``, global numpy RNG like upstream)."""
+    points = np.asanyarray(points, dtype=np.float64)
+    bounds = intersector.mesh.bounds
+    inside_aabb = (points > bounds[0]).all(axis=1) & (points < bounds[1]).all(axis=1)
+    contains = np.zeros(len(points), dtype=bool)
+    if not inside_aabb.any():
+        return contains
+    direction = CONTAINS_DIRECTION if check_direction is None else check_direction
+    q = points[inside_aabb]
+    ray_directions = np.tile(direction, (len(q), 1))
+    _, index_ray, _ = intersector.intersects_location(np.vstack((q, q)), np.vstack((ray_directions, -ray_directions)))
+    if len(index_ray) == 0:
+        return contains
+    hits = np.bincount(index_ray, minlength=len(q) * 2).reshape((2, -1))
+    odd = np.mod(hits, 2) == 1
+    agree = np.equal(*odd)
+    mask = inside_aabb.copy()
+    mask[mask] = agree
+    contains[mask] = odd[0][agree]
+    one_freespace = (hits == 0).any(axis=0)
+    broken = np.logical_and(np.logical_not(agree), np.logical_not(one_freespace))
+    if not broken.any():
+        return contains
+    if check_direction is None:
+        new_direction = unitize(np.random.random(3) - .5)
+        mask = inside_aabb.copy()
+        mask[mask] = broken
+        contains[mask] = contains_points(intersector, q[broken], check_direction=new_direction)
+    return contains
+
 
 # ---------------------------------------------------------------------------------------------
 # FCL triangle-triangle test and the CollisionManager facade
@@ -277,6 +319,20 @@ class CollisionManager:
         if transform is not None:
             tris = transform_points(tris, np.asarray(transform, dtype=np.float64))
         return any(meshes_collide(tris, scene) for scene in self._objects.values())
+
+    def in_collision_internal(self, return_names=False, return_data=False):
+        """any pair of the managed objects in collision (mesh_processing.py:279, sampling.py:551); with
+        ``return_names`` also the set of colliding pairs, each a tuple of the two NAMES sorted alphabetically (trimesh:
+        ``tuple(sorted((name1, name2)))``).  FCL's P role goes to the object added first."""
+        names = list(self._objects)
+        pairs = set()
+        for a in range(len(names)):
+            for b in range(a + 1, len(names)):
+                if meshes_collide(self._objects[names[b]], self._objects[names[a]]):
+                    pairs.add(tuple(sorted((names[a], names[b]))))
+        if return_names:
+            return len(pairs) > 0, pairs
+        return len(pairs) > 0
 
 
 # ---------------------------------------------------------------------------------------------

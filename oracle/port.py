@@ -474,3 +474,33 @@ def farthest_point_sampling(point_cloud, k):
         dist = np.minimum(dist, cur)
         idx[i] = np.argmax(dist)
     return idx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scene composition
+# ---------------------------------------------------------------------------------------------------------------
+def collisions(mesh_triangles):
+    """mesh_processing.py:266-281 for a list of (F_i, 3, 3) world-frame triangle arrays -> sorted list of index pairs,
+    each ordered like the reference orders it (by the decimal STRINGS of the two indices)."""
+    out = []
+    for i in range(len(mesh_triangles)):
+        for j in range(i + 1, len(mesh_triangles)):
+            if leaves.meshes_collide(np.asarray(mesh_triangles[j], dtype=np.float64), np.asarray(mesh_triangles[i], dtype=np.float64)):
+                out.append(tuple(int(s) for s in sorted((str(i), str(j)))))
+    return sorted(out)
+
+
+def colliding_instances(pairs, n_objects):
+    """core.py:680-687: indices < n_objects that occur in a colliding pair, in order of first occurrence"""
+    out = []
+    for i1, i2 in pairs:
+        for i in (i1, i2):
+            if i <= n_objects - 1 and i not in out:
+                out.append(i)
+    return out
+
+
+def contains_points(mesh, points, check_direction=None):
+    """util.py:268-292 -> trimesh contains_points (first pass is deterministic; broken points use np.random)"""
+    tm = leaves.Trimesh(mesh.vertices, mesh.faces)
+    return leaves.contains_points(leaves.RayMeshIntersector(tm), np.asarray(points, dtype=np.float64)[:, :3], check_direction)

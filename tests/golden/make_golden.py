@@ -19,6 +19,8 @@ Outputs (tests/golden/):
                       max_targets_per_ref_point=3 and only_grasp_from_above in a second pass
   generators.npz      grasp_perturbations (default radii / one custom radius) and farthest_point_sampling (f64 / f32)
   collisions.npz      check_collisions of the icosphere / screwdriver grasps (shape only, + plane)
+  scene.npz           mesh_processing.collisions on 13 posed meshes (colliding pairs, colliding instances) and
+                      util.mesh_contains_points on an icosphere / the bumpy shape
 """
 import os
 import sys
@@ -284,7 +286,72 @@ def make_generators():
     print('generators:', p_default._gs_array.shape, p_custom._gs_array.shape)
 
 
+def scene_meshes():
+    """13 posed meshes: overlapping / touching-free / nested / far-apart icospheres and boxes, more than ten so that the
+    reference's alphabetical ordering of the pair names ('10' < '2') shows in the fixture"""
+    def ico(sub, r, c):
+        m = bmesh.create_icosphere(sub, r)
+        m.translate(c)
+        return m
+    def box(w, h, d, c, rotz=0.0):
+        m = bmesh.create_box(w, h, d)
+        tf = np.eye(4)
+        tf[:3, :3] = Rotation.from_euler('z', rotz).as_matrix()
+        tf[:3, 3] = c
+        m.transform(tf)
+        return m
+    return [ico(2, 0.03, [0, 0, 0]),                 # 0
+            ico(2, 0.03, [0.05, 0, 0]),              # 1 overlaps 0
+            ico(1, 0.01, [0, 0, 0]),                 # 2 nested in 0: containment is not a collision
+            ico(2, 0.03, [0.2, 0.2, 0]),             # 3 far away
+            box(0.04, 0.04, 0.04, [0.2, 0.2, 0.0]),  # 4 its corners poke out of sphere 3
+            box(0.1, 0.1, 0.002, [0.3, 0, 0]),       # 5 thin plate
+            ico(2, 0.02, [0.34, 0.03, 0.0195]),      # 6 dips into the plate's top face
+            ico(2, 0.02, [0.37, -0.04, 0.0225]),     # 7 hovers 0.5 mm above the plate
+            box(0.02, 0.02, 0.02, [0.5, 0.5, 0.5]),  # 8 alone
+            ico(3, 0.03, [0.6, 0, 0]),               # 9
+            ico(3, 0.03, [0.63, 0.01, 0]),           # 10 overlaps 9
+            box(0.05, 0.01, 0.01, [0.05, 0.0, 0.03], 0.4),   # 11 bar through the tops of 0 and 1
+            ico(1, 0.005, [0.6, 0, 0])]              # 12 nested in 9
+
+
+def make_scene():
+    meshes = scene_meshes()
+    ref_meshes = [harness.o3d_mesh(m.vertices, m.triangles) for m in meshes]
+    pairs = ns.mesh_processing.collisions(ref_meshes)
+    # Scene.colliding_instances (core.py:666-687) with the last three meshes as background objects
+    n_obj = len(meshes) - 3
+    colliding = []
+    for i1, i2 in sorted(pairs):
+        for i in (i1, i2):
+            if i <= n_obj - 1 and i not in colliding:
+                colliding.append(i)
+    # util.mesh_contains_points on two shapes
+    rng = np.random.default_rng(77)
+    ico = bmesh.create_icosphere(3, 0.03)
+    bumpy = bmesh.create_bumpy_sphere(24, 24, radius=0.035, amplitude=0.15, seed=1)
+    pts_ico = np.concatenate([rng.uniform(-0.04, 0.04, (3000, 3)), rng.normal(size=(3000, 2))], axis=1)
+    pts_bumpy = rng.uniform(-0.05, 0.05, (3000, 3))
+    np.random.seed(5)                                   # the 'broken' branch draws its second direction from np.random
+    in_ico = ns.util.mesh_contains_points(harness.o3d_mesh(ico.vertices, ico.triangles), pts_ico)
+    np.random.seed(5)
+    in_bumpy = ns.util.mesh_contains_points(harness.o3d_mesh(bumpy.vertices, bumpy.triangles), pts_bumpy)
+    mv, mv_off = ragged([m.vertices for m in meshes])
+    mt, mt_off = ragged([m.triangles for m in meshes], np.int32)
+    np.savez_compressed(os.path.join(HERE, 'scene.npz'),
+                        mesh_vertices=mv, mesh_vertices_off=mv_off, mesh_triangles=mt, mesh_triangles_off=mt_off,
+                        pairs=np.array(sorted(pairs), dtype=np.int64).reshape(-1, 2), n_objects=n_obj,
+                        colliding_instances=np.array(colliding, dtype=np.int64),
+                        ico_vertices=ico.vertices, ico_triangles=ico.triangles, pts_ico=pts_ico, in_ico=in_ico,
+                        bumpy_vertices=bumpy.vertices, bumpy_triangles=bumpy.triangles, pts_bumpy=pts_bumpy, in_bumpy=in_bumpy)
+    print('scene: pairs', sorted(pairs), 'colliding instances', colliding, 'inside', len(in_ico), len(in_bumpy))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'scene':
+        make_scene()
+        sys.exit(0)
+    make_scene()
     make_generators()
     make_known_answers()
     make_metrics()

@@ -85,7 +85,7 @@ def test_scene_mesh_list():
     ico = bmesh.create_icosphere(1, 0.02)
     pose = np.eye(4)
     pose[:3, 3] = [0.1, 0.2, 0.02]
-    scene = Scene(ground_area=(0.4, 0.3), objects=[ObjectInstance(ObjectType('ball', ico), pose)])
+    scene = Scene(ground_area=(0.4, 0.3), objects=[ObjectInstance(ObjectType('ball', mesh=ico), pose)])
     meshes = scene.get_mesh_list()
     assert len(meshes) == 2 and len(meshes[0].triangles) == 12
     assert np.allclose(meshes[0].get_min_bound(), [0, 0, -0.001]) and np.allclose(meshes[0].get_max_bound(), [0.4, 0.3, 0])
