@@ -187,6 +187,7 @@ def cpu_ags(mesh, n_ref, seed=100, scene_meshes=None):
         cs = cm if scene_meshes is None else cport.Mesh(*merged_scene(scene_meshes))
         _CPU_MESHES[key] = (cm, cs)
     cm, cs = _CPU_MESHES[key]
+    cport.set_num_threads(os.cpu_count() or 1)            # all host threads, also under torchrun (OMP_NUM_THREADS=1 there)
     pts, nrm, dirs, fv = host_candidates_fast(mesh, n_ref, seed)
     gt = ParallelJawGripper().tcp_triangles()
     t0 = time.perf_counter()
@@ -434,14 +435,16 @@ def run_b200(args, rank, world, local_rank):
             if args.workload == 'ags_c3':
                 line['secondary'] = coverage_numbers(args, torch, metrics, flush, barrier, short=True)
     else:
-        line = coverage_numbers(args, torch, metrics, flush, barrier, short=False, clocks=clocks)
+        line = coverage_numbers(args, torch, metrics, flush, barrier, short=False, clocks=clocks, rank=rank, world=world,
+                                dist=dist if world > 1 else None)
         clk = line.pop('clocks')
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             p, dt, threads, cov = cpu_coverage(args.cpu_coverage_n)
             line['cpu_baseline'] = {'value': p / dt, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                                     'sample': f'{args.cpu_coverage_n} x {args.cpu_coverage_n} grasps, kd-tree coverage '
                                               f'(scipy cKDTree + Python loop as metrics.py:161-229), {dt:.1f} s'}
-    line.update({'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak',
+    line.update({'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True,
+                 'scaling': 'weak' if args.workload.startswith('ags') else 'strong',
                  'vs_baseline': None, 'data': 'synthetic', 'clocks': clk})
     if rank == 0:
         print(json.dumps(line))
@@ -449,12 +452,24 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
-    """coverage 100k x 100k (perturbed pair, eps 15): device-resident pairs/s and e2e (host rows in, fraction out)"""
+def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None, rank=0, world=1, dist=None):
+    """coverage (perturbed pair, eps 15): device-resident pairs/s and e2e (host rows in, fraction out).  With several
+    ranks the REFERENCE rows are sharded (query set replicated, one all-reduce of the covered count inside the step):
+    the total work is fixed, i.e. strong scaling."""
     n_cov = 1_000_000 if args.workload == 'coverage_c5' else COV_N
-    ref, qry = coverage_sets(n_cov)
+    ref_all, qry = coverage_sets(n_cov)
+    pairs = float(len(ref_all)) * float(len(qry))
+    from burg_toolkit_b200.distributed import shard_range
+    b, e = shard_range(len(ref_all), rank, world)
+    ref = ref_all[b:e]
     dref, dqry = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
-    pairs = float(len(ref)) * float(len(qry))
+
+    def reduce_max(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     res = {}
     steps = max(3, args.steps // 2) if short else args.steps
     for algo in (('grid',) if n_cov > 200_000 else ('grid', 'tiles')):
@@ -469,21 +484,27 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _, count = metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
+            if world > 1:
+                dist.all_reduce(count, op=dist.ReduceOp.SUM)           # the path's only exchange: one int64 per rank
             e1.record()
             ev.append((e0, e1))
         barrier()
-        ms = statistics.mean(event_ms(ev))
-        res[algo] = {'ms': ms, 'pairs_per_s': pairs / (ms * 1e-3), 'coverage': int(count.item()) / len(ref)}
+        ms = reduce_max(statistics.mean(event_ms(ev)))
+        res[algo] = {'ms': ms, 'pairs_per_s': pairs / (ms * 1e-3), 'coverage': int(count.item()) / len(ref_all)}
     clk = clocks.stop() if clocks is not None else None
     ev = []
     for s in range(steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         frac = metrics.coverage(ref, qry)                       # host rows in (pageable), python float out
+        if world > 1:
+            t = torch.tensor([frac * len(ref)], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            frac = float(t.item()) / len(ref_all)
         e1.record()
         ev.append((e0, e1))
     barrier()
-    e2e_ms = statistics.mean(event_ms(ev))
+    e2e_ms = reduce_max(statistics.mean(event_ms(ev)))
     # FP32-issue roofline: 4 lane-ops per tested pair (3 FFMA + 1 compare).  The all-pairs kernel tests
     # every pair; the grid kernels test only the pairs of the 27 neighbouring cells, counted here on the host.
     lane_ops = 148 * 128 * 1.965e9
@@ -491,18 +512,19 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
         roof_kernel, tested, roof_ms = 'coverage_tiles_kernel', pairs, res['tiles']['ms']
     else:
         cell = 1.01 * 15.0 / 1000.0
-        lo = np.minimum(ref[:, :3].min(0), qry[:, :3].min(0))
-        cr, cq = np.floor((ref[:, :3] - lo) / cell).astype(np.int64), np.floor((qry[:, :3] - lo) / cell).astype(np.int64)
+        lo = np.minimum(ref_all[:, :3].min(0), qry[:, :3].min(0))
+        cr, cq = np.floor((ref_all[:, :3] - lo) / cell).astype(np.int64), np.floor((qry[:, :3] - lo) / cell).astype(np.int64)
         dims = np.maximum(cr.max(0), cq.max(0)) + 3
         occ = np.zeros(tuple(dims), dtype=np.int64)
         np.add.at(occ, tuple((cq + 1).T), 1)
         nb = sum(np.roll(occ, (dx, dy, dz), axis=(0, 1, 2)) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1))
         tested = float(nb[tuple((cr + 1).T)].sum())
         roof_kernel, roof_ms = 'coverage_cells_kernel / coverage_grid_kernel (27-cell neighbourhood)', res['grid']['ms']
-    achieved_ops = tested * 4 / (roof_ms * 1e-3)
+    achieved_ops = tested / world * 4 / (roof_ms * 1e-3)            # per GPU (every rank tests 1/world of the pairs)
     out = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
            'ms_per_step': res['grid']['ms'],
-           'config': {'workload': args.workload if not args.workload.startswith('ags') else 'coverage_c2', 'n_ref': len(ref), 'n_query': len(qry), 'epsilon': 15.0,
+           'config': {'workload': args.workload if not args.workload.startswith('ags') else 'coverage_c2', 'n_ref': len(ref_all), 'n_query': len(qry), 'epsilon': 15.0,
+                      'sharding': f'reference rows split over {world} rank(s), query set replicated, all-reduce of the covered count',
                       'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
                       'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
                       'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
@@ -512,7 +534,7 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None):
                         'pairs_tested_per_launch': tested, 'traffic': None,
                         'note': '4 FP32 lane-ops per tested pair (3 FFMA + 1 compare); value counts nominal N*M pairs, the roofline '
                                 'counts the pairs the kernel actually tests; HBM bytes are negligible'},
-           'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes),
+           'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes) * world,
                    'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac},
            'gpu_launches': 8 * steps, 'clocks': clk}
     return out

@@ -143,6 +143,15 @@ void co_mesh_free(CoMesh *m) {
     free(m->V); free(m->VN); free(m->F); free(m->fn); free(m->order); free(m->nodes); free(m);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the benchmark's CPU arm asks for all host threads explicitly */
+void co_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int co_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

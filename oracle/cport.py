@@ -36,6 +36,7 @@ def lib():
         l.co_mesh_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         l.co_mesh_free.argtypes = [C.c_void_p]
         l.co_num_threads.restype = C.c_int
+        l.co_set_num_threads.argtypes = [C.c_int]
         l.co_ags_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(Params),
                                   C.c_void_p, C.c_void_p]
         l.co_collide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
@@ -50,6 +51,11 @@ def lib():
 
 def num_threads():
     return lib().co_num_threads()
+
+
+def set_num_threads(n):
+    """OpenMP threads of the following calls (torchrun exports OMP_NUM_THREADS=1 to its ranks)"""
+    lib().co_set_num_threads(int(n))
 
 
 class Mesh:
