@@ -16,12 +16,14 @@
 namespace bt {
 
 constexpr int STACK_SIZE = 64;
+constexpr int WIDE_STACK = 96;             // 4-wide walk: up to 3 parked children per wide level, depth <= 60 binary levels
 constexpr float T_BEHIND = -1e-5f;        // boxes wholly behind the origin by more than this cannot hold a
                                           // hit that passes the reference's forward test (> -1e-6)
 
 struct MeshView {
     const float4* __restrict__ nodes;
     const uint4* __restrict__ qnodes;
+    const uint4* __restrict__ wnodes;
     double gmin[3], gscale[3];
     const double* __restrict__ tri_rec;
     const float4* __restrict__ tri_f32;
@@ -157,7 +159,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     const int DONE = (int)0x80000000;                 // never a leaf code: leaf codes are ~index with index < 2^30
     int64_t ray = -1;
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
-    int stack[STACK_SIZE];
+    int stack[WIDE_STACK];
     int sp = 0, cur = DONE, n_cand = 0;
     bool active = false;
 
@@ -192,21 +194,28 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
             if (next >= slice_len) break;
             continue;
         }
-        // ---- a short burst of node steps for the lanes that stand on an internal node ---------------------------------
+        // ---- a short burst of node steps for the lanes that stand on an internal (4-wide) node ---------------------------
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 3; ++k) {
             if (cur >= 0) {
                 if (STATS) ++st_nodes;
-                const uint4 A = __ldg(mv.qnodes + 2 * (int64_t)cur);            // 32-byte node: 2 x LDG.128
-                const uint4 B = __ldg(mv.qnodes + 2 * (int64_t)cur + 1);
-                const bool hl = slab_hit(m16lo(A.x), m16hi(A.x), m16lo(A.y), m16hi(A.y), m16lo(A.z), m16hi(A.z), idx, idy, idz, oox, ooy, ooz);
-                const bool hr = slab_hit(m16lo(A.w), m16hi(A.w), m16lo(B.x), m16hi(B.x), m16lo(B.y), m16hi(B.y), idx, idy, idz, oox, ooy, ooz);
-                const int l = (int)B.z, r = (int)B.w;
-                if (hl && hr) { stack[sp++] = r; cur = l; }
-                else if (hl) cur = l;
-                else if (hr) cur = r;
-                else if (sp > 0) cur = stack[--sp];
-                else cur = DONE;                                    // walk finished
+                const uint4* np = mv.wnodes + 4 * (int64_t)cur;                 // 64-byte node: 4 x LDG.128
+                const uint4 A = __ldg(np), B = __ldg(np + 1), Cq = __ldg(np + 2), D = __ldg(np + 3);
+                const bool h0 = slab_hit(m16lo(A.x), m16hi(A.x), m16lo(A.y), m16hi(A.y), m16lo(A.z), m16hi(A.z), idx, idy, idz, oox, ooy, ooz);
+                const bool h1 = slab_hit(m16lo(A.w), m16hi(A.w), m16lo(B.x), m16hi(B.x), m16lo(B.y), m16hi(B.y), idx, idy, idz, oox, ooy, ooz) &
+                                ((int)D.y != BT_WIDE_EMPTY);
+                const bool h2 = slab_hit(m16lo(B.z), m16hi(B.z), m16lo(B.w), m16hi(B.w), m16lo(Cq.x), m16hi(Cq.x), idx, idy, idz, oox, ooy, ooz) &
+                                ((int)D.z != BT_WIDE_EMPTY);
+                const bool h3 = slab_hit(m16lo(Cq.y), m16hi(Cq.y), m16lo(Cq.z), m16hi(Cq.z), m16lo(Cq.w), m16hi(Cq.w), idx, idy, idz, oox, ooy, ooz) &
+                                ((int)D.w != BT_WIDE_EMPTY);
+                // continue with the last child that was hit, park the others on the stack
+                int nxt = DONE;
+                if (h0) nxt = (int)D.x;
+                if (h1) { if (nxt != DONE) stack[sp++] = nxt; nxt = (int)D.y; }
+                if (h2) { if (nxt != DONE) stack[sp++] = nxt; nxt = (int)D.z; }
+                if (h3) { if (nxt != DONE) stack[sp++] = nxt; nxt = (int)D.w; }
+                if (nxt == DONE && sp > 0) nxt = stack[--sp];
+                cur = nxt;
             }
         }
         // ---- one leaf step for the lanes that stand on a leaf ------------------------------------------------------------
@@ -653,6 +662,7 @@ static MeshView view_of(const MeshDev& m) {
     MeshView v;
     v.nodes = m.nodes;
     v.qnodes = m.qnodes;
+    v.wnodes = m.wnodes;
     for (int k = 0; k < 3; ++k) { v.gmin[k] = m.grid_min[k]; v.gscale[k] = m.grid_scale[k]; }
     v.tri_rec = m.tri_rec; v.tri_f32 = m.tri_f32; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
     v.vnormals = m.vnormals;

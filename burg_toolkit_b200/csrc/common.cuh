@@ -14,6 +14,8 @@
 
 namespace bt {
 
+constexpr int BT_WIDE_EMPTY = 0x7fffffff;       // child code of an unused slot of a 4-wide node
+
 // ---- error plumbing ---------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -77,6 +79,7 @@ extern unsigned long long* g_counters_host_copy;      // device pointer as seen 
 // halves the bytes -- and the L1 wavefronts -- per traversal step:
 //   A = (l.lo.x | l.lo.y << 16,  l.lo.z | l.hi.x << 16,  l.hi.y | l.hi.z << 16,  r.lo.x | r.lo.y << 16)
 //   B = (r.lo.z | r.hi.x << 16,  r.hi.y | r.hi.z << 16,  left,  right)
+// 4-wide quantised node for the ray caster: 64 bytes = 4 x uint4, see emit_wide_nodes_kernel (mesh.cu).
 // Triangle record for the exact ray test: 128 bytes = 16 doubles (one cache line):
 //   v0[3] n[3] e0[3] e1[3] d00 d01 d11 inv_den     (e0 = v1-v0, e1 = v2-v0, trimesh 'cramer' constants)
 // Triangle vertices for the exact triangle/triangle test: 9 doubles (v0 v1 v2).
@@ -91,7 +94,8 @@ struct MeshDev {
     double*  area_cdf = nullptr;   // [nF] inclusive normalised cumulative area (caller order)
     // LBVH (leaf order = Morton order)
     float4*  nodes = nullptr;      // [max(nF-1,1)*4]   float32 boxes (collision kernel)
-    uint4*   qnodes = nullptr;     // [max(nF-1,1)*2]   the same nodes, boxes as uint16 on a global grid (ray caster): 32 B
+    uint4*   qnodes = nullptr;     // [max(nF-1,1)*2]   the same nodes, boxes as uint16 on a global grid (ray caster fallback): 32 B
+    uint4*   wnodes = nullptr;     // [max(nF-1,1)*4]   4-wide nodes (every other level skipped), uint16 boxes (ray caster): 64 B
     double   grid_min[3] = {0, 0, 0}, grid_scale[3] = {1, 1, 1};   // grid coordinate = (x - grid_min) * grid_scale
     double*  tri_rec = nullptr;    // [nF,16]  leaf order
     double*  tri_verts = nullptr;  // [nF,9]   leaf order

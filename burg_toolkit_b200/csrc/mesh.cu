@@ -197,6 +197,60 @@ __global__ void quantize_nodes_kernel(int n_nodes, const float4* __restrict__ no
     qnodes[2 * i + 1] = B;
 }
 
+// 4-wide LBVH for the ray caster: every internal node of EVEN depth becomes a wide node whose children are its
+// grandchildren (a leaf child of the binary node stays a direct child), i.e. every other level of the binary tree is
+// skipped and a ray's chain of dependent node fetches is halved.  The wide node keeps the binary node's index (the array
+// is sparse: odd-depth entries are unused), so no allocation pass is needed and the build stays deterministic.
+//   64 bytes = 4 x uint4: words 3k..3k+2 = child k's box as uint16 on the global grid (rounded outward by one cell):
+//       (lo.x | lo.y << 16,  lo.z | hi.x << 16,  hi.y | hi.z << 16);   words 12..15 = child codes
+//   child code: >= 0 wide node (binary index), < 0 leaf ~code, BT_WIDE_EMPTY = no child
+__global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                       const int32_t* __restrict__ parent, const float* __restrict__ box_min,
+                                       const float* __restrict__ box_max, double3 gmin, double3 gscale,
+                                       uint4* __restrict__ wnodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int depth = 0;
+    for (int p = parent[i]; p >= 0; p = parent[p]) ++depth;
+    if (depth & 1) return;
+    int32_t child[4];
+    int nc = 0;
+    const int32_t two[2] = {left[i], right[i]};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (two[k] < 0) child[nc++] = two[k];
+        else { child[nc++] = left[two[k]]; child[nc++] = right[two[k]]; }
+    }
+    unsigned w[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nc) {
+            const int sl = box_slot(child[k], n);
+            w[3 * k + 0] = quant_lo(box_min[3 * sl], gmin.x, gscale.x) | (quant_lo(box_min[3 * sl + 1], gmin.y, gscale.y) << 16);
+            w[3 * k + 1] = quant_lo(box_min[3 * sl + 2], gmin.z, gscale.z) | (quant_hi(box_max[3 * sl], gmin.x, gscale.x) << 16);
+            w[3 * k + 2] = quant_hi(box_max[3 * sl + 1], gmin.y, gscale.y) | (quant_hi(box_max[3 * sl + 2], gmin.z, gscale.z) << 16);
+            w[12 + k] = (unsigned)child[k];
+        } else {
+            w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0u;
+            w[12 + k] = (unsigned)BT_WIDE_EMPTY;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wnodes[4 * i + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+// nF == 1: wide node 0 = (leaf 0 | empty | empty | empty)
+__global__ void single_leaf_wide_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
+                                             double3 gmin, double3 gscale, uint4* __restrict__ wnodes) {
+    const unsigned w0 = quant_lo(box_min[0], gmin.x, gscale.x) | (quant_lo(box_min[1], gmin.y, gscale.y) << 16);
+    const unsigned w1 = quant_lo(box_min[2], gmin.z, gscale.z) | (quant_hi(box_max[0], gmin.x, gscale.x) << 16);
+    const unsigned w2 = quant_hi(box_max[1], gmin.y, gscale.y) | (quant_hi(box_max[2], gmin.z, gscale.z) << 16);
+    wnodes[0] = make_uint4(w0, w1, w2, 0u);
+    wnodes[1] = make_uint4(0u, 0u, 0u, 0u);
+    wnodes[2] = make_uint4(0u, 0u, 0u, 0u);
+    wnodes[3] = make_uint4((unsigned)~0, (unsigned)BT_WIDE_EMPTY, (unsigned)BT_WIDE_EMPTY, (unsigned)BT_WIDE_EMPTY);
+}
+
 __global__ void single_leaf_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
                                         float4* __restrict__ nodes) {
     // nF == 1: node 0 = (leaf 0 | empty box)
@@ -269,7 +323,7 @@ extern "C" int bt_stream_sync(void* stream) {
 // ---- mesh ------------------------------------------------------------------------------------------
 static int mesh_free(MeshDev& m) {
     cudaFree(m.verts); cudaFree(m.vnormals); cudaFree(m.faces); cudaFree(m.area_cdf);
-    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
+    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.wnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
     m = MeshDev();
     return BT_OK;
 }
@@ -328,6 +382,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cudaMalloc(&m.area_cdf, sizeof(double) * nF));
     MESH_TRY(cudaMalloc(&m.nodes, sizeof(float4) * 4 * nNodes));
     MESH_TRY(cudaMalloc(&m.qnodes, sizeof(uint4) * 2 * nNodes));
+    MESH_TRY(cudaMalloc(&m.wnodes, sizeof(uint4) * 4 * nNodes));
     MESH_TRY(cudaMalloc(&m.tri_rec, sizeof(double) * 16 * nF));
     MESH_TRY(cudaMalloc(&m.tri_verts, sizeof(double) * 9 * nF));
     MESH_TRY(cudaMalloc(&m.tri_f32, sizeof(float4) * 3 * nF));
@@ -410,6 +465,13 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
             (int)nNodes, m.nodes, make_double3(m.grid_min[0], m.grid_min[1], m.grid_min[2]),
             make_double3(m.grid_scale[0], m.grid_scale[1], m.grid_scale[2]), m.qnodes);
         MESH_TRY(cudaGetLastError());
+        const double3 gm = make_double3(m.grid_min[0], m.grid_min[1], m.grid_min[2]);
+        const double3 gs = make_double3(m.grid_scale[0], m.grid_scale[1], m.grid_scale[2]);
+        if (nF > 1)
+            emit_wide_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, parent, box_min, box_max, gm, gs, m.wnodes);
+        else
+            single_leaf_wide_node_kernel<<<1, 1, 0, st>>>(box_min, box_max, gm, gs, m.wnodes);
+        MESH_TRY(cudaGetLastError());
     }
     MESH_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, cub_bytes, area, m.area_cdf, n, st));
     normalise_cdf_kernel<<<G, T, 0, st>>>(m.area_cdf, nF);
@@ -436,7 +498,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     }
     m.root = 0;
     m.info.n_vertices = nV; m.info.n_triangles = nF; m.info.n_nodes = nNodes;
-    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 26 * nF) + sizeof(int32_t) * 4 * nF + 48 * nF + 96 * nNodes);
+    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 26 * nF) + sizeof(int32_t) * 4 * nF + 48 * nF + 160 * nNodes);
     m.info.surface_area = total;
     m.info.build_ms = ms;
     for (int k = 0; k < 3; ++k) { m.info.bounds_min[k] = (float)lo[k]; m.info.bounds_max[k] = (float)hi[k]; }
