@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libburgb200.so')
+LIB_PATH = os.environ.get('BT_LIB') or os.path.join(_HERE, 'csrc', 'libburgb200.so')      # BT_LIB: a tuning variant (A/B runs)
 
 BT_HIT_ORIGIN, BT_HIT_WIDTH, BT_HIT_SIGN, BT_HIT_CONE, BT_HIT_BELOW_Z = 1, 2, 4, 8, 16
 

@@ -136,101 +136,171 @@ constexpr int NPEND = 32;
 // ---- stage 1 of the ray caster: float32 traversal with ray re-fetch ---------------------------------------------------
 // Every warp owns a contiguous slice of rays (rays of one reference point are neighbours, so the slice is coherent) and
 // keeps its 32 lanes busy: a lane whose ray has left the tree immediately takes the next ray of the slice (warp-uniform
-// counter, no atomics).  Per ray the kernel emits the leaves that survive the conservative float32 pre-test (at most
-// CCAP; a ray with more is flagged and re-walked by the resolve kernel).  Only float32 state is live, so occupancy is
-// high; the float64 work happens in the second kernel with all lanes converged.
+// counter, no atomics).  The lanes only ever execute 4-wide NODE steps: the two planes of an axis share a word of the
+// node, the ray picks its near / far plane by the sign of its direction with one byte-permute each, so a box test is
+// 6 permutes + 6 FMAs + one max3 + one min3 + the compares.  Leaves that a ray reaches are not tested in line (that
+// would serialise the warp): they go to the warp's leaf queue in shared memory, and once 32 are queued every lane runs
+// one conservative float32 ray/triangle pre-test -- for whatever ray the entry belongs to.  Survivors are appended to
+// that ray's candidate list (at most CCAP; a ray with more is flagged and re-walked by the resolve kernel).  Only
+// float32 state is live, so occupancy is high; the float64 work happens in the second kernel with all lanes converged.
 constexpr int CCAP = 16;
+constexpr int TBURST = 2;                              // node steps between two looks at the leaf queue
+constexpr int LQ_CAP = 32 + 128 * TBURST;              // < 32 left over + at most 4 leaves per lane and step
+constexpr int TWARPS = 4;
+#ifndef TRAV_MINB
+#define TRAV_MINB 8
+#endif
+#ifndef TRAV_PREFETCH
+#define TRAV_PREFETCH 0
+#endif
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// near / far plane of one axis as 2^23 + q: selector 0x7610 takes the low half of the word, 0x7632 the high half
+__device__ __forceinline__ float plane16(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+
+__device__ __forceinline__ bool slab_hit_signed(unsigned wx, unsigned wy, unsigned wz, unsigned snx, unsigned sny, unsigned snz,
+                                                unsigned sfx, unsigned sfy, unsigned sfz, float idx, float idy, float idz,
+                                                float oox, float ooy, float ooz) {
+    const float tnear = fmaxf(fmaxf(fmaf(plane16(wx, snx), idx, -oox), fmaf(plane16(wy, sny), idy, -ooy)), fmaf(plane16(wz, snz), idz, -ooz));
+    const float tfar = fminf(fminf(fmaf(plane16(wx, sfx), idx, -oox), fmaf(plane16(wy, sfy), idy, -ooy)), fmaf(plane16(wz, sfz), idz, -ooz));
+    return (tnear <= tfar) & (tfar >= T_BEHIND);
+}
 
 template <bool STATS>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(32 * TWARPS, TRAV_MINB)
 traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
                 int n_rays, int rays_per_warp, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
                 unsigned long long* __restrict__ counters) {
     unsigned long long st_nodes = 0, st_leaves = 0, st_cand = 0;
+    __shared__ int s_lq_ray[TWARPS][LQ_CAP], s_lq_leaf[TWARPS][LQ_CAP], s_lq_n[TWARPS];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t slice_begin = warp * rays_per_warp;
-    if (slice_begin >= n_total) return;
+    if (slice_begin >= n_total) return;                 // whole warps leave together (no block-wide barrier below)
     const int slice_len = (int)min((int64_t)rays_per_warp, n_total - slice_begin);
     const unsigned ref0 = (unsigned)(slice_begin / n_rays), rem0 = (unsigned)(slice_begin - (int64_t)ref0 * n_rays);
     int next = 0;                                     // warp-uniform: first ray of the slice nobody has taken yet
+    int* lq_ray = s_lq_ray[w];
+    int* lq_leaf = s_lq_leaf[w];
+    if (lane == 0) s_lq_n[w] = 0;
+    __syncwarp();
 
     const int DONE = (int)0x80000000;                 // never a leaf code: leaf codes are ~index with index < 2^30
-    int64_t ray = -1;
-    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
+    int my = 0;                                       // this lane's ray, as an offset into the slice
+    float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
+    unsigned snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;
     int stack[WIDE_STACK];
-    int sp = 0, cur = DONE, n_cand = 0;
-    bool active = false;
+    int sp = 0, cur = DONE;
+
+    // one conservative float32 pre-test per lane for queue entries [first, first + count)
+    auto pretest_pass = [&](int first, int count) {
+        if (lane < count) {
+            const int off = lq_ray[first + lane], leaf = lq_leaf[first + lane];
+            const unsigned k = rem0 + (unsigned)off;
+            const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays, ray = slice_begin + off;
+            const float ox = (float)ref_pts[3 * ref], oy = (float)ref_pts[3 * ref + 1], oz = (float)ref_pts[3 * ref + 2];
+            const float dx = (float)dirs[3 * ray], dy = (float)dirs[3 * ray + 1], dz = (float)dirs[3 * ray + 2];
+            if (STATS) ++st_leaves;
+            if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
+                const int slot = atomicAdd(cand_count + ray, 1);
+                if (slot < CCAP) cand[ray * CCAP + slot] = leaf;
+                if (STATS) ++st_cand;
+            }
+        }
+    };
 
     while (true) {
         // ---- re-fetch: when enough lanes have run dry they take the next rays of the slice ---------------------------
-        const unsigned idle = __ballot_sync(FULL, !active);
+        const unsigned idle = __ballot_sync(FULL, cur == DONE);
         if (next < slice_len && (__popc(idle) >= 8 || idle == FULL)) {
             const int rank = __popc(idle & ((1u << lane) - 1u));
-            if (!active && next + rank < slice_len) {
-                const unsigned k = rem0 + (unsigned)(next + rank);           // 32-bit arithmetic: no 64-bit division here
-                const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays;
-                ray = slice_begin + next + rank;
-                ox = (float)ref_pts[3 * ref]; oy = (float)ref_pts[3 * ref + 1]; oz = (float)ref_pts[3 * ref + 2];
-                dx = (float)dirs[3 * ray]; dy = (float)dirs[3 * ray + 1]; dz = (float)dirs[3 * ray + 2];
+            if (cur == DONE && next + rank < slice_len) {
+                my = next + rank;
+                const unsigned k = rem0 + (unsigned)my;                           // 32-bit arithmetic: no 64-bit division here
+                const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays, ray = slice_begin + my;
                 // the ray in grid coordinates (same parameter t): origin (o - gmin) * scale, direction d * scale.
-                // Box coordinates arrive as 2^23 + q (uint16 OR-ed into the mantissa of 2^23); instead of subtracting 2^23
+                // Box coordinates arrive as 2^23 + q (uint16 permuted into the mantissa of 2^23); instead of subtracting 2^23
                 // per coordinate the offset is folded into the FMA constant: t = fma(2^23 + q, 1/dg, -(2^23/dg + og/dg)).
                 // The rounding of that constant displaces the plane by < 0.52 grid cells -- the boxes were rounded
-                // outward by one extra cell for exactly this reason (quantize_nodes_kernel).
-                const float gdx = dx * (float)mv.gscale[0], gdy = dy * (float)mv.gscale[1], gdz = dz * (float)mv.gscale[2];
+                // outward by one extra cell for exactly this reason (quantize_nodes_kernel / emit_wide_nodes_kernel).
+                const float gdx = (float)dirs[3 * ray] * (float)mv.gscale[0], gdy = (float)dirs[3 * ray + 1] * (float)mv.gscale[1],
+                            gdz = (float)dirs[3 * ray + 2] * (float)mv.gscale[2];
                 idx = __frcp_rn(fabsf(gdx) < 1e-20f ? copysignf(1e-20f, gdx) : gdx);
                 idy = __frcp_rn(fabsf(gdy) < 1e-20f ? copysignf(1e-20f, gdy) : gdy);
                 idz = __frcp_rn(fabsf(gdz) < 1e-20f ? copysignf(1e-20f, gdz) : gdz);
                 oox = fmaf(8388608.0f, idx, (float)((ref_pts[3 * ref] - mv.gmin[0]) * mv.gscale[0]) * idx);
                 ooy = fmaf(8388608.0f, idy, (float)((ref_pts[3 * ref + 1] - mv.gmin[1]) * mv.gscale[1]) * idy);
                 ooz = fmaf(8388608.0f, idz, (float)((ref_pts[3 * ref + 2] - mv.gmin[2]) * mv.gscale[2]) * idz);
-                sp = 0; cur = 0; n_cand = 0; active = true;
+                // near plane = the low one where the ray runs in +axis direction (sign bit of 1/d, so -0 counts as negative)
+                const bool nx = __float_as_uint(idx) >> 31, ny = __float_as_uint(idy) >> 31, nz = __float_as_uint(idz) >> 31;
+                snx = nx ? 0x7632u : 0x7610u; sfx = nx ? 0x7610u : 0x7632u;
+                sny = ny ? 0x7632u : 0x7610u; sfy = ny ? 0x7610u : 0x7632u;
+                snz = nz ? 0x7632u : 0x7610u; sfz = nz ? 0x7610u : 0x7632u;
+                sp = 0; cur = 0;
             }
             next = min(slice_len, next + __popc(idle));
         }
-        if (!__any_sync(FULL, active)) {
+        if (__all_sync(FULL, cur == DONE)) {
             if (next >= slice_len) break;
             continue;
         }
-        // ---- a short burst of node steps for the lanes that stand on an internal (4-wide) node ---------------------------
+        // ---- a short burst of 4-wide node steps -----------------------------------------------------------------------
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) {
-            if (cur >= 0) {
+        for (int step = 0; step < TBURST; ++step) {
+            if (cur != DONE) {
                 if (STATS) ++st_nodes;
                 const uint4* np = mv.wnodes + 4 * (int64_t)cur;                 // 64-byte node: 4 x LDG.128
                 const uint4 A = __ldg(np), B = __ldg(np + 1), Cq = __ldg(np + 2), D = __ldg(np + 3);
-                const bool h0 = slab_hit(m16lo(A.x), m16hi(A.x), m16lo(A.y), m16hi(A.y), m16lo(A.z), m16hi(A.z), idx, idy, idz, oox, ooy, ooz);
-                const bool h1 = slab_hit(m16lo(A.w), m16hi(A.w), m16lo(B.x), m16hi(B.x), m16lo(B.y), m16hi(B.y), idx, idy, idz, oox, ooy, ooz) &
-                                ((int)D.y != BT_WIDE_EMPTY);
-                const bool h2 = slab_hit(m16lo(B.z), m16hi(B.z), m16lo(B.w), m16hi(B.w), m16lo(Cq.x), m16hi(Cq.x), idx, idy, idz, oox, ooy, ooz) &
-                                ((int)D.z != BT_WIDE_EMPTY);
-                const bool h3 = slab_hit(m16lo(Cq.y), m16hi(Cq.y), m16lo(Cq.z), m16hi(Cq.z), m16lo(Cq.w), m16hi(Cq.w), idx, idy, idz, oox, ooy, ooz) &
-                                ((int)D.w != BT_WIDE_EMPTY);
-                // continue with the last child that was hit, park the others on the stack
+                const bool h0 = slab_hit_signed(A.x, A.y, A.z, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
+                const bool h1 = slab_hit_signed(A.w, B.x, B.y, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.y != BT_WIDE_EMPTY);
+                const bool h2 = slab_hit_signed(B.z, B.w, Cq.x, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.z != BT_WIDE_EMPTY);
+                const bool h3 = slab_hit_signed(Cq.y, Cq.z, Cq.w, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.w != BT_WIDE_EMPTY);
+                // leaves -> the warp's leaf queue (one shared-memory atomic per lane that reached leaves)
+                const int c0 = (int)D.x, c1 = (int)D.y, c2 = (int)D.z, c3 = (int)D.w;
+                const bool l0 = h0 & (c0 < 0), l1 = h1 & (c1 < 0), l2 = h2 & (c2 < 0), l3 = h3 & (c3 < 0);
+                const int nl = (int)l0 + (int)l1 + (int)l2 + (int)l3;
+                if (nl) {
+                    int q = atomicAdd(&s_lq_n[w], nl);
+                    if (l0) { lq_ray[q] = my; lq_leaf[q] = ~c0; ++q; }
+                    if (l1) { lq_ray[q] = my; lq_leaf[q] = ~c1; ++q; }
+                    if (l2) { lq_ray[q] = my; lq_leaf[q] = ~c2; ++q; }
+                    if (l3) { lq_ray[q] = my; lq_leaf[q] = ~c3; }
+                }
+                // inner children: continue with the last one that was hit, park the others (predicated, no branches)
                 int nxt = DONE;
-                if (h0) nxt = (int)D.x;
-                if (h1) { if (nxt != DONE) stack[sp++] = nxt; nxt = (int)D.y; }
-                if (h2) { if (nxt != DONE) stack[sp++] = nxt; nxt = (int)D.z; }
-                if (h3) { if (nxt != DONE) stack[sp++] = nxt; nxt = (int)D.w; }
+#define BT_TAKE(hit, code)                                                       \
+                {                                                                \
+                    const bool in = (hit) & ((code) >= 0);                       \
+                    const bool park = in & (nxt != DONE);                        \
+                    if (park) stack[sp] = nxt;                                   \
+                    sp += (int)park;                                             \
+                    nxt = in ? (code) : nxt;                                     \
+                    if (TRAV_PREFETCH && park) prefetch_l1(mv.wnodes + 4 * (int64_t)stack[sp - 1]); \
+                }
+                BT_TAKE(h0, c0) BT_TAKE(h1, c1) BT_TAKE(h2, c2) BT_TAKE(h3, c3)
+#undef BT_TAKE
                 if (nxt == DONE && sp > 0) nxt = stack[--sp];
                 cur = nxt;
             }
         }
-        // ---- one leaf step for the lanes that stand on a leaf ------------------------------------------------------------
-        if (cur < 0 && cur != DONE) {
-            const int leaf = ~cur;
-            if (STATS) ++st_leaves;
-            if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
-                if (n_cand < CCAP) cand[ray * CCAP + n_cand] = leaf;
-                ++n_cand;
-                if (STATS) ++st_cand;
-            }
-            cur = sp > 0 ? stack[--sp] : DONE;
+        __syncwarp();
+        // ---- leaf queue: 32 pre-tests at a time ------------------------------------------------------------------------
+        int nq = s_lq_n[w];
+        if (nq >= 32) {
+            do {
+                nq -= 32;
+                pretest_pass(nq, 32);
+            } while (nq >= 32);
+            __syncwarp();
+            if (lane == 0) s_lq_n[w] = nq;
+            __syncwarp();
         }
-        if (active && cur == DONE) { cand_count[ray] = n_cand; active = false; }
     }
+    __syncwarp();
+    const int nq = s_lq_n[w];
+    if (nq > 0) pretest_pass(0, nq);                   // fewer than 32 entries are left
     if (STATS) { atomicAdd(counters + 0, st_nodes); atomicAdd(counters + 1, st_leaves); atomicAdd(counters + 2, st_cand); }
 }
 
@@ -722,6 +792,7 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
     Scratch cc, cl;
     BT_CUDA(cc.alloc(sizeof(int32_t) * total, st));
     BT_CUDA(cl.alloc(sizeof(int32_t) * total * CCAP, st));
+    BT_CUDA(cudaMemsetAsync(cc.p, 0, sizeof(int32_t) * total, st));        // the traversal appends with atomics
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mesh->m.device);
     // slice length: a few rays per lane for balance, but enough warps to fill the machine (32 warps / SM)

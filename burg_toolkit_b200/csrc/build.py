@@ -28,21 +28,25 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """``out`` / ``defines``: build a tuning variant next to the product library (A/B runs: BT_LIB=<path> selects it)"""
+    lib = out or LIB
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          [os.path.join(HERE, s) for s in SOURCES] + ['-o', LIB + '.tmp']
+    cmd = [nvcc] + NVCC_FLAGS + [f'-D{d}' for d in defines] + (['-Xptxas', '-v'] if verbose else []) + \
+          [os.path.join(HERE, s) for s in SOURCES] + ['-o', lib + '.tmp']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError('nvcc failed building libburgb200.so')
     if verbose:
         sys.stderr.write(res.stderr)
-    os.replace(LIB + '.tmp', LIB)
-    return LIB
+    os.replace(lib + '.tmp', lib)
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    out = next((a.split('=', 1)[1] for a in sys.argv if a.startswith('--out=')), None)
+    defs = [a[2:] for a in sys.argv if a.startswith('-D')]
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, out=out, defines=defs))

@@ -202,7 +202,8 @@ __global__ void quantize_nodes_kernel(int n_nodes, const float4* __restrict__ no
 // skipped and a ray's chain of dependent node fetches is halved.  The wide node keeps the binary node's index (the array
 // is sparse: odd-depth entries are unused), so no allocation pass is needed and the build stays deterministic.
 //   64 bytes = 4 x uint4: words 3k..3k+2 = child k's box as uint16 on the global grid (rounded outward by one cell):
-//       (lo.x | lo.y << 16,  lo.z | hi.x << 16,  hi.y | hi.z << 16);   words 12..15 = child codes
+//       (lo.x | hi.x << 16,  lo.y | hi.y << 16,  lo.z | hi.z << 16) -- both planes of an axis in one word, so that the
+//       traversal picks a ray's near / far plane with one byte-permute each;   words 12..15 = child codes
 //   child code: >= 0 wide node (binary index), < 0 leaf ~code, BT_WIDE_EMPTY = no child
 __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
                                        const int32_t* __restrict__ parent, const float* __restrict__ box_min,
@@ -226,9 +227,9 @@ __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, 
     for (int k = 0; k < 4; ++k) {
         if (k < nc) {
             const int sl = box_slot(child[k], n);
-            w[3 * k + 0] = quant_lo(box_min[3 * sl], gmin.x, gscale.x) | (quant_lo(box_min[3 * sl + 1], gmin.y, gscale.y) << 16);
-            w[3 * k + 1] = quant_lo(box_min[3 * sl + 2], gmin.z, gscale.z) | (quant_hi(box_max[3 * sl], gmin.x, gscale.x) << 16);
-            w[3 * k + 2] = quant_hi(box_max[3 * sl + 1], gmin.y, gscale.y) | (quant_hi(box_max[3 * sl + 2], gmin.z, gscale.z) << 16);
+            w[3 * k + 0] = quant_lo(box_min[3 * sl], gmin.x, gscale.x) | (quant_hi(box_max[3 * sl], gmin.x, gscale.x) << 16);
+            w[3 * k + 1] = quant_lo(box_min[3 * sl + 1], gmin.y, gscale.y) | (quant_hi(box_max[3 * sl + 1], gmin.y, gscale.y) << 16);
+            w[3 * k + 2] = quant_lo(box_min[3 * sl + 2], gmin.z, gscale.z) | (quant_hi(box_max[3 * sl + 2], gmin.z, gscale.z) << 16);
             w[12 + k] = (unsigned)child[k];
         } else {
             w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0u;
@@ -242,9 +243,9 @@ __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, 
 // nF == 1: wide node 0 = (leaf 0 | empty | empty | empty)
 __global__ void single_leaf_wide_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
                                              double3 gmin, double3 gscale, uint4* __restrict__ wnodes) {
-    const unsigned w0 = quant_lo(box_min[0], gmin.x, gscale.x) | (quant_lo(box_min[1], gmin.y, gscale.y) << 16);
-    const unsigned w1 = quant_lo(box_min[2], gmin.z, gscale.z) | (quant_hi(box_max[0], gmin.x, gscale.x) << 16);
-    const unsigned w2 = quant_hi(box_max[1], gmin.y, gscale.y) | (quant_hi(box_max[2], gmin.z, gscale.z) << 16);
+    const unsigned w0 = quant_lo(box_min[0], gmin.x, gscale.x) | (quant_hi(box_max[0], gmin.x, gscale.x) << 16);
+    const unsigned w1 = quant_lo(box_min[1], gmin.y, gscale.y) | (quant_hi(box_max[1], gmin.y, gscale.y) << 16);
+    const unsigned w2 = quant_lo(box_min[2], gmin.z, gscale.z) | (quant_hi(box_max[2], gmin.z, gscale.z) << 16);
     wnodes[0] = make_uint4(w0, w1, w2, 0u);
     wnodes[1] = make_uint4(0u, 0u, 0u, 0u);
     wnodes[2] = make_uint4(0u, 0u, 0u, 0u);
