@@ -205,7 +205,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
             if (STATS) ++st_leaves;
             if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
                 const int slot = atomicAdd(cand_count + ray, 1);
-                if (slot < CCAP) cand[ray * CCAP + slot] = leaf;
+                if (slot < CCAP) cand[(int64_t)slot * n_total + ray] = leaf;       // slot-major: the resolve kernel reads it coalesced
                 if (STATS) ++st_cand;
             }
         }
@@ -329,9 +329,10 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         const d3 d = ld3(dirs + 3 * ray);
         for (int i = 0; i < n_pend; ++i) {
             const int leaf = pend[i];
+            const int32_t tri = __ldg(mv.leaf_tri + leaf);            // issued with the record loads, not after the test
             double t;
             if (exact_ray_triangle(mv.tri_rec + 16 * (int64_t)leaf, o, d, t)) {
-                if (n_hit < cap) { hit_t[n_hit] = t; hit_tri[n_hit] = __ldg(mv.leaf_tri + leaf); ++n_hit; }
+                if (n_hit < cap) { hit_t[n_hit] = t; hit_tri[n_hit] = tri; ++n_hit; }
                 else over = true;
             }
         }
@@ -343,7 +344,7 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         // the usual case: stage 1 (traverse_kernel) already found this ray's candidate leaves
         for (int i = 0; i < n_cand; ++i) {
             if (n_pend == NPEND) run_exact();
-            pend[n_pend++] = cand[ray * CCAP + i];
+            pend[n_pend++] = cand[(int64_t)i * n_total + ray];
         }
     } else {
         // no candidate list (or it overflowed): walk the tree here
@@ -400,17 +401,17 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
     bt_hit* out = hits + ray * (int64_t)cap;
     int n_out = 0;
     uint32_t vmask = 0;
+    double key_x[CAP], key_y[CAP], key_z[CAP];        // 1e-8 merge keys of the hits kept so far
     for (int i = 0; i < n_hit; ++i) {
         const double t = hit_t[i];
         const d3 p = add3(scl3(d, t), o);
         // trimesh intersects_id(return_locations=True): unique rows of (location, ray) at 1e-8
         const double kx = rint(p.x * 1e8 - 1e-6), ky = rint(p.y * 1e8 - 1e-6), kz = rint(p.z * 1e8 - 1e-6);
         bool dup = false;
-        for (int j = 0; j < n_out; ++j) {
-            const double* q = out[j].loc;
-            if (rint(q[0] * 1e8 - 1e-6) == kx && rint(q[1] * 1e8 - 1e-6) == ky && rint(q[2] * 1e8 - 1e-6) == kz) { dup = true; break; }
-        }
+        for (int j = 0; j < n_out; ++j)
+            if (key_x[j] == kx && key_y[j] == ky && key_z[j] == kz) { dup = true; break; }
         if (dup) continue;
+        key_x[n_out] = kx; key_y[n_out] = ky; key_z[n_out] = kz;
         const int32_t tri = hit_tri[i];
         // The reference applies its masks in sequence and computes normals / angles only for the hits that are still
         // alive (sampling.py:239-319).  flags = the FIRST filter that rejects the hit; later quantities of a rejected
