@@ -144,7 +144,13 @@ constexpr int NPEND = 32;
 // that ray's candidate list (at most CCAP; a ray with more is flagged and re-walked by the resolve kernel).  Only
 // float32 state is live, so occupancy is high; the float64 work happens in the second kernel with all lanes converged.
 constexpr int CCAP = 16;
-constexpr int TBURST = 2;                              // node steps between two looks at the leaf queue
+#ifndef TRAV_BURST
+#define TRAV_BURST 2
+#endif
+#ifndef TRAV_REFETCH
+#define TRAV_REFETCH 8
+#endif
+constexpr int TBURST = TRAV_BURST;                     // node steps between two looks at the leaf queue
 constexpr int LQ_CAP = 32 + 128 * TBURST;              // < 32 left over + at most 4 leaves per lane and step
 constexpr int TWARPS = 4;
 #ifndef TRAV_MINB
@@ -214,7 +220,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     while (true) {
         // ---- re-fetch: when enough lanes have run dry they take the next rays of the slice ---------------------------
         const unsigned idle = __ballot_sync(FULL, cur == DONE);
-        if (next < slice_len && (__popc(idle) >= 8 || idle == FULL)) {
+        if (next < slice_len && (__popc(idle) >= TRAV_REFETCH || idle == FULL)) {
             const int rank = __popc(idle & ((1u << lane) - 1u));
             if (cur == DONE && next + rank < slice_len) {
                 my = next + rank;
@@ -796,9 +802,11 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
     BT_CUDA(cudaMemsetAsync(cc.p, 0, sizeof(int32_t) * total, st));        // the traversal appends with atomics
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mesh->m.device);
-    // slice length: a few rays per lane for balance, but enough warps to fill the machine (32 warps / SM)
-    int64_t rpw = ceil_div(total, (int64_t)sm_count * 32 * 2);
-    rpw = std::max<int64_t>(32, std::min<int64_t>(256, ceil_div(rpw, 32) * 32));
+    // slice length: two rays per lane so that re-fetching can even out the walks, but several waves of warps per SM
+    // for balance (32 warps / SM resident; measured at C3: 64 rays 0.60 ms, 96-128 rays 0.63 ms, 192 rays 0.70 ms)
+    int64_t rpw = ceil_div(total, (int64_t)sm_count * 32 * 4);
+    rpw = std::max<int64_t>(64, std::min<int64_t>(256, ceil_div(rpw, 32) * 32));
+    if (const char* e = getenv("BT_CAST_RPW")) { const int v = atoi(e); if (v >= 32 && v <= 256) rpw = v; }       // tuning knob
     const int64_t n_warps = ceil_div(total, rpw);
     if (g_counters_host_copy)
         traverse_kernel<true><<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,

@@ -1,7 +1,16 @@
-python -m pytest tests/test_gpu_ags.py -x -q -m gpu 2>&1 | tail -2
-for lib in libburgb200 libvar_m10_p0 libvar_m12_p0 libvar_m8_p1 libvar_m10_p1; do
+for lib in libburgb200 libvar_b1_r8 libvar_b3_r8 libvar_b4_r8 libvar_b2_r4 libvar_b2_r16; do
   echo "== $lib"
   BT_LIB=/root/repo/burg_toolkit_b200/csrc/$lib.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print(d['ms_per_step'], 'cast', d['stage_ms']['cast'], 'collide', d['stage_ms']['collide'])
+    else: print(l, end='')
+"
+done
+for rpw in 64 96 192 256; do
+  echo "== rpw $rpw"
+  BT_CAST_RPW=$rpw python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
