@@ -63,6 +63,10 @@ __device__ __forceinline__ bool obb_overlaps_aabb(const Obb& b, float x0, float 
 //   1 = certainly strictly inside the box (all vertices inside the box shrunk by `m`)  -- only meaningful for is_box parts:
 //       a triangle inside a closed box cannot touch the box's surface triangles
 //   2 = undecided -> run the exact float64 test
+//   3 = certainly crossing the box's surface: one vertex strictly inside the box shrunk by `m`, another strictly outside
+//       the box grown by `m`, so an edge of the triangle pierces one of the box's surface triangles (is_box parts only:
+//       the 12 triangles cover the whole surface).  The exact test of that pair finds a proper crossing with a margin
+//       many orders of magnitude above float64 rounding, i.e. it is certain to report the collision.
 __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, float e1, float e2, float m,
                                                  const float off[3], const float fe[3]) {
     const float E[3] = {e0 + m, e1 + m, e2 + m};
@@ -75,6 +79,22 @@ __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, 
         inside = inside && (lo + off[k] > -(fe[k] - m)) && (hi + off[k] < (fe[k] - m));
     }
     if (inside) return 1;
+    {
+        bool any_in = false, any_out = false;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            bool vin = true, vout = false;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float c = fabsf(q[v][k] + off[k]);
+                vin = vin && (c < fe[k] - m);
+                vout = vout || (c > fe[k] + m);
+            }
+            any_in = any_in || vin;
+            any_out = any_out || vout;
+        }
+        if (any_in && any_out) return 3;
+    }
     // triangle plane
     const float f0[3] = {q[1][0] - q[0][0], q[1][1] - q[0][1], q[1][2] - q[0][2]};
     const float f1[3] = {q[2][0] - q[1][0], q[2][1] - q[1][1], q[2][2] - q[1][2]};
@@ -120,8 +140,11 @@ __device__ __forceinline__ int classify_triangle(const float q[3][3], float e0, 
 //                            coordinates: disjoint / inside-a-closed-box / undecided.  Undecided entries go to the exact queue.
 //   exact    (half warps)    two queued entries per pass: lane l of a half tests gripper triangle l of the part with FCL's
 //                            float64 17-axis test.  A hit sets out[row] and tells the lane still walking that item to stop.
+#ifndef LEAN_MINB
+#define LEAN_MINB 5
+#endif
 constexpr int WU = 1;                      // tasks per lane and pass
-constexpr int TQ_CAP = 768;               // task stack entries per warp
+constexpr int TQ_CAP = 512;               // task stack entries per warp
 constexpr int CWARPS = 4;                  // warps per block
 constexpr int CQ_CAP = 32 + 64 * WU;        // classification queue: < 32 left over + at most 64 * WU new entries per pass
 constexpr int XQ_CAP = 64;                 // exact queue: <= 1 left over + 32 new entries
@@ -213,8 +236,9 @@ __device__ __forceinline__ uint8_t load_flag(const uint8_t* p) { return *reinter
 
 struct CollideParams { float ow, tol, inflate; int use_width; };
 
-// classify scene triangle `tv` against the box of item (row, part): true = undecided, run the exact test
-__device__ __forceinline__ bool leaf_undecided(const float* __restrict__ gs, int row, const PartDev* pd_ptr, const double* __restrict__ tv,
+// classify scene triangle `tv` against the box of item (row, part): 0 = no contact, 2 = undecided (run the exact test),
+// 3 = certain collision
+__device__ __forceinline__ int leaf_class(const float* __restrict__ gs, int row, const PartDev* pd_ptr, const double* __restrict__ tv,
                                             CollideParams cp) {
     const PartDev pd = *pd_ptr;
     LaneBox cb;
@@ -227,7 +251,9 @@ __device__ __forceinline__ bool leaf_undecided(const float* __restrict__ gs, int
         for (int j = 0; j < 3; ++j) q[v][j] = fmaf(dx, cb.u[j][0], fmaf(dy, cb.u[j][1], dz * cb.u[j][2])) * cb.inv_n[j];
     }
     const int cls = classify_triangle(q, cb.le[0], cb.le[1], cb.le[2], cb.margin, cb.off, cb.fe);
-    return !(cls == 0 || (cls == 1 && pd.is_box));
+    if (cls == 0) return 0;
+    if (!pd.is_box) return 2;                      // 'inside' and 'crossing' only mean something for closed boxes
+    return cls == 1 ? 0 : cls;
 }
 
 // FCL's exact test of scene triangle `tv` against gripper triangle `gt` (TCP frame) under the affine map of grasp `row`
@@ -253,14 +279,18 @@ struct DrainArgs {
     const float* gs; const double* tri_verts; const double* gtris; const PartDev* parts; uint8_t* out;
     int *cq_row, *cq_leaf, *cq_meta, *xq_row, *xq_leaf, *xq_meta, *slot_row, *slot_dead;
     CollideParams cp;
+    // lean mode (INLINE_EXACT == false): undecided leaves leave the kernel through a global queue
+    int4* gx; unsigned* gx_count; unsigned gx_cap; uint8_t* unknown; unsigned* overflow;
 };
 
-// exact passes first (keeps the exact queue below 2 + 32 entries), then classification; returns (nx, ncq)
-template <bool STATS>
+// exact passes first (keeps the exact queue below 2 + 32 entries), then classification; returns (nx, ncq).
+// INLINE_EXACT == false: no exact passes here -- undecided entries are appended to the global queue `gx` (one atomic per
+// warp and pass) for collide_exact_kernel; entries that do not fit mark their row in `unknown` for the rescue launch.
+template <bool STATS, bool INLINE_EXACT>
 __device__ __noinline__ int2 drain_queues(const DrainArgs& a, int nx, int ncq, bool final, int lane, unsigned long long* st) {
     const unsigned FULL = 0xffffffffu;
 while (true) {
-        if (nx >= 2 || (final && ncq == 0 && nx > 0)) {
+        if (INLINE_EXACT && (nx >= 2 || (final && ncq == 0 && nx > 0))) {
             // exact: two queued entries per pass, one per half warp
             const int half = lane >> 4, sub = lane & 15;
             const int e = nx - 1 - half;
@@ -289,16 +319,32 @@ while (true) {
             if (lane < take) {
                 e_row = a.cq_row[qbase + lane]; e_leaf = a.cq_leaf[qbase + lane]; e_meta = a.cq_meta[qbase + lane];
                 if (!load_flag(a.out + e_row)) {
-                    undecided = leaf_undecided(a.gs, e_row, &a.parts[e_meta & 0xff], a.tri_verts + 9 * (int64_t)e_leaf, a.cp);
+                    const int cls = leaf_class(a.gs, e_row, &a.parts[e_meta & 0xff], a.tri_verts + 9 * (int64_t)e_leaf, a.cp);
+                    if (cls == 3) {                                     // certain collision: no exact test needed
+                        a.out[e_row] = 1;
+                        if (a.slot_row[e_meta >> 8] == e_row) a.slot_dead[e_meta >> 8] = 1;
+                    }
+                    undecided = cls == 2;
                     if (STATS) { ++st[0]; if (undecided) ++st[1]; }
                 }
             }
             const unsigned ub = __ballot_sync(FULL, undecided);
-            if (undecided) {
-                const int slot = nx + __popc(ub & ((1u << lane) - 1u));
-                a.xq_row[slot] = e_row; a.xq_leaf[slot] = e_leaf; a.xq_meta[slot] = e_meta;
+            if (INLINE_EXACT) {
+                if (undecided) {
+                    const int slot = nx + __popc(ub & ((1u << lane) - 1u));
+                    a.xq_row[slot] = e_row; a.xq_leaf[slot] = e_leaf; a.xq_meta[slot] = e_meta;
+                }
+                nx += __popc(ub);
+            } else if (ub) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(a.gx_count, (unsigned)__popc(ub));
+                base = __shfl_sync(FULL, base, 0);
+                if (undecided) {
+                    const unsigned pos = base + (unsigned)__popc(ub & ((1u << lane) - 1u));
+                    if (pos < a.gx_cap) a.gx[pos] = make_int4(e_row, e_leaf, e_meta & 0xff, 0);
+                    else { a.unknown[e_row] = 1; atomicAdd(a.overflow, 1u); }
+                }
             }
-            nx += __popc(ub);
             ncq = qbase;
             __syncwarp();
         } else {
@@ -337,13 +383,23 @@ __device__ __forceinline__ bool box_overlaps(const float* bx, float x0, float y0
 //            float64 17-axis test.  A hit sets out[row] and marks the slot dead (its remaining tasks are discarded).
 // Stack bound: a multi-pop pass grows the stack by at most 32, a single-pop pass (taken near the capacity) by at most
 // one per tree level, so TQ_CAP - (max_depth + 2) is a safe threshold for switching to single pops.
-template <bool STATS, int MINB>
-__global__ void __launch_bounds__(32 * CWARPS, MINB)
+// Two instantiations:
+//   INLINE_EXACT == false (the normal launch): the kernel only walks and classifies in float32 -- few registers, twice the
+//       resident warps; the classifier settles most collisions itself (class 3), the undecided leaves go to a global
+//       queue that collide_exact_kernel drains afterwards.
+//   INLINE_EXACT == true  (rescue launch, and the instrumented build): exact tests run inside the kernel as described
+//       above; with `only_rows` it handles just the rows whose queue entries did not fit (it returns at once if there
+//       are none).
+struct GlobalExactQueue { int4* entries; unsigned* count; unsigned cap; uint8_t* unknown; unsigned* overflow; };
+
+template <bool STATS, bool INLINE_EXACT>
+__global__ void __launch_bounds__(32 * CWARPS, INLINE_EXACT ? 4 : LEAN_MINB)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
                int64_t n_cap, const int64_t* __restrict__ d_n, const double* __restrict__ gtris,
                const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
                int max_depth, int refill_at, unsigned long long* __restrict__ work_counter, uint8_t* out,
-               unsigned long long* __restrict__ counters) {
+               GlobalExactQueue gq, const uint8_t* __restrict__ only_rows, unsigned long long* __restrict__ counters) {
+    if (INLINE_EXACT && only_rows && *reinterpret_cast<volatile unsigned*>(gq.overflow) == 0u) return;   // nothing to rescue
     unsigned long long st_nodes = 0;
     extern __shared__ double s_gtris[];            // gripper triangles, TCP frame
     __shared__ PartDev s_parts[MAX_PARTS];
@@ -356,7 +412,8 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int n_gt = parts[n_parts - 1].tri_end;
-    for (int i = threadIdx.x; i < 9 * n_gt; i += blockDim.x) s_gtris[i] = gtris[i];
+    if (INLINE_EXACT)
+        for (int i = threadIdx.x; i < 9 * n_gt; i += blockDim.x) s_gtris[i] = gtris[i];
     for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_parts[i] = parts[i];
     s_row[w][lane] = -1; s_pending[w][lane] = 0; s_dead[w][lane] = 0;
     __syncthreads();
@@ -373,6 +430,7 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     da.cq_row = cq_row; da.cq_leaf = cq_leaf; da.cq_meta = cq_meta;
     da.xq_row = s_xq_row[w]; da.xq_leaf = s_xq_leaf[w]; da.xq_meta = s_xq_meta[w];
     da.slot_row = s_row[w]; da.slot_dead = s_dead[w];
+    da.gx = gq.entries; da.gx_count = gq.count; da.gx_cap = gq.cap; da.unknown = gq.unknown; da.overflow = gq.overflow;
     da.cp.ow = ow; da.cp.tol = tol; da.cp.inflate = inflate; da.cp.use_width = use_width;
     unsigned long long st_drain[2] = {0, 0};
 
@@ -394,7 +452,7 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
                 if (item < total) {
                     const int part = (int)(item / n);
                     const int64_t row = item - (int64_t)part * n;
-                    if (!load_flag(out + row)) {                               // another part of this grasp may already collide
+                    if (!load_flag(out + row) && !(INLINE_EXACT && only_rows && !only_rows[row])) {   // may already collide
                         slot = __fns(free_mask, 0, lane + 1);
                         WalkBox b;
                         build_walkbox(b, gs, row, s_parts[part], inv_ow, tol, use_width, inflate);
@@ -484,12 +542,44 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
         __syncwarp();
         // ---- drain the queues ---------------------------------------------------------------------------------------------
         if (nx >= 2 || ncq >= 32) {
-            const int2 res = drain_queues<STATS>(da, nx, ncq, false, lane, st_drain);
+            const int2 res = drain_queues<STATS, INLINE_EXACT>(da, nx, ncq, false, lane, st_drain);
             nx = res.x; ncq = res.y;
         }
     }
-    if (nx > 0 || ncq > 0) drain_queues<STATS>(da, nx, ncq, true, lane, st_drain);
+    if (nx > 0 || ncq > 0) drain_queues<STATS, INLINE_EXACT>(da, nx, ncq, true, lane, st_drain);
     if (STATS) { atomicAdd(counters + 3, st_nodes); atomicAdd(counters + 4, st_drain[0]); atomicAdd(counters + 5, st_drain[1]); }
+}
+
+// The undecided (row, leaf, part) entries of the lean launch: one half warp per entry, lane l <-> gripper triangle l of the
+// part, FCL's float64 17-axis test.  Entries of rows that are already known to collide are skipped.
+__global__ void __launch_bounds__(128)
+collide_exact_kernel(const int4* __restrict__ entries, const unsigned* __restrict__ count, unsigned cap,
+                     const double* __restrict__ tri_verts, const float* __restrict__ gs, const double* __restrict__ gtris,
+                     const PartDev* __restrict__ parts, int n_parts, float ow, float tol, int use_width, float inflate,
+                     uint8_t* out) {
+    extern __shared__ double s_gtris[];
+    __shared__ PartDev s_parts[MAX_PARTS];
+    const int n_gt = parts[n_parts - 1].tri_end;
+    for (int i = threadIdx.x; i < 9 * n_gt; i += blockDim.x) s_gtris[i] = gtris[i];
+    for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_parts[i] = parts[i];
+    __syncthreads();
+    const unsigned n = min(*count, cap);
+    const int sub = threadIdx.x & 15;
+    const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
+    const CollideParams cp = {ow, tol, inflate, use_width};
+    const unsigned stride = gridDim.x * (blockDim.x >> 4);
+    for (unsigned e = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); e < n; e += stride) {
+        const int4 en = entries[e];
+        if (load_flag(out + en.x)) continue;
+        const int tb = s_parts[en.z].tri_begin, cnt = s_parts[en.z].tri_end - tb;
+        bool found = false;
+        for (int t0 = 0; t0 < cnt && !found; t0 += 16) {
+            bool hit = false;
+            if (t0 + sub < cnt) hit = exact_pair_hit(gs, en.x, tri_verts + 9 * (int64_t)en.y, s_gtris + 9 * (tb + t0 + sub), cp);
+            found = __ballot_sync(half_mask, hit) != 0u;
+        }
+        if (found && sub == 0) out[en.x] = 1;
+    }
 }
 
 // ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------
@@ -664,36 +754,64 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
     const float inflate = 2e-5f * max_abs + 1e-6f;
     const size_t tri_bytes = sizeof(double) * 9 * (size_t)gripper->n_tris;
     // tuning knobs (environment, read once): traversal burst length, refill threshold, occupancy variant
-    static int refill_at = 0, minb = 0;
+    static int refill_at = 0, inline_exact = 0;
     if (!refill_at) {
         const char* e;
-        refill_at = (e = getenv("BT_COLLIDE_REFILL")) ? std::max(1, std::min(32, atoi(e))) : 24;
-        minb = (e = getenv("BT_COLLIDE_MINB")) ? atoi(e) : 4;
+        refill_at = (e = getenv("BT_COLLIDE_REFILL")) ? std::max(1, std::min(32, atoi(e))) : 32;
+        inline_exact = (e = getenv("BT_COLLIDE_INLINE")) ? atoi(e) : 0;
     }
     BT_REQUIRE(scene->m.info.n_nodes < (1 << 26), "scene LBVH has more than 2^26 nodes");
     BT_REQUIRE(scene->m.info.max_depth + 2 + 64 * WU <= TQ_CAP, "scene LBVH too deep for the task stack");
-    Scratch counter;
-    BT_CUDA(counter.alloc(sizeof(unsigned long long), st));
-    BT_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    Scratch counter, gx_entries, gx_meta, unknown;
+    BT_CUDA(counter.alloc(2 * sizeof(unsigned long long), st));                 // work counters of the two launches
+    BT_CUDA(cudaMemsetAsync(counter.p, 0, 2 * sizeof(unsigned long long), st));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->m.device);
     const int64_t items = n * gripper->n_parts;
-    const int per_sm = (minb == 5 || minb == 6) ? minb : 4;
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * per_sm);   // persistent CTAs
-#define BT_COLLIDE_LAUNCH(STATS, MINB, CNT)                                                                                   \
-    do {                                                                                                                      \
-        if (tri_bytes > 8 * 1024)                                                                                             \
-            BT_CUDA(cudaFuncSetAttribute(collide_kernel<STATS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes)); \
-        collide_kernel<STATS, MINB><<<grid, 32 * CWARPS, tri_bytes, st>>>(                                                    \
-            scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts,               \
-            (float)opening_width, (float)width_tolerance, use_width, inflate, (int)scene->m.info.max_depth, refill_at,                              \
-            counter.as<unsigned long long>(), d_colliding, CNT);                                                              \
-    } while (0)
-    if (g_counters_host_copy) BT_COLLIDE_LAUNCH(true, 4, g_counters_host_copy);
-    else if (minb == 6) BT_COLLIDE_LAUNCH(false, 6, nullptr);
-    else if (minb == 5) BT_COLLIDE_LAUNCH(false, 5, nullptr);
-    else BT_COLLIDE_LAUNCH(false, 4, nullptr);
-#undef BT_COLLIDE_LAUNCH
+    // global queue of undecided leaves: 2 entries per item is ~15x what config 3 / 4 produce; what does not fit is
+    // handled by the rescue launch below
+    const unsigned gx_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(2 * items, 1 << 16), (int64_t)1 << 26);
+    BT_CUDA(gx_entries.alloc(sizeof(int4) * (size_t)gx_cap, st));
+    BT_CUDA(gx_meta.alloc(2 * sizeof(unsigned), st));                            // [0] entries appended, [1] entries dropped
+    BT_CUDA(cudaMemsetAsync(gx_meta.p, 0, 2 * sizeof(unsigned), st));
+    BT_CUDA(unknown.alloc((size_t)n, st));
+    BT_CUDA(cudaMemsetAsync(unknown.p, 0, (size_t)n, st));
+    GlobalExactQueue gq;
+    gq.entries = gx_entries.as<int4>(); gq.count = gx_meta.as<unsigned>(); gq.cap = gx_cap;
+    gq.unknown = unknown.as<uint8_t>(); gq.overflow = gx_meta.as<unsigned>() + 1;
+    unsigned long long* wc = counter.as<unsigned long long>();
+    if (tri_bytes > 8 * 1024) {
+        BT_CUDA(cudaFuncSetAttribute(collide_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+        BT_CUDA(cudaFuncSetAttribute(collide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+        BT_CUDA(cudaFuncSetAttribute(collide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+        BT_CUDA(cudaFuncSetAttribute(collide_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_bytes));
+    }
+#define BT_COLLIDE_ARGS(WC, ONLY, CNT)                                                                                         \
+    scene->m.nodes, scene->m.tri_verts, d_gs, n, d_n, gripper->tris, gripper->parts, gripper->n_parts, (float)opening_width,    \
+        (float)width_tolerance, use_width, inflate, (int)scene->m.info.max_depth, refill_at, WC, d_colliding, gq, ONLY, CNT
+    if (g_counters_host_copy || inline_exact) {
+        // instrumented build / BT_COLLIDE_INLINE=1: everything in one kernel
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * 4);
+        if (g_counters_host_copy)
+            collide_kernel<true, true><<<grid, 32 * CWARPS, tri_bytes, st>>>(BT_COLLIDE_ARGS(wc, nullptr, g_counters_host_copy));
+        else
+            collide_kernel<false, true><<<grid, 32 * CWARPS, tri_bytes, st>>>(BT_COLLIDE_ARGS(wc, nullptr, nullptr));
+        BT_LAUNCH_CHECK();
+        return BT_OK;
+    }
+    {
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * LEAN_MINB);
+        collide_kernel<false, false><<<grid, 32 * CWARPS, 0, st>>>(BT_COLLIDE_ARGS(wc, nullptr, nullptr));
+        BT_LAUNCH_CHECK();
+        collide_exact_kernel<<<sm_count * 8, 128, tri_bytes, st>>>(gq.entries, gq.count, gq.cap, scene->m.tri_verts, d_gs, gripper->tris,
+                                                                   gripper->parts, gripper->n_parts, (float)opening_width,
+                                                                   (float)width_tolerance, use_width, inflate, d_colliding);
+        BT_LAUNCH_CHECK();
+        // rescue: rows whose queue entries were dropped are redone with in-kernel exact tests (returns at once if none)
+        const unsigned rgrid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * 4);
+        collide_kernel<false, true><<<rgrid, 32 * CWARPS, tri_bytes, st>>>(BT_COLLIDE_ARGS(wc + 1, gq.unknown, nullptr));
+    }
+#undef BT_COLLIDE_ARGS
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
