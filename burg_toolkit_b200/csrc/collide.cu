@@ -770,7 +770,8 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
     const int64_t items = n * gripper->n_parts;
     // global queue of undecided leaves: 2 entries per item is ~15x what config 3 / 4 produce; what does not fit is
     // handled by the rescue launch below
-    const unsigned gx_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(2 * items, 1 << 16), (int64_t)1 << 26);
+    unsigned gx_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(2 * items, 1 << 16), (int64_t)1 << 26);
+    if (const char* e = getenv("BT_COLLIDE_GXCAP")) { const long v = atol(e); if (v >= 1) gx_cap = (unsigned)std::min<long>(v, 1l << 26); }   // tests: force the rescue path
     BT_CUDA(gx_entries.alloc(sizeof(int4) * (size_t)gx_cap, st));
     BT_CUDA(gx_meta.alloc(2 * sizeof(unsigned), st));                            // [0] entries appended, [1] entries dropped
     BT_CUDA(cudaMemsetAsync(gx_meta.p, 0, 2 * sizeof(unsigned), st));

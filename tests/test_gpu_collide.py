@@ -104,3 +104,17 @@ def test_compaction_keeps_order():
         assert k == int((mask == 0).sum())
         assert np.array_equal(out_rows[:k].cpu().numpy(), rows[mask == 0])
         assert np.array_equal(out_c[:k].cpu().numpy(), contacts[mask == 0])
+
+
+def test_exact_queue_overflow_is_rescued(monkeypatch):
+    """the lean launch hands undecided leaves to a global queue; rows whose entries do not fit are redone by the rescue
+    launch with in-kernel exact tests -- with a 1-entry queue almost everything takes that path, same answers"""
+    from burg_toolkit_b200.gripper import ParallelJawGripper
+    c = load_golden('collisions')
+    ags = sampler_for(load_golden('ags_icosphere'), ParallelJawGripper())
+    gs = _gs(c['ico_gs'])
+    monkeypatch.setenv('BT_COLLIDE_GXCAP', '1')
+    assert np.array_equal(ags.check_collisions(gs), c['ico_colliding'])
+    assert np.array_equal(ags.check_collisions(gs, width_tolerance=-0.0005), c['ico_colliding_tight'])
+    monkeypatch.delenv('BT_COLLIDE_GXCAP')
+    assert np.array_equal(ags.check_collisions(gs, width_tolerance=-0.0005), c['ico_colliding_tight'])
