@@ -313,8 +313,11 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
 // One thread per ray.  Phase 1 walks the LBVH in float32 (both child boxes per 64-byte node) and parks the leaves that
 // survive the float32 pre-test; phase 2 runs the reference's float64 narrow phase on the parked leaves (threads of a
 // warp are converged again by then); phase 3 orders, de-duplicates and filters the hits and writes the records.
+#ifndef CAST_MINB
+#define CAST_MINB 6
+#endif
 template <int CAP>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, CAST_MINB)
 cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
             int n_rays, bt_ags_params P, int cap, const int32_t* __restrict__ cand_count, const int32_t* __restrict__ cand,
             int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, uint32_t* __restrict__ valid_mask,

@@ -205,15 +205,23 @@ __global__ void quantize_nodes_kernel(int n_nodes, const float4* __restrict__ no
 //       (lo.x | hi.x << 16,  lo.y | hi.y << 16,  lo.z | hi.z << 16) -- both planes of an axis in one word, so that the
 //       traversal picks a ray's near / far plane with one byte-permute each;   words 12..15 = child codes
 //   child code: >= 0 wide node (binary index), < 0 leaf ~code, BT_WIDE_EMPTY = no child
-__global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                                       const int32_t* __restrict__ parent, const float* __restrict__ box_min,
-                                       const float* __restrict__ box_max, double3 gmin, double3 gscale,
-                                       uint4* __restrict__ wnodes) {
+// flag[i] = 1 iff internal node i has even depth (it becomes a wide node); an exclusive scan of the flags gives the wide
+// nodes dense indices in the order of the binary indices (= along the Morton curve), so the array has no holes
+__global__ void wide_flags_kernel(int n, const int32_t* __restrict__ parent, int32_t* __restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int depth = 0;
     for (int p = parent[i]; p >= 0; p = parent[p]) ++depth;
-    if (depth & 1) return;
+    flag[i] = (depth & 1) ? 0 : 1;
+}
+
+__global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                       const int32_t* __restrict__ flag, const int32_t* __restrict__ widx,
+                                       const float* __restrict__ box_min, const float* __restrict__ box_max, double3 gmin,
+                                       double3 gscale, uint4* __restrict__ wnodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (!flag[i]) return;
     int32_t child[4];
     int nc = 0;
     const int32_t two[2] = {left[i], right[i]};
@@ -230,14 +238,14 @@ __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, 
             w[3 * k + 0] = quant_lo(box_min[3 * sl], gmin.x, gscale.x) | (quant_hi(box_max[3 * sl], gmin.x, gscale.x) << 16);
             w[3 * k + 1] = quant_lo(box_min[3 * sl + 1], gmin.y, gscale.y) | (quant_hi(box_max[3 * sl + 1], gmin.y, gscale.y) << 16);
             w[3 * k + 2] = quant_lo(box_min[3 * sl + 2], gmin.z, gscale.z) | (quant_hi(box_max[3 * sl + 2], gmin.z, gscale.z) << 16);
-            w[12 + k] = (unsigned)child[k];
+            w[12 + k] = (unsigned)(child[k] < 0 ? child[k] : widx[child[k]]);       // inner children: dense wide index
         } else {
             w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0u;
             w[12 + k] = (unsigned)BT_WIDE_EMPTY;
         }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) wnodes[4 * i + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) wnodes[4 * (int64_t)widx[i] + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
 // nF == 1: wide node 0 = (leaf 0 | empty | empty | empty)
@@ -425,6 +433,8 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_sorted, ids, ids_sorted, n, 0, 30, st));
     MESH_TRY(cub::DeviceScan::InclusiveSum(nullptr, cub_bytes2, area, m.area_cdf, n, st));
     if (cub_bytes2 > cub_bytes) cub_bytes = cub_bytes2;
+    MESH_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes2, ids, ids_sorted, n, st));      // wide-node index scan
+    if (cub_bytes2 > cub_bytes) cub_bytes = cub_bytes2;
     MESH_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1));
 
     double ext[3], inv_ext[3], max_abs = 0.0;
@@ -468,9 +478,15 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
         MESH_TRY(cudaGetLastError());
         const double3 gm = make_double3(m.grid_min[0], m.grid_min[1], m.grid_min[2]);
         const double3 gs = make_double3(m.grid_scale[0], m.grid_scale[1], m.grid_scale[2]);
-        if (nF > 1)
-            emit_wide_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, parent, box_min, box_max, gm, gs, m.wnodes);
-        else
+        if (nF > 1) {
+            // ids / ids_sorted (n int32 each) are free again at this point: reuse them for the flags and their scan
+            int32_t* flag = reinterpret_cast<int32_t*>(ids);
+            int32_t* widx = reinterpret_cast<int32_t*>(ids_sorted);
+            wide_flags_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, parent, flag);
+            MESH_TRY(cudaGetLastError());
+            MESH_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flag, widx, n - 1, st));
+            emit_wide_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, flag, widx, box_min, box_max, gm, gs, m.wnodes);
+        } else
             single_leaf_wide_node_kernel<<<1, 1, 0, st>>>(box_min, box_max, gm, gs, m.wnodes);
         MESH_TRY(cudaGetLastError());
     }
