@@ -7,6 +7,7 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json `configs`):
   ags_c3       config 3: AGS on the 99 904-triangle 'YCB-like' mesh, 10 000 reference points x 100 rays = 1 M
                candidates per step per GPU, max_targets_per_ref_point = 1, 12 orientations, gripper-vs-object
                collision + compaction.  metric: candidates/s.  (default; the config the metric's target is quoted on)
+  ags_c1       config 1: AntipodalGraspSampler.sample(1000) + check_collisions on a 20 480-triangle icosphere (public API call).
   ags_c4       config 4: 20 objects (~1 M triangles) + ground slab, the target object changes every step, gripper vs scene.
   coverage_c2  config 2: coverage of two 100k grasp sets (perturbed pair).  metric: pairs/s.
   coverage_c5  config 5: 1 M x 1 M grasps; with several ranks the reference rows are sharded (strong scaling).
@@ -37,9 +38,10 @@ N_REF = 10_000
 N_RAYS = 100
 N_ORIENT = 12
 COV_N = 100_000
+# own kernels launched by one bt_ags_pipeline call, in order (CUB scans and memsets not counted)
 AGS_KERNELS = ['sample_surface_kernel', 'cone_rays_kernel', 'traverse_kernel', 'cast_kernel', 'zero_first_kernel', 'select_count_kernel',
-               'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'scale_count_kernel', 'collide_kernel', 'compact_count_kernel',
-               'compact_scatter_kernel']
+               'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'scale_count_kernel', 'collide_kernel<lean>',
+               'collide_exact_kernel', 'collide_kernel<rescue>', 'compact_count_kernel', 'compact_scatter_kernel']
 
 
 def measured_peaks():
@@ -212,10 +214,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count()
-    if args.workload in ('ags_c3', 'ags_c4'):
+    if args.workload in ('ags_c1', 'ags_c3', 'ags_c4'):
         scene_meshes = None
         if args.workload == 'ags_c3':
             mesh = c3_mesh()
+        elif args.workload == 'ags_c1':
+            from burg_toolkit_b200 import mesh as bmesh
+            mesh = bmesh.create_icosphere(5, 0.03)
         else:
             scene_meshes = c4_scene().get_mesh_list()
             mesh = scene_meshes[1]
@@ -441,6 +446,52 @@ def run_b200(args, rank, world, local_rank):
             # secondary metric of BASELINE.json: coverage pairs/s (config 2), same JSON line
             if args.workload == 'ags_c3':
                 line['secondary'] = coverage_numbers(args, torch, metrics, flush, barrier, short=True)
+    elif args.workload == 'ags_c1':
+        # config 0 of BASELINE.json: the reference's own CPU-runnable case through the public API --
+        # AntipodalGraspSampler.sample(1000) on a 20 480-triangle icosphere, 12 orientations, then check_collisions
+        from burg_toolkit_b200 import mesh as bmesh
+        ags = sampling.AntipodalGraspSampler()
+        ags.mesh, ags.gripper, ags.verbose, ags.device = bmesh.create_icosphere(5, 0.03), ParallelJawGripper(), False, local_rank
+        ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
+        np.random.seed(1234 + rank)
+        clocks.start()
+        for _ in range(args.warmup):
+            gs, _ = ags.sample(1000)
+            ags.check_collisions(gs)
+        barrier()
+        ev, cands, grasps = [], 0, 0
+        for s in range(args.steps):
+            flush.fill_(s & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gs, contacts = ags.sample(1000)                    # host call: numpy results come back every time
+            coll = ags.check_collisions(gs)
+            e1.record()
+            ev.append((e0, e1))
+            cands += ags.last_stats['candidates']
+            grasps += len(gs)
+        barrier()
+        clk = clocks.stop()
+        total_ms = max_over_ranks(sum(event_ms(ev)))
+        cand_all = sum_over_ranks(cands)
+        value = cand_all / (total_ms * 1e-3)
+        line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
+                'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
+                'config': {'workload': 'ags_c1', 'mesh': 'icosphere, 5 subdivisions, r = 0.03', 'mesh_triangles': 20480,
+                           'call': 'AntipodalGraspSampler.sample(1000) + check_collisions(gs), numpy in / numpy out',
+                           'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1,
+                           'candidates_per_step_per_gpu': cands / args.steps, 'grasps_per_step': grasps / args.steps,
+                           'l2': 'flushed between steps (256 MB write)'},
+                'roofline': None,
+                'e2e': {'value': value, 'unit': 'candidates/s', 'ms_per_step': total_ms / args.steps,
+                        'h2d_bytes_per_step': int(grasps / args.steps * 56), 'd2h_bytes_per_step': int(grasps / args.steps * (56 + 48 + 1)),
+                        'note': 'this workload IS the end-to-end call: value and e2e coincide'},
+                'gpu_launches': None, 'note': 'launch-latency bound: ~100 reference points per call; the throughput '
+                                              'configurations are ags_c3 / ags_c4'}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            c, dt, threads, _ = cpu_ags(ags.mesh, 2000)
+            line['cpu_baseline'] = {'value': c / dt, 'unit': 'candidates/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'2000 reference points x {N_RAYS} rays of the same mesh, oracle/coracle.c with OpenMP, {dt:.2f} s'}
     else:
         line = coverage_numbers(args, torch, metrics, flush, barrier, short=False, clocks=clocks, rank=rank, world=world,
                                 dist=dist if world > 1 else None)
@@ -553,7 +604,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='ags_c3', choices=['ags_c3', 'ags_c4', 'coverage_c2', 'coverage_c5'])
+    ap.add_argument('--workload', default='ags_c3', choices=['ags_c1', 'ags_c3', 'ags_c4', 'coverage_c2', 'coverage_c5'])
     ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
