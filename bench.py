@@ -322,15 +322,31 @@ def run_b200(args, rank, world, local_rank):
         ags.mesh = mesh
         dm = ags._device_mesh()
         info = dm.info
-        gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if (world > 1 and rank == 0) else None
+        # the path's only exchange: compacted grasp rows + contacts + counts to rank 0.  Every rank's compaction
+        # kernel stores its kept rows straight into its slot of rank 0's buffer over NVLink (distributed.PeerGather, CUDA IPC);
+        # NCCL carries the 8-byte counts, which is also the completion barrier.  If the box refuses the IPC mapping the
+        # bench says so and uses a plain NCCL gather of the padded rows.
+        peer, gather_buf, exchange = None, None, 'none (1 GPU)'
+        if world > 1:
+            from burg_toolkit_b200 import distributed as bdist
+            from burg_toolkit_b200._native import NativeError
+            try:
+                peer = bdist.PeerGather(N_REF * N_ORIENT, with_contacts=True, device=local_rank)
+                exchange = 'compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer), NCCL all_gather of counts'
+            except NativeError as ex:
+                exchange = f'NCCL all_reduce + gather of padded rows (peer mapping unavailable: {ex})'
+                gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if rank == 0 else None
 
         from burg_toolkit_b200.device import StageTimer
         stage_timer = StageTimer(local_rank)
 
         def step(seed, timer=None):
             ags.mesh = targets[seed % len(targets)]
-            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer, **pipe_kw)
-            if world > 1:       # the path's only exchange: compacted grasp lists + counts to rank 0 over NVLink
+            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer,
+                                   destinations=peer.destinations() if peer else None, **pipe_kw)
+            if peer is not None:
+                peer.complete(out['n_free'])
+            elif world > 1:
                 dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
                 dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
             return out
@@ -363,7 +379,7 @@ def run_b200(args, rank, world, local_rank):
         value = candidates / (total_ms * 1e-3)
         stage_ms = {k: statistics.mean(v) for k, v in stage_acc.items()}
         n_grasps = int(torch.stack([a.reshape(()) for a, _, _ in stats]).double().mean().item())
-        n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // max(world, 1)
+        n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // (1 if (peer is not None or world == 1) else world)
         overflow = int(torch.stack([c.reshape(()) for _, _, c in stats]).sum().item())
 
         # work counters (instrumented kernel instantiations, one extra untimed step) for the L2 traffic model
@@ -420,6 +436,8 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         e2e_ms = max_over_ranks(sum(event_ms(e2e_events)))
         e2e_value = candidates / (e2e_ms * 1e-3)
+        if peer is not None:
+            peer.close()
 
         line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
                 'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
@@ -433,7 +451,8 @@ def run_b200(args, rank, world, local_rank):
                            'collision': ('gripper-vs-object' if scene_meshes is None else 'gripper-vs-scene') + ', use_width, tol 0.01',
                            'mode': 'reference mode (one pair per reference point)', 'l2': 'flushed between steps (256 MB write)',
                            'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
-                           'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow},
+                           'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow,
+                           'exchange': exchange},
                 'roofline': roofline, 'stage_ms': stage_ms,
                 'e2e': {'value': e2e_value, 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_ms / args.steps},

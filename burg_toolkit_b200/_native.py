@@ -90,6 +90,10 @@ _SIGNATURES = {
     'bt_gripper_destroy': (C.c_int, [_P]),
     'bt_collide': (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P, _P]),
     'bt_compact': (C.c_int, [_P, C.c_uint8, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    'bt_peer_alloc': (C.c_int, [C.c_int, C.c_int64, C.POINTER(_P), _P]),
+    'bt_peer_open': (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    'bt_peer_close': (C.c_int, [C.c_int, _P]),
+    'bt_peer_free': (C.c_int, [C.c_int, _P]),
     'bt_timer_create': (C.c_int, [C.c_int, C.POINTER(_P)]),
     'bt_timer_destroy': (C.c_int, [_P]),
     'bt_timer_read': (C.c_int, [_P, C.POINTER(C.c_float)]),
@@ -135,12 +139,20 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
 
 
+_torch = None
+
+
 def require_cuda():
-    import torch
-    if not torch.cuda.is_available():
-        raise NativeError('no CUDA device visible: burg_toolkit_b200 runs on B200 (sm_100a) only, '
-                          'there is no CPU fallback')
-    return torch
+    """-> the torch module, after checking ONCE per process that a CUDA device is visible (the check costs microseconds
+    and this sits on every call of the hot path)"""
+    global _torch
+    if _torch is None:
+        import torch
+        if not torch.cuda.is_available():
+            raise NativeError('no CUDA device visible: burg_toolkit_b200 runs on B200 (sm_100a) only, '
+                              'there is no CPU fallback')
+        _torch = torch
+    return _torch
 
 
 def ptr(t):

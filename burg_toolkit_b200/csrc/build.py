@@ -7,12 +7,12 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['mesh.cu', 'ags.cu', 'collide.cu', 'coverage.cu', 'pipeline.cu', 'generators.cu', 'scene.cu']
+SOURCES = ['mesh.cu', 'ags.cu', 'collide.cu', 'coverage.cu', 'pipeline.cu', 'generators.cu', 'scene.cu', 'peer.cu']
 HEADERS = ['common.cuh', 'tritri.cuh', os.path.join('..', '..', 'include', 'burg_b200.h')]
 LIB = os.path.join(HERE, 'libburgb200.so')
 
 NVCC_FLAGS = [
-    '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+    '-O3', '-std=c++17', '-t', '0', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
     # float64 paths must reproduce numpy's separate multiply/add roundings; wanted FMAs are explicit
     '-fmad=false',
     '--shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-Xcompiler', '-fvisibility=hidden',

@@ -602,32 +602,56 @@ __global__ void compact_count_kernel(const uint8_t* __restrict__ mask, uint8_t k
     }
 }
 
-__global__ void compact_scatter_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
+// The kept rows of a block are contiguous in the destination ([block_offset, block_offset + run)), so the block stages its
+// 256 source rows in shared memory (coalesced 8-byte loads), builds the dst->src map from the ballot ranks and streams
+// the run out as consecutive 8-byte words: full-line writes whatever the destination is -- local HBM, a peer GPU's
+// memory over NVLink (the multi-GPU gather is this store, see distributed.PeerGather) or mapped host memory over PCIe
+// (AntipodalGraspSampler.evaluate_host).  A 14-float row is 7 words, a 6-double contact record 6 words; both row sizes
+// are multiples of 8 bytes, so every word is aligned.
+__global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
                                        const int64_t* __restrict__ d_n, const int64_t* __restrict__ block_offset,
                                        int64_t n_blocks, const float* __restrict__ gs, const double* __restrict__ contacts,
                                        float* __restrict__ out_gs, double* __restrict__ out_contacts, int64_t* __restrict__ n_out) {
     __shared__ int warp_off[CB / 32];
+    __shared__ int run_s;
+    __shared__ uint16_t src_of[CB];
+    __shared__ double tile[CB * 7];                       // 14 KB: the block's rows (7 words each), then its contacts (6 each)
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    const int64_t i = blockIdx.x * (int64_t)CB + threadIdx.x;
+    const int64_t row0 = blockIdx.x * (int64_t)CB;
+    const int64_t i = row0 + threadIdx.x;
     const bool k = (i < n) && (mask[i] == keep);
     const unsigned bal = __ballot_sync(0xffffffffu, k);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) warp_off[w] = __popc(bal);
+    const int rows_here = (int)max((int64_t)0, min((int64_t)CB, n - row0));
+    {   // stage the source rows while the offsets settle
+        const double* src = reinterpret_cast<const double*>(gs) + 7 * row0;
+        for (int e = threadIdx.x; e < rows_here * 7; e += CB) tile[e] = src[e];
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
 #pragma unroll
         for (int q = 0; q < CB / 32; ++q) { int c = warp_off[q]; warp_off[q] = run; run += c; }
+        run_s = run;
         if (blockIdx.x == n_blocks - 1 && n_out) *n_out = block_offset[blockIdx.x] + run;
     }
     __syncthreads();
-    if (!k) return;
-    const int64_t dst = block_offset[blockIdx.x] + warp_off[w] + __popc(bal & ((1u << lane) - 1u));
-#pragma unroll
-    for (int c = 0; c < 14; ++c) out_gs[14 * dst + c] = gs[14 * i + c];
+    if (k) src_of[warp_off[w] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+    __syncthreads();
+    const int run = run_s;
+    const int64_t dst0 = block_offset[blockIdx.x];
+    {
+        double* dst = reinterpret_cast<double*>(out_gs) + 7 * dst0;
+        for (int e = threadIdx.x; e < run * 7; e += CB) { const int r = e / 7; dst[e] = tile[7 * src_of[r] + (e - 7 * r)]; }
+    }
     if (contacts && out_contacts) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) out_contacts[6 * dst + c] = contacts[6 * i + c];
+        __syncthreads();
+        const double* src = contacts + 6 * row0;
+        for (int e = threadIdx.x; e < rows_here * 6; e += CB) tile[e] = src[e];
+        __syncthreads();
+        double* dst = out_contacts + 6 * dst0;
+        for (int e = threadIdx.x; e < run * 6; e += CB) { const int r = e / 6; dst[e] = tile[6 * src_of[r] + (e - 6 * r)]; }
     }
 }
 
@@ -822,6 +846,7 @@ extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float
                           void* stream) {
     BT_REQUIRE(d_mask && d_gs && d_out_gs && d_n_out, "null pointer");
     BT_REQUIRE(n >= 0, "negative count");
+    BT_REQUIRE(((reinterpret_cast<uintptr_t>(d_gs) | reinterpret_cast<uintptr_t>(d_out_gs)) & 7) == 0, "grasp rows must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { BT_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), st)); return BT_OK; }
     const int64_t n_blocks = ceil_div(n, CB);

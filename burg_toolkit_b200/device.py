@@ -84,12 +84,14 @@ MESH_CACHE_SIZE = 256
 
 
 def cached_device_mesh(mesh, device=None):
-    """DeviceMesh for ``mesh`` keyed by object identity + vertex/triangle counts (rebuilds if the
-    mesh object was replaced)."""
+    """DeviceMesh for ``mesh`` keyed by object identity + vertex/triangle counts + a sampled vertex checksum (rebuilds
+    if the mesh object was replaced or visibly edited; meshes are otherwise treated as immutable)."""
     dev = device_index(device)
     m = as_mesh(mesh)
     key = (id(mesh), dev)
-    tag = (len(m.vertices), len(m.triangles), float(np.asarray(m.vertices).sum()))
+    v = np.asarray(m.vertices)
+    # cheap fingerprint (this sits on every pipeline call): counts + 32 strided rows, not the whole vertex array
+    tag = (len(v), len(m.triangles), float(v[::max(1, len(v) // 32)].sum()))
     hit = _mesh_cache.pop(key, None)
     if hit is not None and hit[0] == tag:
         _mesh_cache[key] = hit                       # most recently used last
@@ -227,6 +229,9 @@ class PipelineWorkspace:
         self.free_contacts = torch.zeros((rows, 2, 3), dtype=f64, device=d) if compact else None
         self.n_free = torch.zeros((1,), dtype=i64, device=d) if compact else None
         self.rows = rows
+        # optional raw destinations for the compaction outputs ('free_gs', 'free_contacts', 'n_free' -> address): a peer
+        # GPU's buffer (distributed.PeerGather) or mapped pinned host memory (evaluate_host); the kernel stores there directly
+        self.redirect = {}
 
     def buffers(self, sample_surface, generate_dirs, generate_frame_vecs):
         b = nat.PipelineBuffers()
@@ -234,7 +239,7 @@ class PipelineWorkspace:
                      'pair_offset', 'pair_ref', 'pair_q', 'gs', 'contacts', 'n_grasps', 'colliding', 'free_gs',
                      'free_contacts', 'n_free'):
             t = getattr(self, name)
-            setattr(b, name, None if t is None else t.data_ptr())
+            setattr(b, name, None if t is None else int(self.redirect.get(name) or t.data_ptr()))
         b.sample_surface, b.generate_dirs, b.generate_frame_vecs = int(sample_surface), int(generate_dirs), int(generate_frame_vecs)
         b.cap_pairs = self.cap_pairs
         return b

@@ -9,7 +9,14 @@ broadcast) and holds the full query set; there is NO collective inside the compu
   * coverage: all-reduce(SUM) of one int64 covered-count per rank (+ optional gather of the mask).
 
 All helpers work with any backend (NCCL over NVLink on the B200 box, gloo on CPU for the host-logic tests).
+
+``PeerGather`` is the B200 form of the AGS exchange: the destination rank owns one buffer with a slot per rank, the
+others map it through CUDA IPC, and every rank's compaction kernel stores its kept rows straight into its slot over
+NVLink while it runs (``bt_compact`` / ``bt_ags_pipeline`` write to whatever address they are given).  What is left for
+NCCL is one 8-byte-per-rank ``all_gather`` of the counts, which is also the completion barrier.
 """
+import ctypes as C
+
 import numpy as np
 
 
@@ -82,3 +89,111 @@ def sharded_candidates(ref_points, ref_normals, evaluate_fn, dst=0, group=None, 
     if rank != dst:
         return None, None
     return all_rows.cpu().numpy(), all_contacts.cpu().numpy()
+
+
+class _DeviceArray:
+    """``__cuda_array_interface__`` wrapper so torch can view memory that libburgb200 allocated (bt_peer_alloc)."""
+
+    def __init__(self, address, shape, typestr):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(address), False),
+                                         'version': 2, 'strides': None}
+
+
+class PeerGather:
+    """Gather of the compacted grasp rows (and contacts) to ``dst`` WITHOUT a payload collective.
+
+    ``dst`` allocates ``[world, cap_rows, 14] float32`` (+ ``[world, cap_rows, 2, 3] float64``) with ``bt_peer_alloc``; the
+    IPC handle is broadcast once; every rank passes ``destinations()`` to ``AntipodalGraspSampler.run_pipeline`` so that
+    its ``compact_scatter_kernel`` writes slot ``rank`` directly (peer stores over NVLink / NVSwitch; local stores on
+    ``dst`` itself).  ``complete(n_free)`` all-gathers the per-rank counts: each rank's contribution is enqueued behind
+    its scatter kernel, so when the collective has finished on ``dst`` every slot is complete.  Rank order = candidate
+    order, so ``result()`` equals the single-GPU output on the same candidates."""
+
+    def __init__(self, cap_rows, with_contacts=True, device=None, dst=0, group=None):
+        import torch
+        from . import _native as nat
+        dist = _dist()
+        self.group, self.dst = group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap_rows, self.with_contacts = int(cap_rows), bool(with_contacts)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._nat = nat
+        gs_bytes = self.world * self.cap_rows * 56
+        total = gs_bytes + (self.world * self.cap_rows * 48 if with_contacts else 0)
+        base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self.owner = self.rank == dst
+        error = None
+        try:
+            if self.owner:
+                nat.call('bt_peer_alloc', self.device, total, C.byref(base), handle)
+        except nat.NativeError as ex:
+            error = str(ex)
+        box = [bytes(handle) if self.owner and error is None else None]
+        dist.broadcast_object_list(box, src=dst, group=group)
+        try:
+            if not self.owner and box[0] is not None:
+                handle = (C.c_ubyte * 64).from_buffer_copy(box[0])
+                nat.call('bt_peer_open', self.device, handle, C.byref(base))
+        except nat.NativeError as ex:
+            error = str(ex)
+        errors = [None] * self.world                      # every rank takes the same decision
+        dist.all_gather_object(errors, error if (error or box[0] is not None) else 'owner could not allocate', group=group)
+        if any(errors):
+            if base.value:
+                nat.call('bt_peer_free' if self.owner else 'bt_peer_close', self.device, base)
+            raise nat.NativeError('PeerGather: no peer mapping (%s)' % '; '.join(f'rank {r}: {e}' for r, e in enumerate(errors) if e))
+        self.base = int(base.value)
+        self.gs_ptr = self.base + self.rank * self.cap_rows * 56
+        self.contacts_ptr = self.base + gs_bytes + self.rank * self.cap_rows * 48 if with_contacts else None
+        self.counts = torch.zeros((self.world,), dtype=torch.int64, device=f'cuda:{self.device}')
+        self.rows = self.contacts = None
+        if self.owner:
+            dev = f'cuda:{self.device}'
+            self.rows = torch.as_tensor(_DeviceArray(self.base, (self.world, self.cap_rows, 14), '<f4'), device=dev)
+            if with_contacts:
+                self.contacts = torch.as_tensor(_DeviceArray(self.base + gs_bytes, (self.world, self.cap_rows, 2, 3), '<f8'), device=dev)
+
+    def destinations(self):
+        """``run_pipeline(destinations=...)``: where this rank's compaction stores its output"""
+        d = {'free_gs': self.gs_ptr}
+        if self.with_contacts:
+            d['free_contacts'] = self.contacts_ptr
+        return d
+
+    def complete(self, n_free):
+        """enqueue the count exchange behind the scatter kernel of the current stream (-> counts [world] on every rank)"""
+        import torch
+        dist = _dist()
+        if dist.get_backend(self.group) == 'nccl':
+            dist.all_gather_into_tensor(self.counts, n_free.reshape(1), group=self.group)
+        else:                           # host-side backends (the single-GPU two-process test): order by a stream wait
+            torch.cuda.current_stream().synchronize()
+            parts = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+            dist.all_gather(parts, n_free.reshape(1).cpu(), group=self.group)
+            self.counts.copy_(torch.cat(parts))
+        return self.counts
+
+    def result(self):
+        """on ``dst``: (rows [sum n_r, 14], contacts [sum n_r, 2, 3] or None) in rank order; (None, None) elsewhere"""
+        import torch
+        if not self.owner:
+            return None, None
+        counts = [int(c) for c in self.counts.cpu().tolist()]
+        rows = torch.cat([self.rows[r, :c] for r, c in enumerate(counts)], dim=0)
+        contacts = torch.cat([self.contacts[r, :c] for r, c in enumerate(counts)], dim=0) if self.with_contacts else None
+        return rows, contacts
+
+    def close(self):
+        import torch
+        if not self.base:
+            return
+        torch.cuda.synchronize(self.device)
+        self.rows = self.contacts = None
+        _dist().barrier(group=self.group)                     # nobody is still storing into the buffer
+        if self.owner:
+            _dist().barrier(group=self.group)                 # the peers have unmapped it
+            self._nat.call('bt_peer_free', self.device, C.c_void_p(self.base))
+        else:
+            self._nat.call('bt_peer_close', self.device, C.c_void_p(self.base))
+            _dist().barrier(group=self.group)
+        self.base = 0

@@ -253,7 +253,7 @@ class AntipodalGraspSampler:
 
     def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, directions=None, frame_vecs=None,
                      check_collisions=True, collision_width_tolerance=0.01, use_width=True, additional_objects=None,
-                     exclude_shape=False, compact=True, timer=None):
+                     exclude_shape=False, compact=True, timer=None, destinations=None):
         """The whole device pipeline for one batch of candidates in ONE C-ABI call (``bt_ags_pipeline``); nothing
         leaves the GPU and the host never waits:
 
@@ -263,6 +263,9 @@ class AntipodalGraspSampler:
         ``ref_points`` / ``ref_normals``: [n_ref, 3] numpy arrays or CUDA tensors; if None, ``n_ref`` points are
         drawn on the device (S1).  ``directions`` / ``frame_vecs``: host-seeded inputs for parity runs, else device
         RNG keyed by ``seed``.  Candidates evaluated = n_ref * n_rays.  ``timer``: optional ``device.StageTimer``.
+        ``destinations``: optional raw addresses for the compaction outputs (``{'free_gs': .., 'free_contacts': ..,
+        'n_free': ..}``) -- a peer GPU's slot (``distributed.PeerGather``) or mapped pinned host memory; the scatter
+        kernel stores there directly and the workspace tensors of those names are then NOT written.
         -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
         torch = nat.require_cuda()
         device = self._device()
@@ -278,29 +281,37 @@ class AntipodalGraspSampler:
         if ws is None or ws.key != key:
             ws = self._workspace = dev.PipelineWorkspace(*key)
         with torch.cuda.device(device):
-            if ref_points is not None:
-                ws.ref_pts.copy_(self._tensor(ref_points, torch.float64).reshape(-1, 3), non_blocking=True)
-                if ref_normals is not None:
-                    ws.ref_nrm.copy_(self._tensor(ref_normals, torch.float64).reshape(-1, 3), non_blocking=True)
-            if directions is not None:
-                ws.dirs.copy_(self._tensor(directions, torch.float64).reshape(n_ref, -1, 3), non_blocking=True)
-            if frame_vecs is not None:
-                ws.frame_vecs.copy_(self._tensor(frame_vecs, torch.float64).reshape(-1, 3), non_blocking=True)
-            cfg = nat.PipelineConfig()
-            cfg.ags = self._params(cap)
-            cfg.n_rays, cfg.n_orientations, cfg.max_targets = int(self.n_rays), n_o, k
-            cfg.halfspace = 1 if self.only_grasp_from_above else 0
-            cfg.check_collisions, cfg.use_width = int(bool(check_collisions)), int(bool(use_width))
-            cfg.compact = int(bool(check_collisions and compact))
-            cfg.collision_width_tolerance = float(collision_width_tolerance)
-            cos_t, sin_t = _orientation_tables(n_o, cfg.halfspace)
-            cfg.orient_cos[:n_o] = cos_t.tolist()
-            cfg.orient_sin[:n_o] = sin_t.tolist()
+            # inputs go straight into the workspace (one copy each; a pinned host tensor becomes one asynchronous H2D)
+            for buf, src, shape in ((ws.ref_pts, ref_points, (-1, 3)), (ws.ref_nrm, ref_normals if ref_points is not None else None, (-1, 3)),
+                                    (ws.dirs, directions, (n_ref, -1, 3)), (ws.frame_vecs, frame_vecs, (-1, 3))):
+                if src is not None:
+                    if not isinstance(src, torch.Tensor):
+                        src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))
+                    buf.copy_(src.reshape(shape), non_blocking=True)
+            sig = (float(self.mu), float(self.gripper.opening_width) if self.gripper is not None else None, float(self.width_tolerance),
+                   float(self.min_grasp_width), self.no_contact_below_z, cap, int(self.n_rays), n_o, k, bool(self.only_grasp_from_above),
+                   bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance))
+            cached = getattr(ws, 'config_cache', None)
+            if cached is not None and cached[0] == sig:
+                cfg = cached[1]
+            else:
+                cfg = nat.PipelineConfig()
+                cfg.ags = self._params(cap)
+                cfg.n_rays, cfg.n_orientations, cfg.max_targets = int(self.n_rays), n_o, k
+                cfg.halfspace = 1 if self.only_grasp_from_above else 0
+                cfg.check_collisions, cfg.use_width = int(bool(check_collisions)), int(bool(use_width))
+                cfg.compact = int(bool(check_collisions and compact))
+                cfg.collision_width_tolerance = float(collision_width_tolerance)
+                cos_t, sin_t = _orientation_tables(n_o, cfg.halfspace)
+                cfg.orient_cos[:n_o] = cos_t.tolist()
+                cfg.orient_sin[:n_o] = sin_t.tolist()
+                ws.config_cache = (sig, cfg)
             scene = gripper = None
             if check_collisions:
                 meshes = ([] if exclude_shape else [self.mesh]) + list(additional_objects or [])
                 scene = self._scene(meshes, device)
                 gripper = self._device_gripper(device)
+            ws.redirect = dict(destinations or {})
             bufs = ws.buffers(ref_points is None, directions is None, frame_vecs is None)
             nat.call('bt_ags_pipeline', dm.handle, None if scene is None else scene.handle,
                      None if gripper is None else gripper.handle, C.byref(cfg), C.byref(bufs), n_ref, int(seed),
@@ -313,37 +324,49 @@ class AntipodalGraspSampler:
             out['colliding'] = ws.colliding[:ws.rows]
             if compact:
                 out.update(free_gs=ws.free_gs, free_contacts=ws.free_contacts, n_free=ws.n_free)
+                for name in ws.redirect:                                  # stored elsewhere: the workspace copy is stale
+                    out[name] = None
         return out
 
     def evaluate_host(self, ref_points, ref_normals, seed=1, pinned=None, **kwargs):
         """End-to-end call with HOST buffers: uploads the reference points / normals, runs ``run_pipeline`` and
         returns host results (GraspSet of collision-free grasps, contacts, counts).  ``pinned``: optional dict of
-        reusable pinned staging tensors (created on first use)."""
+        reusable pinned staging tensors (created on first use).
+
+        With the collision stage on, there is no separate device-to-host copy: the pinned result buffers are mapped
+        into the device's address space (every ``cudaHostAlloc`` block is, under unified addressing) and the compaction
+        kernel stores the kept rows, their contacts and the count straight into them over PCIe -- exactly the rows that
+        survive, no count read-back before sizing a copy, one host wait per call."""
         torch = nat.require_cuda()
         device = self._device()
         pinned = {} if pinned is None else pinned
         n = len(ref_points)
+        cap = max(1, n * int(self.max_targets_per_ref_point)) * int(self.n_orientations)
+        push = bool(kwargs.get('check_collisions', True) and kwargs.get('compact', True))
         with torch.cuda.device(device):
             for key, arr in (('pts', ref_points), ('nrm', ref_normals)):
                 if key not in pinned or pinned[key].shape[0] != n:
                     pinned[key] = torch.empty((n, 3), dtype=torch.float64).pin_memory()
                 pinned[key].numpy()[...] = arr
-            pts = pinned['pts'].to(f'cuda:{device}', non_blocking=True)
-            nrm = pinned['nrm'].to(f'cuda:{device}', non_blocking=True)
-            out = self.run_pipeline(pts, nrm, seed=seed, **kwargs)
-            key_gs, key_c, key_n = ('free_gs', 'free_contacts', 'n_free') if 'free_gs' in out else ('gs', 'contacts', 'n_grasps')
-            cap = out[key_gs].shape[0]
             if 'out_gs' not in pinned or pinned['out_gs'].shape[0] != cap:
                 pinned['out_gs'] = torch.empty((cap, 14), dtype=torch.float32).pin_memory()
                 pinned['out_c'] = torch.empty((cap, 2, 3), dtype=torch.float64).pin_memory()
-                pinned['out_n'] = torch.empty((2,), dtype=torch.int64).pin_memory()
-            pinned['out_n'][0:1].copy_(out[key_n], non_blocking=True)
+                pinned['out_n'] = torch.zeros((2,), dtype=torch.int64).pin_memory()
+            pts, nrm = pinned['pts'], pinned['nrm']               # run_pipeline uploads them into its workspace (async H2D)
+            dest = {'free_gs': pinned['out_gs'].data_ptr(), 'free_contacts': pinned['out_c'].data_ptr(),
+                    'n_free': pinned['out_n'].data_ptr()} if push else None
+            out = self.run_pipeline(pts, nrm, seed=seed, destinations=dest, **kwargs)
             pinned['out_n'][1:2].copy_(out['n_grasps'], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            k = int(pinned['out_n'][0])                    # read the count, then copy exactly that many rows
-            pinned['out_gs'][:k].copy_(out[key_gs][:k], non_blocking=True)
-            pinned['out_c'][:k].copy_(out[key_c][:k], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            if push:
+                torch.cuda.current_stream().synchronize()
+                k = int(pinned['out_n'][0])
+            else:
+                pinned['out_n'][0:1].copy_(out['n_grasps'], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                k = int(pinned['out_n'][0])                # read the count, then copy exactly that many rows
+                pinned['out_gs'][:k].copy_(out['gs'][:k], non_blocking=True)
+                pinned['out_c'][:k].copy_(out['contacts'][:k], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         h2d = 2 * n * 24
         d2h = k * (56 + 48) + 16
         return dict(gs=GraspSet.from_array(pinned['out_gs'][:k].numpy()), contacts=pinned['out_c'][:k].numpy(),

@@ -196,6 +196,21 @@ BT_API int bt_mesh_pair_collide(const bt_mesh* a, const bt_mesh* b, int32_t* d_f
 BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
                int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
                void* stream);
+/* The outputs of bt_compact (and free_gs / free_contacts / n_free of bt_ags_pipeline) may be ANY memory the device can
+ * store to: local HBM, a peer GPU's buffer mapped with bt_peer_open (the multi-GPU gather of SURVEY 8e: the kept rows
+ * travel over NVLink while the scatter kernel runs, no collective afterwards), or mapped pinned host memory (the
+ * device-to-host copy of the end-to-end call).  The kernel emits each block's run as consecutive aligned 8-byte words. */
+
+/* ---- peer-visible buffers for the gather to rank 0 (one process per GPU, so the mapping crosses processes: CUDA IPC).
+ * bt_peer_alloc: plain cudaMalloc block of `bytes` (zeroed) on `device` + its 64-byte IPC handle; the handle travels
+ * through any host channel (torch.distributed broadcast).  bt_peer_open maps it into another process on that process's
+ * `device` (peer access enabled lazily); bt_peer_close / bt_peer_free undo them.  All four synchronise. */
+#define BT_IPC_HANDLE_BYTES 64
+typedef struct bt_ipc_handle { unsigned char bytes[BT_IPC_HANDLE_BYTES]; } bt_ipc_handle;
+BT_API int bt_peer_alloc(int device, int64_t bytes, void** d_ptr, bt_ipc_handle* handle);
+BT_API int bt_peer_open(int device, const bt_ipc_handle* handle, void** d_ptr);
+BT_API int bt_peer_close(int device, void* d_ptr);
+BT_API int bt_peer_free(int device, void* d_ptr);
 
 /* ---- the whole AGS pipeline in ONE call (what AntipodalGraspSampler.sample's loop body + check_collisions do
  * per batch, sampling.py:220-350 and :354-397): [S1] -> [S2] -> R1..R6 -> R7 -> [frame vectors] -> O1/O2 ->
