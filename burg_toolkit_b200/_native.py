@@ -45,7 +45,7 @@ STAGE_NAMES = ('sample_surface', 'cone_rays', 'cast', 'select', 'frame_vectors',
 class PipelineConfig(C.Structure):
     _fields_ = [('ags', AgsParams), ('n_rays', C.c_int32), ('n_orientations', C.c_int32), ('max_targets', C.c_int32),
                 ('halfspace', C.c_int32), ('check_collisions', C.c_int32), ('use_width', C.c_int32),
-                ('compact', C.c_int32), ('reserved', C.c_int32), ('collision_width_tolerance', C.c_double),
+                ('compact', C.c_int32), ('tail_splits', C.c_int32), ('collision_width_tolerance', C.c_double),
                 ('orient_cos', C.c_double * 64), ('orient_sin', C.c_double * 64)]
 
 
@@ -56,7 +56,8 @@ class PipelineBuffers(C.Structure):
                 ('hit_count', C.c_void_p), ('valid_mask', C.c_void_p), ('hits', C.c_void_p), ('overflow', C.c_void_p), ('pair_count', C.c_void_p),
                 ('pair_offset', C.c_void_p), ('pair_ref', C.c_void_p), ('pair_q', C.c_void_p), ('cap_pairs', C.c_int64),
                 ('gs', C.c_void_p), ('contacts', C.c_void_p), ('n_grasps', C.c_void_p), ('colliding', C.c_void_p),
-                ('free_gs', C.c_void_p), ('free_contacts', C.c_void_p), ('n_free', C.c_void_p)]
+                ('free_gs', C.c_void_p), ('free_contacts', C.c_void_p), ('n_free', C.c_void_p),
+                ('free_base', C.c_void_p), ('compact_after', C.c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -89,7 +90,7 @@ _SIGNATURES = {
     'bt_gripper_create': (C.c_int, [_P, C.c_int32, C.POINTER(GripperPart), C.c_int32, C.c_int, C.POINTER(_P)]),
     'bt_gripper_destroy': (C.c_int, [_P]),
     'bt_collide': (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P, _P]),
-    'bt_compact': (C.c_int, [_P, C.c_uint8, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    'bt_compact': (C.c_int, [_P, C.c_uint8, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     'bt_peer_alloc': (C.c_int, [C.c_int, C.c_int64, C.POINTER(_P), _P]),
     'bt_peer_open': (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     'bt_peer_close': (C.c_int, [C.c_int, _P]),

@@ -611,7 +611,8 @@ __global__ void compact_count_kernel(const uint8_t* __restrict__ mask, uint8_t k
 __global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
                                        const int64_t* __restrict__ d_n, const int64_t* __restrict__ block_offset,
                                        int64_t n_blocks, const float* __restrict__ gs, const double* __restrict__ contacts,
-                                       float* __restrict__ out_gs, double* __restrict__ out_contacts, int64_t* __restrict__ n_out) {
+                                       float* __restrict__ out_gs, double* __restrict__ out_contacts, int64_t* __restrict__ n_out,
+                                       const int64_t* __restrict__ d_base) {
     __shared__ int warp_off[CB / 32];
     __shared__ int run_s;
     __shared__ uint16_t src_of[CB];
@@ -634,13 +635,13 @@ __global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __re
 #pragma unroll
         for (int q = 0; q < CB / 32; ++q) { int c = warp_off[q]; warp_off[q] = run; run += c; }
         run_s = run;
-        if (blockIdx.x == n_blocks - 1 && n_out) *n_out = block_offset[blockIdx.x] + run;
+        if (blockIdx.x == n_blocks - 1 && n_out) *n_out = block_offset[blockIdx.x] + run + (d_base ? *d_base : 0);
     }
     __syncthreads();
     if (k) src_of[warp_off[w] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
     __syncthreads();
     const int run = run_s;
-    const int64_t dst0 = block_offset[blockIdx.x];
+    const int64_t dst0 = block_offset[blockIdx.x] + (d_base ? *d_base : 0);      // appending behind an earlier batch's rows
     {
         double* dst = reinterpret_cast<double*>(out_gs) + 7 * dst0;
         for (int e = threadIdx.x; e < run * 7; e += CB) { const int r = e / 7; dst[e] = tile[7 * src_of[r] + (e - 7 * r)]; }
@@ -843,12 +844,17 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
 
 extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
                           int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
-                          void* stream) {
+                          const int64_t* d_base, void* stream) {
     BT_REQUIRE(d_mask && d_gs && d_out_gs && d_n_out, "null pointer");
     BT_REQUIRE(n >= 0, "negative count");
     BT_REQUIRE(((reinterpret_cast<uintptr_t>(d_gs) | reinterpret_cast<uintptr_t>(d_out_gs)) & 7) == 0, "grasp rows must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { BT_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), st)); return BT_OK; }
+    BT_REQUIRE(d_base != d_n_out, "d_base and d_n_out must be different addresses");
+    if (n == 0) {
+        if (d_base) BT_CUDA(cudaMemcpyAsync(d_n_out, d_base, sizeof(int64_t), cudaMemcpyDefault, st));
+        else BT_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), st));
+        return BT_OK;
+    }
     const int64_t n_blocks = ceil_div(n, CB);
     Scratch counts, offsets, tmp;
     BT_CUDA(counts.alloc(sizeof(int32_t) * n_blocks, st));
@@ -860,7 +866,7 @@ extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float
     BT_CUDA(tmp.alloc(tmp_bytes, st));
     BT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
     compact_scatter_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, offsets.as<int64_t>(), n_blocks,
-                                                              d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out);
+                                                              d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out, d_base);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

@@ -5,6 +5,8 @@
 // copied to or from the host and no stage waits for the CPU.
 #include "common.cuh"
 
+#include <algorithm>
+
 struct bt_timer {
     int device = 0;
     cudaEvent_t ev[BT_N_STAGES + 1][2];
@@ -14,6 +16,35 @@ struct bt_timer {
 namespace bt {
 __global__ void scale_count_kernel(const int64_t* __restrict__ n_pairs, int n_o, int64_t* __restrict__ n_rows) {
     *n_rows = *n_pairs * n_o;
+}
+// number of valid rows inside the range [row0, row0 + n_cap) of a list whose valid length is *d_n
+__global__ void range_count_kernel(const int64_t* __restrict__ d_n, int64_t row0, int64_t n_cap, int64_t* __restrict__ out) {
+    const int64_t v = *d_n - row0;
+    *out = v < 0 ? 0 : (v > n_cap ? n_cap : v);
+}
+
+// Side stream, events and counters of the split tail (cfg->tail_splits > 1): the posed grasps are cut into row ranges and
+// range s+1 is collision-checked on the other stream while range s is being compacted -- which matters when the
+// compaction stores over PCIe (mapped host memory) or NVLink and is bound by the link, not by the SMs.
+struct TailState {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr};
+    int64_t* counts = nullptr;            // [2 * BT_MAX_TAIL_SPLITS]: running kept-row counts, then valid rows per range
+};
+constexpr int BT_MAX_TAIL_SPLITS = 8;
+static TailState g_tail[64];
+
+static int tail_state(int device, TailState** out) {
+    BT_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    TailState& t = g_tail[device];
+    if (!t.side) {
+        BT_CUDA(cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking));
+        BT_CUDA(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) BT_CUDA(cudaEventCreateWithFlags(&t.done[k], cudaEventDisableTiming));
+        BT_CUDA(cudaMalloc(&t.counts, sizeof(int64_t) * 2 * BT_MAX_TAIL_SPLITS));
+    }
+    *out = &t;
+    return BT_OK;
 }
 }  // namespace bt
 
@@ -106,15 +137,46 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     STAGE_END(5);
     if (cfg->check_collisions) {
         const int64_t cap_rows = b->cap_pairs * n_o;
-        STAGE_BEGIN(6);
-        STAGE_CALL(bt_collide(scene, gripper, b->gs, cap_rows, b->n_grasps, cfg->ags.opening_width,
-                              cfg->collision_width_tolerance, cfg->use_width, b->colliding, stream));
-        STAGE_END(6);
-        if (cfg->compact) {
-            STAGE_BEGIN(7);
-            STAGE_CALL(bt_compact(b->colliding, 0, b->gs, b->contacts, cap_rows, b->n_grasps, b->free_gs,
-                                  b->contacts ? b->free_contacts : nullptr, b->n_free, stream));
-            STAGE_END(7);
+        const int splits = (cfg->compact && !timer) ? std::min(std::max(cfg->tail_splits, 1), BT_MAX_TAIL_SPLITS) : 1;
+        const int64_t rows_per = ceil_div(ceil_div(cap_rows, splits), 256) * 256;      // ranges start on compaction-block boundaries
+        if (splits == 1 || rows_per >= cap_rows) {
+            STAGE_BEGIN(6);
+            STAGE_CALL(bt_collide(scene, gripper, b->gs, cap_rows, b->n_grasps, cfg->ags.opening_width,
+                                  cfg->collision_width_tolerance, cfg->use_width, b->colliding, stream));
+            STAGE_END(6);
+            if (cfg->compact) {
+                if (b->compact_after) BT_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)b->compact_after, 0));
+                STAGE_BEGIN(7);
+                STAGE_CALL(bt_compact(b->colliding, 0, b->gs, b->contacts, cap_rows, b->n_grasps, b->free_gs,
+                                      b->contacts ? b->free_contacts : nullptr, b->n_free, b->free_base, stream));
+                STAGE_END(7);
+            }
+        } else {
+            // split tail: collide(range s+1) on one stream overlaps compact(range s) on the other; every compaction appends
+            // behind the previous range's rows (device-side running count), so the output is the same contiguous list
+            TailState* t = nullptr;
+            STAGE_CALL(tail_state(target->m.device, &t));
+            BT_CUDA(cudaEventRecord(t->ready, st));
+            BT_CUDA(cudaStreamWaitEvent(t->side, t->ready, 0));
+            int last = 0;
+            for (int s = 0; s * rows_per < cap_rows; ++s) {
+                const int64_t r0 = s * rows_per, n_s = std::min(rows_per, cap_rows - r0);
+                cudaStream_t x = (s & 1) ? t->side : st;
+                int64_t* range_n = t->counts + BT_MAX_TAIL_SPLITS + s;
+                const bool final_range = (s + 1) * rows_per >= cap_rows;
+                range_count_kernel<<<1, 1, 0, x>>>(b->n_grasps, r0, n_s, range_n);
+                BT_LAUNCH_CHECK();
+                STAGE_CALL(bt_collide(scene, gripper, b->gs + 14 * r0, n_s, range_n, cfg->ags.opening_width,
+                                      cfg->collision_width_tolerance, cfg->use_width, b->colliding + r0, x));
+                if (s > 0) BT_CUDA(cudaStreamWaitEvent(x, t->done[(s - 1) & 1], 0));
+                else if (b->compact_after) BT_CUDA(cudaStreamWaitEvent(x, (cudaEvent_t)b->compact_after, 0));
+                STAGE_CALL(bt_compact(b->colliding + r0, 0, b->gs + 14 * r0, b->contacts ? b->contacts + 6 * r0 : nullptr, n_s, range_n,
+                                      b->free_gs, b->contacts ? b->free_contacts : nullptr, final_range ? b->n_free : t->counts + s,
+                                      s > 0 ? t->counts + s - 1 : b->free_base, x));
+                BT_CUDA(cudaEventRecord(t->done[s & 1], x));
+                last = s;
+            }
+            if (last & 1) BT_CUDA(cudaStreamWaitEvent(st, t->done[1], 0));      // the caller's stream owns the result again
         }
     }
     return BT_OK;

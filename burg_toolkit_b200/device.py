@@ -240,6 +240,7 @@ class PipelineWorkspace:
                      'free_contacts', 'n_free'):
             t = getattr(self, name)
             setattr(b, name, None if t is None else int(self.redirect.get(name) or t.data_ptr()))
+        b.free_base, b.compact_after = self.redirect.get('free_base'), self.redirect.get('compact_after')
         b.sample_surface, b.generate_dirs, b.generate_frame_vecs = int(sample_surface), int(generate_dirs), int(generate_frame_vecs)
         b.cap_pairs = self.cap_pairs
         return b

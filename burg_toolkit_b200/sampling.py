@@ -253,7 +253,7 @@ class AntipodalGraspSampler:
 
     def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, directions=None, frame_vecs=None,
                      check_collisions=True, collision_width_tolerance=0.01, use_width=True, additional_objects=None,
-                     exclude_shape=False, compact=True, timer=None, destinations=None):
+                     exclude_shape=False, compact=True, timer=None, destinations=None, slot=0, tail_splits=1):
         """The whole device pipeline for one batch of candidates in ONE C-ABI call (``bt_ags_pipeline``); nothing
         leaves the GPU and the host never waits:
 
@@ -265,7 +265,12 @@ class AntipodalGraspSampler:
         RNG keyed by ``seed``.  Candidates evaluated = n_ref * n_rays.  ``timer``: optional ``device.StageTimer``.
         ``destinations``: optional raw addresses for the compaction outputs (``{'free_gs': .., 'free_contacts': ..,
         'n_free': ..}``) -- a peer GPU's slot (``distributed.PeerGather``) or mapped pinned host memory; the scatter
-        kernel stores there directly and the workspace tensors of those names are then NOT written.
+        kernel stores there directly and the workspace tensors of those names are then NOT written.  Two more keys chain
+        batches on the device: ``'free_base'`` (address of an int64 = rows already at the destination; this batch's rows are
+        appended behind them) and ``'compact_after'`` (a CUDA event handle the compaction stage waits for).
+        ``slot``: which cached workspace to use (batches in flight on different streams need different ones).
+        ``tail_splits`` > 1: collision check + compaction run over that many row ranges on two streams, so a link-bound
+        compaction (host / peer destination) overlaps the next range's collision walk; the output is identical.
         -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
         torch = nat.require_cuda()
         device = self._device()
@@ -277,9 +282,10 @@ class AntipodalGraspSampler:
         if not 1 <= n_o <= 64:
             raise ValueError('n_orientations must be in [1, 64]')
         key = (n_ref, int(self.n_rays), cap, n_o, k, device, bool(check_collisions), bool(check_collisions and compact))
-        ws = getattr(self, '_workspace', None)
+        spaces = self.__dict__.setdefault('_workspaces', {})
+        ws = spaces.get(slot)
         if ws is None or ws.key != key:
-            ws = self._workspace = dev.PipelineWorkspace(*key)
+            ws = spaces[slot] = dev.PipelineWorkspace(*key)
         with torch.cuda.device(device):
             # inputs go straight into the workspace (one copy each; a pinned host tensor becomes one asynchronous H2D)
             for buf, src, shape in ((ws.ref_pts, ref_points, (-1, 3)), (ws.ref_nrm, ref_normals if ref_points is not None else None, (-1, 3)),
@@ -290,7 +296,7 @@ class AntipodalGraspSampler:
                     buf.copy_(src.reshape(shape), non_blocking=True)
             sig = (float(self.mu), float(self.gripper.opening_width) if self.gripper is not None else None, float(self.width_tolerance),
                    float(self.min_grasp_width), self.no_contact_below_z, cap, int(self.n_rays), n_o, k, bool(self.only_grasp_from_above),
-                   bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance))
+                   bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance), int(tail_splits))
             cached = getattr(ws, 'config_cache', None)
             if cached is not None and cached[0] == sig:
                 cfg = cached[1]
@@ -302,6 +308,7 @@ class AntipodalGraspSampler:
                 cfg.check_collisions, cfg.use_width = int(bool(check_collisions)), int(bool(use_width))
                 cfg.compact = int(bool(check_collisions and compact))
                 cfg.collision_width_tolerance = float(collision_width_tolerance)
+                cfg.tail_splits = int(tail_splits)
                 cos_t, sin_t = _orientation_tables(n_o, cfg.halfspace)
                 cfg.orient_cos[:n_o] = cos_t.tolist()
                 cfg.orient_sin[:n_o] = sin_t.tolist()
@@ -324,11 +331,12 @@ class AntipodalGraspSampler:
             out['colliding'] = ws.colliding[:ws.rows]
             if compact:
                 out.update(free_gs=ws.free_gs, free_contacts=ws.free_contacts, n_free=ws.n_free)
-                for name in ws.redirect:                                  # stored elsewhere: the workspace copy is stale
-                    out[name] = None
+                for name in ('free_gs', 'free_contacts', 'n_free'):       # stored elsewhere: the workspace copy is stale
+                    if name in ws.redirect:
+                        out[name] = None
         return out
 
-    def evaluate_host(self, ref_points, ref_normals, seed=1, pinned=None, **kwargs):
+    def evaluate_host(self, ref_points, ref_normals, seed=1, pinned=None, chunks=None, **kwargs):
         """End-to-end call with HOST buffers: uploads the reference points / normals, runs ``run_pipeline`` and
         returns host results (GraspSet of collision-free grasps, contacts, counts).  ``pinned``: optional dict of
         reusable pinned staging tensors (created on first use).
@@ -336,13 +344,29 @@ class AntipodalGraspSampler:
         With the collision stage on, there is no separate device-to-host copy: the pinned result buffers are mapped
         into the device's address space (every ``cudaHostAlloc`` block is, under unified addressing) and the compaction
         kernel stores the kept rows, their contacts and the count straight into them over PCIe -- exactly the rows that
-        survive, no count read-back before sizing a copy, one host wait per call."""
+        survive, no count read-back before sizing a copy, one host wait per call.
+
+        Two ways of overlapping those PCIe stores (0.25 ms for 11.4 MB at config 3) with compute exist and are tested for
+        identical output, but both measured SLOWER on B200 and are therefore off by default: ``tail_splits`` > 1 (collision
+        check + compaction over row ranges on two streams inside ``bt_ags_pipeline``: 1.40 / 1.46 / 1.66 ms at 1 / 2 / 4
+        ranges -- the fixed cost of a collision launch exceeds what the overlap returns) and
+
+        ``chunks`` > 1, which splits the REFERENCE POINTS into batches on two alternating streams (whole pipelines
+        overlap; each compaction appends behind the previous batch's rows through a device-side running count): 1.41 /
+        1.47 / 1.75 ms at 1 / 2 / 4 chunks (the ~20 launches per batch cost more host time than the overlap wins).  Both
+        are kept for callers with far larger batches.  The device RNG streams are keyed per batch, so for ``seed != 0`` the
+        random draws (not their distribution) depend on ``chunks``."""
         torch = nat.require_cuda()
         device = self._device()
         pinned = {} if pinned is None else pinned
         n = len(ref_points)
         cap = max(1, n * int(self.max_targets_per_ref_point)) * int(self.n_orientations)
         push = bool(kwargs.get('check_collisions', True) and kwargs.get('compact', True))
+        chunks = int(chunks or 1)
+        kwargs.setdefault('tail_splits', int(getattr(self, 'host_tail_splits', 1)))
+        chunks = max(1, min(chunks, n // 256, 64)) if push else 1
+        while n % chunks:                                   # equal batches only (one workspace shape per stream)
+            chunks -= 1
         with torch.cuda.device(device):
             for key, arr in (('pts', ref_points), ('nrm', ref_normals)):
                 if key not in pinned or pinned[key].shape[0] != n:
@@ -351,26 +375,56 @@ class AntipodalGraspSampler:
             if 'out_gs' not in pinned or pinned['out_gs'].shape[0] != cap:
                 pinned['out_gs'] = torch.empty((cap, 14), dtype=torch.float32).pin_memory()
                 pinned['out_c'] = torch.empty((cap, 2, 3), dtype=torch.float64).pin_memory()
-                pinned['out_n'] = torch.zeros((2,), dtype=torch.int64).pin_memory()
+                pinned['out_n'] = torch.zeros((66,), dtype=torch.int64).pin_memory()      # [0] kept rows, [1] spare, [2 + c] posed grasps of batch c
             pts, nrm = pinned['pts'], pinned['nrm']               # run_pipeline uploads them into its workspace (async H2D)
+            out_n = pinned['out_n']
             dest = {'free_gs': pinned['out_gs'].data_ptr(), 'free_contacts': pinned['out_c'].data_ptr(),
-                    'n_free': pinned['out_n'].data_ptr()} if push else None
-            out = self.run_pipeline(pts, nrm, seed=seed, destinations=dest, **kwargs)
-            pinned['out_n'][1:2].copy_(out['n_grasps'], non_blocking=True)
-            if push:
-                torch.cuda.current_stream().synchronize()
-                k = int(pinned['out_n'][0])
+                    'n_free': out_n.data_ptr()} if push else None
+            main = torch.cuda.current_stream()
+            if chunks == 1:
+                out = self.run_pipeline(pts, nrm, seed=seed, destinations=dest, **kwargs)
+                out_n[2:3].copy_(out['n_grasps'], non_blocking=True)
+                n_candidates = out['n_candidates']
             else:
-                pinned['out_n'][0:1].copy_(out['n_grasps'], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                k = int(pinned['out_n'][0])                # read the count, then copy exactly that many rows
+                side = self.__dict__.setdefault('_host_streams', {}).setdefault(device, [torch.cuda.Stream(device), torch.cuda.Stream(device)])
+                events = self.__dict__.setdefault('_host_events', [torch.cuda.Event() for _ in range(2)])
+                counts = self.__dict__.setdefault('_host_counts', {}).setdefault(device, torch.zeros((2,), dtype=torch.int64, device=f'cuda:{device}'))
+                sliced = {k: kwargs.pop(k) for k in ('directions', 'frame_vecs') if k in kwargs}
+                n_candidates = 0
+                for c in range(chunks):
+                    b, e = (n * c) // chunks, (n * (c + 1)) // chunks
+                    st = side[c & 1]
+                    if c < 2:
+                        st.wait_stream(main)
+                    last = c == chunks - 1
+                    d = dict(dest)
+                    d['n_free'] = out_n.data_ptr() if last else counts[c & 1:].data_ptr()      # the running count stays on the device until the last batch
+                    if c > 0:
+                        d['free_base'] = counts[(c - 1) & 1:].data_ptr()
+                        d['compact_after'] = events[(c - 1) & 1].cuda_event
+                    with torch.cuda.stream(st):
+                        out = self.run_pipeline(pts[b:e], nrm[b:e], seed=seed if seed == 0 else seed + 0x10000 * c, destinations=d, slot=1 + (c & 1),
+                                                **{k: (None if v is None else v[b:e]) for k, v in sliced.items()}, **kwargs)
+                        out_n[2 + c:3 + c].copy_(out['n_grasps'], non_blocking=True)
+                        events[c & 1].record(st)
+                    n_candidates += out['n_candidates']
+                main.wait_stream(side[0])
+                main.wait_stream(side[1])
+            if push:
+                main.synchronize()
+                k = int(out_n[0])
+            else:
+                out_n[0:1].copy_(out['n_grasps'], non_blocking=True)
+                main.synchronize()
+                k = int(out_n[0])                          # read the count, then copy exactly that many rows
                 pinned['out_gs'][:k].copy_(out['gs'][:k], non_blocking=True)
                 pinned['out_c'][:k].copy_(out['contacts'][:k], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                main.synchronize()
         h2d = 2 * n * 24
-        d2h = k * (56 + 48) + 16
+        d2h = k * (56 + 48) + 8 * (1 + chunks)
         return dict(gs=GraspSet.from_array(pinned['out_gs'][:k].numpy()), contacts=pinned['out_c'][:k].numpy(),
-                    n_grasps=int(pinned['out_n'][1]), n_free=k, h2d_bytes=h2d, d2h_bytes=d2h, n_candidates=out['n_candidates'])
+                    n_grasps=int(out_n[2:2 + chunks].sum()), n_free=k, h2d_bytes=h2d, d2h_bytes=d2h, n_candidates=n_candidates,
+                    chunks=chunks)
 
     # -----------------------------------------------------------------------------------------------
     # reference API
@@ -539,7 +593,7 @@ def compact_rows(mask, keep_value, rows, contacts=None, n_valid=None):
         out_contacts = None if contacts is None else torch.empty_like(contacts)
         count = torch.zeros((1,), dtype=torch.int64, device=rows.device)
         nat.call('bt_compact', nat.ptr(mask), int(keep_value), nat.ptr(rows), nat.ptr(contacts), n, nat.ptr(n_valid),
-                 nat.ptr(out_rows), nat.ptr(out_contacts), nat.ptr(count), nat.current_stream())
+                 nat.ptr(out_rows), nat.ptr(out_contacts), nat.ptr(count), None, nat.current_stream())
     return out_rows, out_contacts, count
 
 

@@ -192,10 +192,12 @@ BT_API int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const flo
 BT_API int bt_mesh_pair_collide(const bt_mesh* a, const bt_mesh* b, int32_t* d_flag, void* stream);
 
 /* ---- stream compaction of the surviving grasps: keeps rows with mask[i] == keep_value.
- *   d_out_gs [n,14], d_out_contacts [n,2,3] (may be NULL with d_contacts), d_n_out [1] i64 */
+ *   d_out_gs [n,14], d_out_contacts [n,2,3] (may be NULL with d_contacts), d_n_out [1] i64
+ *   d_base (nullable, [1] i64 on the device): number of rows ALREADY in the outputs -- the kept rows are appended
+ *   behind them and d_n_out becomes *d_base + kept (batches of one call chained on the device, no host round trip) */
 BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
                int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
-               void* stream);
+               const int64_t* d_base, void* stream);
 /* The outputs of bt_compact (and free_gs / free_contacts / n_free of bt_ags_pipeline) may be ANY memory the device can
  * store to: local HBM, a peer GPU's buffer mapped with bt_peer_open (the multi-GPU gather of SURVEY 8e: the kept rows
  * travel over NVLink while the scatter kernel runs, no collective afterwards), or mapped pinned host memory (the
@@ -227,7 +229,10 @@ BT_API int bt_timer_read(bt_timer* timer, float* h_stage_ms /* [BT_N_STAGES], -1
 typedef struct bt_pipeline_config {
     bt_ags_params ags;
     int32_t n_rays, n_orientations, max_targets, halfspace;
-    int32_t check_collisions, use_width, compact, reserved;
+    int32_t check_collisions, use_width, compact;
+    int32_t tail_splits;     /* > 1: collide + compact run over that many row ranges on two streams, so that the compaction of
+                                one range (link-bound when it stores to mapped host / peer memory) overlaps the collision
+                                walk of the next; same output, bit for bit.  0 / 1 = off.  Max 8.                       */
     double  collision_width_tolerance;
     double  orient_cos[64], orient_sin[64];   /* numpy-evaluated cos/sin of the orientation angles */
 } bt_pipeline_config;
@@ -254,6 +259,9 @@ typedef struct bt_pipeline_buffers {
     float*   free_gs;        /* [cap rows,14]             (compact)                          */
     double*  free_contacts;  /* [cap rows,2,3]            (compact)                          */
     int64_t* n_free;         /* [1]                       (compact)                          */
+    const int64_t* free_base; /* nullable [1]: rows already in free_gs / free_contacts (see bt_compact d_base)  */
+    void*    compact_after;  /* nullable cudaEvent_t: the compaction stage waits for it (the previous batch's
+                                compaction on another stream, whose count is free_base)                       */
 } bt_pipeline_buffers;
 
 BT_API int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, const bt_gripper* gripper,

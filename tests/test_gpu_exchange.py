@@ -41,6 +41,21 @@ def test_evaluate_host_equals_device_pipeline():
         assert np.array_equal(res['gs']._gs_array, rows)
         assert np.array_equal(res['contacts'], contacts)
         assert res['d2h_bytes'] == len(rows) * 104 + 16
+    # collide + compact over row ranges on two streams: same bytes, same order
+    for splits in (1, 2, 3, 8):
+        res = ags.evaluate_host(pts, nrm, seed=0, pinned=pinned, tail_splits=splits, directions=dirs, frame_vecs=fv)
+        assert res['n_free'] == len(rows) and res['n_grasps'] == n_grasps
+        assert np.array_equal(res['gs']._gs_array, rows) and np.array_equal(res['contacts'], contacts)
+    out = ags.run_pipeline(pts, nrm, directions=dirs, frame_vecs=fv, seed=0, tail_splits=4)          # device-resident destination
+    k = int(out['n_free'].item())
+    assert k == len(rows) and np.array_equal(out['free_gs'][:k].cpu().numpy(), rows)
+    assert np.array_equal(out['free_contacts'][:k].cpu().numpy(), contacts)
+    assert np.array_equal(out['colliding'][:n_grasps].cpu().numpy().astype(bool).sum(), n_grasps - len(rows))
+    # batches on two streams, each compaction appended behind the previous one's rows: same bytes, same order
+    for chunks in (2, 3, 5):
+        res = ags.evaluate_host(pts, nrm, seed=0, pinned=pinned, chunks=chunks, directions=dirs, frame_vecs=fv)
+        assert res['chunks'] == chunks and res['n_free'] == len(rows) and res['n_grasps'] == n_grasps
+        assert np.array_equal(res['gs']._gs_array, rows) and np.array_equal(res['contacts'], contacts)
     # without the collision stage the rows come back through plain copies
     res = ags.evaluate_host(pts, nrm, seed=0, directions=dirs, frame_vecs=fv, check_collisions=False)
     assert res['n_free'] == n_grasps
@@ -60,7 +75,7 @@ def test_compact_to_mapped_host_memory_ragged():
         for frac in (0.0, 0.5, 1.0):
             mask = torch.from_numpy((rng.random(n) < frac).astype(np.uint8)).cuda()
             nat.call('bt_compact', nat.ptr(mask), 0, nat.ptr(rows), nat.ptr(contacts), n, None, nat.ptr(out_rows),
-                     nat.ptr(out_contacts), nat.ptr(count), nat.current_stream())
+                     nat.ptr(out_contacts), nat.ptr(count), None, nat.current_stream())
             torch.cuda.synchronize()
             keep = ~mask.cpu().numpy().astype(bool)
             k = int(count[0])

@@ -23,28 +23,21 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-for mode in ('host', 'host+timer', 'device'):
+for chunks in (1, 2, 3, 4, 6, 8, 1, 2, 4):
     rec = []
-    for s in range(8):
+    for s in range(12):
         flush.fill_(s)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e0, e1 = ev(), ev()
         e0.record()
-        if mode.startswith('host'):
-            res = ags.evaluate_host(pts, nrm, seed=s + 1, pinned=pinned, **({'timer': timer} if 'timer' in mode else {}))
-        else:
-            out = ags.run_pipeline(pts, nrm, seed=s + 1)
-            t_enq = time.perf_counter()
-            torch.cuda.synchronize()
+        res = ags.evaluate_host(pts, nrm, seed=s + 1, pinned=pinned, tail_splits=chunks)
         e1.record()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        rec.append((e0.elapsed_time(e1), (t1 - t0) * 1e3, (t_enq - t0) * 1e3 if mode == 'device' else 0.0))
+        rec.append((e0.elapsed_time(e1), (t1 - t0) * 1e3))
     rec = np.array(rec[2:])
-    print(mode, 'event ms %.3f  wall ms %.3f  enqueue ms %.3f' % tuple(rec.mean(0)))
-    if 'timer' in mode:
-        print('   stages', {k: round(v, 4) for k, v in timer.read().items()})
+    print('tail_splits', chunks, 'event ms %.3f  wall ms %.3f' % tuple(rec.mean(0)), 'n_free', res['n_free'])
 
 # raw PCIe: DMA copy vs kernel stores of the same 11.4 MB
 n = 109_000
@@ -72,11 +65,3 @@ e1.record()
 torch.cuda.synchronize()
 print('H2D 480 KB %.4f ms' % (e0.elapsed_time(e1) / 10))
 
-import cProfile
-import pstats
-pr = cProfile.Profile()
-pr.enable()
-for s in range(50):
-    ags.evaluate_host(pts, nrm, seed=s + 1, pinned=pinned)
-pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(35)
