@@ -16,6 +16,8 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace bt {
 
 constexpr int COV_THREADS = 256;
@@ -284,8 +286,34 @@ constexpr int CELL_REFS = CELL_THREADS * CELL_RPT;
 constexpr int CELL_TILE = 1024;
 constexpr int CELL_QCAP = 2048;
 
+// Chunk table of the cell-tile kernel: the references in cell order are cut at every (x, y) column boundary and every
+// column into equal parts of at most CELL_REFS rows.  A chunk that straddled columns (as fixed 256-row chunks do) has a
+// bounding cell box spanning the whole z -- or y and z -- range: 4x .. 20x the work of a normal chunk, and those few
+// blocks decided the kernel's duration (simulated makespan 4.5x the balanced one at 1 M x 1 M).
+__global__ void column_bounds_kernel(const uint32_t* __restrict__ sorted_keys, int64_t n, uint32_t nz,
+                                     int32_t* __restrict__ col_start, int32_t* __restrict__ col_end) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = sorted_keys[i] / nz;
+    if (i == 0 || sorted_keys[i - 1] / nz != c) col_start[c] = (int32_t)i;
+    if (i == n - 1 || sorted_keys[i + 1] / nz != c) col_end[c] = (int32_t)i + 1;
+}
+
+__global__ void emit_chunks_kernel(const int32_t* __restrict__ col_start, const int32_t* __restrict__ col_end, int n_cols,
+                                   int chunk_rows, int2* __restrict__ chunks, int* __restrict__ n_chunks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const int b = col_start[c], e = col_end[c];
+    if (e <= b) return;
+    const int k = (e - b + chunk_rows - 1) / chunk_rows;
+    const int part = (e - b + k - 1) / k;                   // equal parts, not 256, 256, ..., remainder
+    const int pos = atomicAdd(n_chunks, k);                 // chunk order is irrelevant: every row owns its output flag
+    for (int j = 0; j < k; ++j) chunks[pos + j] = make_int2(b + j * part, min(e, b + (j + 1) * part));
+}
+
 __global__ void __launch_bounds__(CELL_THREADS)
-coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__ ref_sorted_ids, int64_t n_ref,
+coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__ ref_sorted_ids, const int2* __restrict__ chunks,
+                      const int* __restrict__ n_chunks,
                       const float* __restrict__ qry, const float4* __restrict__ q_sorted, const float4* __restrict__ q_quat_sorted,
                       const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_end, Grid g,
                       const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
@@ -296,7 +324,10 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
     __shared__ unsigned char s_cov[CELL_REFS];
     __shared__ int s_box[6];                               // min x y z, max x y z (cell coordinates of the chunk)
     __shared__ int q_count;
-    const int64_t s0 = (int64_t)blockIdx.x * CELL_REFS;
+    if ((int)blockIdx.x >= *n_chunks) return;               // the grid is the upper bound of the chunk count
+    const int2 chunk = chunks[blockIdx.x];
+    const int64_t s0 = chunk.x;
+    const int n_here = chunk.y - chunk.x;
     if (threadIdx.x < 3) { s_box[threadIdx.x] = 0x7fffffff; s_box[3 + threadIdx.x] = -1; }
     if (threadIdx.x == 0) q_count = 0;
     __syncthreads();
@@ -309,7 +340,7 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
         s_cov[lr] = 0;
         row[r] = -1;
         quat[r] = make_float4(0.f, 0.f, 0.f, 1.f);
-        if (s0 + lr < n_ref) {
+        if (lr < n_here) {
             row[r] = ref_sorted_ids[s0 + lr];
             px[r] = ref[14 * row[r]]; py[r] = ref[14 * row[r] + 1]; pz[r] = ref[14 * row[r] + 2];
             quat[r] = quat_of(ref + 14 * row[r] + 3);
@@ -370,18 +401,17 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
                     float4 qq[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) qq[u] = tile_quat[j0 + u];
-                    // slack[u] = max over the rows of (|q_row . q_u| - qmin_row): >= 0 iff some row passes the orientation bound
-                    float slack[4] = {-4.f, -4.f, -4.f, -4.f};
+                    // one compare-and-OR per pair (FSETP.GE.OR on |q_row . q_u|): true iff some pair passes the orientation bound
+                    bool any_pass = false;
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
                         for (int r = 0; r < CELL_RPT; ++r) {
                             const float qd = fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)));
-                            slack[u] = fmaxf(slack[u], fabsf(qd) - qmin[r]);
+                            any_pass |= fabsf(qd) >= qmin[r];
                         }
-                    const float any_slack = fmaxf(fmaxf(slack[0], slack[1]), fmaxf(slack[2], slack[3]));
                     unsigned pass = 0;
-                    if (any_slack >= 0.f) {
+                    if (any_pass) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -556,8 +586,11 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
     g.nz = (int)fminf(1024.f, floorf((hi[2] - lo[2]) / h) + 1.f);
     const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
     const bool dense = n_cells <= (1ll << 24);
-    // dense data (hundreds of queries per cell): block-per-chunk tiles; sparse data: warp-per-reference walk
-    const bool use_cells = dense && (double)n_qry / (double)n_cells >= 128.0;
+    // dense data (>= 16 queries per cell; measured at ~30 per cell: 0.79 -> 0.45 ms for 100k x 100k): block-per-chunk tiles;
+    // sparse data: warp-per-reference walk
+    static double cells_min = -1.0;                       // tuning knob (environment, read once): queries per cell from which the cell-tile kernel runs
+    if (cells_min < 0.0) { const char* e = getenv("BT_COVERAGE_CELLS_MIN"); cells_min = e ? atof(e) : 16.0; }
+    const bool use_cells = dense && (double)n_qry / (double)n_cells >= cells_min;
     int key_bits = 1;
     while ((1ll << key_bits) < n_cells) ++key_bits;
 
@@ -588,10 +621,21 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
                                                                           use_cells ? qq.as<float4>() : nullptr,
                                                                           dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr);
     BT_LAUNCH_CHECK();
-    if (use_cells)
-        coverage_cells_kernel<<<(unsigned)ceil_div(n_ref, CELL_REFS), CELL_THREADS, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(),
-                                                                                             qq.as<float4>(), cs.as<int32_t>(), ce.as<int32_t>(), g, lut, P, d_covered);
-    else
+    if (use_cells) {
+        const int n_cols = g.nx * g.ny;
+        const int64_t max_chunks = ceil_div(n_ref, CELL_REFS) + n_cols;
+        Scratch col_b, col_e, chunks, n_chunks;
+        BT_CUDA(col_b.alloc(sizeof(int32_t) * n_cols, st)); BT_CUDA(col_e.alloc(sizeof(int32_t) * n_cols, st));
+        BT_CUDA(chunks.alloc(sizeof(int2) * max_chunks, st)); BT_CUDA(n_chunks.alloc(sizeof(int), st));
+        BT_CUDA(cudaMemsetAsync(col_b.p, 0, sizeof(int32_t) * n_cols, st));
+        BT_CUDA(cudaMemsetAsync(col_e.p, 0, sizeof(int32_t) * n_cols, st));
+        BT_CUDA(cudaMemsetAsync(n_chunks.p, 0, sizeof(int), st));
+        column_bounds_kernel<<<(unsigned)ceil_div(n_ref, 256), 256, 0, st>>>(rkeys_s.as<uint32_t>(), n_ref, (uint32_t)g.nz, col_b.as<int32_t>(), col_e.as<int32_t>());
+        emit_chunks_kernel<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(col_b.as<int32_t>(), col_e.as<int32_t>(), n_cols, CELL_REFS, chunks.as<int2>(), n_chunks.as<int>());
+        BT_LAUNCH_CHECK();
+        coverage_cells_kernel<<<(unsigned)max_chunks, CELL_THREADS, 0, st>>>(d_ref, rids_s.as<int32_t>(), chunks.as<int2>(), n_chunks.as<int>(), d_qry, qs.as<float4>(),
+                                                                             qq.as<float4>(), cs.as<int32_t>(), ce.as<int32_t>(), g, lut, P, d_covered);
+    } else
         coverage_grid_kernel<<<(unsigned)ceil_div(n_ref * 32, 256), 256, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
                                                                                   (int)n_qry, dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr,
                                                                                   g, lut, P, d_covered);
