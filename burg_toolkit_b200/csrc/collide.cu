@@ -642,17 +642,28 @@ __global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __re
     __syncthreads();
     const int run = run_s;
     const int64_t dst0 = block_offset[blockIdx.x] + (d_base ? *d_base : 0);      // appending behind an earlier batch's rows
-    {
-        double* dst = reinterpret_cast<double*>(out_gs) + 7 * dst0;
-        for (int e = threadIdx.x; e < run * 7; e += CB) { const int r = e / 7; dst[e] = tile[7 * src_of[r] + (e - 7 * r)]; }
-    }
+    // the run leaves as 16-byte stores (one 8-byte word in front / behind where the run is not 16-byte aligned): a warp
+    // store covers 512 contiguous bytes, which is what a link (NVLink / PCIe) wants to see
+    auto stream_out = [&](double* dst, int words_per_row) {
+        const int n = run * words_per_row;
+        const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1u);
+        auto word = [&](int e) { const int r = e / words_per_row; return tile[words_per_row * src_of[r] + (e - words_per_row * r)]; };
+        if (n == 0) return;
+        if (threadIdx.x == 0 && head) dst[0] = word(0);
+        const int n_pairs = (n - head) >> 1;
+        for (int p2 = threadIdx.x; p2 < n_pairs; p2 += CB) {
+            const int e = head + 2 * p2;
+            *reinterpret_cast<double2*>(dst + e) = make_double2(word(e), word(e + 1));
+        }
+        if (threadIdx.x == 32 && ((n - head) & 1)) dst[n - 1] = word(n - 1);
+    };
+    stream_out(reinterpret_cast<double*>(out_gs) + 7 * dst0, 7);
     if (contacts && out_contacts) {
         __syncthreads();
         const double* src = contacts + 6 * row0;
         for (int e = threadIdx.x; e < rows_here * 6; e += CB) tile[e] = src[e];
         __syncthreads();
-        double* dst = out_contacts + 6 * dst0;
-        for (int e = threadIdx.x; e < run * 6; e += CB) { const int r = e / 6; dst[e] = tile[6 * src_of[r] + (e - 6 * r)]; }
+        stream_out(out_contacts + 6 * dst0, 6);
     }
 }
 

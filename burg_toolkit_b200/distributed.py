@@ -102,12 +102,17 @@ class _DeviceArray:
 class PeerGather:
     """Gather of the compacted grasp rows (and contacts) to ``dst`` WITHOUT a payload collective.
 
-    ``dst`` allocates ``[world, cap_rows, 14] float32`` (+ ``[world, cap_rows, 2, 3] float64``) with ``bt_peer_alloc``; the
-    IPC handle is broadcast once; every rank passes ``destinations()`` to ``AntipodalGraspSampler.run_pipeline`` so that
-    its ``compact_scatter_kernel`` writes slot ``rank`` directly (peer stores over NVLink / NVSwitch; local stores on
+    ``dst`` allocates ``[2, world, cap_rows, 14] float32`` (+ ``[2, world, cap_rows, 2, 3] float64``) with ``bt_peer_alloc``;
+    the IPC handle is broadcast once; every rank passes ``destinations()`` to ``AntipodalGraspSampler.run_pipeline`` so
+    that its ``compact_scatter_kernel`` writes slot ``rank`` directly (peer stores over NVLink / NVSwitch; local stores on
     ``dst`` itself).  ``complete(n_free)`` all-gathers the per-rank counts: each rank's contribution is enqueued behind
     its scatter kernel, so when the collective has finished on ``dst`` every slot is complete.  Rank order = candidate
-    order, so ``result()`` equals the single-GPU output on the same candidates."""
+    order, so ``result()`` equals the single-GPU output on the same candidates.
+
+    The slots are double-buffered by call parity: ``complete()`` flips the half that ``destinations()`` hands out, and
+    ``result()`` reads the half just completed.  A peer can only reach the compaction of call s+2 (same half as s) after
+    the count exchange of call s+1 has finished, and ``dst`` enqueues its contribution to that exchange behind its own
+    reads of call s -- so nobody overwrites rows that ``dst`` is still reading."""
 
     def __init__(self, cap_rows, with_contacts=True, device=None, dst=0, group=None):
         import torch
@@ -118,8 +123,8 @@ class PeerGather:
         self.cap_rows, self.with_contacts = int(cap_rows), bool(with_contacts)
         self.device = torch.cuda.current_device() if device is None else int(device)
         self._nat = nat
-        gs_bytes = self.world * self.cap_rows * 56
-        total = gs_bytes + (self.world * self.cap_rows * 48 if with_contacts else 0)
+        gs_bytes = 2 * self.world * self.cap_rows * 56
+        total = gs_bytes + (2 * self.world * self.cap_rows * 48 if with_contacts else 0)
         base, handle = C.c_void_p(), (C.c_ubyte * 64)()
         self.owner = self.rank == dst
         error = None
@@ -143,21 +148,22 @@ class PeerGather:
                 nat.call('bt_peer_free' if self.owner else 'bt_peer_close', self.device, base)
             raise nat.NativeError('PeerGather: no peer mapping (%s)' % '; '.join(f'rank {r}: {e}' for r, e in enumerate(errors) if e))
         self.base = int(base.value)
-        self.gs_ptr = self.base + self.rank * self.cap_rows * 56
-        self.contacts_ptr = self.base + gs_bytes + self.rank * self.cap_rows * 48 if with_contacts else None
+        self.gs_bytes = gs_bytes
+        self.half = 0                                     # which half the next run_pipeline writes
         self.counts = torch.zeros((self.world,), dtype=torch.int64, device=f'cuda:{self.device}')
         self.rows = self.contacts = None
         if self.owner:
             dev = f'cuda:{self.device}'
-            self.rows = torch.as_tensor(_DeviceArray(self.base, (self.world, self.cap_rows, 14), '<f4'), device=dev)
+            self.rows = torch.as_tensor(_DeviceArray(self.base, (2, self.world, self.cap_rows, 14), '<f4'), device=dev)
             if with_contacts:
-                self.contacts = torch.as_tensor(_DeviceArray(self.base + gs_bytes, (self.world, self.cap_rows, 2, 3), '<f8'), device=dev)
+                self.contacts = torch.as_tensor(_DeviceArray(self.base + gs_bytes, (2, self.world, self.cap_rows, 2, 3), '<f8'), device=dev)
 
     def destinations(self):
-        """``run_pipeline(destinations=...)``: where this rank's compaction stores its output"""
-        d = {'free_gs': self.gs_ptr}
+        """``run_pipeline(destinations=...)``: where this rank's compaction stores its output (current half, slot ``rank``)"""
+        slot = self.half * self.world + self.rank
+        d = {'free_gs': self.base + slot * self.cap_rows * 56}
         if self.with_contacts:
-            d['free_contacts'] = self.contacts_ptr
+            d['free_contacts'] = self.base + self.gs_bytes + slot * self.cap_rows * 48
         return d
 
     def complete(self, n_free):
@@ -171,6 +177,7 @@ class PeerGather:
             parts = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
             dist.all_gather(parts, n_free.reshape(1).cpu(), group=self.group)
             self.counts.copy_(torch.cat(parts))
+        self.done_half, self.half = self.half, self.half ^ 1
         return self.counts
 
     def result(self):
@@ -179,8 +186,9 @@ class PeerGather:
         if not self.owner:
             return None, None
         counts = [int(c) for c in self.counts.cpu().tolist()]
-        rows = torch.cat([self.rows[r, :c] for r, c in enumerate(counts)], dim=0)
-        contacts = torch.cat([self.contacts[r, :c] for r, c in enumerate(counts)], dim=0) if self.with_contacts else None
+        h = self.done_half
+        rows = torch.cat([self.rows[h, r, :c] for r, c in enumerate(counts)], dim=0)
+        contacts = torch.cat([self.contacts[h, r, :c] for r, c in enumerate(counts)], dim=0) if self.with_contacts else None
         return rows, contacts
 
     def close(self):
