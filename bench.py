@@ -596,8 +596,13 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None, r
         np.add.at(occ, tuple((cq + 1).T), 1)
         nb = sum(np.roll(occ, (dx, dy, dz), axis=(0, 1, 2)) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1))
         tested = float(nb[tuple((cr + 1).T)].sum())
-        roof_kernel, roof_ms = 'coverage_cells_kernel / coverage_grid_kernel (27-cell neighbourhood)', res['grid']['ms']
-    achieved_ops = tested / world * 4 / (roof_ms * 1e-3)            # per GPU (every rank tests 1/world of the pairs)
+        cells = len(qry) / float(np.prod(dims - 2)) >= 16.0         # the library's kernel choice (queries per cell)
+        roof_kernel = ('coverage_cells_kernel' if cells else 'coverage_grid_kernel') + ' (27-cell neighbourhood)'
+        roof_ms = res['grid']['ms']
+    # lane-ops per tested pair: 3 FFMA + 1 compare (translation reject first: tiles / grid kernels), 3 FFMA + 1 FMUL + 1 compare
+    # (orientation bound first: cell-tile kernel)
+    ops_per_pair = 5 if roof_kernel.startswith('coverage_cells') else 4
+    achieved_ops = tested / world * ops_per_pair / (roof_ms * 1e-3)            # per GPU (every rank tests 1/world of the pairs)
     out = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
            'ms_per_step': res['grid']['ms'],
            'config': {'workload': args.workload if not args.workload.startswith('ags') else 'coverage_c2', 'n_ref': len(ref_all), 'n_query': len(qry), 'epsilon': 15.0,
@@ -609,11 +614,12 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None, r
            'roofline': {'bound': 'fp32-issue', 'kernel': roof_kernel, 'achieved': achieved_ops / 1e12,
                         'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': achieved_ops / lane_ops,
                         'pairs_tested_per_launch': tested, 'traffic': None,
-                        'note': '4 FP32 lane-ops per tested pair (3 FFMA + 1 compare); value counts nominal N*M pairs, the roofline '
+                        'lane_ops_per_pair': ops_per_pair,
+                        'note': 'FP32 lane-ops per tested pair: 4 (3 FFMA + compare) or 5 (quaternion dot + compare, cell-tile kernel); value counts nominal N*M pairs, the roofline '
                                 'counts the pairs the kernel actually tests; HBM bytes are negligible'},
            'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes) * world,
                    'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac},
-           'gpu_launches': 8 * steps, 'clocks': clk}
+           'gpu_launches': (10 if roof_kernel.startswith('coverage_cells') else 8) * steps, 'clocks': clk}
     return out
 
 
