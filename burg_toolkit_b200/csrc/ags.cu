@@ -787,8 +787,9 @@ extern "C" int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, v
 extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
                            int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
                            uint32_t* d_valid_mask, int32_t* d_overflow, void* stream) {
-    BT_REQUIRE(mesh && d_ref_pts && d_dirs && params && d_hit_count && d_hits, "null pointer");
+    BT_REQUIRE(mesh && params, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
+    BT_REQUIRE(n_ref == 0 || (d_ref_pts && d_dirs && d_hit_count && d_hits), "null pointer");     // empty arrays may be NULL
     const int cap = params->max_hits_per_ray;
     BT_REQUIRE(cap >= 1 && cap <= 32, "max_hits_per_ray must be in [1, 32]");
     BT_CUDA(cudaSetDevice(mesh->m.device));

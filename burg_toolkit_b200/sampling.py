@@ -288,12 +288,15 @@ class AntipodalGraspSampler:
             ws = spaces[slot] = dev.PipelineWorkspace(*key)
         with torch.cuda.device(device):
             # inputs go straight into the workspace (one copy each; a pinned host tensor becomes one asynchronous H2D)
-            for buf, src, shape in ((ws.ref_pts, ref_points, (-1, 3)), (ws.ref_nrm, ref_normals if ref_points is not None else None, (-1, 3)),
-                                    (ws.dirs, directions, (n_ref, -1, 3)), (ws.frame_vecs, frame_vecs, (-1, 3))):
+            for buf, src, per_ref in ((ws.ref_pts, ref_points, 3), (ws.ref_nrm, ref_normals if ref_points is not None else None, 3),
+                                      (ws.dirs, directions, 3 * int(self.n_rays)), (ws.frame_vecs, frame_vecs, 3)):
                 if src is not None:
                     if not isinstance(src, torch.Tensor):
                         src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))
-                    buf.copy_(src.reshape(shape), non_blocking=True)
+                    if src.numel() != n_ref * per_ref:
+                        raise ValueError(f'expected {n_ref} x {per_ref} values, got {src.numel()}')
+                    if n_ref:                          # (the workspace buffers hold at least one row)
+                        buf.reshape(-1)[:n_ref * per_ref].copy_(src.reshape(-1), non_blocking=True)
             sig = (float(self.mu), float(self.gripper.opening_width) if self.gripper is not None else None, float(self.width_tolerance),
                    float(self.min_grasp_width), self.no_contact_below_z, cap, int(self.n_rays), n_o, k, bool(self.only_grasp_from_above),
                    bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance), int(tail_splits))
