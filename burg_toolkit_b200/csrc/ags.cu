@@ -31,6 +31,7 @@ struct MeshView {
     const int32_t* __restrict__ faces;
     const double* __restrict__ verts;
     const double* __restrict__ vnormals;
+    const double* __restrict__ tri_vvn;            // [nF,20] leaf order: v0 v1 v2 pad | n0 n1 n2 pad
 };
 
 __device__ __forceinline__ bool slab_hit(float bx0, float by0, float bz0, float bx1, float by1, float bz1,
@@ -83,18 +84,21 @@ __device__ __forceinline__ bool exact_ray_triangle(const double* __restrict__ re
     return hit;
 }
 
-// mesh_processing.compute_interpolated_vertex_normals for one point on triangle `tri`
-__device__ __forceinline__ d3 interpolated_normal(const MeshView& mv, int32_t tri, d3 p) {
-    const int32_t* fc = mv.faces + 3 * (int64_t)tri;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// mesh_processing.compute_interpolated_vertex_normals for one point on the triangle of `leaf`: the three vertices and
+// their normals come from one 160-byte leaf-order record (no faces -> vertices -> normals chain, 10 sector accesses not 19)
+__device__ __forceinline__ d3 interpolated_normal(const MeshView& mv, int32_t leaf, d3 p) {
+    const double2* r2 = reinterpret_cast<const double2*>(mv.tri_vvn + 20 * (int64_t)leaf);      // ten LDG.128, 160-byte aligned record
+    const double2 a0 = __ldg(r2 + 0), a1 = __ldg(r2 + 1), a2 = __ldg(r2 + 2), a3 = __ldg(r2 + 3), a4 = __ldg(r2 + 4);
+    const double2 b0 = __ldg(r2 + 5), b1 = __ldg(r2 + 6), b2 = __ldg(r2 + 7), b3 = __ldg(r2 + 8), b4 = __ldg(r2 + 9);
+    const d3 vert[3] = {mk3(a0.x, a0.y, a1.x), mk3(a1.y, a2.x, a2.y), mk3(a3.x, a3.y, a4.x)};
+    const d3 vn[3] = {mk3(b0.x, b0.y, b1.x), mk3(b1.y, b2.x, b2.y), mk3(b3.x, b3.y, b4.x)};
     double w[3];
-    d3 vn[3];
     int onehot = -1;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        int64_t v = fc[k];
-        d3 vert = ld3(mv.verts + 3 * v);
-        vn[k] = ld3(mv.vnormals + 3 * v);
-        double dist = norm3(sub3(vert, p));
+        double dist = norm3(sub3(vert[k], p));
         w[k] = 1.0 / sqrt(dist);
         if (dist == 0.0) onehot = k;             // later vertices win, like the reference's loop
     }
@@ -160,7 +164,6 @@ constexpr int TWARPS = 4;
 #define TRAV_PREFETCH 0
 #endif
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // near / far plane of one axis as 2^23 + q: selector 0x7610 takes the low half of the word, 0x7632 the high half
 __device__ __forceinline__ float plane16(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
@@ -316,32 +319,55 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
 #ifndef CAST_MINB
 #define CAST_MINB 6
 #endif
+#ifndef BT_RESOLVE_PREFETCH
+#define BT_RESOLVE_PREFETCH 0      // measured: no effect (0.600 vs 0.597 ms cast stage); the kernel is bound by sector throughput, not by the chain
+#endif
+#ifndef RSTAGE
+#define RSTAGE 2                    // hits per ray staged in shared memory (the usual ray has the origin's triangle + one far hit)
+#endif
 template <int CAP>
 __global__ void __launch_bounds__(128, CAST_MINB)
 cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
             int n_rays, bt_ags_params P, int cap, const int32_t* __restrict__ cand_count, const int32_t* __restrict__ cand,
             int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, uint32_t* __restrict__ valid_mask,
             int32_t* __restrict__ overflow) {
+    // 72-byte hit records written field by field by one thread per ray are 8-byte stores 576 bytes apart: 32 sectors per
+    // store instruction, 584 MB of sector traffic for 144 MB of records at config 3.  The first RSTAGE hits of every ray are
+    // staged per warp in shared memory instead and leave as whole records (9 consecutive lanes per record).
+    __shared__ double s_rec[4][32 * RSTAGE * 9 + 32];
+    const int64_t ray0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31);       // first ray of this warp
     int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (ray >= n_total) return;
+    const bool live = ray < n_total;
+    if (ray0 >= n_total) return;                                                       // the whole warp is past the end
+    if (!live) ray = n_total - 1;                  // lanes past the end shadow the last ray (no outputs), the warp stays whole
     const int64_t ref = ray / n_rays;
     int pend[NPEND];
     int n_pend = 0;
     bool over = false;
     double hit_t[CAP];
-    int32_t hit_tri[CAP];
+    int32_t hit_tri[CAP], hit_leaf[CAP];
     int n_hit = 0;
 
     // phase 2 (also used as an emergency flush when the parking list fills up): exact float64 tests
     auto run_exact = [&]() {
         const d3 o = ld3(ref_pts + 3 * ref);
         const d3 d = ld3(dirs + 3 * ray);
+#if BT_RESOLVE_PREFETCH
+        for (int i = 1; i < n_pend; ++i) prefetch_l1(mv.tri_rec + 16 * (int64_t)pend[i]);      // one 128-byte line per record
+#endif
         for (int i = 0; i < n_pend; ++i) {
             const int leaf = pend[i];
             const int32_t tri = __ldg(mv.leaf_tri + leaf);            // issued with the record loads, not after the test
             double t;
             if (exact_ray_triangle(mv.tri_rec + 16 * (int64_t)leaf, o, d, t)) {
-                if (n_hit < cap) { hit_t[n_hit] = t; hit_tri[n_hit] = tri; ++n_hit; }
+                if (n_hit < cap) {
+                    hit_t[n_hit] = t; hit_tri[n_hit] = tri; hit_leaf[n_hit] = leaf; ++n_hit;
+#if BT_RESOLVE_PREFETCH
+                    if (t > 1e-9) {             // not the origin's own triangle: its vertices and normals will be wanted by the filters
+                        prefetch_l1(mv.tri_vvn + 20 * (int64_t)leaf); prefetch_l1(mv.tri_vvn + 20 * (int64_t)leaf + 16);
+                    }
+#endif
+                }
                 else over = true;
             }
         }
@@ -399,12 +425,12 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
     // canonical order: (t, triangle id) ascending
     for (int i = 1; i < n_hit; ++i) {
         double t = hit_t[i];
-        int32_t tr = hit_tri[i];
+        int32_t tr = hit_tri[i], lf = hit_leaf[i];
         int j = i - 1;
         while (j >= 0 && (hit_t[j] > t || (hit_t[j] == t && hit_tri[j] > tr))) {
-            hit_t[j + 1] = hit_t[j]; hit_tri[j + 1] = hit_tri[j]; --j;
+            hit_t[j + 1] = hit_t[j]; hit_tri[j + 1] = hit_tri[j]; hit_leaf[j + 1] = hit_leaf[j]; --j;
         }
-        hit_t[j + 1] = t; hit_tri[j + 1] = tr;
+        hit_t[j + 1] = t; hit_tri[j + 1] = tr; hit_leaf[j + 1] = lf;
     }
 
     bt_hit* out = hits + ray * (int64_t)cap;
@@ -437,7 +463,7 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
                  !((dist <= P.opening_width - P.width_tolerance) | (dist >= P.min_grasp_width))) flags = BT_HIT_WIDTH;
         else {
             // sampling.py:259, :289-308
-            nrm = interpolated_normal(mv, tri, p);
+            nrm = interpolated_normal(mv, hit_leaf[i], p);
             const double dotp = dot3(dv, nrm);
             ang = atan(norm3(cross3(dv, nrm)) / dotp);
             if (!(dotp > 0.0)) flags = BT_HIT_SIGN;
@@ -449,8 +475,31 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         h.nrm[0] = nrm.x; h.nrm[1] = nrm.y; h.nrm[2] = nrm.z;
         h.t = t; h.angle = ang; h.tri = tri; h.flags = flags;
         if (flags == 0u) vmask |= 1u << n_out;
-        out[n_out++] = h;
+        if (n_out < RSTAGE) {
+            double* sr = s_rec[threadIdx.x >> 5] + ((threadIdx.x & 31) * RSTAGE + n_out) * 9;
+            sr[0] = p.x; sr[1] = p.y; sr[2] = p.z; sr[3] = nrm.x; sr[4] = nrm.y; sr[5] = nrm.z; sr[6] = t; sr[7] = ang;
+            sr[8] = __hiloint2double((int)flags, tri);                                 // tri in the low word, flags in the high word
+        } else if (live) {
+            out[n_out] = h;
+        }
+        ++n_out;
     }
+    {
+        const int lane = threadIdx.x & 31;
+        const double* sw = s_rec[threadIdx.x >> 5];
+        double* gw = reinterpret_cast<double*>(hits + ray0 * (int64_t)cap);
+        __syncwarp();                                                                  // the staged records are visible to the whole warp
+#pragma unroll
+        for (int k = 0; k < RSTAGE; ++k) {
+            const unsigned has = __ballot_sync(0xffffffffu, live && n_out > k);
+            if (!has) break;
+            for (int e = lane; e < 32 * 9; e += 32) {
+                const int r = e / 9, w = e - 9 * r;
+                if ((has >> r) & 1u) gw[((int64_t)r * cap + k) * 9 + w] = sw[(r * RSTAGE + k) * 9 + w];
+            }
+        }
+    }
+    if (!live) return;
     hit_count[ray] = n_out;
     if (valid_mask) valid_mask[ray] = vmask;
     if (over && overflow) atomicAdd(overflow, 1);
@@ -745,7 +794,7 @@ static MeshView view_of(const MeshDev& m) {
     v.wnodes = m.wnodes;
     for (int k = 0; k < 3; ++k) { v.gmin[k] = m.grid_min[k]; v.gscale[k] = m.grid_scale[k]; }
     v.tri_rec = m.tri_rec; v.tri_f32 = m.tri_f32; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
-    v.vnormals = m.vnormals;
+    v.vnormals = m.vnormals; v.tri_vvn = m.tri_vvn;
     return v;
 }
 

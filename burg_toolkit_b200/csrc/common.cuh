@@ -99,6 +99,8 @@ struct MeshDev {
     double   grid_min[3] = {0, 0, 0}, grid_scale[3] = {1, 1, 1};   // grid coordinate = (x - grid_min) * grid_scale
     double*  tri_rec = nullptr;    // [nF,16]  leaf order
     double*  tri_verts = nullptr;  // [nF,9]   leaf order
+    double*  tri_vvn = nullptr;    // [nF,20]  leaf order: v0 v1 v2 pad | n0 n1 n2 pad -- vertices + vertex normals of the leaf's triangle as
+                                   //          ten 16-byte words (normal interpolation without the faces -> vertices -> normals chain)
     float4*  tri_f32 = nullptr;    // [nF,3]   leaf order: (v0 | 0) (e0 | 0) (e1 | 0) for the float32 pre-test
     int32_t* leaf_tri = nullptr;   // [nF]     leaf -> caller's triangle id
     int32_t  root = 0;             // root child code (internal 0, or ~0 if single triangle)

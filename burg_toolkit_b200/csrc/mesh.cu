@@ -54,9 +54,9 @@ __global__ void morton_kernel(const double* __restrict__ verts, const int32_t* _
 }
 
 // per leaf (Morton order): exact-test records, f32 leaf boxes (rounded outward + pad), areas in caller order
-__global__ void leaf_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces,
+__global__ void leaf_kernel(const double* __restrict__ verts, const double* __restrict__ vnormals, const int32_t* __restrict__ faces,
                             const int32_t* __restrict__ sorted_ids, int64_t nF, float pad,
-                            double* __restrict__ tri_rec, double* __restrict__ tri_verts, float4* __restrict__ tri_f32,
+                            double* __restrict__ tri_rec, double* __restrict__ tri_verts, double* __restrict__ tri_vvn, float4* __restrict__ tri_f32,
                             int32_t* __restrict__ leaf_tri,
                             float* __restrict__ box_min, float* __restrict__ box_max, double* __restrict__ area) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -76,6 +76,10 @@ __global__ void leaf_kernel(const double* __restrict__ verts, const int32_t* __r
     r[12] = d00; r[13] = d01; r[14] = d11; r[15] = inv_den;
     double* tv = tri_verts + 9 * i;
     st3(tv + 0, v0); st3(tv + 3, v1); st3(tv + 6, v2);
+    double* tn = tri_vvn + 20 * i;
+    st3(tn + 0, v0); st3(tn + 3, v1); st3(tn + 6, v2); tn[9] = 0.0;
+    st3(tn + 10, ld3(vnormals + 3 * (int64_t)fc[0])); st3(tn + 13, ld3(vnormals + 3 * (int64_t)fc[1])); st3(tn + 16, ld3(vnormals + 3 * (int64_t)fc[2]));
+    tn[19] = 0.0;
     tri_f32[3 * i + 0] = make_float4((float)v0.x, (float)v0.y, (float)v0.z, 0.f);
     tri_f32[3 * i + 1] = make_float4((float)e0.x, (float)e0.y, (float)e0.z, 0.f);
     tri_f32[3 * i + 2] = make_float4((float)e1.x, (float)e1.y, (float)e1.z, 0.f);
@@ -332,7 +336,7 @@ extern "C" int bt_stream_sync(void* stream) {
 // ---- mesh ------------------------------------------------------------------------------------------
 static int mesh_free(MeshDev& m) {
     cudaFree(m.verts); cudaFree(m.vnormals); cudaFree(m.faces); cudaFree(m.area_cdf);
-    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.wnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
+    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.wnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_vvn); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
     m = MeshDev();
     return BT_OK;
 }
@@ -394,6 +398,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cudaMalloc(&m.wnodes, sizeof(uint4) * 4 * nNodes));
     MESH_TRY(cudaMalloc(&m.tri_rec, sizeof(double) * 16 * nF));
     MESH_TRY(cudaMalloc(&m.tri_verts, sizeof(double) * 9 * nF));
+    MESH_TRY(cudaMalloc(&m.tri_vvn, sizeof(double) * 20 * nF));
     MESH_TRY(cudaMalloc(&m.tri_f32, sizeof(float4) * 3 * nF));
     MESH_TRY(cudaMalloc(&m.leaf_tri, sizeof(int32_t) * nF));
     MESH_TRY(cudaMemcpy(m.verts, h_V, sizeof(double) * 3 * nV, cudaMemcpyHostToDevice));
@@ -452,7 +457,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
                                    make_double3(inv_ext[0], inv_ext[1], inv_ext[2]), keys, ids);
     MESH_TRY(cudaGetLastError());
     MESH_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, ids, ids_sorted, n, 0, 30, st));
-    leaf_kernel<<<G, T, 0, st>>>(m.verts, m.faces, ids_sorted, nF, pad, m.tri_rec, m.tri_verts, m.tri_f32, m.leaf_tri,
+    leaf_kernel<<<G, T, 0, st>>>(m.verts, m.vnormals, m.faces, ids_sorted, nF, pad, m.tri_rec, m.tri_verts, m.tri_vvn, m.tri_f32, m.leaf_tri,
                                  box_min, box_max, area);
     MESH_TRY(cudaGetLastError());
     if (nF > 1) {
@@ -515,7 +520,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     }
     m.root = 0;
     m.info.n_vertices = nV; m.info.n_triangles = nF; m.info.n_nodes = nNodes;
-    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 26 * nF) + sizeof(int32_t) * 4 * nF + 48 * nF + 160 * nNodes);
+    m.info.device_bytes = (int64_t)(sizeof(double) * (6 * nV + 46 * nF) + sizeof(int32_t) * 4 * nF + 48 * nF + 160 * nNodes);
     m.info.surface_area = total;
     m.info.build_ms = ms;
     for (int k = 0; k < 3; ++k) { m.info.bounds_min[k] = (float)lo[k]; m.info.bounds_max[k] = (float)hi[k]; }
