@@ -329,8 +329,10 @@ template <int CAP>
 __global__ void __launch_bounds__(128, CAST_MINB)
 cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
             int n_rays, bt_ags_params P, int cap, const int32_t* __restrict__ cand_count, const int32_t* __restrict__ cand,
-            int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, uint32_t* __restrict__ valid_mask,
+            int32_t* __restrict__ hit_count, bt_hit* __restrict__ hits, double* __restrict__ hit_tt, uint32_t* __restrict__ valid_mask,
             int32_t* __restrict__ overflow) {
+    // `hits` == NULL is the lean mode of bt_ags_pipeline: no records, only the ray parameter of every kept hit in the
+    // slot-major array hit_tt[h * n_total + ray] (coalesced 8-byte stores); the target choice rebuilds o + t d from it.
     // 72-byte hit records written field by field by one thread per ray are 8-byte stores 576 bytes apart: 32 sectors per
     // store instruction, 584 MB of sector traffic for 144 MB of records at config 3.  The first RSTAGE hits of every ray are
     // staged per warp in shared memory instead and leave as whole records (9 consecutive lanes per record).
@@ -475,7 +477,9 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         h.nrm[0] = nrm.x; h.nrm[1] = nrm.y; h.nrm[2] = nrm.z;
         h.t = t; h.angle = ang; h.tri = tri; h.flags = flags;
         if (flags == 0u) vmask |= 1u << n_out;
-        if (n_out < RSTAGE) {
+        if (!hits) {
+            if (live) hit_tt[(int64_t)n_out * n_total + ray] = t;
+        } else if (n_out < RSTAGE) {
             double* sr = s_rec[threadIdx.x >> 5] + ((threadIdx.x & 31) * RSTAGE + n_out) * 9;
             sr[0] = p.x; sr[1] = p.y; sr[2] = p.z; sr[3] = nrm.x; sr[4] = nrm.y; sr[5] = nrm.z; sr[6] = t; sr[7] = ang;
             sr[8] = __hiloint2double((int)flags, tri);                                 // tri in the low word, flags in the high word
@@ -484,7 +488,7 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         }
         ++n_out;
     }
-    {
+    if (hits) {
         const int lane = threadIdx.x & 31;
         const double* sw = s_rec[threadIdx.x >> 5];
         double* gw = reinterpret_cast<double*>(hits + ray0 * (int64_t)cap);
@@ -619,7 +623,16 @@ __global__ void select_count_kernel(const int32_t* __restrict__ hit_count, const
 
 __global__ void zero_first_kernel(int64_t* p) { *p = 0; }
 
-__global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits,
+// where the location of hit h of a ray comes from: its record, or (lean pipeline) o + t d with the stored ray parameter --
+// the same expression, on the same float64 inputs, as cast_kernel evaluates for the record
+struct HitSource { const double* hit_tt; const double* ref_pts; const double* dirs; int64_t n_total; };
+__device__ __forceinline__ d3 hit_location(const bt_hit* __restrict__ hits, const HitSource& hs, int64_t ref, int64_t ray, int h, int cap) {
+    if (hits) { const bt_hit* hp = hits + ray * cap + h; return mk3(hp->loc[0], hp->loc[1], hp->loc[2]); }
+    const double t = hs.hit_tt[(int64_t)h * hs.n_total + ray];
+    return add3(scl3(ld3(hs.dirs + 3 * ray), t), ld3(hs.ref_pts + 3 * ref));
+}
+
+__global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits, HitSource hs,
                                    const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
                                    const int64_t* __restrict__ pair_offset, int64_t cap_pairs,
                                    int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
@@ -654,13 +667,13 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
             int ord = run + incl - nv;
             for (; vm; vm &= vm - 1) {
                 const int h = __ffs(vm) - 1;
-                const bt_hit* hp = hits + ray * cap + h;
                 {
                     if (ord < n_take && base + ord < cap_pairs) {
+                        const d3 q = hit_location(hits, hs, ref, ray, h, cap);
                         pair_ref[base + ord] = (int32_t)ref;
-                        pair_q[3 * (base + ord) + 0] = hp->loc[0];
-                        pair_q[3 * (base + ord) + 1] = hp->loc[1];
-                        pair_q[3 * (base + ord) + 2] = hp->loc[2];
+                        pair_q[3 * (base + ord) + 0] = q.x;
+                        pair_q[3 * (base + ord) + 1] = q.y;
+                        pair_q[3 * (base + ord) + 2] = q.z;
                     }
                     ++ord;
                 }
@@ -709,11 +722,11 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
             if (ok < best_key || (ok == best_key && oo < best_ord)) { best_key = ok; best_ord = oo; best_slot = os; }
         }
         if (lane == 0 && best_slot >= 0 && base + pick < cap_pairs) {
-            const bt_hit* hp = hits + ref * n_rays * (int64_t)cap + best_slot;
+            const d3 q = hit_location(hits, hs, ref, ref * n_rays + best_slot / cap, best_slot % cap, cap);      // best_slot = r * cap + h
             pair_ref[base + pick] = (int32_t)ref;
-            pair_q[3 * (base + pick) + 0] = hp->loc[0];
-            pair_q[3 * (base + pick) + 1] = hp->loc[1];
-            pair_q[3 * (base + pick) + 2] = hp->loc[2];
+            pair_q[3 * (base + pick) + 0] = q.x;
+            pair_q[3 * (base + pick) + 1] = q.y;
+            pair_q[3 * (base + pick) + 2] = q.z;
         }
         prev_key = best_key;
         prev_ord = best_ord;
@@ -836,9 +849,17 @@ extern "C" int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, v
 extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
                            int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
                            uint32_t* d_valid_mask, int32_t* d_overflow, void* stream) {
+    BT_REQUIRE(n_ref == 0 || d_hits, "null pointer");
+    return bt::ags_cast_impl(mesh, d_ref_pts, d_dirs, n_ref, n_rays, params, d_hit_count, d_hits, nullptr, d_valid_mask, d_overflow, stream);
+}
+
+// d_hits == NULL: lean mode (bt_ags_pipeline without hit records), the ray parameters go to d_hit_t [cap, n_ref * n_rays]
+int bt::ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
+                      int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits, double* d_hit_t,
+                      uint32_t* d_valid_mask, int32_t* d_overflow, void* stream) {
     BT_REQUIRE(mesh && params, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
-    BT_REQUIRE(n_ref == 0 || (d_ref_pts && d_dirs && d_hit_count && d_hits), "null pointer");     // empty arrays may be NULL
+    BT_REQUIRE(n_ref == 0 || (d_ref_pts && d_dirs && d_hit_count && (d_hits || (d_hit_t && d_valid_mask))), "null pointer");     // empty arrays may be NULL
     const int cap = params->max_hits_per_ray;
     BT_REQUIRE(cap >= 1 && cap <= 32, "max_hits_per_ray must be in [1, 32]");
     BT_CUDA(cudaSetDevice(mesh->m.device));
@@ -870,11 +891,11 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
     BT_LAUNCH_CHECK();
     // stage 2: exact float64 narrow phase, ordering, de-duplication, filters, hit records
     if (cap <= 8)
-        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_valid_mask, d_overflow);
+        cast_kernel<8><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_hit_t, d_valid_mask, d_overflow);
     else if (cap <= 16)
-        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_valid_mask, d_overflow);
+        cast_kernel<16><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_hit_t, d_valid_mask, d_overflow);
     else
-        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_valid_mask, d_overflow);
+        cast_kernel<32><<<grid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, *params, cap, cc.as<int32_t>(), cl.as<int32_t>(), d_hit_count, d_hits, d_hit_t, d_valid_mask, d_overflow);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
@@ -883,8 +904,19 @@ extern "C" int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, c
                              int32_t cap, int32_t max_targets, uint64_t seed, int32_t* d_pair_count,
                              int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs,
                              void* stream) {
-    BT_REQUIRE(d_hit_count && d_hits && d_pair_count && d_pair_offset && d_pair_ref && d_pair_q, "null pointer");
+    BT_REQUIRE(d_hits, "null pointer");
+    return bt::ags_select_impl(d_hit_count, d_hits, nullptr, nullptr, nullptr, d_valid_mask, n_ref, n_rays, cap, max_targets, seed, d_pair_count,
+                               d_pair_offset, d_pair_ref, d_pair_q, cap_pairs, stream);
+}
+
+int bt::ags_select_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const double* d_hit_t, const double* d_ref_pts, const double* d_dirs,
+                        const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays, int32_t cap, int32_t max_targets, uint64_t seed,
+                        int32_t* d_pair_count, int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs,
+                        void* stream) {
+    BT_REQUIRE(d_hit_count && d_pair_count && d_pair_offset && d_pair_ref && d_pair_q, "null pointer");
+    BT_REQUIRE(d_hits || (d_hit_t && d_ref_pts && d_dirs && d_valid_mask), "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0 && cap >= 1 && max_targets >= 1, "bad counts");
+    HitSource hs{d_hit_t, d_ref_pts, d_dirs, n_ref * (int64_t)n_rays};
     cudaStream_t st = (cudaStream_t)stream;
     zero_first_kernel<<<1, 1, 0, st>>>(d_pair_offset);
     BT_LAUNCH_CHECK();
@@ -897,7 +929,7 @@ extern "C" int bt_ags_select(const int32_t* d_hit_count, const bt_hit* d_hits, c
     Scratch tmp;
     BT_CUDA(tmp.alloc(tmp_bytes, st));
     BT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
-    select_fill_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, d_valid_mask, n_ref, n_rays, cap, max_targets, seed,
+    select_fill_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, hs, d_valid_mask, n_ref, n_rays, cap, max_targets, seed,
                                              d_pair_offset, cap_pairs, d_pair_ref, d_pair_q);
     BT_LAUNCH_CHECK();
     return BT_OK;

@@ -107,6 +107,14 @@ struct MeshDev {
     bt_mesh_info info{};
 };
 
+// internal forms of bt_ags_cast / bt_ags_select with the lean hit representation of bt_ags_pipeline (ags.cu)
+int ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref, int32_t n_rays,
+                  const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits, double* d_hit_t, uint32_t* d_valid_mask,
+                  int32_t* d_overflow, void* stream);
+int ags_select_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const double* d_hit_t, const double* d_ref_pts, const double* d_dirs,
+                    const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays, int32_t cap, int32_t max_targets, uint64_t seed,
+                    int32_t* d_pair_count, int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs, void* stream);
+
 }  // namespace bt
 
 struct bt_mesh {

@@ -95,8 +95,9 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
                                uint64_t seed, bt_timer* timer, void* stream) {
     BT_REQUIRE(target && cfg && b, "null pointer");
     BT_REQUIRE(n_ref >= 0, "negative count");
-    BT_REQUIRE(b->ref_pts && b->dirs && b->hit_count && b->hits && b->overflow && b->pair_count && b->pair_offset &&
+    BT_REQUIRE(b->ref_pts && b->dirs && b->hit_count && b->overflow && b->pair_count && b->pair_offset &&
                b->pair_ref && b->pair_q && b->gs && b->n_grasps, "missing buffer");
+    BT_REQUIRE(b->hits || (b->hit_t && b->valid_mask), "either hit records or the lean pair (hit_t, valid_mask) is required");
     BT_REQUIRE(b->ref_nrm || (!b->sample_surface && !b->generate_dirs), "reference normals required to generate rays");
     BT_REQUIRE(cfg->halfspace || b->frame_vecs, "frame vector buffer required unless halfspace");
     BT_REQUIRE(b->cap_pairs >= n_ref * (int64_t)cfg->max_targets, "cap_pairs too small");
@@ -118,11 +119,13 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
         STAGE_END(1);
     }
     STAGE_BEGIN(2);
-    STAGE_CALL(bt_ags_cast(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->valid_mask, b->overflow, stream));
+    STAGE_CALL(ags_cast_impl(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->hits ? nullptr : b->hit_t,
+                             b->valid_mask, b->overflow, stream));
     STAGE_END(2);
     STAGE_BEGIN(3);
-    STAGE_CALL(bt_ags_select(b->hit_count, b->hits, b->valid_mask, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray, cfg->max_targets,
-                             seed ? seed + 0x2000 : 0 /* seed 0: first valid hit in canonical order */, b->pair_count, b->pair_offset, b->pair_ref, b->pair_q, b->cap_pairs, stream));
+    STAGE_CALL(ags_select_impl(b->hit_count, b->hits, b->hit_t, b->ref_pts, b->dirs, b->valid_mask, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray,
+                               cfg->max_targets, seed ? seed + 0x2000 : 0 /* seed 0: first valid hit in canonical order */, b->pair_count,
+                               b->pair_offset, b->pair_ref, b->pair_q, b->cap_pairs, stream));
     STAGE_END(3);
     if (b->generate_frame_vecs && !cfg->halfspace) {
         STAGE_BEGIN(4);

@@ -202,9 +202,9 @@ class StageTimer:
 class PipelineWorkspace:
     """All device buffers of one ``bt_ags_pipeline`` call, allocated once per shape (torch owns the memory)."""
 
-    def __init__(self, n_ref, n_rays, cap, n_orientations, max_targets, device, collisions, compact):
+    def __init__(self, n_ref, n_rays, cap, n_orientations, max_targets, device, collisions, compact, keep_hits=False):
         torch = nat.require_cuda()
-        self.key = (n_ref, n_rays, cap, n_orientations, max_targets, device, collisions, compact)
+        self.key = (n_ref, n_rays, cap, n_orientations, max_targets, device, collisions, compact, keep_hits)
         d = f'cuda:{device}'
         self.n_ref, self.cap_pairs = n_ref, max(1, n_ref * max_targets)
         rows = self.cap_pairs * n_orientations
@@ -215,7 +215,10 @@ class PipelineWorkspace:
         self.frame_vecs = torch.empty((max(n_ref, 1), 3), dtype=f64, device=d)
         self.hit_count = torch.empty((max(n_ref, 1) * n_rays,), dtype=i32, device=d)
         self.valid_mask = torch.empty((max(n_ref, 1) * n_rays,), dtype=i32, device=d)
-        self.hits = torch.empty((max(n_ref, 1) * n_rays * cap, 72), dtype=u8, device=d)
+        # hit records are an intermediate of the pipeline (72 B x cap per ray: 576 MB per million rays); unless the caller
+        # wants to look at them the caster keeps only the ray parameter of every kept hit (slot-major) + the valid-hit masks
+        self.hits = torch.empty((max(n_ref, 1) * n_rays * cap, 72), dtype=u8, device=d) if keep_hits else None
+        self.hit_t = None if keep_hits else torch.empty((cap, max(n_ref, 1) * n_rays), dtype=f64, device=d)
         self.overflow = torch.zeros((1,), dtype=i32, device=d)
         self.pair_count = torch.empty((max(n_ref, 1),), dtype=i32, device=d)
         self.pair_offset = torch.zeros((n_ref + 1,), dtype=i64, device=d)
@@ -235,7 +238,7 @@ class PipelineWorkspace:
 
     def buffers(self, sample_surface, generate_dirs, generate_frame_vecs):
         b = nat.PipelineBuffers()
-        for name in ('ref_pts', 'ref_nrm', 'dirs', 'frame_vecs', 'hit_count', 'valid_mask', 'hits', 'overflow', 'pair_count',
+        for name in ('ref_pts', 'ref_nrm', 'dirs', 'frame_vecs', 'hit_count', 'valid_mask', 'hits', 'hit_t', 'overflow', 'pair_count',
                      'pair_offset', 'pair_ref', 'pair_q', 'gs', 'contacts', 'n_grasps', 'colliding', 'free_gs',
                      'free_contacts', 'n_free'):
             t = getattr(self, name)

@@ -253,7 +253,7 @@ class AntipodalGraspSampler:
 
     def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, directions=None, frame_vecs=None,
                      check_collisions=True, collision_width_tolerance=0.01, use_width=True, additional_objects=None,
-                     exclude_shape=False, compact=True, timer=None, destinations=None, slot=0, tail_splits=1):
+                     exclude_shape=False, compact=True, timer=None, destinations=None, slot=0, tail_splits=1, keep_hits=False):
         """The whole device pipeline for one batch of candidates in ONE C-ABI call (``bt_ags_pipeline``); nothing
         leaves the GPU and the host never waits:
 
@@ -269,6 +269,10 @@ class AntipodalGraspSampler:
         batches on the device: ``'free_base'`` (address of an int64 = rows already at the destination; this batch's rows are
         appended behind them) and ``'compact_after'`` (a CUDA event handle the compaction stage waits for).
         ``slot``: which cached workspace to use (batches in flight on different streams need different ones).
+        ``keep_hits``: materialise the per-ray hit records (``out['cast']``, as ``cast()`` returns them).  They are an
+        intermediate of the path -- the reference's ``locations / index_ray / index_tri`` arrays -- and cost 144 MB of stores
+        per million rays, so by default the caster keeps only the valid-hit masks and the ray parameters, from which the
+        target choice rebuilds each contact with the caster's own expression (same bits).
         ``tail_splits`` > 1: collision check + compaction run over that many row ranges on two streams, so a link-bound
         compaction (host / peer destination) overlaps the next range's collision walk; the output is identical.
         -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
@@ -281,7 +285,7 @@ class AntipodalGraspSampler:
         n_o, k, cap = int(self.n_orientations), int(self.max_targets_per_ref_point), int(self.max_hits_per_ray)
         if not 1 <= n_o <= 64:
             raise ValueError('n_orientations must be in [1, 64]')
-        key = (n_ref, int(self.n_rays), cap, n_o, k, device, bool(check_collisions), bool(check_collisions and compact))
+        key = (n_ref, int(self.n_rays), cap, n_o, k, device, bool(check_collisions), bool(check_collisions and compact), bool(keep_hits))
         spaces = self.__dict__.setdefault('_workspaces', {})
         ws = spaces.get(slot)
         if ws is None or ws.key != key:
@@ -329,7 +333,8 @@ class AntipodalGraspSampler:
         out = dict(n_ref=n_ref, n_candidates=n_ref * int(self.n_rays), pair_count=ws.pair_count, pair_offset=ws.pair_offset,
                    pair_ref=ws.pair_ref, pair_q=ws.pair_q, gs=ws.gs, contacts=ws.contacts, n_grasps=ws.n_grasps,
                    overflow=ws.overflow, ref_pts=ws.ref_pts, ref_nrm=ws.ref_nrm, directions=ws.dirs,
-                   cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap, ws.valid_mask), cap_pairs=ws.cap_pairs)
+                   cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap, ws.valid_mask) if keep_hits else None,
+                   hit_count=ws.hit_count, valid_mask=ws.valid_mask, cap_pairs=ws.cap_pairs)
         if check_collisions:
             out['colliding'] = ws.colliding[:ws.rows]
             if compact:

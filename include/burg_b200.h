@@ -245,7 +245,10 @@ typedef struct bt_pipeline_buffers {
     int32_t  sample_surface, generate_dirs, generate_frame_vecs, reserved;
     int32_t* hit_count;      /* [n_ref*n_rays]                                               */
     uint32_t* valid_mask;    /* [n_ref*n_rays]                                               */
-    bt_hit*  hits;           /* [n_ref*n_rays*max_hits_per_ray]                              */
+    bt_hit*  hits;           /* [n_ref*n_rays*max_hits_per_ray], or NULL = lean mode: no hit records are
+                                materialised (they are an intermediate: 144 MB per million rays), the caster
+                                keeps only valid_mask and hit_t, from which the target choice rebuilds the
+                                contact o + t d with the caster's own expression                          */
     int32_t* overflow;       /* [1]                                                          */
     int32_t* pair_count;     /* [n_ref]                                                      */
     int64_t* pair_offset;    /* [n_ref+1]                                                    */
@@ -260,6 +263,7 @@ typedef struct bt_pipeline_buffers {
     double*  free_contacts;  /* [cap rows,2,3]            (compact)                          */
     int64_t* n_free;         /* [1]                       (compact)                          */
     const int64_t* free_base; /* nullable [1]: rows already in free_gs / free_contacts (see bt_compact d_base)  */
+    double*  hit_t;          /* [max_hits_per_ray, n_ref*n_rays] slot-major ray parameters (lean mode only)   */
     void*    compact_after;  /* nullable cudaEvent_t: the compaction stage waits for it (the previous batch's
                                 compaction on another stream, whose count is free_base)                       */
 } bt_pipeline_buffers;

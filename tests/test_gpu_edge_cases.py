@@ -119,3 +119,33 @@ def test_halfspace_and_multi_target_pipeline_at_batch_size():
     assert np.array_equal(coll[idx], cport.collide(cm, rows[idx], ags.gripper.tcp_triangles(), 0.08, 0.01))
     k = int(out['n_free'].item())
     assert k == (~coll).sum() and np.array_equal(out['free_gs'][:k].cpu().numpy(), rows[~coll])
+
+
+@pytest.mark.parametrize('seed,k', [(0, 1), (7, 1), (7, 3)])
+def test_lean_pipeline_equals_pipeline_with_hit_records(seed, k):
+    """by default the pipeline keeps no hit records (valid masks + ray parameters only); pairs, rows, contacts and masks
+    must be the bytes of the run that materialises them -- for the canonical choice and for seeded random subsets"""
+    from burg_toolkit_b200 import mesh as bmesh
+    from test_gpu_fullsize import host_candidates
+    mesh = bmesh.create_bumpy_sphere(64, 64, radius=0.035, amplitude=0.15, seed=2)
+    pts, nrm, dirs, fv = host_candidates(mesh, 700, 9)
+    ags = _sampler(mesh, max_targets_per_ref_point=k)
+    full = ags.run_pipeline(pts, nrm, directions=dirs, frame_vecs=fv, seed=seed, keep_hits=True)
+    assert full['cast'] is not None
+    want = {n: full[n].cpu().numpy().copy() for n in ('pair_count', 'pair_q', 'gs', 'contacts', 'colliding', 'n_grasps', 'n_free', 'free_gs')}
+    cnt, hits = full['cast'].to_host()
+    lean = ags.run_pipeline(pts, nrm, directions=dirs, frame_vecs=fv, seed=seed)
+    assert lean['cast'] is None
+    n, nf = int(want['n_grasps'][0]), int(want['n_free'][0])
+    assert n > 3000 and int(lean['n_grasps'].item()) == n and int(lean['n_free'].item()) == nf
+    n_pairs = n // 12
+    assert np.array_equal(lean['pair_count'].cpu().numpy(), want['pair_count'])
+    assert np.array_equal(lean['pair_q'].cpu().numpy()[:n_pairs], want['pair_q'][:n_pairs])
+    assert np.array_equal(lean['gs'].cpu().numpy()[:n], want['gs'][:n]) and np.array_equal(lean['contacts'].cpu().numpy()[:n], want['contacts'][:n])
+    assert np.array_equal(lean['colliding'].cpu().numpy()[:n], want['colliding'][:n])
+    assert np.array_equal(lean['free_gs'].cpu().numpy()[:nf], want['free_gs'][:nf])
+    assert np.array_equal(lean['hit_count'].cpu().numpy().reshape(cnt.shape), cnt)
+    sel = np.arange(hits.shape[2])[None, None, :] < cnt[:, :, None]
+    vm = lean['valid_mask'].cpu().numpy().reshape(cnt.shape)
+    want_vm = ((hits['flags'] == 0) & sel).astype(np.int64) @ (1 << np.arange(hits.shape[2]))
+    assert np.array_equal(vm.astype(np.int64), want_vm)

@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_ags.py tests/test_gpu_fullsize.py tests/test_gpu_edge_cases.py tests/test_gpu_scene.py -x -q -m gpu > gpurun_out/t20.log 2>&1
+python -m pytest tests -x -q -m gpu > gpurun_out/t20.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/t20.log
 for lib in libburgb200 libburgb200; do
   BT_LIB=/root/repo/burg_toolkit_b200/csrc/$lib.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
