@@ -401,7 +401,7 @@ def run_b200(args, rank, world, local_rank):
         cast_ms = stage_ms['cast']
         alg_bytes = N_REF * N_RAYS * 64 + 80 * info.n_triangles
         achieved = alg_bytes / (cast_ms * 1e-3) / 1e9
-        l2_bytes = cnt[0] * 64 + cnt[1] * 48 + cnt[2] * 128 + n_cand * (24 + 2 * 72)
+        l2_bytes = cnt[0] * 64 + cnt[1] * 48 + cnt[2] * 128 + n_cand * (24 + 48 + 2 * 8 + 8)
         prof = {}
         ppath = os.path.join(ROOT, 'profiles', 'roofline_inputs.json')
         if os.path.exists(ppath):
@@ -412,7 +412,7 @@ def run_b200(args, rank, world, local_rank):
                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': cast_ms,
                     'rays_per_s': N_REF * N_RAYS / (cast_ms * 1e-3),
                     'l2_model': {'bytes_per_launch': l2_bytes, 'achieved_gbs': l2_bytes / (cast_ms * 1e-3) / 1e9,
-                                 'definition': 'wide_nodes*64 + leaf_pretests*48 + exact_tests*128 + rays*(24 in + 2*72 out)',
+                                 'definition': 'wide_nodes*64 + leaf_pretests*48 + exact_tests*128 + rays*(24 B float32 ray in traverse + 48 B float64 ray in resolve + 2*8 B ray parameters + 8 B count and mask out)',
                                  'per_ray': per_ray},
                     'collide_per_grasp': per_grasp,
                     'note': 'mesh+LBVH (34 MB) is L2-resident by design, so HBM is not the binding roof; see DESIGN.md section 4'}
