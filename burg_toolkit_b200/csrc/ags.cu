@@ -59,7 +59,8 @@ __device__ __forceinline__ float safe_rcp(float d) {
 // trimesh ray_triangle_id narrow phase for one (ray, triangle record); returns true and t if it is a hit
 __device__ __forceinline__ bool exact_ray_triangle(const double* __restrict__ rec, d3 o, d3 d, double& t_out) {
     const double2* r2 = reinterpret_cast<const double2*>(rec);
-    double2 a = __ldg(r2 + 0), b = __ldg(r2 + 1), c = __ldg(r2 + 2);
+    double2 a, b, c, e;
+    ldg256(r2, a, b); ldg256(r2 + 2, c, e);          // 128-byte record, one line: 4 x LDG.256
     d3 v0 = mk3(a.x, a.y, b.x), n = mk3(b.y, c.x, c.y);
     // intersections.planes_lines
     double proj_ori = dot3(sub3(v0, o), n);
@@ -70,7 +71,8 @@ __device__ __forceinline__ bool exact_ray_triangle(const double* __restrict__ re
     // forward test: dot(location - origin, direction) > -1e-6
     if (!(dot3(sub3(p, o), d) > -1e-6)) return false;
     // triangles.points_to_barycentric(method='cramer')
-    double2 e = __ldg(r2 + 3), f = __ldg(r2 + 4), g = __ldg(r2 + 5), h = __ldg(r2 + 6), k = __ldg(r2 + 7);
+    double2 f, g, h, k;
+    ldg256(r2 + 4, f, g); ldg256(r2 + 6, h, k);
     d3 e0 = mk3(e.x, e.y, f.x), e1 = mk3(f.y, g.x, g.y);
     double d00 = h.x, d01 = h.y, d11 = k.x, inv = k.y;
     d3 w = sub3(p, v0);
@@ -89,9 +91,9 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // mesh_processing.compute_interpolated_vertex_normals for one point on the triangle of `leaf`: the three vertices and
 // their normals come from one 160-byte leaf-order record (no faces -> vertices -> normals chain, 10 sector accesses not 19)
 __device__ __forceinline__ d3 interpolated_normal(const MeshView& mv, int32_t leaf, d3 p) {
-    const double2* r2 = reinterpret_cast<const double2*>(mv.tri_vvn + 20 * (int64_t)leaf);      // ten LDG.128, 160-byte aligned record
-    const double2 a0 = __ldg(r2 + 0), a1 = __ldg(r2 + 1), a2 = __ldg(r2 + 2), a3 = __ldg(r2 + 3), a4 = __ldg(r2 + 4);
-    const double2 b0 = __ldg(r2 + 5), b1 = __ldg(r2 + 6), b2 = __ldg(r2 + 7), b3 = __ldg(r2 + 8), b4 = __ldg(r2 + 9);
+    const double2* r2 = reinterpret_cast<const double2*>(mv.tri_vvn + 20 * (int64_t)leaf);      // five LDG.256, 160-byte (32-byte aligned) record
+    double2 a0, a1, a2, a3, a4, b0, b1, b2, b3, b4;
+    ldg256(r2 + 0, a0, a1); ldg256(r2 + 2, a2, a3); ldg256(r2 + 4, a4, b0); ldg256(r2 + 6, b1, b2); ldg256(r2 + 8, b3, b4);
     const d3 vert[3] = {mk3(a0.x, a0.y, a1.x), mk3(a1.y, a2.x, a2.y), mk3(a3.x, a3.y, a4.x)};
     const d3 vn[3] = {mk3(b0.x, b0.y, b1.x), mk3(b1.y, b2.x, b2.y), mk3(b3.x, b3.y, b4.x)};
     double w[3];
@@ -261,7 +263,8 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
             if (cur != DONE) {
                 if (STATS) ++st_nodes;
                 const uint4* np = mv.wnodes + 4 * (int64_t)cur;                 // 64-byte node: 4 x LDG.128
-                const uint4 A = __ldg(np), B = __ldg(np + 1), Cq = __ldg(np + 2), D = __ldg(np + 3);
+                uint4 A, B, Cq, D;
+                ldg256(np, A, B); ldg256(np + 2, Cq, D);                        // 64-byte node: 2 x LDG.256
                 const bool h0 = slab_hit_signed(A.x, A.y, A.z, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
                 const bool h1 = slab_hit_signed(A.w, B.x, B.y, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.y != BT_WIDE_EMPTY);
                 const bool h2 = slab_hit_signed(B.z, B.w, Cq.x, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.z != BT_WIDE_EMPTY);

@@ -498,10 +498,9 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
             live[u] = has[u] && !s_dead[w][slot[u]];
             if (live[u]) {
                 const int node = task[u] & 0x3ffffff;
-                q0[u] = __ldg(nodes + 4 * (int64_t)node + 0);
-                q1[u] = __ldg(nodes + 4 * (int64_t)node + 1);
-                q2[u] = __ldg(nodes + 4 * (int64_t)node + 2);
-                const float4 q3 = __ldg(nodes + 4 * (int64_t)node + 3);
+                float4 q3;
+                ldg256(nodes + 4 * (int64_t)node, q0[u], q1[u]);                  // 64-byte node: 2 x LDG.256
+                ldg256(nodes + 4 * (int64_t)node + 2, q2[u], q3);
                 l[u] = __float_as_int(q3.x); r[u] = __float_as_int(q3.y);
             }
         }

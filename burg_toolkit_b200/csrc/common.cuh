@@ -62,6 +62,39 @@ struct Scratch {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// ---- 256-bit read-only global loads (LDG.E.256, sm_100+; PTX ld.global.nc.v8.b32 / .v4.f64).  A lane that fetches a
+// 64-byte node on its own address costs one L1 sector access per instruction whatever the width, so two 32-byte loads do
+// the work of four 16-byte ones -- and the traversal kernels are bound by exactly those accesses.
+// The address must be 32-byte aligned.
+#ifndef BT_LDG256
+#define BT_LDG256 1
+#endif
+#ifdef __CUDACC__
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+#if BT_LDG256
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#else
+    a = __ldg(reinterpret_cast<const uint4*>(p)); b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+#endif
+}
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+#if BT_LDG256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+}
+__device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
+#if BT_LDG256
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#else
+    a = __ldg(reinterpret_cast<const double2*>(p)); b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+#endif
+}
+#endif
+
 // ---- instrumentation (bt_debug_set_counters): when a counter array is installed the traversal kernels are launched in
 // their STATS instantiation and accumulate work counts there; slots:
 //   0 cast: LBVH nodes visited      1 cast: float32 leaf pre-tests     2 cast: exact float64 ray/triangle tests
