@@ -322,9 +322,6 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
 #ifndef CAST_MINB
 #define CAST_MINB 6
 #endif
-#ifndef BT_RESOLVE_PREFETCH
-#define BT_RESOLVE_PREFETCH 0      // measured: no effect (0.600 vs 0.597 ms cast stage); the kernel is bound by sector throughput, not by the chain
-#endif
 #ifndef RSTAGE
 #define RSTAGE 2                    // hits per ray staged in shared memory (the usual ray has the origin's triangle + one far hit)
 #endif
@@ -353,39 +350,28 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
     int32_t hit_tri[CAP], hit_leaf[CAP];
     int n_hit = 0;
 
-    // phase 2 (also used as an emergency flush when the parking list fills up): exact float64 tests
-    auto run_exact = [&]() {
-        const d3 o = ld3(ref_pts + 3 * ref);
-        const d3 d = ld3(dirs + 3 * ray);
-#if BT_RESOLVE_PREFETCH
-        for (int i = 1; i < n_pend; ++i) prefetch_l1(mv.tri_rec + 16 * (int64_t)pend[i]);      // one 128-byte line per record
-#endif
-        for (int i = 0; i < n_pend; ++i) {
-            const int leaf = pend[i];
-            const int32_t tri = __ldg(mv.leaf_tri + leaf);            // issued with the record loads, not after the test
-            double t;
-            if (exact_ray_triangle(mv.tri_rec + 16 * (int64_t)leaf, o, d, t)) {
-                if (n_hit < cap) {
-                    hit_t[n_hit] = t; hit_tri[n_hit] = tri; hit_leaf[n_hit] = leaf; ++n_hit;
-#if BT_RESOLVE_PREFETCH
-                    if (t > 1e-9) {             // not the origin's own triangle: its vertices and normals will be wanted by the filters
-                        prefetch_l1(mv.tri_vvn + 20 * (int64_t)leaf); prefetch_l1(mv.tri_vvn + 20 * (int64_t)leaf + 16);
-                    }
-#endif
-                }
-                else over = true;
-            }
+    // the reference's float64 narrow phase for one candidate leaf
+    const d3 ray_o = ld3(ref_pts + 3 * ref);
+    const d3 ray_d = ld3(dirs + 3 * ray);
+    auto test_leaf = [&](int leaf) {
+        const int32_t tri = __ldg(mv.leaf_tri + leaf);            // issued with the record loads, not after the test
+        double t;
+        if (exact_ray_triangle(mv.tri_rec + 16 * (int64_t)leaf, ray_o, ray_d, t)) {
+            if (n_hit < cap) { hit_t[n_hit] = t; hit_tri[n_hit] = tri; hit_leaf[n_hit] = leaf; ++n_hit; }
+            else over = true;
         }
+    };
+    // phase 2 of the in-kernel walk (also an emergency flush when the parking list fills up): the parked leaves
+    auto run_exact = [&]() {
+        for (int i = 0; i < n_pend; ++i) test_leaf(pend[i]);
         n_pend = 0;
     };
 
     const int n_cand = cand_count ? cand_count[ray] : CCAP + 1;
     if (n_cand <= CCAP) {
-        // the usual case: stage 1 (traverse_kernel) already found this ray's candidate leaves
-        for (int i = 0; i < n_cand; ++i) {
-            if (n_pend == NPEND) run_exact();
-            pend[n_pend++] = cand[(int64_t)i * n_total + ray];
-        }
+        // the usual case: stage 1 (traverse_kernel) already found this ray's candidate leaves -- test them straight from
+        // the slot-major list (coalesced loads), nothing is parked in local memory
+        for (int i = 0; i < n_cand; ++i) test_leaf(cand[(int64_t)i * n_total + ray]);
     } else {
         // no candidate list (or it overflowed): walk the tree here
         const double odx = ref_pts[3 * ref], ody = ref_pts[3 * ref + 1], odz = ref_pts[3 * ref + 2];
@@ -424,8 +410,7 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
         }
     }
     run_exact();
-    const d3 o = ld3(ref_pts + 3 * ref);
-    const d3 d = ld3(dirs + 3 * ray);
+    const d3 o = ray_o, d = ray_d;
 
     // canonical order: (t, triangle id) ascending
     for (int i = 1; i < n_hit; ++i) {

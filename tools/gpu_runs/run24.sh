@@ -1,6 +1,6 @@
 python -m pytest tests -x -q -m gpu > gpurun_out/t24.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/t24.log
-for lib in libburgb200 libvar_l128 libburgb200 libvar_l128; do
+for lib in libburgb200 libburgb200; do
   BT_LIB=/root/repo/burg_toolkit_b200/csrc/$lib.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
