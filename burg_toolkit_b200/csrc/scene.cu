@@ -36,10 +36,9 @@ mesh_pair_kernel(const float4* __restrict__ nodes, const double* __restrict__ tr
     int sp = 0, cur = 0, steps = 0;
     while (true) {
         if (cur >= 0) {
-            const float4 q0 = __ldg(nodes + 4 * (int64_t)cur + 0);
-            const float4 q1 = __ldg(nodes + 4 * (int64_t)cur + 1);
-            const float4 q2 = __ldg(nodes + 4 * (int64_t)cur + 2);
-            const float4 q3 = __ldg(nodes + 4 * (int64_t)cur + 3);
+            float4 q0, q1, q2, q3;                                     // 64-byte node: 2 x LDG.256
+            ldg256(nodes + 4 * (int64_t)cur, q0, q1);
+            ldg256(nodes + 4 * (int64_t)cur + 2, q2, q3);
             // left box (q0.x q0.y q0.z)-(q0.w q1.x q1.y), right box (q1.z q1.w q2.x)-(q2.y q2.z q2.w)
             const bool hl = (q0.x <= x1) & (q0.w >= x0) & (q0.y <= y1) & (q1.x >= y0) & (q0.z <= z1) & (q1.y >= z0);
             const bool hr = (q1.z <= x1) & (q2.y >= x0) & (q1.w <= y1) & (q2.z >= y0) & (q2.x <= z1) & (q2.w >= z0);
