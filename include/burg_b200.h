@@ -201,7 +201,7 @@ BT_API int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_
 /* The outputs of bt_compact (and free_gs / free_contacts / n_free of bt_ags_pipeline) may be ANY memory the device can
  * store to: local HBM, a peer GPU's buffer mapped with bt_peer_open (the multi-GPU gather of SURVEY 8e: the kept rows
  * travel over NVLink while the scatter kernel runs, no collective afterwards), or mapped pinned host memory (the
- * device-to-host copy of the end-to-end call).  The kernel emits each block's run as consecutive aligned 8-byte words. */
+ * device-to-host copy of the end-to-end call).  The kernel emits each block's run as consecutive aligned 32-byte stores. */
 
 /* ---- peer-visible buffers for the gather to rank 0 (one process per GPU, so the mapping crosses processes: CUDA IPC).
  * bt_peer_alloc: plain cudaMalloc block of `bytes` (zeroed) on `device` + its 64-byte IPC handle; the handle travels
