@@ -331,8 +331,11 @@ def run_b200(args, rank, world, local_rank):
             from burg_toolkit_b200 import distributed as bdist
             from burg_toolkit_b200._native import NativeError
             try:
-                peer = bdist.PeerGather(N_REF * N_ORIENT, with_contacts=True, device=local_rank)
-                exchange = 'compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer), NCCL all_gather of counts'
+                mode = os.environ.get('BT_PEER_ONE_SIDED')                  # A/B knob; default: one-sided from 4 ranks on
+                peer = bdist.PeerGather(N_REF * N_ORIENT, with_contacts=True, device=local_rank, one_sided=None if mode is None else mode != '0')
+                exchange = ('compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer); ' +
+                            ('counts + epoch flags stored the same way, rank 0 polls them (no collective in the step)' if peer.one_sided
+                             else 'NCCL all_gather of counts'))
             except NativeError as ex:
                 exchange = f'NCCL all_reduce + gather of padded rows (peer mapping unavailable: {ex})'
                 gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if rank == 0 else None

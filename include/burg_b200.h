@@ -213,6 +213,14 @@ BT_API int bt_peer_alloc(int device, int64_t bytes, void** d_ptr, bt_ipc_handle*
 BT_API int bt_peer_open(int device, const bt_ipc_handle* handle, void** d_ptr);
 BT_API int bt_peer_close(int device, void* d_ptr);
 BT_API int bt_peer_free(int device, void* d_ptr);
+/* One-sided completion of the gather (no collective in the step).  bt_peer_signal: enqueued behind the compaction on
+ * `stream`, stores *d_local_count to d_count_slot and then `epoch` to d_flag_slot (both usually peer addresses).
+ * bt_peer_wait: one small kernel that polls d_words[0 .. n_words) until each is >= epoch, for at most timeout_s seconds
+ * (then d_status[0] = 1 and the kernel ends: a lost peer cannot hang the device); afterwards, if d_ack is not NULL,
+ * stores ack_value there (the destination telling the peers which epoch it has consumed). */
+BT_API int bt_peer_signal(const int64_t* d_local_count, int64_t* d_count_slot, int64_t* d_flag_slot, int64_t epoch, void* stream);
+BT_API int bt_peer_wait(const int64_t* d_words, int32_t n_words, int64_t epoch, double timeout_s, int32_t* d_status,
+                 int64_t* d_ack, int64_t ack_value, void* stream);
 
 /* ---- the whole AGS pipeline in ONE call (what AntipodalGraspSampler.sample's loop body + check_collisions do
  * per batch, sampling.py:220-350 and :354-397): [S1] -> [S2] -> R1..R6 -> R7 -> [frame vectors] -> O1/O2 ->

@@ -84,7 +84,7 @@ def test_compact_to_mapped_host_memory_ragged():
             assert np.array_equal(out_contacts.numpy()[:k], contacts.cpu().numpy()[keep])
 
 
-def _peer_job(rank, world, port, queue):
+def _peer_job(rank, world, port, queue, one_sided):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -95,9 +95,9 @@ def _peer_job(rank, world, port, queue):
         mesh, pts, nrm, dirs, fv = _inputs(1200, 5)
         ags = _sampler(mesh)
         b, e = bdist.shard_range(len(pts), rank, world)
-        peer = bdist.PeerGather((e - b + 1) * 12, with_contacts=True, device=0)
+        peer = bdist.PeerGather((e - b + 1) * 12, with_contacts=True, device=0, one_sided=one_sided, timeout_s=30.0)
         ok = True
-        for rep in range(3):                                            # the slots are reused call after call
+        for rep in range(4):                                            # the slots are reused call after call
             out = ags.run_pipeline(pts[b:e], nrm[b:e], directions=dirs[b:e], frame_vecs=fv[b:e], seed=0,
                                    destinations=peer.destinations())
             assert out['free_gs'] is None and out['n_free'] is not None
@@ -114,14 +114,17 @@ def _peer_job(rank, world, port, queue):
         dist.destroy_process_group()
 
 
-def test_peer_gather_two_processes_share_a_buffer_through_ipc():
+@pytest.mark.parametrize('one_sided', [True, False])
+def test_peer_gather_two_processes_share_a_buffer_through_ipc(one_sided):
     """two ranks (processes) on one GPU: rank 1's compaction stores into rank 0's buffer through the IPC mapping; the
-    gathered rows / contacts equal the single-process result on all reference points, bit for bit."""
+    gathered rows / contacts equal the single-process result on all reference points, bit for bit.  one_sided: completion
+    through count + epoch-flag stores and a polling kernel on rank 0 (the two processes time-slice the GPU here); otherwise
+    through an all_gather of the counts."""
     import torch.multiprocessing as mp
     from test_distributed_gloo import _free_port
     ctx = mp.get_context('spawn')
     queue, port = ctx.Queue(), _free_port()
-    procs = [ctx.Process(target=_peer_job, args=(r, 2, port, queue)) for r in range(2)]
+    procs = [ctx.Process(target=_peer_job, args=(r, 2, port, queue, one_sided)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict(queue.get(timeout=300) for _ in range(2))
