@@ -332,7 +332,7 @@ def run_b200(args, rank, world, local_rank):
             from burg_toolkit_b200._native import NativeError
             try:
                 mode = os.environ.get('BT_PEER_ONE_SIDED')                  # A/B knob; default: one-sided from 4 ranks on
-                peer = bdist.PeerGather(N_REF * N_ORIENT, with_contacts=True, device=local_rank, one_sided=None if mode is None else mode != '0')
+                peer = bdist.PeerGather(N_REF * N_ORIENT, with_contacts=True, device=local_rank, one_sided=None if mode is None else mode != '0', timeout_s=30.0)
                 exchange = ('compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer); ' +
                             ('counts + epoch flags stored the same way, rank 0 polls them (no collective in the step)' if peer.one_sided
                              else 'NCCL all_gather of counts'))
@@ -439,8 +439,9 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         e2e_ms = max_over_ranks(sum(event_ms(e2e_events)))
         e2e_value = candidates / (e2e_ms * 1e-3)
-        if peer is not None:
-            peer.close()
+        exchange_timed_out = False
+        if peer is not None:                                   # a timed-out wait kernel must not cost the JSON line: it is reported in it
+            exchange_timed_out = sum_over_ranks(1.0 if peer.close(raise_on_timeout=False) else 0.0) > 0
 
         line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
                 'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
@@ -455,7 +456,7 @@ def run_b200(args, rank, world, local_rank):
                            'mode': 'reference mode (one pair per reference point)', 'l2': 'flushed between steps (256 MB write)',
                            'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
                            'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow,
-                           'exchange': exchange},
+                           'exchange': exchange, 'exchange_timed_out': exchange_timed_out},
                 'roofline': roofline, 'stage_ms': stage_ms,
                 'e2e': {'value': e2e_value, 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_ms / args.steps},

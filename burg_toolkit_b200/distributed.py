@@ -243,10 +243,12 @@ class PeerGather:
         contacts = torch.cat([self.contacts[h, r, :c] for r, c in enumerate(counts)], dim=0) if self.with_contacts else None
         return rows, contacts
 
-    def close(self):
+    def close(self, raise_on_timeout=True):
+        """release the mapping (collective: every rank calls it).  -> True if a wait kernel of this rank had timed out
+        (raises instead unless ``raise_on_timeout`` is False)"""
         import torch
         if not self.base:
-            return
+            return False
         torch.cuda.synchronize(self.device)
         status = int(self.status.item())
         self.rows = self.contacts = self.slot_counts = None
@@ -258,5 +260,6 @@ class PeerGather:
             self._nat.call('bt_peer_close', self.device, C.c_void_p(self.base))
             _dist().barrier(group=self.group)
         self.base = 0
-        if status:
+        if status and raise_on_timeout:
             raise self._nat.NativeError(f'PeerGather: rank {self.rank} waited more than {self.timeout_s} s for a peer')
+        return bool(status)
