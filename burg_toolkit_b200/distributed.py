@@ -12,8 +12,9 @@ All helpers work with any backend (NCCL over NVLink on the B200 box, gloo on CPU
 
 ``PeerGather`` is the B200 form of the AGS exchange: the destination rank owns one buffer with a slot per rank, the
 others map it through CUDA IPC, and every rank's compaction kernel stores its kept rows straight into its slot over
-NVLink while it runs (``bt_compact`` / ``bt_ags_pipeline`` write to whatever address they are given).  What is left for
-NCCL is one 8-byte-per-rank ``all_gather`` of the counts, which is also the completion barrier.
+NVLink while it runs (``bt_compact`` / ``bt_ags_pipeline`` write to whatever address they are given).  Completion is
+signalled the same way (count + epoch flag stored into the destination's control block, one polling kernel there), or --
+below 4 ranks -- by one 8-byte-per-rank ``all_gather`` of the counts.
 """
 import ctypes as C
 
