@@ -418,7 +418,7 @@ def run_b200(args, rank, world, local_rank):
                                  'definition': 'wide_nodes*64 + leaf_pretests*48 + exact_tests*128 + rays*(24 B float32 ray in traverse + 48 B float64 ray in resolve + 2*8 B ray parameters + 8 B count and mask out)',
                                  'per_ray': per_ray},
                     'collide_per_grasp': per_grasp,
-                    'note': 'mesh+LBVH (34 MB) is L2-resident by design, so HBM is not the binding roof; see DESIGN.md section 4'}
+                    'note': 'mesh + LBVH + per-leaf records (~50 MB) are L2-resident by design, so HBM is not the binding roof: the stage is bound by L1 data-pipe wavefronts of divergent node fetches; see DESIGN.md section 4'}
 
         # end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
         ags.mesh = mesh
