@@ -68,3 +68,29 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
                 assert 'oracle/' not in src.replace('oracle/port.py', '') or fn.endswith('.md'), fn
+
+
+def test_ctypes_mirrors_agree_with_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the C ABI, as gcc sees include/burg_b200.h, against the ctypes mirror"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    structs = {'bt_ags_params': nat.AgsParams, 'bt_mesh_info': nat.MeshInfo, 'bt_gripper_part': nat.GripperPart,
+               'bt_pipeline_config': nat.PipelineConfig, 'bt_pipeline_buffers': nat.PipelineBuffers}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "burg_b200.h")}"', 'int main(void) {']
+    for cname, mirror in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'  printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    lines.append('  printf("bt_hit %zu\\n", sizeof(bt_hit));  return 0; }')
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-o', str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, mirror in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(mirror), cname
+        for field, _ in mirror._fields_:
+            assert int(out[f'{cname}.{field}']) == getattr(mirror, field).offset, f'{cname}.{field}'
+    assert int(out['bt_hit']) == nat.HIT_DTYPE.itemsize
