@@ -400,6 +400,14 @@ __device__ __forceinline__ bool box_overlaps(const float* bx, float x0, float y0
 //       are none).
 struct GlobalExactQueue { int4* entries; unsigned* count; unsigned cap; uint8_t* unknown; unsigned* overflow; };
 
+#ifndef BT_COLLIDE_DBG
+#define BT_COLLIDE_DBG 0               // 1: pass / batch statistics of the lean kernel (tools/collide_batches.py)
+#endif
+#if BT_COLLIDE_DBG
+__device__ unsigned long long g_cdbg[8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <bool STATS, bool INLINE_EXACT>
 __global__ void __launch_bounds__(32 * CWARPS, INLINE_EXACT ? 4 : LEAN_MINB)
 collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_verts, const float* __restrict__ gs,
@@ -450,10 +458,17 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
     unsigned long long last_base = 0;                              // queue position after this warp's latest fetch
 #endif
 
+#if BT_COLLIDE_DBG
+    unsigned long long dbg_t0 = gtimer(), dbg_tb = dbg_t0, dbg_maxbt = 0;
+    unsigned dbg_pass = 0, dbg_pass_b = 0, dbg_single = 0, dbg_maxb = 0, dbg_batches = 0;
+#endif
     while (true) {
         // ---- refill free slots with new items ---------------------------------------------------------------------------
         int n_free = __popc(free_mask);
         if (!exhausted && n_free >= refill_at && nt <= multi_limit) {
+#if BT_COLLIDE_DBG
+            { const unsigned long long now = gtimer(); dbg_maxb = max(dbg_maxb, dbg_pass_b); dbg_maxbt = max(dbg_maxbt, now - dbg_tb); dbg_tb = now; dbg_pass_b = 0; ++dbg_batches; }
+#endif
 #if COLLIDE_ADAPT
             // adaptive batch size: a batch that took many passes (expensive items come in runs: one gripper part is
             // costlier than the others, and so are whole neighbourhoods of contact pairs) is followed by a smaller fetch,
@@ -508,6 +523,9 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
         }
         // ---- walk: pop up to 32 * WU tasks (WU per lane: independent node fetches in flight), test both children, push ---
         const int take_n = nt <= multi_limit ? min(32 * WU, nt) : 1;
+#if BT_COLLIDE_DBG
+        ++dbg_pass; ++dbg_pass_b; if (nt > multi_limit) ++dbg_single;
+#endif
 #if COLLIDE_ADAPT
         ++batch_passes;
 #endif
@@ -577,6 +595,16 @@ collide_kernel(const float4* __restrict__ nodes, const double* __restrict__ tri_
         }
     }
     if (nx > 0 || ncq > 0) drain_queues<STATS, INLINE_EXACT>(da, nx, ncq, true, lane, st_drain);
+#if BT_COLLIDE_DBG
+    if (lane == 0 && !INLINE_EXACT) {
+        const unsigned long long now = gtimer();
+        dbg_maxb = max(dbg_maxb, dbg_pass_b); dbg_maxbt = max(dbg_maxbt, now - dbg_tb);
+        atomicMax(&g_cdbg[0], (unsigned long long)dbg_maxb); atomicAdd(&g_cdbg[1], (unsigned long long)dbg_pass);
+        atomicAdd(&g_cdbg[2], (unsigned long long)dbg_batches); atomicMax(&g_cdbg[3], (unsigned long long)dbg_pass);
+        atomicAdd(&g_cdbg[4], 1ull); atomicMax(&g_cdbg[5], (unsigned long long)dbg_single);
+        atomicMax(&g_cdbg[6], dbg_maxbt); atomicMax(&g_cdbg[7], now - dbg_t0);
+    }
+#endif
     if (STATS) { atomicAdd(counters + 3, st_nodes); atomicAdd(counters + 4, st_drain[0]); atomicAdd(counters + 5, st_drain[1]); }
 }
 
@@ -885,6 +913,16 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
+
+#if BT_COLLIDE_DBG
+// [0] max passes of a batch, [1] passes (sum over warps), [2] batches, [3] max passes of a warp, [4] warps,
+// [5] max single-pop passes of a warp, [6] longest batch (ns), [7] longest warp (ns)
+extern "C" __attribute__((visibility("default"))) int bt_debug_collide_stats(unsigned long long* h_out, int reset) {
+    if (h_out) BT_CUDA(cudaMemcpyFromSymbol(h_out, bt::g_cdbg, sizeof(unsigned long long) * 8));
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; BT_CUDA(cudaMemcpyToSymbol(bt::g_cdbg, z, sizeof(z))); }
+    return BT_OK;
+}
+#endif
 
 extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
                           int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
