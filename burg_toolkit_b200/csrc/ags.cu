@@ -906,17 +906,26 @@ int bt::ags_select_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const 
     BT_REQUIRE(n_ref >= 0 && n_rays > 0 && cap >= 1 && max_targets >= 1, "bad counts");
     HitSource hs{d_hit_t, d_ref_pts, d_dirs, n_ref * (int64_t)n_rays};
     cudaStream_t st = (cudaStream_t)stream;
-    zero_first_kernel<<<1, 1, 0, st>>>(d_pair_offset);
-    BT_LAUNCH_CHECK();
-    if (n_ref == 0) return BT_OK;
+    if (n_ref == 0) {
+        zero_first_kernel<<<1, 1, 0, st>>>(d_pair_offset);
+        BT_LAUNCH_CHECK();
+        return BT_OK;
+    }
     const unsigned grid = (unsigned)ceil_div(n_ref * 32, 128);
     select_count_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, d_valid_mask, n_ref, n_rays, cap, max_targets, d_pair_count);
     BT_LAUNCH_CHECK();
-    size_t tmp_bytes = 0;
-    BT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
     Scratch tmp;
-    BT_CUDA(tmp.alloc(tmp_bytes, st));
-    BT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
+    if (n_ref <= BT_SMALL_SCAN_MAX) {
+        small_scan_kernel<int32_t><<<1, 1024, 0, st>>>(d_pair_count, d_pair_offset, (int)n_ref, 1);      // pair_offset[0 .. n_ref]
+        BT_LAUNCH_CHECK();
+    } else {
+        zero_first_kernel<<<1, 1, 0, st>>>(d_pair_offset);
+        BT_LAUNCH_CHECK();
+        size_t tmp_bytes = 0;
+        BT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
+        BT_CUDA(tmp.alloc(tmp_bytes, st));
+        BT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_pair_count, d_pair_offset + 1, (int)n_ref, st));
+    }
     select_fill_kernel<<<grid, 128, 0, st>>>(d_hit_count, d_hits, hs, d_valid_mask, n_ref, n_rays, cap, max_targets, seed,
                                              d_pair_offset, cap_pairs, d_pair_ref, d_pair_q);
     BT_LAUNCH_CHECK();

@@ -943,10 +943,15 @@ extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float
     BT_CUDA(offsets.alloc(sizeof(int64_t) * n_blocks, st));
     compact_count_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, counts.as<int32_t>());
     BT_LAUNCH_CHECK();
-    size_t tmp_bytes = 0;
-    BT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
-    BT_CUDA(tmp.alloc(tmp_bytes, st));
-    BT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
+    if (n_blocks <= BT_SMALL_SCAN_MAX) {
+        small_scan_kernel<int32_t><<<1, 1024, 0, st>>>(counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, 0);
+        BT_LAUNCH_CHECK();
+    } else {
+        size_t tmp_bytes = 0;
+        BT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
+        BT_CUDA(tmp.alloc(tmp_bytes, st));
+        BT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
+    }
     compact_scatter_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, offsets.as<int64_t>(), n_blocks,
                                                               d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out, d_base);
     BT_LAUNCH_CHECK();

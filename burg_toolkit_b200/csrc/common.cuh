@@ -95,6 +95,45 @@ __device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
 }
 #endif
 
+// ---- exclusive scan of a short array by ONE 1024-thread block: out[i] = in[0] + ... + in[i-1] (and out[n] = total if
+// write_total).  The scans of the pipeline are short (pair counts per reference point, kept rows per compaction block:
+// 10^2 .. 10^5 entries), where a device-wide scan is two launches of mostly launch latency; beyond BT_SMALL_SCAN_MAX the
+// callers use cub::DeviceScan.
+constexpr int BT_SMALL_SCAN_MAX = 1 << 18;
+#ifdef __CUDACC__
+template <typename TIn>
+__global__ void __launch_bounds__(1024) small_scan_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out, int n, int write_total) {
+    __shared__ int64_t warp_base[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int b = min(n, tid * per), e = min(n, b + per);
+    int64_t s = 0;
+    for (int i = b; i < e; ++i) s += (int64_t)in[i];
+    int64_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_base[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int64_t w = warp_base[lane];
+        int64_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        warp_base[lane] = wi - w;                       // exclusive prefix over the warps
+    }
+    __syncthreads();
+    int64_t run = warp_base[warp] + incl - s;
+    for (int i = b; i < e; ++i) { out[i] = run; run += (int64_t)in[i]; }
+    if (write_total && tid == 1023) out[n] = run;       // the last thread's chunk ends at n, so its running sum is the total
+}
+#endif
+
 // ---- instrumentation (bt_debug_set_counters): when a counter array is installed the traversal kernels are launched in
 // their STATS instantiation and accumulate work counts there; slots:
 //   0 cast: LBVH nodes visited      1 cast: float32 leaf pre-tests     2 cast: exact float64 ray/triangle tests
