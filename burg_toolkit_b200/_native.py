@@ -45,7 +45,8 @@ STAGE_NAMES = ('sample_surface', 'cone_rays', 'cast', 'select', 'frame_vectors',
 class PipelineConfig(C.Structure):
     _fields_ = [('ags', AgsParams), ('n_rays', C.c_int32), ('n_orientations', C.c_int32), ('max_targets', C.c_int32),
                 ('halfspace', C.c_int32), ('check_collisions', C.c_int32), ('use_width', C.c_int32),
-                ('compact', C.c_int32), ('tail_splits', C.c_int32), ('collision_width_tolerance', C.c_double),
+                ('compact', C.c_int32), ('tail_splits', C.c_int32), ('cone_culling', C.c_int32), ('reserved', C.c_int32),
+                ('collision_width_tolerance', C.c_double),
                 ('orient_cos', C.c_double * 64), ('orient_sin', C.c_double * 64)]
 
 

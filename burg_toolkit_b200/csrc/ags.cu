@@ -32,6 +32,7 @@ struct MeshView {
     const double* __restrict__ verts;
     const double* __restrict__ vnormals;
     const double* __restrict__ tri_vvn;            // [nF,20] leaf order: v0 v1 v2 pad | n0 n1 n2 pad
+    const uint32_t* __restrict__ leaf_cone;       // [nF] leaf order: packed normal cones (mesh.cu: pack_cone)
 };
 
 __device__ __forceinline__ bool slab_hit(float bx0, float by0, float bz0, float bx1, float by1, float bz1,
@@ -178,15 +179,39 @@ __device__ __forceinline__ bool slab_hit_signed(unsigned wx, unsigned wy, unsign
     return (tnear <= tfar) & (tfar >= T_BEHIND);
 }
 
-template <bool STATS>
+// 24-bit child code of the packed node format -> the plain code (sign extension: one BFE)
+__device__ __forceinline__ int sext24(unsigned w) { int r; asm("bfe.s32 %0, %1, 0, 24;" : "=r"(r) : "r"(w)); return r; }
+// byte 3 of w as the float 2^15 + byte (the byte lands in mantissa bits 8..15 of 0x47000000): one byte-permute
+__device__ __forceinline__ float top_byte_m15(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7434)); }
+__device__ __forceinline__ float byte_m15(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x47000000u, sel)); }
+constexpr float CONE_BIAS = 32768.0f + 128.0f;        // 2^15 + the int8 bias of a packed cone axis
+constexpr float CONE_NEVER = -1e30f;
+
+// threshold table of the cone test for this launch: code c -> 127 * (cos(c * pi/255 + angle_max + slack) - margin).  The
+// axis bytes have length 127 +- 0.9 instead of exactly 127, which the cosine margin of 0.01 covers (|1/r - 1| < 0.0075).
+__device__ __forceinline__ void fill_cone_table(float* tab, float angle_max) {
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        const float phi = (float)c * (3.14159265f / 255.f) + angle_max + 3e-3f;
+        tab[c] = (c == 255 || !(phi < 3.14159f)) ? CONE_NEVER : 127.f * (cosf(phi) - 0.01f);
+    }
+}
+
+// PACKED: 24-bit child codes with the node's normal cone in the top bytes (meshes below 2^23 triangles).
+// CULL (needs PACKED; lean pipeline only): a node / leaf whose normal cone cannot hold a VALID antipodal hit for this
+// ray's direction is skipped.  What is skipped are hits the filters would reject anyway (wrong sign or outside the
+// friction cone), and -- because leaf cones are widened over all touching triangles, see leaf_cone_kernel -- never a hit
+// that could take part in the 1e-8 de-duplication of a valid one: the valid-hit masks and contacts are unchanged.
+template <bool STATS, bool PACKED, bool CULL>
 __global__ void __launch_bounds__(32 * TWARPS, TRAV_MINB)
 traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
-                int n_rays, int rays_per_warp, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
+                int n_rays, int rays_per_warp, float angle_max, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
                 unsigned long long* __restrict__ counters) {
-    unsigned long long st_nodes = 0, st_leaves = 0, st_cand = 0;
+    unsigned long long st_nodes = 0, st_leaves = 0, st_cand = 0, st_culled = 0;
     __shared__ int s_lq_ray[TWARPS][LQ_CAP], s_lq_leaf[TWARPS][LQ_CAP], s_lq_n[TWARPS];
+    __shared__ float s_thr[CULL ? 256 : 1];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (CULL) { fill_cone_table(s_thr, angle_max); __syncthreads(); }
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t slice_begin = warp * rays_per_warp;
     if (slice_begin >= n_total) return;                 // whole warps leave together (no block-wide barrier below)
@@ -202,6 +227,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     int my = 0;                                       // this lane's ray, as an offset into the slice
     float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
     unsigned snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;
+    float ux = 0, uy = 0, uz = 0, ubias = 0;             // CULL: unit direction and CONE_BIAS * (ux + uy + uz)
     int stack[WIDE_STACK];
     int sp = 0, cur = DONE;
 
@@ -213,8 +239,15 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
             const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays, ray = slice_begin + off;
             const float ox = (float)ref_pts[3 * ref], oy = (float)ref_pts[3 * ref + 1], oz = (float)ref_pts[3 * ref + 2];
             const float dx = (float)dirs[3 * ray], dy = (float)dirs[3 * ray + 1], dz = (float)dirs[3 * ray + 2];
-            if (STATS) ++st_leaves;
-            if (maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
+            bool keep = true;
+            if (CULL) {                                   // the leaf's own (widened) normal cone
+                const unsigned cw = __ldg(mv.leaf_cone + leaf);
+                const float inv = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                const float dq = fmaf(byte_m15(cw, 0x7404) - CONE_BIAS, dx, fmaf(byte_m15(cw, 0x7414) - CONE_BIAS, dy, (byte_m15(cw, 0x7424) - CONE_BIAS) * dz)) * inv;
+                keep = !(dq < s_thr[cw >> 24]);
+            }
+            if (STATS && keep) ++st_leaves;
+            if (keep && maybe_hit_f32(mv.tri_f32 + 3 * (int64_t)leaf, ox, oy, oz, dx, dy, dz)) {
                 const int slot = atomicAdd(cand_count + ray, 1);
                 if (slot < CCAP) cand[(int64_t)slot * n_total + ray] = leaf;       // slot-major: the resolve kernel reads it coalesced
                 if (STATS) ++st_cand;
@@ -249,6 +282,12 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
                 snx = nx ? 0x7632u : 0x7610u; sfx = nx ? 0x7610u : 0x7632u;
                 sny = ny ? 0x7632u : 0x7610u; sfy = ny ? 0x7610u : 0x7632u;
                 snz = nz ? 0x7632u : 0x7610u; sfz = nz ? 0x7610u : 0x7632u;
+                if (CULL) {
+                    const float wx = (float)dirs[3 * ray], wy = (float)dirs[3 * ray + 1], wz = (float)dirs[3 * ray + 2];
+                    const float inv = rsqrtf(fmaf(wx, wx, fmaf(wy, wy, wz * wz)));
+                    ux = wx * inv; uy = wy * inv; uz = wz * inv;
+                    ubias = CONE_BIAS * (ux + uy + uz);
+                }
                 sp = 0; cur = 0;
             }
             next = min(slice_len, next + __popc(idle));
@@ -265,12 +304,24 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
                 const uint4* np = mv.wnodes + 4 * (int64_t)cur;                 // 64-byte node: 4 x LDG.128
                 uint4 A, B, Cq, D;
                 ldg256(np, A, B); ldg256(np + 2, Cq, D);                        // 64-byte node: 2 x LDG.256
-                const bool h0 = slab_hit_signed(A.x, A.y, A.z, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
-                const bool h1 = slab_hit_signed(A.w, B.x, B.y, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.y != BT_WIDE_EMPTY);
-                const bool h2 = slab_hit_signed(B.z, B.w, Cq.x, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.z != BT_WIDE_EMPTY);
-                const bool h3 = slab_hit_signed(Cq.y, Cq.z, Cq.w, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz) & ((int)D.w != BT_WIDE_EMPTY);
+                // unused child slots carry an inverted box (emit_wide_nodes_kernel): no ray hits them, no test needed
+                bool h0 = false, h1 = false, h2 = false, h3 = false;
+                bool walk = true;
+                if (CULL) {
+                    // the node's own normal cone: (2^15 + b_k) u_k summed minus the bias term = q . u  (q = int8 axis)
+                    const float dq = fmaf(top_byte_m15(D.x), ux, fmaf(top_byte_m15(D.y), uy, fmaf(top_byte_m15(D.z), uz, -ubias)));
+                    walk = !(dq < s_thr[D.w >> 24]);
+                    if (STATS && !walk) ++st_culled;
+                }
+                if (walk) {
+                    h0 = slab_hit_signed(A.x, A.y, A.z, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
+                    h1 = slab_hit_signed(A.w, B.x, B.y, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
+                    h2 = slab_hit_signed(B.z, B.w, Cq.x, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
+                    h3 = slab_hit_signed(Cq.y, Cq.z, Cq.w, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
+                }
                 // leaves -> the warp's leaf queue (one shared-memory atomic per lane that reached leaves)
-                const int c0 = (int)D.x, c1 = (int)D.y, c2 = (int)D.z, c3 = (int)D.w;
+                const int c0 = PACKED ? sext24(D.x) : (int)D.x, c1 = PACKED ? sext24(D.y) : (int)D.y,
+                          c2 = PACKED ? sext24(D.z) : (int)D.z, c3 = PACKED ? sext24(D.w) : (int)D.w;
                 const bool l0 = h0 & (c0 < 0), l1 = h1 & (c1 < 0), l2 = h2 & (c2 < 0), l3 = h3 & (c3 < 0);
                 const int nl = (int)l0 + (int)l1 + (int)l2 + (int)l3;
                 if (nl) {
@@ -313,7 +364,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     __syncwarp();
     const int nq = s_lq_n[w];
     if (nq > 0) pretest_pass(0, nq);                   // fewer than 32 entries are left
-    if (STATS) { atomicAdd(counters + 0, st_nodes); atomicAdd(counters + 1, st_leaves); atomicAdd(counters + 2, st_cand); }
+    if (STATS) { atomicAdd(counters + 0, st_nodes); atomicAdd(counters + 1, st_leaves); atomicAdd(counters + 2, st_cand); atomicAdd(counters + 6, st_culled); }
 }
 
 // One thread per ray.  Phase 1 walks the LBVH in float32 (both child boxes per 64-byte node) and parks the leaves that
@@ -795,7 +846,7 @@ static MeshView view_of(const MeshDev& m) {
     v.wnodes = m.wnodes;
     for (int k = 0; k < 3; ++k) { v.gmin[k] = m.grid_min[k]; v.gscale[k] = m.grid_scale[k]; }
     v.tri_rec = m.tri_rec; v.tri_f32 = m.tri_f32; v.leaf_tri = m.leaf_tri; v.faces = m.faces; v.verts = m.verts;
-    v.vnormals = m.vnormals; v.tri_vvn = m.tri_vvn;
+    v.vnormals = m.vnormals; v.tri_vvn = m.tri_vvn; v.leaf_cone = m.leaf_cone;
     return v;
 }
 
@@ -838,13 +889,13 @@ extern "C" int bt_ags_cast(const bt_mesh* mesh, const double* d_ref_pts, const d
                            int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits,
                            uint32_t* d_valid_mask, int32_t* d_overflow, void* stream) {
     BT_REQUIRE(n_ref == 0 || d_hits, "null pointer");
-    return bt::ags_cast_impl(mesh, d_ref_pts, d_dirs, n_ref, n_rays, params, d_hit_count, d_hits, nullptr, d_valid_mask, d_overflow, stream);
+    return bt::ags_cast_impl(mesh, d_ref_pts, d_dirs, n_ref, n_rays, params, d_hit_count, d_hits, nullptr, d_valid_mask, d_overflow, false, stream);
 }
 
 // d_hits == NULL: lean mode (bt_ags_pipeline without hit records), the ray parameters go to d_hit_t [cap, n_ref * n_rays]
 int bt::ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref,
                       int32_t n_rays, const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits, double* d_hit_t,
-                      uint32_t* d_valid_mask, int32_t* d_overflow, void* stream) {
+                      uint32_t* d_valid_mask, int32_t* d_overflow, bool cull, void* stream) {
     BT_REQUIRE(mesh && params, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
     BT_REQUIRE(n_ref == 0 || (d_ref_pts && d_dirs && d_hit_count && (d_hits || (d_hit_t && d_valid_mask))), "null pointer");     // empty arrays may be NULL
@@ -870,12 +921,25 @@ int bt::ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double
     rpw = std::max<int64_t>(64, std::min<int64_t>(256, ceil_div(rpw, 32) * 32));
     if (const char* e = getenv("BT_CAST_RPW")) { const int v = atoi(e); if (v >= 32 && v <= 256) rpw = v; }       // tuning knob
     const int64_t n_warps = ceil_div(total, rpw);
-    if (g_counters_host_copy)
-        traverse_kernel<true><<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,
-                                                                                     cc.as<int32_t>(), cl.as<int32_t>(), g_counters_host_copy);
-    else
-        traverse_kernel<false><<<(unsigned)ceil_div(n_warps * 32, 128), 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,
-                                                                                      cc.as<int32_t>(), cl.as<int32_t>(), nullptr);
+    // cone culling: only where the caller wants valid hits and nothing else (lean pipeline), on packed nodes
+    static int cull_env = -1;
+    if (cull_env < 0) { const char* e = getenv("BT_CAST_CULL"); cull_env = e ? atoi(e) : 1; }
+    const bool packed = mesh->m.wide_packed != 0;
+    const bool do_cull = cull && packed && cull_env != 0 && params->angle_max >= 0.0 && params->angle_max < 1.5;
+    const unsigned tgrid = (unsigned)ceil_div(n_warps * 32, 128);
+#define BT_TRAVERSE(STATS, PACKED, CULL, CNT)                                                                              \
+    traverse_kernel<STATS, PACKED, CULL><<<tgrid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,            \
+                                                                (float)params->angle_max, cc.as<int32_t>(), cl.as<int32_t>(), CNT)
+    if (g_counters_host_copy) {
+        if (do_cull) BT_TRAVERSE(true, true, true, g_counters_host_copy);
+        else if (packed) BT_TRAVERSE(true, true, false, g_counters_host_copy);
+        else BT_TRAVERSE(true, false, false, g_counters_host_copy);
+    } else {
+        if (do_cull) BT_TRAVERSE(false, true, true, nullptr);
+        else if (packed) BT_TRAVERSE(false, true, false, nullptr);
+        else BT_TRAVERSE(false, false, false, nullptr);
+    }
+#undef BT_TRAVERSE
     BT_LAUNCH_CHECK();
     // stage 2: exact float64 narrow phase, ordering, de-duplication, filters, hit records
     if (cap <= 8)

@@ -15,6 +15,7 @@
 namespace bt {
 
 constexpr int BT_WIDE_EMPTY = 0x7fffffff;       // child code of an unused slot of a 4-wide node
+constexpr int BT_WIDE_EMPTY_PACKED = 0x7fffff;  // the same in the packed (24-bit) code format, see emit_wide_nodes_kernel
 
 // ---- error plumbing ---------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -175,6 +176,8 @@ struct MeshDev {
                                    //          ten 16-byte words (normal interpolation without the faces -> vertices -> normals chain)
     float4*  tri_f32 = nullptr;    // [nF,3]   leaf order: (v0 | 0) (e0 | 0) (e1 | 0) for the float32 pre-test
     int32_t* leaf_tri = nullptr;   // [nF]     leaf -> caller's triangle id
+    uint32_t* leaf_cone = nullptr; // [nF]     leaf order: packed normal cone of the leaf, widened over its touching neighbours (mesh.cu: pack_cone)
+    int32_t  wide_packed = 0;      // wnodes use 24-bit child codes + the node's own cone in their top bytes (nF < 2^23)
     int32_t  root = 0;             // root child code (internal 0, or ~0 if single triangle)
     bt_mesh_info info{};
 };
@@ -182,7 +185,7 @@ struct MeshDev {
 // internal forms of bt_ags_cast / bt_ags_select with the lean hit representation of bt_ags_pipeline (ags.cu)
 int ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double* d_dirs, int64_t n_ref, int32_t n_rays,
                   const bt_ags_params* params, int32_t* d_hit_count, bt_hit* d_hits, double* d_hit_t, uint32_t* d_valid_mask,
-                  int32_t* d_overflow, void* stream);
+                  int32_t* d_overflow, bool cull, void* stream);
 int ags_select_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const double* d_hit_t, const double* d_ref_pts, const double* d_dirs,
                     const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays, int32_t cap, int32_t max_targets, uint64_t seed,
                     int32_t* d_pair_count, int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs, void* stream);

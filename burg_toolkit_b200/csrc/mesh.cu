@@ -219,10 +219,31 @@ __global__ void wide_flags_kernel(int n, const int32_t* __restrict__ parent, int
     flag[i] = (depth & 1) ? 0 : 1;
 }
 
+// Packed child code (meshes below 2^23 triangles): low 24 bits = the code sign-extended (inner: wide index, leaf: ~leaf,
+// empty: BT_WIDE_EMPTY_PACKED), top byte = one byte of the NODE's own normal cone (word 12: axis x, 13: axis y, 14: axis z,
+// 15: half-angle code), see pack_cone.  Empty slots carry an inverted box (lo = 65535, hi = 0 on every axis): no ray can
+// hit it, so the traversal needs no test for them.
+__device__ __forceinline__ unsigned pack_code(int32_t code, unsigned cone_byte) { return ((unsigned)code & 0x00ffffffu) | (cone_byte << 24); }
+
+// Normal cone (unit axis a, half-angle th) -> 32 bits: axis as three biased int8 (q + 128), half-angle as an 8-bit code in
+// steps of pi/255, rounded UP after adding the angle between the true and the quantised axis; 255 = "never cull".
+__device__ unsigned pack_cone(float ax, float ay, float az, float th) {
+    if (!(th >= 0.f) || !(th < 3.1f) || !(ax == ax) || !(ay == ay) || !(az == az)) return 0xff808080u;   // code 255 = never cull
+    const int qx = max(-127, min(127, __float2int_rn(ax * 127.f))), qy = max(-127, min(127, __float2int_rn(ay * 127.f))),
+              qz = max(-127, min(127, __float2int_rn(az * 127.f)));
+    const float ql = sqrtf((float)(qx * qx + qy * qy + qz * qz));
+    if (ql < 64.f) return 0xff808080u;                  // the axis was not a unit vector
+    const float c = ((float)qx * ax + (float)qy * ay + (float)qz * az) / ql;
+    const float err = acosf(fminf(1.f, fmaxf(-1.f, c)));
+    const float total = th + err + 2e-3f;
+    const int code = (int)ceilf(total * (255.f / 3.14159265f));
+    return (unsigned)(qx + 128) | ((unsigned)(qy + 128) << 8) | ((unsigned)(qz + 128) << 16) | ((unsigned)min(255, max(0, code)) << 24);
+}
+
 __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
                                        const int32_t* __restrict__ flag, const int32_t* __restrict__ widx,
                                        const float* __restrict__ box_min, const float* __restrict__ box_max, double3 gmin,
-                                       double3 gscale, uint4* __restrict__ wnodes) {
+                                       double3 gscale, const float4* __restrict__ cone, int packed, uint4* __restrict__ wnodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     if (!flag[i]) return;
@@ -234,6 +255,8 @@ __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, 
         if (two[k] < 0) child[nc++] = two[k];
         else { child[nc++] = left[two[k]]; child[nc++] = right[two[k]]; }
     }
+    unsigned cone_word = 0xff808080u;
+    if (packed && i != 0) { const float4 c = cone[i]; cone_word = pack_cone(c.x, c.y, c.z, c.w); }      // the root is always walked
     unsigned w[16];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -242,26 +265,142 @@ __global__ void emit_wide_nodes_kernel(int n, const int32_t* __restrict__ left, 
             w[3 * k + 0] = quant_lo(box_min[3 * sl], gmin.x, gscale.x) | (quant_hi(box_max[3 * sl], gmin.x, gscale.x) << 16);
             w[3 * k + 1] = quant_lo(box_min[3 * sl + 1], gmin.y, gscale.y) | (quant_hi(box_max[3 * sl + 1], gmin.y, gscale.y) << 16);
             w[3 * k + 2] = quant_lo(box_min[3 * sl + 2], gmin.z, gscale.z) | (quant_hi(box_max[3 * sl + 2], gmin.z, gscale.z) << 16);
-            w[12 + k] = (unsigned)(child[k] < 0 ? child[k] : widx[child[k]]);       // inner children: dense wide index
+            const int32_t code = child[k] < 0 ? child[k] : widx[child[k]];          // inner children: dense wide index
+            w[12 + k] = packed ? pack_code(code, (cone_word >> (8 * k)) & 0xffu) : (unsigned)code;
         } else {
-            w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0u;
-            w[12 + k] = (unsigned)BT_WIDE_EMPTY;
+            w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0x0000ffffu;               // inverted box: never hit
+            w[12 + k] = packed ? pack_code(BT_WIDE_EMPTY_PACKED, (cone_word >> (8 * k)) & 0xffu) : (unsigned)BT_WIDE_EMPTY;
         }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) wnodes[4 * (int64_t)widx[i] + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
+// ---- normal cones: which directions can a VALID antipodal hit on this subtree have? ----------------------------------
+// A hit is valid only if the interpolated vertex normal n at the hit lies within atan(mu) of the ray direction
+// (sampling.py:289-308); n is a positive combination of the triangle's three vertex normals, so it lies inside any
+// circular cone (half-angle < 90 deg) that holds them.  The lean ray caster uses a cone per leaf and per node to skip
+// what cannot hold a valid hit.  The skipped hits must not change what happens to the valid ones: the only coupling
+// between hits of a ray is trimesh's 1e-8 de-duplication, which can only merge hits on triangles whose (padded) boxes
+// touch -- so a leaf's cone is widened to hold the vertex normals of EVERY triangle whose box overlaps its own
+// (found by a walk of the finished LBVH).  Then: valid hit on B found => every hit that can share its location is found.
+//   cone[slot] = (axis.xyz, half-angle); slot numbering as for the boxes (internal nodes, then leaves)
+__device__ __forceinline__ float angle_between(float ax, float ay, float az, float bx, float by, float bz) {
+    // atan2(|a x b|, a . b): accurate for small angles, where acos of a float32 dot product is not
+    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    return atan2f(sqrtf(cx * cx + cy * cy + cz * cz), ax * bx + ay * by + az * bz);
+}
+
+__global__ void leaf_cone_kernel(int n, const float4* __restrict__ nodes, const double* __restrict__ tri_vvn,
+                                 const float* __restrict__ box_min, const float* __restrict__ box_max, float grow,
+                                 float4* __restrict__ cone) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // own axis: normalised sum of the (normalised) vertex normals
+    float vn[3][3];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    int n_ok = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double* p = tri_vvn + 20 * (int64_t)i + 10 + 3 * k;
+        const float x = (float)p[0], y = (float)p[1], z = (float)p[2];
+        const float l = sqrtf(x * x + y * y + z * z);
+        const bool ok = (l > 1e-30f) && (l < 1e30f);           // zero / NaN / inf normals contribute nothing to an interpolated normal that can pass the filters
+        vn[k][0] = ok ? x / l : 0.f; vn[k][1] = ok ? y / l : 0.f; vn[k][2] = ok ? z / l : 0.f;
+        sx += vn[k][0]; sy += vn[k][1]; sz += vn[k][2];
+        n_ok += ok ? 1 : 0;
+    }
+    const int slot = (n - 1) + i;
+    const float sl = sqrtf(sx * sx + sy * sy + sz * sz);
+    if (n_ok < 3 || !(sl > 1e-3f)) { cone[slot] = make_float4(1.f, 0.f, 0.f, 4.f); return; }      // degenerate: never culled
+    const float ax = sx / sl, ay = sy / sl, az = sz / sl;
+    float th = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) th = fmaxf(th, angle_between(ax, ay, az, vn[k][0], vn[k][1], vn[k][2]));
+    // neighbours: every leaf whose box overlaps this leaf's box grown by `grow`
+    const float lx = box_min[3 * slot] - grow, ly = box_min[3 * slot + 1] - grow, lz = box_min[3 * slot + 2] - grow;
+    const float hx = box_max[3 * slot] + grow, hy = box_max[3 * slot + 1] + grow, hz = box_max[3 * slot + 2] + grow;
+    if (n > 1) {
+        int stack[64];
+        int sp = 0, cur = 0;
+        bool bad = false;
+        while (true) {
+            if (cur >= 0) {
+                const float4 q0 = nodes[4 * (int64_t)cur], q1 = nodes[4 * (int64_t)cur + 1], q2 = nodes[4 * (int64_t)cur + 2], q3 = nodes[4 * (int64_t)cur + 3];
+                const bool ol = (q0.x <= hx) & (q0.w >= lx) & (q0.y <= hy) & (q1.x >= ly) & (q0.z <= hz) & (q1.y >= lz);
+                const bool orr = (q1.z <= hx) & (q2.y >= lx) & (q1.w <= hy) & (q2.z >= ly) & (q2.x <= hz) & (q2.w >= lz);
+                const int l = __float_as_int(q3.x), r = __float_as_int(q3.y);
+                if (ol && orr) { if (sp >= 64) { bad = true; break; } stack[sp++] = r; cur = l; continue; }
+                if (ol) { cur = l; continue; }
+                if (orr) { cur = r; continue; }
+            } else {
+                const int j = ~cur;
+                if (j != i) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double* p = tri_vvn + 20 * (int64_t)j + 10 + 3 * k;
+                        const float x = (float)p[0], y = (float)p[1], z = (float)p[2];
+                        const float l = sqrtf(x * x + y * y + z * z);
+                        if ((l > 1e-30f) && (l < 1e30f)) th = fmaxf(th, angle_between(ax, ay, az, x / l, y / l, z / l));
+                    }
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+        if (bad) th = 4.f;
+    }
+    // the "positive combinations stay inside" argument needs a convex cone, i.e. a half-angle below 90 degrees
+    cone[slot] = make_float4(ax, ay, az, th < 1.5f ? th + 1e-4f : 4.f);
+}
+
+// bottom-up merge (same arrival-counter scheme as refit_kernel): axis = normalised sum of the children's axes,
+// half-angle = the larger of (angle to a child's axis + that child's half-angle)
+__global__ void cone_refit_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                  const int32_t* __restrict__ parent, float4* cone, int* __restrict__ arrivals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cur = parent[(n - 1) + i];
+    while (cur >= 0) {
+        __threadfence();
+        if (atomicAdd(&arrivals[cur], 1) == 0) return;
+        __threadfence();
+        const float4 a = __ldcg(cone + box_slot(left[cur], n)), b = __ldcg(cone + box_slot(right[cur], n));
+        float4 m = make_float4(1.f, 0.f, 0.f, 4.f);
+        const float sx = a.x + b.x, sy = a.y + b.y, sz = a.z + b.z;
+        const float sl = sqrtf(sx * sx + sy * sy + sz * sz);
+        if (a.w < 3.2f && b.w < 3.2f && sl > 1e-3f) {
+            const float ax = sx / sl, ay = sy / sl, az = sz / sl;
+            const float th = fmaxf(angle_between(ax, ay, az, a.x, a.y, a.z) + a.w, angle_between(ax, ay, az, b.x, b.y, b.z) + b.w) + 1e-4f;
+            m = make_float4(ax, ay, az, th);
+        }
+        __stcg(cone + cur, m);
+        cur = parent[cur];
+    }
+}
+
+__global__ void pack_leaf_cones_kernel(int n, const float4* __restrict__ cone, uint32_t* __restrict__ leaf_cone) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = cone[(n - 1) + i];
+    leaf_cone[i] = pack_cone(c.x, c.y, c.z, c.w);
+}
+
 // nF == 1: wide node 0 = (leaf 0 | empty | empty | empty)
 __global__ void single_leaf_wide_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
-                                             double3 gmin, double3 gscale, uint4* __restrict__ wnodes) {
+                                             double3 gmin, double3 gscale, int packed, uint4* __restrict__ wnodes) {
     const unsigned w0 = quant_lo(box_min[0], gmin.x, gscale.x) | (quant_hi(box_max[0], gmin.x, gscale.x) << 16);
     const unsigned w1 = quant_lo(box_min[1], gmin.y, gscale.y) | (quant_hi(box_max[1], gmin.y, gscale.y) << 16);
     const unsigned w2 = quant_lo(box_min[2], gmin.z, gscale.z) | (quant_hi(box_max[2], gmin.z, gscale.z) << 16);
-    wnodes[0] = make_uint4(w0, w1, w2, 0u);
-    wnodes[1] = make_uint4(0u, 0u, 0u, 0u);
-    wnodes[2] = make_uint4(0u, 0u, 0u, 0u);
-    wnodes[3] = make_uint4((unsigned)~0, (unsigned)BT_WIDE_EMPTY, (unsigned)BT_WIDE_EMPTY, (unsigned)BT_WIDE_EMPTY);
+    const unsigned inv = 0x0000ffffu;                  // inverted box (lo = 65535, hi = 0): never hit
+    wnodes[0] = make_uint4(w0, w1, w2, inv);
+    wnodes[1] = make_uint4(inv, inv, inv, inv);
+    wnodes[2] = make_uint4(inv, inv, inv, inv);
+    if (packed) {                                      // cone bytes: axis (128, 128, 128) is irrelevant with half-angle code 255 = never cull
+        const unsigned e = pack_code(BT_WIDE_EMPTY_PACKED, 0x80u);
+        wnodes[3] = make_uint4(pack_code(~0, 0x80u), e, e, pack_code(BT_WIDE_EMPTY_PACKED, 0xffu));
+    } else
+        wnodes[3] = make_uint4((unsigned)~0, (unsigned)BT_WIDE_EMPTY, (unsigned)BT_WIDE_EMPTY, (unsigned)BT_WIDE_EMPTY);
 }
 
 __global__ void single_leaf_node_kernel(const float* __restrict__ box_min, const float* __restrict__ box_max,
@@ -336,7 +475,7 @@ extern "C" int bt_stream_sync(void* stream) {
 // ---- mesh ------------------------------------------------------------------------------------------
 static int mesh_free(MeshDev& m) {
     cudaFree(m.verts); cudaFree(m.vnormals); cudaFree(m.faces); cudaFree(m.area_cdf);
-    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.wnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_vvn); cudaFree(m.tri_f32); cudaFree(m.leaf_tri);
+    cudaFree(m.nodes); cudaFree(m.qnodes); cudaFree(m.wnodes); cudaFree(m.tri_rec); cudaFree(m.tri_verts); cudaFree(m.tri_vvn); cudaFree(m.tri_f32); cudaFree(m.leaf_tri); cudaFree(m.leaf_cone);
     m = MeshDev();
     return BT_OK;
 }
@@ -401,6 +540,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cudaMalloc(&m.tri_vvn, sizeof(double) * 20 * nF));
     MESH_TRY(cudaMalloc(&m.tri_f32, sizeof(float4) * 3 * nF));
     MESH_TRY(cudaMalloc(&m.leaf_tri, sizeof(int32_t) * nF));
+    MESH_TRY(cudaMalloc(&m.leaf_cone, sizeof(uint32_t) * nF));
     MESH_TRY(cudaMemcpy(m.verts, h_V, sizeof(double) * 3 * nV, cudaMemcpyHostToDevice));
     MESH_TRY(cudaMemcpy(m.vnormals, h_VN, sizeof(double) * 3 * nV, cudaMemcpyHostToDevice));
     MESH_TRY(cudaMemcpy(m.faces, h_F, sizeof(int32_t) * 3 * nF, cudaMemcpyHostToDevice));
@@ -416,6 +556,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     float *box_min = nullptr, *box_max = nullptr;
     int *arrivals = nullptr, *max_depth = nullptr;
     double *area = nullptr, *total_area = nullptr;
+    float4* cone = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0, cub_bytes2 = 0;
     const int n = (int)nF;
@@ -432,6 +573,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cudaMalloc(&max_depth, sizeof(int)));
     MESH_TRY(cudaMalloc(&area, sizeof(double) * nF));
     MESH_TRY(cudaMalloc(&total_area, sizeof(double)));
+    MESH_TRY(cudaMalloc(&cone, sizeof(float4) * 2 * nF));
     MESH_TRY(cudaMemsetAsync(arrivals, 0, sizeof(int) * nNodes, st));
     MESH_TRY(cudaMemsetAsync(max_depth, 0, sizeof(int), st));
     MESH_TRY(cudaMemsetAsync(parent, 0xFF, sizeof(int32_t) * (2 * nF), st));
@@ -483,6 +625,17 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
         MESH_TRY(cudaGetLastError());
         const double3 gm = make_double3(m.grid_min[0], m.grid_min[1], m.grid_min[2]);
         const double3 gs = make_double3(m.grid_scale[0], m.grid_scale[1], m.grid_scale[2]);
+        // normal cones of the leaves (widened over every triangle whose box touches the leaf's) and of the internal nodes
+        m.wide_packed = nF < BT_WIDE_EMPTY_PACKED ? 1 : 0;         // 24-bit child codes + cone bytes; larger meshes: plain codes, no culling
+        leaf_cone_kernel<<<G, T, 0, st>>>(n, m.nodes, m.tri_vvn, box_min, box_max, 1e-7f + 2.0f * pad, cone);
+        MESH_TRY(cudaGetLastError());
+        if (nF > 1) {
+            MESH_TRY(cudaMemsetAsync(arrivals, 0, sizeof(int) * nNodes, st));
+            cone_refit_kernel<<<G, T, 0, st>>>(n, left, right, parent, cone, arrivals);
+            MESH_TRY(cudaGetLastError());
+        }
+        pack_leaf_cones_kernel<<<G, T, 0, st>>>(n, cone, m.leaf_cone);
+        MESH_TRY(cudaGetLastError());
         if (nF > 1) {
             // ids / ids_sorted (n int32 each) are free again at this point: reuse them for the flags and their scan
             int32_t* flag = reinterpret_cast<int32_t*>(ids);
@@ -490,9 +643,9 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
             wide_flags_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, parent, flag);
             MESH_TRY(cudaGetLastError());
             MESH_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flag, widx, n - 1, st));
-            emit_wide_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, flag, widx, box_min, box_max, gm, gs, m.wnodes);
+            emit_wide_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, flag, widx, box_min, box_max, gm, gs, cone, m.wide_packed, m.wnodes);
         } else
-            single_leaf_wide_node_kernel<<<1, 1, 0, st>>>(box_min, box_max, gm, gs, m.wnodes);
+            single_leaf_wide_node_kernel<<<1, 1, 0, st>>>(box_min, box_max, gm, gs, m.wide_packed, m.wnodes);
         MESH_TRY(cudaGetLastError());
     }
     MESH_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, cub_bytes, area, m.area_cdf, n, st));
@@ -511,7 +664,7 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     cudaFree(keys); cudaFree(keys_sorted); cudaFree(ids); cudaFree(ids_sorted); cudaFree(left); cudaFree(right);
     cudaFree(parent); cudaFree(box_min); cudaFree(box_max); cudaFree(arrivals); cudaFree(max_depth);
-    cudaFree(area); cudaFree(total_area); cudaFree(cub_tmp);
+    cudaFree(area); cudaFree(total_area); cudaFree(cub_tmp); cudaFree(cone);
 #undef MESH_TRY
     if (depth > 60) {
         set_error("bt_mesh_create: LBVH depth %d exceeds the traversal stack (64)", depth);

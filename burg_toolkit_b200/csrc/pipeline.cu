@@ -120,7 +120,7 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     }
     STAGE_BEGIN(2);
     STAGE_CALL(ags_cast_impl(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->hits ? nullptr : b->hit_t,
-                             b->valid_mask, b->overflow, stream));
+                             b->valid_mask, b->overflow, !b->hits && cfg->cone_culling, stream));
     STAGE_END(2);
     STAGE_BEGIN(3);
     STAGE_CALL(ags_select_impl(b->hit_count, b->hits, b->hit_t, b->ref_pts, b->dirs, b->valid_mask, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray,

@@ -106,6 +106,7 @@ class AntipodalGraspSampler:
         self.surface_samples = None         # optional (n_sample, 6) [point | normal] override of stage S1
         self.max_hits_per_ray = 8           # per-ray hit list capacity (doubled automatically on overflow)
         self.max_passes = 10                # cap on wrap-arounds of the reference-point list (the reference spins forever)
+        self.cone_culling = True            # lean pipeline: skip triangles / LBVH subtrees whose vertex normals rule out a valid hit
         self.last_stats = {}
 
     # -----------------------------------------------------------------------------------------------
@@ -272,7 +273,10 @@ class AntipodalGraspSampler:
         ``keep_hits``: materialise the per-ray hit records (``out['cast']``, as ``cast()`` returns them).  They are an
         intermediate of the path -- the reference's ``locations / index_ray / index_tri`` arrays -- and cost 144 MB of stores
         per million rays, so by default the caster keeps only the valid-hit masks and the ray parameters, from which the
-        target choice rebuilds each contact with the caster's own expression (same bits).
+        target choice rebuilds each contact with the caster's own expression (same bits).  In this lean mode, with
+        ``self.cone_culling`` (default), the caster also skips every triangle and LBVH subtree whose vertex normals rule out a
+        VALID hit for the ray (the interpolated normal has to lie within atan(mu) of the ray, sampling.py:289-308): the valid
+        masks, contacts and grasps are the same bits, ``hit_count`` then counts only the crossings that were looked at.
         ``tail_splits`` > 1: collision check + compaction run over that many row ranges on two streams, so a link-bound
         compaction (host / peer destination) overlaps the next range's collision walk; the output is identical.
         -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
@@ -303,7 +307,7 @@ class AntipodalGraspSampler:
                         buf.reshape(-1)[:n_ref * per_ref].copy_(src.reshape(-1), non_blocking=True)
             sig = (float(self.mu), float(self.gripper.opening_width) if self.gripper is not None else None, float(self.width_tolerance),
                    float(self.min_grasp_width), self.no_contact_below_z, cap, int(self.n_rays), n_o, k, bool(self.only_grasp_from_above),
-                   bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance), int(tail_splits))
+                   bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance), int(tail_splits), bool(self.cone_culling))
             cached = getattr(ws, 'config_cache', None)
             if cached is not None and cached[0] == sig:
                 cfg = cached[1]
@@ -316,6 +320,7 @@ class AntipodalGraspSampler:
                 cfg.compact = int(bool(check_collisions and compact))
                 cfg.collision_width_tolerance = float(collision_width_tolerance)
                 cfg.tail_splits = int(tail_splits)
+                cfg.cone_culling = int(bool(self.cone_culling))
                 cos_t, sin_t = _orientation_tables(n_o, cfg.halfspace)
                 cfg.orient_cos[:n_o] = cos_t.tolist()
                 cfg.orient_sin[:n_o] = sin_t.tolist()
@@ -334,7 +339,7 @@ class AntipodalGraspSampler:
                    pair_ref=ws.pair_ref, pair_q=ws.pair_q, gs=ws.gs, contacts=ws.contacts, n_grasps=ws.n_grasps,
                    overflow=ws.overflow, ref_pts=ws.ref_pts, ref_nrm=ws.ref_nrm, directions=ws.dirs,
                    cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap, ws.valid_mask) if keep_hits else None,
-                   hit_count=ws.hit_count, valid_mask=ws.valid_mask, cap_pairs=ws.cap_pairs)
+                   hit_count=ws.hit_count, valid_mask=ws.valid_mask, hit_t=ws.hit_t, cap_pairs=ws.cap_pairs)
         if check_collisions:
             out['colliding'] = ws.colliding[:ws.rows]
             if compact:

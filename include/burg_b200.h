@@ -99,6 +99,7 @@ BT_API int         bt_stream_sync(void* stream);
  * bt_collide run instrumented instantiations of their kernels that add to it:
  *   [0] cast LBVH nodes visited  [1] cast float32 leaf pre-tests  [2] cast exact float64 tests
  *   [3] collide LBVH nodes visited  [4] collide leaves classified  [5] collide leaves sent to the exact test
+ *   [6] cast LBVH nodes fetched but skipped by the normal-cone test
  * (used by bench.py, outside the timed region, for the L2 traffic model of the roofline) */
 BT_API int bt_debug_set_counters(uint64_t* d_counters);
 
@@ -241,6 +242,11 @@ typedef struct bt_pipeline_config {
     int32_t tail_splits;     /* > 1: collide + compact run over that many row ranges on two streams, so that the compaction of
                                 one range (link-bound when it stores to mapped host / peer memory) overlaps the collision
                                 walk of the next; same output, bit for bit.  0 / 1 = off.  Max 8.                       */
+    int32_t cone_culling;    /* lean mode (buffers->hits == NULL) only: the ray caster skips triangles and LBVH subtrees whose
+                                vertex normals rule out a VALID antipodal hit for the ray (interpolated normal within
+                                atan(mu) of the ray); valid_mask / contacts / grasps are unchanged, hit_count then counts
+                                only the hits that were looked at.  0 = find every crossing                               */
+    int32_t reserved;
     double  collision_width_tolerance;
     double  orient_cos[64], orient_sin[64];   /* numpy-evaluated cos/sin of the orientation angles */
 } bt_pipeline_config;
