@@ -169,20 +169,24 @@ constexpr int TWARPS = 4;
 
 
 // near / far plane of one axis as 2^23 + q: selector 0x7610 takes the low half of the word, 0x7632 the high half
-__device__ __forceinline__ float plane16(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+// (PTX prmt directly: __byte_perm masks a run-time selector with 0x7777 first -- one LOP3 per use -- which the selectors
+// used here (0x7610 / 0x7632: every nibble below 8, i.e. no sign replication) do not need)
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) { unsigned r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
+__device__ __forceinline__ float plane16(unsigned w, unsigned sel) { return __uint_as_float(prmt(w, 0x4B000000u, sel)); }
 
+// `behind`: T_BEHIND, or +inf for a node the cone test has ruled out (then no child is hit, without a branch)
 __device__ __forceinline__ bool slab_hit_signed(unsigned wx, unsigned wy, unsigned wz, unsigned snx, unsigned sny, unsigned snz,
                                                 unsigned sfx, unsigned sfy, unsigned sfz, float idx, float idy, float idz,
-                                                float oox, float ooy, float ooz) {
+                                                float oox, float ooy, float ooz, float behind = T_BEHIND) {
     const float tnear = fmaxf(fmaxf(fmaf(plane16(wx, snx), idx, -oox), fmaf(plane16(wy, sny), idy, -ooy)), fmaf(plane16(wz, snz), idz, -ooz));
     const float tfar = fminf(fminf(fmaf(plane16(wx, sfx), idx, -oox), fmaf(plane16(wy, sfy), idy, -ooy)), fmaf(plane16(wz, sfz), idz, -ooz));
-    return (tnear <= tfar) & (tfar >= T_BEHIND);
+    return (tnear <= tfar) & (tfar >= behind);
 }
 
 // 24-bit child code of the packed node format -> the plain code (sign extension: one BFE)
 __device__ __forceinline__ int sext24(unsigned w) { int r; asm("bfe.s32 %0, %1, 0, 24;" : "=r"(r) : "r"(w)); return r; }
 // byte 3 of w as the float 2^15 + byte (the byte lands in mantissa bits 8..15 of 0x47000000): one byte-permute
-__device__ __forceinline__ float top_byte_m15(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7434)); }
+__device__ __forceinline__ float top_byte_m15(unsigned w) { unsigned r; asm("prmt.b32 %0, %1, 0x47000000, 0x7434;" : "=r"(r) : "r"(w)); return __uint_as_float(r); }
 __device__ __forceinline__ float byte_m15(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x47000000u, sel)); }
 constexpr float CONE_BIAS = 32768.0f + 128.0f;        // 2^15 + the int8 bias of a packed cone axis
 constexpr float CONE_NEVER = -1e30f;
@@ -207,7 +211,8 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
                 int n_rays, int rays_per_warp, float angle_max, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
                 unsigned long long* __restrict__ counters) {
     unsigned long long st_nodes = 0, st_leaves = 0, st_cand = 0, st_culled = 0;
-    __shared__ int s_lq_ray[TWARPS][LQ_CAP], s_lq_leaf[TWARPS][LQ_CAP], s_lq_n[TWARPS];
+    __shared__ int2 s_lq[TWARPS][LQ_CAP];            // leaf queue entries: (ray offset in the slice, leaf)
+    __shared__ int s_lq_n[TWARPS];
     __shared__ float s_thr[CULL ? 256 : 1];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -218,8 +223,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     const int slice_len = (int)min((int64_t)rays_per_warp, n_total - slice_begin);
     const unsigned ref0 = (unsigned)(slice_begin / n_rays), rem0 = (unsigned)(slice_begin - (int64_t)ref0 * n_rays);
     int next = 0;                                     // warp-uniform: first ray of the slice nobody has taken yet
-    int* lq_ray = s_lq_ray[w];
-    int* lq_leaf = s_lq_leaf[w];
+    int2* lq = s_lq[w];
     if (lane == 0) s_lq_n[w] = 0;
     __syncwarp();
 
@@ -234,7 +238,8 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     // one conservative float32 pre-test per lane for queue entries [first, first + count)
     auto pretest_pass = [&](int first, int count) {
         if (lane < count) {
-            const int off = lq_ray[first + lane], leaf = lq_leaf[first + lane];
+            const int2 en = lq[first + lane];
+            const int off = en.x, leaf = en.y;
             const unsigned k = rem0 + (unsigned)off;
             const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays, ray = slice_begin + off;
             const float ox = (float)ref_pts[3 * ref], oy = (float)ref_pts[3 * ref + 1], oz = (float)ref_pts[3 * ref + 2];
@@ -305,31 +310,32 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
                 uint4 A, B, Cq, D;
                 ldg256(np, A, B); ldg256(np + 2, Cq, D);                        // 64-byte node: 2 x LDG.256
                 // unused child slots carry an inverted box (emit_wide_nodes_kernel): no ray hits them, no test needed
-                bool h0 = false, h1 = false, h2 = false, h3 = false;
-                bool walk = true;
+                float behind = T_BEHIND;
                 if (CULL) {
-                    // the node's own normal cone: (2^15 + b_k) u_k summed minus the bias term = q . u  (q = int8 axis)
+                    // the node's own normal cone: (2^15 + b_k) u_k summed minus the bias term = q . u  (q = int8 axis).  A node
+                    // that is ruled out gets an unreachable far-plane bound instead of a branch around the box tests, so the
+                    // table look-up's latency hides behind them
                     const float dq = fmaf(top_byte_m15(D.x), ux, fmaf(top_byte_m15(D.y), uy, fmaf(top_byte_m15(D.z), uz, -ubias)));
-                    walk = !(dq < s_thr[D.w >> 24]);
-                    if (STATS && !walk) ++st_culled;
+                    const bool skip = dq < s_thr[D.w >> 24];
+                    behind = skip ? __int_as_float(0x7f800000) : T_BEHIND;
+                    if (STATS && skip) ++st_culled;
                 }
-                if (walk) {
-                    h0 = slab_hit_signed(A.x, A.y, A.z, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
-                    h1 = slab_hit_signed(A.w, B.x, B.y, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
-                    h2 = slab_hit_signed(B.z, B.w, Cq.x, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
-                    h3 = slab_hit_signed(Cq.y, Cq.z, Cq.w, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz);
-                }
-                // leaves -> the warp's leaf queue (one shared-memory atomic per lane that reached leaves)
+                const bool h0 = slab_hit_signed(A.x, A.y, A.z, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz, behind);
+                const bool h1 = slab_hit_signed(A.w, B.x, B.y, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz, behind);
+                const bool h2 = slab_hit_signed(B.z, B.w, Cq.x, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz, behind);
+                const bool h3 = slab_hit_signed(Cq.y, Cq.z, Cq.w, snx, sny, snz, sfx, sfy, sfz, idx, idy, idz, oox, ooy, ooz, behind);
+                // leaves -> the warp's leaf queue (one shared-memory atomic per lane that reached leaves; each entry is one
+                // 8-byte store: ray offset and leaf side by side)
                 const int c0 = PACKED ? sext24(D.x) : (int)D.x, c1 = PACKED ? sext24(D.y) : (int)D.y,
                           c2 = PACKED ? sext24(D.z) : (int)D.z, c3 = PACKED ? sext24(D.w) : (int)D.w;
                 const bool l0 = h0 & (c0 < 0), l1 = h1 & (c1 < 0), l2 = h2 & (c2 < 0), l3 = h3 & (c3 < 0);
-                const int nl = (int)l0 + (int)l1 + (int)l2 + (int)l3;
-                if (nl) {
-                    int q = atomicAdd(&s_lq_n[w], nl);
-                    if (l0) { lq_ray[q] = my; lq_leaf[q] = ~c0; ++q; }
-                    if (l1) { lq_ray[q] = my; lq_leaf[q] = ~c1; ++q; }
-                    if (l2) { lq_ray[q] = my; lq_leaf[q] = ~c2; ++q; }
-                    if (l3) { lq_ray[q] = my; lq_leaf[q] = ~c3; }
+                if (l0 | l1 | l2 | l3) {
+                    const int nl = (int)l0 + (int)l1 + (int)l2 + (int)l3;
+                    const int q0 = atomicAdd(&s_lq_n[w], nl), q1 = q0 + (int)l0, q2 = q1 + (int)l1, q3 = q2 + (int)l2;
+                    if (l0) lq[q0] = make_int2(my, ~c0);
+                    if (l1) lq[q1] = make_int2(my, ~c1);
+                    if (l2) lq[q2] = make_int2(my, ~c2);
+                    if (l3) lq[q3] = make_int2(my, ~c3);
                 }
                 // inner children: continue with the last one that was hit, park the others (predicated, no branches)
                 int nxt = DONE;
