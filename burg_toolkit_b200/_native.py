@@ -39,7 +39,7 @@ class GripperPart(C.Structure):
 
 
 N_STAGES = 8
-STAGE_NAMES = ('sample_surface', 'cone_rays', 'cast', 'select', 'frame_vectors', 'expand', 'collide', 'compact')
+STAGE_NAMES = ('generate', '_unused1', 'cast', 'select', '_unused4', 'expand', 'collide', 'compact')
 
 
 class PipelineConfig(C.Structure):
@@ -58,7 +58,7 @@ class PipelineBuffers(C.Structure):
                 ('pair_offset', C.c_void_p), ('pair_ref', C.c_void_p), ('pair_q', C.c_void_p), ('cap_pairs', C.c_int64),
                 ('gs', C.c_void_p), ('contacts', C.c_void_p), ('n_grasps', C.c_void_p), ('colliding', C.c_void_p),
                 ('free_gs', C.c_void_p), ('free_contacts', C.c_void_p), ('n_free', C.c_void_p),
-                ('free_base', C.c_void_p), ('hit_t', C.c_void_p), ('compact_after', C.c_void_p)]
+                ('free_base', C.c_void_p), ('hit_t', C.c_void_p), ('compact_after', C.c_void_p), ('seed_add', C.c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -103,6 +103,12 @@ _SIGNATURES = {
     'bt_timer_read': (C.c_int, [_P, C.POINTER(C.c_float)]),
     'bt_ags_pipeline': (C.c_int, [_P, _P, _P, C.POINTER(PipelineConfig), C.POINTER(PipelineBuffers), C.c_int64,
                                   C.c_uint64, _P, _P]),
+    'bt_graph_begin_capture': (C.c_int, [_P]),
+    'bt_graph_end_capture': (C.c_int, [_P, C.POINTER(_P)]),
+    'bt_graph_launch': (C.c_int, [_P, _P]),
+    'bt_graph_info': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.c_int64]),
+    'bt_graph_destroy': (C.c_int, [_P]),
+    'bt_set_u64': (C.c_int, [_P, C.c_uint64, _P]),
     'bt_coverage': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     'bt_avg_gripper_point_distances': (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P]),
     'bt_mesh_pair_collide': (C.c_int, [_P, _P, _P, _P]),

@@ -555,12 +555,11 @@ cast_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __res
 }
 
 // ---- S1 ------------------------------------------------------------------------------------------------
-__global__ void sample_surface_kernel(const double* __restrict__ cdf, const int32_t* __restrict__ faces,
-                                      const double* __restrict__ verts, int64_t nF, int64_t n, uint64_t seed,
-                                      double* __restrict__ pts, double* __restrict__ nrm, int32_t* __restrict__ tri_out) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // open3d SamplePointsUniformlyImpl: triangle f owns sample slots [round(cdf[f-1]*n), round(cdf[f]*n))
+// one area-weighted surface sample (open3d SamplePointsUniformlyImpl: triangle f owns sample slots
+// [round(cdf[f-1]*n), round(cdf[f]*n)) ) -> point, triangle normal, triangle
+__device__ __forceinline__ int32_t surface_sample(const double* __restrict__ cdf, const int32_t* __restrict__ faces,
+                                                  const double* __restrict__ verts, int64_t nF, int64_t n, int64_t i, uint64_t seed,
+                                                  d3& p, d3& nv) {
     int64_t lo = 0, hi = nF - 1;
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
@@ -574,21 +573,28 @@ __global__ void sample_surface_kernel(const double* __restrict__ cdf, const int3
     const double a = 1.0 - s, b = s * (1.0 - r2), c = s * r2;
     const int32_t* fc = faces + 3 * (int64_t)f;
     d3 v0 = ld3(verts + 3 * (int64_t)fc[0]), v1 = ld3(verts + 3 * (int64_t)fc[1]), v2 = ld3(verts + 3 * (int64_t)fc[2]);
-    d3 p = add3(add3(scl3(v0, a), scl3(v1, b)), scl3(v2, c));
+    p = add3(add3(scl3(v0, a), scl3(v1, b)), scl3(v2, c));
     d3 cr = cross3(sub3(v1, v0), sub3(v2, v0));
     double nn = norm3(cr);
-    d3 nv = nn > 0 ? div3(cr, nn) : mk3(0, 0, 1);
+    nv = nn > 0 ? div3(cr, nn) : mk3(0, 0, 1);
+    return f;
+}
+
+__global__ void sample_surface_kernel(const double* __restrict__ cdf, const int32_t* __restrict__ faces,
+                                      const double* __restrict__ verts, int64_t nF, int64_t n, uint64_t seed,
+                                      double* __restrict__ pts, double* __restrict__ nrm, int32_t* __restrict__ tri_out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 p, nv;
+    const int32_t f = surface_sample(cdf, faces, verts, nF, n, i, seed, p, nv);
     st3(pts + 3 * i, p);
     st3(nrm + 3 * i, nv);
     if (tri_out) tri_out[i] = f;
 }
 
 // ---- S2 ------------------------------------------------------------------------------------------------
-__global__ void cone_rays_kernel(const double* __restrict__ normals, int64_t n_ref, int n_rays, double angle,
-                                 uint64_t seed, double* __restrict__ dirs) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n_ref * n_rays) return;
-    const int64_t ref = i / n_rays;
+// ray i (= ref * n_rays + r) of the friction cone about -normal  (sampling.py:17-48, util.py:7-29)
+__device__ __forceinline__ d3 cone_ray(d3 normal, int64_t ref, int64_t i, double angle, uint64_t seed) {
     uint32_t r[4];
     philox4x32(seed, (uint64_t)i, 0x434f4e45ull, r);
     const double az = u01(r[0], r[1]) * (2.0 * 3.14159265358979323846);      // U(0, 2 pi)   sampling.py:32
@@ -598,8 +604,7 @@ __global__ void cone_rays_kernel(const double* __restrict__ normals, int64_t n_r
     sincos(az, &sa, &ca);
     const d3 c = mk3(si * ca, si * sa, ci);
     // util.rotation_to_align_vectors([0,0,1], axis): R = 2 k k^T / (k^T k) - I,  k = z + axis/|axis|
-    d3 axis = ld3(normals + 3 * ref);
-    axis = mk3(-axis.x, -axis.y, -axis.z);
+    d3 axis = mk3(-normal.x, -normal.y, -normal.z);
     const double an = norm3(axis);
     d3 k = mk3(axis.x / an, axis.y / an, 1.0 + axis.z / an);
     if (norm3(k) == 0.0) {                      // axis == -z exactly: half turn about any vector orthogonal to z
@@ -611,12 +616,19 @@ __global__ void cone_rays_kernel(const double* __restrict__ normals, int64_t n_r
     const double kk = dot3(k, k);
     const double kc = dot3(k, c);
     const double f = 2.0 * kc / kk;
-    st3(dirs + 3 * i, mk3(f * k.x - c.x, f * k.y - c.y, f * k.z - c.z));
+    return mk3(f * k.x - c.x, f * k.y - c.y, f * k.z - c.z);
 }
 
-__global__ void unit_vectors_kernel(int64_t n, uint64_t seed, double* __restrict__ out) {
+__global__ void cone_rays_kernel(const double* __restrict__ normals, int64_t n_ref, int n_rays, double angle,
+                                 uint64_t seed, double* __restrict__ dirs) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_ref * n_rays) return;
+    const int64_t ref = i / n_rays;
+    st3(dirs + 3 * i, cone_ray(ld3(normals + 3 * ref), ref, i, angle, seed));
+}
+
+// util.generate_random_unit_vector (util.py:32-43): normalised N(0,1)^3, redrawn while shorter than 1e-5
+__device__ __forceinline__ d3 random_unit_vector(int64_t i, uint64_t seed) {
     d3 v = mk3(0, 0, 1);
     for (uint64_t attempt = 0; attempt < 8; ++attempt) {
         uint32_t a[4], b[4];
@@ -630,7 +642,52 @@ __global__ void unit_vectors_kernel(int64_t n, uint64_t seed, double* __restrict
         const double mag = norm3(g);
         if (mag > 1e-5) { v = div3(g, mag); break; }
     }
-    st3(out + 3 * i, v);
+    return v;
+}
+
+__global__ void unit_vectors_kernel(int64_t n, uint64_t seed, double* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st3(out + 3 * i, random_unit_vector(i, seed));
+}
+
+// ---- S1 + S2 + frame vectors in one launch (bt_ags_pipeline with device-generated candidates) ---------------------
+// A block owns GEN_REFS reference points: warp 0 draws their surface samples, warp 1 their frame vectors, then all
+// threads generate the GEN_REFS x n_rays cone rays from the normals in shared memory.  Same Philox keys as the three
+// stand-alone kernels, so the values are the same bits.  `seed_add` (nullable): a device-resident offset added to the
+// seed -- lets a captured CUDA graph of the pipeline be replayed with a new seed (see bt_graph_*).
+constexpr int GEN_REFS = 8;
+__global__ void __launch_bounds__(256)
+generate_kernel(const double* __restrict__ cdf, const int32_t* __restrict__ faces, const double* __restrict__ verts, int64_t nF,
+                int64_t n_ref, int n_rays, double angle, uint64_t seed, const uint64_t* __restrict__ seed_add, int do_sample, int do_dirs,
+                int do_frame, double* __restrict__ pts, double* __restrict__ nrm, double* __restrict__ frame, double* __restrict__ dirs) {
+    __shared__ double s_n[GEN_REFS][3];
+    if (seed_add) seed += *seed_add;
+    const int64_t ref0 = blockIdx.x * (int64_t)GEN_REFS;
+    const int t = threadIdx.x;
+    if (t < GEN_REFS && ref0 + t < n_ref) {
+        const int64_t i = ref0 + t;
+        d3 nv;
+        if (do_sample) {
+            d3 p;
+            surface_sample(cdf, faces, verts, nF, n_ref, i, seed, p, nv);
+            st3(pts + 3 * i, p);
+            st3(nrm + 3 * i, nv);
+        } else nv = ld3(nrm + 3 * i);
+        s_n[t][0] = nv.x; s_n[t][1] = nv.y; s_n[t][2] = nv.z;
+    }
+    if (do_frame && t >= 32 && t < 32 + GEN_REFS && ref0 + (t - 32) < n_ref) {
+        const int64_t i = ref0 + (t - 32);
+        st3(frame + 3 * i, random_unit_vector(i, seed + 0x3000));
+    }
+    if (!do_dirs) return;
+    __syncthreads();
+    const int n_here = (int)min((int64_t)GEN_REFS, n_ref - ref0) * n_rays;
+    for (int j = t; j < n_here; j += blockDim.x) {
+        const int lr = j / n_rays;
+        const int64_t ref = ref0 + lr, i = ref0 * n_rays + j;
+        st3(dirs + 3 * i, cone_ray(mk3(s_n[lr][0], s_n[lr][1], s_n[lr][2]), ref, i, angle, seed + 0x1000));
+    }
 }
 
 // ---- R7 ------------------------------------------------------------------------------------------------
@@ -677,21 +734,12 @@ __device__ __forceinline__ d3 hit_location(const bt_hit* __restrict__ hits, cons
     return add3(scl3(ld3(hs.dirs + 3 * ray), t), ld3(hs.ref_pts + 3 * ref));
 }
 
-__global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits, HitSource hs,
-                                   const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
-                                   const int64_t* __restrict__ pair_offset, int64_t cap_pairs,
-                                   int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
-    const int64_t ref = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (ref >= n_ref) return;
-    const int64_t base = pair_offset[ref];
-    const int n_take = (int)(pair_offset[ref + 1] - base);
-    if (n_take == 0) return;
-    // total number of valid hits (to know whether a random subset has to be drawn)
-    int total = 0;
-    for (int r = lane; r < n_rays; r += 32) total += __popc(ray_valid_mask(valid_mask, hit_count, hits, ref * n_rays + r, cap));
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
+// one warp writes the n_take chosen contact pairs of reference point `ref` to slots [base, base + n_take)
+// (`total` = number of valid hits of the reference point; a random subset is drawn iff seed != 0 and total > max_targets)
+__device__ __forceinline__ void select_fill_ref(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits, const HitSource& hs,
+                                                const uint32_t* __restrict__ valid_mask, int64_t ref, int lane, int n_rays, int cap,
+                                                int max_targets, uint64_t seed, int64_t base, int n_take, int total, int64_t cap_pairs,
+                                                int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
     const bool random_subset = (seed != 0) && (total > max_targets);
 
     if (!random_subset) {
@@ -778,15 +826,85 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
     }
 }
 
+// number of valid hits of reference point `ref` (all lanes of the warp get the sum)
+__device__ __forceinline__ int ref_valid_total(const uint32_t* __restrict__ valid_mask, const int32_t* __restrict__ hit_count,
+                                               const bt_hit* __restrict__ hits, int64_t ref, int lane, int n_rays, int cap) {
+    int total = 0;
+    for (int r = lane; r < n_rays; r += 32) total += __popc(ray_valid_mask(valid_mask, hit_count, hits, ref * n_rays + r, cap));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
+    return total;
+}
+
+__global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits, HitSource hs,
+                                   const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
+                                   const int64_t* __restrict__ pair_offset, int64_t cap_pairs,
+                                   int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
+    const int64_t ref = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ref >= n_ref) return;
+    const int64_t base = pair_offset[ref];
+    const int n_take = (int)(pair_offset[ref + 1] - base);
+    if (n_take == 0) return;
+    const int total = ref_valid_total(valid_mask, hit_count, hits, ref, lane, n_rays, cap);
+    select_fill_ref(hit_count, hits, hs, valid_mask, ref, lane, n_rays, cap, max_targets, seed, base, n_take, total, cap_pairs, pair_ref, pair_q);
+}
+
+// ---- R7 in ONE launch (bt_ags_pipeline): count, exclusive scan and fill ---------------------------------------------------
+// A block owns SEL_REFS reference points, one warp each.  The blocks' pair counts are scanned across the grid with a
+// single-pass chained scan (decoupled look-back): a block publishes its aggregate, looks back over its predecessors'
+// status words until it meets an inclusive prefix, and publishes its own.  Block ids come from a ticket counter, so a block
+// only ever waits for blocks that are already running.  Status word: bits 63..62 = 1 aggregate / 2 inclusive prefix.
+constexpr int SEL_REFS = 32;
+__global__ void __launch_bounds__(32 * SEL_REFS)
+select_fused_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits, HitSource hs,
+                    const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
+                    const uint64_t* __restrict__ seed_add, unsigned long long* status, unsigned* ticket, unsigned n_blocks,
+                    int32_t* __restrict__ pair_count, int64_t* __restrict__ pair_offset, int64_t cap_pairs,
+                    int32_t* __restrict__ pair_ref, double* __restrict__ pair_q) {
+    __shared__ unsigned s_bid;
+    __shared__ int s_cnt[SEL_REFS];
+    __shared__ unsigned long long s_base;
+    if (seed != 0 && seed_add) seed += *seed_add;              // seed 0 = canonical choice, whatever the offset
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ref = (int64_t)bid * SEL_REFS + w;
+    int total = 0;
+    if (ref < n_ref) total = ref_valid_total(valid_mask, hit_count, hits, ref, lane, n_rays, cap);
+    const int n_take = min(total, max_targets);
+    if (lane == 0) { s_cnt[w] = n_take; if (ref < n_ref) pair_count[ref] = n_take; }
+    __syncthreads();
+    if (w == 0) {
+        const int c = s_cnt[lane];
+        int incl = c;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += v; }
+        const unsigned long long agg = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+        const unsigned long long excl = lookback_exclusive(status, bid, agg, lane);
+        s_cnt[lane] = incl - c;                                // exclusive prefix inside the block
+        if (lane == 0) s_base = excl;
+        const int64_t r = (int64_t)bid * SEL_REFS + lane;
+        if (r < n_ref) pair_offset[r] = (int64_t)excl + (incl - c);
+        if (bid == n_blocks - 1 && lane == 31) pair_offset[n_ref] = (int64_t)(excl + agg);
+    }
+    __syncthreads();
+    if (ref >= n_ref || n_take == 0) return;
+    select_fill_ref(hit_count, hits, hs, valid_mask, ref, lane, n_rays, cap, max_targets, seed, (int64_t)s_base + s_cnt[w], n_take, total,
+                    cap_pairs, pair_ref, pair_q);
+}
+
 // ---- O1 / O2 -------------------------------------------------------------------------------------------
 struct OrientTable { double c[64]; double s[64]; };
 
 __global__ void expand_kernel(const double* __restrict__ ref_pts, const int64_t* __restrict__ pair_offset,
                               const int32_t* __restrict__ pair_ref, const double* __restrict__ pair_q,
                               const double* __restrict__ frame_vecs, int64_t n_ref, int n_o, int halfspace,
-                              OrientTable tab, float* __restrict__ gs, double* __restrict__ contacts) {
+                              OrientTable tab, float* __restrict__ gs, double* __restrict__ contacts, int64_t* __restrict__ n_rows_out) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n_pairs = pair_offset[n_ref];
+    if (row == 0 && n_rows_out) *n_rows_out = n_pairs * n_o;       // number of posed grasps (bt_ags_pipeline: n_grasps)
     if (row >= n_pairs * n_o) return;
     const int64_t slot = row / n_o;                   // target-major slot: owns width + contacts of this row
     const int64_t ref = pair_ref[slot];
@@ -1007,14 +1125,65 @@ extern "C" int bt_expand_orientations(const double* d_ref_pts, const int64_t* d_
                                       int64_t n_ref, int64_t cap_pairs, int32_t n_o, int32_t halfspace,
                                       const double* h_cos, const double* h_sin, float* d_gs, double* d_contacts,
                                       void* stream) {
+    return bt::expand_impl(d_ref_pts, d_pair_offset, d_pair_ref, d_pair_q, d_frame_vecs, n_ref, cap_pairs, n_o, halfspace, h_cos, h_sin,
+                           d_gs, d_contacts, nullptr, stream);
+}
+
+int bt::expand_impl(const double* d_ref_pts, const int64_t* d_pair_offset, const int32_t* d_pair_ref, const double* d_pair_q,
+                    const double* d_frame_vecs, int64_t n_ref, int64_t cap_pairs, int32_t n_o, int32_t halfspace, const double* h_cos,
+                    const double* h_sin, float* d_gs, double* d_contacts, int64_t* d_n_rows, void* stream) {
     BT_REQUIRE(d_ref_pts && d_pair_offset && d_pair_ref && d_pair_q && d_gs && h_cos && h_sin, "null pointer");
     BT_REQUIRE(halfspace || d_frame_vecs, "frame vectors required unless halfspace");
     BT_REQUIRE(n_o >= 1 && n_o <= 64, "n_orientations must be in [1, 64]");
-    if (cap_pairs <= 0 || n_ref <= 0) return BT_OK;
+    if (cap_pairs <= 0 || n_ref <= 0) {
+        if (d_n_rows) BT_CUDA(cudaMemsetAsync(d_n_rows, 0, sizeof(int64_t), (cudaStream_t)stream));
+        return BT_OK;
+    }
     OrientTable tab;
     for (int i = 0; i < 64; ++i) { tab.c[i] = i < n_o ? h_cos[i] : 0.0; tab.s[i] = i < n_o ? h_sin[i] : 0.0; }
     expand_kernel<<<(unsigned)ceil_div(cap_pairs * n_o, 128), 128, 0, (cudaStream_t)stream>>>(
-        d_ref_pts, d_pair_offset, d_pair_ref, d_pair_q, d_frame_vecs, n_ref, n_o, halfspace, tab, d_gs, d_contacts);
+        d_ref_pts, d_pair_offset, d_pair_ref, d_pair_q, d_frame_vecs, n_ref, n_o, halfspace, tab, d_gs, d_contacts, d_n_rows);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
+
+// S1 + S2 + frame vectors in one launch (any subset; see generate_kernel).  d_seed_add: nullable device-resident seed offset.
+int bt::generate_impl(const bt_mesh* mesh, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed, const uint64_t* d_seed_add,
+                      int do_sample, int do_dirs, int do_frame, double* d_pts, double* d_nrm, double* d_frame, double* d_dirs, void* stream) {
+    BT_REQUIRE(mesh && d_nrm, "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
+    BT_REQUIRE((!do_sample || d_pts) && (!do_dirs || d_dirs) && (!do_frame || d_frame), "missing output buffer");
+    if (n_ref == 0 || !(do_sample || do_dirs || do_frame)) return BT_OK;
+    generate_kernel<<<(unsigned)ceil_div(n_ref, GEN_REFS), 256, 0, (cudaStream_t)stream>>>(
+        mesh->m.area_cdf, mesh->m.faces, mesh->m.verts, mesh->m.nF, n_ref, n_rays, angle, seed, d_seed_add, do_sample, do_dirs, do_frame,
+        d_pts, d_nrm, d_frame, d_dirs);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+// R7 in one launch + one memset (lean or record hits; see select_fused_kernel)
+int bt::ags_select_fused_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const double* d_hit_t, const double* d_ref_pts,
+                              const double* d_dirs, const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays, int32_t cap,
+                              int32_t max_targets, uint64_t seed, const uint64_t* d_seed_add, int32_t* d_pair_count,
+                              int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs, void* stream) {
+    BT_REQUIRE(d_hit_count && d_pair_count && d_pair_offset && d_pair_ref && d_pair_q, "null pointer");
+    BT_REQUIRE(d_hits || (d_hit_t && d_ref_pts && d_dirs && d_valid_mask), "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_rays > 0 && cap >= 1 && max_targets >= 1, "bad counts");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_ref == 0) {
+        BT_CUDA(cudaMemsetAsync(d_pair_offset, 0, sizeof(int64_t), st));
+        return BT_OK;
+    }
+    HitSource hs{d_hit_t, d_ref_pts, d_dirs, n_ref * (int64_t)n_rays};
+    const int64_t n_blocks = ceil_div(n_ref, SEL_REFS);
+    Scratch state;                                              // [n_blocks] status words + the ticket counter
+    BT_CUDA(state.alloc(sizeof(unsigned long long) * (n_blocks + 1), st));
+    BT_CUDA(cudaMemsetAsync(state.p, 0, sizeof(unsigned long long) * (n_blocks + 1), st));
+    select_fused_kernel<<<(unsigned)n_blocks, 32 * SEL_REFS, 0, st>>>(
+        d_hit_count, d_hits, hs, d_valid_mask, n_ref, n_rays, cap, max_targets, seed, d_seed_add, state.as<unsigned long long>(),
+        reinterpret_cast<unsigned*>(state.as<unsigned long long>() + n_blocks), (unsigned)n_blocks, d_pair_count, d_pair_offset, cap_pairs,
+        d_pair_ref, d_pair_q);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+

@@ -640,43 +640,32 @@ collide_exact_kernel(const int4* __restrict__ entries, const unsigned* __restric
     }
 }
 
-// ---- compaction: block counts via ballot/popc -> scan of block totals -> ordered scatter ---------------------
+// ---- compaction in ONE launch: ballot/popc counts per block, a single-pass chained scan of the block totals across the
+// grid (decoupled look-back, common.cuh), ordered scatter ---------------------------------------------------------------
 constexpr int CB = 256;
 
-__global__ void compact_count_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
-                                     const int64_t* __restrict__ d_n, int32_t* __restrict__ block_count) {
-    __shared__ int warp_tot[CB / 32];
-    const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    const int64_t i = blockIdx.x * (int64_t)CB + threadIdx.x;
-    const bool k = (i < n) && (mask[i] == keep);
-    const unsigned bal = __ballot_sync(0xffffffffu, k);
-    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-#pragma unroll
-        for (int w = 0; w < CB / 32; ++w) t += warp_tot[w];
-        block_count[blockIdx.x] = t;
-    }
-}
-
-// The kept rows of a block are contiguous in the destination ([block_offset, block_offset + run)), so the block stages its
-// 256 source rows in shared memory (coalesced 8-byte loads), builds the dst->src map from the ballot ranks and streams
-// the run out as consecutive 32-byte stores: full-line writes whatever the destination is -- local HBM, a peer GPU's
-// memory over NVLink (the multi-GPU gather is this store, see distributed.PeerGather) or mapped host memory over PCIe
+// The kept rows of a block are contiguous in the destination ([offset, offset + run)), so the block stages its 256 source
+// rows in shared memory (coalesced 8-byte loads), builds the dst->src map from the ballot ranks and streams the run out as
+// consecutive 32-byte stores: full-line writes whatever the destination is -- local HBM, a peer GPU's memory over NVLink
+// (the multi-GPU gather is this store, see distributed.PeerGather) or mapped host memory over PCIe
 // (AntipodalGraspSampler.evaluate_host).  A 14-float row is 7 words, a 6-double contact record 6 words; both row sizes
 // are multiples of 8 bytes, so every word is aligned.
-__global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
-                                       const int64_t* __restrict__ d_n, const int64_t* __restrict__ block_offset,
-                                       int64_t n_blocks, const float* __restrict__ gs, const double* __restrict__ contacts,
+__global__ void __launch_bounds__(CB) compact_kernel(const uint8_t* __restrict__ mask, uint8_t keep, int64_t n_cap,
+                                       const int64_t* __restrict__ d_n, unsigned long long* status, unsigned* ticket,
+                                       unsigned n_blocks, const float* __restrict__ gs, const double* __restrict__ contacts,
                                        float* __restrict__ out_gs, double* __restrict__ out_contacts, int64_t* __restrict__ n_out,
                                        const int64_t* __restrict__ d_base) {
     __shared__ int warp_off[CB / 32];
     __shared__ int run_s;
+    __shared__ unsigned s_bid;
+    __shared__ unsigned long long s_excl;
     __shared__ uint16_t src_of[CB];
     __shared__ double tile[CB * 7];                       // 14 KB: the block's rows (7 words each), then its contacts (6 each)
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
     const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    const int64_t row0 = blockIdx.x * (int64_t)CB;
+    const int64_t row0 = bid * (int64_t)CB;
     const int64_t i = row0 + threadIdx.x;
     const bool k = (i < n) && (mask[i] == keep);
     const unsigned bal = __ballot_sync(0xffffffffu, k);
@@ -688,18 +677,25 @@ __global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __re
         for (int e = threadIdx.x; e < rows_here * 7; e += CB) tile[e] = src[e];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
+    if (w == 0) {
+        int c = lane < CB / 32 ? warp_off[lane] : 0;
+        int incl = c;
 #pragma unroll
-        for (int q = 0; q < CB / 32; ++q) { int c = warp_off[q]; warp_off[q] = run; run += c; }
-        run_s = run;
-        if (blockIdx.x == n_blocks - 1 && n_out) *n_out = block_offset[blockIdx.x] + run + (d_base ? *d_base : 0);
+        for (int s = 1; s < CB / 32; s <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += v; }
+        if (lane < CB / 32) warp_off[lane] = incl - c;
+        const int run = __shfl_sync(0xffffffffu, incl, CB / 32 - 1);
+        const unsigned long long excl = lookback_exclusive(status, bid, (unsigned long long)run, lane);
+        if (lane == 0) {
+            run_s = run;
+            s_excl = excl;
+            if (bid == n_blocks - 1 && n_out) *n_out = (int64_t)excl + run + (d_base ? *d_base : 0);
+        }
     }
     __syncthreads();
     if (k) src_of[warp_off[w] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
     __syncthreads();
     const int run = run_s;
-    const int64_t dst0 = block_offset[blockIdx.x] + (d_base ? *d_base : 0);      // appending behind an earlier batch's rows
+    const int64_t dst0 = (int64_t)s_excl + (d_base ? *d_base : 0);      // appending behind an earlier batch's rows
     // the run leaves as 32-byte stores (STG.E.256; up to three 8-byte words in front / behind where the run is not 32-byte
     // aligned): a warp store covers 1 KB of contiguous destination, which is what a link wants to see (against 16-byte
     // stores: the same over NVLink, 1.26 -> 1.20 ms for the end-to-end call over PCIe)
@@ -927,6 +923,12 @@ extern "C" __attribute__((visibility("default"))) int bt_debug_collide_stats(uns
 extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts,
                           int64_t n, const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out,
                           const int64_t* d_base, void* stream) {
+    return bt::compact_impl(d_mask, keep_value, d_gs, d_contacts, n, d_n, d_out_gs, d_out_contacts, d_n_out, d_base, stream);
+}
+
+int bt::compact_impl(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts, int64_t n,
+                     const int64_t* d_n, float* d_out_gs, double* d_out_contacts, int64_t* d_n_out, const int64_t* d_base,
+                     void* stream) {
     BT_REQUIRE(d_mask && d_gs && d_out_gs && d_n_out, "null pointer");
     BT_REQUIRE(n >= 0, "negative count");
     BT_REQUIRE(((reinterpret_cast<uintptr_t>(d_gs) | reinterpret_cast<uintptr_t>(d_out_gs)) & 7) == 0, "grasp rows must be 8-byte aligned");
@@ -938,22 +940,13 @@ extern "C" int bt_compact(const uint8_t* d_mask, uint8_t keep_value, const float
         return BT_OK;
     }
     const int64_t n_blocks = ceil_div(n, CB);
-    Scratch counts, offsets, tmp;
-    BT_CUDA(counts.alloc(sizeof(int32_t) * n_blocks, st));
-    BT_CUDA(offsets.alloc(sizeof(int64_t) * n_blocks, st));
-    compact_count_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, counts.as<int32_t>());
-    BT_LAUNCH_CHECK();
-    if (n_blocks <= BT_SMALL_SCAN_MAX) {
-        small_scan_kernel<int32_t><<<1, 1024, 0, st>>>(counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, 0);
-        BT_LAUNCH_CHECK();
-    } else {
-        size_t tmp_bytes = 0;
-        BT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
-        BT_CUDA(tmp.alloc(tmp_bytes, st));
-        BT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int32_t>(), offsets.as<int64_t>(), (int)n_blocks, st));
-    }
-    compact_scatter_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, offsets.as<int64_t>(), n_blocks,
-                                                              d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out, d_base);
+    BT_REQUIRE(n_blocks < ((int64_t)1 << 31), "too many rows");
+    Scratch state;                                              // [n_blocks] status words of the chained scan + the ticket counter
+    BT_CUDA(state.alloc(sizeof(unsigned long long) * (n_blocks + 1), st));
+    BT_CUDA(cudaMemsetAsync(state.p, 0, sizeof(unsigned long long) * (n_blocks + 1), st));
+    compact_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, state.as<unsigned long long>(),
+                                                      reinterpret_cast<unsigned*>(state.as<unsigned long long>() + n_blocks), (unsigned)n_blocks,
+                                                      d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out, d_base);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

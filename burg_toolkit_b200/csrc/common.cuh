@@ -135,6 +135,45 @@ __global__ void __launch_bounds__(1024) small_scan_kernel(const TIn* __restrict_
 }
 #endif
 
+// ---- single-pass chained scan across the blocks of a grid (decoupled look-back), used by the one-launch target selection
+// and the one-launch compaction.  Status word per block: bits 63..62 = 1 aggregate / 2 inclusive prefix, rest = value.
+// Block ids must come from a ticket counter (atomicAdd), so that a block only waits for blocks that are already running.
+#ifdef __CUDACC__
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// warp-wide look-back of block `bid` with aggregate `agg`: returns the exclusive prefix (sum of the aggregates of blocks
+// 0 .. bid-1) to every lane and publishes the inclusive prefix of `bid`
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status, unsigned bid, unsigned long long agg, int lane) {
+    if (lane == 0) st_status(status + bid, (bid == 0 ? LB_PREFIX : LB_AGG) | agg);
+    unsigned long long run = 0;
+    int pos = (int)bid - 1;
+    while (pos >= 0) {
+        const int idx = pos - lane;
+        unsigned long long st = LB_PREFIX;                     // lanes before block 0: an empty inclusive prefix
+        if (idx >= 0) { do { st = ld_status(status + idx); } while ((st >> 62) == 0ull); }
+        const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
+        const int first = pm ? __ffs(pm) - 1 : 31;             // nearest predecessor that already knows its inclusive prefix
+        unsigned long long v = lane <= first ? (st & LB_VALUE) : 0ull;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        run += v;
+        if (pm) break;
+        pos -= 32;
+    }
+    if (lane == 0 && bid != 0) st_status(status + bid, LB_PREFIX | (run + agg));
+    return run;
+}
+#endif
+
 // ---- instrumentation (bt_debug_set_counters): when a counter array is installed the traversal kernels are launched in
 // their STATS instantiation and accumulate work counts there; slots:
 //   0 cast: LBVH nodes visited      1 cast: float32 leaf pre-tests     2 cast: exact float64 ray/triangle tests
@@ -189,6 +228,19 @@ int ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double* d_
 int ags_select_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const double* d_hit_t, const double* d_ref_pts, const double* d_dirs,
                     const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays, int32_t cap, int32_t max_targets, uint64_t seed,
                     int32_t* d_pair_count, int64_t* d_pair_offset, int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs, void* stream);
+
+int ags_select_fused_impl(const int32_t* d_hit_count, const bt_hit* d_hits, const double* d_hit_t, const double* d_ref_pts,
+                          const double* d_dirs, const uint32_t* d_valid_mask, int64_t n_ref, int32_t n_rays, int32_t cap,
+                          int32_t max_targets, uint64_t seed, const uint64_t* d_seed_add, int32_t* d_pair_count, int64_t* d_pair_offset,
+                          int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs, void* stream);
+int generate_impl(const bt_mesh* mesh, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed, const uint64_t* d_seed_add,
+                  int do_sample, int do_dirs, int do_frame, double* d_pts, double* d_nrm, double* d_frame, double* d_dirs, void* stream);
+int expand_impl(const double* d_ref_pts, const int64_t* d_pair_offset, const int32_t* d_pair_ref, const double* d_pair_q,
+                const double* d_frame_vecs, int64_t n_ref, int64_t cap_pairs, int32_t n_o, int32_t halfspace, const double* h_cos,
+                const double* h_sin, float* d_gs, double* d_contacts, int64_t* d_n_rows, void* stream);
+// single-pass stream compaction (collide.cu); bt_compact is its C-ABI face
+int compact_impl(const uint8_t* d_mask, uint8_t keep_value, const float* d_gs, const double* d_contacts, int64_t n, const int64_t* d_n,
+                 float* d_out_gs, double* d_out_contacts, int64_t* d_n_out, const int64_t* d_base, void* stream);
 
 }  // namespace bt
 

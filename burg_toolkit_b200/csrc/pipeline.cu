@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <vector>
 
 struct bt_timer {
     int device = 0;
@@ -14,9 +15,6 @@ struct bt_timer {
 };
 
 namespace bt {
-__global__ void scale_count_kernel(const int64_t* __restrict__ n_pairs, int n_o, int64_t* __restrict__ n_rows) {
-    *n_rows = *n_pairs * n_o;
-}
 // number of valid rows inside the range [row0, row0 + n_cap) of a list whose valid length is *d_n
 __global__ void range_count_kernel(const int64_t* __restrict__ d_n, int64_t row0, int64_t n_cap, int64_t* __restrict__ out) {
     const int64_t v = *d_n - row0;
@@ -108,35 +106,27 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     if (timer) for (int i = 0; i < BT_N_STAGES; ++i) timer->ran[i] = false;
     const int n_o = cfg->n_orientations;
 
-    if (b->sample_surface) {
+    // S1 + S2 + frame vectors: whatever the caller did not supply, in one launch
+    const int gen_frame = (b->generate_frame_vecs && !cfg->halfspace) ? 1 : 0;
+    if (b->sample_surface || b->generate_dirs || gen_frame) {
         STAGE_BEGIN(0);
-        STAGE_CALL(bt_sample_surface(target, n_ref, seed, b->ref_pts, b->ref_nrm, nullptr, stream));
+        STAGE_CALL(generate_impl(target, n_ref, cfg->n_rays, cfg->ags.angle_max, seed, b->seed_add, b->sample_surface, b->generate_dirs,
+                                 gen_frame, b->ref_pts, b->ref_nrm, b->frame_vecs, b->dirs, stream));
         STAGE_END(0);
-    }
-    if (b->generate_dirs) {
-        STAGE_BEGIN(1);
-        STAGE_CALL(bt_cone_rays(b->ref_nrm, n_ref, cfg->n_rays, cfg->ags.angle_max, seed + 0x1000, b->dirs, stream));
-        STAGE_END(1);
     }
     STAGE_BEGIN(2);
     STAGE_CALL(ags_cast_impl(target, b->ref_pts, b->dirs, n_ref, cfg->n_rays, &cfg->ags, b->hit_count, b->hits, b->hits ? nullptr : b->hit_t,
                              b->valid_mask, b->overflow, !b->hits && cfg->cone_culling, stream));
     STAGE_END(2);
     STAGE_BEGIN(3);
-    STAGE_CALL(ags_select_impl(b->hit_count, b->hits, b->hit_t, b->ref_pts, b->dirs, b->valid_mask, n_ref, cfg->n_rays, cfg->ags.max_hits_per_ray,
-                               cfg->max_targets, seed ? seed + 0x2000 : 0 /* seed 0: first valid hit in canonical order */, b->pair_count,
-                               b->pair_offset, b->pair_ref, b->pair_q, b->cap_pairs, stream));
+    STAGE_CALL(ags_select_fused_impl(b->hit_count, b->hits, b->hit_t, b->ref_pts, b->dirs, b->valid_mask, n_ref, cfg->n_rays,
+                                     cfg->ags.max_hits_per_ray, cfg->max_targets,
+                                     seed ? seed + 0x2000 : 0 /* seed 0: first valid hit in canonical order */, b->seed_add, b->pair_count,
+                                     b->pair_offset, b->pair_ref, b->pair_q, b->cap_pairs, stream));
     STAGE_END(3);
-    if (b->generate_frame_vecs && !cfg->halfspace) {
-        STAGE_BEGIN(4);
-        STAGE_CALL(bt_random_unit_vectors(n_ref, seed + 0x3000, b->frame_vecs, stream));
-        STAGE_END(4);
-    }
     STAGE_BEGIN(5);
-    STAGE_CALL(bt_expand_orientations(b->ref_pts, b->pair_offset, b->pair_ref, b->pair_q, b->frame_vecs, n_ref, b->cap_pairs,
-                                      n_o, cfg->halfspace, cfg->orient_cos, cfg->orient_sin, b->gs, b->contacts, stream));
-    scale_count_kernel<<<1, 1, 0, st>>>(b->pair_offset + n_ref, n_o, b->n_grasps);
-    BT_LAUNCH_CHECK();
+    STAGE_CALL(expand_impl(b->ref_pts, b->pair_offset, b->pair_ref, b->pair_q, b->frame_vecs, n_ref, b->cap_pairs, n_o, cfg->halfspace,
+                           cfg->orient_cos, cfg->orient_sin, b->gs, b->contacts, b->n_grasps, stream));
     STAGE_END(5);
     if (cfg->check_collisions) {
         const int64_t cap_rows = b->cap_pairs * n_o;
@@ -184,3 +174,93 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     }
     return BT_OK;
 }
+
+// ---- CUDA graphs: capture a sequence of library calls on a stream once, replay it with one launch -------------------------
+// bt_ags_pipeline enqueues ~10 kernels, a handful of memsets and stream-ordered scratch allocations: ~0.2 ms of host time
+// per call, which is what a small batch (config 1) and the end-to-end call pay.  Captured into a graph the same work is one
+// cudaGraphLaunch (~10 us); the seed of a replay comes from the device (bt_pipeline_buffers.seed_add, set with bt_set_u64).
+struct bt_graph {
+    int device = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+
+namespace bt {
+__global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
+}
+
+extern "C" int bt_set_u64(uint64_t* d_ptr, uint64_t value, void* stream) {
+    BT_REQUIRE(d_ptr, "null pointer");
+    bt::set_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_ptr, value);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_graph_begin_capture(void* stream) {
+    BT_REQUIRE(stream, "capture needs a non-default stream");
+    bt::retain_pool_memory();
+    BT_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return BT_OK;
+}
+
+extern "C" int bt_graph_end_capture(void* stream, bt_graph** out) {
+    BT_REQUIRE(stream && out, "null pointer");
+    cudaGraph_t g = nullptr;
+    BT_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    BT_REQUIRE(g, "the capture produced no graph (a call failed while capturing)");
+    bt_graph* h = new bt_graph();
+    cudaGetDevice(&h->device);
+    h->graph = g;
+    cudaError_t e = cudaGraphInstantiate(&h->exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); delete h; return bt::cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+    *out = h;
+    return BT_OK;
+}
+
+extern "C" int bt_graph_launch(bt_graph* g, void* stream) {
+    BT_REQUIRE(g && g->exec, "null graph");
+    BT_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+extern "C" int bt_graph_destroy(bt_graph* g) {
+    if (!g) return BT_OK;
+    cudaSetDevice(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return BT_OK;
+}
+
+// what a graph holds: number of nodes, number of kernel nodes, and the kernels' names ('\n'-separated, in node order) --
+// bench.py counts its launches with this instead of keeping a list by hand
+extern "C" int bt_graph_info(const bt_graph* g, int32_t* n_nodes, int32_t* n_kernel_nodes, char* names, int64_t names_cap) {
+    BT_REQUIRE(g && g->graph, "null graph");
+    size_t n = 0;
+    BT_CUDA(cudaGraphGetNodes(g->graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) BT_CUDA(cudaGraphGetNodes(g->graph, nodes.data(), &n));
+    int kernels = 0;
+    int64_t used = 0;
+    if (names && names_cap > 0) names[0] = 0;
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType type;
+        BT_CUDA(cudaGraphNodeGetType(nodes[i], &type));
+        if (type != cudaGraphNodeTypeKernel) continue;
+        ++kernels;
+        cudaKernelNodeParams kp;
+        const char* nm = "?";
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func) {
+            const char* raw = nullptr;
+            if (cudaFuncGetName(&raw, kp.func) == cudaSuccess && raw) nm = raw;
+        } else cudaGetLastError();
+        if (names && names_cap > 0) {
+            const int64_t len = (int64_t)strlen(nm);
+            if (used + len + 2 <= names_cap) { memcpy(names + used, nm, len); names[used + len] = '\n'; used += len + 1; names[used] = 0; }
+        }
+    }
+    if (n_nodes) *n_nodes = (int32_t)n;
+    if (n_kernel_nodes) *n_kernel_nodes = kernels;
+    return BT_OK;
+}
+

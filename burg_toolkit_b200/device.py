@@ -199,6 +199,46 @@ class StageTimer:
         return {name: float(ms[i]) for i, name in enumerate(nat.STAGE_NAMES) if ms[i] >= 0}
 
 
+class DeviceGraph:
+    """A captured sequence of library calls (``bt_graph_*``): one ``cudaGraphLaunch`` per replay.  ``keep`` holds the
+    objects whose device memory the graph refers to (meshes, gripper, workspace tensors)."""
+
+    def __init__(self, handle, keep=()):
+        self.handle, self.keep = handle, keep
+        self._finalizer = weakref.finalize(self, _destroy, 'bt_graph_destroy', handle)
+
+    def launch(self, stream):
+        nat.call('bt_graph_launch', self.handle, stream)
+
+    def info(self):
+        """-> (n_nodes, n_kernel_nodes, [kernel names in node order])"""
+        n, k = C.c_int32(), C.c_int32()
+        buf = C.create_string_buffer(1 << 16)
+        nat.call('bt_graph_info', self.handle, C.byref(n), C.byref(k), buf, len(buf))
+        return n.value, k.value, [short_kernel_name(x) for x in buf.value.decode().split('\n') if x]
+
+
+def short_kernel_name(mangled):
+    """'_ZN2bt15traverse_kernelILb0ELb1ELb1EEEv...' -> 'traverse_kernel<0,1,1>' (enough of an Itanium demangler for the
+    kernels of this library; anything else is returned as it is)"""
+    import re
+    m = re.match(r'_ZN2bt(\d+)', mangled)
+    if not m:
+        m2 = re.match(r'_Z(\d+)', mangled)
+        if not m2:
+            return mangled
+        n = int(m2.group(1))
+        return mangled[m2.end():m2.end() + n]
+    n = int(m.group(1))
+    name = mangled[m.end():m.end() + n]
+    rest = mangled[m.end() + n:]
+    if rest.startswith('I'):
+        args = re.findall(r'L[bi](\d+)E', rest.split('EEv')[0] + 'E')
+        if args:
+            name += '<' + ','.join(args) + '>'
+    return name
+
+
 class PipelineWorkspace:
     """All device buffers of one ``bt_ags_pipeline`` call, allocated once per shape (torch owns the memory)."""
 
@@ -232,6 +272,8 @@ class PipelineWorkspace:
         self.free_contacts = torch.zeros((rows, 2, 3), dtype=f64, device=d) if compact else None
         self.n_free = torch.zeros((1,), dtype=i64, device=d) if compact else None
         self.rows = rows
+        self.seed_add = torch.zeros((1,), dtype=i64, device=d)      # device-resident seed offset (graph replays: bt_set_u64)
+        self.graphs = {}                                             # captured bt_ags_pipeline calls (DeviceGraph) by call signature
         # optional raw destinations for the compaction outputs ('free_gs', 'free_contacts', 'n_free' -> address): a peer
         # GPU's buffer (distributed.PeerGather) or mapped pinned host memory (evaluate_host); the kernel stores there directly
         self.redirect = {}
@@ -244,6 +286,7 @@ class PipelineWorkspace:
             t = getattr(self, name)
             setattr(b, name, None if t is None else int(self.redirect.get(name) or t.data_ptr()))
         b.free_base, b.compact_after = self.redirect.get('free_base'), self.redirect.get('compact_after')
+        b.seed_add = self.seed_add.data_ptr()
         b.sample_surface, b.generate_dirs, b.generate_frame_vecs = int(sample_surface), int(generate_dirs), int(generate_frame_vecs)
         b.cap_pairs = self.cap_pairs
         return b

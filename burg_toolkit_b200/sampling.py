@@ -82,6 +82,23 @@ class CastResult:
         return ref_idx, ray_idx, raw[sel]
 
 
+class PendingHostBatch:
+    """A batch in flight (``AntipodalGraspSampler.submit_host``); ``result()`` waits for it and returns host views."""
+
+    def __init__(self, event, pinned, n_ref, n_candidates):
+        self.event, self.pinned, self.n_ref, self.n_candidates = event, pinned, n_ref, n_candidates
+
+    def done(self):
+        return self.event.query()
+
+    def result(self):
+        self.event.synchronize()
+        p = self.pinned
+        k = int(p['out_n'][0])
+        return dict(gs=GraspSet.from_array(p['out_gs'][:k].numpy()), contacts=p['out_c'][:k].numpy(), n_grasps=int(p['out_n'][2]),
+                    n_free=k, h2d_bytes=2 * self.n_ref * 24, d2h_bytes=k * (56 + 48) + 16, n_candidates=self.n_candidates, chunks=1)
+
+
 class AntipodalGraspSampler:
     """A sampler for antipodal grasps: looks for two contact points that satisfy the antipodal
     constraint for a friction coefficient ``mu`` (reference sampling.py:51-397)."""
@@ -254,7 +271,8 @@ class AntipodalGraspSampler:
 
     def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, directions=None, frame_vecs=None,
                      check_collisions=True, collision_width_tolerance=0.01, use_width=True, additional_objects=None,
-                     exclude_shape=False, compact=True, timer=None, destinations=None, slot=0, tail_splits=1, keep_hits=False):
+                     exclude_shape=False, compact=True, timer=None, destinations=None, slot=0, tail_splits=1, keep_hits=False,
+                     graph=False):
         """The whole device pipeline for one batch of candidates in ONE C-ABI call (``bt_ags_pipeline``); nothing
         leaves the GPU and the host never waits:
 
@@ -279,6 +297,9 @@ class AntipodalGraspSampler:
         masks, contacts and grasps are the same bits, ``hit_count`` then counts only the crossings that were looked at.
         ``tail_splits`` > 1: collision check + compaction run over that many row ranges on two streams, so a link-bound
         compaction (host / peer destination) overlaps the next range's collision walk; the output is identical.
+        ``graph``: replay the call as a captured CUDA graph (``bt_graph_*``): the first call with a given shape, mesh and
+        configuration captures it, later ones cost one graph launch instead of ~25 driver calls (the seed reaches the
+        kernels through device memory); same results, bit for bit.  Ignored with a ``timer`` or a ``compact_after`` event.
         -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
         torch = nat.require_cuda()
         device = self._device()
@@ -331,13 +352,43 @@ class AntipodalGraspSampler:
                 scene = self._scene(meshes, device)
                 gripper = self._device_gripper(device)
             ws.redirect = dict(destinations or {})
-            bufs = ws.buffers(ref_points is None, directions is None, frame_vecs is None)
-            nat.call('bt_ags_pipeline', dm.handle, None if scene is None else scene.handle,
-                     None if gripper is None else gripper.handle, C.byref(cfg), C.byref(bufs), n_ref, int(seed),
-                     None if timer is None else timer.handle, nat.current_stream())
+            gen = (ref_points is None, directions is None, frame_vecs is None)
+            stream = nat.current_stream()
+            seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            if graph and timer is None and tail_splits <= 1 and 'compact_after' not in ws.redirect:
+                # the captured call carries the seed's "zero or not" (canonical vs random target choice); the rest of the
+                # seed reaches the kernels through ws.seed_add, so one graph serves every seed
+                base = 0 if seed == 0 else 1
+                gkey = (sig, dm.handle.value, None if scene is None else scene.handle.value,
+                        None if gripper is None else gripper.handle.value, gen, tuple(sorted(ws.redirect.items())), base, n_ref)
+                g = ws.graphs.get(gkey)
+                if g is None:
+                    if len(ws.graphs) >= 16:
+                        ws.graphs.pop(next(iter(ws.graphs)))
+                    cap = self.__dict__.setdefault('_capture_streams', {}).setdefault(device, torch.cuda.Stream(device))
+                    bufs = ws.buffers(*gen)
+                    nat.call('bt_graph_begin_capture', cap.cuda_stream)
+                    try:
+                        nat.call('bt_ags_pipeline', dm.handle, None if scene is None else scene.handle,
+                                 None if gripper is None else gripper.handle, C.byref(cfg), C.byref(bufs), n_ref, base, None, cap.cuda_stream)
+                    finally:
+                        handle = C.c_void_p()
+                        nat.call('bt_graph_end_capture', cap.cuda_stream, C.byref(handle))
+                    g = ws.graphs[gkey] = dev.DeviceGraph(handle, keep=(dm, scene, gripper, ws))
+                nat.call('bt_set_u64', ws.seed_add.data_ptr(), (seed - base) & 0xFFFFFFFFFFFFFFFF, stream)
+                g.launch(stream)
+                ws.last_graph, ws.seed_add_dirty = g, True
+            else:
+                if getattr(ws, 'seed_add_dirty', False):               # a graph replay left its offset there
+                    ws.seed_add.zero_()
+                    ws.seed_add_dirty = False
+                bufs = ws.buffers(*gen)
+                nat.call('bt_ags_pipeline', dm.handle, None if scene is None else scene.handle,
+                         None if gripper is None else gripper.handle, C.byref(cfg), C.byref(bufs), n_ref, seed,
+                         None if timer is None else timer.handle, stream)
         out = dict(n_ref=n_ref, n_candidates=n_ref * int(self.n_rays), pair_count=ws.pair_count, pair_offset=ws.pair_offset,
                    pair_ref=ws.pair_ref, pair_q=ws.pair_q, gs=ws.gs, contacts=ws.contacts, n_grasps=ws.n_grasps,
-                   overflow=ws.overflow, ref_pts=ws.ref_pts, ref_nrm=ws.ref_nrm, directions=ws.dirs,
+                   overflow=ws.overflow, ref_pts=ws.ref_pts, ref_nrm=ws.ref_nrm, directions=ws.dirs, frame_vecs=ws.frame_vecs,
                    cast=CastResult(ws.hit_count, ws.hits, ws.overflow, n_ref, int(self.n_rays), cap, ws.valid_mask) if keep_hits else None,
                    hit_count=ws.hit_count, valid_mask=ws.valid_mask, hit_t=ws.hit_t, cap_pairs=ws.cap_pairs)
         if check_collisions:
@@ -380,6 +431,8 @@ class AntipodalGraspSampler:
         chunks = max(1, min(chunks, n // 256, 64)) if push else 1
         while n % chunks:                                   # equal batches only (one workspace shape per stream)
             chunks -= 1
+        if push and chunks == 1 and kwargs['tail_splits'] <= 1 and n > 0:
+            return self.submit_host(ref_points, ref_normals, seed=seed, slot=0, pinned=pinned, **kwargs).result()
         with torch.cuda.device(device):
             for key, arr in (('pts', ref_points), ('nrm', ref_normals)):
                 if key not in pinned or pinned[key].shape[0] != n:
@@ -438,6 +491,51 @@ class AntipodalGraspSampler:
         return dict(gs=GraspSet.from_array(pinned['out_gs'][:k].numpy()), contacts=pinned['out_c'][:k].numpy(),
                     n_grasps=int(out_n[2:2 + chunks].sum()), n_free=k, h2d_bytes=h2d, d2h_bytes=d2h, n_candidates=n_candidates,
                     chunks=chunks)
+
+    def submit_host(self, ref_points, ref_normals, seed=1, slot=0, pinned=None, **kwargs):
+        """Asynchronous form of ``evaluate_host`` (collision check + compaction on): copies the reference points into
+        pinned staging memory, enqueues upload + pipeline (replayed as a CUDA graph) on the private stream of ``slot`` and
+        returns at once; ``.result()`` of the returned handle waits for that batch only.  With two slots used
+        alternately, batch i's PCIe stores (the compaction kernel writes the kept rows straight into the pinned result
+        arrays) overlap batch i + 1's ray casting:
+
+            pending = ags.submit_host(pts0, nrm0, seed=1, slot=0)
+            for i in range(1, n_batches):
+                nxt = ags.submit_host(pts[i], nrm[i], seed=i + 1, slot=i & 1)
+                use(pending.result())            # views into slot (i - 1) & 1's pinned arrays: valid until that slot is resubmitted
+                pending = nxt
+
+        Results are the bits ``evaluate_host`` returns for the same arguments."""
+        torch = nat.require_cuda()
+        device = self._device()
+        n = len(ref_points)
+        cap = max(1, n * int(self.max_targets_per_ref_point)) * int(self.n_orientations)
+        if not (kwargs.get('check_collisions', True) and kwargs.get('compact', True)):
+            raise ValueError('submit_host needs the collision check and the compaction (use evaluate_host otherwise)')
+        slots = self.__dict__.setdefault('_host_slots', {})
+        hs = slots.get((device, slot))
+        if hs is None:
+            hs = slots[(device, slot)] = dict(stream=torch.cuda.Stream(device), event=torch.cuda.Event(), pinned={})
+        pinned = hs['pinned'] if pinned is None else pinned
+        with torch.cuda.device(device):
+            for key, arr in (('pts', ref_points), ('nrm', ref_normals)):
+                if key not in pinned or pinned[key].shape[0] != n:
+                    pinned[key] = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+                pinned[key].numpy()[...] = arr
+            if 'out_gs' not in pinned or pinned['out_gs'].shape[0] != cap:
+                pinned['out_gs'] = torch.empty((cap, 14), dtype=torch.float32).pin_memory()
+                pinned['out_c'] = torch.empty((cap, 2, 3), dtype=torch.float64).pin_memory()
+                pinned['out_n'] = torch.zeros((66,), dtype=torch.int64).pin_memory()      # [0] kept rows, [2] posed grasps
+            out_n = pinned['out_n']
+            dest = {'free_gs': pinned['out_gs'].data_ptr(), 'free_contacts': pinned['out_c'].data_ptr(), 'n_free': out_n.data_ptr()}
+            st = hs['stream']
+            st.wait_stream(torch.cuda.current_stream())
+            kwargs.setdefault('graph', True)
+            with torch.cuda.stream(st):
+                out = self.run_pipeline(pinned['pts'], pinned['nrm'], seed=seed, destinations=dest, slot=('host', slot), **kwargs)
+                out_n[2:3].copy_(out['n_grasps'], non_blocking=True)
+                hs['event'].record(st)
+        return PendingHostBatch(hs['event'], pinned, n, out['n_candidates'])
 
     # -----------------------------------------------------------------------------------------------
     # reference API

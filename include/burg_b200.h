@@ -230,7 +230,7 @@ BT_API int bt_peer_wait(const int64_t* d_words, int32_t n_words, int64_t epoch, 
  * boundary so a benchmark can read per-stage device times afterwards.  seed == 0 makes the target choice deterministic
  * (first valid hit in canonical order), any other seed keys the device RNG streams. */
 typedef struct bt_timer bt_timer;
-#define BT_N_STAGES 8        /* sample_surface, cone_rays, cast, select, frame_vectors, expand, collide, compact */
+#define BT_N_STAGES 8        /* generate (S1 + S2 + frame vectors), -, cast, select, -, expand, collide, compact */
 BT_API int bt_timer_create(int device, bt_timer** out);
 BT_API int bt_timer_destroy(bt_timer* timer);
 BT_API int bt_timer_read(bt_timer* timer, float* h_stage_ms /* [BT_N_STAGES], -1 for stages that did not run */);  /* synchronises */
@@ -280,11 +280,26 @@ typedef struct bt_pipeline_buffers {
     double*  hit_t;          /* [max_hits_per_ray, n_ref*n_rays] slot-major ray parameters (lean mode only)   */
     void*    compact_after;  /* nullable cudaEvent_t: the compaction stage waits for it (the previous batch's
                                 compaction on another stream, whose count is free_base)                       */
+    const uint64_t* seed_add; /* nullable [1] on the device: added to `seed` by every kernel that draws random numbers
+                                (a captured graph of the call is replayed with a new seed by storing it here: bt_set_u64) */
 } bt_pipeline_buffers;
 
 BT_API int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, const bt_gripper* gripper,
                     const bt_pipeline_config* config, const bt_pipeline_buffers* buffers, int64_t n_ref,
                     uint64_t seed, bt_timer* timer, void* stream);
+
+/* ---- CUDA graphs.  Every call of this library only enqueues work on the caller's stream, so a sequence of calls can be
+ * captured once (bt_graph_begin_capture ... calls ... bt_graph_end_capture; `stream` must not be the default stream) and
+ * replayed with bt_graph_launch: one launch instead of ~25 driver calls per bt_ags_pipeline.  The buffers are baked into
+ * the graph; a replay's random numbers are keyed by bt_pipeline_buffers.seed_add (device memory, set with bt_set_u64 on
+ * the same stream before the launch).  bt_graph_info: node counts and the '\n'-separated names of the kernel nodes. */
+typedef struct bt_graph bt_graph;
+BT_API int bt_graph_begin_capture(void* stream);
+BT_API int bt_graph_end_capture(void* stream, bt_graph** out);
+BT_API int bt_graph_launch(bt_graph* graph, void* stream);
+BT_API int bt_graph_info(const bt_graph* graph, int32_t* n_nodes, int32_t* n_kernel_nodes, char* names, int64_t names_cap);
+BT_API int bt_graph_destroy(bt_graph* graph);
+BT_API int bt_set_u64(uint64_t* d_ptr, uint64_t value, void* stream);
 
 /* ---- M1..M5: coverage (replaces metrics.coverage / coverage_brute_force, metrics.py:141-229, and the
  * distance functions they call, :9-77).  covered[i] = any_j ( 1000*|t_i - t_j| + deg(R_i, R_j) <= eps ),
