@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of the AGS + coverage hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ags_c3|ags_c4|coverage_c2|coverage_c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ags_c3|ags_c1|ags_c4|ags_c3_exhaustive|coverage_c2|coverage_c5]
 
-Prints ONE JSON line (rank 0).  Workloads (BASELINE.json `configs`):
+Prints ONE JSON line (rank 0).  The default workload (ags_c3, the configuration the metric is quoted on) also carries a
+`secondary` list with one block per other BASELINE configuration (each with its own roofline / e2e / cpu_baseline), at
+every N: coverage_c2, ags_c4, coverage_c5, ags_c3_exhaustive and (N = 1) ags_c1.  Workloads (BASELINE.json `configs`):
   ags_c3       config 3: AGS on the 99 904-triangle 'YCB-like' mesh, 10 000 reference points x 100 rays = 1 M
                candidates per step per GPU, max_targets_per_ref_point = 1, 12 orientations, gripper-vs-object
                collision + compaction.  metric: candidates/s.  (default; the config the metric's target is quoted on)
@@ -11,6 +13,8 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json `configs`):
   ags_c4       config 4: 20 objects (~1 M triangles) + ground slab, the target object changes every step, gripper vs scene.
   coverage_c2  config 2: coverage of two 100k grasp sets (perturbed pair).  metric: pairs/s.
   coverage_c5  config 5: 1 M x 1 M grasps; with several ranks the reference rows are sharded (strong scaling).
+  ags_c3_exhaustive  config 3 with EVERY valid hit of a reference point expanded (max_targets_per_ref_point = 128, reference
+               sampling.py:328-338): ~0.9 M contact pairs = ~11 M posed grippers per 1 M candidates -- the collision stage under load.
 
 A "step" is one pass of the device pipeline over one batch of synthetic candidates.  The timed region holds
 exactly K steps, each bracketed by CUDA events on the launching stream; L2 is flushed between steps (outside the
@@ -38,10 +42,7 @@ N_REF = 10_000
 N_RAYS = 100
 N_ORIENT = 12
 COV_N = 100_000
-# own kernels launched by one bt_ags_pipeline call, in order (CUB scans and memsets not counted)
-AGS_KERNELS = ['sample_surface_kernel', 'cone_rays_kernel', 'traverse_kernel', 'cast_kernel', 'zero_first_kernel', 'select_count_kernel',
-               'select_fill_kernel', 'unit_vectors_kernel', 'expand_kernel', 'scale_count_kernel', 'collide_kernel<lean>',
-               'collide_exact_kernel', 'collide_kernel<rescue>', 'compact_count_kernel', 'compact_scatter_kernel']
+EXHAUSTIVE_TARGETS = 128
 
 
 def measured_peaks():
@@ -168,7 +169,7 @@ def host_candidates_fast(mesh, n_ref, seed):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm (oracle port, all host threads)
+# CPU arm (oracle port: the reference's arithmetic in C with a BVH and OpenMP)
 # ---------------------------------------------------------------------------------------------------------------
 _CPU_MESHES = {}
 
@@ -181,7 +182,7 @@ def merged_scene(meshes):
     return v, f
 
 
-def cpu_ags(mesh, n_ref, seed=100, scene_meshes=None):
+def cpu_ags(mesh, n_ref, seed=100, scene_meshes=None, threads=None):
     """one bounded CPU sample of the AGS workload -> (candidates, seconds, threads); the BVH builds are not timed"""
     from oracle import cport
     from burg_toolkit_b200.gripper import ParallelJawGripper
@@ -191,7 +192,7 @@ def cpu_ags(mesh, n_ref, seed=100, scene_meshes=None):
         cs = cm if scene_meshes is None else cport.Mesh(*merged_scene(scene_meshes))
         _CPU_MESHES[key] = (cm, cs)
     cm, cs = _CPU_MESHES[key]
-    cport.set_num_threads(os.cpu_count() or 1)            # all host threads, also under torchrun (OMP_NUM_THREADS=1 there)
+    cport.set_num_threads(threads or os.cpu_count() or 1)   # all host threads by default, also under torchrun (OMP_NUM_THREADS=1 there)
     pts, nrm, dirs, fv = host_candidates_fast(mesh, n_ref, seed)
     gt = ParallelJawGripper().tcp_triangles()
     t0 = time.perf_counter()
@@ -200,31 +201,68 @@ def cpu_ags(mesh, n_ref, seed=100, scene_meshes=None):
     return len(pts) * N_RAYS, dt, cport.num_threads(), out
 
 
-def cpu_coverage(n, seed=0):
-    """the reference's kd-tree coverage (scipy cKDTree + Python loop, metrics.py:161-229) restated in oracle/port.py"""
+def cpu_ags_record(mesh, n_ref_all, n_ref_one, scene_meshes=None, what='the same workload'):
+    """cpu_baseline record of an AGS workload: all host threads (the line's value) and ONE thread (the reference itself is
+    single-threaded Python), both on bounded samples"""
+    c, dt, threads, _ = cpu_ags(mesh, n_ref_all, scene_meshes=scene_meshes)
+    c1, dt1, _, _ = cpu_ags(mesh, n_ref_one, seed=101, scene_meshes=scene_meshes, threads=1)
+    return {'value': c / dt, 'unit': 'candidates/s', 'cores': threads, 'kind': 'port',
+            'sample': f'{n_ref_all} reference points x {N_RAYS} rays ({c} candidates) of {what}, oracle/coracle.c with OpenMP on '
+                      f'{threads} threads, {dt:.1f} s',
+            'one_thread': {'value': c1 / dt1, 'unit': 'candidates/s', 'cores': 1,
+                           'sample': f'{n_ref_one} reference points x {N_RAYS} rays ({c1} candidates), 1 thread, {dt1:.1f} s'},
+            'host_cpus': os.cpu_count()}
+
+
+def cpu_coverage(n, n_ref_sample=None):
+    """the reference's kd-tree coverage (scipy cKDTree + Python loop, metrics.py:161-229) restated in oracle/port.py; with
+    ``n_ref_sample`` only that many reference rows are evaluated against the FULL query set (config 5: the whole job would
+    take the better part of an hour and tens of GB of Python lists) and the pairs/s of the sample is reported"""
     from oracle import port
     ref, qry = coverage_sets(n)
+    if n_ref_sample is not None and n_ref_sample < len(ref):
+        ref = ref[np.random.default_rng(5).choice(len(ref), n_ref_sample, replace=False)]
     t0 = time.perf_counter()
     cov = port.covered_kd(ref, qry)
     dt = time.perf_counter() - t0
-    return n * len(qry), dt, 1, float(cov.mean())
+    return float(len(ref)) * len(qry), dt, 1, float(cov.mean())
+
+
+def cpu_coverage_record(workload, n_sample_c2=100_000, n_ref_sample_c5=4000):
+    if workload == 'coverage_c5':
+        p, dt, threads, cov = cpu_coverage(1_000_000, n_ref_sample_c5)
+        sample = (f'{n_ref_sample_c5} of the 1 000 000 reference rows against all 1 000 000 query rows (kd-tree coverage as metrics.py:161-229: scipy '
+                  f'cKDTree + Python loop, 1 thread), {dt:.1f} s; the rows are independent, so the whole 1 M x 1 M job extrapolates to '
+                  f'{dt * 1_000_000 / n_ref_sample_c5 / 60:.0f} min')
+    else:
+        p, dt, threads, cov = cpu_coverage(n_sample_c2)
+        sample = f'{n_sample_c2} x {n_sample_c2} grasps, kd-tree coverage (scipy cKDTree + Python loop as metrics.py:161-229), 1 thread, {dt:.1f} s'
+    return {'value': p / dt, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample, 'coverage_of_sample': cov,
+            'host_cpus': os.cpu_count()}
+
+
+def ags_workload_meshes(workload):
+    """-> (target meshes, scene meshes or None)"""
+    if workload in ('ags_c3', 'ags_c3_exhaustive'):
+        return [c3_mesh()], None
+    if workload == 'ags_c1':
+        from burg_toolkit_b200 import mesh as bmesh
+        return [bmesh.create_icosphere(5, 0.03)], None
+    scene_meshes = c4_scene().get_mesh_list()
+    return scene_meshes[1:], scene_meshes
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm on the host cores.  The reference is pure Python on third-party
+    leaves that cannot be installed here, so this arm runs the oracle port (oracle/coracle.c: same arithmetic, BVH broad
+    phase, OpenMP over all host threads -- far faster than the reference's own Python would be) on bounded samples."""
     if rank != 0:
         return
     cores = os.cpu_count()
-    if args.workload in ('ags_c1', 'ags_c3', 'ags_c4'):
-        scene_meshes = None
-        if args.workload == 'ags_c3':
-            mesh = c3_mesh()
-        elif args.workload == 'ags_c1':
-            from burg_toolkit_b200 import mesh as bmesh
-            mesh = bmesh.create_icosphere(5, 0.03)
-        else:
-            scene_meshes = c4_scene().get_mesh_list()
-            mesh = scene_meshes[1]
-        n_ref = args.cpu_ref_points
+    if args.workload.startswith('ags'):
+        targets, scene_meshes = ags_workload_meshes(args.workload)
+        mesh = targets[0]
+        n_ref = args.cpu_ref_points if args.workload != 'ags_c1' else 2000
         for _ in range(max(args.warmup, 0)):
             cpu_ags(mesh, max(8, n_ref // 8), scene_meshes=scene_meshes)
         times, cands, threads = [], 0, 1
@@ -233,29 +271,35 @@ def run_reference(args, rank, world):
             times.append(dt)
             cands += c
         total = sum(times)
+        c1, dt1, _, _ = cpu_ags(mesh, max(100, n_ref // 10), seed=99, scene_meshes=scene_meshes, threads=1)
         value, unit, metric = cands / total, 'candidates/s', 'AGS candidates/sec (ray+cone+collision)'
-        sample = f'{n_ref} reference points x {N_RAYS} rays per step ({n_ref * N_RAYS} candidates) of the {args.workload} workload'
+        sample = f'{n_ref} reference points x {N_RAYS} rays per step ({n_ref * N_RAYS} candidates) of the {args.workload} workload, {threads} threads'
+        one_thread = {'value': c1 / dt1, 'unit': unit, 'cores': 1, 'sample': f'{c1} candidates on 1 thread, {dt1:.1f} s'}
         config = {'workload': args.workload, 'mesh_triangles': len(mesh.triangles), 'ref_points_per_step': n_ref,
                   'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1,
                   'collision': 'gripper-vs-object' if scene_meshes is None else
                   f'gripper-vs-scene ({sum(len(m.triangles) for m in scene_meshes)} triangles)'}
     else:
-        n = args.cpu_coverage_n
         times, pairs, threads = [], 0, 1
         for s in range(args.steps):
-            p, dt, threads, _ = cpu_coverage(n)
+            if args.workload == 'coverage_c5':
+                p, dt, threads, _ = cpu_coverage(1_000_000, 2000)
+            else:
+                p, dt, threads, _ = cpu_coverage(args.cpu_coverage_n)
             times.append(dt)
             pairs += p
         total = sum(times)
         value, unit, metric = pairs / total, 'pairs/s', 'coverage pairs/sec'
-        sample = f'{n} x {n} grasps per step (kd-tree coverage, single-threaded like the reference)'
-        config = {'workload': args.workload, 'n_ref': n, 'n_query': n}
+        sample = ('2000 reference rows x 1 000 000 query rows per step' if args.workload == 'coverage_c5' else
+                  f'{args.cpu_coverage_n} x {args.cpu_coverage_n} grasps per step') + ' (kd-tree coverage, single-threaded like the reference)'
+        one_thread = None
+        config = {'workload': args.workload}
     line = {'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(args.steps, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.workload.startswith('ags') else 'f32',
             'data': 'synthetic', 'config': config,
             'cpu_baseline': {'value': value, 'unit': unit, 'cores': threads, 'kind': 'port', 'sample': sample,
-                             'host_cpus': cores},
+                             'one_thread': one_thread, 'host_cpus': cores},
             'e2e': {'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
 
@@ -267,301 +311,403 @@ def event_ms(pairs):
     return [a.elapsed_time(b) for a, b in pairs]
 
 
-def run_b200(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
-    from burg_toolkit_b200 import metrics, sampling
+class Ctx:
+    """what every block needs: torch, the process group, the L2 flush buffer, reductions over ranks"""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+        self.peak_gbs, self.peak_src = measured_peaks()
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')       # > 126 MB L2
+        self._l2_gbs = None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device='cuda')
+        if self.world > 1:
+            self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX)
+
+    def sum_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM)
+
+    def l2_gbs(self):
+        """measured L2 read bandwidth of this GPU (bt_debug_l2_probe: 32 MB buffer, all SMs, ld.global.cg)"""
+        if self._l2_gbs is None:
+            import ctypes
+            from burg_toolkit_b200 import _native as nat
+            out = ctypes.c_double()
+            nat.call('bt_debug_l2_probe', self.local_rank, 32 << 20, 20, ctypes.byref(out))
+            self._l2_gbs = float(out.value)
+        return self._l2_gbs
+
+
+def ncu_inputs():
+    path = os.path.join(ROOT, 'profiles', 'roofline_inputs.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
+def ags_block(ctx, workload, steps, warmup, with_cpu):
+    """one AGS workload (config 3, config 3 exhaustive, config 4): device-resident candidates/s, per-stage times, roofline of
+    the ray caster, end-to-end through the host API, multi-GPU gather (+ its bit-for-bit verification), CPU baseline"""
+    torch, dist, rank, world, local_rank = ctx.torch, ctx.dist, ctx.rank, ctx.world, ctx.local_rank
+    from burg_toolkit_b200 import sampling
+    from burg_toolkit_b200 import mesh as bmesh
     from burg_toolkit_b200.gripper import ParallelJawGripper
+    exhaustive = workload == 'ags_c3_exhaustive'
+    ags = sampling.AntipodalGraspSampler()
+    ags.gripper, ags.verbose, ags.device = ParallelJawGripper(), False, local_rank
+    ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
+    ags.max_targets_per_ref_point = EXHAUSTIVE_TARGETS if exhaustive else 1
+    targets, scene_meshes = ags_workload_meshes(workload)
+    mesh = targets[0]
+    pipe_kw = {} if scene_meshes is None else {'additional_objects': scene_meshes, 'exclude_shape': True}
+    scene_tris = sum(len(m.triangles) for m in scene_meshes) if scene_meshes else len(mesh.triangles)
+    ags.mesh = bmesh.create_icosphere(1, 0.03)               # first build in the process also loads the CUDA module
+    ags._device_mesh()
+    build_ms = []
+    for t in targets:                                       # build every target's LBVH before the timed region
+        ags.mesh = t
+        build_ms.append(ags._device_mesh().info.build_ms)
+    ags.mesh = mesh
+    info = ags._device_mesh().info
+    cap_rows = N_REF * ags.max_targets_per_ref_point * N_ORIENT
+    # the path's only exchange (SURVEY 8e): compacted grasp rows + contacts + counts to rank 0.  Every rank's compaction
+    # kernel stores its kept rows straight into its slot of rank 0's buffer over NVLink (distributed.PeerGather, CUDA IPC).
+    # If the box refuses the IPC mapping the bench says so and uses a plain NCCL gather of the padded rows.
+    peer, gather_buf, exchange = None, None, 'none (1 GPU)'
+    if world > 1 and exhaustive:
+        exchange = 'none: every rank keeps its ~10 M rows (the gather buffer of this mode would hold 3 x world x 1.6 GB on rank 0)'
+    elif world > 1:
+        from burg_toolkit_b200 import distributed as bdist
+        from burg_toolkit_b200._native import NativeError
+        try:
+            mode = os.environ.get('BT_PEER_ONE_SIDED')                  # A/B knob; default: one-sided from 4 ranks on
+            peer = bdist.PeerGather(cap_rows, with_contacts=True, device=local_rank, one_sided=None if mode is None else mode != '0', timeout_s=30.0)
+            exchange = ('compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer); ' +
+                        ('counts + epoch flags stored the same way, rank 0 polls them (no collective in the step)' if peer.one_sided
+                         else 'NCCL all_gather of counts'))
+        except NativeError as ex:
+            exchange = f'NCCL all_reduce + gather of padded rows (peer mapping unavailable: {ex})'
+            gather_buf = torch.empty((world, cap_rows, 14), dtype=torch.float32, device='cuda') if rank == 0 else None
 
-    peak_gbs, peak_src = measured_peaks()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')       # > 126 MB L2
+    from burg_toolkit_b200.device import StageTimer
+    stage_timer = StageTimer(local_rank)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    # Steps are independent batches: they are issued round-robin on `n_streams` streams, so the latency-bound tail of one
+    # batch (target choice, expansion, compaction -- and a compaction whose stores cross NVLink / PCIe) overlaps the ray
+    # casting of the next.  Each stream owns a workspace (slot) and an L2-flush buffer.
+    n_streams = max(1, int(ctx.args.streams))
+    streams = [torch.cuda.Stream() for _ in range(n_streams)]
+    flushes = [ctx.flush] + [torch.empty_like(ctx.flush) for _ in range(n_streams - 1)]
 
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def step(seed, timer=None, graph=True, to_peer=True, slot=0):
+        ags.mesh = targets[seed % len(targets)]
+        dest = peer.destinations() if (peer is not None and to_peer) else None
+        out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer, destinations=dest, slot=slot,
+                               graph=graph and timer is None, **pipe_kw)
+        if peer is not None and to_peer:
+            peer.complete(out['n_free'])
+        elif world > 1 and gather_buf is not None and to_peer:
+            dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
+            dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
+        return out
 
-    def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def run_steps(n, timed):
+        """n steps round-robin over the streams, L2 flushed before every step on the step's stream -> (ms, stats)"""
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stats = []
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
+        for s in range(n):
+            k = s % n_streams
+            with torch.cuda.stream(streams[k]):
+                flushes[k].fill_(s & 0xff)                                       # > L2, written between consecutive steps
+                out = step(7919 * (rank + 1) + s, slot=k)
+                if timed:
+                    stats.append((out['n_grasps'].clone(), (out['n_free'] if out.get('n_free') is not None else out['n_grasps']).clone(), out['overflow'].clone()))
+        for st in streams:
+            main.wait_stream(st)
+        e1.record(main)
+        return (e0, e1), stats
 
     clocks = ClockSampler(local_rank)
-    line = {}
-    if args.workload in ('ags_c3', 'ags_c4'):
-        ags = sampling.AntipodalGraspSampler()
-        ags.gripper, ags.verbose, ags.device = ParallelJawGripper(), False, local_rank
-        ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
-        if args.workload == 'ags_c3':
-            mesh = c3_mesh()
-            targets, scene_meshes, pipe_kw = [mesh], None, {}
-        else:       # config 4: 20 objects + ground slab; every step samples on one object, gripper vs the WHOLE scene
-            scene_meshes = c4_scene().get_mesh_list()
-            targets = scene_meshes[1:]
-            mesh = targets[0]
-            pipe_kw = {'additional_objects': scene_meshes, 'exclude_shape': True}
-        scene_tris = sum(len(m.triangles) for m in scene_meshes) if scene_meshes else len(mesh.triangles)
-        from burg_toolkit_b200 import mesh as bmesh
-        ags.mesh = bmesh.create_icosphere(1, 0.03)               # first build in the process also loads the CUDA module
-        ags._device_mesh()
-        build_ms = []
-        for t in targets:                                       # build every target's LBVH before the timed region
-            ags.mesh = t
-            build_ms.append(ags._device_mesh().info.build_ms)
-        ags.mesh = mesh
-        dm = ags._device_mesh()
-        info = dm.info
-        # the path's only exchange: compacted grasp rows + contacts + counts to rank 0.  Every rank's compaction
-        # kernel stores its kept rows straight into its slot of rank 0's buffer over NVLink (distributed.PeerGather, CUDA IPC);
-        # NCCL carries the 8-byte counts, which is also the completion barrier.  If the box refuses the IPC mapping the
-        # bench says so and uses a plain NCCL gather of the padded rows.
-        peer, gather_buf, exchange = None, None, 'none (1 GPU)'
-        if world > 1:
-            from burg_toolkit_b200 import distributed as bdist
-            from burg_toolkit_b200._native import NativeError
-            try:
-                mode = os.environ.get('BT_PEER_ONE_SIDED')                  # A/B knob; default: one-sided from 4 ranks on
-                peer = bdist.PeerGather(N_REF * N_ORIENT, with_contacts=True, device=local_rank, one_sided=None if mode is None else mode != '0', timeout_s=30.0)
-                exchange = ('compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer); ' +
-                            ('counts + epoch flags stored the same way, rank 0 polls them (no collective in the step)' if peer.one_sided
-                             else 'NCCL all_gather of counts'))
-            except NativeError as ex:
-                exchange = f'NCCL all_reduce + gather of padded rows (peer mapping unavailable: {ex})'
-                gather_buf = torch.empty((world, N_REF * N_ORIENT, 14), dtype=torch.float32, device='cuda') if rank == 0 else None
-
-        from burg_toolkit_b200.device import StageTimer
-        stage_timer = StageTimer(local_rank)
-
-        def step(seed, timer=None):
-            ags.mesh = targets[seed % len(targets)]
-            out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer,
-                                   destinations=peer.destinations() if peer else None, **pipe_kw)
-            if peer is not None:
-                peer.complete(out['n_free'])
-            elif world > 1:
-                dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
-                dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
-            return out
-
-        clocks.start()                                          # samples cover warm-up + timed region (all under load)
-        for w in range(args.warmup):
-            step(1000 * rank + w + 1)
-        barrier()
-        stage_acc, step_events, stats = {}, [], []
-        for s in range(args.steps):
-            flush.fill_(s & 0xff)                                                    # L2 flush, outside the event pair
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = step(7919 * (rank + 1) + s)                                        # no per-stage events inside the timed region
-            e1.record()
-            step_events.append((e0, e1))
-            stats.append((out['n_grasps'].clone(), out['n_free'].clone(), out['overflow'].clone()))
-        barrier()
-        clk = clocks.stop()
-        # per-stage device times: a few extra, untimed steps with the stage timer (its 16 event records and the host wait
-        # per step are instrumentation, so they stay out of the timed region above)
-        for s in range(min(args.steps, 5)):
-            flush.fill_(s & 0xff)
-            step(104729 * (rank + 1) + s, stage_timer)
-            for name, ms in stage_timer.read().items():
-                stage_acc.setdefault(name, []).append(ms)
-        step_ms = event_ms(step_events)
-        total_ms = max_over_ranks(sum(step_ms))
-        candidates = sum_over_ranks(N_REF * N_RAYS * args.steps)
-        value = candidates / (total_ms * 1e-3)
-        stage_ms = {k: statistics.mean(v) for k, v in stage_acc.items()}
-        n_grasps = int(torch.stack([a.reshape(()) for a, _, _ in stats]).double().mean().item())
-        n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // (1 if (peer is not None or world == 1) else world)
-        overflow = int(torch.stack([c.reshape(()) for _, _, c in stats]).sum().item())
-
-        # work counters (instrumented kernel instantiations, one extra untimed step) for the L2 traffic model
-        from burg_toolkit_b200 import _native as nat
-        counters = torch.zeros(8, dtype=torch.int64, device='cuda')
-        nat.call('bt_debug_set_counters', counters.data_ptr())
-        step(424242 + rank)
+    clocks.start()                                          # samples cover warm-up + timed region (all under load)
+    # warm-up = the timed sequence itself (same seeds, hence same target meshes and stream slots), a multiple of the gather
+    # ring's depth long, so that every CUDA graph the timed region replays has been captured
+    ring = peer.depth if peer is not None else 1
+    n_warm = max(warmup, steps)
+    n_warm = ((n_warm + ring * n_streams - 1) // (ring * n_streams)) * (ring * n_streams)
+    run_steps(n_warm, False)
+    ctx.barrier()
+    (e0, e1), stats = run_steps(steps, True)
+    ctx.barrier()
+    clk = clocks.stop()
+    total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    # the same steps one at a time on one stream (continuity with round 1, and what the per-stage times below add up to)
+    single_events = []
+    for s in range(min(steps, 5)):
+        ctx.flush.fill_(s & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(31337 * (rank + 1) + s, to_peer=False)
+        b.record()
+        single_events.append((a, b))
+    torch.cuda.synchronize()
+    single_ms = ctx.max_over_ranks(statistics.median(event_ms(single_events)))
+    # launches of one step, counted from the captured graph (kernel nodes), not kept by hand
+    ws = ags._workspaces[0]
+    launch = {'nodes': None, 'kernels': None, 'names': None}
+    if getattr(ws, 'last_graph', None) is not None:
+        n_nodes, n_kernels, names = ws.last_graph.info()
+        launch = {'nodes': n_nodes, 'kernels': n_kernels, 'names': names}
+    # per-stage device times: a few extra, untimed steps with the stage timer (its event records and the host wait per
+    # step are instrumentation, so they stay out of the timed region above)
+    stage_acc = {}
+    for s in range(min(steps, 5) + 1):
+        ctx.flush.fill_(s & 0xff)
         torch.cuda.synchronize()
-        nat.call('bt_debug_set_counters', None)
-        cnt = [int(x) for x in counters.cpu().tolist()]
-        n_cand = N_REF * N_RAYS
-        per_ray = {'nodes': cnt[0] / n_cand, 'leaf_pretests': cnt[1] / n_cand, 'exact_tests': cnt[2] / n_cand}
-        per_grasp = {'nodes': cnt[3] / max(n_grasps, 1), 'leaves_classified': cnt[4] / max(n_grasps, 1),
-                     'leaves_exact': cnt[5] / max(n_grasps, 1)}
+        step(104729 * (rank + 1) + s, stage_timer, to_peer=False)
+        for name, ms in stage_timer.read().items():
+            if s > 0:                                       # the first plain (not graph-replayed) call grows the scratch pool
+                stage_acc.setdefault(name, []).append(ms)
+    candidates = ctx.sum_over_ranks(N_REF * N_RAYS * steps)
+    value = candidates / (total_ms * 1e-3)
+    stage_ms = {k: statistics.median(v) for k, v in stage_acc.items()}
+    n_grasps = int(torch.stack([a.reshape(()) for a, _, _ in stats]).double().mean().item())
+    n_free = int(torch.stack([b.reshape(()) for _, b, _ in stats]).double().mean().item()) // (world if (peer is None and gather_buf is not None) else 1)
+    overflow = int(torch.stack([c.reshape(()) for _, _, c in stats]).sum().item())
 
-        # roofline of the dominant stage (the ray caster = traverse_kernel + cast_kernel): algorithmic HBM bytes per launch
-        # (64 B per candidate + 80 B per triangle) over its event-timed duration, against the measured HBM peak;
-        # plus the traversal-traffic model against L2 (the mesh + LBVH are L2-resident by design, HBM is not the binding roof)
-        cast_ms = stage_ms['cast']
-        alg_bytes = N_REF * N_RAYS * 64 + 80 * info.n_triangles
-        achieved = alg_bytes / (cast_ms * 1e-3) / 1e9
-        l2_bytes = cnt[0] * 64 + cnt[1] * 48 + cnt[2] * 128 + n_cand * (24 + 48 + 2 * 8 + 8)
-        prof = {}
-        ppath = os.path.join(ROOT, 'profiles', 'roofline_inputs.json')
-        if os.path.exists(ppath):
-            with open(ppath) as fh:
-                prof = json.load(fh)
-        roofline = {'bound': 'hbm', 'kernel': 'traverse_kernel + cast_kernel (ray caster stage)', 'achieved': achieved, 'peak': peak_gbs,
-                    'unit': 'GB/s', 'frac': achieved / peak_gbs, 'traffic': prof.get('cast_stage', {}).get('dram_bytes_per_launch'), 'traffic_source': prof.get('cast_stage', {}).get('source'),
-                    'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': cast_ms,
-                    'rays_per_s': N_REF * N_RAYS / (cast_ms * 1e-3),
-                    'l2_model': {'bytes_per_launch': l2_bytes, 'achieved_gbs': l2_bytes / (cast_ms * 1e-3) / 1e9,
-                                 'definition': 'wide_nodes*64 + leaf_pretests*48 + exact_tests*128 + rays*(24 B float32 ray in traverse + 48 B float64 ray in resolve + 2*8 B ray parameters + 8 B count and mask out)',
-                                 'per_ray': per_ray},
-                    'collide_per_grasp': per_grasp,
-                    'note': 'mesh + LBVH + per-leaf records (~50 MB) are L2-resident by design, so HBM is not the binding roof: the stage is bound by L1 data-pipe wavefronts of divergent node fetches; see DESIGN.md section 4'}
+    # work counters (instrumented kernel instantiations, one extra untimed step) for the traffic model
+    from burg_toolkit_b200 import _native as nat
+    counters = torch.zeros(8, dtype=torch.int64, device='cuda')
+    nat.call('bt_debug_set_counters', counters.data_ptr())
+    step(424242 + rank, graph=False, to_peer=False)
+    torch.cuda.synchronize()
+    nat.call('bt_debug_set_counters', None)
+    cnt = [int(x) for x in counters.cpu().tolist()]
+    n_cand = N_REF * N_RAYS
+    per_ray = {'nodes_fetched': cnt[0] / n_cand, 'nodes_skipped_by_normal_cone': cnt[6] / n_cand, 'leaf_pretests': cnt[1] / n_cand,
+               'exact_tests': cnt[2] / n_cand}
+    per_grasp = {'nodes': cnt[3] / max(n_grasps, 1), 'leaves_classified': cnt[4] / max(n_grasps, 1),
+                 'leaves_exact': cnt[5] / max(n_grasps, 1)}
 
-        # end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    # roofline of the dominant stage (the ray caster = traverse_kernel + cast_kernel): algorithmic HBM bytes per launch
+    # (SURVEY 8d: 64 B per candidate + 80 B per triangle) over its event-timed duration, against the measured HBM peak.
+    # The mesh + LBVH are L2-resident by design, so HBM is not what binds: `binding` states the roofs that do.
+    cast_ms = stage_ms['cast']
+    alg_bytes = N_REF * N_RAYS * 64 + 80 * info.n_triangles
+    achieved = alg_bytes / (cast_ms * 1e-3) / 1e9
+    model_bytes = cnt[0] * 64 + cnt[1] * (48 + 4) + cnt[2] * 128 + n_cand * (24 + 48 + 2 * 8 + 8)
+    prof = ncu_inputs()
+    l2_peak = ctx.l2_gbs()
+    trav = prof.get('traverse_kernel', {})
+    roofline = {'bound': 'hbm', 'kernel': 'traverse_kernel + cast_kernel (ray caster stage)', 'achieved': achieved, 'peak': ctx.peak_gbs,
+                'unit': 'GB/s', 'frac': achieved / ctx.peak_gbs, 'traffic': prof.get('cast_stage', {}).get('dram_bytes_per_launch'),
+                'traffic_source': prof.get('cast_stage', {}).get('source'),
+                'peak_source': ctx.peak_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': cast_ms,
+                'rays_per_s': N_REF * N_RAYS / (cast_ms * 1e-3),
+                'binding': {'what': 'L1 data-pipe wavefronts and ALU issue of divergent 64-byte node fetches over an L2-resident tree (not HBM)',
+                            'traffic_model_bytes_per_launch': model_bytes, 'traffic_model_gbs': model_bytes / (cast_ms * 1e-3) / 1e9,
+                            'l2_peak_gbs_measured': l2_peak, 'frac_of_l2_peak': model_bytes / (cast_ms * 1e-3) / 1e9 / l2_peak,
+                            'definition': 'nodes_fetched*64 + leaf_pretests*(48 + 4) + exact_tests*128 + rays*(24 B float32 ray in traverse + 48 B float64 ray in '
+                                          'resolve + 2*8 B ray parameters + 8 B count and mask out); l2 peak = bt_debug_l2_probe (32 MB, ld.global.cg, all SMs)',
+                            'ncu_traverse_kernel': {k: trav.get(k) for k in ('l1tex_data_pipe_lsu_wavefronts_pct', 'alu_pipe_pct', 'issue_active_pct',
+                                                                            'duration_us', 'source')},
+                            'per_ray': per_ray},
+                'collide_per_grasp': per_grasp,
+                'note': 'mesh + LBVH + per-leaf records (~50 MB at 100k triangles) are L2-resident by design, so the HBM fraction is small by construction; '
+                        'see binding and DESIGN.md section 4'}
+
+    # end-to-end through the public API with HOST buffers: pinned staging, H2D, pipeline, the compaction kernel's stores
+    # into pinned host memory, all inside the timed region; timed on the host's wall clock around synchronised calls.
+    #   serial:    evaluate_host, one batch at a time (L2 flushed between batches, outside the clock)
+    #   pipelined: submit_host on two slots, batch i+1 submitted before batch i's result is awaited (its PCIe stores overlap
+    #              the next batch's ray casting); L2 is NOT flushed between overlapping batches (they stream > 100 MB each)
+    e2e = None
+    if not exhaustive:
         ags.mesh = mesh
-        pts, nrm, _ = [t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank)]
-        pinned = {}
-        for w in range(max(args.warmup, 1)):
-            ags.evaluate_host(pts, nrm, seed=w + 1, pinned=pinned, **pipe_kw)
-        barrier()
-        e2e_events, h2d, d2h = [], 0, 0
-        for s in range(args.steps):
-            flush.fill_(s & 0xff)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            res = ags.evaluate_host(pts, nrm, seed=s + 11, pinned=pinned, **pipe_kw)
-            e1.record()
-            e2e_events.append((e0, e1))
+        host_batches = [[t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank + 17 * b)[:2]] for b in range(4)]
+        for w in range(max(warmup, 2)):
+            ags.evaluate_host(*host_batches[w % 4], seed=w + 1, **pipe_kw)
+            ags.submit_host(*host_batches[w % 4], seed=w + 1, slot=1, **pipe_kw).result()
+        ctx.barrier()
+        serial_s, h2d, d2h = 0.0, 0, 0
+        for s in range(steps):
+            ctx.flush.fill_(s & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = ags.evaluate_host(*host_batches[s % 4], seed=s + 11, **pipe_kw)
+            serial_s += time.perf_counter() - t0
             h2d, d2h = res['h2d_bytes'], res['d2h_bytes']
-        barrier()
-        e2e_ms = max_over_ranks(sum(event_ms(e2e_events)))
-        e2e_value = candidates / (e2e_ms * 1e-3)
-        exchange_timed_out = False
-        if peer is not None:                                   # a timed-out wait kernel must not cost the JSON line: it is reported in it
-            exchange_timed_out = sum_over_ranks(1.0 if peer.close(raise_on_timeout=False) else 0.0) > 0
+        ctx.barrier()
+        t0 = time.perf_counter()
+        pending = ags.submit_host(*host_batches[0], seed=11, slot=0, **pipe_kw)
+        got = 0
+        for s in range(1, steps):
+            nxt = ags.submit_host(*host_batches[s % 4], seed=s + 11, slot=s & 1, **pipe_kw)
+            got += pending.result()['n_free']
+            pending = nxt
+        got += pending.result()['n_free']
+        pipelined_s = time.perf_counter() - t0
+        ctx.barrier()
+        pipe_ms = ctx.max_over_ranks(pipelined_s * 1e3)
+        serial_ms = ctx.max_over_ranks(serial_s * 1e3)
+        e2e = {'value': candidates / (pipe_ms * 1e-3), 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+               'ms_per_step': pipe_ms / steps, 'clock': 'host wall clock (time.perf_counter) around submit ... result',
+               'mode': 'AntipodalGraspSampler.submit_host on two alternating slots (one batch in flight while the next is submitted); '
+                       'every batch: pinned staging copy, H2D, graph-replayed pipeline, kept rows stored into pinned host memory by the compaction kernel',
+               'serial': {'value': candidates / (serial_ms * 1e-3), 'ms_per_step': serial_ms / steps,
+                          'mode': 'AntipodalGraspSampler.evaluate_host, one synchronous call per batch, L2 flushed between calls'},
+               'rows_received_per_step': got / steps}
 
-        line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
-                'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
-                'config': {'workload': args.workload,
-                           'mesh': 'bumpy sphere 224x224 (YCB-like, seed 1)' if scene_meshes is None else
-                                   '20 bumpy objects (158x158 grids, seeds 10-29) on a 1.0 x 0.5 m ground slab; target object changes every step',
-                           'mesh_triangles': int(info.n_triangles), 'scene_triangles': int(scene_tris),
-                           'ref_points_per_step_per_gpu': N_REF, 'n_rays': N_RAYS,
-                           'candidates_per_step_per_gpu': N_REF * N_RAYS, 'n_orientations': N_ORIENT,
-                           'max_targets_per_ref_point': 1,
-                           'collision': ('gripper-vs-object' if scene_meshes is None else 'gripper-vs-scene') + ', use_width, tol 0.01',
-                           'mode': 'reference mode (one pair per reference point)', 'l2': 'flushed between steps (256 MB write)',
-                           'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
-                           'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow,
-                           'exchange': exchange, 'exchange_timed_out': exchange_timed_out},
-                'roofline': roofline, 'stage_ms': stage_ms,
-                'e2e': {'value': e2e_value, 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'ms_per_step': e2e_ms / args.steps},
-                'gpu_launches': len(AGS_KERNELS) * args.steps, 'kernels': AGS_KERNELS}
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            c, dt, threads, _ = cpu_ags(mesh, args.cpu_ref_points, scene_meshes=scene_meshes)
-            line['cpu_baseline'] = {'value': c / dt, 'unit': 'candidates/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'{args.cpu_ref_points} reference points x {N_RAYS} rays ({c} candidates) of the same '
-                                              f'workload, oracle/coracle.c with OpenMP, {dt:.1f} s', 'host_cpus': os.cpu_count()}
-            # secondary metric of BASELINE.json: coverage pairs/s (config 2), same JSON line
-            if args.workload == 'ags_c3':
-                line['secondary'] = coverage_numbers(args, torch, metrics, flush, barrier, short=True)
-    elif args.workload == 'ags_c1':
-        # config 0 of BASELINE.json: the reference's own CPU-runnable case through the public API --
-        # AntipodalGraspSampler.sample(1000) on a 20 480-triangle icosphere, 12 orientations, then check_collisions
-        from burg_toolkit_b200 import mesh as bmesh
-        ags = sampling.AntipodalGraspSampler()
-        ags.mesh, ags.gripper, ags.verbose, ags.device = bmesh.create_icosphere(5, 0.03), ParallelJawGripper(), False, local_rank
-        ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
-        np.random.seed(1234 + rank)
-        clocks.start()
-        for _ in range(args.warmup):
-            gs, _ = ags.sample(1000)
-            ags.check_collisions(gs)
-        barrier()
-        ev, cands, grasps = [], 0, 0
-        for s in range(args.steps):
-            flush.fill_(s & 0xff)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            gs, contacts = ags.sample(1000)                    # host call: numpy results come back every time
-            coll = ags.check_collisions(gs)
-            e1.record()
-            ev.append((e0, e1))
-            cands += ags.last_stats['candidates']
-            grasps += len(gs)
-        barrier()
-        clk = clocks.stop()
-        total_ms = max_over_ranks(sum(event_ms(ev)))
-        cand_all = sum_over_ranks(cands)
-        value = cand_all / (total_ms * 1e-3)
-        line = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
-                'ms_per_step': total_ms / args.steps, 'dtype': 'f64',
-                'config': {'workload': 'ags_c1', 'mesh': 'icosphere, 5 subdivisions, r = 0.03', 'mesh_triangles': 20480,
-                           'call': 'AntipodalGraspSampler.sample(1000) + check_collisions(gs), numpy in / numpy out',
-                           'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1,
-                           'candidates_per_step_per_gpu': cands / args.steps, 'grasps_per_step': grasps / args.steps,
-                           'l2': 'flushed between steps (256 MB write)'},
-                'roofline': None,
-                'e2e': {'value': value, 'unit': 'candidates/s', 'ms_per_step': total_ms / args.steps,
-                        'h2d_bytes_per_step': int(grasps / args.steps * 56), 'd2h_bytes_per_step': int(grasps / args.steps * (56 + 48 + 1)),
-                        'note': 'this workload IS the end-to-end call: value and e2e coincide'},
-                'gpu_launches': None, 'note': 'launch-latency bound: ~100 reference points per call; the throughput '
-                                              'configurations are ags_c3 / ags_c4'}
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            c, dt, threads, _ = cpu_ags(ags.mesh, 2000)
-            line['cpu_baseline'] = {'value': c / dt, 'unit': 'candidates/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'2000 reference points x {N_RAYS} rays of the same mesh, oracle/coracle.c with OpenMP, {dt:.2f} s'}
-    else:
-        line = coverage_numbers(args, torch, metrics, flush, barrier, short=False, clocks=clocks, rank=rank, world=world,
-                                dist=dist if world > 1 else None)
-        clk = line.pop('clocks')
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            p, dt, threads, cov = cpu_coverage(args.cpu_coverage_n)
-            line['cpu_baseline'] = {'value': p / dt, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'{args.cpu_coverage_n} x {args.cpu_coverage_n} grasps, kd-tree coverage '
-                                              f'(scipy cKDTree + Python loop as metrics.py:161-229), {dt:.1f} s'}
-    line.update({'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True,
-                 'scaling': 'weak' if args.workload.startswith('ags') else 'strong',
-                 'vs_baseline': None, 'data': 'synthetic', 'clocks': clk})
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    # multi-GPU: does rank 0 hold, bit for bit, what the ranks computed?  One more step into the peer buffer, the same step
+    # (same seed: the pipeline is deterministic) into local memory, the local rows sent through a plain NCCL gather.
+    gather_verified = None
+    exchange_timed_out = False
+    if peer is not None:
+        from burg_toolkit_b200 import distributed as bdist
+        vseed = 555 + 31 * rank
+        step(vseed)
+        got_rows, got_contacts = peer.result()
+        local = step(vseed, to_peer=False)
+        k = int(local['n_free'].item())
+        want_rows = bdist.gather_rows(local['free_gs'][:k].contiguous(), 0)
+        want_contacts = bdist.gather_rows(local['free_contacts'][:k].contiguous(), 0)
+        ok = 1.0
+        if rank == 0:
+            ok = float(got_rows.shape == want_rows.shape and torch.equal(got_rows, want_rows) and torch.equal(got_contacts, want_contacts)
+                       and want_rows.shape[0] > 0)
+        gather_verified = ctx.sum_over_ranks(ok if rank == 0 else 0.0) == 1.0
+        exchange_timed_out = ctx.sum_over_ranks(1.0 if peer.close(raise_on_timeout=False) else 0.0) > 0
+
+    mesh_desc = {'ags_c3': 'bumpy sphere 224x224 (YCB-like, seed 1)', 'ags_c3_exhaustive': 'bumpy sphere 224x224 (YCB-like, seed 1)',
+                 'ags_c4': '20 bumpy objects (158x158 grids, seeds 10-29) on a 1.0 x 0.5 m ground slab; target object changes every step'}[workload]
+    block = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
+             'ms_per_step': total_ms / steps, 'dtype': 'f64', 'scaling': 'weak',
+             'config': {'workload': workload, 'mesh': mesh_desc,
+                        'mesh_triangles': int(info.n_triangles), 'scene_triangles': int(scene_tris),
+                        'ref_points_per_step_per_gpu': N_REF, 'n_rays': N_RAYS,
+                        'candidates_per_step_per_gpu': N_REF * N_RAYS, 'n_orientations': N_ORIENT,
+                        'max_targets_per_ref_point': int(ags.max_targets_per_ref_point),
+                        'collision': ('gripper-vs-object' if scene_meshes is None else 'gripper-vs-scene') + ', use_width, tol 0.01',
+                        'mode': 'exhaustive (every valid hit of a reference point becomes a contact pair)' if exhaustive else
+                                'reference mode (one pair per reference point)',
+                        'l2': 'a 256 MB buffer is written before every step, on the step\'s stream, inside the timed region',
+                        'launch': 'bt_ags_pipeline replayed as a CUDA graph (bt_graph_*)', 'streams': n_streams,
+                        'timing': f'one CUDA-event pair around all {steps} steps (issued round-robin on {n_streams} streams, joined on the launching stream)',
+                        'single_stream_ms_per_step': single_ms,
+                        'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
+                        'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow,
+                        'exchange': exchange, 'exchange_timed_out': exchange_timed_out},
+             'roofline': roofline, 'stage_ms': stage_ms, 'e2e': e2e,
+             'gpu_launches': None if launch['kernels'] is None else launch['kernels'] * steps,
+             'launches_per_step': {'kernel_nodes': launch['kernels'], 'graph_nodes': launch['nodes'], 'kernels': launch['names'],
+                                   'source': 'bt_graph_info of the captured step (kernel nodes of the CUDA graph)'},
+             'clocks': clk}
+    if exhaustive:
+        block['collision_stage'] = {'posed_grippers_per_s_per_gpu': n_grasps / (stage_ms['collide'] * 1e-3), 'ms': stage_ms['collide'],
+                                    'posed_grippers_per_step': n_grasps}
+    if gather_verified is not None:
+        block['gather_verified'] = bool(gather_verified)
+    if with_cpu and rank == 0 and world == 1:
+        n_all = ctx.args.cpu_ref_points if scene_meshes is None else ctx.args.cpu_ref_points // 2
+        block['cpu_baseline'] = cpu_ags_record(mesh, n_all, max(1000, n_all // 20), scene_meshes, what=f'the {workload} workload (one pair per reference point)')
+    del ags
+    return block
 
 
-def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None, rank=0, world=1, dist=None):
+def ags_c1_block(ctx, steps, warmup, with_cpu):
+    """config 0 of BASELINE.json: the reference's own CPU-runnable case through the public API --
+    AntipodalGraspSampler.sample(1000) on a 20 480-triangle icosphere, 12 orientations, then check_collisions"""
+    torch, rank, world, local_rank = ctx.torch, ctx.rank, ctx.world, ctx.local_rank
+    from burg_toolkit_b200 import mesh as bmesh, sampling
+    from burg_toolkit_b200.gripper import ParallelJawGripper
+    ags = sampling.AntipodalGraspSampler()
+    ags.mesh, ags.gripper, ags.verbose, ags.device = bmesh.create_icosphere(5, 0.03), ParallelJawGripper(), False, local_rank
+    ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
+    np.random.seed(1234 + rank)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for _ in range(warmup):
+        gs, _ = ags.sample(1000)
+        ags.check_collisions(gs)
+    ctx.barrier()
+    wall, cands, grasps = 0.0, 0, 0
+    for s in range(steps):
+        ctx.flush.fill_(s & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gs, contacts = ags.sample(1000)                    # host call: numpy results come back every time
+        coll = ags.check_collisions(gs)
+        wall += time.perf_counter() - t0
+        cands += ags.last_stats['candidates']
+        grasps += len(gs)
+    ctx.barrier()
+    clk = clocks.stop()
+    total_ms = ctx.max_over_ranks(wall * 1e3)
+    cand_all = ctx.sum_over_ranks(cands)
+    value = cand_all / (total_ms * 1e-3)
+    block = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
+             'ms_per_step': total_ms / steps, 'dtype': 'f64', 'scaling': 'weak',
+             'config': {'workload': 'ags_c1', 'mesh': 'icosphere, 5 subdivisions, r = 0.03', 'mesh_triangles': 20480,
+                        'call': 'AntipodalGraspSampler.sample(1000) + check_collisions(gs), numpy in / numpy out',
+                        'n_rays': N_RAYS, 'n_orientations': N_ORIENT, 'max_targets_per_ref_point': 1,
+                        'candidates_per_step_per_gpu': cands / steps, 'grasps_per_step': grasps / steps,
+                        'l2': 'flushed between steps (256 MB write)', 'clock': 'host wall clock around the two calls'},
+             'roofline': None,
+             'e2e': {'value': value, 'unit': 'candidates/s', 'ms_per_step': total_ms / steps,
+                     'h2d_bytes_per_step': int(grasps / steps * 56), 'd2h_bytes_per_step': int(grasps / steps * (56 + 48 + 1)),
+                     'note': 'this workload IS the end-to-end call: value and e2e coincide'},
+             'gpu_launches': None, 'clocks': clk,
+             'note': 'launch-latency bound: ~100 reference points per call; the throughput configurations are ags_c3 / ags_c4'}
+    if with_cpu and rank == 0 and world == 1:
+        block['cpu_baseline'] = cpu_ags_record(ags.mesh, 2000, 500, what='the same mesh')
+    return block
+
+
+def coverage_block(ctx, workload, steps, warmup, with_cpu):
     """coverage (perturbed pair, eps 15): device-resident pairs/s and e2e (host rows in, fraction out).  With several
     ranks the REFERENCE rows are sharded (query set replicated, one all-reduce of the covered count inside the step):
     the total work is fixed, i.e. strong scaling."""
-    n_cov = 1_000_000 if args.workload == 'coverage_c5' else COV_N
+    torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
+    from burg_toolkit_b200 import metrics
+    from burg_toolkit_b200.distributed import shard_range
+    n_cov = 1_000_000 if workload == 'coverage_c5' else COV_N
     ref_all, qry = coverage_sets(n_cov)
     pairs = float(len(ref_all)) * float(len(qry))
-    from burg_toolkit_b200.distributed import shard_range
     b, e = shard_range(len(ref_all), rank, world)
     ref = ref_all[b:e]
     dref, dqry = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
-
-    def reduce_max(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    clocks = ClockSampler(ctx.local_rank)
     res = {}
-    steps = max(3, args.steps // 2) if short else args.steps
     for algo in (('grid',) if n_cov > 200_000 else ('grid', 'tiles')):
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(warmup, 3)):
             metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
-        barrier()
-        if clocks is not None and algo == 'grid':
+        ctx.barrier()
+        if algo == 'grid':
             clocks.start()
         ev = []
         for s in range(steps):
-            flush.fill_(s & 0xff)
+            ctx.flush.fill_(s & 0xff)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _, count = metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
@@ -569,23 +715,23 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None, r
                 dist.all_reduce(count, op=dist.ReduceOp.SUM)           # the path's only exchange: one int64 per rank
             e1.record()
             ev.append((e0, e1))
-        barrier()
-        ms = reduce_max(statistics.mean(event_ms(ev)))
+        ctx.barrier()
+        if algo == 'grid':
+            clk = clocks.stop()
+        ms = ctx.max_over_ranks(statistics.mean(event_ms(ev)))
         res[algo] = {'ms': ms, 'pairs_per_s': pairs / (ms * 1e-3), 'coverage': int(count.item()) / len(ref_all)}
-    clk = clocks.stop() if clocks is not None else None
-    ev = []
+    wall = 0.0
     for s in range(steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         frac = metrics.coverage(ref, qry)                       # host rows in (pageable), python float out
         if world > 1:
             t = torch.tensor([frac * len(ref)], dtype=torch.float64, device='cuda')
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             frac = float(t.item()) / len(ref_all)
-        e1.record()
-        ev.append((e0, e1))
-    barrier()
-    e2e_ms = reduce_max(statistics.mean(event_ms(ev)))
+        wall += time.perf_counter() - t0
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(wall * 1e3 / steps)
     # FP32-issue roofline: 4 lane-ops per tested pair (3 FFMA + 1 compare).  The all-pairs kernel tests
     # every pair; the grid kernels test only the pairs of the 27 neighbouring cells, counted here on the host.
     lane_ops = 148 * 128 * 1.965e9
@@ -607,24 +753,60 @@ def coverage_numbers(args, torch, metrics, flush, barrier, short, clocks=None, r
     # (orientation bound first: cell-tile kernel)
     ops_per_pair = 5 if roof_kernel.startswith('coverage_cells') else 4
     achieved_ops = tested / world * ops_per_pair / (roof_ms * 1e-3)            # per GPU (every rank tests 1/world of the pairs)
-    out = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
-           'ms_per_step': res['grid']['ms'],
-           'config': {'workload': args.workload if not args.workload.startswith('ags') else 'coverage_c2', 'n_ref': len(ref_all), 'n_query': len(qry), 'epsilon': 15.0,
-                      'sharding': f'reference rows split over {world} rank(s), query set replicated, all-reduce of the covered count',
-                      'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
-                      'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
-                      'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
-           'tiles_all_pairs': res.get('tiles'),
-           'roofline': {'bound': 'fp32-issue', 'kernel': roof_kernel, 'achieved': achieved_ops / 1e12,
-                        'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': achieved_ops / lane_ops,
-                        'pairs_tested_per_launch': tested, 'traffic': None,
-                        'lane_ops_per_pair': ops_per_pair,
-                        'note': 'FP32 lane-ops per tested pair: 4 (3 FFMA + compare) or 5 (quaternion dot + compare, cell-tile kernel); value counts nominal N*M pairs, the roofline '
-                                'counts the pairs the kernel actually tests; HBM bytes are negligible'},
-           'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes) * world,
-                   'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac},
-           'gpu_launches': (10 if roof_kernel.startswith('coverage_cells') else 8) * steps, 'clocks': clk}
-    return out
+    block = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
+             'ms_per_step': res['grid']['ms'], 'scaling': 'strong',
+             'config': {'workload': workload, 'n_ref': len(ref_all), 'n_query': len(qry), 'epsilon': 15.0,
+                        'sharding': f'reference rows split over {world} rank(s), query set replicated, all-reduce of the covered count',
+                        'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
+                        'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
+                        'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
+             'tiles_all_pairs': res.get('tiles'),
+             'roofline': {'bound': 'fp32-issue', 'kernel': roof_kernel, 'achieved': achieved_ops / 1e12,
+                          'peak': lane_ops / 1e12, 'unit': 'Tlane-op/s', 'frac': achieved_ops / lane_ops,
+                          'pairs_tested_per_launch': tested, 'traffic': None,
+                          'lane_ops_per_pair': ops_per_pair,
+                          'note': 'FP32 lane-ops per tested pair: 4 (3 FFMA + compare) or 5 (quaternion dot + compare, cell-tile kernel); value counts nominal N*M pairs, the roofline '
+                                  'counts the pairs the kernel actually tests; HBM bytes are negligible'},
+             'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes) * world,
+                     'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac, 'clock': 'host wall clock around metrics.coverage'},
+             'gpu_launches': (10 if roof_kernel.startswith('coverage_cells') else 8) * steps, 'clocks': clk}
+    if with_cpu and rank == 0 and world == 1:
+        block['cpu_baseline'] = cpu_coverage_record(workload, ctx.args.cpu_coverage_n)
+    del dref, dqry
+    return block
+
+
+def run_block(ctx, workload, steps, warmup, with_cpu):
+    if workload == 'ags_c1':
+        return ags_c1_block(ctx, steps, warmup, with_cpu)
+    if workload.startswith('ags'):
+        return ags_block(ctx, workload, steps, warmup, with_cpu)
+    return coverage_block(ctx, workload, steps, warmup, with_cpu)
+
+
+def run_b200(args, rank, world, local_rank):
+    ctx = Ctx(args, rank, world, local_rank)
+    with_cpu = not args.no_cpu_baseline
+    line = run_block(ctx, args.workload, args.steps, args.warmup, with_cpu)
+    clk = line.pop('clocks')
+    if args.workload == 'ags_c3' and not args.no_secondary:
+        # the other BASELINE configurations, every N (the driver's scaling runs carry config 4 and config 5 this way)
+        short = max(3, args.steps // 2)
+        line['secondary'] = []
+        for wl in ['coverage_c2', 'ags_c4', 'coverage_c5', 'ags_c3_exhaustive'] + (['ags_c1'] if world == 1 else []):
+            ctx.torch.cuda.empty_cache()
+            try:
+                line['secondary'].append(run_block(ctx, wl, short, min(args.warmup, 3), with_cpu))
+            except Exception as ex:             # a secondary block must not cost the headline line
+                line['secondary'].append({'config': {'workload': wl}, 'error': f'{type(ex).__name__}: {ex}'})
+                if world > 1:
+                    raise
+    line.update({'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True,
+                 'vs_baseline': None, 'data': 'synthetic', 'clocks': clk})
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -633,10 +815,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='ags_c3', choices=['ags_c1', 'ags_c3', 'ags_c4', 'coverage_c2', 'coverage_c5'])
+    ap.add_argument('--workload', default='ags_c3', choices=['ags_c1', 'ags_c3', 'ags_c3_exhaustive', 'ags_c4', 'coverage_c2', 'coverage_c5'])
     ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
+    ap.add_argument('--streams', type=int, default=3, help='AGS workloads: batches in flight per GPU (round-robin streams)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='ags_c3 only: skip the blocks of the other configurations')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

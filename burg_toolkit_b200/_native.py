@@ -76,6 +76,7 @@ _SIGNATURES = {
     'bt_memcpy_d2h': (C.c_int, [_P, _P, C.c_int64, _P]),
     'bt_stream_sync': (C.c_int, [_P]),
     'bt_debug_set_counters': (C.c_int, [_P]),
+    'bt_debug_l2_probe': (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     'bt_mesh_create': (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int, C.POINTER(_P)]),
     'bt_mesh_destroy': (C.c_int, [_P]),
     'bt_mesh_get_info': (C.c_int, [_P, C.POINTER(MeshInfo)]),

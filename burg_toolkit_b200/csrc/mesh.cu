@@ -434,6 +434,55 @@ extern "C" int bt_debug_set_counters(uint64_t* d_counters) {
     return BT_OK;
 }
 
+// L2 read-bandwidth probe: every SM streams the same L2-resident buffer (ld.global.cg: cached in L2 only) `iters` times.
+// The ray caster's working set (mesh + LBVH, <= ~50 MB for a 100k-triangle object) lives in L2, so this -- not HBM -- is
+// the memory roof its traffic model is compared with (bench.py: roofline.binding).
+namespace bt {
+__global__ void l2_probe_kernel(const uint4* __restrict__ buf, int64_t n_vec, int iters, uint4* __restrict__ sink) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it)
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    if (acc.x == 0x12345678u && acc.y == 0x9abcdef0u) *sink = acc;       // never true for a zeroed buffer: keeps the loads alive
+}
+}  // namespace bt
+
+extern "C" int bt_debug_l2_probe(int device, int64_t bytes, int32_t iters, double* gbytes_per_s) {
+    BT_REQUIRE(gbytes_per_s && bytes >= (1 << 20) && iters >= 1, "bad arguments");
+    BT_CUDA(cudaSetDevice(device));
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+    uint4* buf = nullptr;
+    BT_CUDA(cudaMalloc(&buf, (size_t)bytes + sizeof(uint4)));
+    cudaError_t e = cudaMemset(buf, 0, (size_t)bytes + sizeof(uint4));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    const int64_t n_vec = bytes / (int64_t)sizeof(uint4);
+    float best = 1e30f;
+    if (e == cudaSuccess) {
+        bt::l2_probe_kernel<<<sm_count * 8, 256>>>(buf, n_vec, 1, buf + n_vec);          // warm L2
+        for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {
+            cudaEventRecord(e0);
+            bt::l2_probe_kernel<<<sm_count * 8, 256>>>(buf, n_vec, iters, buf + n_vec);
+            cudaEventRecord(e1);
+            e = cudaEventSynchronize(e1);
+            float ms = 0.f;
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+            if (ms > 0.f && ms < best) best = ms;
+        }
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (e != cudaSuccess) return cuda_fail(e, "bt_debug_l2_probe", __FILE__, __LINE__);
+    *gbytes_per_s = (double)bytes * iters / (best * 1e-3) / 1e9;
+    return BT_OK;
+}
+
 // ---- library ---------------------------------------------------------------------------------------
 extern "C" int bt_version(void) { return 100; }
 

@@ -34,7 +34,7 @@ __global__ void peer_wait_kernel(const int64_t* words, int n_words, int64_t epoc
             __nanosleep(200);
         }
     }
-    if (!ok) atomicExch(status, 1);
+    if (!ok) *reinterpret_cast<volatile int32_t*>(status) = 1;       // (device or mapped pinned host memory)
     __syncthreads();
     __threadfence_system();
     if (threadIdx.x == 0 && ack) *reinterpret_cast<volatile int64_t*>(ack) = ack_value;

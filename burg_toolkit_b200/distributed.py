@@ -105,26 +105,29 @@ class PeerGather:
 
     ``dst`` allocates ``[depth, world, cap_rows, 14] float32`` (+ ``[depth, world, cap_rows, 2, 3] float64``) with ``bt_peer_alloc``;
     the IPC handle is broadcast once; every rank passes ``destinations()`` to ``AntipodalGraspSampler.run_pipeline`` so
-    that its ``compact_scatter_kernel`` writes slot ``rank`` directly (peer stores over NVLink / NVSwitch; local stores on
+    that its ``compact_kernel`` writes slot ``rank`` directly (peer stores over NVLink / NVSwitch; local stores on
     ``dst`` itself).  Rank order = candidate order, so ``result()`` equals the single-GPU output on the same candidates.
 
-    Completion, ``one_sided=True`` (the default from 4 ranks on): no collective at all.  ``complete(n_free)`` enqueues ``bt_peer_signal`` behind
-    the compaction -- the rank's count and then an epoch flag are stored into ``dst``'s control block -- and on ``dst`` also
-    ``bt_peer_wait``, one small kernel that polls the flags of all ranks (bounded by ``timeout_s``: a lost peer raises
-    ``NativeError`` at the next ``result()`` / ``close()`` instead of hanging the device).  The other ranks never wait for
+    Per step:  ``d = peer.destinations()``  ->  ``run_pipeline(..., destinations=d)``  ->  ``peer.complete(out['n_free'])``,
+    all three on the step's stream.  Steps may be issued on DIFFERENT streams (several batches in flight per rank, so that
+    a link-bound compaction overlaps the next batch's ray casting); the calls only have to be made in step order.
+
+    Completion, ``one_sided=True`` (the default with NCCL): no collective at all.  ``complete`` enqueues
+    ``bt_peer_signal`` behind the compaction -- the rank's count and then an epoch flag are stored into ``dst``'s control
+    block.  ``dst`` additionally runs ``bt_peer_wait`` for the epoch on its private gather stream (behind the step's own
+    compaction): one small kernel that polls the flags of all ranks, bounded by ``timeout_s`` (a lost peer sets a status
+    word in pinned host memory -- ``check()`` raises -- instead of hanging the device).  The other ranks never wait for
     each other, so a step does not cost the slowest rank's time on every rank.
-    ``one_sided=False`` (the default below 4 ranks, where it measured 4 % faster): ``complete`` all-gathers the counts with the process group (each rank's contribution is enqueued
-    behind its scatter kernel, so the collective's completion on ``dst`` means every slot is complete).
+    Slot reuse: every rank owns a ring of ``depth`` slots (epoch e uses slot e % depth).  ``dst`` acknowledges epoch e-2 in
+    the wait kernel of epoch e, i.e. ``result()`` of an epoch has to be called before the second ``complete`` after it;
+    a rank's step e waits (``destinations()``: a polling kernel on a side stream + an event the step's stream waits for) until
+    e-depth is acknowledged -- with the default depth of 6 that is satisfied long before, so nothing stalls.
+    ``one_sided=False``: ``complete`` all-gathers the counts with the process group behind the scatter kernel (NCCL), or --
+    host-side backends, the two-process single-GPU test -- after a stream synchronisation."""
 
-    Every rank owns a ring of ``depth`` slots (call e uses slot e % depth).  One-sided mode: ``dst`` acknowledges epoch e-1
-    in the wait kernel of epoch e (i.e. behind its own reads of e-1 in stream order), and a rank's compaction of epoch e
-    waits -- through the ``compact_after`` event of the pipeline, on a side stream, so only the compaction and not the ray
-    casting is held up -- until e-depth is acknowledged.  With depth 3 a rank may run almost two calls ahead of ``dst``; with
-    depth 2 the ranks stall on the acknowledgement every call (measured: 0.85 - 0.89 ms per step at 2 - 8 GPUs against
-    0.79 on one).  Collective mode needs depth 2: a rank can only reach the compaction of call s+2 after the count exchange
-    of call s+1, which ``dst`` joins behind its reads of call s."""
+    ACK_LAG = 2
 
-    def __init__(self, cap_rows, with_contacts=True, device=None, dst=0, group=None, one_sided=None, timeout_s=10.0, depth=3):
+    def __init__(self, cap_rows, with_contacts=True, device=None, dst=0, group=None, one_sided=None, timeout_s=10.0, depth=6):
         import torch
         from . import _native as nat
         dist = _dist()
@@ -132,10 +135,9 @@ class PeerGather:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.cap_rows, self.with_contacts = int(cap_rows), bool(with_contacts)
         self.device = torch.cuda.current_device() if device is None else int(device)
-        # measured on 2 / 4 / 8 B200s (config 3, ms per step): collective 0.81 / 0.90 / 0.95, one-sided 0.84 / 0.89 / 0.89
-        self.one_sided = (self.world >= 4) if one_sided is None else bool(one_sided)
+        self.one_sided = (dist.get_backend(group) == 'nccl') if one_sided is None else bool(one_sided)
         self.timeout_s = float(timeout_s)
-        self.depth = D = max(2, int(depth))               # slots per rank (ring): how many calls a rank may run ahead of dst
+        self.depth = D = max(self.ACK_LAG + 2, int(depth))   # slots per rank (ring): how many steps a rank may run ahead of dst
         self._nat = nat
         gs_bytes = D * self.world * self.cap_rows * 56
         data_bytes = gs_bytes + (D * self.world * self.cap_rows * 48 if with_contacts else 0)
@@ -168,12 +170,13 @@ class PeerGather:
         self.flags_ptr = self.base + ctrl_off
         self.counts_ptr = self.flags_ptr + 8 * D * self.world
         self.ack_ptr = self.counts_ptr + 8 * D * self.world
-        self.epoch = 0                                    # calls completed so far; the next call writes ring slot (epoch + 1) % depth
+        self.epoch = 0                                    # steps issued so far; the next one writes ring slot (epoch + 1) % depth
+        self.completed = 0
         dev = f'cuda:{self.device}'
         self.counts = torch.zeros((self.world,), dtype=torch.int64, device=dev)
-        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.side = torch.cuda.Stream(self.device)
-        self.ack_event = torch.cuda.Event()
+        self.status = torch.zeros((1,), dtype=torch.int32).pin_memory()       # written by a timed-out wait kernel; the host reads it without a sync
+        self.side = torch.cuda.Stream(self.device)        # dst: the wait kernels, in epoch order; others: the acknowledgement polls
+        self.done_events = {}                             # dst: epoch -> event behind its wait kernel
         self.rows = self.contacts = self.slot_counts = None
         if self.owner:
             self.rows = torch.as_tensor(_DeviceArray(self.base, (D, self.world, self.cap_rows, 14), '<f4'), device=dev)
@@ -181,42 +184,52 @@ class PeerGather:
                 self.contacts = torch.as_tensor(_DeviceArray(self.base + gs_bytes, (D, self.world, self.cap_rows, 2, 3), '<f8'), device=dev)
             self.slot_counts = torch.as_tensor(_DeviceArray(self.counts_ptr, (D, self.world), '<i8'), device=dev)
 
-    @property
-    def half(self):
-        return (self.epoch + 1) % self.depth
-
     def destinations(self):
-        """``run_pipeline(destinations=...)``: where this rank's compaction stores its output (current half, slot ``rank``).
-        One-sided mode, from the third call on: also the event the compaction has to wait for (``dst`` has consumed the
-        call that used this half before)."""
+        """begin the next step on the current stream: -> ``run_pipeline(destinations=...)``, where this rank's compaction
+        stores its output (ring slot of the step, slot ``rank``).  One-sided mode, from step depth + 1 on: the current stream
+        first waits until ``dst`` has acknowledged the step that used this ring slot before."""
         import torch
-        slot = self.half * self.world + self.rank
+        self.epoch += 1
+        e, h = self.epoch, self.epoch % self.depth
+        slot = h * self.world + self.rank
         d = {'free_gs': self.base + slot * self.cap_rows * 56}
         if self.with_contacts:
             d['free_contacts'] = self.base + self.gs_bytes + slot * self.cap_rows * 48
-        e = self.epoch + 1
         if self.one_sided and not self.owner and e > self.depth:
+            ev = torch.cuda.Event()
             with torch.cuda.stream(self.side):
                 self._nat.call('bt_peer_wait', self.ack_ptr, 1, e - self.depth, self.timeout_s, self.status.data_ptr(), None, 0,
                                self.side.cuda_stream)
-                self.ack_event.record(self.side)
-            d['compact_after'] = self.ack_event.cuda_event
+                ev.record(self.side)
+            torch.cuda.current_stream().wait_event(ev)
+        if e % self.depth == 0:
+            self.check()
         return d
 
     def complete(self, n_free):
-        """enqueue the completion of this call behind the scatter kernel of the current stream; on ``dst`` the per-rank
-        counts are then in ``counts`` (device tensor [world])"""
+        """enqueue the completion of the step begun by the last ``destinations()`` behind its scatter kernel (current stream)"""
         import torch
         dist = _dist()
-        e, h = self.epoch + 1, self.half
+        self.completed += 1
+        e = self.completed
+        if e > self.epoch:
+            raise RuntimeError('PeerGather.complete() without a matching destinations()')
+        h = e % self.depth
         if self.one_sided:
-            stream = torch.cuda.current_stream().cuda_stream
+            cur = torch.cuda.current_stream()
             self._nat.call('bt_peer_signal', n_free.data_ptr(), self.counts_ptr + 8 * (h * self.world + self.rank),
-                           self.flags_ptr + 8 * (h * self.world + self.rank), e, stream)
+                           self.flags_ptr + 8 * (h * self.world + self.rank), e, cur.cuda_stream)
             if self.owner:
-                self._nat.call('bt_peer_wait', self.flags_ptr + 8 * h * self.world, self.world, e, self.timeout_s,
-                               self.status.data_ptr(), self.ack_ptr, e - 1, stream)
-                self.counts = self.slot_counts[h]
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.side.wait_event(ev)
+                done = torch.cuda.Event()
+                with torch.cuda.stream(self.side):
+                    self._nat.call('bt_peer_wait', self.flags_ptr + 8 * h * self.world, self.world, e, self.timeout_s,
+                                   self.status.data_ptr(), self.ack_ptr, max(0, e - self.ACK_LAG), self.side.cuda_stream)
+                    done.record(self.side)
+                self.done_events[e] = done
+                self.done_events.pop(e - self.depth, None)
         elif dist.get_backend(self.group) == 'nccl':
             dist.all_gather_into_tensor(self.counts, n_free.reshape(1), group=self.group)
         else:                           # host-side backends (the single-GPU two-process test): order by a stream wait
@@ -224,22 +237,27 @@ class PeerGather:
             parts = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
             dist.all_gather(parts, n_free.reshape(1).cpu(), group=self.group)
             self.counts.copy_(torch.cat(parts))
-        self.done_half, self.epoch = h, e
-        return self.counts
+        return e
 
     def check(self):
-        """raise if a wait kernel of this rank has timed out (host sync)"""
-        if int(self.status.item()):
+        """raise if a wait kernel of this rank has timed out (no device synchronisation: the status word is host memory)"""
+        if int(self.status[0]):
             raise self._nat.NativeError(f'PeerGather: rank {self.rank} waited more than {self.timeout_s} s for a peer')
 
-    def result(self):
-        """on ``dst``: (rows [sum n_r, 14], contacts [sum n_r, 2, 3] or None) in rank order; (None, None) elsewhere"""
+    def result(self, epoch=None):
+        """on ``dst``: (rows [sum n_r, 14], contacts [sum n_r, 2, 3] or None) of step ``epoch`` (default: the last completed
+        one) in rank order, as new tensors; (None, None) elsewhere.  Waits for that step's completion only."""
         import torch
         if not self.owner:
             return None, None
-        counts = [int(c) for c in self.counts.cpu().tolist()]
-        self.check()
-        h = self.done_half
+        e = self.completed if epoch is None else int(epoch)
+        h = e % self.depth
+        if self.one_sided:
+            self.done_events[e].synchronize()
+            self.check()
+            counts = [int(c) for c in self.slot_counts[h].cpu().tolist()]
+        else:
+            counts = [int(c) for c in self.counts.cpu().tolist()]
         rows = torch.cat([self.rows[h, r, :c] for r, c in enumerate(counts)], dim=0)
         contacts = torch.cat([self.contacts[h, r, :c] for r, c in enumerate(counts)], dim=0) if self.with_contacts else None
         return rows, contacts
@@ -251,7 +269,7 @@ class PeerGather:
         if not self.base:
             return False
         torch.cuda.synchronize(self.device)
-        status = int(self.status.item())
+        status = int(self.status[0])
         self.rows = self.contacts = self.slot_counts = None
         _dist().barrier(group=self.group)                     # nobody is still storing into the buffer
         if self.owner:

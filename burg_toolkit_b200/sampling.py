@@ -85,8 +85,8 @@ class CastResult:
 class PendingHostBatch:
     """A batch in flight (``AntipodalGraspSampler.submit_host``); ``result()`` waits for it and returns host views."""
 
-    def __init__(self, event, pinned, n_ref, n_candidates):
-        self.event, self.pinned, self.n_ref, self.n_candidates = event, pinned, n_ref, n_candidates
+    def __init__(self, event, pinned, n_ref, n_candidates, retry=None):
+        self.event, self.pinned, self.n_ref, self.n_candidates, self.retry = event, pinned, n_ref, n_candidates, retry
 
     def done(self):
         return self.event.query()
@@ -94,9 +94,17 @@ class PendingHostBatch:
     def result(self):
         self.event.synchronize()
         p = self.pinned
+        n_over = int(p['out_n'][3])
+        if n_over and self.retry is not None:
+            again = self.retry()                       # a longer hit list (up to 32 crossings per ray)
+            if again is not None:
+                return again
+            import warnings
+            warnings.warn(f'{n_over} rays cross more than 32 surfaces of the mesh: their farthest crossings were not considered')
         k = int(p['out_n'][0])
         return dict(gs=GraspSet.from_array(p['out_gs'][:k].numpy()), contacts=p['out_c'][:k].numpy(), n_grasps=int(p['out_n'][2]),
-                    n_free=k, h2d_bytes=2 * self.n_ref * 24, d2h_bytes=k * (56 + 48) + 16, n_candidates=self.n_candidates, chunks=1)
+                    n_free=k, h2d_bytes=2 * self.n_ref * 24, d2h_bytes=k * (56 + 48) + 16, n_candidates=self.n_candidates, chunks=1,
+                    hit_list_overflows=n_over)
 
 
 class AntipodalGraspSampler:
@@ -363,7 +371,7 @@ class AntipodalGraspSampler:
                         None if gripper is None else gripper.handle.value, gen, tuple(sorted(ws.redirect.items())), base, n_ref)
                 g = ws.graphs.get(gkey)
                 if g is None:
-                    if len(ws.graphs) >= 16:
+                    if len(ws.graphs) >= 64:
                         ws.graphs.pop(next(iter(ws.graphs)))
                     cap = self.__dict__.setdefault('_capture_streams', {}).setdefault(device, torch.cuda.Stream(device))
                     bufs = ws.buffers(*gen)
@@ -422,6 +430,7 @@ class AntipodalGraspSampler:
         random draws (not their distribution) depend on ``chunks``."""
         torch = nat.require_cuda()
         device = self._device()
+        caller_pinned = pinned
         pinned = {} if pinned is None else pinned
         n = len(ref_points)
         cap = max(1, n * int(self.max_targets_per_ref_point)) * int(self.n_orientations)
@@ -432,7 +441,7 @@ class AntipodalGraspSampler:
         while n % chunks:                                   # equal batches only (one workspace shape per stream)
             chunks -= 1
         if push and chunks == 1 and kwargs['tail_splits'] <= 1 and n > 0:
-            return self.submit_host(ref_points, ref_normals, seed=seed, slot=0, pinned=pinned, **kwargs).result()
+            return self.submit_host(ref_points, ref_normals, seed=seed, slot=0, pinned=caller_pinned, **kwargs).result()      # (staging buffers: the caller's, else the slot's own)
         with torch.cuda.device(device):
             for key, arr in (('pts', ref_points), ('nrm', ref_normals)):
                 if key not in pinned or pinned[key].shape[0] != n:
@@ -534,8 +543,20 @@ class AntipodalGraspSampler:
             with torch.cuda.stream(st):
                 out = self.run_pipeline(pinned['pts'], pinned['nrm'], seed=seed, destinations=dest, slot=('host', slot), **kwargs)
                 out_n[2:3].copy_(out['n_grasps'], non_blocking=True)
+                out_n[3:4].copy_(out['overflow'], non_blocking=True)
                 hs['event'].record(st)
-        return PendingHostBatch(hs['event'], pinned, n, out['n_candidates'])
+
+        def retry():
+            # some ray crossed more surfaces than the hit list holds (the reference has no cap): again with a longer list
+            cap_hits = int(self.max_hits_per_ray)
+            if cap_hits >= 32:
+                return None
+            self.max_hits_per_ray = min(32, 2 * cap_hits)
+            try:
+                return self.submit_host(ref_points, ref_normals, seed=seed, slot=slot, pinned=pinned, **kwargs).result()
+            finally:
+                self.max_hits_per_ray = cap_hits
+        return PendingHostBatch(hs['event'], pinned, n, out['n_candidates'], retry)
 
     # -----------------------------------------------------------------------------------------------
     # reference API
@@ -587,12 +608,18 @@ class AntipodalGraspSampler:
         n_o, k = int(self.n_orientations), int(self.max_targets_per_ref_point)
         seed = int(np.random.randint(1, 2 ** 62))
         rows, contacts, total = [], [], 0
-        cursor, consumed, n_refs_used = 0, 0, 0
+        cursor, consumed, n_refs_used, overflowed = 0, 0, 0, 0
         batch = max(64, int(np.ceil(n / (n_o * 0.8))) + 16)
         while total < n and consumed < self.max_passes * len(ref):
             idx = (cursor + torch.arange(batch, device=ref.device)) % len(ref)
             pts, nrm = ref[idx, 0:3].contiguous(), ref[idx, 3:6].contiguous()
             out = self.run_pipeline(pts, nrm, seed=seed + consumed, check_collisions=False)
+            n_over = int(out['overflow'].item())
+            while n_over and self.max_hits_per_ray < 32:                # the reference has no cap on crossings per ray:
+                self.max_hits_per_ray = min(32, 2 * int(self.max_hits_per_ray))        # redo the batch with a longer hit list
+                out = self.run_pipeline(pts, nrm, seed=seed + consumed, check_collisions=False)
+                n_over = int(out['overflow'].item())
+            overflowed += n_over
             per_ref = out['pair_count'][:batch].to(torch.int64) * n_o
             cum = torch.cumsum(per_ref, 0)
             need = n - total
@@ -607,7 +634,10 @@ class AntipodalGraspSampler:
             consumed += take_refs
             batch = min(1 << 16, max(64, int((n - total) / max(total / max(n_refs_used, 1), 1e-3)) + 16))
         self.last_stats = dict(ref_points_used=n_refs_used, candidates=n_refs_used * self.n_rays, grasps=total,
-                               exhausted=total < n)
+                               exhausted=total < n, hit_list_overflows=overflowed)
+        if overflowed:
+            import warnings
+            warnings.warn(f'{overflowed} rays cross more than 32 surfaces of the mesh: their farthest crossings were not considered')
         if total < n and self.verbose:
             print(f'warning: only {total} grasps found after {self.max_passes} passes over the reference points')
         gs = GraspSet.from_array(np.concatenate(rows) if rows else np.zeros((0, 14), dtype=np.float32))

@@ -102,6 +102,9 @@ BT_API int         bt_stream_sync(void* stream);
  *   [6] cast LBVH nodes fetched but skipped by the normal-cone test
  * (used by bench.py, outside the timed region, for the L2 traffic model of the roofline) */
 BT_API int bt_debug_set_counters(uint64_t* d_counters);
+/* measured L2 read bandwidth [GB/s]: all SMs stream one L2-resident buffer of `bytes` (1 MiB ..) `iters` times (synchronises).
+ * The mesh + LBVH of the ray caster live in L2, so this is the memory roof of its traffic model (bench.py roofline.binding) */
+BT_API int bt_debug_l2_probe(int device, int64_t bytes, int32_t iters, double* gbytes_per_s);
 
 /* ---- mesh / scene ---------------------------------------------------------------------------------
  * replaces mesh_processing.as_trimesh + trimesh.Trimesh construction + RayMeshIntersector / collision
