@@ -58,7 +58,8 @@ class PipelineBuffers(C.Structure):
                 ('pair_offset', C.c_void_p), ('pair_ref', C.c_void_p), ('pair_q', C.c_void_p), ('cap_pairs', C.c_int64),
                 ('gs', C.c_void_p), ('contacts', C.c_void_p), ('n_grasps', C.c_void_p), ('colliding', C.c_void_p),
                 ('free_gs', C.c_void_p), ('free_contacts', C.c_void_p), ('n_free', C.c_void_p),
-                ('free_base', C.c_void_p), ('hit_t', C.c_void_p), ('compact_after', C.c_void_p), ('seed_add', C.c_void_p)]
+                ('free_base', C.c_void_p), ('hit_t', C.c_void_p), ('compact_after', C.c_void_p), ('seed_add', C.c_void_p),
+                ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64)]
 
 
 class NativeError(RuntimeError):

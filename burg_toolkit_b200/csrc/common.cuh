@@ -50,16 +50,29 @@ inline void retain_pool_memory() {
     done[dev] = true;
 }
 
-// stream-ordered scratch buffer (cudaMallocAsync / cudaFreeAsync)
+// Caller-provided scratch arena of the running bt_ags_pipeline call (bt_pipeline_buffers.scratch): a bump allocator that
+// lives for one call.  With it the call makes no stream-ordered allocations -- which matters when the call is captured
+// into a CUDA graph: allocation nodes give every graph its own memory, mapped at launch (hundreds of graphs -- one per
+// target mesh, stream and gather slot -- then cost milliseconds per launch and gigabytes).
+struct Arena { char* base = nullptr; size_t size = 0, used = 0; };
+extern thread_local Arena* g_arena;
+
+// scratch buffer: from the arena if there is one with room, else stream-ordered (cudaMallocAsync / cudaFreeAsync)
 struct Scratch {
     void* p = nullptr;
     cudaStream_t s = nullptr;
+    bool owned = false;
     cudaError_t alloc(size_t bytes, cudaStream_t stream) {
         s = stream;
+        if (g_arena) {
+            const size_t off = (g_arena->used + 255) & ~(size_t)255;
+            if (off + bytes <= g_arena->size) { p = g_arena->base + off; g_arena->used = off + bytes; return cudaSuccess; }
+        }
         retain_pool_memory();
+        owned = true;
         return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
     }
-    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    ~Scratch() { if (p && owned) cudaFreeAsync(p, s); }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

@@ -15,6 +15,14 @@ struct bt_timer {
 };
 
 namespace bt {
+thread_local Arena* g_arena = nullptr;
+struct ArenaScope {               // installs the call's scratch arena for the duration of bt_ags_pipeline
+    Arena a;
+    ArenaScope(void* base, int64_t bytes) {
+        if (base && bytes > 0) { a.base = static_cast<char*>(base); a.size = (size_t)bytes; g_arena = &a; }
+    }
+    ~ArenaScope() { g_arena = nullptr; }
+};
 // number of valid rows inside the range [row0, row0 + n_cap) of a list whose valid length is *d_n
 __global__ void range_count_kernel(const int64_t* __restrict__ d_n, int64_t row0, int64_t n_cap, int64_t* __restrict__ out) {
     const int64_t v = *d_n - row0;
@@ -103,6 +111,8 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     BT_REQUIRE(!cfg->compact || (cfg->check_collisions && b->free_gs && b->n_free), "compaction needs the collision stage and its buffers");
     cudaStream_t st = (cudaStream_t)stream;
     BT_CUDA(cudaSetDevice(target->m.device));
+    BT_REQUIRE((reinterpret_cast<uintptr_t>(b->scratch) & 255) == 0, "scratch must be 256-byte aligned");
+    ArenaScope arena(b->scratch, b->scratch_bytes);
     if (timer) for (int i = 0; i < BT_N_STAGES; ++i) timer->ran[i] = false;
     const int n_o = cfg->n_orientations;
 

@@ -273,6 +273,9 @@ class PipelineWorkspace:
         self.n_free = torch.zeros((1,), dtype=i64, device=d) if compact else None
         self.rows = rows
         self.seed_add = torch.zeros((1,), dtype=i64, device=d)      # device-resident seed offset (graph replays: bt_set_u64)
+        # scratch arena of bt_ags_pipeline (candidate lists, scan states, collision queues): no allocations inside the call
+        arena = 80 * max(n_ref, 1) * n_rays + (200 * rows if collisions else 0) + (1 << 20)
+        self.scratch = torch.empty((min(arena, 3 << 30),), dtype=u8, device=d)
         self.graphs = {}                                             # captured bt_ags_pipeline calls (DeviceGraph) by call signature
         # optional raw destinations for the compaction outputs ('free_gs', 'free_contacts', 'n_free' -> address): a peer
         # GPU's buffer (distributed.PeerGather) or mapped pinned host memory (evaluate_host); the kernel stores there directly
@@ -287,6 +290,7 @@ class PipelineWorkspace:
             setattr(b, name, None if t is None else int(self.redirect.get(name) or t.data_ptr()))
         b.free_base, b.compact_after = self.redirect.get('free_base'), self.redirect.get('compact_after')
         b.seed_add = self.seed_add.data_ptr()
+        b.scratch, b.scratch_bytes = self.scratch.data_ptr(), self.scratch.numel()
         b.sample_surface, b.generate_dirs, b.generate_frame_vecs = int(sample_surface), int(generate_dirs), int(generate_frame_vecs)
         b.cap_pairs = self.cap_pairs
         return b

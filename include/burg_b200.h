@@ -285,6 +285,10 @@ typedef struct bt_pipeline_buffers {
                                 compaction on another stream, whose count is free_base)                       */
     const uint64_t* seed_add; /* nullable [1] on the device: added to `seed` by every kernel that draws random numbers
                                 (a captured graph of the call is replayed with a new seed by storing it here: bt_set_u64) */
+    void*    scratch;        /* nullable, 256-byte aligned device memory the call may use for its intermediates (candidate
+                                lists, scan states, collision queues) instead of stream-ordered allocations; what does not
+                                fit is allocated as before.  ~80 B per ray + 200 B per posed grasp holds everything.     */
+    int64_t  scratch_bytes;
 } bt_pipeline_buffers;
 
 BT_API int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, const bt_gripper* gripper,
