@@ -6,6 +6,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 struct bt_timer {
@@ -38,11 +41,15 @@ struct TailState {
     int64_t* counts = nullptr;            // [2 * BT_MAX_TAIL_SPLITS]: running kept-row counts, then valid rows per range
 };
 constexpr int BT_MAX_TAIL_SPLITS = 8;
-static TailState g_tail[64];
+// one state per (device, caller stream): two pipelines in flight on different streams of a device must not share the side
+// stream, the events or the running counts
+static std::map<std::pair<int, cudaStream_t>, TailState> g_tail;
+static std::mutex g_tail_mutex;
 
-static int tail_state(int device, TailState** out) {
+static int tail_state(int device, cudaStream_t caller, TailState** out) {
     BT_REQUIRE(device >= 0 && device < 64, "device index out of range");
-    TailState& t = g_tail[device];
+    std::lock_guard<std::mutex> lock(g_tail_mutex);
+    TailState& t = g_tail[std::make_pair(device, caller)];
     if (!t.side) {
         BT_CUDA(cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking));
         BT_CUDA(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
@@ -158,7 +165,7 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
             // split tail: collide(range s+1) on one stream overlaps compact(range s) on the other; every compaction appends
             // behind the previous range's rows (device-side running count), so the output is the same contiguous list
             TailState* t = nullptr;
-            STAGE_CALL(tail_state(target->m.device, &t));
+            STAGE_CALL(tail_state(target->m.device, st, &t));
             BT_CUDA(cudaEventRecord(t->ready, st));
             BT_CUDA(cudaStreamWaitEvent(t->side, t->ready, 0));
             int last = 0;

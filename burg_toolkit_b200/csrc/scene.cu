@@ -66,6 +66,7 @@ using namespace bt;
 extern "C" int bt_mesh_pair_collide(const bt_mesh* a, const bt_mesh* b, int32_t* d_flag, void* stream) {
     BT_REQUIRE(a && b && d_flag, "null pointer");
     BT_REQUIRE(a->m.device == b->m.device, "the two meshes live on different devices");
+    BT_REQUIRE(a->m.info.max_depth + 2 <= 64 && b->m.info.max_depth + 2 <= 64, "LBVH too deep for the traversal stack (64)");
     cudaStream_t st = (cudaStream_t)stream;
     BT_CUDA(cudaSetDevice(a->m.device));
     BT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int32_t), st));

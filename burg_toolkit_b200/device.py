@@ -83,20 +83,35 @@ _mesh_cache = {}
 MESH_CACHE_SIZE = 256
 
 
+def mesh_tag(mesh):
+    """what identifies a mesh's GEOMETRY for the device-side caches: our own ``TriangleMesh`` carries a version counter
+    (bumped by every assignment; its arrays are read-only once uploaded, so nothing changes behind it); any other object
+    (open3d / trimesh meshes, whose buffers can be edited in place) is hashed in full -- vertices and faces"""
+    from .mesh import TriangleMesh
+    if isinstance(mesh, TriangleMesh):
+        return ('v', mesh.version, len(mesh.vertices), len(mesh.triangles))
+    import zlib
+    m = as_mesh(mesh, need_vertex_normals=False)
+    v, f = np.ascontiguousarray(m.vertices), np.ascontiguousarray(m.triangles)
+    return ('h', v.shape, f.shape, zlib.adler32(v.view(np.uint8).reshape(-1)), zlib.adler32(f.view(np.uint8).reshape(-1)))
+
+
 def cached_device_mesh(mesh, device=None):
-    """DeviceMesh for ``mesh`` keyed by object identity + vertex/triangle counts + a sampled vertex checksum (rebuilds
-    if the mesh object was replaced or visibly edited; meshes are otherwise treated as immutable)."""
+    """DeviceMesh for ``mesh`` keyed by object identity + ``mesh_tag`` (rebuilds if the mesh object was replaced or its
+    geometry changed)."""
+    from .mesh import TriangleMesh
     dev = device_index(device)
-    m = as_mesh(mesh)
     key = (id(mesh), dev)
-    v = np.asarray(m.vertices)
-    # cheap fingerprint (this sits on every pipeline call): counts + 32 strided rows, not the whole vertex array
-    tag = (len(v), len(m.triangles), float(v[::max(1, len(v) // 32)].sum()))
+    tag = mesh_tag(mesh)
     hit = _mesh_cache.pop(key, None)
     if hit is not None and hit[0] == tag:
         _mesh_cache[key] = hit                       # most recently used last
         return hit[1]
+    m = as_mesh(mesh)
     dm = DeviceMesh(m.vertices, m.triangles, m.vertex_normals, dev)
+    if isinstance(mesh, TriangleMesh):
+        mesh.freeze()
+        tag = mesh_tag(mesh)
     _mesh_cache[key] = (tag, dm)
     if len(_mesh_cache) > MESH_CACHE_SIZE:           # least recently used first (a cluttered scene has tens of objects)
         _mesh_cache.pop(next(iter(_mesh_cache)))

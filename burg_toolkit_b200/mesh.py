@@ -17,6 +17,27 @@ import numpy as np
 
 
 class TriangleMesh:
+    """``vertices`` / ``triangles`` / ``vertex_normals`` are properties: assigning a new array bumps ``version``, which is
+    what the device-side caches key on (``device.cached_device_mesh``).  Once a mesh has been uploaded its arrays are made
+    read-only, so an in-place edit (``mesh.vertices[i] += ...``) raises instead of leaving a stale LBVH on the GPU --
+    assign a new array, or use ``transform`` / ``translate``."""
+
+    version = 0
+
+    def _set(self, name, value):
+        self.__dict__[name] = value
+        self.__dict__['version'] = self.__dict__.get('version', 0) + 1
+
+    vertices = property(lambda self: self.__dict__['_v'], lambda self, a: self._set('_v', a))
+    triangles = property(lambda self: self.__dict__['_f'], lambda self, a: self._set('_f', a))
+    vertex_normals = property(lambda self: self.__dict__.get('_vn'), lambda self, a: self._set('_vn', a))
+
+    def freeze(self):
+        """make the geometry arrays read-only (called when the mesh is uploaded to a device)"""
+        for a in (self.vertices, self.triangles, self.vertex_normals):
+            if isinstance(a, np.ndarray):
+                a.setflags(write=False)
+
     def __init__(self, vertices=None, triangles=None, vertex_normals=None, triangle_normals=None):
         self.vertices = np.zeros((0, 3)) if vertices is None else np.array(vertices, dtype=np.float64).reshape(-1, 3)
         self.triangles = np.zeros((0, 3), dtype=np.int32) if triangles is None else \

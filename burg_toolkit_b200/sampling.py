@@ -697,11 +697,18 @@ class AntipodalGraspSampler:
         return colliding.cpu().numpy().astype(bool)
 
     def _scene(self, meshes, device):
-        key = tuple(id(m) for m in meshes)
+        """the collision scene of ``meshes`` on ``device``: a single mesh shares the ray caster's cached DeviceMesh (one
+        LBVH, never two views of one object); several are merged, keyed by every member's identity AND geometry tag"""
+        if len(meshes) == 1:
+            return dev.cached_device_mesh(meshes[0], device)
+        key = tuple((id(m), dev.mesh_tag(m)) for m in meshes)
         cache = getattr(self, '_scene_cache', None)
         if cache is not None and cache[0] == key and cache[1].device == device:
             return cache[1]
-        scene = dev.cached_device_mesh(meshes[0], device) if len(meshes) == 1 else dev.DeviceMesh.from_meshes(meshes, device)
+        scene = dev.DeviceMesh.from_meshes(meshes, device)
+        for m in meshes:
+            if hasattr(m, 'freeze'):
+                m.freeze()
         self._scene_cache = (key, scene, meshes)
         return scene
 
