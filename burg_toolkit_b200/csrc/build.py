@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['mesh.cu', 'ags.cu', 'collide.cu', 'coverage.cu', 'pipeline.cu', 'generators.cu', 'scene.cu', 'peer.cu']
+SOURCES = ['mesh.cu', 'ags.cu', 'collide.cu', 'coverage.cu', 'pipeline.cu', 'generators.cu', 'scene.cu', 'peer.cu', 'poisson.cu']
 HEADERS = ['common.cuh', 'tritri.cuh', os.path.join('..', '..', 'include', 'burg_b200.h')]
 LIB = os.path.join(HERE, 'libburgb200.so')
 

@@ -98,13 +98,14 @@ def mesh_tag(mesh):
 
 def cached_device_mesh(mesh, device=None):
     """DeviceMesh for ``mesh`` keyed by object identity + ``mesh_tag`` (rebuilds if the mesh object was replaced or its
-    geometry changed)."""
+    geometry changed).  Identity means THE object, not its address: the entry holds a weak reference, so the id of a
+    collected temporary (``ObjectInstance.get_mesh()`` returns a new mesh every call) reused by another mesh never hits."""
     from .mesh import TriangleMesh
     dev = device_index(device)
     key = (id(mesh), dev)
     tag = mesh_tag(mesh)
     hit = _mesh_cache.pop(key, None)
-    if hit is not None and hit[0] == tag:
+    if hit is not None and hit[0] == tag and (hit[2] is None or hit[2]() is mesh):
         _mesh_cache[key] = hit                       # most recently used last
         return hit[1]
     m = as_mesh(mesh)
@@ -112,7 +113,11 @@ def cached_device_mesh(mesh, device=None):
     if isinstance(mesh, TriangleMesh):
         mesh.freeze()
         tag = mesh_tag(mesh)
-    _mesh_cache[key] = (tag, dm)
+    try:
+        ref = weakref.ref(mesh)
+    except TypeError:                                # objects without weak references are identified by their full hash
+        ref = None
+    _mesh_cache[key] = (tag, dm, ref)
     if len(_mesh_cache) > MESH_CACHE_SIZE:           # least recently used first (a cluttered scene has tens of objects)
         _mesh_cache.pop(next(iter(_mesh_cache)))
     return dm

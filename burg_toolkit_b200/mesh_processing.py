@@ -42,16 +42,23 @@ def collisions(meshes, device=None):
     return sorted(pairs)
 
 
-def poisson_disk_sampling(mesh, radius=0.003, n_points=None, with_normals=True, init_factor=5, seed=1, device=None):
-    """Area-weighted surface samples with triangle normals (mesh_processing.py:52-83).  The reference delegates to
-    open3d's unseedable sampler; here the uniform stage runs on the device (``bt_sample_surface``) and ``n_points``
-    defaults to ``surface_area / radius**2`` like the reference.  -> (n, 6) float64 (or (n, 3) without normals)."""
+def poisson_disk_sampling(mesh, radius=0.003, n_points=None, with_normals=True, init_factor=5, seed=1, device=None,
+                          eliminate=True):
+    """Evenly spread surface samples with triangle normals (reference mesh_processing.py:52-83 -> open3d
+    ``sample_points_poisson_disk``): ``init_factor * n_points`` area-weighted uniform samples (``bt_sample_surface``), then
+    weighted sample elimination down to ``n_points`` (``bt_poisson_disk_eliminate``: open3d's weights, parallel rounds
+    instead of its serial priority queue).  ``n_points`` defaults to the reference's estimate from ``radius`` (square
+    packing of circles on a square of the mesh's surface area).  ``eliminate=False`` returns ``n_points`` uniform samples
+    (the first stage only).  open3d's sampler cannot be seeded; here ``seed`` makes the set reproducible.
+    -> (n, 6) float64 (or (n, 3) without normals), in the order of the triangles they lie on."""
     from .sampling import AntipodalGraspSampler
     m = as_mesh(mesh)
     if n_points is None:
-        n_points = int(m.get_surface_area() / (radius ** 2))
+        s = np.sqrt(m.get_surface_area())
+        n_s = (s + 2 * radius) / (2 * radius)
+        n_points = int(n_s ** 2)
     ags = AntipodalGraspSampler()
     ags.mesh, ags.device, ags.verbose = m, device, False
-    pts, nrm, _ = ags.sample_surface(int(n_points), int(seed))
+    pts, nrm = ags.surface_points(int(n_points), int(seed), poisson_disk=bool(eliminate), init_factor=init_factor)
     pts, nrm = pts.cpu().numpy(), nrm.cpu().numpy()
     return np.concatenate([pts, nrm], axis=1) if with_normals else pts

@@ -131,6 +131,8 @@ class AntipodalGraspSampler:
         self.surface_samples = None         # optional (n_sample, 6) [point | normal] override of stage S1
         self.max_hits_per_ray = 8           # per-ray hit list capacity (doubled automatically on overflow)
         self.max_passes = 10                # cap on wrap-arounds of the reference-point list (the reference spins forever)
+        self.poisson_disk = False           # first-contact candidates: weighted sample elimination after the uniform samples (open3d's
+                                            # Poisson-disk stage, mesh_processing.py:77-81); off: the uniform stage only
         self.cone_culling = True            # lean pipeline: skip triangles / LBVH subtrees whose vertex normals rule out a valid hit
         self.last_stats = {}
 
@@ -176,6 +178,26 @@ class AntipodalGraspSampler:
             nat.call('bt_sample_surface', dm.handle, n, int(seed), nat.ptr(pts), nat.ptr(nrm), nat.ptr(tri),
                      nat.current_stream())
         return pts, nrm, tri
+
+    def surface_points(self, n, seed, poisson_disk=False, init_factor=5):
+        """S1 as the reference calls it (mesh_processing.poisson_disk_sampling): ``n`` surface points + triangle normals.
+        ``poisson_disk``: draw ``init_factor * n`` uniform samples and keep the ``n`` that weighted sample elimination
+        leaves (open3d's alpha = 8, beta = 0.5, gamma = 1.5); else the uniform stage only.  -> (pts, nrm) CUDA tensors."""
+        torch = nat.require_cuda()
+        if not poisson_disk or init_factor <= 1:
+            pts, nrm, _ = self.sample_surface(n, seed)
+            return pts, nrm
+        dm = self._device_mesh()
+        n0 = int(init_factor) * int(n)
+        pts, nrm, _ = self.sample_surface(n0, seed)
+        with torch.cuda.device(dm.device):
+            keep = torch.empty((n0,), dtype=torch.uint8, device='cuda')
+            rounds = C.c_int32()
+            nat.call('bt_poisson_disk_eliminate', nat.ptr(pts), n0, int(n), float(dm.info.surface_area), 8.0, 0.5, 1.5,
+                     nat.ptr(keep), C.byref(rounds), nat.current_stream())
+            self.last_stats = dict(self.last_stats, poisson_disk_rounds=int(rounds.value), poisson_disk_initial=n0)
+            sel = keep.bool()
+            return pts[sel].contiguous(), nrm[sel].contiguous()
 
     def cone_rays(self, ref_normals, seed):
         """S2: [n_ref, n_rays, 3] directions in the friction cone about ``-normal`` (device RNG)."""
@@ -584,7 +606,7 @@ class AntipodalGraspSampler:
             ref = torch.from_numpy(ref).to(f'cuda:{self._device()}')
         else:
             seed = int(np.random.randint(1, 2 ** 62))
-            pts, nrm, _ = self.sample_surface(n_sample, seed)
+            pts, nrm = self.surface_points(n_sample, seed, poisson_disk=bool(self.poisson_disk))
             ref = torch.cat([pts, nrm], dim=1)
             gen = torch.Generator(device=ref.device)
             gen.manual_seed(seed)
@@ -702,8 +724,8 @@ class AntipodalGraspSampler:
         if len(meshes) == 1:
             return dev.cached_device_mesh(meshes[0], device)
         key = tuple((id(m), dev.mesh_tag(m)) for m in meshes)
-        cache = getattr(self, '_scene_cache', None)
-        if cache is not None and cache[0] == key and cache[1].device == device:
+        cache = getattr(self, '_scene_cache', None)      # (the cache entry keeps the mesh objects alive, so their ids cannot be reused)
+        if cache is not None and cache[0] == key and cache[1].device == device and all(a is b for a, b in zip(cache[2], meshes)):
             return cache[1]
         scene = dev.DeviceMesh.from_meshes(meshes, device)
         for m in meshes:

@@ -124,6 +124,15 @@ BT_API int bt_mesh_copy_bvh(const bt_mesh* mesh, float* h_nodes, int32_t* h_leaf
 BT_API int bt_sample_surface(const bt_mesh* mesh, int64_t n, uint64_t seed, double* d_pts, double* d_nrm,
                       int32_t* d_tri, void* stream);
 
+/* ---- S1, second stage: weighted sample elimination (replaces the elimination loop of open3d's
+ * TriangleMesh::SamplePointsPoissonDisk behind mesh_processing.poisson_disk_sampling, mesh_processing.py:77-81; Yuksel 2015
+ * with open3d's alpha = 8, beta = 0.5, gamma = 1.5).  d_pts [n0,3] f64: the init_factor * n uniform samples of
+ * bt_sample_surface; d_keep [n0] u8 out: 1 for the n_target samples that stay.  Parallel rounds (every sample that outweighs
+ * all its living neighbours goes at once) instead of open3d's serial priority queue; h_rounds (nullable, host): rounds taken.
+ * Synchronises. */
+BT_API int bt_poisson_disk_eliminate(const double* d_pts, int64_t n0, int64_t n_target, double surface_area, double alpha,
+                                     double beta, double gamma, uint8_t* d_keep, int32_t* h_rounds, void* stream);
+
 /* ---- S2: friction-cone ray directions (replaces sampling.rays_within_cone, sampling.py:17-48, for
  * axis = -normal).  d_normals: [n_ref,3] f64, d_dirs: [n_ref,n_rays,3] f64. */
 BT_API int bt_cone_rays(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed,

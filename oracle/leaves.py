@@ -366,6 +366,49 @@ def sample_points_uniformly(vertices, triangles, triangle_normals, n_points, rng
     return pts, triangle_normals[tri_idx], tri_idx
 
 
+def poisson_disk_eliminate(points, n_points, surface_area, alpha=8.0, beta=0.5, gamma=1.5):
+    """open3d 0.12 ``TriangleMesh::SamplePointsPoissonDisk``, elimination stage (SURVEY.md Appendix A.2; Yuksel 2015,
+    weighted sample elimination): weights ``(1 - max(d, r_min) / r_max) ** alpha`` summed over the neighbours within
+    ``r_max``, a max-priority queue, and one removal at a time with the neighbours' weights updated -- the SERIAL
+    algorithm.  -> bool[len(points)] of the ``n_points`` samples that stay.  (open3d draws the initial samples from an
+    unseedable generator, so this restates the algorithm, not a reproducible output.)"""
+    import heapq
+    from scipy.spatial import cKDTree
+    pts = np.asarray(points, dtype=np.float64)
+    n0 = len(pts)
+    if n_points >= n0:
+        return np.ones(n0, dtype=bool)
+    ratio = n_points / n0
+    r_max = 2.0 * np.sqrt((surface_area / n_points) / (2.0 * np.sqrt(3.0)))
+    r_min = r_max * beta * (1.0 - ratio ** gamma)
+
+    def wf(d):
+        return (1.0 - np.maximum(d, r_min) / r_max) ** alpha
+    tree = cKDTree(pts)
+    nbrs = tree.query_ball_point(pts, r_max)
+    weight = np.zeros(n0)
+    for i, js in enumerate(nbrs):
+        js = np.array([j for j in js if j != i], dtype=np.int64)
+        nbrs[i] = js
+        if len(js):
+            weight[i] = wf(np.linalg.norm(pts[js] - pts[i], axis=1)).sum()
+    alive = np.ones(n0, dtype=bool)
+    heap = [(-weight[i], i) for i in range(n0)]
+    heapq.heapify(heap)
+    living = n0
+    while living > n_points:
+        w, i = heapq.heappop(heap)
+        if not alive[i] or -w != weight[i]:            # dead, or a stale entry (the weight changed since it was pushed)
+            continue
+        alive[i] = False
+        living -= 1
+        for j in nbrs[i]:
+            if alive[j]:
+                weight[j] -= wf(np.linalg.norm(pts[j] - pts[i]))
+                heapq.heappush(heap, (-weight[j], j))
+    return alive
+
+
 class O3dTriangleMesh:
     """Stand-in for ``open3d.geometry.TriangleMesh`` (the attribute surface used on the path and by
     the reference's ``gripper.py`` / ``visualization.create_plane``)."""
