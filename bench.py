@@ -690,18 +690,30 @@ def coverage_block(ctx, workload, steps, warmup, with_cpu):
     the total work is fixed, i.e. strong scaling."""
     torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
     from burg_toolkit_b200 import metrics
-    from burg_toolkit_b200.distributed import shard_range
+    from burg_toolkit_b200.distributed import shard_range, spatial_order
     n_cov = 1_000_000 if workload == 'coverage_c5' else COV_N
     ref_all, qry = coverage_sets(n_cov)
     pairs = float(len(ref_all)) * float(len(qry))
     b, e = shard_range(len(ref_all), rank, world)
-    ref = ref_all[b:e]
+    # shards = spatial tiles of the pair matrix: the reference rows in grid-cell order, one contiguous slice per rank
+    # (input partitioning, done once on the host; coverage does not depend on the row order)
+    ref = ref_all[spatial_order(ref_all)[b:e]] if world > 1 else ref_all
     dref, dqry = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
     clocks = ClockSampler(ctx.local_rank)
     res = {}
-    for algo in (('grid',) if n_cov > 200_000 else ('grid', 'tiles')):
+    # 'grid': the query set prepared once (resident, binned, sorted: metrics.prepare_query) -- the sweep of BASELINE config 5
+    # evaluates many reference sets / shards against one query set; 'grid_unprepared': every call bins the queries again
+    t0 = time.perf_counter()
+    prepared = metrics.prepare_query(dqry, 15.0)
+    torch.cuda.synchronize()
+    prepare_ms = (time.perf_counter() - t0) * 1e3
+    for algo in (('grid', 'grid_unprepared') if n_cov > 200_000 else ('grid', 'grid_unprepared', 'tiles')):
+        def call():
+            if algo == 'grid':
+                return metrics.covered_mask(dref, prepared, return_device=True)
+            return metrics.covered_mask(dref, dqry, algo='grid' if algo == 'grid_unprepared' else algo, return_device=True)
         for _ in range(max(warmup, 3)):
-            metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
+            call()
         ctx.barrier()
         if algo == 'grid':
             clocks.start()
@@ -710,7 +722,7 @@ def coverage_block(ctx, workload, steps, warmup, with_cpu):
             ctx.flush.fill_(s & 0xff)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _, count = metrics.covered_mask(dref, dqry, algo=algo, return_device=True)
+            _, count = call()
             if world > 1:
                 dist.all_reduce(count, op=dist.ReduceOp.SUM)           # the path's only exchange: one int64 per rank
             e1.record()
@@ -720,11 +732,15 @@ def coverage_block(ctx, workload, steps, warmup, with_cpu):
             clk = clocks.stop()
         ms = ctx.max_over_ranks(statistics.mean(event_ms(ev)))
         res[algo] = {'ms': ms, 'pairs_per_s': pairs / (ms * 1e-3), 'coverage': int(count.item()) / len(ref_all)}
-    wall = 0.0
+    # end to end: host reference rows in (this rank's shard, through reusable pinned staging), python float out, against
+    # the prepared query set; 'unprepared' = metrics.coverage(ref, qry) with both sets as pageable host arrays
+    pinned, wall = {}, 0.0
+    metrics.coverage(ref, prepared, pinned=pinned)
+    ctx.barrier()
     for s in range(steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        frac = metrics.coverage(ref, qry)                       # host rows in (pageable), python float out
+        frac = metrics.coverage(ref, prepared, pinned=pinned)
         if world > 1:
             t = torch.tensor([frac * len(ref)], dtype=torch.float64, device='cuda')
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -732,6 +748,14 @@ def coverage_block(ctx, workload, steps, warmup, with_cpu):
         wall += time.perf_counter() - t0
     ctx.barrier()
     e2e_ms = ctx.max_over_ranks(wall * 1e3 / steps)
+    wall = 0.0
+    for s in range(min(steps, 3)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        metrics.coverage(ref, qry)
+        wall += time.perf_counter() - t0
+    ctx.barrier()
+    e2e_unprepared_ms = ctx.max_over_ranks(wall * 1e3 / min(steps, 3))
     # FP32-issue roofline: 4 lane-ops per tested pair (3 FFMA + 1 compare).  The all-pairs kernel tests
     # every pair; the grid kernels test only the pairs of the 27 neighbouring cells, counted here on the host.
     lane_ops = 148 * 128 * 1.965e9
@@ -756,9 +780,11 @@ def coverage_block(ctx, workload, steps, warmup, with_cpu):
     block = {'metric': 'coverage pairs/sec', 'value': res['grid']['pairs_per_s'], 'unit': 'pairs/s', 'dtype': 'f32',
              'ms_per_step': res['grid']['ms'], 'scaling': 'strong',
              'config': {'workload': workload, 'n_ref': len(ref_all), 'n_query': len(qry), 'epsilon': 15.0,
-                        'sharding': f'reference rows split over {world} rank(s), query set replicated, all-reduce of the covered count',
+                        'sharding': f'reference rows split over {world} rank(s) as spatial tiles (contiguous slices of the grid-cell order, distributed.spatial_order), '
+                                    'query set replicated, all-reduce of the covered count',
                         'sets': 'random_poses x0.2 m cube; query = 50% uniform + 50% perturbed (5 mm / 5 deg)',
-                        'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells)',
+                        'semantics': 'metrics.coverage (kd-tree radius test)', 'algo': 'uniform grid (27 cells), query set prepared once (metrics.prepare_query)',
+                        'unprepared_ms_per_step': res['grid_unprepared']['ms'],
                         'coverage': res['grid']['coverage'], 'l2': 'flushed between steps (256 MB write)'},
              'tiles_all_pairs': res.get('tiles'),
              'roofline': {'bound': 'fp32-issue', 'kernel': roof_kernel, 'achieved': achieved_ops / 1e12,
@@ -767,8 +793,12 @@ def coverage_block(ctx, workload, steps, warmup, with_cpu):
                           'lane_ops_per_pair': ops_per_pair,
                           'note': 'FP32 lane-ops per tested pair: 4 (3 FFMA + compare) or 5 (quaternion dot + compare, cell-tile kernel); value counts nominal N*M pairs, the roofline '
                                   'counts the pairs the kernel actually tests; HBM bytes are negligible'},
-             'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes) * world,
-                     'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac, 'clock': 'host wall clock around metrics.coverage'},
+             'e2e': {'value': pairs / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(ref.nbytes) * world,
+                     'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms, 'coverage': frac,
+                     'clock': 'host wall clock around metrics.coverage(host reference rows, prepared query set)',
+                     'query_prepare_ms_once': prepare_ms,
+                     'unprepared': {'ms_per_step': e2e_unprepared_ms, 'h2d_bytes_per_step': int(ref.nbytes + qry.nbytes) * world,
+                                    'mode': 'metrics.coverage(ref, qry): both sets pageable host arrays, queries uploaded and binned per call'}},
              'gpu_launches': (10 if roof_kernel.startswith('coverage_cells') else 8) * steps, 'clocks': clk}
     if with_cpu and rank == 0 and world == 1:
         block['cpu_baseline'] = cpu_coverage_record(workload, ctx.args.cpu_coverage_n)

@@ -113,6 +113,9 @@ _SIGNATURES = {
     'bt_graph_destroy': (C.c_int, [_P]),
     'bt_set_u64': (C.c_int, [_P, C.c_uint64, _P]),
     'bt_coverage': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    'bt_coverage_prepare': (C.c_int, [_P, C.c_int64, C.c_double, C.POINTER(_P), _P]),
+    'bt_coverage_prepared': (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, _P, _P, _P]),
+    'bt_coverage_query_destroy': (C.c_int, [_P]),
     'bt_avg_gripper_point_distances': (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P]),
     'bt_mesh_pair_collide': (C.c_int, [_P, _P, _P, _P]),
     'bt_random_poses': (C.c_int, [C.c_int64, C.c_uint64, _P, _P]),

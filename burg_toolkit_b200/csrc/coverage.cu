@@ -316,7 +316,10 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
                       const int* __restrict__ n_chunks,
                       const float* __restrict__ qry, const float4* __restrict__ q_sorted, const float4* __restrict__ q_quat_sorted,
                       const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_end, Grid g,
-                      const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
+                      const float* __restrict__ lut, CovParams P, int split, uint8_t* __restrict__ covered) {
+    // split (gridDim.y) = 1: the block walks the whole 3 x 3 column neighbourhood of its chunk; 3: one x-slab of it per
+    // block; 9: one column per block.  A reference shard of a multi-GPU run has few chunks (1 M rows / 8 ranks = 488),
+    // each ~0.3 ms of work: without the split the 148 SMs get 1.6 waves of long blocks and the call does not scale.
     __shared__ float4 tile[CELL_TILE];
     __shared__ float4 tile_quat[CELL_TILE + 4];            // query orientations as unit quaternions (+ zero padding for the 4-wide loop)
     __shared__ int tile_id[CELL_TILE];
@@ -367,8 +370,13 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
         thr[r] = r2 - fmaf(x, x, fmaf(y, y, z * z));
         qmin[r] = row[r] >= 0 ? P.qdot_min : 2.0f;
     }
-    for (int ix = x0; ix <= x1; ++ix)
-        for (int iy = y0; iy <= y1; ++iy) {
+    // this block's part of the neighbourhood (a chunk lies in one column, so x0..x1 and y0..y1 hold at most 3 values)
+    int xa = x0, xb = x1, ya = y0, yb = y1;
+    if (split == 3) { xa = xb = x0 + (int)blockIdx.y; }
+    else if (split == 9) { xa = xb = x0 + (int)blockIdx.y / 3; ya = yb = y0 + (int)blockIdx.y % 3; }
+    if (xa > x1 || ya > y1) return;                         // (whole block: nothing was staged yet)
+    for (int ix = xa; ix <= xb; ++ix)
+        for (int iy = ya; iy <= yb; ++iy) {
             // contiguous range of the column's cells z0..z1 (empty cells have start == end == 0)
             int b = -1, e = 0;
             for (int iz = z0; iz <= z1; ++iz) {
@@ -563,12 +571,46 @@ static int data_bounds(const float* d_ref, int64_t n_ref, const float* d_qry, in
     return BT_OK;
 }
 
-static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64_t n_qry, const float* lut,
-                    CovParams P, float r_bound, uint8_t* d_covered, cudaStream_t st) {
-    // bounds of both sets -> grid
+// ---- the query side of the uniform-grid coverage, prepared once: grid over the QUERY set's bounds (cell >= the largest
+// distance that can pass the exact test), queries sorted by cell (float4 translations + unit quaternions) and the cell range
+// table.  A sweep -- many reference sets, or the shards of one reference set on several GPUs, against one query set --
+// bins only its reference rows per call.  Reference rows outside the query bounds fall into the clamped border cells:
+// their 27-cell neighbourhood then still holds every query within reach, and the exact test rejects the rest.
+struct bt_coverage_query {
+    int device = 0;
+    const float* d_qry = nullptr;         // the caller's rows (must outlive the handle: the exact test reads them)
+    int64_t n_qry = 0;
+    double epsilon = 0.0;
+    bt::Grid g{};
+    bool dense = false, use_cells = false;
+    int key_bits = 1;
+    float4* qs = nullptr;                 // [n_qry] sorted translations (+ original index)
+    float4* qq = nullptr;                 // [n_qry] sorted unit quaternions (cell-tile kernel)
+    int32_t *cs = nullptr, *ce = nullptr; // dense cell ranges
+    uint32_t* keys_s = nullptr;           // sorted cell keys (sparse grids: binary search)
+    cudaStream_t transient = nullptr;     // one-shot handles (bt_coverage, algo 1): stream-ordered memory, freed on this stream
+    bool is_transient = false;
+};
+
+namespace bt {
+
+static void free_query(bt_coverage_query* q) {
+    if (!q) return;
+    void* bufs[5] = {q->qs, q->qq, q->cs, q->ce, q->keys_s};
+    for (void* b : bufs) {
+        if (!b) continue;
+        if (q->is_transient) cudaFreeAsync(b, q->transient); else cudaFree(b);
+    }
+    delete q;
+}
+
+static int prepare_query(const float* d_qry, int64_t n_qry, double epsilon, float r_bound, bt_coverage_query** out, cudaStream_t st,
+                         bool transient = false) {
+    int device = 0;
+    BT_CUDA(cudaGetDevice(&device));
     float lo[3], hi[3];
     {
-        int rc = data_bounds(d_ref, n_ref, d_qry, n_qry, lo, hi, st);   // host sync: the grid shape is decided here
+        int rc = data_bounds(d_qry, n_qry, nullptr, 0, lo, hi, st);   // host sync: the grid shape is decided here
         if (rc != BT_OK) return rc;
     }
     float extent = 0.f;
@@ -578,50 +620,67 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
     // the cell index, and at most 1023 cells per axis
     float h = fmaxf(r_bound * 1.01f, extent / 1023.0f);
     if (!(h > 0.f)) h = 1.0f;
-    Grid g;
+    bt_coverage_query* q = new bt_coverage_query();
+    q->device = device; q->d_qry = d_qry; q->n_qry = n_qry; q->epsilon = epsilon;
+    q->is_transient = transient; q->transient = st;
+    if (transient) retain_pool_memory();
+    auto q_alloc = [&](void** p, size_t bytes) { return transient ? cudaMallocAsync(p, bytes ? bytes : 1, st) : cudaMalloc(p, bytes ? bytes : 1); };
+    Grid& g = q->g;
     g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
     g.inv_h = 1.0f / h;
     g.nx = (int)fminf(1024.f, floorf((hi[0] - lo[0]) / h) + 1.f);
     g.ny = (int)fminf(1024.f, floorf((hi[1] - lo[1]) / h) + 1.f);
     g.nz = (int)fminf(1024.f, floorf((hi[2] - lo[2]) / h) + 1.f);
     const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
-    const bool dense = n_cells <= (1ll << 24);
+    q->dense = n_cells <= (1ll << 24);
     // dense data (>= 16 queries per cell; measured at ~30 per cell: 0.79 -> 0.45 ms for 100k x 100k): block-per-chunk tiles;
     // sparse data: warp-per-reference walk
     static double cells_min = -1.0;                       // tuning knob (environment, read once): queries per cell from which the cell-tile kernel runs
     if (cells_min < 0.0) { const char* e = getenv("BT_COVERAGE_CELLS_MIN"); cells_min = e ? atof(e) : 16.0; }
-    const bool use_cells = dense && (double)n_qry / (double)n_cells >= cells_min;
-    int key_bits = 1;
-    while ((1ll << key_bits) < n_cells) ++key_bits;
+    q->use_cells = q->dense && (double)n_qry / (double)n_cells >= cells_min;
+    while ((1ll << q->key_bits) < n_cells) ++q->key_bits;
+#define Q_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { free_query(q); return cuda_fail(_e, #call, __FILE__, __LINE__); } } while (0)
+    Q_TRY(q_alloc((void**)&q->qs, sizeof(float4) * n_qry));
+    Q_TRY(q_alloc((void**)&q->keys_s, sizeof(uint32_t) * n_qry));
+    if (q->use_cells) Q_TRY(q_alloc((void**)&q->qq, sizeof(float4) * n_qry));
+    if (q->dense) {
+        Q_TRY(q_alloc((void**)&q->cs, sizeof(int32_t) * n_cells));
+        Q_TRY(q_alloc((void**)&q->ce, sizeof(int32_t) * n_cells));
+        Q_TRY(cudaMemsetAsync(q->cs, 0, sizeof(int32_t) * n_cells, st));
+        Q_TRY(cudaMemsetAsync(q->ce, 0, sizeof(int32_t) * n_cells, st));
+    }
+    Scratch keys, ids, ids_s, tmp;
+    Q_TRY(keys.alloc(sizeof(uint32_t) * n_qry, st));
+    Q_TRY(ids.alloc(sizeof(int32_t) * n_qry, st)); Q_TRY(ids_s.alloc(sizeof(int32_t) * n_qry, st));
+    size_t b1 = 0;
+    Q_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b1, keys.as<uint32_t>(), q->keys_s, ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, q->key_bits, st));
+    Q_TRY(tmp.alloc(b1, st));
+    cell_key_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, n_qry, g, keys.as<uint32_t>(), ids.as<int32_t>());
+    Q_TRY(cudaGetLastError());
+    Q_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, b1, keys.as<uint32_t>(), q->keys_s, ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, q->key_bits, st));
+    gather_sorted_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, ids_s.as<int32_t>(), q->keys_s, n_qry, q->qs, q->qq, q->cs, q->ce);
+    Q_TRY(cudaGetLastError());
+#undef Q_TRY
+    *out = q;
+    return BT_OK;
+}
 
-    Scratch keys, keys_s, ids, ids_s, rkeys, rkeys_s, rids, rids_s, qs, cs, ce, tmp;
-    BT_CUDA(keys.alloc(sizeof(uint32_t) * n_qry, st)); BT_CUDA(keys_s.alloc(sizeof(uint32_t) * n_qry, st));
-    BT_CUDA(ids.alloc(sizeof(int32_t) * n_qry, st));   BT_CUDA(ids_s.alloc(sizeof(int32_t) * n_qry, st));
+// the reference side, per call: bin the reference rows in the query's grid, then one of the two grid kernels
+static int run_prepared(const float* d_ref, int64_t n_ref, const bt_coverage_query* q, const float* lut, CovParams P,
+                        uint8_t* d_covered, cudaStream_t st) {
+    const Grid g = q->g;
+    const float* d_qry = q->d_qry;
+    const int64_t n_qry = q->n_qry;
+    Scratch rkeys, rkeys_s, rids, rids_s, tmp;
     BT_CUDA(rkeys.alloc(sizeof(uint32_t) * n_ref, st)); BT_CUDA(rkeys_s.alloc(sizeof(uint32_t) * n_ref, st));
     BT_CUDA(rids.alloc(sizeof(int32_t) * n_ref, st));   BT_CUDA(rids_s.alloc(sizeof(int32_t) * n_ref, st));
-    BT_CUDA(qs.alloc(sizeof(float4) * n_qry, st));
-    if (dense) {
-        BT_CUDA(cs.alloc(sizeof(int32_t) * n_cells, st));
-        BT_CUDA(ce.alloc(sizeof(int32_t) * n_cells, st));
-        BT_CUDA(cudaMemsetAsync(cs.p, 0, sizeof(int32_t) * n_cells, st));
-        BT_CUDA(cudaMemsetAsync(ce.p, 0, sizeof(int32_t) * n_cells, st));
-    }
-    size_t b1 = 0, b2 = 0;
-    BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, keys.as<uint32_t>(), keys_s.as<uint32_t>(), ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, key_bits, st));
-    BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, key_bits, st));
-    BT_CUDA(tmp.alloc(b1 > b2 ? b1 : b2, st));
-    cell_key_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, n_qry, g, keys.as<uint32_t>(), ids.as<int32_t>());
+    size_t b2 = 0;
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, q->key_bits, st));
+    BT_CUDA(tmp.alloc(b2, st));
     cell_key_kernel<<<(unsigned)ceil_div(n_ref, 256), 256, 0, st>>>(d_ref, n_ref, g, rkeys.as<uint32_t>(), rids.as<int32_t>());
     BT_LAUNCH_CHECK();
-    BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b1, keys.as<uint32_t>(), keys_s.as<uint32_t>(), ids.as<int32_t>(), ids_s.as<int32_t>(), (int)n_qry, 0, key_bits, st));
-    BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, key_bits, st));
-    Scratch qq;
-    if (use_cells) BT_CUDA(qq.alloc(sizeof(float4) * n_qry, st));
-    gather_sorted_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, ids_s.as<int32_t>(), keys_s.as<uint32_t>(), n_qry, qs.as<float4>(),
-                                                                          use_cells ? qq.as<float4>() : nullptr,
-                                                                          dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr);
-    BT_LAUNCH_CHECK();
-    if (use_cells) {
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, b2, rkeys.as<uint32_t>(), rkeys_s.as<uint32_t>(), rids.as<int32_t>(), rids_s.as<int32_t>(), (int)n_ref, 0, q->key_bits, st));
+    if (q->use_cells) {
         const int n_cols = g.nx * g.ny;
         const int64_t max_chunks = ceil_div(n_ref, CELL_REFS) + n_cols;
         Scratch col_b, col_e, chunks, n_chunks;
@@ -633,12 +692,73 @@ static int run_grid(const float* d_ref, int64_t n_ref, const float* d_qry, int64
         column_bounds_kernel<<<(unsigned)ceil_div(n_ref, 256), 256, 0, st>>>(rkeys_s.as<uint32_t>(), n_ref, (uint32_t)g.nz, col_b.as<int32_t>(), col_e.as<int32_t>());
         emit_chunks_kernel<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(col_b.as<int32_t>(), col_e.as<int32_t>(), n_cols, CELL_REFS, chunks.as<int2>(), n_chunks.as<int>());
         BT_LAUNCH_CHECK();
-        coverage_cells_kernel<<<(unsigned)max_chunks, CELL_THREADS, 0, st>>>(d_ref, rids_s.as<int32_t>(), chunks.as<int2>(), n_chunks.as<int>(), d_qry, qs.as<float4>(),
-                                                                             qq.as<float4>(), cs.as<int32_t>(), ce.as<int32_t>(), g, lut, P, d_covered);
+        // enough blocks for ~16 per SM: split the chunks' neighbourhoods when the shard is small
+        static int split_env = -1;
+        if (split_env < 0) { const char* e = getenv("BT_COVERAGE_SPLIT"); split_env = e ? atoi(e) : 0; }
+        const int64_t est_chunks = ceil_div(n_ref, CELL_REFS);
+        int split = est_chunks >= 148 * 16 ? 1 : (est_chunks * 3 >= 148 * 16 ? 3 : 9);
+        if (split_env == 1 || split_env == 3 || split_env == 9) split = split_env;
+        coverage_cells_kernel<<<dim3((unsigned)max_chunks, (unsigned)split), CELL_THREADS, 0, st>>>(d_ref, rids_s.as<int32_t>(), chunks.as<int2>(), n_chunks.as<int>(),
+                                                                                                    d_qry, q->qs, q->qq, q->cs, q->ce, g, lut, P, split, d_covered);
     } else
-        coverage_grid_kernel<<<(unsigned)ceil_div(n_ref * 32, 256), 256, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, qs.as<float4>(), keys_s.as<uint32_t>(),
-                                                                                  (int)n_qry, dense ? cs.as<int32_t>() : nullptr, dense ? ce.as<int32_t>() : nullptr,
+        coverage_grid_kernel<<<(unsigned)ceil_div(n_ref * 32, 256), 256, 0, st>>>(d_ref, rids_s.as<int32_t>(), n_ref, d_qry, q->qs, q->keys_s,
+                                                                                  (int)n_qry, q->dense ? q->cs : nullptr, q->dense ? q->ce : nullptr,
                                                                                   g, lut, P, d_covered);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+// exact-test parameters of a coverage call (the float32 compare of metrics.py:157/:219, the float64 radius of :209)
+static CovParams coverage_params(double epsilon, int mode, float* r_bound_out) {
+    CovParams P;
+    P.eps = (float)epsilon; P.weight = 1000.0f; P.mode = mode;
+    const double r = epsilon / 1000.0;
+    P.r2_kd = r * r;
+    // largest d with fl(1000*d) <= eps is eps/1000 * (1 + 2^-23); add margin
+    const float r_bound = (float)(r * (1.0 + 1e-6)) + 1e-12f;
+    P.cx = P.cy = P.cz = 0.f;
+    // deg <= eps needs angle <= eps (+ the 4-decimal rounding of the cosine, < 0.03 deg at eps >= 1): |q1.q2| >= cos((eps + 0.1 deg)/2)
+    P.qdot_min = epsilon >= 179.0 ? -1.0f : (float)(cos((epsilon + 0.1) * 0.5 * 3.14159265358979323846 / 180.0) - 2e-5);
+    P.r2_reject = r_bound * r_bound * 1.0001f;          // direct-difference form: a few ulps of rounding only
+    *r_bound_out = r_bound;
+    return P;
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+extern "C" int bt_coverage_prepare(const float* d_qry, int64_t n_qry, double epsilon, bt_coverage_query** out, void* stream) {
+    BT_REQUIRE(d_qry && out, "null pointer");
+    BT_REQUIRE(n_qry >= 1 && n_qry < (1ll << 31), "bad counts");
+    BT_REQUIRE(epsilon >= 0.0, "epsilon must be >= 0");
+    float r_bound;
+    coverage_params(epsilon, 1, &r_bound);
+    return prepare_query(d_qry, n_qry, epsilon, r_bound, out, (cudaStream_t)stream);
+}
+
+extern "C" int bt_coverage_query_destroy(bt_coverage_query* q) {
+    if (!q) return BT_OK;
+    cudaSetDevice(q->device);
+    free_query(q);
+    return BT_OK;
+}
+
+extern "C" int bt_coverage_prepared(const float* d_ref, int64_t n_ref, const bt_coverage_query* query, const float* d_lut,
+                                    int32_t mode, uint8_t* d_covered, int64_t* d_count, void* stream) {
+    BT_REQUIRE(query && d_lut && d_count, "null pointer");
+    BT_REQUIRE(n_ref >= 0 && n_ref < (1ll << 31), "bad counts");
+    BT_REQUIRE((d_ref && d_covered) || n_ref == 0, "null reference set");
+    BT_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (brute force semantics) or 1 (kd-tree semantics)");
+    cudaStream_t st = (cudaStream_t)stream;
+    BT_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    if (n_ref == 0) return BT_OK;
+    BT_CUDA(cudaMemsetAsync(d_covered, 0, (size_t)n_ref, st));
+    float r_bound;
+    const CovParams P = coverage_params(query->epsilon, mode, &r_bound);
+    int rc = run_prepared(d_ref, n_ref, query, d_lut, P, d_covered, st);
+    if (rc != BT_OK) return rc;
+    count_covered_kernel<<<148, 256, 0, st>>>(d_covered, n_ref, reinterpret_cast<unsigned long long*>(d_count));
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
@@ -657,18 +777,14 @@ extern "C" int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry
     if (n_ref == 0) return BT_OK;
     BT_CUDA(cudaMemsetAsync(d_covered, 0, (size_t)n_ref, st));
     if (n_qry == 0 || !(epsilon >= 0.0)) return BT_OK;
-    CovParams P;
-    P.eps = (float)epsilon; P.weight = 1000.0f; P.mode = mode;      // the float32 compare of metrics.py:157/:219
-    const double r = epsilon / 1000.0;                              // the float64 radius of metrics.py:209
-    P.r2_kd = r * r;
-    // largest d with fl(1000*d) <= eps is eps/1000 * (1 + 2^-23); add margin
-    const float r_bound = (float)(r * (1.0 + 1e-6)) + 1e-12f;
-    P.cx = P.cy = P.cz = 0.f;
-    // deg <= eps needs angle <= eps (+ the 4-decimal rounding of the cosine, < 0.03 deg at eps >= 1): |q1.q2| >= cos((eps + 0.1 deg)/2)
-    P.qdot_min = epsilon >= 179.0 ? -1.0f : (float)(cos((epsilon + 0.1) * 0.5 * 3.14159265358979323846 / 180.0) - 2e-5);
+    float r_bound;
+    CovParams P = coverage_params(epsilon, mode, &r_bound);
     if (algo == 1) {
-        P.r2_reject = r_bound * r_bound * 1.0001f;          // direct-difference form: a few ulps of rounding only
-        int rc = run_grid(d_ref, n_ref, d_qry, n_qry, d_lut, P, r_bound, d_covered, st);
+        bt_coverage_query* q = nullptr;
+        int rc = prepare_query(d_qry, n_qry, epsilon, r_bound, &q, st, /*transient=*/true);
+        if (rc != BT_OK) return rc;
+        rc = run_prepared(d_ref, n_ref, q, d_lut, P, d_covered, st);
+        free_query(q);                                      // stream-ordered: behind the kernels that read the buffers
         if (rc != BT_OK) return rc;
     } else {
         // centre on the first query row and bound the rounding of the expanded form by the data's spread; both are

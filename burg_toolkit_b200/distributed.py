@@ -33,6 +33,19 @@ def _dist():
     return dist
 
 
+def spatial_order(rows, epsilon=15.0):
+    """permutation that sorts grasp rows by the cell of the coverage grid (cell = 1.01 * epsilon / 1000, x-major) their
+    translation falls into.  Coverage shards should be SPATIAL tiles: contiguous slices of this order give every rank a
+    compact block of cells (and each rank's grid kernel the same cell-dense blocks of reference rows as a single GPU has);
+    contiguous slices of an arbitrary row order spread every rank's rows thinly over the whole grid, which makes the
+    per-rank work shrink much more slowly than 1 / world.  Masks and counts do not depend on the row order."""
+    t = np.asarray(rows, dtype=np.float32).reshape(-1, 14)[:, 0:3].astype(np.float64)
+    cell = 1.01 * float(epsilon) / 1000.0
+    c = np.floor((t - t.min(axis=0)) / cell).astype(np.int64)
+    dims = c.max(axis=0) + 1
+    return np.argsort((c[:, 0] * dims[1] + c[:, 1]) * dims[2] + c[:, 2], kind='stable')
+
+
 def gather_rows(local_rows, dst=0, group=None):
     """Variable-length gather of per-rank [n_r, ...] tensors to ``dst`` in rank order (-> concatenated tensor on
     ``dst``, None elsewhere).  Counts travel first (all_gather of one int64), then padded payloads."""

@@ -126,16 +126,74 @@ def avg_gripper_point_distances(graspset1, graspset2, gripper_points=None, consi
         return out.cpu().numpy()
 
 
+class PreparedQuery:
+    """A query grasp set resident on the device and binned for the uniform-grid coverage at one ``epsilon``
+    (``bt_coverage_prepare``): pass it wherever a query grasp set is expected.  For sweeps -- many reference sets, or the
+    shards of one reference set on several GPUs, against one query set -- only the reference rows are uploaded and binned
+    per call."""
+
+    def __init__(self, query_grasp_set, epsilon=15.0, device=None):
+        import ctypes as C
+        import weakref
+        torch = nat.require_cuda()
+        rows = _rows(query_grasp_set)
+        self.device = _device_of(rows) if device is None else dev.device_index(device)
+        self.epsilon = float(epsilon)
+        with torch.cuda.device(self.device):
+            self.rows = _to_device(rows, self.device)           # kept alive: the exact test reads the rows
+            handle = C.c_void_p()
+            nat.call('bt_coverage_prepare', nat.ptr(self.rows), self.rows.shape[0], self.epsilon, C.byref(handle), nat.current_stream())
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, dev._destroy, 'bt_coverage_query_destroy', handle)
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+
+def prepare_query(query_grasp_set, epsilon=15.0, device=None):
+    """-> ``PreparedQuery`` (see there)"""
+    return PreparedQuery(query_grasp_set, epsilon, device)
+
+
 def covered_mask(reference_grasp_set, query_grasp_set, epsilon=15.0, kd_semantics=True, algo='auto',
-                 return_device=False):
+                 return_device=False, pinned=None):
     """bool[N]: which reference grasps have a query grasp within ``epsilon`` (B200 extension; the
     reference only returns the fraction).
 
     kd_semantics=True  follows ``metrics.coverage`` (candidates restricted by the float64 radius test of
                        cKDTree.query_ball_tree, metrics.py:203-220),
     kd_semantics=False follows ``metrics.coverage_brute_force`` (metrics.py:157).
-    algo: 'tiles' (all pairs), 'grid' (uniform-grid culled) or 'auto'."""
+    algo: 'tiles' (all pairs), 'grid' (uniform-grid culled) or 'auto'.
+    ``query_grasp_set`` may be a ``PreparedQuery`` (resident + binned once, for sweeps); ``pinned``: optional dict of
+    reusable pinned staging for host reference rows in that case."""
     torch = nat.require_cuda()
+    if isinstance(query_grasp_set, PreparedQuery):
+        pq = query_grasp_set
+        if float(epsilon) != pq.epsilon:
+            raise ValueError(f'the query set was prepared for epsilon {pq.epsilon}, not {epsilon}')
+        if algo == 'tiles':
+            raise ValueError("a prepared query set is a grid: algo must be 'grid' or 'auto'")
+        a = _rows(reference_grasp_set)
+        with torch.cuda.device(pq.device):
+            if isinstance(a, np.ndarray) and pinned is not None:
+                # reusable pinned staging of the reference rows: one asynchronous H2D instead of a pageable copy
+                if pinned.get('ref') is None or pinned['ref'].shape[0] < len(a):
+                    pinned['ref'] = torch.empty((len(a), 14), dtype=torch.float32).pin_memory()
+                    pinned['dref'] = torch.empty((len(a), 14), dtype=torch.float32, device=f'cuda:{pq.device}')
+                pinned['ref'][:len(a)].numpy()[...] = a
+                da = pinned['dref'][:len(a)]
+                da.copy_(pinned['ref'][:len(a)], non_blocking=True)
+            else:
+                da = _to_device(a, pq.device)
+            n = da.shape[0]
+            deg, _ = dev.acos_luts(pq.device)
+            covered = torch.empty(((n + 3) // 4) * 4, dtype=torch.uint8, device=da.device)
+            count = torch.empty(1, dtype=torch.int64, device=da.device)
+            nat.call('bt_coverage_prepared', nat.ptr(da), n, pq.handle, nat.ptr(deg), 1 if kd_semantics else 0, nat.ptr(covered),
+                     nat.ptr(count), nat.current_stream())
+            if return_device:
+                return covered[:n], count
+            return covered[:n].cpu().numpy().astype(bool)
     a, b = _rows(reference_grasp_set), _rows(query_grasp_set)
     device = _device_of(a, b)
     with torch.cuda.device(device):
@@ -164,12 +222,12 @@ def coverage_brute_force(reference_grasp_set, query_grasp_set, epsilon=15.0):
     return int(count.item()) / n
 
 
-def coverage(reference_grasp_set, query_grasp_set, epsilon=15.0, print_timings=False):
+def coverage(reference_grasp_set, query_grasp_set, epsilon=15.0, print_timings=False, pinned=None):
     """Fraction of reference grasps covered by the query set, kd-tree semantics
     (reference metrics.py:161-229)."""
     t1 = timer()
     n = len(_rows(reference_grasp_set))
-    _, count = covered_mask(reference_grasp_set, query_grasp_set, epsilon, kd_semantics=True, return_device=True)
+    _, count = covered_mask(reference_grasp_set, query_grasp_set, epsilon, kd_semantics=True, return_device=True, pinned=pinned)
     covered = int(count.item())
     if print_timings:
         print('it took:')

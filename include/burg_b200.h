@@ -330,6 +330,16 @@ BT_API int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry, in
                 const float* d_acos_deg_lut, int32_t mode, int32_t algo, uint8_t* d_covered,
                 int64_t* d_count, void* stream);
 
+/* The query side of the uniform-grid coverage, prepared once and reused: a sweep (many reference sets, or the shards of one
+ * reference set on several GPUs, against ONE query set -- BASELINE config 5) bins only its reference rows per call.
+ * bt_coverage_prepare: grid over the query set's bounds for `epsilon`, queries sorted by cell (synchronises; d_qry must
+ * outlive the handle).  bt_coverage_prepared: bt_coverage(algo = 1) against the prepared set, same masks. */
+typedef struct bt_coverage_query bt_coverage_query;
+BT_API int bt_coverage_prepare(const float* d_qry, int64_t n_qry, double epsilon, bt_coverage_query** out, void* stream);
+BT_API int bt_coverage_prepared(const float* d_ref, int64_t n_ref, const bt_coverage_query* query, const float* d_acos_deg_lut,
+                                int32_t mode, uint8_t* d_covered, int64_t* d_count, void* stream);
+BT_API int bt_coverage_query_destroy(bt_coverage_query* query);
+
 /* pairwise distance matrices (metrics.py:9-77), [n1,n2] f32 out; which: 0 euclidean, 1 angular [rad lut
  * supplied by caller as d_lut], 2 combined (lut = degrees) */
 BT_API int bt_pairwise_distances(const float* d_gs1, int64_t n1, const float* d_gs2, int64_t n2, int32_t which,

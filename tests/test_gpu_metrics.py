@@ -158,3 +158,29 @@ def test_full_size_properties(metrics):
     idx = np.random.default_rng(0).choice(n, 300, replace=False)
     assert np.array_equal(grid[idx], port.covered_kd(ref[idx], qry))           # spot check against the oracle
     assert 0.2 < grid.mean() < 0.8
+
+
+def test_prepared_query_gives_the_same_masks():
+    """metrics.prepare_query (query set resident + binned once, reference rows binned per call) against the one-shot grid
+    call and the all-pairs kernel: dense and sparse grids, both semantics, reference rows outside the query set's bounds,
+    shards of the reference set, pinned staging"""
+    from burg_toolkit_b200 import metrics
+    from burg_toolkit_b200.synthetic import coverage_sets
+    for n, cube in ((6000, 0.05), (3000, 2.0)):                      # ~30 queries per cell (cell-tile kernel) / sparse (grid walk)
+        ref, qry = coverage_sets(n, cube)
+        ref = ref.copy()
+        ref[:40, 0:3] += np.float32(1.5 * cube)                       # far outside the query bounds
+        ref[40:80, 0:3] -= np.float32(0.004)                          # just outside / at the border
+        pq = metrics.prepare_query(qry, 15.0)
+        for kd in (True, False):
+            want = metrics.covered_mask(ref, qry, kd_semantics=kd, algo='tiles')
+            assert np.array_equal(metrics.covered_mask(ref, qry, kd_semantics=kd, algo='grid'), want)
+            assert np.array_equal(metrics.covered_mask(ref, pq, kd_semantics=kd), want)
+            pinned = {}
+            got = np.concatenate([metrics.covered_mask(ref[b:e], pq, kd_semantics=kd, pinned=pinned) for b, e in ((0, 1000), (1000, 1001), (1001, len(ref)))])
+            assert np.array_equal(got, want)
+        assert want.sum() > 10 and not want[:40].any()
+        assert metrics.coverage(ref, pq) == metrics.coverage(ref, qry)
+    with pytest.raises(ValueError):
+        metrics.covered_mask(ref, pq, epsilon=10.0)
+
