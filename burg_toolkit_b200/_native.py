@@ -47,7 +47,7 @@ class PipelineConfig(C.Structure):
                 ('halfspace', C.c_int32), ('check_collisions', C.c_int32), ('use_width', C.c_int32),
                 ('compact', C.c_int32), ('tail_splits', C.c_int32), ('cone_culling', C.c_int32), ('reserved', C.c_int32),
                 ('collision_width_tolerance', C.c_double),
-                ('orient_cos', C.c_double * 64), ('orient_sin', C.c_double * 64)]
+                ('orient_cos', C.c_double * 64), ('orient_sin', C.c_double * 64), ('surface_total', C.c_int64)]
 
 
 class PipelineBuffers(C.Structure):
@@ -112,6 +112,7 @@ _SIGNATURES = {
     'bt_graph_info': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.c_int64]),
     'bt_graph_destroy': (C.c_int, [_P]),
     'bt_set_u64': (C.c_int, [_P, C.c_uint64, _P]),
+    'bt_set_u64x3': (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     'bt_coverage': (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     'bt_coverage_prepare': (C.c_int, [_P, C.c_int64, C.c_double, C.POINTER(_P), _P]),
     'bt_coverage_prepared': (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, _P, _P, _P]),

@@ -656,19 +656,52 @@ __global__ void unit_vectors_kernel(int64_t n, uint64_t seed, double* __restrict
 // threads generate the GEN_REFS x n_rays cone rays from the normals in shared memory.  Same Philox keys as the three
 // stand-alone kernels, so the values are the same bits.  `seed_add` (nullable): a device-resident offset added to the
 // seed -- lets a captured CUDA graph of the pipeline be replayed with a new seed (see bt_graph_*).
+// A keyed pseudo-random PERMUTATION of [0, n): balanced Feistel network on the smallest even number of bits that holds
+// n - 1, cycle-walked back into the domain.  sample() uses it as the reference's np.random.shuffle of the surface samples
+// (sampling.py:201) without materialising them: reference point j of a call is surface sample perm(j).
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t x, uint64_t n, uint64_t key) {
+    int half = 1;
+    while ((1ull << (2 * half)) < n) ++half;
+    const uint64_t mask = (1ull << half) - 1;
+    do {
+        uint64_t l = x >> half, r = x & mask;
+#pragma unroll 1
+        for (int round = 0; round < 6; ++round) {
+            uint32_t o[4];
+            philox4x32(key, r, 0x5045524dull + ((uint64_t)round << 32), o);
+            const uint64_t f = (((uint64_t)o[0] << 32) | o[1]) & mask;
+            const uint64_t nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        x = (l << half) | r;
+    } while (x >= n);
+    return x;
+}
+
 constexpr int GEN_REFS = 8;
+// `dyn` (nullable, device): [0] added to the seed, [1] position of this batch in the shuffled sample list, [2] key of the
+// shuffle and of the surface samples -- what changes from call to call when the pipeline is replayed as a CUDA graph.
+// surface_total > 0: the batch's reference points are samples perm(dyn[1] + i mod surface_total) of a set of surface_total
+// area-weighted samples (S1 of a whole sample() call, never materialised); else plain samples 0 .. n_ref - 1.
 __global__ void __launch_bounds__(256)
 generate_kernel(const double* __restrict__ cdf, const int32_t* __restrict__ faces, const double* __restrict__ verts, int64_t nF,
-                int64_t n_ref, int n_rays, double angle, uint64_t seed, const uint64_t* __restrict__ seed_add, int do_sample, int do_dirs,
+                int64_t n_ref, int n_rays, double angle, uint64_t seed, const uint64_t* __restrict__ dyn, int64_t surface_total, int do_sample, int do_dirs,
                 int do_frame, double* __restrict__ pts, double* __restrict__ nrm, double* __restrict__ frame, double* __restrict__ dirs) {
     __shared__ double s_n[GEN_REFS][3];
-    if (seed_add) seed += *seed_add;
+    if (dyn) seed += dyn[0];
     const int64_t ref0 = blockIdx.x * (int64_t)GEN_REFS;
     const int t = threadIdx.x;
     if (t < GEN_REFS && ref0 + t < n_ref) {
         const int64_t i = ref0 + t;
         d3 nv;
-        if (do_sample) {
+        if (do_sample && surface_total > 0 && dyn) {
+            d3 p;
+            const uint64_t slot = feistel_perm((dyn[1] + (uint64_t)i) % (uint64_t)surface_total, (uint64_t)surface_total, dyn[2]);
+            surface_sample(cdf, faces, verts, nF, surface_total, (int64_t)slot, dyn[2], p, nv);
+            st3(pts + 3 * i, p);
+            st3(nrm + 3 * i, nv);
+        } else if (do_sample) {
             d3 p;
             surface_sample(cdf, faces, verts, nF, n_ref, i, seed, p, nv);
             st3(pts + 3 * i, p);
@@ -1149,13 +1182,14 @@ int bt::expand_impl(const double* d_ref_pts, const int64_t* d_pair_offset, const
 
 // S1 + S2 + frame vectors in one launch (any subset; see generate_kernel).  d_seed_add: nullable device-resident seed offset.
 int bt::generate_impl(const bt_mesh* mesh, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed, const uint64_t* d_seed_add,
-                      int do_sample, int do_dirs, int do_frame, double* d_pts, double* d_nrm, double* d_frame, double* d_dirs, void* stream) {
+                      int64_t surface_total, int do_sample, int do_dirs, int do_frame, double* d_pts, double* d_nrm, double* d_frame,
+                      double* d_dirs, void* stream) {
     BT_REQUIRE(mesh && d_nrm, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
     BT_REQUIRE((!do_sample || d_pts) && (!do_dirs || d_dirs) && (!do_frame || d_frame), "missing output buffer");
     if (n_ref == 0 || !(do_sample || do_dirs || do_frame)) return BT_OK;
     generate_kernel<<<(unsigned)ceil_div(n_ref, GEN_REFS), 256, 0, (cudaStream_t)stream>>>(
-        mesh->m.area_cdf, mesh->m.faces, mesh->m.verts, mesh->m.nF, n_ref, n_rays, angle, seed, d_seed_add, do_sample, do_dirs, do_frame,
+        mesh->m.area_cdf, mesh->m.faces, mesh->m.verts, mesh->m.nF, n_ref, n_rays, angle, seed, d_seed_add, surface_total, do_sample, do_dirs, do_frame,
         d_pts, d_nrm, d_frame, d_dirs);
     BT_LAUNCH_CHECK();
     return BT_OK;

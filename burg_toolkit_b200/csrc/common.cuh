@@ -247,7 +247,8 @@ int ags_select_fused_impl(const int32_t* d_hit_count, const bt_hit* d_hits, cons
                           int32_t max_targets, uint64_t seed, const uint64_t* d_seed_add, int32_t* d_pair_count, int64_t* d_pair_offset,
                           int32_t* d_pair_ref, double* d_pair_q, int64_t cap_pairs, void* stream);
 int generate_impl(const bt_mesh* mesh, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed, const uint64_t* d_seed_add,
-                  int do_sample, int do_dirs, int do_frame, double* d_pts, double* d_nrm, double* d_frame, double* d_dirs, void* stream);
+                  int64_t surface_total, int do_sample, int do_dirs, int do_frame, double* d_pts, double* d_nrm, double* d_frame,
+                  double* d_dirs, void* stream);
 int expand_impl(const double* d_ref_pts, const int64_t* d_pair_offset, const int32_t* d_pair_ref, const double* d_pair_q,
                 const double* d_frame_vecs, int64_t n_ref, int64_t cap_pairs, int32_t n_o, int32_t halfspace, const double* h_cos,
                 const double* h_sin, float* d_gs, double* d_contacts, int64_t* d_n_rows, void* stream);

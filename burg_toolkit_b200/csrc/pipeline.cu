@@ -116,6 +116,7 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     BT_REQUIRE(b->cap_pairs >= n_ref * (int64_t)cfg->max_targets, "cap_pairs too small");
     BT_REQUIRE(!cfg->check_collisions || (scene && gripper && b->colliding), "collision stage needs scene, gripper and mask buffer");
     BT_REQUIRE(!cfg->compact || (cfg->check_collisions && b->free_gs && b->n_free), "compaction needs the collision stage and its buffers");
+    BT_REQUIRE(cfg->surface_total == 0 || (cfg->surface_total > 0 && b->seed_add && b->sample_surface), "surface_total needs sample_surface and the device-side parameters (seed_add)");
     cudaStream_t st = (cudaStream_t)stream;
     BT_CUDA(cudaSetDevice(target->m.device));
     BT_REQUIRE((reinterpret_cast<uintptr_t>(b->scratch) & 255) == 0, "scratch must be 256-byte aligned");
@@ -127,7 +128,7 @@ extern "C" int bt_ags_pipeline(const bt_mesh* target, const bt_mesh* scene, cons
     const int gen_frame = (b->generate_frame_vecs && !cfg->halfspace) ? 1 : 0;
     if (b->sample_surface || b->generate_dirs || gen_frame) {
         STAGE_BEGIN(0);
-        STAGE_CALL(generate_impl(target, n_ref, cfg->n_rays, cfg->ags.angle_max, seed, b->seed_add, b->sample_surface, b->generate_dirs,
+        STAGE_CALL(generate_impl(target, n_ref, cfg->n_rays, cfg->ags.angle_max, seed, b->seed_add, cfg->surface_total, b->sample_surface, b->generate_dirs,
                                  gen_frame, b->ref_pts, b->ref_nrm, b->frame_vecs, b->dirs, stream));
         STAGE_END(0);
     }
@@ -204,6 +205,14 @@ struct bt_graph {
 
 namespace bt {
 __global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
+__global__ void set_u64x3_kernel(uint64_t* p, uint64_t a, uint64_t b, uint64_t c) { p[0] = a; p[1] = b; p[2] = c; }
+}
+
+extern "C" int bt_set_u64x3(uint64_t* d_ptr, uint64_t v0, uint64_t v1, uint64_t v2, void* stream) {
+    BT_REQUIRE(d_ptr, "null pointer");
+    bt::set_u64x3_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_ptr, v0, v1, v2);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
 }
 
 extern "C" int bt_set_u64(uint64_t* d_ptr, uint64_t value, void* stream) {

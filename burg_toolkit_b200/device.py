@@ -292,7 +292,7 @@ class PipelineWorkspace:
         self.free_contacts = torch.zeros((rows, 2, 3), dtype=f64, device=d) if compact else None
         self.n_free = torch.zeros((1,), dtype=i64, device=d) if compact else None
         self.rows = rows
-        self.seed_add = torch.zeros((1,), dtype=i64, device=d)      # device-resident seed offset (graph replays: bt_set_u64)
+        self.seed_add = torch.zeros((4,), dtype=i64, device=d)      # device-resident call parameters (graph replays): seed offset, shuffle position, shuffle key
         # scratch arena of bt_ags_pipeline (candidate lists, scan states, collision queues): no allocations inside the call
         arena = 80 * max(n_ref, 1) * n_rays + (200 * rows if collisions else 0) + (1 << 20)
         self.scratch = torch.empty((min(arena, 3 << 30),), dtype=u8, device=d)

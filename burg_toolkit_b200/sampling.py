@@ -302,7 +302,7 @@ class AntipodalGraspSampler:
     def run_pipeline(self, ref_points=None, ref_normals=None, n_ref=None, seed=1, directions=None, frame_vecs=None,
                      check_collisions=True, collision_width_tolerance=0.01, use_width=True, additional_objects=None,
                      exclude_shape=False, compact=True, timer=None, destinations=None, slot=0, tail_splits=1, keep_hits=False,
-                     graph=False):
+                     graph=False, surface=None):
         """The whole device pipeline for one batch of candidates in ONE C-ABI call (``bt_ags_pipeline``); nothing
         leaves the GPU and the host never waits:
 
@@ -330,6 +330,9 @@ class AntipodalGraspSampler:
         ``graph``: replay the call as a captured CUDA graph (``bt_graph_*``): the first call with a given shape, mesh and
         configuration captures it, later ones cost one graph launch instead of ~25 driver calls (the seed reaches the
         kernels through device memory); same results, bit for bit.  Ignored with a ``timer`` or a ``compact_after`` event.
+        ``surface`` = (total, offset, key), with ``ref_points=None``: the batch's reference points are entries ``offset ..
+        offset + n_ref - 1`` (mod total) of a keyed pseudo-random ordering of ONE set of ``total`` area-weighted surface
+        samples -- stage S1 plus the shuffle of a whole ``sample()`` call (sampling.py:199-201), generated on the fly.
         -> dict of CUDA tensors (views into the cached workspace: valid until the next call)."""
         torch = nat.require_cuda()
         device = self._device()
@@ -356,7 +359,10 @@ class AntipodalGraspSampler:
                         raise ValueError(f'expected {n_ref} x {per_ref} values, got {src.numel()}')
                     if n_ref:                          # (the workspace buffers hold at least one row)
                         buf.reshape(-1)[:n_ref * per_ref].copy_(src.reshape(-1), non_blocking=True)
-            sig = (float(self.mu), float(self.gripper.opening_width) if self.gripper is not None else None, float(self.width_tolerance),
+            if surface is not None and ref_points is not None:
+                raise ValueError('surface=(total, offset, key) generates the reference points: ref_points must be None')
+            surface_total = 0 if surface is None else int(surface[0])
+            sig = (surface_total, float(self.mu), float(self.gripper.opening_width) if self.gripper is not None else None, float(self.width_tolerance),
                    float(self.min_grasp_width), self.no_contact_below_z, cap, int(self.n_rays), n_o, k, bool(self.only_grasp_from_above),
                    bool(check_collisions), bool(use_width), bool(compact), float(collision_width_tolerance), int(tail_splits), bool(self.cone_culling))
             cached = getattr(ws, 'config_cache', None)
@@ -372,6 +378,7 @@ class AntipodalGraspSampler:
                 cfg.collision_width_tolerance = float(collision_width_tolerance)
                 cfg.tail_splits = int(tail_splits)
                 cfg.cone_culling = int(bool(self.cone_culling))
+                cfg.surface_total = surface_total
                 cos_t, sin_t = _orientation_tables(n_o, cfg.halfspace)
                 cfg.orient_cos[:n_o] = cos_t.tolist()
                 cfg.orient_sin[:n_o] = sin_t.tolist()
@@ -405,11 +412,18 @@ class AntipodalGraspSampler:
                         handle = C.c_void_p()
                         nat.call('bt_graph_end_capture', cap.cuda_stream, C.byref(handle))
                     g = ws.graphs[gkey] = dev.DeviceGraph(handle, keep=(dm, scene, gripper, ws))
-                nat.call('bt_set_u64', ws.seed_add.data_ptr(), (seed - base) & 0xFFFFFFFFFFFFFFFF, stream)
+                if surface is None:
+                    nat.call('bt_set_u64', ws.seed_add.data_ptr(), (seed - base) & 0xFFFFFFFFFFFFFFFF, stream)
+                else:
+                    nat.call('bt_set_u64x3', ws.seed_add.data_ptr(), (seed - base) & 0xFFFFFFFFFFFFFFFF, int(surface[1]) & 0xFFFFFFFFFFFFFFFF,
+                             int(surface[2]) & 0xFFFFFFFFFFFFFFFF, stream)
                 g.launch(stream)
                 ws.last_graph, ws.seed_add_dirty = g, True
             else:
-                if getattr(ws, 'seed_add_dirty', False):               # a graph replay left its offset there
+                if surface is not None:
+                    nat.call('bt_set_u64x3', ws.seed_add.data_ptr(), 0, int(surface[1]) & 0xFFFFFFFFFFFFFFFF, int(surface[2]) & 0xFFFFFFFFFFFFFFFF, stream)
+                    ws.seed_add_dirty = False
+                elif getattr(ws, 'seed_add_dirty', False):             # a graph replay left its offset there
                     ws.seed_add.zero_()
                     ws.seed_add_dirty = False
                 bufs = ws.buffers(*gen)
@@ -620,6 +634,8 @@ class AntipodalGraspSampler:
         if self.verbose:
             print('preparing to sample grasps...')
         torch = nat.require_cuda()
+        if not self.reference_rng and self.surface_samples is None and self.no_contact_below_z is None and not self.poisson_disk:
+            return self._sample_on_device(n)
         ref = self._ref_points(n)
         if self.verbose:
             print(f'sampled {len(ref)} first contact point candidates, beginning to find grasps.')
@@ -664,6 +680,65 @@ class AntipodalGraspSampler:
             print(f'warning: only {total} grasps found after {self.max_passes} passes over the reference points')
         gs = GraspSet.from_array(np.concatenate(rows) if rows else np.zeros((0, 14), dtype=np.float32))
         return gs, (np.concatenate(contacts) if contacts else np.empty((0, 2, 3)))
+
+    def _sample_on_device(self, n):
+        """``sample(n)`` without materialising the first-contact candidates: batch b of reference points is a slice of a
+        keyed pseudo-random ordering of the ``max(n, 1000, #triangles)`` surface samples (S1 + shuffle, sampling.py:199-201),
+        generated inside the graph-replayed pipeline; per batch ONE wait for the device -- pair counts, rows and contacts come
+        back in three asynchronous copies into pinned memory and are cut on the host at the first reference point where
+        >= n grasps exist (the reference's stopping rule)."""
+        torch = nat.require_cuda()
+        device = self._device()
+        m = as_mesh(self.mesh)
+        n_sample = int(np.max([n, 1000, len(m.triangles)]))
+        n_o, k = int(self.n_orientations), int(self.max_targets_per_ref_point)
+        key = int(np.random.randint(1, 2 ** 62))
+        seed = int(np.random.randint(1, 2 ** 62))
+        if self.verbose:
+            print(f'sampled {n_sample} first contact point candidates, beginning to find grasps.')
+        rows, contacts, total = [], [], 0
+        consumed, n_refs_used, overflowed = 0, 0, 0
+        batch = -(-max(64, int(np.ceil(n / (n_o * 0.8))) + 16) // 64) * 64            # (multiples of 64: few distinct workspace shapes)
+        stage = self.__dict__.setdefault('_sample_pinned', {})
+        with torch.cuda.device(device):
+            while total < n and consumed < self.max_passes * n_sample:
+                cap_rows = batch * k * n_o
+                if stage.get('cap', 0) < cap_rows or stage.get('batch', 0) < batch:
+                    stage.update(cap=cap_rows, batch=batch, gs=torch.empty((cap_rows, 14), dtype=torch.float32).pin_memory(),
+                                 contacts=torch.empty((cap_rows, 2, 3), dtype=torch.float64).pin_memory(),
+                                 counts=torch.empty((batch + 1,), dtype=torch.int32).pin_memory())
+                while True:
+                    out = self.run_pipeline(n_ref=batch, seed=seed + consumed, check_collisions=False, graph=True,
+                                            surface=(n_sample, consumed % n_sample, key), slot=('sample', batch))
+                    stage['counts'][:batch].copy_(out['pair_count'][:batch], non_blocking=True)
+                    stage['counts'][batch:batch + 1].copy_(out['overflow'], non_blocking=True)
+                    stage['gs'][:cap_rows].copy_(out['gs'][:cap_rows], non_blocking=True)
+                    stage['contacts'][:cap_rows].copy_(out['contacts'][:cap_rows], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()               # the one wait of this batch
+                    n_over = int(stage['counts'][batch])
+                    if not n_over or self.max_hits_per_ray >= 32:
+                        break
+                    self.max_hits_per_ray = min(32, 2 * int(self.max_hits_per_ray))      # the reference has no cap on crossings per ray
+                overflowed += n_over
+                cum = np.cumsum(stage['counts'][:batch].numpy().astype(np.int64) * n_o)
+                reached = np.nonzero(cum >= n - total)[0]
+                take_refs = int(reached[0]) + 1 if len(reached) else batch
+                take_rows = int(cum[take_refs - 1])
+                rows.append(stage['gs'][:take_rows].numpy().copy())
+                contacts.append(stage['contacts'][:take_rows].numpy().copy())
+                total += take_rows
+                n_refs_used += take_refs
+                consumed += take_refs
+                batch = -(-min(1 << 16, max(64, int((n - total) / max(total / max(n_refs_used, 1), 1e-3)) + 16)) // 64) * 64
+        self.last_stats = dict(ref_points_used=n_refs_used, candidates=n_refs_used * self.n_rays, grasps=total,
+                               exhausted=total < n, hit_list_overflows=overflowed)
+        if overflowed:
+            import warnings
+            warnings.warn(f'{overflowed} rays cross more than 32 surfaces of the mesh: their farthest crossings were not considered')
+        if total < n and self.verbose:
+            print(f'warning: only {total} grasps found after {self.max_passes} passes over the reference points')
+        gs = GraspSet.from_array(np.concatenate(rows) if len(rows) != 1 else rows[0]) if rows else GraspSet.from_array(np.zeros((0, 14), dtype=np.float32))
+        return gs, (np.concatenate(contacts) if len(contacts) != 1 else contacts[0]) if contacts else np.empty((0, 2, 3))
 
     def _sample_sequential(self, n, ref_points):
         """the reference's loop verbatim in structure (sampling.py:215-352), one launch per reference point,

@@ -261,6 +261,11 @@ typedef struct bt_pipeline_config {
     int32_t reserved;
     double  collision_width_tolerance;
     double  orient_cos[64], orient_sin[64];   /* numpy-evaluated cos/sin of the orientation angles */
+    int64_t surface_total;   /* > 0 (with buffers->sample_surface and ->seed_add): the batch's reference points are taken from ONE set
+                                of surface_total area-weighted surface samples in a keyed pseudo-random order -- reference point i is
+                                sample perm(seed_add[1] + i mod surface_total), the samples keyed by seed_add[2] -- i.e. stage S1 and the
+                                np.random.shuffle of a whole sample() call (sampling.py:199-201) without materialising the set.
+                                0: the batch draws its own n_ref samples keyed by `seed`                                          */
 } bt_pipeline_config;
 
 typedef struct bt_pipeline_buffers {
@@ -292,8 +297,9 @@ typedef struct bt_pipeline_buffers {
     double*  hit_t;          /* [max_hits_per_ray, n_ref*n_rays] slot-major ray parameters (lean mode only)   */
     void*    compact_after;  /* nullable cudaEvent_t: the compaction stage waits for it (the previous batch's
                                 compaction on another stream, whose count is free_base)                       */
-    const uint64_t* seed_add; /* nullable [1] on the device: added to `seed` by every kernel that draws random numbers
-                                (a captured graph of the call is replayed with a new seed by storing it here: bt_set_u64) */
+    const uint64_t* seed_add; /* nullable [4] on the device, what changes between replays of a captured call: [0] added to `seed` by
+                                every kernel that draws random numbers, [1] / [2] position in and key of the shuffled surface
+                                samples (config->surface_total), [3] spare.  Set with bt_set_u64 / bt_set_u64x3.           */
     void*    scratch;        /* nullable, 256-byte aligned device memory the call may use for its intermediates (candidate
                                 lists, scan states, collision queues) instead of stream-ordered allocations; what does not
                                 fit is allocated as before.  ~80 B per ray + 200 B per posed grasp holds everything.     */
@@ -316,6 +322,7 @@ BT_API int bt_graph_launch(bt_graph* graph, void* stream);
 BT_API int bt_graph_info(const bt_graph* graph, int32_t* n_nodes, int32_t* n_kernel_nodes, char* names, int64_t names_cap);
 BT_API int bt_graph_destroy(bt_graph* graph);
 BT_API int bt_set_u64(uint64_t* d_ptr, uint64_t value, void* stream);
+BT_API int bt_set_u64x3(uint64_t* d_ptr, uint64_t v0, uint64_t v1, uint64_t v2, void* stream);
 
 /* ---- M1..M5: coverage (replaces metrics.coverage / coverage_brute_force, metrics.py:141-229, and the
  * distance functions they call, :9-77).  covered[i] = any_j ( 1000*|t_i - t_j| + deg(R_i, R_j) <= eps ),

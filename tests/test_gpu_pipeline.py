@@ -112,3 +112,33 @@ def test_pipelined_host_submission_equals_evaluate_host():
     got.append((r['gs']._gs_array.copy(), r['contacts'].copy(), r['n_grasps'], r['n_free']))
     for w, g in zip(want, got):
         assert w[2:] == g[2:] and np.array_equal(w[0], g[0]) and np.array_equal(w[1], g[1])
+
+
+def test_shuffled_surface_samples_are_a_permutation_of_stage_s1():
+    """run_pipeline(surface=(total, offset, key)): reference point i of the batch is surface sample perm(offset + i) of ONE
+    set of `total` samples -- all of them exactly once over a full cycle, whatever the batch boundaries, in an order that
+    depends on the key; and sample() built on it keeps the reference's contract"""
+    mesh, ags = _setup()
+    total, key = 1000, 424242
+    want = ags.sample_surface(total, key)[0].cpu().numpy()
+    got = []
+    for off, n in ((0, 333), (333, 600), (933, 67)):
+        out = ags.run_pipeline(n_ref=n, seed=5, check_collisions=False, surface=(total, off, key), graph=(n != 600))
+        got.append(out['ref_pts'][:n].cpu().numpy().copy())
+    got = np.concatenate(got)
+    assert not np.array_equal(got, want)                                   # shuffled ...
+    assert np.array_equal(got[np.lexsort(got.T)], want[np.lexsort(want.T)])     # ... but the same 1000 points, each once
+    other = ags.run_pipeline(n_ref=333, seed=5, check_collisions=False, surface=(total, 0, key + 1))['ref_pts'][:333].cpu().numpy()
+    assert not np.array_equal(other, got[:333])
+    wrap = ags.run_pipeline(n_ref=100, seed=5, check_collisions=False, surface=(total, 950, key))['ref_pts'][:100].cpu().numpy()
+    assert np.array_equal(wrap[:50], got[950:]) and np.array_equal(wrap[50:], got[:50])
+    np.random.seed(3)
+    gs, contacts = ags.sample(500)
+    assert len(gs) >= 500 and len(gs) % 12 == 0 and contacts.shape == (len(gs), 2, 3)
+    assert ags.last_stats['grasps'] == len(gs) and ags.last_stats['candidates'] == ags.last_stats['ref_points_used'] * 100
+    np.random.seed(3)
+    gs2, _ = ags.sample(500)
+    assert np.array_equal(gs._gs_array, gs2._gs_array)                      # np.random.seed makes runs reproducible
+    # widths of the returned grasps = distance of their contact pairs (row r belongs to contacts r)
+    assert np.allclose(gs._gs_array[:, 13], np.linalg.norm(contacts[:, 1] - contacts[:, 0], axis=1), rtol=1e-6)
+
