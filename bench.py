@@ -17,8 +17,10 @@ every N: coverage_c2, ags_c4, coverage_c5, ags_c3_exhaustive and (N = 1) ags_c1.
                sampling.py:328-338): ~0.9 M contact pairs = ~11 M posed grippers per 1 M candidates -- the collision stage under load.
 
 A "step" is one pass of the device pipeline over one batch of synthetic candidates.  The timed region holds
-exactly K steps, each bracketed by CUDA events on the launching stream; L2 is flushed between steps (outside the
-event pairs); the reported time is the max over ranks of the summed step times.
+exactly K steps between one CUDA-event pair on the launching stream (the steps are issued round-robin on --streams
+streams and joined), bracketed by a barrier + synchronize; the reported time is the max over ranks.  L2 between steps
+(--l2): `rotate` (default) = inputs larger than L2, consecutive steps work on different objects (4 x ~50 MB at config 3);
+`flush` = round 1's 256 MB fill before every step inside the timed region; the line carries both.
 
 --impl reference times the reference's CPU algorithm on the host cores instead: the reference is pure Python on
 un-installable third-party leaves, so this arm runs the oracle port (oracle/coracle.c: same arithmetic, BVH broad
@@ -41,6 +43,7 @@ sys.path.insert(0, ROOT)
 N_REF = 10_000
 N_RAYS = 100
 N_ORIENT = 12
+C3_OBJECTS = 4                          # distinct config-3 objects the steps rotate over (4 x ~50 MB > L2)
 COV_N = 100_000
 EXHAUSTIVE_TARGETS = 128
 
@@ -244,7 +247,10 @@ def cpu_coverage_record(workload, n_sample_c2=100_000, n_ref_sample_c5=4000):
 def ags_workload_meshes(workload):
     """-> (target meshes, scene meshes or None)"""
     if workload in ('ags_c3', 'ags_c3_exhaustive'):
-        return [c3_mesh()], None
+        # C3_OBJECTS distinct objects of the same kind, one per step in turn: with the per-leaf records each is ~50 MB on the
+        # device, so consecutive uses of one object are separated by > 126 MB (L2) of other objects and per-step buffers
+        from burg_toolkit_b200 import mesh as bmesh
+        return [c3_mesh()] + [bmesh.create_bumpy_sphere(224, 224, radius=0.035, amplitude=0.15, seed=1 + k) for k in range(1, C3_OBJECTS)], None
     if workload == 'ags_c1':
         from burg_toolkit_b200 import mesh as bmesh
         return [bmesh.create_icosphere(5, 0.03)], None
@@ -415,6 +421,16 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
     # casting of the next.  Each stream owns a workspace (slot) and an L2-flush buffer.
     n_streams = max(1, int(ctx.args.streams))
     streams = [torch.cuda.Stream() for _ in range(n_streams)]
+    # L2 between steps (timing rules: "flush L2 or use inputs larger than L2"):
+    #   rotate (default): every step works on the next of several distinct objects (config 3: C3_OBJECTS x ~50 MB of mesh,
+    #           LBVH and per-leaf records; config 4: 20 targets in a 340 MB scene), so an object's data has been displaced by
+    #           > 126 MB of other objects' data and per-step buffers before it is used again -- nothing but the path is timed;
+    #   flush:  round 1's method, a 256 MB fill on the step's stream inside the timed region (reported as l2_flush_variant).
+    l2_mode = ctx.args.l2
+    l2_desc = ('a 256 MB buffer is written before every step, on the step\'s stream, inside the timed region' if l2_mode == 'flush' else
+               f'inputs larger than L2: consecutive steps work on different objects ({len(targets)} objects in turn' +
+               (f', ~50 MB of mesh + LBVH + per-leaf records each' if scene_meshes is None else f', inside a scene of {scene_tris} triangles = 340 MB') +
+               '), so an object is displaced from L2 by the other objects and > 100 MB of per-step buffers before it is used again; no flush kernel in the timed region')
     flushes = [ctx.flush] + [torch.empty_like(ctx.flush) for _ in range(n_streams - 1)]
 
     def step(seed, timer=None, graph=True, to_peer=True, slot=0):
@@ -429,8 +445,8 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
             dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
         return out
 
-    def run_steps(n, timed):
-        """n steps round-robin over the streams, L2 flushed before every step on the step's stream -> (ms, stats)"""
+    def run_steps(n, timed, flush=(l2_mode == 'flush')):
+        """n steps round-robin over the streams (flush: a 256 MB fill before every step on the step's stream) -> (events, stats)"""
         main = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stats = []
@@ -440,7 +456,8 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
         for s in range(n):
             k = s % n_streams
             with torch.cuda.stream(streams[k]):
-                flushes[k].fill_(s & 0xff)                                       # > L2, written between consecutive steps
+                if flush:
+                    flushes[k].fill_(s & 0xff)                                   # > L2, written between consecutive steps
                 out = step(7919 * (rank + 1) + s, slot=k)
                 if timed:
                     stats.append((out['n_grasps'].clone(), (out['n_free'] if out.get('n_free') is not None else out['n_grasps']).clone(), out['overflow'].clone()))
@@ -462,6 +479,13 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
     ctx.barrier()
     clk = clocks.stop()
     total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    # the other L2 method on the same steps, for continuity with round 1 (first re-align the gather ring with the step
+    # sequence, so that the same captured graphs are replayed)
+    while peer is not None and peer.epoch % ring:
+        step(1)
+    (f0, f1), _ = run_steps(steps, False, flush=(l2_mode != 'flush'))
+    ctx.barrier()
+    other_ms = ctx.max_over_ranks(f0.elapsed_time(f1))
     # the same steps one at a time on one stream (continuity with round 1, and what the per-stage times below add up to)
     single_events = []
     for s in range(min(steps, 5)):
@@ -544,26 +568,35 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
     #              the next batch's ray casting); L2 is NOT flushed between overlapping batches (they stream > 100 MB each)
     e2e = None
     if not exhaustive:
-        ags.mesh = mesh
-        host_batches = [[t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank + 17 * b)[:2]] for b in range(4)]
-        for w in range(max(warmup, 2)):
-            ags.evaluate_host(*host_batches[w % 4], seed=w + 1, **pipe_kw)
-            ags.submit_host(*host_batches[w % 4], seed=w + 1, slot=1, **pipe_kw).result()
+        # batch b works on object b % len(targets) (the same rotation as the device-resident steps)
+        n_hb = 4 if len(targets) == 1 else len(targets)
+        host_batches = []
+        for b in range(n_hb):
+            ags.mesh = targets[b % len(targets)]
+            host_batches.append([t.cpu().numpy() for t in ags.sample_surface(N_REF, 4242 + rank + 17 * b)[:2]])
+
+        def host_call(fn, b, **kw):
+            ags.mesh = targets[b % len(targets)]
+            return fn(*host_batches[b % n_hb], **kw, **pipe_kw)
+        for w in range(max(warmup, 2, n_hb)):
+            host_call(ags.evaluate_host, w, seed=w + 1)
+            host_call(ags.submit_host, w, seed=w + 1, slot=1).result()
         ctx.barrier()
         serial_s, h2d, d2h = 0.0, 0, 0
         for s in range(steps):
-            ctx.flush.fill_(s & 0xff)
+            if l2_mode == 'flush':
+                ctx.flush.fill_(s & 0xff)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            res = ags.evaluate_host(*host_batches[s % 4], seed=s + 11, **pipe_kw)
+            res = host_call(ags.evaluate_host, s, seed=s + 11)
             serial_s += time.perf_counter() - t0
             h2d, d2h = res['h2d_bytes'], res['d2h_bytes']
         ctx.barrier()
         t0 = time.perf_counter()
-        pending = ags.submit_host(*host_batches[0], seed=11, slot=0, **pipe_kw)
+        pending = host_call(ags.submit_host, 0, seed=11, slot=0)
         got = 0
         for s in range(1, steps):
-            nxt = ags.submit_host(*host_batches[s % 4], seed=s + 11, slot=s & 1, **pipe_kw)
+            nxt = host_call(ags.submit_host, s, seed=s + 11, slot=s & 1)
             got += pending.result()['n_free']
             pending = nxt
         got += pending.result()['n_free']
@@ -576,7 +609,7 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
                'mode': 'AntipodalGraspSampler.submit_host on two alternating slots (one batch in flight while the next is submitted); '
                        'every batch: pinned staging copy, H2D, graph-replayed pipeline, kept rows stored into pinned host memory by the compaction kernel',
                'serial': {'value': candidates / (serial_ms * 1e-3), 'ms_per_step': serial_ms / steps,
-                          'mode': 'AntipodalGraspSampler.evaluate_host, one synchronous call per batch, L2 flushed between calls'},
+                          'mode': 'AntipodalGraspSampler.evaluate_host, one synchronous call per batch (' + l2_desc + ')'},
                'rows_received_per_step': got / steps}
 
     # multi-GPU: does rank 0 hold, bit for bit, what the ranks computed?  One more step into the peer buffer, the same step
@@ -599,7 +632,7 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
         gather_verified = ctx.sum_over_ranks(ok if rank == 0 else 0.0) == 1.0
         exchange_timed_out = ctx.sum_over_ranks(1.0 if peer.close(raise_on_timeout=False) else 0.0) > 0
 
-    mesh_desc = {'ags_c3': 'bumpy sphere 224x224 (YCB-like, seed 1)', 'ags_c3_exhaustive': 'bumpy sphere 224x224 (YCB-like, seed 1)',
+    mesh_desc = {'ags_c3': f'bumpy spheres 224x224 (YCB-like, seeds 1-{C3_OBJECTS}), one per step in turn', 'ags_c3_exhaustive': f'bumpy spheres 224x224 (YCB-like, seeds 1-{C3_OBJECTS}), one per step in turn',
                  'ags_c4': '20 bumpy objects (158x158 grids, seeds 10-29) on a 1.0 x 0.5 m ground slab; target object changes every step'}[workload]
     block = {'metric': 'AGS candidates/sec (ray+cone+collision)', 'value': value, 'unit': 'candidates/s',
              'ms_per_step': total_ms / steps, 'dtype': 'f64', 'scaling': 'weak',
@@ -611,7 +644,9 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
                         'collision': ('gripper-vs-object' if scene_meshes is None else 'gripper-vs-scene') + ', use_width, tol 0.01',
                         'mode': 'exhaustive (every valid hit of a reference point becomes a contact pair)' if exhaustive else
                                 'reference mode (one pair per reference point)',
-                        'l2': 'a 256 MB buffer is written before every step, on the step\'s stream, inside the timed region',
+                        'l2': l2_desc,
+                        'l2_other_method': {'method': 'rotate' if l2_mode == 'flush' else 'flush (256 MB written before every step, on the step\'s stream, inside the timed region: round 1\'s method)',
+                                            'ms_per_step': other_ms / steps, 'value': candidates / (other_ms * 1e-3)},
                         'launch': 'bt_ags_pipeline replayed as a CUDA graph (bt_graph_*)', 'streams': n_streams,
                         'timing': f'one CUDA-event pair around all {steps} steps (issued round-robin on {n_streams} streams, joined on the launching stream)',
                         'single_stream_ms_per_step': single_ms,
@@ -849,6 +884,7 @@ def main():
     ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
     ap.add_argument('--streams', type=int, default=3, help='AGS workloads: batches in flight per GPU (round-robin streams)')
+    ap.add_argument('--l2', default='rotate', choices=['rotate', 'flush'], help='AGS workloads: how L2 is kept cold between steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='ags_c3 only: skip the blocks of the other configurations')
     args = ap.parse_args()

@@ -141,9 +141,9 @@ __device__ __forceinline__ bool maybe_hit_f32(const float4* __restrict__ tr, flo
 constexpr int NPEND = 32;
 
 // ---- stage 1 of the ray caster: float32 traversal with ray re-fetch ---------------------------------------------------
-// Every warp owns a contiguous slice of rays (rays of one reference point are neighbours, so the slice is coherent) and
-// keeps its 32 lanes busy: a lane whose ray has left the tree immediately takes the next ray of the slice (warp-uniform
-// counter, no atomics).  The lanes only ever execute 4-wide NODE steps: the two planes of an axis share a word of the
+// Persistent warps take chunks of consecutive rays from a global counter (rays of one reference point are neighbours, so
+// a chunk is coherent) and keep their 32 lanes busy: a lane whose ray has left the tree takes the next ray of the chunk,
+// and the next chunk when that one is used up.  The lanes only ever execute 4-wide NODE steps: the two planes of an axis share a word of the
 // node, the ray picks its near / far plane by the sign of its direction with one byte-permute each, so a box test is
 // 6 permutes + 6 FMAs + one max3 + one min3 + the compares.  Leaves that a ray reaches are not tested in line (that
 // would serialise the warp): they go to the warp's leaf queue in shared memory, and once 32 are queued every lane runs
@@ -208,27 +208,27 @@ __device__ __forceinline__ void fill_cone_table(float* tab, float angle_max) {
 template <bool STATS, bool PACKED, bool CULL>
 __global__ void __launch_bounds__(32 * TWARPS, TRAV_MINB)
 traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* __restrict__ dirs, int64_t n_total,
-                int n_rays, int rays_per_warp, float angle_max, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
-                unsigned long long* __restrict__ counters) {
+                int n_rays, int chunk_len, float angle_max, int32_t* __restrict__ cand_count, int32_t* __restrict__ cand,
+                unsigned* __restrict__ chunk_counter, unsigned long long* __restrict__ counters) {
     unsigned long long st_nodes = 0, st_leaves = 0, st_cand = 0, st_culled = 0;
-    __shared__ int2 s_lq[TWARPS][LQ_CAP];            // leaf queue entries: (ray offset in the slice, leaf)
+    __shared__ int2 s_lq[TWARPS][LQ_CAP];            // leaf queue entries: (ray, leaf)
     __shared__ int s_lq_n[TWARPS];
     __shared__ float s_thr[CULL ? 256 : 1];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (CULL) { fill_cone_table(s_thr, angle_max); __syncthreads(); }
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t slice_begin = warp * rays_per_warp;
-    if (slice_begin >= n_total) return;                 // whole warps leave together (no block-wide barrier below)
-    const int slice_len = (int)min((int64_t)rays_per_warp, n_total - slice_begin);
-    const unsigned ref0 = (unsigned)(slice_begin / n_rays), rem0 = (unsigned)(slice_begin - (int64_t)ref0 * n_rays);
-    int next = 0;                                     // warp-uniform: first ray of the slice nobody has taken yet
+    // Rays are handed out in chunks of `chunk_len` consecutive rays (rays of one reference point are neighbours, so a chunk
+    // is coherent) from a global counter: a warp whose lanes run dry takes the next chunk instead of idling until the
+    // slowest ray of a fixed slice has finished, so only the kernel's last chunks see a thinning warp.
+    const int total = (int)n_total;
+    int next = 0, chunk_end = 0;                      // warp-uniform: rays [next, chunk_end) of the current chunk are untaken
+    bool exhausted = false;                           // warp-uniform: the counter has run past the last chunk
     int2* lq = s_lq[w];
     if (lane == 0) s_lq_n[w] = 0;
     __syncwarp();
 
     const int DONE = (int)0x80000000;                 // never a leaf code: leaf codes are ~index with index < 2^30
-    int my = 0;                                       // this lane's ray, as an offset into the slice
+    int my = 0;                                       // this lane's ray
     float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
     unsigned snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;
     float ux = 0, uy = 0, uz = 0, ubias = 0;             // CULL: unit direction and CONE_BIAS * (ux + uy + uz)
@@ -239,9 +239,8 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     auto pretest_pass = [&](int first, int count) {
         if (lane < count) {
             const int2 en = lq[first + lane];
-            const int off = en.x, leaf = en.y;
-            const unsigned k = rem0 + (unsigned)off;
-            const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays, ray = slice_begin + off;
+            const int leaf = en.y;
+            const int64_t ray = en.x, ref = (unsigned)en.x / (unsigned)n_rays;
             const float ox = (float)ref_pts[3 * ref], oy = (float)ref_pts[3 * ref + 1], oz = (float)ref_pts[3 * ref + 2];
             const float dx = (float)dirs[3 * ray], dy = (float)dirs[3 * ray + 1], dz = (float)dirs[3 * ray + 2];
             bool keep = true;
@@ -261,14 +260,22 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
     };
 
     while (true) {
-        // ---- re-fetch: when enough lanes have run dry they take the next rays of the slice ---------------------------
+        // ---- re-fetch: when enough lanes have run dry they take the next rays of the chunk (or of a new chunk) ----------
         const unsigned idle = __ballot_sync(FULL, cur == DONE);
-        if (next < slice_len && (__popc(idle) >= TRAV_REFETCH || idle == FULL)) {
+        if (!exhausted && (__popc(idle) >= TRAV_REFETCH || idle == FULL)) {
+            if (next >= chunk_end) {
+                unsigned c = 0;
+                if (lane == 0) c = atomicAdd(chunk_counter, 1u);
+                c = __shfl_sync(FULL, c, 0);
+                const int64_t begin = (int64_t)c * chunk_len;
+                exhausted = begin >= n_total;
+                next = exhausted ? total : (int)begin;
+                chunk_end = (int)min((int64_t)total, begin + chunk_len);
+            }
             const int rank = __popc(idle & ((1u << lane) - 1u));
-            if (cur == DONE && next + rank < slice_len) {
+            if (cur == DONE && next + rank < chunk_end) {
                 my = next + rank;
-                const unsigned k = rem0 + (unsigned)my;                           // 32-bit arithmetic: no 64-bit division here
-                const int64_t ref = (int64_t)ref0 + k / (unsigned)n_rays, ray = slice_begin + my;
+                const int64_t ray = my, ref = (unsigned)my / (unsigned)n_rays;
                 // the ray in grid coordinates (same parameter t): origin (o - gmin) * scale, direction d * scale.
                 // Box coordinates arrive as 2^23 + q (uint16 permuted into the mantissa of 2^23); instead of subtracting 2^23
                 // per coordinate the offset is folded into the FMA constant: t = fma(2^23 + q, 1/dg, -(2^23/dg + og/dg)).
@@ -295,10 +302,10 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
                 }
                 sp = 0; cur = 0;
             }
-            next = min(slice_len, next + __popc(idle));
+            next = min(chunk_end, next + __popc(idle));
         }
         if (__all_sync(FULL, cur == DONE)) {
-            if (next >= slice_len) break;
+            if (exhausted) break;
             continue;
         }
         // ---- a short burst of 4-wide node steps -----------------------------------------------------------------------
@@ -1067,17 +1074,18 @@ int bt::ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double
     MeshView mv = view_of(mesh->m);
     // stage 1: float32 traversal with ray re-fetch -> candidate leaves per ray
     Scratch cc, cl;
-    BT_CUDA(cc.alloc(sizeof(int32_t) * total, st));
+    BT_CUDA(cc.alloc(sizeof(int32_t) * (total + 1), st));                 // [total] candidate counts + the chunk counter
     BT_CUDA(cl.alloc(sizeof(int32_t) * total * CCAP, st));
-    BT_CUDA(cudaMemsetAsync(cc.p, 0, sizeof(int32_t) * total, st));        // the traversal appends with atomics
+    BT_CUDA(cudaMemsetAsync(cc.p, 0, sizeof(int32_t) * (total + 1), st)); // the traversal appends with atomics
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mesh->m.device);
-    // slice length: two rays per lane so that re-fetching can even out the walks, but several waves of warps per SM
-    // for balance (32 warps / SM resident; measured at C3: 64 rays 0.60 ms, 96-128 rays 0.63 ms, 192 rays 0.70 ms)
-    int64_t rpw = ceil_div(total, (int64_t)sm_count * 32 * 4);
-    rpw = std::max<int64_t>(64, std::min<int64_t>(256, ceil_div(rpw, 32) * 32));
-    if (const char* e = getenv("BT_CAST_RPW")) { const int v = atoi(e); if (v >= 32 && v <= 256) rpw = v; }       // tuning knob
-    const int64_t n_warps = ceil_div(total, rpw);
+    // chunk of rays a warp takes from the global counter at a time (coherent: consecutive rays of one reference point);
+    // persistent grid, TRAV_MINB blocks per SM.  Fixed slices per warp (round 1) left the lanes of every warp idle while
+    // the slowest ray of the slice finished: 21.6 of 32 lanes active at C3.
+    int64_t rpw = 32;
+    if (const char* e = getenv("BT_CAST_RPW")) { const int v = atoi(e); if (v >= 32 && v <= 4096) rpw = v; }       // tuning knob
+    BT_REQUIRE(total + rpw < ((int64_t)1 << 31), "more than 2^31 rays in one call");
+    const int64_t n_warps = std::min<int64_t>(ceil_div(total, rpw), (int64_t)sm_count * TRAV_MINB * TWARPS);
     // cone culling: only where the caller wants valid hits and nothing else (lean pipeline), on packed nodes
     static int cull_env = -1;
     if (cull_env < 0) { const char* e = getenv("BT_CAST_CULL"); cull_env = e ? atoi(e) : 1; }
@@ -1086,7 +1094,8 @@ int bt::ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double
     const unsigned tgrid = (unsigned)ceil_div(n_warps * 32, 128);
 #define BT_TRAVERSE(STATS, PACKED, CULL, CNT)                                                                              \
     traverse_kernel<STATS, PACKED, CULL><<<tgrid, 128, 0, st>>>(mv, d_ref_pts, d_dirs, total, n_rays, (int)rpw,            \
-                                                                (float)params->angle_max, cc.as<int32_t>(), cl.as<int32_t>(), CNT)
+                                                                (float)params->angle_max, cc.as<int32_t>(), cl.as<int32_t>(),      \
+                                                                reinterpret_cast<unsigned*>(cc.as<int32_t>() + total), CNT)
     if (g_counters_host_copy) {
         if (do_cull) BT_TRAVERSE(true, true, true, g_counters_host_copy);
         else if (packed) BT_TRAVERSE(true, true, false, g_counters_host_copy);

@@ -16,7 +16,7 @@
 // cell >= r_max (CUB radix sort by cell), so a sample's neighbours are in its 27 surrounding cells.
 //
 // open3d seeds its generator from std::random_device, i.e. the reference's sample set is not reproducible and parity at
-// this stage is distributional (blue-noise statistics against the serial algorithm in oracle/leaves.py on the same
+// this stage is distributional (blue-noise statistics against the serial restatement in the test oracle on the same
 // initial samples: tests/test_gpu_poisson.py).
 #include <cub/cub.cuh>
 #include <math.h>
