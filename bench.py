@@ -400,13 +400,16 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
     peer, gather_buf, exchange = None, None, 'none (1 GPU)'
     if world > 1 and exhaustive:
         exchange = 'none: every rank keeps its ~10 M rows (the gather buffer of this mode would hold 3 x world x 1.6 GB on rank 0)'
+    elif world > 1 and os.environ.get('BT_BENCH_NO_EXCHANGE') == '1':              # diagnostic: what the exchange costs
+        exchange = 'none: disabled by BT_BENCH_NO_EXCHANGE (diagnostic run, every rank keeps its rows)'
     elif world > 1:
         from burg_toolkit_b200 import distributed as bdist
         from burg_toolkit_b200._native import NativeError
         try:
             mode = os.environ.get('BT_PEER_ONE_SIDED')                  # A/B knob; default: one-sided from 4 ranks on
             peer = bdist.PeerGather(cap_rows, with_contacts=True, device=local_rank, one_sided=None if mode is None else mode != '0', timeout_s=30.0)
-            exchange = ('compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer); ' +
+            exchange = (('compaction into local memory, then the exchange stream moves rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer; ' + ('copy engine, padded to the capacity' if peer.push_blocks == 0 else f'bt_peer_push, {peer.push_blocks} blocks, exactly the kept rows') + '); '
+                         if peer.staged else 'compaction kernel stores rows + contacts into rank 0 over NVLink (CUDA IPC peer buffer); ') +
                         ('counts + epoch flags stored the same way, rank 0 polls them (no collective in the step)' if peer.one_sided
                          else 'NCCL all_gather of counts'))
         except NativeError as ex:
@@ -435,15 +438,17 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
 
     def step(seed, timer=None, graph=True, to_peer=True, slot=0):
         ags.mesh = targets[seed % len(targets)]
-        dest = peer.destinations() if (peer is not None and to_peer) else None
+        dest = peer.destinations(slot=slot) if (peer is not None and to_peer) else None
         out = ags.run_pipeline(n_ref=N_REF, seed=seed, check_collisions=True, timer=timer, destinations=dest, slot=slot,
                                graph=graph and timer is None, **pipe_kw)
         if peer is not None and to_peer:
-            peer.complete(out['n_free'])
+            peer.complete(out['n_free'], rows=out.get('free_gs'), contacts=out.get('free_contacts'), slot=slot)
         elif world > 1 and gather_buf is not None and to_peer:
             dist.all_reduce(out['n_free'], op=dist.ReduceOp.SUM)
             dist.gather(out['free_gs'], list(gather_buf.unbind(0)) if rank == 0 else None, dst=0)
         return out
+
+    issue_s = [0.0]
 
     def run_steps(n, timed, flush=(l2_mode == 'flush')):
         """n steps round-robin over the streams (flush: a 256 MB fill before every step on the step's stream) -> (events, stats)"""
@@ -453,6 +458,7 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
         e0.record(main)
         for st in streams:
             st.wait_event(e0)
+        t_issue = time.perf_counter()
         for s in range(n):
             k = s % n_streams
             with torch.cuda.stream(streams[k]):
@@ -461,6 +467,7 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
                 out = step(7919 * (rank + 1) + s, slot=k)
                 if timed:
                     stats.append((out['n_grasps'].clone(), (out['n_free'] if out.get('n_free') is not None else out['n_grasps']).clone(), out['overflow'].clone()))
+        issue_s[0] = time.perf_counter() - t_issue          # host time spent issuing the n steps (no waits in there)
         for st in streams:
             main.wait_stream(st)
         e1.record(main)
@@ -478,7 +485,14 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
     (e0, e1), stats = run_steps(steps, True)
     ctx.barrier()
     clk = clocks.stop()
-    total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    my_ms = e0.elapsed_time(e1)
+    total_ms = ctx.max_over_ranks(my_ms)
+    host_issue_ms = ctx.max_over_ranks(issue_s[0] * 1e3) / steps
+    rank_ms, clk_by_rank = [my_ms / steps], [clk.get('sm_mhz')]
+    if world > 1:
+        rank_ms, clk_by_rank = [None] * world, [None] * world
+        dist.all_gather_object(rank_ms, my_ms / steps)
+        dist.all_gather_object(clk_by_rank, clk.get('sm_mhz'))
     # the other L2 method on the same steps, for continuity with round 1 (first re-align the gather ring with the step
     # sequence, so that the same captured graphs are replayed)
     while peer is not None and peer.epoch % ring:
@@ -649,7 +663,8 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
                                             'ms_per_step': other_ms / steps, 'value': candidates / (other_ms * 1e-3)},
                         'launch': 'bt_ags_pipeline replayed as a CUDA graph (bt_graph_*)', 'streams': n_streams,
                         'timing': f'one CUDA-event pair around all {steps} steps (issued round-robin on {n_streams} streams, joined on the launching stream)',
-                        'single_stream_ms_per_step': single_ms,
+                        'single_stream_ms_per_step': single_ms, 'host_issue_ms_per_step': host_issue_ms,
+                        'ms_per_step_by_rank': [round(x, 4) for x in rank_ms], 'sm_mhz_by_rank': clk_by_rank,
                         'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
                         'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow,
                         'exchange': exchange, 'exchange_timed_out': exchange_timed_out},
@@ -883,7 +898,7 @@ def main():
     ap.add_argument('--workload', default='ags_c3', choices=['ags_c1', 'ags_c3', 'ags_c3_exhaustive', 'ags_c4', 'coverage_c2', 'coverage_c5'])
     ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
-    ap.add_argument('--streams', type=int, default=3, help='AGS workloads: batches in flight per GPU (round-robin streams)')
+    ap.add_argument('--streams', type=int, default=4, help='AGS workloads: batches in flight per GPU (round-robin streams)')
     ap.add_argument('--l2', default='rotate', choices=['rotate', 'flush'], help='AGS workloads: how L2 is kept cold between steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='ags_c3 only: skip the blocks of the other configurations')

@@ -100,6 +100,8 @@ _SIGNATURES = {
     'bt_peer_close': (C.c_int, [C.c_int, _P]),
     'bt_peer_free': (C.c_int, [C.c_int, _P]),
     'bt_peer_signal': (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    'bt_peer_copy': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'bt_peer_push': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, _P]),
     'bt_peer_wait': (C.c_int, [_P, C.c_int32, C.c_int64, C.c_double, _P, _P, C.c_int64, _P]),
     'bt_timer_create': (C.c_int, [C.c_int, C.POINTER(_P)]),
     'bt_timer_destroy': (C.c_int, [_P]),

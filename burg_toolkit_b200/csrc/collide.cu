@@ -661,66 +661,75 @@ __global__ void __launch_bounds__(CB) compact_kernel(const uint8_t* __restrict__
     __shared__ unsigned long long s_excl;
     __shared__ uint16_t src_of[CB];
     __shared__ double tile[CB * 7];                       // 14 KB: the block's rows (7 words each), then its contacts (6 each)
-    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned bid = s_bid;
-    const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
-    const int64_t row0 = bid * (int64_t)CB;
-    const int64_t i = row0 + threadIdx.x;
-    const bool k = (i < n) && (mask[i] == keep);
-    const unsigned bal = __ballot_sync(0xffffffffu, k);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) warp_off[w] = __popc(bal);
-    const int rows_here = (int)max((int64_t)0, min((int64_t)CB, n - row0));
-    {   // stage the source rows while the offsets settle
-        const double* src = reinterpret_cast<const double*>(gs) + 7 * row0;
-        for (int e = threadIdx.x; e < rows_here * 7; e += CB) tile[e] = src[e];
-    }
-    __syncthreads();
-    if (w == 0) {
-        int c = lane < CB / 32 ? warp_off[lane] : 0;
-        int incl = c;
+    const int64_t n = d_n ? min(n_cap, *d_n) : n_cap;
+    // Persistent blocks take 256-row tiles in ticket order (the look-back only ever waits for lower tickets, which are done
+    // or held by a running block).  The grid is sized by the destination: many blocks for local HBM, ONE block per SM when
+    // the stores cross NVLink or PCIe -- there the kernel lives as long as the link needs (80 us for 11 MB into a peer that
+    // seven ranks write at once, 250 us into host memory), and a block per tile would sit on a third of every SM's warp
+    // slots for that time and starve the next batch's ray caster running beside it.
+    while (true) {
+        __syncthreads();                                  // the previous tile's shared state is no longer read
+        if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned bid = s_bid;
+        if (bid >= n_blocks) return;
+        const int64_t row0 = bid * (int64_t)CB;
+        const int64_t i = row0 + threadIdx.x;
+        const bool k = (i < n) && (mask[i] == keep);
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) warp_off[w] = __popc(bal);
+        const int rows_here = (int)max((int64_t)0, min((int64_t)CB, n - row0));
+        {   // stage the source rows while the offsets settle
+            const double* src = reinterpret_cast<const double*>(gs) + 7 * row0;
+            for (int e = threadIdx.x; e < rows_here * 7; e += CB) tile[e] = src[e];
+        }
+        __syncthreads();
+        if (w == 0) {
+            int c = lane < CB / 32 ? warp_off[lane] : 0;
+            int incl = c;
 #pragma unroll
-        for (int s = 1; s < CB / 32; s <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += v; }
-        if (lane < CB / 32) warp_off[lane] = incl - c;
-        const int run = __shfl_sync(0xffffffffu, incl, CB / 32 - 1);
-        const unsigned long long excl = lookback_exclusive(status, bid, (unsigned long long)run, lane);
-        if (lane == 0) {
-            run_s = run;
-            s_excl = excl;
-            if (bid == n_blocks - 1 && n_out) *n_out = (int64_t)excl + run + (d_base ? *d_base : 0);
+            for (int s = 1; s < CB / 32; s <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += v; }
+            if (lane < CB / 32) warp_off[lane] = incl - c;
+            const int run = __shfl_sync(0xffffffffu, incl, CB / 32 - 1);
+            const unsigned long long excl = lookback_exclusive(status, bid, (unsigned long long)run, lane);
+            if (lane == 0) {
+                run_s = run;
+                s_excl = excl;
+                if (bid == n_blocks - 1 && n_out) *n_out = (int64_t)excl + run + (d_base ? *d_base : 0);
+            }
         }
-    }
-    __syncthreads();
-    if (k) src_of[warp_off[w] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
-    __syncthreads();
-    const int run = run_s;
-    const int64_t dst0 = (int64_t)s_excl + (d_base ? *d_base : 0);      // appending behind an earlier batch's rows
-    // the run leaves as 32-byte stores (STG.E.256; up to three 8-byte words in front / behind where the run is not 32-byte
-    // aligned): a warp store covers 1 KB of contiguous destination, which is what a link wants to see (against 16-byte
-    // stores: the same over NVLink, 1.26 -> 1.20 ms for the end-to-end call over PCIe)
-    auto stream_out = [&](double* dst, int words_per_row) {
-        const int n = run * words_per_row;
-        if (n == 0) return;
-        auto word = [&](int e) { const int r = e / words_per_row; return tile[words_per_row * src_of[r] + (e - words_per_row * r)]; };
-        const int head = min(n, (int)((4u - ((unsigned)(reinterpret_cast<uintptr_t>(dst) >> 3) & 3u)) & 3u));
-        const int n_quads = (n - head) >> 2;
-        const int tail0 = head + 4 * n_quads;
-        if (threadIdx.x < head) dst[threadIdx.x] = word(threadIdx.x);
-        for (int q = threadIdx.x; q < n_quads; q += CB) {
-            const int e = head + 4 * q;
-            const double w0 = word(e), w1 = word(e + 1), w2 = word(e + 2), w3 = word(e + 3);
-            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(dst + e), "d"(w0), "d"(w1), "d"(w2), "d"(w3) : "memory");
+        __syncthreads();
+        if (k) src_of[warp_off[w] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+        __syncthreads();
+        const int run = run_s;
+        const int64_t dst0 = (int64_t)s_excl + (d_base ? *d_base : 0);      // appending behind an earlier batch's rows
+        // the run leaves as 32-byte stores (STG.E.256; up to three 8-byte words in front / behind where the run is not 32-byte
+        // aligned): a warp store covers 1 KB of contiguous destination, which is what a link wants to see (against 16-byte
+        // stores: the same over NVLink, 1.26 -> 1.20 ms for the end-to-end call over PCIe)
+        auto stream_out = [&](double* dst, int words_per_row) {
+            const int n = run * words_per_row;
+            if (n == 0) return;
+            auto word = [&](int e) { const int r = e / words_per_row; return tile[words_per_row * src_of[r] + (e - words_per_row * r)]; };
+            const int head = min(n, (int)((4u - ((unsigned)(reinterpret_cast<uintptr_t>(dst) >> 3) & 3u)) & 3u));
+            const int n_quads = (n - head) >> 2;
+            const int tail0 = head + 4 * n_quads;
+            if (threadIdx.x < head) dst[threadIdx.x] = word(threadIdx.x);
+            for (int q = threadIdx.x; q < n_quads; q += CB) {
+                const int e = head + 4 * q;
+                const double w0 = word(e), w1 = word(e + 1), w2 = word(e + 2), w3 = word(e + 3);
+                asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(dst + e), "d"(w0), "d"(w1), "d"(w2), "d"(w3) : "memory");
+            }
+            if (threadIdx.x >= 32 && threadIdx.x < 32 + (n - tail0)) dst[tail0 + threadIdx.x - 32] = word(tail0 + threadIdx.x - 32);
+        };
+        stream_out(reinterpret_cast<double*>(out_gs) + 7 * dst0, 7);
+        if (contacts && out_contacts) {
+            __syncthreads();
+            const double* src = contacts + 6 * row0;
+            for (int e = threadIdx.x; e < rows_here * 6; e += CB) tile[e] = src[e];
+            __syncthreads();
+            stream_out(out_contacts + 6 * dst0, 6);
         }
-        if (threadIdx.x >= 32 && threadIdx.x < 32 + (n - tail0)) dst[tail0 + threadIdx.x - 32] = word(tail0 + threadIdx.x - 32);
-    };
-    stream_out(reinterpret_cast<double*>(out_gs) + 7 * dst0, 7);
-    if (contacts && out_contacts) {
-        __syncthreads();
-        const double* src = contacts + 6 * row0;
-        for (int e = threadIdx.x; e < rows_here * 6; e += CB) tile[e] = src[e];
-        __syncthreads();
-        stream_out(out_contacts + 6 * dst0, 6);
     }
 }
 
@@ -944,9 +953,21 @@ int bt::compact_impl(const uint8_t* d_mask, uint8_t keep_value, const float* d_g
     Scratch state;                                              // [n_blocks] status words of the chained scan + the ticket counter
     BT_CUDA(state.alloc(sizeof(unsigned long long) * (n_blocks + 1), st));
     BT_CUDA(cudaMemsetAsync(state.p, 0, sizeof(unsigned long long) * (n_blocks + 1), st));
-    compact_kernel<<<(unsigned)n_blocks, CB, 0, st>>>(d_mask, keep_value, n, d_n, state.as<unsigned long long>(),
-                                                      reinterpret_cast<unsigned*>(state.as<unsigned long long>() + n_blocks), (unsigned)n_blocks,
-                                                      d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out, d_base);
+    // grid: one block per SM when the destination is not this GPU's memory (peer over NVLink, mapped host memory over
+    // PCIe), else up to six per SM (see compact_kernel)
+    int device = 0, sm_count = 148;
+    BT_CUDA(cudaGetDevice(&device));
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaPointerAttributes attr;
+    bool local = true;
+    if (cudaPointerGetAttributes(&attr, d_out_gs) == cudaSuccess) local = attr.type == cudaMemoryTypeDevice && attr.device == device;
+    else cudaGetLastError();
+    static int remote_blocks = -1;
+    if (remote_blocks < 0) { const char* e = getenv("BT_COMPACT_REMOTE_BLOCKS"); remote_blocks = e ? std::max(1, atoi(e)) : sm_count; }     // tuning knob
+    const int64_t grid = std::min<int64_t>(n_blocks, local ? (int64_t)sm_count * 6 : (int64_t)remote_blocks);
+    compact_kernel<<<(unsigned)grid, CB, 0, st>>>(d_mask, keep_value, n, d_n, state.as<unsigned long long>(),
+                                                  reinterpret_cast<unsigned*>(state.as<unsigned long long>() + n_blocks), (unsigned)n_blocks,
+                                                  d_gs, d_contacts, d_out_gs, d_out_contacts, d_n_out, d_base);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

@@ -19,6 +19,29 @@ __global__ void peer_signal_kernel(const int64_t* __restrict__ local_count, int6
     *reinterpret_cast<volatile int64_t*>(flag_slot) = epoch;
 }
 
+// Staged form of the gather: the compaction has written this rank's kept rows into LOCAL memory (at HBM speed, inside the
+// step's graph); this kernel -- on the rank's exchange stream, off the step's critical path -- streams exactly *d_n rows
+// (56-byte grasp rows, then 48-byte contact records) into the rank's slot of the destination's buffer as 16-byte peer
+// stores, grid-stride, with a few blocks only: it lives as long as the link needs and must not crowd the SMs.
+// Source and destination are 16-byte aligned (bt_peer_push checks); both row sizes are multiples of 8 bytes.
+__global__ void __launch_bounds__(256) peer_push_kernel(const int64_t* __restrict__ d_n, int64_t cap, const float* __restrict__ gs,
+                                                        const double* __restrict__ contacts, float* dst_gs, double* dst_contacts) {
+    const int64_t n = min(cap, *d_n);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = gridDim.x * (int64_t)blockDim.x;
+    auto push = [&](const void* src, void* dst, int64_t bytes) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        const int64_t n4 = bytes >> 4;
+        for (int64_t i = tid; i < n4; i += stride) {
+            const uint4 v = __ldcs(s4 + i);
+            asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(d4 + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        if ((bytes & 8) && tid == 0) reinterpret_cast<uint2*>(dst)[2 * n4] = reinterpret_cast<const uint2*>(src)[2 * n4];
+    };
+    push(gs, dst_gs, n * 56);
+    if (contacts && dst_contacts) push(contacts, dst_contacts, n * 48);
+}
+
 // lane r polls word r until it has reached `epoch`; gives up after `timeout_ns` (status[0] = 1) so that a lost peer
 // can never hang the device.  With `ack` the waiter then publishes that it has seen (consumed) `ack_value`.
 __global__ void peer_wait_kernel(const int64_t* words, int n_words, int64_t epoch, unsigned long long timeout_ns,
@@ -87,6 +110,25 @@ extern "C" int bt_peer_signal(const int64_t* d_local_count, int64_t* d_count_slo
     BT_REQUIRE(d_local_count && d_count_slot && d_flag_slot, "null pointer");
     peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_local_count, d_count_slot, d_flag_slot, epoch);
     BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_peer_push(const int64_t* d_n, int64_t cap_rows, const float* d_gs, const double* d_contacts, float* d_dst_gs,
+                            double* d_dst_contacts, int32_t n_blocks, void* stream) {
+    BT_REQUIRE(d_n && d_gs && d_dst_gs, "null pointer");
+    BT_REQUIRE(cap_rows >= 0 && n_blocks >= 1 && n_blocks <= 4096, "bad arguments");
+    BT_REQUIRE(((reinterpret_cast<uintptr_t>(d_gs) | reinterpret_cast<uintptr_t>(d_dst_gs) | reinterpret_cast<uintptr_t>(d_contacts) |
+                 reinterpret_cast<uintptr_t>(d_dst_contacts)) & 15) == 0, "buffers must be 16-byte aligned");
+    if (cap_rows == 0) return BT_OK;
+    peer_push_kernel<<<(unsigned)n_blocks, 256, 0, (cudaStream_t)stream>>>(d_n, cap_rows, d_gs, d_contacts, d_dst_gs, d_dst_contacts);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+extern "C" int bt_peer_copy(void* d_dst, const void* d_src, int64_t bytes, void* stream) {
+    BT_REQUIRE(d_dst && d_src && bytes >= 0, "bad arguments");
+    if (bytes == 0) return BT_OK;
+    BT_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));     // peer destination: a copy engine over NVLink, no SM
     return BT_OK;
 }
 

@@ -231,6 +231,14 @@ BT_API int bt_peer_free(int device, void* d_ptr);
  * bt_peer_wait: one small kernel that polls d_words[0 .. n_words) until each is >= epoch, for at most timeout_s seconds
  * (then d_status[0] = 1 and the kernel ends: a lost peer cannot hang the device); afterwards, if d_ack is not NULL,
  * stores ack_value there (the destination telling the peers which epoch it has consumed). */
+/* Staged gather: stream min(*d_n, cap_rows) compacted rows (56 B) and contact records (48 B, optional) from local memory
+ * into a peer-mapped destination with a thin grid of `n_blocks` blocks (16-byte stores); enqueue it on an exchange stream
+ * behind the step, followed by bt_peer_signal.  All four buffers 16-byte aligned. */
+BT_API int bt_peer_push(const int64_t* d_n, int64_t cap_rows, const float* d_gs, const double* d_contacts, float* d_dst_gs,
+                        double* d_dst_contacts, int32_t n_blocks, void* stream);
+/* The same transfer by a copy engine (cudaMemcpyAsync, no SM): `bytes` of a padded buffer, for callers that accept moving
+ * the whole capacity instead of the counted rows. */
+BT_API int bt_peer_copy(void* d_dst, const void* d_src, int64_t bytes, void* stream);
 BT_API int bt_peer_signal(const int64_t* d_local_count, int64_t* d_count_slot, int64_t* d_flag_slot, int64_t epoch, void* stream);
 BT_API int bt_peer_wait(const int64_t* d_words, int32_t n_words, int64_t epoch, double timeout_s, int32_t* d_status,
                  int64_t* d_ack, int64_t ack_value, void* stream);

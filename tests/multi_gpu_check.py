@@ -4,7 +4,8 @@ that wait for one another must not share a GPU, so this cannot run in the single
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 tests/multi_gpu_check.py
 
 Every rank runs STEPS batches of the AGS pipeline, several in flight on different streams, its compaction kernel storing
-the kept rows straight into rank 0's buffer over NVLink.  For EVERY step rank 0 compares what arrived (PeerGather.result)
+the kept rows straight into rank 0's buffer over NVLink (BT_PEER_TRANSPORT=direct) or its exchange stream pushing them there
+from the local compaction output (BT_PEER_TRANSPORT=staged).  For EVERY step rank 0 compares what arrived (PeerGather.result)
 with the ranks' locally computed rows sent through a plain NCCL gather, bit for bit.  Prints one JSON line on rank 0."""
 import json
 import os
@@ -37,8 +38,8 @@ def main():
         k = s % STREAMS
         seed = 1000 * (rank + 1) + s
         with torch.cuda.stream(streams[k]):
-            out = ags.run_pipeline(n_ref=N_REF, seed=seed, destinations=peer.destinations(), slot=k, graph=True)
-            epochs.append((peer.complete(out['n_free']), seed))
+            out = ags.run_pipeline(n_ref=N_REF, seed=seed, destinations=peer.destinations(slot=k), slot=k, graph=True)
+            epochs.append((peer.complete(out['n_free'], rows=out.get('free_gs'), contacts=out.get('free_contacts'), slot=k), seed))
         # verify with a lag of one step, so that two steps are always in flight while rank 0 reads an older one
         if len(epochs) >= 2 or s == STEPS - 1:
             for e, sd in (epochs[:-1] if s < STEPS - 1 else epochs):
@@ -56,7 +57,7 @@ def main():
     flag = torch.tensor([0.0 if (ok and not timed_out) else 1.0], device='cuda')
     dist.all_reduce(flag)
     if rank == 0:
-        print(json.dumps({'check': 'PeerGather one-sided, multi-stream', 'world': world, 'steps': STEPS, 'streams': STREAMS,
+        print(json.dumps({'check': 'PeerGather one-sided, multi-stream', 'transport': 'staged' if peer.staged else 'direct', 'world': world, 'steps': STEPS, 'streams': STREAMS,
                           'rows_compared': rows_seen, 'ok': bool(flag.item() == 0.0)}))
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 0.0 else 1)

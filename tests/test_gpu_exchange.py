@@ -133,3 +133,24 @@ def test_peer_gather_two_processes_share_a_buffer_through_ipc(one_sided):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results == {0: True, 1: True}
+
+
+def test_peer_push_copies_exactly_the_counted_rows():
+    """bt_peer_push (the staged gather's transfer kernel) with a device-side count: rows and contact records up to the
+    count arrive bit for bit, nothing behind them is touched; odd counts exercise the 8-byte tail of the 16-byte copy."""
+    import torch
+    from burg_toolkit_b200 import _native as nat
+    rng = np.random.default_rng(1)
+    cap = 4096
+    rows = torch.from_numpy(rng.normal(size=(cap, 14)).astype(np.float32)).cuda()
+    contacts = torch.from_numpy(rng.normal(size=(cap, 2, 3))).cuda()
+    for n, blocks in ((0, 1), (1, 1), (255, 3), (1001, 32), (cap, 8), (cap + 77, 4)):
+        dst_rows = torch.full((cap, 14), -1.0, dtype=torch.float32, device='cuda')
+        dst_contacts = torch.full((cap, 2, 3), -1.0, dtype=torch.float64, device='cuda')
+        count = torch.tensor([n], dtype=torch.int64, device='cuda')
+        nat.call('bt_peer_push', nat.ptr(count), cap, nat.ptr(rows), nat.ptr(contacts), nat.ptr(dst_rows), nat.ptr(dst_contacts),
+                 blocks, nat.current_stream())
+        torch.cuda.synchronize()
+        k = min(n, cap)
+        assert torch.equal(dst_rows[:k], rows[:k]) and torch.equal(dst_contacts[:k], contacts[:k])
+        assert bool((dst_rows[k:] == -1).all()) and bool((dst_contacts[k:] == -1).all())

@@ -13,6 +13,8 @@ def show(b, ind=''):
           '| single-stream %.4f' % c['single_stream_ms_per_step'] if 'single_stream_ms_per_step' in c else '',
           '| e2e %.3e (%.3f ms)' % (e.get('value', 0), e.get('ms_per_step', 0)) if e else '',
           '| serial %.3f' % e['serial']['ms_per_step'] if e.get('serial') else '', '| gather_verified %s' % b['gather_verified'] if 'gather_verified' in b else '')
+    if 'host_issue_ms_per_step' in c:
+        print(ind, '   host issue %.4f ms/step' % c['host_issue_ms_per_step'], '| by rank', c.get('ms_per_step_by_rank'), c.get('sm_mhz_by_rank'), '| other L2 method %.4f' % c['l2_other_method']['ms_per_step'] if 'l2_other_method' in c else '')
     if 'stage_ms' in b:
         print(ind, '   stages', {k: round(v, 4) for k, v in b['stage_ms'].items()})
     if 'launches_per_step' in b:
