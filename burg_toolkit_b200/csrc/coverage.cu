@@ -21,8 +21,8 @@
 namespace bt {
 
 constexpr int COV_THREADS = 256;
-constexpr int COV_RPT = 8;                       // reference rows per thread
-constexpr int COV_TILE = 1024;                   // queries staged per shared-memory tile (16 KB)
+constexpr int COV_RPT = 8;                       // reference rows per thread (16: measured 1.7x slower, 128 registers)
+constexpr int COV_TILE = 512;                    // queries staged per shared-memory tile (8 KB)
 
 struct CovParams {
     float eps;              // epsilon (float32 compare, metrics.py:157/:219)
@@ -58,23 +58,41 @@ __device__ __noinline__ bool pair_covered(const float* __restrict__ a, const flo
 }
 
 // ---- algo 0: all pairs, query tiles in shared memory ---------------------------------------------------------
-// Fast path per pair: 3 FFMA + 1 compare on the expanded form |q|^2 - 2 a.q <= r^2 - |a|^2 (centred coordinates).
-// Survivors (a few per thousand) are NOT evaluated in place -- that would leave one lane of a warp running the exact
-// recipe while 31 wait -- but appended to a shared-memory queue and drained by the whole block after each tile.
-constexpr int COV_QCAP = 4096;
+// Fast path per pair: 3 FFMA + 1 compare on the expanded form |q|^2 - 2 a.q <= r^2 - |a|^2 (centred coordinates); the
+// compares of a thread's COV_RPT rows against one query are OR-ed into two predicates (FSETP.LE.OR), so the hot loop is
+// one broadcast LDS.128 + 4 COV_RPT instructions + one branch per query.  A thread with a passing pair (the volume ratio
+// of the epsilon ball to the data: a few pairs per thousand, i.e. one warp in three per query) leaves the loop for exactly
+// two instructions -- one shared-memory atomic, one store of (thread, query) -- because a rare path run by one lane costs
+// the whole warp its issue slots.  After the tile the whole block drains the queue in two passes with all lanes busy:
+// (A) every entry repeats the conservative test of its COV_RPT rows from a shared-memory copy of the row constants and
+// queues the (row, query) pairs that pass, (B) every queued pair runs the exact recipe.  Round 1 sorted the rows out
+// inside the loop (15 compares per 8 pairs on the half-rate ALU pipe, ~70 instructions per divergent entry: 8.7 issued
+// instructions per pair); one drain pass that ran the exact recipe straight from the entries had 4 of 32 lanes in it.
+constexpr int COV_QCAP = 3072;                   // (thread, query) entries per tile: ~COV_THREADS * COV_RPT * COV_TILE * a few per thousand
+constexpr int COV_PCAP = 3072;                   // (row, query) pairs per tile that pass the conservative test
+
+struct CovTilesSmem {
+    float4 tile[COV_TILE];                                  // centred query translations + squared norm
+    float4 rows[COV_THREADS * COV_RPT];                     // the block's rows for the drain: (-2 x, -2 y, -2 z, threshold)
+    unsigned int queue[COV_QCAP];
+    unsigned int pairs[COV_PCAP];
+    unsigned char cov[COV_THREADS * COV_RPT];
+    int q_count, p_count;
+};
 
 __global__ void __launch_bounds__(COV_THREADS)
 coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ qry, int64_t n_qry,
                       int64_t q_per_split, const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
-    __shared__ float4 tile[COV_TILE];
-    __shared__ unsigned int queue[COV_QCAP];
-    __shared__ unsigned char s_cov[COV_THREADS * COV_RPT];
-    __shared__ int q_count;
-    const int64_t block_row0 = (int64_t)blockIdx.x * (COV_THREADS * COV_RPT);
+    constexpr int RPT = COV_RPT, TILE = COV_TILE;
+    extern __shared__ __align__(16) unsigned char cov_smem_raw[];
+    CovTilesSmem& S = *reinterpret_cast<CovTilesSmem*>(cov_smem_raw);
+    float4* tile = S.tile;
+    unsigned char* s_cov = S.cov;
+    const int64_t block_row0 = (int64_t)blockIdx.x * (COV_THREADS * RPT);
     // per-row constants of the expanded form (centred coordinates)
-    float ax[COV_RPT], ay[COV_RPT], az[COV_RPT], thr[COV_RPT];
+    float ax[RPT], ay[RPT], az[RPT], thr[RPT];
 #pragma unroll
-    for (int r = 0; r < COV_RPT; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         const int lr = threadIdx.x + r * COV_THREADS;
         const int64_t i = block_row0 + lr;
         s_cov[lr] = 0;
@@ -83,12 +101,27 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
             ax[r] = -2.0f * x; ay[r] = -2.0f * y; az[r] = -2.0f * z;
             thr[r] = P.r2_reject - fmaf(x, x, fmaf(y, y, z * z));
         } else { ax[r] = ay[r] = az[r] = 0.f; thr[r] = -1e30f; }
+        S.rows[lr] = make_float4(ax[r], ay[r], az[r], thr[r]);
     }
-    if (threadIdx.x == 0) q_count = 0;
+    if (threadIdx.x == 0) { S.q_count = 0; S.p_count = 0; }
+    // pass A for one (thread, query) entry: the conservative test of its rows again (same expression, same operands)
+    auto sort_out = [&](int t, int j, int64_t q0) {
+        const float4 q = tile[j];
+#pragma unroll 1
+        for (int r = 0; r < RPT; ++r) {
+            const int lr = t + r * COV_THREADS;
+            const float4 a = S.rows[lr];
+            if (fmaf(a.x, q.x, fmaf(a.y, q.y, fmaf(a.z, q.z, q.w))) <= a.w && !s_cov[lr]) {
+                const int pos = atomicAdd(&S.p_count, 1);
+                if (pos < COV_PCAP) S.pairs[pos] = ((unsigned)lr << 10) | (unsigned)j;
+                else if (pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
+            }
+        }
+    };
     const int64_t q_begin = (int64_t)blockIdx.y * q_per_split;
     const int64_t q_end = min(n_qry, q_begin + q_per_split);
-    for (int64_t q0 = q_begin; q0 < q_end; q0 += COV_TILE) {
-        const int cnt = (int)min((int64_t)COV_TILE, q_end - q0);
+    for (int64_t q0 = q_begin; q0 < q_end; q0 += TILE) {
+        const int cnt = (int)min((int64_t)TILE, q_end - q0);
         __syncthreads();
         for (int j = threadIdx.x; j < cnt; j += COV_THREADS) {
             const float* q = qry + 14 * (q0 + j);
@@ -96,42 +129,41 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
             tile[j] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
         }
         __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < cnt; ++j) {
             const float4 q = tile[j];
-            bool any = false;
-            bool pass[COV_RPT];
+            // two OR-chains (even / odd rows) so that the compares of one query do not form a single dependent chain
+            bool any0 = false, any1 = false;
 #pragma unroll
-            for (int r = 0; r < COV_RPT; ++r) {
-                const float s = fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w)));
-                pass[r] = s <= thr[r];
-                any |= pass[r];
+            for (int r = 0; r < RPT; r += 2) {
+                any0 |= fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w))) <= thr[r];
+                any1 |= fmaf(ax[r + 1], q.x, fmaf(ay[r + 1], q.y, fmaf(az[r + 1], q.z, q.w))) <= thr[r + 1];
             }
-            if (any) {
-#pragma unroll
-                for (int r = 0; r < COV_RPT; ++r) {
-                    if (pass[r]) {
-                        const int lr = threadIdx.x + r * COV_THREADS;
-                        const int pos = atomicAdd(&q_count, 1);
-                        if (pos < COV_QCAP) queue[pos] = ((unsigned)lr << 10) | (unsigned)j;
-                        else if (!s_cov[lr] && pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
-                    }
-                }
+            if (any0 | any1) {
+                const int pos = atomicAdd(&S.q_count, 1);
+                if (pos < COV_QCAP) S.queue[pos] = ((unsigned)threadIdx.x << 10) | (unsigned)j;
+                else sort_out(threadIdx.x, j, q0);
             }
         }
         __syncthreads();
-        const int n_q = min(q_count, COV_QCAP);
+        const int n_q = min(S.q_count, COV_QCAP);
         for (int e = threadIdx.x; e < n_q; e += COV_THREADS) {
-            const unsigned code = queue[e];
+            const unsigned code = S.queue[e];
+            sort_out((int)(code >> 10), (int)(code & 1023u), q0);
+        }
+        __syncthreads();
+        const int n_p = min(S.p_count, COV_PCAP);
+        for (int e = threadIdx.x; e < n_p; e += COV_THREADS) {
+            const unsigned code = S.pairs[e];
             const int lr = (int)(code >> 10), j = (int)(code & 1023u);
             if (!s_cov[lr] && pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
         }
         __syncthreads();
-        if (threadIdx.x == 0) q_count = 0;
+        if (threadIdx.x == 0) { S.q_count = 0; S.p_count = 0; }
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < COV_RPT; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         const int lr = threadIdx.x + r * COV_THREADS;
         const int64_t i = block_row0 + lr;
         if (i < n_ref && s_cov[lr]) covered[i] = 1;                  // all writers store the same value
@@ -283,8 +315,9 @@ coverage_grid_kernel(const float* __restrict__ ref, const int32_t* __restrict__ 
 constexpr int CELL_THREADS = 128;
 constexpr int CELL_RPT = 2;
 constexpr int CELL_REFS = CELL_THREADS * CELL_RPT;
-constexpr int CELL_TILE = 1024;
-constexpr int CELL_QCAP = 2048;
+constexpr int CELL_TILE = 768;                   // queries staged per tile (4 | CELL_TILE <= 1024: queue entries carry 10 bits of it)
+constexpr int CELL_QCAP = 1024;                  // queue entries = (thread, group of 4 queries) with a passing orientation bound
+constexpr int CELL_PCAP = 1024;                  // (row, query) pairs per tile that pass both conservative tests
 
 // Chunk table of the cell-tile kernel: the references in cell order are cut at every (x, y) column boundary and every
 // column into equal parts of at most CELL_REFS rows.  A chunk that straddled columns (as fixed 256-row chunks do) has a
@@ -324,6 +357,10 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
     __shared__ float4 tile_quat[CELL_TILE + 4];            // query orientations as unit quaternions (+ zero padding for the 4-wide loop)
     __shared__ int tile_id[CELL_TILE];
     __shared__ unsigned int queue[CELL_QCAP];
+    __shared__ unsigned int pairs[CELL_PCAP];
+    __shared__ int p_count;
+    __shared__ float4 s_rquat[CELL_REFS];                   // the chunk's rows for the drain: unit quaternion,
+    __shared__ float4 s_rpos[CELL_REFS];                    // (-2 x, -2 y, -2 z, threshold) of the centred translation test
     __shared__ unsigned char s_cov[CELL_REFS];
     __shared__ int s_box[6];                               // min x y z, max x y z (cell coordinates of the chunk)
     __shared__ int q_count;
@@ -332,7 +369,7 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
     const int64_t s0 = chunk.x;
     const int n_here = chunk.y - chunk.x;
     if (threadIdx.x < 3) { s_box[threadIdx.x] = 0x7fffffff; s_box[3 + threadIdx.x] = -1; }
-    if (threadIdx.x == 0) q_count = 0;
+    if (threadIdx.x == 0) { q_count = 0; p_count = 0; }
     __syncthreads();
     int64_t row[CELL_RPT];
     float px[CELL_RPT], py[CELL_RPT], pz[CELL_RPT];
@@ -369,7 +406,29 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
         ax[r] = -2.0f * x; ay[r] = -2.0f * y; az[r] = -2.0f * z;
         thr[r] = r2 - fmaf(x, x, fmaf(y, y, z * z));
         qmin[r] = row[r] >= 0 ? P.qdot_min : 2.0f;
+        s_rquat[threadIdx.x + r * CELL_THREADS] = quat[r];
+        s_rpos[threadIdx.x + r * CELL_THREADS] = make_float4(ax[r], ay[r], az[r], row[r] >= 0 ? thr[r] : -1e30f);
     }
+    // pass A of the drain for the 4 x CELL_RPT pairs of (thread t, queries j0 .. j0 + 3 of the staged tile): orientation
+    // bound and translation reject from shared memory, by whichever thread drains the entry; survivors -> pair queue
+    auto drain_group = [&](int t, int j0, int cnt) {
+#pragma unroll 1
+        for (int r = 0; r < CELL_RPT; ++r) {
+            const int lr = t + r * CELL_THREADS;
+            if (lr >= n_here || s_cov[lr]) continue;
+            const float4 rq = s_rquat[lr], rp = s_rpos[lr];
+#pragma unroll 1
+            for (int j = j0; j < min(j0 + 4, cnt); ++j) {
+                const float4 qq = tile_quat[j];
+                if (fabsf(fmaf(rq.x, qq.x, fmaf(rq.y, qq.y, fmaf(rq.z, qq.z, rq.w * qq.w)))) < P.qdot_min) continue;
+                const float4 q = tile[j];
+                if (fmaf(rp.x, q.x, fmaf(rp.y, q.y, fmaf(rp.z, q.z, q.w))) > rp.w) continue;
+                const int pos = atomicAdd(&p_count, 1);                 // pass B runs the exact recipe with all lanes busy
+                if (pos < CELL_PCAP) pairs[pos] = ((unsigned)lr << 10) | (unsigned)j;
+                else if (pair_covered(ref + 14 * (int64_t)ref_sorted_ids[s0 + lr], qry + 14 * (int64_t)tile_id[j], lut, P)) { s_cov[lr] = 1; break; }
+            }
+        }
+    };
     // this block's part of the neighbourhood (a chunk lies in one column, so x0..x1 and y0..y1 hold at most 3 values)
     int xa = x0, xb = x1, ya = y0, yb = y1;
     if (split == 3) { xa = xb = x0 + (int)blockIdx.y; }
@@ -403,58 +462,42 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
                 __syncthreads();
                 // In a grid walk ~15 % of the candidates pass the translation test but only ~0.1 % the rotation test, so the
                 // orientation bound goes FIRST here: |q1 . q2| = cos(angle / 2), 4 FMAs on the staged quaternions.  Four
-                // queries x CELL_RPT rows are evaluated branch-free (8 independent FMA chains); the rare passes are handled
-                // afterwards so that the hot loop has no control dependencies.
+                // queries x CELL_RPT rows are evaluated branch-free (8 independent FMA chains) with the compares OR-ed
+                // into one predicate; a thread with a passing pair only queues (thread, query group) -- one atomic, one
+                // store -- and the block sorts the group out after the tile with all lanes busy (a rare path run by one
+                // lane costs the warp its issue slots: round 1 recomputed the eight dot products there, 8.6 issued
+                // instructions per pair against a loop body of 5.9).
                 for (int j0 = 0; j0 < cnt; j0 += 4) {
                     float4 qq[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) qq[u] = tile_quat[j0 + u];
-                    // one compare-and-OR per pair (FSETP.GE.OR on |q_row . q_u|): true iff some pair passes the orientation bound
-                    bool any_pass = false;
+                    bool any_pass = false;                       // (|=, not ||: no short-circuit branches between the chains)
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
-                        for (int r = 0; r < CELL_RPT; ++r) {
-                            const float qd = fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)));
-                            any_pass |= fabsf(qd) >= qmin[r];
-                        }
-                    unsigned pass = 0;
+                        for (int r = 0; r < CELL_RPT; ++r)
+                            any_pass |= fabsf(fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)))) >= qmin[r];
                     if (any_pass) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int r = 0; r < CELL_RPT; ++r) {
-                                const float qd = fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)));
-                                pass |= (fabsf(qd) >= qmin[r] ? 1u : 0u) << (u * CELL_RPT + r);
-                            }
-                    }
-                    if (pass) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int r = 0; r < CELL_RPT; ++r) {
-                                const int j = j0 + u;
-                                if (!((pass >> (u * CELL_RPT + r)) & 1u) || j >= cnt) continue;
-                                const float4 q = tile[j];
-                                const float sv = fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w)));
-                                if (sv > thr[r]) continue;
-                                const int lr = threadIdx.x + r * CELL_THREADS;
-                                const int pos = atomicAdd(&q_count, 1);
-                                if (pos < CELL_QCAP) queue[pos] = ((unsigned)lr << 10) | (unsigned)j;
-                                else if (!s_cov[lr] && pair_covered(ref + 14 * row[r], qry + 14 * (int64_t)tile_id[j], lut, P)) s_cov[lr] = 1;
-                            }
+                        const int pos = atomicAdd(&q_count, 1);
+                        if (pos < CELL_QCAP) queue[pos] = ((unsigned)threadIdx.x << 10) | (unsigned)j0;
+                        else drain_group(threadIdx.x, j0, cnt);
                     }
                 }
                 __syncthreads();
                 const int n_q = min(q_count, CELL_QCAP);
                 for (int i = threadIdx.x; i < n_q; i += CELL_THREADS) {
                     const unsigned code = queue[i];
-                    const int lr = (int)(code >> 10), j = (int)(code & 1023u);
-                    const int64_t rr = ref_sorted_ids[s0 + lr];
-                    if (!s_cov[lr] && pair_covered(ref + 14 * rr, qry + 14 * (int64_t)tile_id[j], lut, P)) s_cov[lr] = 1;
+                    drain_group((int)(code >> 10), (int)(code & 1023u), cnt);
                 }
                 __syncthreads();
-                if (threadIdx.x == 0) q_count = 0;
+                const int n_p = min(p_count, CELL_PCAP);
+                for (int i = threadIdx.x; i < n_p; i += CELL_THREADS) {
+                    const unsigned code = pairs[i];
+                    const int lr = (int)(code >> 10), j = (int)(code & 1023u);
+                    if (!s_cov[lr] && pair_covered(ref + 14 * (int64_t)ref_sorted_ids[s0 + lr], qry + 14 * (int64_t)tile_id[j], lut, P)) s_cov[lr] = 1;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) { q_count = 0; p_count = 0; }
             }
         }
     __syncthreads();
@@ -805,7 +848,14 @@ extern "C" int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry
         int64_t q_per_split = ceil_div(ceil_div(n_qry, splits), COV_TILE) * COV_TILE;
         splits = ceil_div(n_qry, q_per_split);
         dim3 grid((unsigned)row_blocks, (unsigned)splits);
-        coverage_tiles_kernel<<<grid, COV_THREADS, 0, st>>>(d_ref, n_ref, d_qry, n_qry, q_per_split, d_lut, P, d_covered);
+        static bool smem_opt_in[64] = {};                   // > 48 KB of shared memory per block: opt in once per device
+        int dev = 0;
+        BT_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !smem_opt_in[dev]) {
+            BT_CUDA(cudaFuncSetAttribute(coverage_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CovTilesSmem)));
+            if (dev >= 0 && dev < 64) smem_opt_in[dev] = true;
+        }
+        coverage_tiles_kernel<<<grid, COV_THREADS, sizeof(CovTilesSmem), st>>>(d_ref, n_ref, d_qry, n_qry, q_per_split, d_lut, P, d_covered);
         BT_LAUNCH_CHECK();
     }
     count_covered_kernel<<<148, 256, 0, st>>>(d_covered, n_ref, reinterpret_cast<unsigned long long*>(d_count));
