@@ -85,6 +85,7 @@ _SIGNATURES = {
     'bt_sample_surface': (C.c_int, [_P, C.c_int64, C.c_uint64, _P, _P, _P, _P]),
     'bt_poisson_disk_eliminate': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _P, C.POINTER(C.c_int32), _P]),
     'bt_cone_rays': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_uint64, _P, _P]),
+    'bt_cone_rays_ex': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_uint64, _P, _P]),
     'bt_random_unit_vectors': (C.c_int, [C.c_int64, C.c_uint64, _P, _P]),
     'bt_ags_cast': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(AgsParams), _P, _P, _P, _P, _P]),
     'bt_ags_select': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P, _P, _P, _P,

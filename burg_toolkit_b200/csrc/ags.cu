@@ -601,11 +601,12 @@ __global__ void sample_surface_kernel(const double* __restrict__ cdf, const int3
 
 // ---- S2 ------------------------------------------------------------------------------------------------
 // ray i (= ref * n_rays + r) of the friction cone about -normal  (sampling.py:17-48, util.py:7-29)
-__device__ __forceinline__ d3 cone_ray(d3 normal, int64_t ref, int64_t i, double angle, uint64_t seed) {
+__device__ __forceinline__ d3 cone_ray(d3 normal, int64_t ref, int64_t i, double angle, uint64_t seed, bool uniform_on_plane = false) {
     uint32_t r[4];
     philox4x32(seed, (uint64_t)i, 0x434f4e45ull, r);
     const double az = u01(r[0], r[1]) * (2.0 * 3.14159265358979323846);      // U(0, 2 pi)   sampling.py:32
-    const double inc = u01(r[2], r[3]) * angle;                               // U(0, angle)  sampling.py:36
+    const double inc = uniform_on_plane ? atan(u01(r[2], r[3]) * tan(angle))   // arctan(U(0, tan(angle)))  sampling.py:34
+                                        : u01(r[2], r[3]) * angle;             // U(0, angle)  sampling.py:36
     double si, ci, sa, ca;
     sincos(inc, &si, &ci);
     sincos(az, &sa, &ca);
@@ -627,11 +628,11 @@ __device__ __forceinline__ d3 cone_ray(d3 normal, int64_t ref, int64_t i, double
 }
 
 __global__ void cone_rays_kernel(const double* __restrict__ normals, int64_t n_ref, int n_rays, double angle,
-                                 uint64_t seed, double* __restrict__ dirs) {
+                                 uint64_t seed, int uniform_on_plane, double* __restrict__ dirs) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_ref * n_rays) return;
     const int64_t ref = i / n_rays;
-    st3(dirs + 3 * i, cone_ray(ld3(normals + 3 * ref), ref, i, angle, seed));
+    st3(dirs + 3 * i, cone_ray(ld3(normals + 3 * ref), ref, i, angle, seed, uniform_on_plane != 0));
 }
 
 // util.generate_random_unit_vector (util.py:32-43): normalised N(0,1)^3, redrawn while shorter than 1e-5
@@ -1030,15 +1031,21 @@ extern "C" int bt_sample_surface(const bt_mesh* mesh, int64_t n, uint64_t seed, 
     return BT_OK;
 }
 
-extern "C" int bt_cone_rays(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed,
-                            double* d_dirs, void* stream) {
+extern "C" int bt_cone_rays_ex(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, int32_t uniform_on_plane,
+                               uint64_t seed, double* d_dirs, void* stream) {
     BT_REQUIRE(d_normals && d_dirs, "null pointer");
     BT_REQUIRE(n_ref >= 0 && n_rays > 0, "bad counts");
+    BT_REQUIRE(!uniform_on_plane || (angle >= 0.0 && angle < 1.5707), "uniform_on_plane needs a cone half-angle below pi/2");
     if (n_ref == 0) return BT_OK;
     cone_rays_kernel<<<(unsigned)ceil_div(n_ref * n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
-        d_normals, n_ref, n_rays, angle, seed, d_dirs);
+        d_normals, n_ref, n_rays, angle, seed, uniform_on_plane, d_dirs);
     BT_LAUNCH_CHECK();
     return BT_OK;
+}
+
+extern "C" int bt_cone_rays(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed,
+                            double* d_dirs, void* stream) {
+    return bt_cone_rays_ex(d_normals, n_ref, n_rays, angle, 0, seed, d_dirs, stream);
 }
 
 extern "C" int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, void* stream) {

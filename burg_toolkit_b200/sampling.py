@@ -199,14 +199,16 @@ class AntipodalGraspSampler:
             sel = keep.bool()
             return pts[sel].contiguous(), nrm[sel].contiguous()
 
-    def cone_rays(self, ref_normals, seed):
-        """S2: [n_ref, n_rays, 3] directions in the friction cone about ``-normal`` (device RNG)."""
+    def cone_rays(self, ref_normals, seed, uniform_on_plane=False):
+        """S2: [n_ref, n_rays, 3] directions in the friction cone about ``-normal`` (device RNG).  ``uniform_on_plane``:
+        the reference's option of ``rays_within_cone`` (sampling.py:33-34) -- rays uniform on the cone's ground plane
+        instead of uniform in the angle (the sampler itself uses the default, like the reference's sample())."""
         torch = nat.require_cuda()
         nrm = self._tensor(ref_normals, torch.float64)
         with torch.cuda.device(nrm.device):
             dirs = torch.empty((nrm.shape[0], self.n_rays, 3), dtype=torch.float64, device=nrm.device)
-            nat.call('bt_cone_rays', nat.ptr(nrm), nrm.shape[0], int(self.n_rays), float(np.arctan(self.mu)),
-                     int(seed), nat.ptr(dirs), nat.current_stream())
+            nat.call('bt_cone_rays_ex', nat.ptr(nrm), nrm.shape[0], int(self.n_rays), float(np.arctan(self.mu)),
+                     int(bool(uniform_on_plane)), int(seed), nat.ptr(dirs), nat.current_stream())
         return dirs
 
     def cast(self, ref_points, directions, cap=None, retry_on_overflow=True):

@@ -137,6 +137,10 @@ BT_API int bt_poisson_disk_eliminate(const double* d_pts, int64_t n0, int64_t n_
  * axis = -normal).  d_normals: [n_ref,3] f64, d_dirs: [n_ref,n_rays,3] f64. */
 BT_API int bt_cone_rays(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, uint64_t seed,
                  double* d_dirs, void* stream);
+/* the same with the reference's `uniform_on_plane` option (sampling.py:33-34): inclination = arctan(U(0, tan(angle))),
+ * i.e. the rays are uniform on the ground plane of the cone instead of uniform in the angle */
+BT_API int bt_cone_rays_ex(const double* d_normals, int64_t n_ref, int32_t n_rays, double angle, int32_t uniform_on_plane,
+                 uint64_t seed, double* d_dirs, void* stream);
 
 /* random unit vectors (util.generate_random_unit_vector, util.py:32-43): normalised N(0,1)^3; [n,3] f64 */
 BT_API int bt_random_unit_vectors(int64_t n, uint64_t seed, double* d_out, void* stream);

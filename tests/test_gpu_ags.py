@@ -227,3 +227,31 @@ def test_surface_sampler_is_area_weighted():
     assert np.allclose(np.linalg.norm(dirs, axis=-1), 1.0, atol=1e-12)
     cosang = np.einsum('rkc,rc->rk', dirs, -nrm[:500])
     assert (cosang >= np.cos(np.arctan(0.25)) - 1e-12).all() and cosang.min() < np.cos(np.arctan(0.25) * 0.98)
+
+
+def test_device_cone_rays_uniform_on_plane():
+    """bt_cone_rays_ex: the reference's two inclination laws (sampling.py:33-36).  Default: inclination ~ U(0, angle);
+    uniform_on_plane: tan(inclination) ~ U(0, tan(angle)).  Same azimuths (same Philox draws), unit length, inside the cone."""
+    from burg_toolkit_b200 import mesh as bmesh
+    from test_gpu_fullsize import make_sampler
+    ags = make_sampler(bmesh.create_icosphere(2, 0.03))
+    ags.n_rays = 200
+    rng = np.random.default_rng(4)
+    nrm = rng.normal(size=(400, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[0] = [0.0, 0.0, 1.0]                                              # axis == -z: the degenerate branch of the alignment
+    angle = np.arctan(ags.mu)
+    a = ags.cone_rays(nrm, seed=9).cpu().numpy()
+    b = ags.cone_rays(nrm, seed=9, uniform_on_plane=True).cpu().numpy()
+    for d in (a, b):
+        assert np.allclose(np.linalg.norm(d, axis=-1), 1.0, atol=1e-12)
+    inc_a = np.arccos(np.clip(np.einsum('rkc,rc->rk', a, -nrm), -1, 1))
+    inc_b = np.arccos(np.clip(np.einsum('rkc,rc->rk', b, -nrm), -1, 1))
+    assert inc_a.max() <= angle + 1e-9 and inc_b.max() <= angle + 1e-9
+    # the same uniform draw u behind both: inc_a = u * angle, inc_b = arctan(u * tan(angle))   (1e-7: arccos near 0)
+    u = inc_a / angle
+    assert np.allclose(inc_b, np.arctan(u * np.tan(angle)), atol=2e-7)
+    assert abs(u.mean() - 0.5) < 0.01 and abs((np.tan(inc_b) / np.tan(angle)).mean() - 0.5) < 0.01
+    # same azimuth: the two rays of a pair and the axis are coplanar
+    tri = np.einsum('rkc,rkc->rk', np.cross(a, b), np.broadcast_to(nrm[:, None, :], a.shape))
+    assert np.abs(tri).max() < 1e-9

@@ -61,7 +61,7 @@ def main(path):
         data['cast_stage'] = {'dram_bytes_per_launch': t['dram_bytes_per_launch'] + c['dram_bytes_per_launch'],
                               'source': f"{rel}: traverse_kernel {t['dram_read_bytes'] / 1e6:.1f} MB read + {t['dram_write_bytes'] / 1e6:.1f} MB written, "
                                         f"cast_kernel {c['dram_read_bytes'] / 1e6:.1f} MB read + {c['dram_write_bytes'] / 1e6:.1f} MB written "
-                                        '(first captured launch of each, L2 flushed before the step; lean pipeline: valid masks + ray parameters, no hit records)'}
+                                        '(first captured launch of each, another object walked in between; lean pipeline: valid masks + ray parameters, no hit records)'}
     with open(out_path, 'w') as fh:
         json.dump(data, fh, indent=2)
         fh.write('\n')
