@@ -381,6 +381,8 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
     ags.gripper, ags.verbose, ags.device = ParallelJawGripper(), False, local_rank
     ags.n_orientations, ags.n_rays = N_ORIENT, N_RAYS
     ags.max_targets_per_ref_point = EXHAUSTIVE_TARGETS if exhaustive else 1
+    if os.environ.get('BT_HOST_TRANSPORT'):                 # A/B knob: 'store' | 'dma'
+        ags.host_transport = os.environ['BT_HOST_TRANSPORT']
     targets, scene_meshes = ags_workload_meshes(workload)
     mesh = targets[0]
     pipe_kw = {} if scene_meshes is None else {'additional_objects': scene_meshes, 'exclude_shape': True}
@@ -592,9 +594,11 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
         def host_call(fn, b, **kw):
             ags.mesh = targets[b % len(targets)]
             return fn(*host_batches[b % n_hb], **kw, **pipe_kw)
-        for w in range(max(warmup, 2, n_hb)):
-            host_call(ags.evaluate_host, w, seed=w + 1)
-            host_call(ags.submit_host, w, seed=w + 1, slot=1).result()
+        n_slots = max(2, int(ctx.args.e2e_slots))
+        for w in range(max(warmup, 2, n_hb) * n_slots):            # every (object, slot) pair of the timed loops: graphs captured
+            if w % n_slots == 0:
+                host_call(ags.evaluate_host, w // n_slots, seed=w + 1)
+            host_call(ags.submit_host, w // n_slots, seed=w + 1, slot=w % n_slots).result()
         ctx.barrier()
         serial_s, h2d, d2h = 0.0, 0, 0
         for s in range(steps):
@@ -606,22 +610,23 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
             serial_s += time.perf_counter() - t0
             h2d, d2h = res['h2d_bytes'], res['d2h_bytes']
         ctx.barrier()
+        from collections import deque
         t0 = time.perf_counter()
-        pending = host_call(ags.submit_host, 0, seed=11, slot=0)
-        got = 0
-        for s in range(1, steps):
-            nxt = host_call(ags.submit_host, s, seed=s + 11, slot=s & 1)
-            got += pending.result()['n_free']
-            pending = nxt
-        got += pending.result()['n_free']
+        pending, got = deque(), 0
+        for s in range(steps):
+            if len(pending) == n_slots:                             # a slot is resubmitted only after its result has been taken
+                got += pending.popleft().result()['n_free']
+            pending.append(host_call(ags.submit_host, s, seed=s + 11, slot=s % n_slots))
+        while pending:
+            got += pending.popleft().result()['n_free']
         pipelined_s = time.perf_counter() - t0
         ctx.barrier()
         pipe_ms = ctx.max_over_ranks(pipelined_s * 1e3)
         serial_ms = ctx.max_over_ranks(serial_s * 1e3)
         e2e = {'value': candidates / (pipe_ms * 1e-3), 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                'ms_per_step': pipe_ms / steps, 'clock': 'host wall clock (time.perf_counter) around submit ... result',
-               'mode': 'AntipodalGraspSampler.submit_host on two alternating slots (one batch in flight while the next is submitted); '
-                       'every batch: pinned staging copy, H2D, graph-replayed pipeline, kept rows stored into pinned host memory by the compaction kernel',
+               'mode': f'AntipodalGraspSampler.submit_host on {n_slots} slots in turn (a slot is resubmitted after its result has been taken, so up to {n_slots} batches are in flight); '
+                       'every batch: pinned staging copy, H2D, graph-replayed pipeline, ' + ('result buffers (padded to the capacity) moved into pinned host memory by a copy engine' if ags.host_transport == 'dma' else 'kept rows stored into pinned host memory by the compaction kernel'),
                'serial': {'value': candidates / (serial_ms * 1e-3), 'ms_per_step': serial_ms / steps,
                           'mode': 'AntipodalGraspSampler.evaluate_host, one synchronous call per batch (' + l2_desc + ')'},
                'rows_received_per_step': got / steps}
@@ -892,13 +897,14 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='ags_c3', choices=['ags_c1', 'ags_c3', 'ags_c3_exhaustive', 'ags_c4', 'coverage_c2', 'coverage_c5'])
     ap.add_argument('--cpu-ref-points', type=int, default=100_000, help='reference points per CPU sample (x100 rays)')
     ap.add_argument('--cpu-coverage-n', type=int, default=100_000)
     ap.add_argument('--streams', type=int, default=4, help='AGS workloads: batches in flight per GPU (round-robin streams)')
+    ap.add_argument('--e2e-slots', type=int, default=8, help='AGS workloads: host batches in flight in the pipelined end-to-end measurement')
     ap.add_argument('--l2', default='rotate', choices=['rotate', 'flush'], help='AGS workloads: how L2 is kept cold between steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='ags_c3 only: skip the blocks of the other configurations')

@@ -36,11 +36,16 @@ def test_evaluate_host_equals_device_pipeline():
     assert 0 < len(rows) < n_grasps                                     # some grasps collide, some do not
     pinned = {}
     for _ in range(2):                                                  # second call reuses the pinned buffers
-        res = ags.evaluate_host(pts, nrm, seed=0, pinned=pinned, directions=dirs, frame_vecs=fv)
+        res = ags.evaluate_host(pts, nrm, seed=0, pinned=pinned, directions=dirs, frame_vecs=fv, host_transport='store')
         assert res['n_free'] == len(rows) and res['n_grasps'] == n_grasps
         assert np.array_equal(res['gs']._gs_array, rows)
         assert np.array_equal(res['contacts'], contacts)
-        assert res['d2h_bytes'] == len(rows) * 104 + 16
+        assert res['d2h_bytes'] == len(rows) * 104 + 16                # the compaction kernel stored exactly the kept rows
+    # the copy-engine transport (local compaction + padded D2H copies; the default) returns the same rows
+    assert ags.host_transport == 'dma'                                 # the default
+    res = ags.evaluate_host(pts, nrm, seed=0, directions=dirs, frame_vecs=fv)
+    assert res['n_free'] == len(rows) and res['n_grasps'] == n_grasps and res['d2h_bytes'] == len(pts) * 12 * 104 + 16
+    assert np.array_equal(res['gs']._gs_array, rows) and np.array_equal(res['contacts'], contacts)
     # collide + compact over row ranges on two streams: same bytes, same order
     for splits in (1, 2, 3, 8):
         res = ags.evaluate_host(pts, nrm, seed=0, pinned=pinned, tail_splits=splits, directions=dirs, frame_vecs=fv)
