@@ -136,6 +136,37 @@ def test_c3_one_million_candidates_properties():
     assert np.array_equal(coll1[idx].astype(bool), cport.collide(cm, rows1[idx], ags.gripper.tcp_triangles(), 0.08, 0.01))
 
 
+def test_c3_one_million_candidates_bit_exact_against_the_oracle():
+    """the bench workload at its full size, every candidate: 10 000 device-sampled reference points x 100 device-generated
+    cone rays through the lean, cone-culling, graph-replayed pipeline; the SAME points / rays / frame vectors (read back) through
+    the C oracle.  Seed 0 = canonical target choice (first valid hit), as the oracle takes it.  Pairs, float32 rows, contacts
+    and all 120 000 collision flags must be the same bits."""
+    from burg_toolkit_b200 import synthetic
+    mesh = synthetic.c3_mesh()
+    ags = make_sampler(mesh)
+    n_ref = 10_000
+    outs = [ags.run_pipeline(n_ref=n_ref, seed=0, graph=g, slot=int(g)) for g in (False, True)]
+    out = outs[1]
+    assert out['n_candidates'] == 1_000_000 and int(out['overflow'].item()) == 0
+    pts, dirs, fv = out['ref_pts'].cpu().numpy()[:n_ref], out['directions'].cpu().numpy()[:n_ref], out['frame_vecs'].cpu().numpy()[:n_ref]
+    assert np.allclose(np.linalg.norm(dirs, axis=-1), 1.0, atol=1e-12)
+    cm = cport.Mesh(mesh.vertices, mesh.triangles, mesh.vertex_normals)
+    want = cport.pipeline(cm, cm, pts, dirs.reshape(n_ref, N_RAYS, 3), fv, ags.gripper.tcp_triangles(), max_hits_per_ray=8)
+    have = want['pair_count'] > 0
+    assert np.array_equal(out['pair_count'].cpu().numpy()[:n_ref], want['pair_count'])
+    n_rows = int(out['n_grasps'].item())
+    assert n_rows == 12 * int(have.sum()) and n_rows > 100_000
+    rows = out['gs'][:n_rows].cpu().numpy()
+    assert np.array_equal(rows, want['rows'].reshape(n_ref, 12, 14)[have].reshape(-1, 14))
+    assert np.array_equal(out['contacts'][:n_rows].cpu().numpy(), want['contacts'].reshape(n_ref, 12, 2, 3)[have].reshape(-1, 2, 3))
+    coll = out['colliding'][:n_rows].cpu().numpy().astype(bool)
+    assert np.array_equal(coll, want['colliding'].reshape(n_ref, 12)[have].reshape(-1))
+    k = int(out['n_free'].item())
+    assert k == int((~coll).sum()) and np.array_equal(out['free_gs'][:k].cpu().numpy(), rows[~coll])
+    # the plain (not graph-replayed) call on another workspace: the same bits
+    assert np.array_equal(outs[0]['gs'][:n_rows].cpu().numpy(), rows) and np.array_equal(outs[0]['colliding'][:n_rows].cpu().numpy().astype(bool), coll)
+
+
 def test_c4_cluttered_scene_collisions():
     """config 4: 20 objects (~1 M triangles) + ground slab; grasps on one object, gripper vs the WHOLE scene."""
     from burg_toolkit_b200 import synthetic
@@ -167,7 +198,7 @@ def test_c5_coverage_one_million():
     grid = metrics.covered_mask(dref, dqry, algo='grid')
     tiles = metrics.covered_mask(dref[:200_000], dqry, algo='tiles')
     assert np.array_equal(grid[:200_000], tiles)
-    idx = np.random.default_rng(1).choice(len(ref), 400, replace=False)
+    idx = np.random.default_rng(1).choice(len(ref), 5000, replace=False)
     assert np.array_equal(grid[idx], port.covered_kd(ref[idx], qry))
     half = metrics.covered_mask(dref, dqry[:500_000], algo='grid')
     assert not (half & ~grid).any() and half.sum() < grid.sum()
