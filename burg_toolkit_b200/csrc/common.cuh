@@ -109,6 +109,45 @@ __device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
 }
 #endif
 
+// ---- packed float32 pairs (Blackwell FFMA2 / FMUL2: fma.rn.f32x2, mul.rn.f32x2) -----------------------------------------
+// One instruction, two IEEE round-to-nearest results per lane -- each half is bit-identical to the scalar fmaf / product
+// of the same operands, so a kernel may pair independent chains freely.  The kernels that are bound by FP32 *issue* (the
+// coverage hot loops: 3-4 multiply-adds + one compare per pair) halve their multiply-add instructions this way.  A pair
+// lives in a 64-bit register (an aligned even/odd register pair): lo = bits 0..31, hi = bits 32..63.
+// BT_F32X2=0 builds the same kernels with two scalar instructions per pair (A/B runs, tools/gpu_runs).
+#ifndef BT_F32X2
+#define BT_F32X2 1
+#endif
+#ifdef __CUDACC__
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ f32x2 dup2(float x) { return pack2(x, x); }        // ptxas folds it into the .F32 broadcast operand form
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+#if BT_F32X2
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+#else
+    return pack2(__fmaf_rn(lo2(a), lo2(b), lo2(c)), __fmaf_rn(hi2(a), hi2(b), hi2(c)));
+#endif
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+#if BT_F32X2
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+#else
+    return pack2(__fmul_rn(lo2(a), lo2(b)), __fmul_rn(hi2(a), hi2(b)));
+#endif
+}
+#endif
+
 // ---- exclusive scan of a short array by ONE 1024-thread block: out[i] = in[0] + ... + in[i-1] (and out[n] = total if
 // write_total).  The scans of the pipeline are short (pair counts per reference point, kept rows per compaction block:
 // 10^2 .. 10^5 entries), where a device-wide scan is two launches of mostly launch latency; beyond BT_SMALL_SCAN_MAX the

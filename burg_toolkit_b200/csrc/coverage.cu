@@ -57,53 +57,104 @@ __device__ __noinline__ bool pair_covered(const float* __restrict__ a, const flo
     return __fadd_rn(wd, deg) <= P.eps;
 }
 
+// unit quaternion (x, y, z, w) of a float32 rotation block (row-major 9 floats); approximate (used only for a conservative
+// bound): |q1 . q2| = cos(angle(R1 R2^T) / 2)
+__device__ __forceinline__ float4 quat_of(const float* __restrict__ R) {
+    const float m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8];
+    const float tr = m00 + m11 + m22;
+    float x, y, z, w;
+    if (tr > 0.f) { w = tr + 1.f; x = m21 - m12; y = m02 - m20; z = m10 - m01; }
+    else if (m00 > m11 && m00 > m22) { x = 1.f + m00 - m11 - m22; w = m21 - m12; y = m01 + m10; z = m02 + m20; }
+    else if (m11 > m22) { y = 1.f + m11 - m00 - m22; w = m02 - m20; x = m01 + m10; z = m12 + m21; }
+    else { z = 1.f + m22 - m00 - m11; w = m10 - m01; x = m02 + m20; y = m12 + m21; }
+    const float inv = rsqrtf(fmaxf(x * x + y * y + z * z + w * w, 1e-30f));
+    return make_float4(x * inv, y * inv, z * inv, w * inv);
+}
+
+// The orientation bound |q1 . q2| >= cos((eps + 0.1 deg) / 2) of both algorithms presumes rotation matrices: a row whose
+// 3 x 3 block is not orthonormal to 1e-4 (or not finite, or a reflection) gets a NaN quaternion, which no comparison of
+// the kernels rules out -- its pairs always reach the exact recipe, whatever the block holds.
+__device__ __forceinline__ float4 quat_checked(const float* __restrict__ R) {
+    float dev = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+            const float d = fmaf(R[3 * a], R[3 * b], fmaf(R[3 * a + 1], R[3 * b + 1], R[3 * a + 2] * R[3 * b + 2])) - (a == b ? 1.f : 0.f);
+            dev = fmaxf(dev, fabsf(d));
+        }
+    const float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+    if (!(dev <= 1e-4f) || !(det > 0.f)) return make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    return quat_of(R);
+}
+
+// quaternions of all rows, once per call of the all-pairs kernel
+__global__ void row_quat_kernel(const float* __restrict__ rows, int64_t n, float4* __restrict__ quat) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) quat[i] = quat_checked(rows + 14 * i + 3);
+}
+
 // ---- algo 0: all pairs, query tiles in shared memory ---------------------------------------------------------
-// Fast path per pair: 3 FFMA + 1 compare on the expanded form |q|^2 - 2 a.q <= r^2 - |a|^2 (centred coordinates); the
-// compares of a thread's COV_RPT rows against one query are OR-ed into two predicates (FSETP.LE.OR), so the hot loop is
-// one broadcast LDS.128 + 4 COV_RPT instructions + one branch per query.  A thread with a passing pair (the volume ratio
-// of the epsilon ball to the data: a few pairs per thousand, i.e. one warp in three per query) leaves the loop for exactly
-// two instructions -- one shared-memory atomic, one store of (thread, query) -- because a rare path run by one lane costs
-// the whole warp its issue slots.  After the tile the whole block drains the queue in two passes with all lanes busy:
-// (A) every entry repeats the conservative test of its COV_RPT rows from a shared-memory copy of the row constants and
-// queues the (row, query) pairs that pass, (B) every queued pair runs the exact recipe.  Round 1 sorted the rows out
-// inside the loop (15 compares per 8 pairs on the half-rate ALU pipe, ~70 instructions per divergent entry: 8.7 issued
-// instructions per pair); one drain pass that ran the exact recipe straight from the entries had 4 of 32 lanes in it.
-constexpr int COV_QCAP = 3072;                   // (thread, query) entries per tile: ~COV_THREADS * COV_RPT * COV_TILE * a few per thousand
-constexpr int COV_PCAP = 3072;                   // (row, query) pairs per tile that pass the conservative test
+// Fast path per pair: 3 multiply-adds + 1 compare on the expanded form |q|^2 - 2 a.q <= r^2 - |a|^2 (centred coordinates).
+// Rows r and r + 1 of a thread live in packed registers, so the multiply-adds of two pairs are three FFMA2 (Blackwell's
+// fma.rn.f32x2; the query's components enter as broadcast operands); the compares of a thread's
+// COV_RPT rows against one query are OR-ed into two predicates.  The hot loop has NO branch: a thread with a passing pair
+// (the volume ratio of the epsilon ball to the data: a few pairs per thousand, i.e. one warp in three per query) appends
+// the query's index to its OWN short list in shared memory -- one predicated 16-bit store and one predicated add -- so
+// per query a thread issues 1 LDS.128 + 12 FFMA2 + 8 FSETP + 5 = 26 instructions for 8 pairs (round 1: 70 with the rows
+// sorted out inside the loop; round 2's first version: 36 + a divergent queue push of ~18 in every third warp).
+// After the tile every WARP drains the lists of its 32 threads with all lanes busy (prefix sum of the list lengths by
+// shuffles, entry e -> (owner, k) by a 5-step search over the prefix): (A) every entry repeats the conservative test of
+// its COV_RPT rows from a shared-memory copy of the row constants and queues the (row, query) pairs that pass, (B) the
+// block runs the exact recipe on every queued pair.  A list that overflows (far denser data than the epsilon ball
+// suggests) makes its thread sort out all queries of the tile for its own rows: slow, never wrong.
+constexpr int COV_LCAP = 24;                     // list entries per thread and tile (mean ~7 at 100k x 100k in a 0.2 m cube)
+constexpr int COV_PCAP = 2048;                   // (row, query) pairs per tile that pass both conservative tests
 
 struct CovTilesSmem {
     float4 tile[COV_TILE];                                  // centred query translations + squared norm
+    float4 tile_quat[COV_TILE];                             // query orientations (pass A's orientation bound)
     float4 rows[COV_THREADS * COV_RPT];                     // the block's rows for the drain: (-2 x, -2 y, -2 z, threshold)
-    unsigned int queue[COV_QCAP];
+    unsigned short lists[COV_LCAP][COV_THREADS];            // per thread: tile indices of the queries with a passing pair
     unsigned int pairs[COV_PCAP];
     unsigned char cov[COV_THREADS * COV_RPT];
-    int q_count, p_count;
+    int p_count;
 };
 
-__global__ void __launch_bounds__(COV_THREADS)
+__global__ void __launch_bounds__(COV_THREADS, 3)
 coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ qry, int64_t n_qry,
+                      const float4* __restrict__ ref_quat, const float4* __restrict__ qry_quat,
                       int64_t q_per_split, const float* __restrict__ lut, CovParams P, uint8_t* __restrict__ covered) {
     constexpr int RPT = COV_RPT, TILE = COV_TILE;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char cov_smem_raw[];
     CovTilesSmem& S = *reinterpret_cast<CovTilesSmem*>(cov_smem_raw);
     float4* tile = S.tile;
     unsigned char* s_cov = S.cov;
     const int64_t block_row0 = (int64_t)blockIdx.x * (COV_THREADS * RPT);
-    // per-row constants of the expanded form (centred coordinates)
-    float ax[RPT], ay[RPT], az[RPT], thr[RPT];
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    // per-row constants of the expanded form (centred coordinates); rows r and r + 1 of a thread share packed registers
+    // (lo = row r, hi = row r + 1)
+    f32x2 ax2[RPT / 2], ay2[RPT / 2], az2[RPT / 2];
+    float thr[RPT];
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int lr = threadIdx.x + r * COV_THREADS;
-        const int64_t i = block_row0 + lr;
-        s_cov[lr] = 0;
-        if (i < n_ref) {
-            const float x = ref[14 * i] - P.cx, y = ref[14 * i + 1] - P.cy, z = ref[14 * i + 2] - P.cz;
-            ax[r] = -2.0f * x; ay[r] = -2.0f * y; az[r] = -2.0f * z;
-            thr[r] = P.r2_reject - fmaf(x, x, fmaf(y, y, z * z));
-        } else { ax[r] = ay[r] = az[r] = 0.f; thr[r] = -1e30f; }
-        S.rows[lr] = make_float4(ax[r], ay[r], az[r], thr[r]);
+    for (int r = 0; r < RPT; r += 2) {
+        float c[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int lr = threadIdx.x + (r + u) * COV_THREADS;
+            const int64_t i = block_row0 + lr;
+            s_cov[lr] = 0;
+            if (i < n_ref) {
+                const float x = ref[14 * i] - P.cx, y = ref[14 * i + 1] - P.cy, z = ref[14 * i + 2] - P.cz;
+                c[u][0] = -2.0f * x; c[u][1] = -2.0f * y; c[u][2] = -2.0f * z;
+                thr[r + u] = P.r2_reject - fmaf(x, x, fmaf(y, y, z * z));
+            } else { c[u][0] = c[u][1] = c[u][2] = 0.f; thr[r + u] = -1e30f; }
+            S.rows[lr] = make_float4(c[u][0], c[u][1], c[u][2], thr[r + u]);
+        }
+        ax2[r / 2] = pack2(c[0][0], c[1][0]); ay2[r / 2] = pack2(c[0][1], c[1][1]); az2[r / 2] = pack2(c[0][2], c[1][2]);
     }
-    if (threadIdx.x == 0) { S.q_count = 0; S.p_count = 0; }
+    if (threadIdx.x == 0) S.p_count = 0;
     // pass A for one (thread, query) entry: the conservative test of its rows again (same expression, same operands)
     auto sort_out = [&](int t, int j, int64_t q0) {
         const float4 q = tile[j];
@@ -112,6 +163,11 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
             const int lr = t + r * COV_THREADS;
             const float4 a = S.rows[lr];
             if (fmaf(a.x, q.x, fmaf(a.y, q.y, fmaf(a.z, q.z, q.w))) <= a.w && !s_cov[lr]) {
+                // a few pairs per thousand get here; only ~1 in 1000 of those is also close in orientation (the fraction
+                // of rotations within eps of a given one), so the orientation bound -- one 16-byte load per side instead
+                // of the exact recipe's 28 scattered floats -- empties the pair queue of nearly everything
+                const float4 rq = __ldg(ref_quat + block_row0 + lr), qq = S.tile_quat[j];
+                if (fabsf(fmaf(rq.x, qq.x, fmaf(rq.y, qq.y, fmaf(rq.z, qq.z, rq.w * qq.w)))) < P.qdot_min) continue;   // (NaN: not ruled out)
                 const int pos = atomicAdd(&S.p_count, 1);
                 if (pos < COV_PCAP) S.pairs[pos] = ((unsigned)lr << 10) | (unsigned)j;
                 else if (pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
@@ -127,29 +183,53 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
             const float* q = qry + 14 * (q0 + j);
             const float x = q[0] - P.cx, y = q[1] - P.cy, z = q[2] - P.cz;
             tile[j] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
+            S.tile_quat[j] = __ldg(qry_quat + q0 + j);
         }
         __syncthreads();
+        // next free entry of this thread's list, as a shared-memory address: the only state the hot loop carries
+        const unsigned slot0 = (unsigned)__cvta_generic_to_shared(&S.lists[0][threadIdx.x]);
+        const unsigned slot_end = slot0 + COV_LCAP * COV_THREADS * (unsigned)sizeof(unsigned short);
+        unsigned slot = slot0;
 #pragma unroll 4
         for (int j = 0; j < cnt; ++j) {
             const float4 q = tile[j];
+            const f32x2 qx = dup2(q.x), qy = dup2(q.y), qz = dup2(q.z), qw = dup2(q.w);     // broadcast operands of the FFMA2s
             // two OR-chains (even / odd rows) so that the compares of one query do not form a single dependent chain
             bool any0 = false, any1 = false;
 #pragma unroll
             for (int r = 0; r < RPT; r += 2) {
-                any0 |= fmaf(ax[r], q.x, fmaf(ay[r], q.y, fmaf(az[r], q.z, q.w))) <= thr[r];
-                any1 |= fmaf(ax[r + 1], q.x, fmaf(ay[r + 1], q.y, fmaf(az[r + 1], q.z, q.w))) <= thr[r + 1];
+                const f32x2 v = fma2(ax2[r / 2], qx, fma2(ay2[r / 2], qy, fma2(az2[r / 2], qz, qw)));
+                any0 |= lo2(v) <= thr[r];
+                any1 |= hi2(v) <= thr[r + 1];
             }
-            if (any0 | any1) {
-                const int pos = atomicAdd(&S.q_count, 1);
-                if (pos < COV_QCAP) S.queue[pos] = ((unsigned)threadIdx.x << 10) | (unsigned)j;
-                else sort_out(threadIdx.x, j, q0);
-            }
+            const bool hit = any0 | any1;
+            if (hit && slot < slot_end) asm volatile("st.shared.u16 [%0], %1;" :: "r"(slot), "h"((unsigned short)j) : "memory");
+            if (hit) slot += COV_THREADS * (unsigned)sizeof(unsigned short);
         }
-        __syncthreads();
-        const int n_q = min(S.q_count, COV_QCAP);
-        for (int e = threadIdx.x; e < n_q; e += COV_THREADS) {
-            const unsigned code = S.queue[e];
-            sort_out((int)(code >> 10), (int)(code & 1023u), q0);
+        int n_mine = (int)((slot - slot0) / (COV_THREADS * (unsigned)sizeof(unsigned short)));
+        // pass A, per warp
+        if (n_mine > COV_LCAP) {
+            for (int j = 0; j < cnt; ++j) sort_out(threadIdx.x, j, q0);
+            n_mine = 0;
+        }
+        __syncwarp();
+        int incl = n_mine;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, s);
+            if (lane >= s) incl += v;
+        }
+        const int excl = incl - n_mine, total = __shfl_sync(FULL, incl, 31);
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            int owner = 0;                                          // the last lane whose list starts at or before entry e
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const int v = __shfl_sync(FULL, excl, owner + s);
+                if (v <= e) owner += s;
+            }
+            const int start = __shfl_sync(FULL, excl, owner);
+            if (e < total) sort_out(wbase + owner, (int)S.lists[e - start][wbase + owner], q0);
         }
         __syncthreads();
         const int n_p = min(S.p_count, COV_PCAP);
@@ -159,7 +239,7 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
             if (!s_cov[lr] && pair_covered(ref + 14 * (block_row0 + lr), qry + 14 * (q0 + j), lut, P)) s_cov[lr] = 1;
         }
         __syncthreads();
-        if (threadIdx.x == 0) { S.q_count = 0; S.p_count = 0; }
+        if (threadIdx.x == 0) S.p_count = 0;
     }
     __syncthreads();
 #pragma unroll
@@ -168,20 +248,6 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
         const int64_t i = block_row0 + lr;
         if (i < n_ref && s_cov[lr]) covered[i] = 1;                  // all writers store the same value
     }
-}
-
-// unit quaternion (x, y, z, w) of a float32 rotation block (row-major 9 floats); approximate (used only for a conservative
-// bound): |q1 . q2| = cos(angle(R1 R2^T) / 2)
-__device__ __forceinline__ float4 quat_of(const float* __restrict__ R) {
-    const float m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8];
-    const float tr = m00 + m11 + m22;
-    float x, y, z, w;
-    if (tr > 0.f) { w = tr + 1.f; x = m21 - m12; y = m02 - m20; z = m10 - m01; }
-    else if (m00 > m11 && m00 > m22) { x = 1.f + m00 - m11 - m22; w = m21 - m12; y = m01 + m10; z = m02 + m20; }
-    else if (m11 > m22) { y = 1.f + m11 - m00 - m22; w = m02 - m20; x = m01 + m10; z = m12 + m21; }
-    else { z = 1.f + m22 - m00 - m11; w = m10 - m01; x = m02 + m20; y = m12 + m21; }
-    const float inv = rsqrtf(fmaxf(x * x + y * y + z * z + w * w, 1e-30f));
-    return make_float4(x * inv, y * inv, z * inv, w * inv);
 }
 
 // ---- algo 1: uniform grid -----------------------------------------------------------------------------------
@@ -244,7 +310,7 @@ __global__ void gather_sorted_kernel(const float* __restrict__ rows, const int32
     if (i >= n) return;
     const int32_t id = sorted_ids[i];
     out[i] = make_float4(rows[14 * (int64_t)id], rows[14 * (int64_t)id + 1], rows[14 * (int64_t)id + 2], __int_as_float(id));
-    if (out_quat) out_quat[i] = quat_of(rows + 14 * (int64_t)id + 3);
+    if (out_quat) out_quat[i] = quat_checked(rows + 14 * (int64_t)id + 3);
     if (cell_start) {
         const uint32_t k = sorted_keys[i];
         if (i == 0 || sorted_keys[i - 1] != k) cell_start[k] = (int32_t)i;
@@ -316,7 +382,7 @@ constexpr int CELL_THREADS = 128;
 constexpr int CELL_RPT = 2;
 constexpr int CELL_REFS = CELL_THREADS * CELL_RPT;
 constexpr int CELL_TILE = 768;                   // queries staged per tile (4 | CELL_TILE <= 1024: queue entries carry 10 bits of it)
-constexpr int CELL_QCAP = 1024;                  // queue entries = (thread, group of 4 queries) with a passing orientation bound
+constexpr int CELL_LCAP = 16;                    // list entries per thread and tile = groups of 4 queries with a passing orientation bound
 constexpr int CELL_PCAP = 1024;                  // (row, query) pairs per tile that pass both conservative tests
 
 // Chunk table of the cell-tile kernel: the references in cell order are cut at every (x, y) column boundary and every
@@ -354,23 +420,26 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
     // block; 9: one column per block.  A reference shard of a multi-GPU run has few chunks (1 M rows / 8 ranks = 488),
     // each ~0.3 ms of work: without the split the 148 SMs get 1.6 waves of long blocks and the call does not scale.
     __shared__ float4 tile[CELL_TILE];
-    __shared__ float4 tile_quat[CELL_TILE + 4];            // query orientations as unit quaternions (+ zero padding for the 4-wide loop)
+    // query orientations as unit quaternions (+ zero padding for the 4-wide loop), two queries per pair of float4:
+    // (x0, x1, y0, y1), (z0, z1, w0, w1) -- the packed operands of the hot loop's FFMA2 / FMUL2
+    __shared__ __align__(16) float tile_quat[4 * (CELL_TILE + 4)];
     __shared__ int tile_id[CELL_TILE];
-    __shared__ unsigned int queue[CELL_QCAP];
+    __shared__ unsigned short lists[CELL_LCAP][CELL_THREADS];   // per thread: the query groups with a passing orientation bound
     __shared__ unsigned int pairs[CELL_PCAP];
     __shared__ int p_count;
     __shared__ float4 s_rquat[CELL_REFS];                   // the chunk's rows for the drain: unit quaternion,
     __shared__ float4 s_rpos[CELL_REFS];                    // (-2 x, -2 y, -2 z, threshold) of the centred translation test
     __shared__ unsigned char s_cov[CELL_REFS];
     __shared__ int s_box[6];                               // min x y z, max x y z (cell coordinates of the chunk)
-    __shared__ int q_count;
     if ((int)blockIdx.x >= *n_chunks) return;               // the grid is the upper bound of the chunk count
     const int2 chunk = chunks[blockIdx.x];
     const int64_t s0 = chunk.x;
     const int n_here = chunk.y - chunk.x;
     if (threadIdx.x < 3) { s_box[threadIdx.x] = 0x7fffffff; s_box[3 + threadIdx.x] = -1; }
-    if (threadIdx.x == 0) { q_count = 0; p_count = 0; }
+    if (threadIdx.x == 0) p_count = 0;
     __syncthreads();
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
     int64_t row[CELL_RPT];
     float px[CELL_RPT], py[CELL_RPT], pz[CELL_RPT];
     float4 quat[CELL_RPT];
@@ -383,7 +452,7 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
         if (lr < n_here) {
             row[r] = ref_sorted_ids[s0 + lr];
             px[r] = ref[14 * row[r]]; py[r] = ref[14 * row[r] + 1]; pz[r] = ref[14 * row[r] + 2];
-            quat[r] = quat_of(ref + 14 * row[r] + 3);
+            quat[r] = quat_checked(ref + 14 * row[r] + 3);
             const int cx = cell_coord(px[r], g.ox, g.inv_h, g.nx), cy = cell_coord(py[r], g.oy, g.inv_h, g.ny), cz = cell_coord(pz[r], g.oz, g.inv_h, g.nz);
             atomicMin(&s_box[0], cx); atomicMin(&s_box[1], cy); atomicMin(&s_box[2], cz);
             atomicMax(&s_box[3], cx); atomicMax(&s_box[4], cy); atomicMax(&s_box[5], cz);
@@ -409,6 +478,11 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
         s_rquat[threadIdx.x + r * CELL_THREADS] = quat[r];
         s_rpos[threadIdx.x + r * CELL_THREADS] = make_float4(ax[r], ay[r], az[r], row[r] >= 0 ? thr[r] : -1e30f);
     }
+    f32x2 rqx[CELL_RPT], rqy[CELL_RPT], rqz[CELL_RPT], rqw[CELL_RPT];      // a row's quaternion against two queries at once
+#pragma unroll
+    for (int r = 0; r < CELL_RPT; ++r) {
+        rqx[r] = dup2(quat[r].x); rqy[r] = dup2(quat[r].y); rqz[r] = dup2(quat[r].z); rqw[r] = dup2(quat[r].w);
+    }
     // pass A of the drain for the 4 x CELL_RPT pairs of (thread t, queries j0 .. j0 + 3 of the staged tile): orientation
     // bound and translation reject from shared memory, by whichever thread drains the entry; survivors -> pair queue
     auto drain_group = [&](int t, int j0, int cnt) {
@@ -419,7 +493,8 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
             const float4 rq = s_rquat[lr], rp = s_rpos[lr];
 #pragma unroll 1
             for (int j = j0; j < min(j0 + 4, cnt); ++j) {
-                const float4 qq = tile_quat[j];
+                const float* tq = tile_quat + 8 * (j >> 1) + (j & 1);
+                const float4 qq = make_float4(tq[0], tq[2], tq[4], tq[6]);
                 if (fabsf(fmaf(rq.x, qq.x, fmaf(rq.y, qq.y, fmaf(rq.z, qq.z, rq.w * qq.w)))) < P.qdot_min) continue;
                 const float4 q = tile[j];
                 if (fmaf(rp.x, q.x, fmaf(rp.y, q.y, fmaf(rp.z, q.z, q.w))) > rp.w) continue;
@@ -453,41 +528,73 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
                     tile[j] = make_float4(x, y, z, fmaf(x, x, fmaf(y, y, z * z)));
                     const int qi = __float_as_int(q.w);
                     tile_id[j] = qi;
-                    tile_quat[j] = __ldg(q_quat_sorted + t0 + j);
+                    const float4 qq = __ldg(q_quat_sorted + t0 + j);
+                    float* tq = tile_quat + 8 * (j >> 1) + (j & 1);
+                    tq[0] = qq.x; tq[2] = qq.y; tq[4] = qq.z; tq[6] = qq.w;
                 }
-                if (threadIdx.x < 4) tile_quat[cnt + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (threadIdx.x < 4) {
+                    const int j = cnt + threadIdx.x;
+                    float* tq = tile_quat + 8 * (j >> 1) + (j & 1);
+                    tq[0] = 0.f; tq[2] = 0.f; tq[4] = 0.f; tq[6] = 0.f;
+                }
 #pragma unroll
                 for (int r = 0; r < CELL_RPT; ++r)
                     if (s_cov[threadIdx.x + r * CELL_THREADS]) qmin[r] = 2.0f;        // already covered: stop testing this row
                 __syncthreads();
                 // In a grid walk ~15 % of the candidates pass the translation test but only ~0.1 % the rotation test, so the
-                // orientation bound goes FIRST here: |q1 . q2| = cos(angle / 2), 4 FMAs on the staged quaternions.  Four
-                // queries x CELL_RPT rows are evaluated branch-free (8 independent FMA chains) with the compares OR-ed
-                // into one predicate; a thread with a passing pair only queues (thread, query group) -- one atomic, one
-                // store -- and the block sorts the group out after the tile with all lanes busy (a rare path run by one
-                // lane costs the warp its issue slots: round 1 recomputed the eight dot products there, 8.6 issued
-                // instructions per pair against a loop body of 5.9).
+                // orientation bound goes FIRST here: |q1 . q2| = cos(angle / 2), one product + 3 multiply-adds on the staged
+                // quaternions.  Four queries x CELL_RPT rows are evaluated branch-free; two queries share packed registers
+                // (FMUL2 + 3 FFMA2 for two pairs), the compares are OR-ed into predicates, and a thread with a passing pair
+                // appends the group's index to its own short list (one predicated store, one predicated add: the loop has
+                // no branch, a rare path run by one lane would cost the warp its issue slots).  Round 1 recomputed the eight
+                // dot products on a divergent path (8.6 issued instructions per pair), round 2's first version pushed
+                // (thread, group) through a shared atomic (5.9 + the divergent push); now 4 LDS.128 + 16 packed + 8 FSETP +
+                // 4 = 32 per 8 pairs.
+                const unsigned slot0 = (unsigned)__cvta_generic_to_shared(&lists[0][threadIdx.x]);
+                const unsigned slot_end = slot0 + CELL_LCAP * CELL_THREADS * (unsigned)sizeof(unsigned short);
+                unsigned slot = slot0;
+                const float4* tq4 = reinterpret_cast<const float4*>(tile_quat);
                 for (int j0 = 0; j0 < cnt; j0 += 4) {
-                    float4 qq[4];
+                    bool any0 = false, any1 = false;             // (|=, not ||: no short-circuit branches between the chains)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qq[u] = tile_quat[j0 + u];
-                    bool any_pass = false;                       // (|=, not ||: no short-circuit branches between the chains)
+                    for (int u = 0; u < 2; ++u) {
+                        const float4 qa = tq4[j0 + 2 * u], qb = tq4[j0 + 2 * u + 1];
+                        const f32x2 qx = pack2(qa.x, qa.y), qy = pack2(qa.z, qa.w), qz = pack2(qb.x, qb.y), qw = pack2(qb.z, qb.w);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int r = 0; r < CELL_RPT; ++r)
-                            any_pass |= fabsf(fmaf(quat[r].x, qq[u].x, fmaf(quat[r].y, qq[u].y, fmaf(quat[r].z, qq[u].z, quat[r].w * qq[u].w)))) >= qmin[r];
-                    if (any_pass) {
-                        const int pos = atomicAdd(&q_count, 1);
-                        if (pos < CELL_QCAP) queue[pos] = ((unsigned)threadIdx.x << 10) | (unsigned)j0;
-                        else drain_group(threadIdx.x, j0, cnt);
+                        for (int r = 0; r < CELL_RPT; ++r) {
+                            const f32x2 v = fma2(rqx[r], qx, fma2(rqy[r], qy, fma2(rqz[r], qz, mul2(rqw[r], qw))));
+                            any0 |= !(fabsf(lo2(v)) < qmin[r]);       // (not >=: a NaN quaternion must pass)
+                            any1 |= !(fabsf(hi2(v)) < qmin[r]);
+                        }
                     }
+                    const bool hit = any0 | any1;
+                    if (hit && slot < slot_end) asm volatile("st.shared.u16 [%0], %1;" :: "r"(slot), "h"((unsigned short)j0) : "memory");
+                    if (hit) slot += CELL_THREADS * (unsigned)sizeof(unsigned short);
                 }
-                __syncthreads();
-                const int n_q = min(q_count, CELL_QCAP);
-                for (int i = threadIdx.x; i < n_q; i += CELL_THREADS) {
-                    const unsigned code = queue[i];
-                    drain_group((int)(code >> 10), (int)(code & 1023u), cnt);
+                // pass A, per warp with all lanes busy: prefix sum of the list lengths, entry e -> (owner lane, k)
+                int n_mine = (int)((slot - slot0) / (CELL_THREADS * (unsigned)sizeof(unsigned short)));
+                if (n_mine > CELL_LCAP) {                        // list overflow: this thread sorts out every group itself
+                    for (int j0 = 0; j0 < cnt; j0 += 4) drain_group(threadIdx.x, j0, cnt);
+                    n_mine = 0;
+                }
+                __syncwarp();
+                int incl = n_mine;
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, sft);
+                    if (lane >= sft) incl += v;
+                }
+                const int excl = incl - n_mine, total = __shfl_sync(FULL, incl, 31);
+                for (int e0 = 0; e0 < total; e0 += 32) {
+                    const int e = e0 + lane;
+                    int owner = 0;                               // the last lane whose list starts at or before entry e
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) {
+                        const int v = __shfl_sync(FULL, excl, owner + sft);
+                        if (v <= e) owner += sft;
+                    }
+                    const int start = __shfl_sync(FULL, excl, owner);
+                    if (e < total) drain_group(wbase + owner, (int)lists[e - start][wbase + owner], cnt);
                 }
                 __syncthreads();
                 const int n_p = min(p_count, CELL_PCAP);
@@ -497,7 +604,7 @@ coverage_cells_kernel(const float* __restrict__ ref, const int32_t* __restrict__
                     if (!s_cov[lr] && pair_covered(ref + 14 * (int64_t)ref_sorted_ids[s0 + lr], qry + 14 * (int64_t)tile_id[j], lut, P)) s_cov[lr] = 1;
                 }
                 __syncthreads();
-                if (threadIdx.x == 0) { q_count = 0; p_count = 0; }
+                if (threadIdx.x == 0) p_count = 0;
             }
         }
     __syncthreads();
@@ -855,7 +962,15 @@ extern "C" int bt_coverage(const float* d_ref, int64_t n_ref, const float* d_qry
             BT_CUDA(cudaFuncSetAttribute(coverage_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CovTilesSmem)));
             if (dev >= 0 && dev < 64) smem_opt_in[dev] = true;
         }
-        coverage_tiles_kernel<<<grid, COV_THREADS, sizeof(CovTilesSmem), st>>>(d_ref, n_ref, d_qry, n_qry, q_per_split, d_lut, P, d_covered);
+        Scratch quats;
+        BT_CUDA(quats.alloc(sizeof(float4) * (size_t)(n_ref + n_qry), st));
+        float4* ref_quat = quats.as<float4>();
+        float4* qry_quat = ref_quat + n_ref;
+        row_quat_kernel<<<(unsigned)ceil_div(n_ref, 256), 256, 0, st>>>(d_ref, n_ref, ref_quat);
+        BT_LAUNCH_CHECK();
+        row_quat_kernel<<<(unsigned)ceil_div(n_qry, 256), 256, 0, st>>>(d_qry, n_qry, qry_quat);
+        BT_LAUNCH_CHECK();
+        coverage_tiles_kernel<<<grid, COV_THREADS, sizeof(CovTilesSmem), st>>>(d_ref, n_ref, d_qry, n_qry, ref_quat, qry_quat, q_per_split, d_lut, P, d_covered);
         BT_LAUNCH_CHECK();
     }
     count_covered_kernel<<<148, 256, 0, st>>>(d_covered, n_ref, reinterpret_cast<unsigned long long*>(d_count));

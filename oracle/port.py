@@ -65,7 +65,10 @@ def rounded_cos_index(r1, r2):
         diag.append(acc)
     tr = (diag[0] + diag[1]) + diag[2]
     c = (tr - F32(1.0)) / F32(2.0)
-    return np.rint(c * F32(10000.0)).astype(np.int64)
+    with np.errstate(invalid='ignore', over='ignore'):
+        kf = np.rint(c * F32(10000.0))
+    # NaN / inf / beyond +-1: arccos gives NaN in the reference (never <= epsilon); any index outside +-10000 says so
+    return np.where(np.isfinite(kf) & (np.abs(kf) <= 10000.0), kf, 20000.0).astype(np.int64)
 
 
 def angular_distances_deg(r1, r2, lut=None):

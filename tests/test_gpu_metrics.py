@@ -142,6 +142,72 @@ def test_threshold_band(metrics):
                 assert np.array_equal(got, want), (float(q[0, 0]), kd, algo)
 
 
+def test_angular_threshold_band(metrics):
+    """pairs whose angular part sits around epsilon (and around epsilon minus the weighted translation): the orientation
+    bound of both kernels (a conservative quaternion test before the exact recipe) must never rule out a pair the
+    reference's recipe accepts -- every case against the oracle, both semantics, both algorithms."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(5)
+    n = 64
+    base = random_rows(n, 31, cube=0.05)
+    refs, qrys = [], []
+    for k, ang in enumerate([14.0, 14.9, 14.97, 14.99, 14.995, 15.0, 15.005, 15.01, 15.03, 15.1, 16.0, 9.99, 10.0, 10.01, 179.9, 180.0]):
+        for d_mm in (0.0, 5.0):                                  # deg + 1000 d against 15: d = 5 mm moves the band to 10 degrees
+            r = base[(2 * k) % n].copy()
+            q = r.copy()
+            axis = rng.normal(size=3)
+            axis /= np.linalg.norm(axis)
+            rot = Rotation.from_rotvec(np.deg2rad(ang) * axis).as_matrix()
+            q[3:12] = (rot @ r[3:12].reshape(3, 3).astype(np.float64)).reshape(9)
+            q[0] += np.float32(d_mm / 1000.0)
+            r[1] += np.float32(1.0 * len(refs))                    # every pair far from all the others
+            q[1] += np.float32(1.0 * len(qrys))
+            refs.append(r)
+            qrys.append(q)
+    ref, qry = np.stack(refs).astype(np.float32), np.stack(qrys).astype(np.float32)
+    for kd in (True, False):
+        want = port.covered_kd(ref, qry) if kd else port.covered_brute_force(ref, qry)
+        assert 0 < want.sum() < len(ref)
+        for algo in ('tiles', 'grid'):
+            got = metrics.covered_mask(_gs(ref), _gs(qry), kd_semantics=kd, algo=algo)
+            assert np.array_equal(got, want), (kd, algo, np.flatnonzero(got != want))
+
+
+def test_rows_that_are_not_rotations(metrics):
+    """the reference's recipe takes any 3 x 3 block (trace of R1 R2^T through arccos, NaN beyond 1); blocks that are not
+    rotation matrices -- scaled, sheared, reflected, zero, NaN -- bypass the kernels' orientation bound and must give
+    the oracle's answer"""
+    rng = np.random.default_rng(6)
+    ref = random_rows(600, 41, cube=0.03)
+    qry = np.concatenate([random_rows(300, 42, cube=0.03), perturbed_rows(ref, 43)])
+    for rows, seed in ((ref, 1), (qry, 2)):
+        r = np.random.default_rng(seed)
+        idx = r.choice(len(rows), len(rows) // 3, replace=False)
+        kinds = r.integers(0, 6, len(idx))
+        for i, kind in zip(idx, kinds):
+            m = rows[i, 3:12].reshape(3, 3).astype(np.float64)
+            if kind == 0:
+                m = m * r.uniform(0.5, 1.02)
+            elif kind == 1:
+                m = m + r.normal(0, 0.05, (3, 3))
+            elif kind == 2:
+                m = m @ np.diag([1.0, 1.0, -1.0])
+            elif kind == 3:
+                m = np.zeros((3, 3))
+            elif kind == 4:
+                m = r.normal(0, 1, (3, 3))
+            else:
+                m = m.copy()
+                m[r.integers(0, 3), r.integers(0, 3)] = np.nan
+            rows[i, 3:12] = m.reshape(9).astype(np.float32)
+    for kd in (True, False):
+        want = port.covered_kd(ref, qry) if kd else port.covered_brute_force(ref, qry)
+        for algo in ('tiles', 'grid'):
+            got = metrics.covered_mask(_gs(ref), _gs(qry), kd_semantics=kd, algo=algo)
+            assert np.array_equal(got, want), (kd, algo, np.flatnonzero(got != want)[:10])
+    assert 0 < want.sum() < len(ref)
+
+
 def test_full_size_properties(metrics):
     """BASELINE config 2 (100k x 100k): size-independent properties instead of an oracle run."""
     import torch
