@@ -174,12 +174,18 @@ constexpr int TWARPS = 4;
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) { unsigned r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
 __device__ __forceinline__ float plane16(unsigned w, unsigned sel) { return __uint_as_float(prmt(w, 0x4B000000u, sel)); }
 
-// `behind`: T_BEHIND, or +inf for a node the cone test has ruled out (then no child is hit, without a branch)
+// `behind`: T_BEHIND, or +inf for a node the cone test has ruled out (then no child is hit, without a branch).
+// The near and the far plane of an axis go through ONE packed multiply-add (FFMA2: lo = near, hi = far; 1/d and the
+// origin term are broadcast operands), so a box costs 6 permutes + 3 FFMA2 + max3 + min3 + the compares; each half is the
+// scalar fmaf of the same operands, bit for bit.  `noox` = -(2^23 / d + o / d), negated once per ray.
 __device__ __forceinline__ bool slab_hit_signed(unsigned wx, unsigned wy, unsigned wz, unsigned snx, unsigned sny, unsigned snz,
                                                 unsigned sfx, unsigned sfy, unsigned sfz, float idx, float idy, float idz,
-                                                float oox, float ooy, float ooz, float behind = T_BEHIND) {
-    const float tnear = fmaxf(fmaxf(fmaf(plane16(wx, snx), idx, -oox), fmaf(plane16(wy, sny), idy, -ooy)), fmaf(plane16(wz, snz), idz, -ooz));
-    const float tfar = fminf(fminf(fmaf(plane16(wx, sfx), idx, -oox), fmaf(plane16(wy, sfy), idy, -ooy)), fmaf(plane16(wz, sfz), idz, -ooz));
+                                                float noox, float nooy, float nooz, float behind = T_BEHIND) {
+    const f32x2 tx = fma2(pack2(plane16(wx, snx), plane16(wx, sfx)), dup2_here(idx), dup2_here(noox));
+    const f32x2 ty = fma2(pack2(plane16(wy, sny), plane16(wy, sfy)), dup2_here(idy), dup2_here(nooy));
+    const f32x2 tz = fma2(pack2(plane16(wz, snz), plane16(wz, sfz)), dup2_here(idz), dup2_here(nooz));
+    const float tnear = fmaxf(fmaxf(lo2(tx), lo2(ty)), lo2(tz));
+    const float tfar = fminf(fminf(hi2(tx), hi2(ty)), hi2(tz));
     return (tnear <= tfar) & (tfar >= behind);
 }
 
@@ -229,7 +235,7 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
 
     const int DONE = (int)0x80000000;                 // never a leaf code: leaf codes are ~index with index < 2^30
     int my = 0;                                       // this lane's ray
-    float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
+    float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;       // oox..: -(2^23 / d + o / d), see the re-fetch below
     unsigned snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;
     float ux = 0, uy = 0, uz = 0, ubias = 0;             // CULL: unit direction and CONE_BIAS * (ux + uy + uz)
     int stack[WIDE_STACK];
@@ -286,9 +292,10 @@ traverse_kernel(MeshView mv, const double* __restrict__ ref_pts, const double* _
                 idx = __frcp_rn(fabsf(gdx) < 1e-20f ? copysignf(1e-20f, gdx) : gdx);
                 idy = __frcp_rn(fabsf(gdy) < 1e-20f ? copysignf(1e-20f, gdy) : gdy);
                 idz = __frcp_rn(fabsf(gdz) < 1e-20f ? copysignf(1e-20f, gdz) : gdz);
-                oox = fmaf(8388608.0f, idx, (float)((ref_pts[3 * ref] - mv.gmin[0]) * mv.gscale[0]) * idx);
-                ooy = fmaf(8388608.0f, idy, (float)((ref_pts[3 * ref + 1] - mv.gmin[1]) * mv.gscale[1]) * idy);
-                ooz = fmaf(8388608.0f, idz, (float)((ref_pts[3 * ref + 2] - mv.gmin[2]) * mv.gscale[2]) * idz);
+                // (kept negated: the addend of the packed multiply-adds)
+                oox = -fmaf(8388608.0f, idx, (float)((ref_pts[3 * ref] - mv.gmin[0]) * mv.gscale[0]) * idx);
+                ooy = -fmaf(8388608.0f, idy, (float)((ref_pts[3 * ref + 1] - mv.gmin[1]) * mv.gscale[1]) * idy);
+                ooz = -fmaf(8388608.0f, idz, (float)((ref_pts[3 * ref + 2] - mv.gmin[2]) * mv.gscale[2]) * idz);
                 // near plane = the low one where the ray runs in +axis direction (sign bit of 1/d, so -0 counts as negative)
                 const bool nx = __float_as_uint(idx) >> 31, ny = __float_as_uint(idy) >> 31, nz = __float_as_uint(idz) >> 31;
                 snx = nx ? 0x7632u : 0x7610u; sfx = nx ? 0x7610u : 0x7632u;
@@ -1092,7 +1099,11 @@ int bt::ags_cast_impl(const bt_mesh* mesh, const double* d_ref_pts, const double
     int64_t rpw = 32;
     if (const char* e = getenv("BT_CAST_RPW")) { const int v = atoi(e); if (v >= 32 && v <= 4096) rpw = v; }       // tuning knob
     BT_REQUIRE(total + rpw < ((int64_t)1 << 31), "more than 2^31 rays in one call");
-    const int64_t n_warps = std::min<int64_t>(ceil_div(total, rpw), (int64_t)sm_count * TRAV_MINB * TWARPS);
+    // blocks per SM of the persistent grid: TRAV_MINB fills the register file; fewer leave room for another batch's
+    // kernels on the same SM (several batches in flight on different streams), BT_TRAV_BPS is the tuning knob
+    static int trav_bps = -1;
+    if (trav_bps < 0) { const char* e = getenv("BT_TRAV_BPS"); const int v = e ? atoi(e) : 0; trav_bps = (v >= 1 && v <= TRAV_MINB) ? v : TRAV_MINB; }
+    const int64_t n_warps = std::min<int64_t>(ceil_div(total, rpw), (int64_t)sm_count * trav_bps * TWARPS);
     // cone culling: only where the caller wants valid hits and nothing else (lean pipeline), on packed nodes
     static int cull_env = -1;
     if (cull_env < 0) { const char* e = getenv("BT_CAST_CULL"); cull_env = e ? atoi(e) : 1; }

@@ -903,7 +903,9 @@ extern "C" int bt_collide(const bt_mesh* scene, const bt_gripper* gripper, const
         return BT_OK;
     }
     {
-        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * LEAN_MINB);
+        static int lean_bps = -1;                           // tuning knob, as BT_TRAV_BPS for the ray caster
+        if (lean_bps < 0) { const char* e = getenv("BT_COLLIDE_BPS"); const int v = e ? atoi(e) : 0; lean_bps = (v >= 1 && v <= LEAN_MINB) ? v : LEAN_MINB; }
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(items, 128), (int64_t)sm_count * lean_bps);
         collide_kernel<false, false><<<grid, 32 * CWARPS, 0, st>>>(BT_COLLIDE_ARGS(wc, nullptr, nullptr));
         BT_LAUNCH_CHECK();
         collide_exact_kernel<<<sm_count * 8, 128, tri_bytes, st>>>(gq.entries, gq.count, gq.cap, scene->m.tri_verts, d_gs, gripper->tris,

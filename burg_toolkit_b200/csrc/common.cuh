@@ -128,6 +128,13 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
 __device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ f32x2 dup2(float x) { return pack2(x, x); }        // ptxas folds it into the .F32 broadcast operand form
+// the same, pinned next to its use: a duplicate that the front end hoists out of a loop lives on as a register pair (two
+// MOVs and two registers per operand); `volatile` keeps the pack where it is written, where ptxas folds it away
+__device__ __forceinline__ f32x2 dup2_here(float x) {
+    f32x2 r;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 #if BT_F32X2
     f32x2 d;
@@ -270,6 +277,8 @@ struct MeshDev {
     uint32_t* leaf_cone = nullptr; // [nF]     leaf order: packed normal cone of the leaf, widened over its touching neighbours (mesh.cu: pack_cone)
     int32_t  wide_packed = 0;      // wnodes use 24-bit child codes + the node's own cone in their top bytes (nF < 2^23)
     int32_t  root = 0;             // root child code (internal 0, or ~0 if single triangle)
+    int32_t  bvh_kind = 0;         // topology of the binary tree: 0 = Karras hierarchy of the Morton codes, 1 = PLOC
+    int32_t  ploc_iterations = 0;
     bt_mesh_info info{};
 };
 

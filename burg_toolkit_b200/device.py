@@ -63,6 +63,13 @@ class DeviceMesh:
         nat.call('bt_mesh_get_info', self.handle, C.byref(out))
         return out
 
+    @property
+    def bvh_kind(self):
+        """('ploc' | 'lbvh', merge rounds of the PLOC build) -- which topology this mesh's tree was built with"""
+        kind, its = C.c_int32(), C.c_int32()
+        nat.call('bt_mesh_bvh_kind', self.handle, C.byref(kind), C.byref(its))
+        return ('ploc' if kind.value == 1 else 'lbvh'), its.value
+
     def bvh(self):
         """(nodes float32 [n_nodes, 16], leaf_tri int32 [n_triangles]) -- validation only"""
         inf = self.info
@@ -70,6 +77,12 @@ class DeviceMesh:
         leaf = np.empty(inf.n_triangles, dtype=np.int32)
         nat.call('bt_mesh_copy_bvh', self.handle, nodes.ctypes.data, leaf.ctypes.data)
         return nodes, leaf
+
+
+def set_bvh_build(kind):
+    """Topology of the trees built from now on: 'ploc' (default) or 'lbvh' (Karras hierarchy of the Morton codes).  Results
+    do not depend on it (the tree is the broad phase); meshes that are already on the device keep their tree."""
+    nat.call('bt_set_bvh_build', {'lbvh': 0, 'ploc': 1}[kind])
 
 
 def _destroy(fn, handle):

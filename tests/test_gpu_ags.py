@@ -24,11 +24,22 @@ def make_sampler(g, **extra):
     return ags
 
 
-def test_lbvh_is_a_valid_hierarchy():
-    from burg_toolkit_b200 import mesh as bmesh
+@pytest.fixture
+def restore_bvh_build():
+    from burg_toolkit_b200 import device
+    yield
+    device.set_bvh_build('ploc')
+
+
+@pytest.mark.parametrize('kind', ['ploc', 'lbvh'])
+def test_lbvh_is_a_valid_hierarchy(kind, restore_bvh_build):
+    from burg_toolkit_b200 import mesh as bmesh, device
     from burg_toolkit_b200.device import DeviceMesh
-    for m in [bmesh.create_icosphere(3, 0.03), bmesh.create_bumpy_sphere(40, 40), bmesh.create_box(0.1, 0.2, 0.3)]:
+    device.set_bvh_build(kind)
+    for m in [bmesh.create_icosphere(3, 0.03), bmesh.create_bumpy_sphere(40, 40), bmesh.create_box(0.1, 0.2, 0.3),
+              bmesh.create_icosphere(0, 1.0)]:
         dm = DeviceMesh.from_mesh(m)
+        assert dm.bvh_kind[0] == kind and (kind == 'lbvh' or dm.bvh_kind[1] >= 1)
         nodes, leaf_tri = dm.bvh()
         n_f = len(m.triangles)
         assert sorted(leaf_tri.tolist()) == list(range(n_f))                 # every triangle is exactly one leaf
@@ -58,6 +69,39 @@ def test_lbvh_is_a_valid_hierarchy():
         box_of(0)
         assert (seen_leaf == 1).all() and (seen_node == 1).all()
         assert dm.info.max_depth <= 60 and abs(dm.info.surface_area - m.get_surface_area()) < 1e-12
+
+
+def test_results_do_not_depend_on_the_tree(restore_bvh_build):
+    """PLOC tree against the Morton hierarchy on the same mesh: every output of the pipeline is the same bits (the tree
+    is a broad phase), the PLOC tree is walked with fewer node visits, and two builds of it are the same tree."""
+    import torch
+    from burg_toolkit_b200 import mesh as bmesh, device, sampling, _native as nat
+    from burg_toolkit_b200.gripper import ParallelJawGripper
+    outs, visits, trees = {}, {}, {}
+    for kind in ('lbvh', 'ploc', 'ploc2'):
+        device.set_bvh_build(kind[:4])
+        ags = sampling.AntipodalGraspSampler()
+        ags.mesh, ags.gripper, ags.verbose = bmesh.create_bumpy_sphere(96, 96, radius=0.035, amplitude=0.15, seed=3), ParallelJawGripper(), False
+        counters = torch.zeros(8, dtype=torch.int64, device='cuda')
+        nat.call('bt_debug_set_counters', counters.data_ptr())
+        try:
+            out = ags.run_pipeline(n_ref=2000, seed=11)
+            torch.cuda.synchronize()
+        finally:
+            nat.call('bt_debug_set_counters', None)
+        n_rows, k = int(out['n_grasps'].item()), int(out['n_free'].item())
+        outs[kind] = (out['pair_count'].cpu().numpy(), out['gs'][:n_rows].cpu().numpy(), out['contacts'][:n_rows].cpu().numpy(),
+                      out['colliding'][:n_rows].cpu().numpy(), out['free_gs'][:k].cpu().numpy())
+        visits[kind] = int(counters[0].item())
+        dm = device.cached_device_mesh(ags.mesh)
+        assert dm.bvh_kind[0] == kind[:4]
+        trees[kind] = dm.bvh()
+    for a, b in zip(outs['lbvh'], outs['ploc']):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert len(outs['ploc'][1]) > 10_000 and 0 < outs['ploc'][3].sum() < len(outs['ploc'][3])
+    assert visits['ploc'] < 0.95 * visits['lbvh'], visits
+    assert np.array_equal(trees['ploc'][0].view(np.uint32), trees['ploc2'][0].view(np.uint32))     # (child codes are not floats)
+    assert np.array_equal(trees['ploc'][1], trees['ploc2'][1])
 
 
 @pytest.mark.parametrize('name', AGS_FIXTURES)

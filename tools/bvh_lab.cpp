@@ -391,11 +391,13 @@ int main(int argc, char** argv) {
 
     BinTree lb; lb.leaf_box = leaf_box;
     lb.root = lbvh_rec(lb, skey, 0, nF - 1);
-    {   // per-node (on entry) culling, neighbour-expanded quantised cones, every-other-level collapse as in the GPU build
-        const BinTree& t = lb;
+    // per-node (on entry) culling, neighbour-expanded quantised cones, every-other-level collapse as in the GPU build
+    auto run_gpu_like = [&](const char* name, const BinTree& t) {
         std::vector<Cone> nc(t.left.size());
         std::function<Cone(int)> cone_of = [&](int c) -> Cone { if (c < 0) return leaf_cone_nb(~c); Cone r = merge_cone(cone_of(t.left[c]), cone_of(t.right[c])); r.th = std::min(M_PI, std::ceil((r.th + 0.012) / (M_PI / 255)) * (M_PI / 255)); nc[c] = r; return r; };
         cone_of(t.root);
+        int max_depth = 0;
+        { std::function<void(int, int)> dep = [&](int c, int d) { if (c < 0) { max_depth = std::max(max_depth, d); return; } dep(t.left[c], d + 1); dep(t.right[c], d + 1); }; dep(t.root, 0); }
         struct WN { Box b[4]; int child[4]; int n; double ax[3]; double cth; };
         std::vector<WN> out;
         const double alpha = std::atan(0.25) + 0.002;
@@ -431,17 +433,20 @@ int main(int argc, char** argv) {
                     }
             }
         }
-        printf("per-node cull (nb-expanded, 8-bit): fetches/ray %.2f  full visits/ray %.2f  leaves reached %.2f  pretests %.2f\n", fetch / n_total, visits / n_total, leaves / n_total, leaves_kept / n_total);
-    }
+        printf("%-28s GPU-like (every other level, per-node cull, nb-expanded 8-bit cones): fetches/ray %.2f  full visits/ray %.2f  leaves reached %.2f  pretests %.2f  binary depth %d\n", name, fetch / n_total, visits / n_total, leaves / n_total, leaves_kept / n_total, max_depth);
+    };
+    run_gpu_like("LBVH", lb);
+
     run_cull("LBVH greedy 4-wide + cone cull", lb, 4);
     run_cull("LBVH greedy 8-wide + cone cull", lb, 8);
     run("LBVH, every other level (round 1)", lb, 4, false);
     run("LBVH, greedy 4-wide", lb, 4, true);
     run("LBVH, greedy 8-wide", lb, 8, true);
-    for (int r : {8, 16, 32, 64}) {
+    for (int r : {4, 8, 16, 32}) {
         BinTree pt; pt.leaf_box = leaf_box;
         ploc(pt, r);
         char nm[64];
+        snprintf(nm, sizeof nm, "PLOC r=%d", r); run_gpu_like(nm, pt);
         snprintf(nm, sizeof nm, "PLOC r=%d, every other level", r); run(nm, pt, 4, false);
         snprintf(nm, sizeof nm, "PLOC r=%d, greedy 4-wide", r); run(nm, pt, 4, true);
         snprintf(nm, sizeof nm, "PLOC r=%d, greedy 8-wide", r); run(nm, pt, 8, true);
