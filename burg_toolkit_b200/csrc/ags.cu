@@ -903,7 +903,13 @@ __global__ void select_fill_kernel(const int32_t* __restrict__ hit_count, const 
 // single-pass chained scan (decoupled look-back): a block publishes its aggregate, looks back over its predecessors'
 // status words until it meets an inclusive prefix, and publishes its own.  Block ids come from a ticket counter, so a block
 // only ever waits for blocks that are already running.  Status word: bits 63..62 = 1 aggregate / 2 inclusive prefix.
-constexpr int SEL_REFS = 32;
+#ifndef BT_SEL_REFS
+#define BT_SEL_REFS 8
+#endif
+// reference points per block, <= 32 (one warp scans the block's counts).  8 = 256-thread blocks: a 1 024-thread block needs
+// a whole SM's register file to itself and waits for one to drain while other batches' kernels are resident (step with four
+// batches in flight: 0.479 ms at 32, 0.474 at 16, 0.472 at 8)
+constexpr int SEL_REFS = BT_SEL_REFS;
 __global__ void __launch_bounds__(32 * SEL_REFS)
 select_fused_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restrict__ hits, HitSource hs,
                     const uint32_t* __restrict__ valid_mask, int64_t n_ref, int n_rays, int cap, int max_targets, uint64_t seed,
@@ -925,16 +931,16 @@ select_fused_kernel(const int32_t* __restrict__ hit_count, const bt_hit* __restr
     if (lane == 0) { s_cnt[w] = n_take; if (ref < n_ref) pair_count[ref] = n_take; }
     __syncthreads();
     if (w == 0) {
-        const int c = s_cnt[lane];
+        const int c = lane < SEL_REFS ? s_cnt[lane] : 0;
         int incl = c;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += v; }
         const unsigned long long agg = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
         const unsigned long long excl = lookback_exclusive(status, bid, agg, lane);
-        s_cnt[lane] = incl - c;                                // exclusive prefix inside the block
+        if (lane < SEL_REFS) s_cnt[lane] = incl - c;           // exclusive prefix inside the block
         if (lane == 0) s_base = excl;
         const int64_t r = (int64_t)bid * SEL_REFS + lane;
-        if (r < n_ref) pair_offset[r] = (int64_t)excl + (incl - c);
+        if (lane < SEL_REFS && r < n_ref) pair_offset[r] = (int64_t)excl + (incl - c);
         if (bid == n_blocks - 1 && lane == 31) pair_offset[n_ref] = (int64_t)(excl + agg);
     }
     __syncthreads();
