@@ -44,8 +44,10 @@ def main(path):
                 def g(m, r=r):
                     return (r[col[m]], units[col[m]]) if m in col else (None, None)
                 rd, wr = g('dram__bytes_read.sum'), g('dram__bytes_write.sum')
+                dur, dur_unit = g('gpu__time_duration.sum')
+                dur_us = num(dur) * {'ns': 1e-3, 'nsecond': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3, 's': 1e6, 'second': 1e6}[dur_unit]
                 rec = {'dram_bytes_per_launch': to_bytes(*rd) + to_bytes(*wr), 'dram_read_bytes': to_bytes(*rd), 'dram_write_bytes': to_bytes(*wr),
-                       'duration_us': num(g('gpu__time_duration.sum')[0]),
+                       'duration_us': dur_us,
                        'l1tex_data_pipe_lsu_wavefronts_pct': num(g('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed')[0]),
                        'alu_pipe_pct': num(g('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active')[0]),
                        'fma_pipe_pct': num(g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')[0]),
