@@ -395,7 +395,7 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
         build_ms.append(ags._device_mesh().info.build_ms)
     ags.mesh = mesh
     info = ags._device_mesh().info
-    bvh_kind, bvh_rounds = ags._device_mesh().bvh_kind
+    bvh_kind, bvh_rounds, walk_kind = ags._device_mesh().bvh_kind
     cap_rows = N_REF * ags.max_targets_per_ref_point * N_ORIENT
     # the path's only exchange: compacted grasp rows + contacts + counts to rank 0.  Every rank's compaction
     # kernel stores its kept rows straight into its slot of rank 0's buffer over NVLink (distributed.PeerGather, CUDA IPC).
@@ -672,8 +672,9 @@ def ags_block(ctx, workload, steps, warmup, with_cpu):
                         'single_stream_ms_per_step': single_ms, 'host_issue_ms_per_step': host_issue_ms,
                         'ms_per_step_by_rank': [round(x, 4) for x in rank_ms], 'sm_mhz_by_rank': clk_by_rank,
                         'bvh_build_ms': float(np.mean(build_ms)), 'bvh_max_depth': int(info.max_depth),
-                        'bvh_build': {'lbvh': 'Karras hierarchy of the Morton codes', 'ploc': f'PLOC (radius 8, {bvh_rounds} merge rounds) on the Morton order'}[bvh_kind]
-                                     + '; 4-wide collapse of every other level, normal cones',
+                        'bvh_build': 'ray tree (target object): ' + {'lbvh': 'Karras hierarchy of the Morton codes', 'ploc': f'PLOC (radius 8, {bvh_rounds} merge rounds) on the Morton order'}[bvh_kind]
+                                     + ', 4-wide collapse of every other level, normal cones; walk tree of the target object (binary nodes): ' + walk_kind
+                                     + ' (the collision scene of config 4 is a mesh of its own: PLOC from 2^18 triangles on)',
                         'posed_grasps_per_step': n_grasps, 'collision_free_per_step': n_free, 'hit_list_overflows': overflow,
                         'exchange': exchange, 'exchange_timed_out': exchange_timed_out},
              'roofline': roofline, 'stage_ms': stage_ms, 'e2e': e2e,

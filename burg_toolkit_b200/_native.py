@@ -83,7 +83,7 @@ _SIGNATURES = {
     'bt_mesh_get_info': (C.c_int, [_P, C.POINTER(MeshInfo)]),
     'bt_mesh_copy_bvh': (C.c_int, [_P, _P, _P]),
     'bt_set_bvh_build': (C.c_int, [C.c_int32]),
-    'bt_mesh_bvh_kind': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'bt_mesh_bvh_kind': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'bt_sample_surface': (C.c_int, [_P, C.c_int64, C.c_uint64, _P, _P, _P, _P]),
     'bt_poisson_disk_eliminate': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _P, C.POINTER(C.c_int32), _P]),
     'bt_cone_rays': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_uint64, _P, _P]),

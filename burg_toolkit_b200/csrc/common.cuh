@@ -277,7 +277,8 @@ struct MeshDev {
     uint32_t* leaf_cone = nullptr; // [nF]     leaf order: packed normal cone of the leaf, widened over its touching neighbours (mesh.cu: pack_cone)
     int32_t  wide_packed = 0;      // wnodes use 24-bit child codes + the node's own cone in their top bytes (nF < 2^23)
     int32_t  root = 0;             // root child code (internal 0, or ~0 if single triangle)
-    int32_t  bvh_kind = 0;         // topology of the binary tree: 0 = Karras hierarchy of the Morton codes, 1 = PLOC
+    int32_t  bvh_kind = 0;         // topology under the 4-wide nodes (ray caster): 0 = Karras hierarchy of the Morton codes, 1 = PLOC
+    int32_t  walk_kind = 0;        // topology of the binary nodes (collision walks): the same coding
     int32_t  ploc_iterations = 0;
     bt_mesh_info info{};
 };

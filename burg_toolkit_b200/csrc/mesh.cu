@@ -630,25 +630,28 @@ extern "C" int bt_stream_sync(void* stream) {
 
 // ---- mesh ------------------------------------------------------------------------------------------
 
-// which topology bt_mesh_create builds: 1 = PLOC (default), 0 = Morton hierarchy; BT_BVH_BUILD=lbvh|ploc sets the initial value
+// which topologies bt_mesh_create builds: 0 = Morton hierarchy for everything, 1 (default) = PLOC for the ray tree, and for the
+// walk tree from PLOC_WALK_MIN_TRIS triangles on, 2 = PLOC for everything; BT_BVH_BUILD=lbvh|ploc|ploc_all sets the initial value
+constexpr int64_t PLOC_WALK_MIN_TRIS = 1 << 18;
 static int g_bvh_build = -1;
 static int bvh_build_kind() {
     if (g_bvh_build < 0) {
         const char* e = getenv("BT_BVH_BUILD");
-        g_bvh_build = (e && (!strcmp(e, "lbvh") || !strcmp(e, "0"))) ? 0 : 1;
+        g_bvh_build = (e && (!strcmp(e, "lbvh") || !strcmp(e, "0"))) ? 0 : (e && (!strcmp(e, "ploc_all") || !strcmp(e, "2"))) ? 2 : 1;
     }
     return g_bvh_build;
 }
 
 extern "C" int bt_set_bvh_build(int32_t kind) {
-    BT_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (Morton LBVH) or 1 (PLOC)");
+    BT_REQUIRE(kind >= 0 && kind <= 2, "kind must be 0 (Morton hierarchy), 1 (PLOC ray tree, size-dependent walk tree) or 2 (PLOC for both)");
     g_bvh_build = kind;
     return BT_OK;
 }
 
-extern "C" int bt_mesh_bvh_kind(const bt_mesh* mesh, int32_t* kind, int32_t* build_iterations) {
-    BT_REQUIRE(mesh && kind, "null pointer");
-    *kind = mesh->m.bvh_kind;
+extern "C" int bt_mesh_bvh_kind(const bt_mesh* mesh, int32_t* ray_kind, int32_t* walk_kind, int32_t* build_iterations) {
+    BT_REQUIRE(mesh && ray_kind, "null pointer");
+    *ray_kind = mesh->m.bvh_kind;
+    if (walk_kind) *walk_kind = mesh->m.walk_kind;
     if (build_iterations) *build_iterations = mesh->m.ploc_iterations;
     return BT_OK;
 }
@@ -795,7 +798,8 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     float4* cone = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0, cub_bytes2 = 0;
-    int ploc_iterations = 0, built_kind = 0;
+    int ploc_iterations = 0, depth_walk = 0, depth_ray = 0;
+    bool walk_is_ploc = false, ray_is_ploc = false;
     const int n = (int)nF;
     // build scratch comes from the device's stream-ordered pool (kept across builds, see retain_pool_memory): fourteen
     // cudaMalloc / cudaFree pairs per mesh cost more than the build itself
@@ -845,29 +849,38 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
                                  box_min, box_max, area);
     MESH_TRY(cudaGetLastError());
     phase();
-    if (nF > 1) {
-        // topology: PLOC (default) or the Karras hierarchy of the Morton codes (bt_set_bvh_build / BT_BVH_BUILD=lbvh, and the
-        // fall-back for a PLOC tree deeper than the traversal stacks allow)
-        bool ploc = bvh_build_kind() == 1;
+    // Two consumers, two topologies (bt_set_bvh_build / BT_BVH_BUILD): the RAY tree under the 4-wide nodes is PLOC by default
+    // (fewer node fetches; the traversal is bound by them), the WALK tree of the binary nodes (collision walks, mesh pairs,
+    // leaf-cone neighbours, fall-back ray walk) is Karras' shallower Morton hierarchy for object-sized meshes -- those walks are
+    // bound by their longest chain of dependent passes, i.e. by depth -- and PLOC from PLOC_WALK_MIN_TRIS triangles on, where
+    // the working set outgrows L2 and fewer fetches win again.  A PLOC tree deeper than the stacks allow falls back to Karras.
+    const int mode = bvh_build_kind();
+    const bool ray_wants_ploc = mode >= 1, walk_wants_ploc = mode == 2 || (mode == 1 && nF >= PLOC_WALK_MIN_TRIS);
+    auto build_topology = [&](bool ploc, bool* got_ploc, int* depth_out) -> cudaError_t {
+        cudaError_t e;
         while (true) {
-            if (ploc) MESH_TRY(ploc_topology(n, box_min, box_max, left, right, parent, cub_tmp, cub_bytes, &ploc_iterations, st));
+            if ((e = cudaMemsetAsync(arrivals, 0, sizeof(int) * nNodes, st)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(max_depth, 0, sizeof(int), st)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(parent, 0xFF, sizeof(int32_t) * (2 * nF), st)) != cudaSuccess) return e;
+            if (ploc) { if ((e = ploc_topology(n, box_min, box_max, left, right, parent, cub_tmp, cub_bytes, &ploc_iterations, st)) != cudaSuccess) return e; }
             else {
                 hierarchy_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(keys_sorted, n, left, right, parent);
-                MESH_TRY(cudaGetLastError());
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
             }
             refit_kernel<<<G, T, 0, st>>>(n, left, right, parent, box_min, box_max, arrivals, max_depth);
-            MESH_TRY(cudaGetLastError());
-            if (!ploc) break;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
             int d = 0;
-            MESH_TRY(cudaMemcpyAsync(&d, max_depth, sizeof(int), cudaMemcpyDeviceToHost, st));
-            MESH_TRY(cudaStreamSynchronize(st));
-            if (d <= 60) break;
-            ploc = false;                                   // too deep for the traversal stacks: the Morton hierarchy instead
-            MESH_TRY(cudaMemsetAsync(arrivals, 0, sizeof(int) * nNodes, st));
-            MESH_TRY(cudaMemsetAsync(max_depth, 0, sizeof(int), st));
-            MESH_TRY(cudaMemsetAsync(parent, 0xFF, sizeof(int32_t) * (2 * nF), st));
+            if ((e = cudaMemcpyAsync(&d, max_depth, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+            *depth_out = d;
+            if (!ploc || d <= 60) break;
+            ploc = false;                               // too deep for the traversal stacks: the Morton hierarchy instead
         }
-        built_kind = ploc ? 1 : 0;
+        *got_ploc = ploc;
+        return cudaSuccess;
+    };
+    if (nF > 1) {
+        MESH_TRY(build_topology(walk_wants_ploc, &walk_is_ploc, &depth_walk));
         phase();
         emit_nodes_kernel<<<(int)ceil_div(nF - 1, T), T, 0, st>>>(n, left, right, box_min, box_max, m.nodes);
         MESH_TRY(cudaGetLastError());
@@ -894,6 +907,11 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
         MESH_TRY(cudaGetLastError());
         phase();
         if (nF > 1) {
+            // the ray tree: the same topology again, or its own (left / right / parent and the internal boxes are rebuilt; the
+            // binary nodes emitted above keep the walk tree)
+            ray_is_ploc = walk_is_ploc; depth_ray = depth_walk;
+            if (ray_wants_ploc != walk_is_ploc && !(ray_wants_ploc && walk_wants_ploc))
+                MESH_TRY(build_topology(ray_wants_ploc, &ray_is_ploc, &depth_ray));
             MESH_TRY(cudaMemsetAsync(arrivals, 0, sizeof(int) * nNodes, st));
             cone_refit_kernel<<<G, T, 0, st>>>(n, left, right, parent, cone, arrivals);
             MESH_TRY(cudaGetLastError());
@@ -925,15 +943,15 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     MESH_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
     if (phase_timing) {
         cudaEvent_t prev = ev0;
-        fprintf(stderr, "bt_mesh_create: %lld triangles, %s", (long long)nF, built_kind ? "PLOC" : "Morton hierarchy");
+        fprintf(stderr, "bt_mesh_create: %lld triangles, ray tree %s, walk tree %s", (long long)nF, ray_is_ploc ? "PLOC" : "Morton hierarchy",
+                walk_is_ploc ? "PLOC" : "Morton hierarchy");
         for (int k = 0; k < n_pe; ++k) { float t = 0.f; cudaEventElapsedTime(&t, prev, pe[k]); fprintf(stderr, " | %s %.3f ms", pe_name[k], t); prev = pe[k]; }
         float t = 0.f; cudaEventElapsedTime(&t, prev, ev1);
         fprintf(stderr, " | area cdf %.3f ms | total %.3f ms\n", t, ms);
     }
     for (int k = 0; k < n_pe; ++k) cudaEventDestroy(pe[k]);
-    int depth = 0;
+    const int depth = depth_walk > depth_ray ? depth_walk : depth_ray;      // the stacks of both kinds of walks are sized by it
     double total = 0.0;
-    MESH_TRY(cudaMemcpy(&depth, max_depth, sizeof(int), cudaMemcpyDeviceToHost));
     MESH_TRY(cudaMemcpy(&total, total_area, sizeof(double), cudaMemcpyDeviceToHost));
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     for (void* p : {(void*)keys, (void*)keys_sorted, (void*)ids, (void*)ids_sorted, (void*)left, (void*)right, (void*)parent, (void*)box_min,
@@ -953,7 +971,8 @@ extern "C" int bt_mesh_create(const double* h_V, int64_t nV, const int32_t* h_F,
     for (int k = 0; k < 3; ++k) { m.info.bounds_min[k] = (float)lo[k]; m.info.bounds_max[k] = (float)hi[k]; }
     m.info.device = device;
     m.info.max_depth = depth;
-    m.bvh_kind = built_kind;
+    m.bvh_kind = ray_is_ploc ? 1 : 0;
+    m.walk_kind = walk_is_ploc ? 1 : 0;
     m.ploc_iterations = ploc_iterations;
     *out = h;
     return BT_OK;

@@ -65,10 +65,12 @@ class DeviceMesh:
 
     @property
     def bvh_kind(self):
-        """('ploc' | 'lbvh', merge rounds of the PLOC build) -- which topology this mesh's tree was built with"""
-        kind, its = C.c_int32(), C.c_int32()
-        nat.call('bt_mesh_bvh_kind', self.handle, C.byref(kind), C.byref(its))
-        return ('ploc' if kind.value == 1 else 'lbvh'), its.value
+        """(ray tree, merge rounds of the last PLOC build, walk tree) with 'ploc' | 'lbvh' for the trees: which topologies
+        this mesh was built with (ray tree: under the ray caster's 4-wide nodes; walk tree: the binary nodes of the collision walks)"""
+        kind, walk, its = C.c_int32(), C.c_int32(), C.c_int32()
+        nat.call('bt_mesh_bvh_kind', self.handle, C.byref(kind), C.byref(walk), C.byref(its))
+        name = {0: 'lbvh', 1: 'ploc'}
+        return name[kind.value], its.value, name[walk.value]
 
     def bvh(self):
         """(nodes float32 [n_nodes, 16], leaf_tri int32 [n_triangles]) -- validation only"""
@@ -80,9 +82,10 @@ class DeviceMesh:
 
 
 def set_bvh_build(kind):
-    """Topology of the trees built from now on: 'ploc' (default) or 'lbvh' (Karras hierarchy of the Morton codes).  Results
-    do not depend on it (the tree is the broad phase); meshes that are already on the device keep their tree."""
-    nat.call('bt_set_bvh_build', {'lbvh': 0, 'ploc': 1}[kind])
+    """Topologies of the trees built from now on: 'ploc' (default: PLOC under the ray caster; the collision walks' tree is
+    Karras' Morton hierarchy for object-sized meshes and PLOC from 2^18 triangles on), 'lbvh' (Morton hierarchy for both) or
+    'ploc_all'.  Results do not depend on it (the trees are the broad phase); meshes already on the device keep theirs."""
+    nat.call('bt_set_bvh_build', {'lbvh': 0, 'ploc': 1, 'ploc_all': 2}[kind])
 
 
 def _destroy(fn, handle):

@@ -117,14 +117,20 @@ BT_API int bt_mesh_destroy(bt_mesh* mesh);
 BT_API int bt_mesh_get_info(const bt_mesh* mesh, bt_mesh_info* info);
 /* debug/validation: copy the LBVH out (nodes: 16 floats each; leaf_tri: sorted leaf -> caller's triangle id) */
 BT_API int bt_mesh_copy_bvh(const bt_mesh* mesh, float* h_nodes, int32_t* h_leaf_tri);
-/* Topology of the binary tree that bt_mesh_create builds from now on (process-wide): 1 = PLOC (default: bottom-up
- * clustering of the Morton order by merged surface area, ~12 % fewer node visits per ray), 0 = Karras hierarchy of the
- * Morton codes (round 1; also the automatic fall-back for a PLOC tree deeper than the traversal stacks).  Results never
- * depend on the tree -- it is the broad phase of trimesh's intersects_location / FCL's collide (sampling.py:231, :354-397).
- * The environment variable BT_BVH_BUILD=lbvh|ploc sets the initial value. */
+/* Topologies that bt_mesh_create builds from now on (process-wide).  The library keeps two trees per mesh: the RAY tree under
+ * the 4-wide nodes of the ray caster and the WALK tree of the binary nodes (collision walks, mesh pairs).
+ *   1 (default)  ray tree by PLOC (bottom-up clustering of the Morton order by merged surface area: ~12 % fewer node fetches
+ *                per ray); walk tree = Karras' Morton hierarchy below 2^18 triangles (shallower: those walks are bound by
+ *                their longest chain of passes), PLOC from there on (fewer fetches win once the scene outgrows L2)
+ *   0            Karras' hierarchy of the Morton codes for both (round 1; also the automatic fall-back for a PLOC tree deeper
+ *                than the traversal stacks)
+ *   2            PLOC for both
+ * Results never depend on the trees -- they are the broad phase of trimesh's intersects_location / FCL's collide
+ * (sampling.py:231, :354-397).  The environment variable BT_BVH_BUILD=lbvh|ploc|ploc_all sets the initial value. */
 BT_API int bt_set_bvh_build(int32_t kind);
-/* kind: what this mesh was built with (0 / 1); build_iterations (may be NULL): PLOC merge rounds */
-BT_API int bt_mesh_bvh_kind(const bt_mesh* mesh, int32_t* kind, int32_t* build_iterations);
+/* what this mesh was built with: ray_kind / walk_kind (0 = Morton hierarchy, 1 = PLOC; walk_kind may be NULL);
+ * build_iterations (may be NULL): merge rounds of the last PLOC build */
+BT_API int bt_mesh_bvh_kind(const bt_mesh* mesh, int32_t* ray_kind, int32_t* walk_kind, int32_t* build_iterations);
 
 /* ---- S1: area-weighted surface samples (replaces mesh_processing.poisson_disk_sampling's uniform
  * stage, mesh_processing.py:52-83 -> open3d SamplePointsUniformlyImpl).  d_pts/d_nrm: [n,3] f64,

@@ -31,7 +31,7 @@ def restore_bvh_build():
     device.set_bvh_build('ploc')
 
 
-@pytest.mark.parametrize('kind', ['ploc', 'lbvh'])
+@pytest.mark.parametrize('kind', ['ploc_all', 'ploc', 'lbvh'])
 def test_lbvh_is_a_valid_hierarchy(kind, restore_bvh_build):
     from burg_toolkit_b200 import mesh as bmesh, device
     from burg_toolkit_b200.device import DeviceMesh
@@ -39,7 +39,9 @@ def test_lbvh_is_a_valid_hierarchy(kind, restore_bvh_build):
     for m in [bmesh.create_icosphere(3, 0.03), bmesh.create_bumpy_sphere(40, 40), bmesh.create_box(0.1, 0.2, 0.3),
               bmesh.create_icosphere(0, 1.0)]:
         dm = DeviceMesh.from_mesh(m)
-        assert dm.bvh_kind[0] == kind and (kind == 'lbvh' or dm.bvh_kind[1] >= 1)
+        ray_tree, rounds, walk_tree = dm.bvh_kind
+        # (the binary nodes checked below are the walk tree: PLOC only under 'ploc_all' for meshes this small)
+        assert ray_tree == kind[:4] and walk_tree == ('ploc' if kind == 'ploc_all' else 'lbvh') and (kind == 'lbvh' or rounds >= 1)
         nodes, leaf_tri = dm.bvh()
         n_f = len(m.triangles)
         assert sorted(leaf_tri.tolist()) == list(range(n_f))                 # every triangle is exactly one leaf
@@ -78,8 +80,8 @@ def test_results_do_not_depend_on_the_tree(restore_bvh_build):
     from burg_toolkit_b200 import mesh as bmesh, device, sampling, _native as nat
     from burg_toolkit_b200.gripper import ParallelJawGripper
     outs, visits, trees = {}, {}, {}
-    for kind in ('lbvh', 'ploc', 'ploc2'):
-        device.set_bvh_build(kind[:4])
+    for kind in ('lbvh', 'ploc', 'ploc_all', 'ploc_all2'):
+        device.set_bvh_build(kind.rstrip('2'))
         ags = sampling.AntipodalGraspSampler()
         ags.mesh, ags.gripper, ags.verbose = bmesh.create_bumpy_sphere(96, 96, radius=0.035, amplitude=0.15, seed=3), ParallelJawGripper(), False
         counters = torch.zeros(8, dtype=torch.int64, device='cuda')
@@ -94,14 +96,16 @@ def test_results_do_not_depend_on_the_tree(restore_bvh_build):
                       out['colliding'][:n_rows].cpu().numpy(), out['free_gs'][:k].cpu().numpy())
         visits[kind] = int(counters[0].item())
         dm = device.cached_device_mesh(ags.mesh)
-        assert dm.bvh_kind[0] == kind[:4]
+        assert dm.bvh_kind[0] == kind[:4] and dm.bvh_kind[2] == ('ploc' if kind.startswith('ploc_all') else 'lbvh')
         trees[kind] = dm.bvh()
-    for a, b in zip(outs['lbvh'], outs['ploc']):
-        assert a.shape == b.shape and np.array_equal(a, b)
+    for other in ('ploc', 'ploc_all'):
+        for a, b in zip(outs['lbvh'], outs[other]):
+            assert a.shape == b.shape and np.array_equal(a, b)
     assert len(outs['ploc'][1]) > 10_000 and 0 < outs['ploc'][3].sum() < len(outs['ploc'][3])
-    assert visits['ploc'] < 0.95 * visits['lbvh'], visits
-    assert np.array_equal(trees['ploc'][0].view(np.uint32), trees['ploc2'][0].view(np.uint32))     # (child codes are not floats)
-    assert np.array_equal(trees['ploc'][1], trees['ploc2'][1])
+    assert visits['ploc'] < 0.95 * visits['lbvh'] and visits['ploc_all'] == visits['ploc'], visits
+    assert np.array_equal(trees['ploc_all'][0].view(np.uint32), trees['ploc_all2'][0].view(np.uint32))     # (child codes are not floats)
+    assert np.array_equal(trees['ploc_all'][1], trees['ploc_all2'][1])
+    assert np.array_equal(trees['ploc'][0].view(np.uint32), trees['lbvh'][0].view(np.uint32))              # 'ploc': the walk tree of a small mesh is Karras'
 
 
 @pytest.mark.parametrize('name', AGS_FIXTURES)
