@@ -106,9 +106,10 @@ __global__ void row_quat_kernel(const float* __restrict__ rows, int64_t n, float
 // After the tile every WARP drains the lists of its 32 threads with all lanes busy (prefix sum of the list lengths by
 // shuffles, entry e -> (owner, k) by a 5-step search over the prefix): (A) every entry repeats the conservative test of
 // its COV_RPT rows from a shared-memory copy of the row constants and queues the (row, query) pairs that pass, (B) the
-// block runs the exact recipe on every queued pair.  A list that overflows (far denser data than the epsilon ball
-// suggests) makes its thread sort out all queries of the tile for its own rows: slow, never wrong.
-constexpr int COV_LCAP = 24;                     // list entries per thread and tile (mean ~7 at 100k x 100k in a 0.2 m cube)
+// block runs the exact recipe on every queued pair.  Between chunks of 8 queries one vote asks whether any lane's list
+// might not hold another chunk; then the warp drains there and then, so the lists never overflow however dense the data.
+constexpr int COV_LCAP = 24;                     // list entries per thread (mean ~7 per tile at 100k x 100k in a 0.2 m cube)
+constexpr int COV_CHUNK = 8;                     // queries between two looks at the fill of the lists (COV_CHUNK <= COV_LCAP / 2)
 constexpr int COV_PCAP = 2048;                   // (row, query) pairs per tile that pass both conservative tests
 
 struct CovTilesSmem {
@@ -187,11 +188,12 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
         }
         __syncthreads();
         // next free entry of this thread's list, as a shared-memory address: the only state the hot loop carries
+        constexpr unsigned STRIDE = COV_THREADS * (unsigned)sizeof(unsigned short);
         const unsigned slot0 = (unsigned)__cvta_generic_to_shared(&S.lists[0][threadIdx.x]);
-        const unsigned slot_end = slot0 + COV_LCAP * COV_THREADS * (unsigned)sizeof(unsigned short);
+        const unsigned slot_high = slot0 + (COV_LCAP - COV_CHUNK) * STRIDE;        // above this mark the next chunk might not fit
         unsigned slot = slot0;
-#pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
+        // conservative test of this thread's RPT rows against query j of the tile (packed multiply-adds), append on a hit
+        auto test_query = [&](int j) {
             const float4 q = tile[j];
             const f32x2 qx = dup2(q.x), qy = dup2(q.y), qz = dup2(q.z), qw = dup2(q.w);     // broadcast operands of the FFMA2s
             // two OR-chains (even / odd rows) so that the compares of one query do not form a single dependent chain
@@ -202,35 +204,48 @@ coverage_tiles_kernel(const float* __restrict__ ref, int64_t n_ref, const float*
                 any0 |= lo2(v) <= thr[r];
                 any1 |= hi2(v) <= thr[r + 1];
             }
-            const bool hit = any0 | any1;
-            if (hit && slot < slot_end) asm volatile("st.shared.u16 [%0], %1;" :: "r"(slot), "h"((unsigned short)j) : "memory");
-            if (hit) slot += COV_THREADS * (unsigned)sizeof(unsigned short);
-        }
-        int n_mine = (int)((slot - slot0) / (COV_THREADS * (unsigned)sizeof(unsigned short)));
-        // pass A, per warp
-        if (n_mine > COV_LCAP) {
-            for (int j = 0; j < cnt; ++j) sort_out(threadIdx.x, j, q0);
-            n_mine = 0;
-        }
-        __syncwarp();
-        int incl = n_mine;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, s);
-            if (lane >= s) incl += v;
-        }
-        const int excl = incl - n_mine, total = __shfl_sync(FULL, incl, 31);
-        for (int e0 = 0; e0 < total; e0 += 32) {
-            const int e = e0 + lane;
-            int owner = 0;                                          // the last lane whose list starts at or before entry e
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-                const int v = __shfl_sync(FULL, excl, owner + s);
-                if (v <= e) owner += s;
+            if (any0 | any1) {                                     // (predicated: one store, one add)
+                asm volatile("st.shared.u16 [%0], %1;" :: "r"(slot), "h"((unsigned short)j) : "memory");
+                slot += STRIDE;
             }
-            const int start = __shfl_sync(FULL, excl, owner);
-            if (e < total) sort_out(wbase + owner, (int)S.lists[e - start][wbase + owner], q0);
+        };
+        // pass A, per warp and with all lanes busy: prefix sum of the list lengths, entry e -> (owner lane, k); empties the lists
+        auto drain_lists = [&]() {
+            const int n_mine = (int)((slot - slot0) / STRIDE);
+            __syncwarp();
+            int incl = n_mine;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, s);
+                if (lane >= s) incl += v;
+            }
+            const int excl = incl - n_mine, total = __shfl_sync(FULL, incl, 31);
+            for (int e0 = 0; e0 < total; e0 += 32) {
+                const int e = e0 + lane;
+                int owner = 0;                                      // the last lane whose list starts at or before entry e
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const int v = __shfl_sync(FULL, excl, owner + s);
+                    if (v <= e) owner += s;
+                }
+                const int start = __shfl_sync(FULL, excl, owner);
+                if (e < total) sort_out(wbase + owner, (int)S.lists[e - start][wbase + owner], q0);
+            }
+            __syncwarp();                                           // every entry has been read before the lists fill again
+            slot = slot0;
+        };
+        // Chunks of COV_CHUNK queries without a branch; between chunks ONE vote: if any lane's list might not hold another
+        // chunk the warp drains its lists there and then (dense data: the epsilon ball holds more than ~0.5 % of the query
+        // set), so a list never overflows and no pair is ever dropped -- at the cost of the same drain the tile's end runs anyway.
+        int j0 = 0;
+        for (; j0 + COV_CHUNK <= cnt; j0 += COV_CHUNK) {
+#pragma unroll
+            for (int u = 0; u < COV_CHUNK; ++u) test_query(j0 + u);
+            if (__any_sync(FULL, slot > slot_high)) drain_lists();
         }
+#pragma unroll 1
+        for (; j0 < cnt; ++j0) test_query(j0);                      // (< COV_CHUNK queries: still fits)
+        drain_lists();
         __syncthreads();
         const int n_p = min(S.p_count, COV_PCAP);
         for (int e = threadIdx.x; e < n_p; e += COV_THREADS) {

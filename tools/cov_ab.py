@@ -48,7 +48,27 @@ def child(tag):
     for kd in (True, False):
         out[f'dense_tiles_{int(kd)}'] = metrics.covered_mask(ref_d, qry_d, kd_semantics=kd, algo='tiles')
         out[f'dense_grid_{int(kd)}'] = metrics.covered_mask(ref_d, qry_d, kd_semantics=kd, algo='grid')
-    del dr, dq, pq
+    # moderately dense translations (the epsilon ball holds ~1 % of the data): per-thread lists fill within a tile
+    ref_m, qry_m = coverage_sets(20_000, 0.07)
+    dm_r, dm_q = torch.from_numpy(ref_m).cuda(), torch.from_numpy(qry_m).cuda()
+    med, best = timed(lambda: metrics.covered_mask(dm_r, dm_q, algo='tiles', return_device=True))
+    out['moderate_tiles'] = metrics.covered_mask(dm_r, dm_q, algo='tiles')
+    print(f'{tag} 20k x 20k in a 7 cm cube, tiles: median {med:.3f} ms, covered {out["moderate_tiles"].mean():.4f}', flush=True)
+    # similar orientations (grasps from above): the orientation bound of the grid kernel passes often
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    def top_rows(n, seed):
+        r = np.zeros((n, 14), dtype=np.float32)
+        r[:, 0:3] = np.random.default_rng(seed).random((n, 3)) * 0.2
+        r[:, 3:12] = Rotation.from_rotvec(np.random.default_rng(seed + 1).normal(0, np.deg2rad(8.0), (n, 3))).as_matrix().reshape(n, 9)
+        return r
+    ref_t, qry_t = top_rows(100_000, 20), top_rows(100_000, 30)
+    dt_r, dt_q = torch.from_numpy(ref_t).cuda(), torch.from_numpy(qry_t).cuda()
+    med, best = timed(lambda: metrics.covered_mask(dt_r, dt_q, algo='grid', return_device=True))
+    out['top_grid'] = metrics.covered_mask(dt_r, dt_q, algo='grid')
+    out['top_tiles'] = metrics.covered_mask(dt_r, dt_q, algo='tiles')
+    print(f'{tag} 100k x 100k, orientations within ~8 deg of one another, grid: median {med:.3f} ms, covered {out["top_grid"].mean():.4f}, tiles agree: {np.array_equal(out["top_grid"], out["top_tiles"])}', flush=True)
+    del dr, dq, pq, dm_r, dm_q, dt_r, dt_q
     ref, qry = coverage_sets(1_000_000)
     dr, dq = torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda()
     pq = metrics.prepare_query(dq, 15.0)
