@@ -101,7 +101,7 @@ __global__ void row_quat_kernel(const float* __restrict__ rows, int64_t n, float
 // COV_RPT rows against one query are OR-ed into two predicates.  The hot loop has NO branch: a thread with a passing pair
 // (the volume ratio of the epsilon ball to the data: a few pairs per thousand, i.e. one warp in three per query) appends
 // the query's index to its OWN short list in shared memory -- one predicated 16-bit store and one predicated add -- so
-// per query a thread issues 1 LDS.128 + 12 FFMA2 + 8 FSETP + 5 = 26 instructions for 8 pairs (round 1: 70 with the rows
+// per query a thread issues 1 LDS.128 + 12 FFMA2 + 8 FSETP + 3 = 24 instructions for 8 pairs (round 1: 70 with the rows
 // sorted out inside the loop; round 2's first version: 36 + a divergent queue push of ~18 in every third warp).
 // After the tile every WARP drains the lists of its 32 threads with all lanes busy (prefix sum of the list lengths by
 // shuffles, entry e -> (owner, k) by a 5-step search over the prefix): (A) every entry repeats the conservative test of
