@@ -40,6 +40,23 @@ def test_argument_validation_needs_no_device():
     assert rc == -1 and b'null pointer' in lib.bt_last_error()
 
 
+def test_tree_build_selector_validates_its_argument():
+    """bt_set_bvh_build is process-wide state and needs no device: 0 / 1 / 2 are accepted, anything else is refused"""
+    from burg_toolkit_b200 import device
+    lib = nat.load()
+    try:
+        for kind in (0, 1, 2):
+            assert lib.bt_set_bvh_build(kind) == 0
+        assert lib.bt_set_bvh_build(3) == -1 and b'kind must be' in lib.bt_last_error()
+        assert lib.bt_set_bvh_build(-1) == -1
+        with pytest.raises(KeyError):
+            device.set_bvh_build('sah')
+        kind = ctypes.c_int32()
+        assert lib.bt_mesh_bvh_kind(None, ctypes.byref(kind), None, None) == -1 and b'null pointer' in lib.bt_last_error()
+    finally:
+        device.set_bvh_build('ploc')
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
